@@ -1,0 +1,85 @@
+"""Generates tests/golden/*.npz by importing the UNMODIFIED reference (dev container only).
+
+    python tests/golden/make_golden.py
+
+gae_golden.npz  inputs + outputs of the reference's generalized_advantage_estimate (loop) and
+                vec_generalized_advantage_estimate (torchrl/objectives/value/functional.py:119-180,
+                270-370) on seeded inputs, CPU fp32.
+per_golden.npz  leaves, uniform draws, sampled indices and IS weights from the compiled reference
+                CPU segment trees (oracle/_ref/cpu) driven by the restated sampler glue
+                (samplers.py:895-956, 966-1091), including the KAT of test_prioritized.py:113-140.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import per_oracle as po  # noqa: E402
+from oracle.ref_loader import reference_ext, reference_functionals, reference_trees  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def gae_cases():
+    F = reference_functionals()
+    out = {}
+    cases = {
+        "c3_small": ((64, 128, 1), 0.99, 0.95, 0.02),
+        "bench_like": ((32, 512, 1), 0.99, 0.95, 0.1),
+        "short": ((7, 3, 1), 0.5, 0.1, 0.3),
+        "multi_f": ((5, 33, 3), 0.9, 0.99, 0.1),
+        "nd_batch": ((3, 4, 50, 1), 0.99, 0.5, 0.05),
+        "odd_T": ((9, 131, 1), 0.99, 0.95, 0.05),
+        "long_T": ((2, 1000, 1), 0.999, 0.97, 0.01),
+    }
+    for i, (name, (shape, gamma, lmbda, p)) in enumerate(cases.items()):
+        g = torch.Generator().manual_seed(100 + i)
+        v, nv, r = (torch.randn(*shape, generator=g) for _ in range(3))
+        term = torch.rand(*shape, generator=g) < p
+        done = term | (torch.rand(*shape, generator=g) < p)
+        gm, lm = torch.tensor(gamma), torch.tensor(lmbda)
+        la, lt = F.generalized_advantage_estimate(gm, lm, v, nv, r, done=done, terminated=term)
+        va, vt = F.vec_generalized_advantage_estimate(gm, lm, v, nv, r, done=done, terminated=term)
+        for k, t in dict(gamma=gm, lmbda=lm, v=v, nv=nv, r=r, done=done, term=term, loop_adv=la,
+                         loop_tgt=lt, vec_adv=va, vec_tgt=vt).items():
+            out[f"{name}/{k}"] = t.numpy()
+    np.savez_compressed(OUT / "gae_golden.npz", **out)
+
+
+def per_cases():
+    assert reference_ext("cpu") is not None
+    out = {}
+    for i, (N, filled, B, alpha, beta) in enumerate(
+            [(16, 16, 32, 0.7, 0.5), (1000, 700, 256, 0.6, 0.4), (4097, 4097, 512, 0.6, 0.4),
+             (100_000, 65_000, 1024, 0.6, 0.4)]):
+        smp = po.OraclePrioritizedSampler(N, alpha, beta, tree_factory=reference_trees("cpu"))
+        g = torch.Generator().manual_seed(200 + i)
+        smp.mark_update(torch.arange(filled))
+        pr = torch.rand(filled, generator=g) * 3
+        ids = torch.randint(0, filled, (filled,), generator=g)      # with duplicates
+        smp.update_priority(ids, pr)
+        leaves = np.array(smp._sum_tree[np.arange(N)], dtype=np.float32)
+        u = torch.rand(B, generator=g)
+        idx, w = smp.sample(filled, B, u=u)
+        k = f"case{i}"
+        out[f"{k}/meta"] = np.array([N, filled, B], dtype=np.int64)
+        out[f"{k}/ab"] = np.array([alpha, beta], dtype=np.float64)
+        out[f"{k}/upd_index"] = ids.numpy()
+        out[f"{k}/upd_priority"] = pr.numpy()
+        out[f"{k}/leaves"] = leaves
+        out[f"{k}/u"] = u.numpy()
+        out[f"{k}/index"] = idx.numpy()
+        out[f"{k}/weight"] = w.numpy()
+        out[f"{k}/p_sum"] = np.float32(smp._sum_tree.query(0, filled))
+        out[f"{k}/p_min"] = np.float32(smp._min_tree.query(0, filled))
+    np.savez_compressed(OUT / "per_golden.npz", **out)
+
+
+if __name__ == "__main__":
+    gae_cases()
+    per_cases()
+    for f in sorted(OUT.glob("*.npz")):
+        print(f.name, f.stat().st_size)

@@ -1,0 +1,177 @@
+"""Pins the CPU oracle: reference KATs, the compiled reference trees, the imported reference GAE.
+
+Runs on CPU (`-m "not gpu"`).  If these fail the oracle is wrong and no parity claim stands.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import per_oracle as po
+from oracle import gae_torch
+
+
+# --------------------------------------------------------------------------- segment tree KATs
+def _kat_trees(factory):
+    # test/rb/test_prioritized.py:113-140 (test_cuda_segment_tree_parity)
+    s, m = factory(16, False), factory(16, True)
+    idx = np.array([0, 3, 4, 7, 12, 15], dtype=np.int64)
+    val = np.array([1, 2, 4, 8, 16, 32], dtype=np.float32)
+    s[idx] = val
+    m[idx] = val
+    return s, m
+
+
+def test_tree_kat_oracle():
+    s, m = _kat_trees(po.OracleTree)
+    assert s.capacity == 32  # strictly-greater power of two, csrc/segment_tree.h:46
+    l = np.array([0, 3, 4, 7]); r = np.array([16, 8, 13, 16])
+    np.testing.assert_array_equal(s.query(l, r), [63, 14, 28, 56])
+    np.testing.assert_array_equal(m.query(l, r), [1, 2, 4, 8])
+    np.testing.assert_array_equal(s.query(l, r, walk=True), [63, 14, 28, 56])
+    np.testing.assert_array_equal(
+        s.scan_lower_bound(np.array([0.5, 1.0, 2.9, 7.1, 30.0], dtype=np.float32)), [0, 0, 3, 7, 12])
+    # value > root -> size (segment_tree.h:250-252)
+    assert s.scan_lower_bound(np.float32(64.0)) == 16
+
+
+def test_tree_kat_reference(ref_cpu):
+    s, m = _kat_trees(lambda n, is_min: (ref_cpu.MinSegmentTreeFp32 if is_min else ref_cpu.SumSegmentTreeFp32)(n))
+    assert s.capacity == 32
+    l = np.array([0, 3, 4, 7]); r = np.array([16, 8, 13, 16])
+    np.testing.assert_array_equal(s.query(l, r), [63, 14, 28, 56])
+    np.testing.assert_array_equal(m.query(l, r), [1, 2, 4, 8])
+    np.testing.assert_array_equal(
+        s.scan_lower_bound(np.array([0.5, 1.0, 2.9, 7.1, 30.0], dtype=np.float32)), [0, 0, 3, 7, 12])
+
+
+def test_writer_kat():
+    # test/rb/test_rb_core.py:598-600: 50 default-priority items in a 100-slot tree
+    smp = po.OraclePrioritizedSampler(100, alpha=0.7, beta=0.5)
+    smp.mark_update(torch.arange(50))
+    assert smp._sum_tree.query(0, 10) == 10
+    assert smp._sum_tree.query(0, 50) == 50
+    assert smp._sum_tree.query(0, 70) == 50
+
+
+@pytest.mark.parametrize("size", [1, 2, 7, 16, 100, 1000, 4097, 100_000])
+def test_tree_matches_reference_random(ref_cpu, size):
+    rng = np.random.default_rng(size)
+    os_, om = po.OracleTree(size, False), po.OracleTree(size, True)
+    rs, rm = ref_cpu.SumSegmentTreeFp32(size), ref_cpu.MinSegmentTreeFp32(size)
+    assert os_.capacity == rs.capacity
+    for _ in range(4):
+        n = int(rng.integers(1, 4 * size + 2))
+        idx = rng.integers(0, size, n).astype(np.int64)          # duplicates on purpose
+        val = rng.random(n, dtype=np.float32) * 3 + 1e-3
+        for t in (os_, om, rs, rm):
+            t[idx] = val
+        l = rng.integers(0, size, 64).astype(np.int64)
+        r = np.minimum(l + rng.integers(1, size + 1, 64), size).astype(np.int64)
+        np.testing.assert_array_equal(os_.query(l, r), rs.query(l, r))
+        np.testing.assert_array_equal(om.query(l, r), rm.query(l, r))
+        assert os_.query(0, size) == rs.query(0, size)
+        mass = (rng.random(257, dtype=np.float32) * np.float32(os_.query(0, size)) * np.float32(1.05))
+        np.testing.assert_array_equal(os_.scan_lower_bound(mass), rs.scan_lower_bound(mass))
+        probe = rng.integers(0, size, 33).astype(np.int64)
+        np.testing.assert_array_equal(os_[probe], rs[probe])
+    # scalar-value overload
+    idx = rng.integers(0, size, 9).astype(np.int64)
+    os_[idx] = 0.25; rs[idx] = 0.25
+    assert os_.query(0, size) == rs.query(0, size)
+    # whole heap equals leaves reloaded bottom-up (LoadValues, segment_tree.h:200-207)
+    t2 = po.OracleTree(size, False); t2.load_leaves(os_.dump_leaves())
+    np.testing.assert_array_equal(t2.values()[1:], os_.values()[1:])
+
+
+def test_sampler_glue_matches_reference_tree(ref_cpu):
+    """OraclePrioritizedSampler over C trees == the same glue over the compiled reference trees."""
+    from oracle.ref_loader import reference_trees
+
+    N, B = 5000, 512
+    a = po.OraclePrioritizedSampler(N, alpha=0.6, beta=0.4)
+    b = po.OraclePrioritizedSampler(N, alpha=0.6, beta=0.4, tree_factory=reference_trees("cpu"))
+    g = torch.Generator().manual_seed(0)
+    for smp in (a, b):
+        smp.mark_update(torch.arange(3000))
+    pr = torch.rand(3000, generator=g) * 4
+    ids = torch.randperm(3000, generator=g)
+    for smp in (a, b):
+        smp.update_priority(ids, pr)
+    assert float(a.default_priority) == float(b.default_priority)
+    ga, gb = torch.Generator().manual_seed(7), torch.Generator().manual_seed(7)
+    ia, wa = a.sample(3000, B, generator=ga)
+    ib, wb = b.sample(3000, B, generator=gb)
+    assert torch.equal(ia, ib) and torch.equal(wa, wb)
+    # and the all-C sample path gives the same thing for the same uniforms
+    u = torch.rand(B, generator=torch.Generator().manual_seed(7)).numpy()
+    ic, wc, _, _ = po.per_sample_c(a._sum_tree, a._min_tree, 3000, u, 0.4)
+    np.testing.assert_array_equal(ic, ia.numpy())
+    np.testing.assert_array_equal(wc, wa.numpy())
+
+
+def test_double_pow_quirk():
+    # SURVEY 8(a'): mark_update passes the already-powered default priority through update_priority
+    s = po.OraclePrioritizedSampler(8, alpha=0.6, beta=0.4)
+    s.update_priority(torch.tensor([0]), torch.tensor([4.0]))
+    s.mark_update(torch.tensor([1]))
+    leaf = s._sum_tree[np.array([0, 1])]
+    np.testing.assert_allclose(leaf, [2.29740, 1.64718], rtol=1e-5)
+
+
+# --------------------------------------------------------------------------- GAE
+def _gae_inputs(shape, seed, p=0.1, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    v, nv, r = (torch.randn(*shape, generator=g, dtype=dtype) for _ in range(3))
+    term = torch.rand(*shape, generator=g) < p
+    done = term | (torch.rand(*shape, generator=g) < p)
+    return v, nv, r, done, term
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 1), (3, 200, 1), (7, 3, 3, 1), (4, 17, 5)])
+@pytest.mark.parametrize("gamma,lmbda", [(0.99, 0.95), (0.5, 0.1), (0.1, 0.99)])
+def test_gae_c_oracle_is_reference_loop(ref_funcs, shape, gamma, lmbda):
+    v, nv, r, done, term = _gae_inputs(shape, 1)
+    g, l = torch.tensor(gamma), torch.tensor(lmbda)
+    ra, rt = ref_funcs.generalized_advantage_estimate(g, l, v, nv, r, done=done, terminated=term)
+    oa, ot = po.gae_f32(g, l, v, nv, r, done, term)
+    assert torch.equal(oa, ra) and torch.equal(ot, rt)      # bit-exact: same op order, no FMA
+    ta, tt = gae_torch.loop_gae(g, l, v, nv, r, done, term)
+    assert torch.equal(ta, ra) and torch.equal(tt, rt)
+    fa, ft = po.gae_f64(g, l, v, nv, r, done, term)
+    torch.testing.assert_close(ra.double(), fa, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 1), (3, 200, 1), (7, 3, 3, 1), (64, 128, 1)])
+def test_gae_torch_restatement_matches_reference(ref_funcs, shape):
+    v, nv, r, done, term = _gae_inputs(shape, 2)
+    g, l = torch.tensor(0.99), torch.tensor(0.95)
+    ra, rt = ref_funcs.vec_generalized_advantage_estimate(g, l, v, nv, r, done=done, terminated=term)
+    ta, tt = gae_torch.vec_gae(g, l, v, nv, r, done, term)
+    assert torch.equal(ta, ra) and torch.equal(tt, rt)
+
+
+def test_gae_golden_fixture():
+    """Committed golden vectors made by the imported reference (tests/golden/make_golden.py)."""
+    from pathlib import Path
+
+    f = Path(__file__).parent / "golden" / "gae_golden.npz"
+    z = np.load(f)
+    for k in sorted({n.split("/")[0] for n in z.files}):
+        gt = lambda n: torch.from_numpy(z[f"{k}/{n}"])
+        g, l = gt("gamma"), gt("lmbda")
+        v, nv, r, done, term = gt("v"), gt("nv"), gt("r"), gt("done"), gt("term")
+        oa, ot = po.gae_f32(g, l, v, nv, r, done, term)
+        assert torch.equal(oa, gt("loop_adv")) and torch.equal(ot, gt("loop_tgt")), k
+        fa, ft = po.gae_f64(g, l, v, nv, r, done, term)
+        torch.testing.assert_close(gt("vec_adv").double(), fa, rtol=1e-4, atol=1e-4)  # reference's own bar
+        torch.testing.assert_close(gt("loop_adv").double(), fa, rtol=1e-5, atol=1e-5)
+
+
+def test_gather_oracle_is_torch_indexing():
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 255, (100, 4, 7, 3), dtype=np.uint8)
+    idx = rng.integers(-60, 60, 33)
+    out = po.gather_rows(src, idx, 60)
+    assert np.array_equal(out, torch.from_numpy(src)[:60][torch.from_numpy(idx)].numpy())
+    with pytest.raises(IndexError):
+        po.gather_rows(src, np.array([60]), 60)
