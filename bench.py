@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py -- the replay-and-advantage hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input (BASELINE.json configs[1] + [2]):
+
+    1. batch = rb.sample(256)            PER sample on a 1M-capacity buffer of Atari transitions (pixels and
+                                         next pixels u8[4,84,84], action i64, reward f32, done, terminated):
+                                         torch.rand -> rlb_per_sample -> rlb_gather of all six leaves
+    2. rb.update_priority(index, |td|)   (p+eps)^alpha, last-writer-wins scatter, touched-ancestor recompute
+    3. adv, tgt = GAE([4096, 128])       gamma=.99, lmbda=.95, done/terminated ~ Bernoulli(.02)
+
+`value` = (256 sampled + 4096*128 GAE) transitions per step / device time per step, whole job.  With N > 1
+the buffer is sharded by capacity (one 1M shard per rank), every rank draws 256 from its shard
+and ONE NCCL all-gather assembles the 256*N global minibatch on every rank; GAE rows are split by rank
+(weak scaling: per-GPU work is fixed).
+
+Timing: CUDA events on the launching stream around exactly K steps after W warm-ups, barrier +
+synchronize on both sides, max over ranks.  Inputs are larger than L2 (the storage is 56 GB; the GAE inputs
+rotate through a ring of sets larger than the 126 MB L2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+ALPHA, BETA, GAMMA, LMBDA = 0.6, 0.4, 0.99, 0.95
+CAPACITY, BATCH = 1_000_000, 256
+GAE_ROWS, GAE_T = 4096, 128
+ROW_BYTES = 2 * 4 * 84 * 84 + 8 + 4 + 1 + 1  # 56 462 B per Atari transition
+TRANSITIONS_PER_STEP = BATCH + GAE_ROWS * GAE_T
+METRIC = "transitions/sec sampled+GAE at 1M buffer / Atari frames"
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def peaks() -> tuple[float, str]:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def timed(fn, steps: int, warmup: int, sync_all) -> float:
+    """ms per step over exactly `steps` calls of fn(i), CUDA events on the current stream."""
+    for i in range(warmup):
+        fn(i)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    sync_all()
+    return e0.elapsed_time(e1) / steps
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def build_buffer(dev, capacity: int, seed: int):
+    """1M-capacity HBM-resident PER buffer of Atari-shaped transitions, filled with synthetic data."""
+    from rl_b200.data import LazyTensorStorage, TensorDict, TensorDictPrioritizedReplayBuffer
+
+    g = torch.Generator(device=dev).manual_seed(seed)
+    rb = TensorDictPrioritizedReplayBuffer(alpha=ALPHA, beta=BETA, storage=LazyTensorStorage(capacity, device=dev),
+                                           batch_size=BATCH, generator=g)
+    chunk = 50_000
+    for lo in range(0, capacity, chunk):
+        n = min(chunk, capacity - lo)
+        td = TensorDict({
+            "pixels": torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+            "action": torch.randint(0, 18, (n, 1), device=dev, generator=g),
+            "next": {"pixels": torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+                     "reward": torch.randn(n, device=dev, generator=g),
+                     "done": torch.rand(n, 1, device=dev, generator=g) < 0.01,
+                     "terminated": torch.rand(n, 1, device=dev, generator=g) < 0.01},
+            "td_error": torch.rand(n, device=dev, generator=g),
+        }, [n])
+        rb.extend(td)
+    return rb, g
+
+
+def gae_ring(dev, rows: int, T: int, g, min_bytes: int = 160 << 20):
+    """Input sets for GAE whose total footprint exceeds L2 so that every call reads cold data."""
+    per = rows * T * 14
+    n = max(2, -(-min_bytes // per))
+    ring = []
+    for _ in range(n):
+        v, nv, r = (torch.randn(rows, T, 1, device=dev, generator=g) for _ in range(3))
+        term = torch.rand(rows, T, 1, device=dev, generator=g) < 0.02
+        done = term | (torch.rand(rows, T, 1, device=dev, generator=g) < 0.02)
+        ring.append((v, nv, r, done, term))
+    return ring
+
+
+def kernel_roofline(dev, rb, ring, hbm_peak: float, peak_src: str) -> dict:
+    """Average launch duration of the dominant kernel (the gather: 28.9 MB/launch vs 11.5 MB for GAE), timed
+    with CUDA events around a CUDA-graph replay of back-to-back launches on cold rows (no host in the loop)."""
+    from rl_b200 import ops
+
+    be = ops.backend()
+    st = rb.storage
+    n_launch = 20
+    g = torch.Generator(device=dev).manual_seed(123)
+    idxs = [torch.randint(0, len(st), (BATCH,), device=dev, generator=g) for _ in range(n_launch)]
+    stream = torch.cuda.Stream(dev)
+    out = {}
+    with torch.cuda.stream(stream):
+        # warm-up outside capture
+        for ix in idxs[:3]:
+            be.gather(st._leaves, ix, len(st))
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            keep = [be.gather(st._leaves, ix, len(st)) for ix in idxs]
+        ms = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            graph.replay()
+            e1.record(stream)
+            stream.synchronize()
+            ms.append(e0.elapsed_time(e1) / n_launch)
+        del keep
+        us = sorted(ms)[len(ms) // 2] * 1e3
+        row_bytes = sum(l[0].numel() * l.element_size() for l in st._leaves)  # every stored leaf, per transition
+        alg = BATCH * row_bytes * 2 + BATCH * 8
+        out = {"bound": "hbm", "kernel": f"gather_kernel<gather> (rlb_gather, {len(st._leaves)} leaves, B=256)",
+               "row_bytes": row_bytes,
+               "achieved": round(alg / us / 1e3, 1), "peak": hbm_peak, "unit": "GB/s",
+               "frac": round(alg / us / 1e3 / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+               "algorithmic_bytes": alg, "us_per_launch": round(us, 3)}
+        # the same kernel at the reference benchmark's own batch size (65 536 rows, pixels only would be 1.8 GB:
+        # use 16 384 full transitions = 1.85 GB moved) -- the steady-state figure
+        big = torch.randint(0, len(st), (16384,), device=dev, generator=g)
+        for _ in range(2):
+            o = be.gather(st._leaves, big, len(st))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        o = be.gather(st._leaves, big, len(st))
+        e1.record(stream)
+        stream.synchronize()
+        del o
+        us_big = e0.elapsed_time(e1) * 1e3
+        alg_big = 16384 * row_bytes * 2 + 16384 * 8
+        out["steady_state_B16384"] = {"achieved": round(alg_big / us_big / 1e3, 1),
+                                      "frac": round(alg_big / us_big / 1e3 / hbm_peak, 4),
+                                      "us_per_launch": round(us_big, 1)}
+        # GAE kernel, same method
+        v, nv, r, d, t = ring[0]
+        graph2 = torch.cuda.CUDAGraph()
+        d8 = [(x[3].view(torch.uint8), x[4].view(torch.uint8)) for x in ring]
+        for i in range(2):
+            be.gae(ring[i][0], ring[i][1], ring[i][2], d8[i][0], d8[i][1], GAMMA, GAMMA * LMBDA, GAE_ROWS, GAE_T, 1)
+        stream.synchronize()
+        with torch.cuda.graph(graph2, stream=stream):
+            keep = [be.gae(x[0], x[1], x[2], dd[0], dd[1], GAMMA, GAMMA * LMBDA, GAE_ROWS, GAE_T, 1)
+                    for x, dd in zip(ring, d8)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        graph2.replay()
+        stream.synchronize()
+        e0.record(stream)
+        graph2.replay()
+        e1.record(stream)
+        stream.synchronize()
+        us_g = e0.elapsed_time(e1) * 1e3 / len(ring)
+        alg_g = GAE_ROWS * GAE_T * 22
+        out["gae_kernel"] = {"achieved": round(alg_g / us_g / 1e3, 1), "frac": round(alg_g / us_g / 1e3 / hbm_peak, 4),
+                             "us_per_launch": round(us_g, 3), "algorithmic_bytes": alg_g}
+        del keep
+    return out
+
+
+def run_ours(args) -> dict:
+    from rl_b200 import ops
+    from rl_b200.objectives.value import GAE
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    be = ops.backend()
+    rb, g = build_buffer(dev, CAPACITY, seed=rank)
+    ring = gae_ring(dev, GAE_ROWS, GAE_T, g)
+    td_err = torch.rand(BATCH, device=dev, generator=g)
+    gae_scalars = (float(torch.tensor(GAMMA)), float(torch.tensor(GAMMA) * torch.tensor(LMBDA)))
+    gather_bufs = None
+    if distributed:
+        from rl_b200.data.sharded import ShardedBatchGather
+
+        gather_bufs = ShardedBatchGather(dev, world)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(i: int):
+        batch = rb.sample()
+        if gather_bufs is not None:
+            batch = gather_bufs.all_gather(batch)
+        rb.update_priority(batch.get("index")[:BATCH] if gather_bufs is None else gather_bufs.local_index, td_err)
+        v, nv, r, d, t = ring[i % len(ring)]
+        a, tg = be.gae(v, nv, r, d.view(torch.uint8), t.view(torch.uint8), *gae_scalars, GAE_ROWS, GAE_T, 1)
+        return batch, a, tg
+
+    # ---- device-resident timing (value)
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms = timed(step, args.steps, args.warmup, sync_all)
+    clk = clocks.stop() if clocks else None
+
+    # ---- sub-metrics, same method
+    ms_sample = timed(lambda i: rb.sample(), args.steps, 3, sync_all)
+    ms_update = timed(lambda i: rb.update_priority(torch.randint(0, CAPACITY, (BATCH,), device=dev), td_err),
+                      args.steps, 3, sync_all)
+
+    def gae_only(i):
+        v, nv, r, d, t = ring[i % len(ring)]
+        be.gae(v, nv, r, d.view(torch.uint8), t.view(torch.uint8), *gae_scalars, GAE_ROWS, GAE_T, 1)
+
+    ms_gae = timed(gae_only, args.steps, 3, sync_all)
+
+    # ---- end to end with HOST buffers: H2D of the step's inputs, D2H of the step's results, every step
+    pin = lambda t: t.cpu().pin_memory()
+    host_in = [tuple(pin(x) for x in s) for s in ring[:2]]
+    host_td = pin(td_err)
+    dev_in = [torch.empty_like(x) for x in ring[0]]
+    dev_td = torch.empty_like(td_err)
+    sample0 = rb.sample()
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in sample0.items(True, True)}
+    host_adv = torch.empty(GAE_ROWS, GAE_T, 1).pin_memory()
+    host_tgt = torch.empty(GAE_ROWS, GAE_T, 1).pin_memory()
+    h2d = sum(x.numel() * x.element_size() for x in host_in[0]) + host_td.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values()) + 2 * host_adv.numel() * 4
+
+    def e2e_step(i: int):
+        for dst, src in zip(dev_in, host_in[i % 2]):
+            dst.copy_(src, non_blocking=True)
+        dev_td.copy_(host_td, non_blocking=True)
+        batch = rb.sample()
+        rb.update_priority(batch.get("index"), dev_td)
+        a, tg = be.gae(dev_in[0], dev_in[1], dev_in[2], dev_in[3].view(torch.uint8), dev_in[4].view(torch.uint8),
+                       *gae_scalars, GAE_ROWS, GAE_T, 1)
+        for k, hv in host_out.items():
+            hv.copy_(batch.get(k), non_blocking=True)
+        host_adv.copy_(a, non_blocking=True)
+        host_tgt.copy_(tg, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller needs the results on the host
+
+    ms_e2e = timed(e2e_step, args.steps, args.warmup, sync_all)
+
+    # ---- max over ranks
+    if distributed:
+        t = torch.tensor([ms, ms_e2e, ms_sample, ms_update, ms_gae], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, ms_sample, ms_update, ms_gae = t.tolist()
+
+    hbm_peak, peak_src = peaks()
+    result = None
+    if rank == 0:
+        roof = kernel_roofline(dev, rb, ring, hbm_peak, peak_src) if world == 1 else None
+        cpu = cpu_baseline_run(steps=None) if world == 1 else None
+        per_step = TRANSITIONS_PER_STEP * world
+        result = {
+            "metric": METRIC, "value": round(per_step / (ms * 1e-3), 1), "unit": "transitions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 rows / f32 priorities+GAE", "data": "synthetic",
+            "config": {"workload": "C2 PER sample+update B=256 @1M Atari transitions (56462 B/row) + C3 GAE [4096,128]",
+                       "capacity_per_gpu": CAPACITY, "batch_per_gpu": BATCH, "gae_shape": [GAE_ROWS, GAE_T, 1],
+                       "alpha": ALPHA, "beta": BETA, "gamma": GAMMA, "lmbda": LMBDA,
+                       "parallelism": f"capacity-sharded x{world}, 1 all-gather/sample" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (56 GB storage, random rows; GAE inputs rotate through >160 MB)"},
+            "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5)},
+            "gpu_launches": 5 * args.steps,
+            "breakdown": {"sample_us": round(ms_sample * 1e3, 2), "update_priority_us": round(ms_update * 1e3, 2),
+                          "gae_us": round(ms_gae * 1e3, 2),
+                          "sample_transitions_per_s": round(BATCH * world / (ms_sample * 1e-3), 1),
+                          "gae_transitions_per_s": round(GAE_ROWS * GAE_T * world / (ms_gae * 1e-3), 1)},
+            "clocks": clk,
+        }
+        if roof:
+            result["roofline"] = roof
+        if cpu:
+            result["cpu_baseline"] = cpu
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_baseline_run(steps: int | None, warmup: int = 2) -> dict:
+    """The reference's own CPU path on the host cores: compiled reference segment trees (oracle/_ref/cpu) under
+    the restated sampler glue, aten::index gather on CPU tensors, and the faster of the reference's two GAE code
+    paths.  Bounded sample: a 20k-row CPU storage (gather cost is per row, not per capacity) and ~10-20 s of work."""
+    from oracle import gae_torch
+    from oracle import per_oracle as po
+    from oracle.ref_loader import reference_trees
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    factory = reference_trees("cpu")
+    kind = "reference" if factory is not None else "port"
+    smp = po.OraclePrioritizedSampler(CAPACITY, ALPHA, BETA, tree_factory=factory)
+    g = torch.Generator().manual_seed(0)
+    rows = 20_000
+    smp.update_priority(torch.arange(CAPACITY), torch.rand(CAPACITY, generator=g))
+    store = {"pixels": torch.randint(0, 256, (rows, 4, 84, 84), dtype=torch.uint8, generator=g),
+             "next_pixels": torch.randint(0, 256, (rows, 4, 84, 84), dtype=torch.uint8, generator=g),
+             "action": torch.randint(0, 18, (rows, 1), generator=g), "reward": torch.randn(rows, generator=g),
+             "done": torch.rand(rows, 1, generator=g) < 0.01, "terminated": torch.rand(rows, 1, generator=g) < 0.01}
+    v, nv, r = (torch.randn(GAE_ROWS, GAE_T, 1, generator=g) for _ in range(3))
+    term = torch.rand(GAE_ROWS, GAE_T, 1, generator=g) < 0.02
+    done = term | (torch.rand(GAE_ROWS, GAE_T, 1, generator=g) < 0.02)
+    gm, lm = torch.tensor(GAMMA), torch.tensor(LMBDA)
+    td = torch.rand(BATCH, generator=g)
+
+    def t_of(fn, n):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t0) / n
+
+    with torch.no_grad():
+        t_loop = t_of(lambda: gae_torch.loop_gae(gm, lm, v, nv, r, done, term), 3)
+        t_vec = t_of(lambda: gae_torch.vec_gae(gm, lm, v, nv, r, done, term), 3)
+    gae_fn = gae_torch.loop_gae if t_loop <= t_vec else gae_torch.vec_gae
+
+    def step():
+        idx, w = smp.sample(CAPACITY, BATCH, generator=g)
+        ridx = idx % rows  # bounded storage: same number of random 28 KB rows touched
+        batch = {k: x[ridx] for k, x in store.items()}
+        smp.update_priority(idx, td)
+        with torch.no_grad():
+            a, t = gae_fn(gm, lm, v, nv, r, done, term)
+        return batch, a, t
+
+    for _ in range(warmup):
+        step()
+    if steps is None:
+        t1 = t_of(step, 2)
+        steps = max(5, min(400, int(12.0 / max(t1, 1e-4))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(TRANSITIONS_PER_STEP / dt, 1), "unit": "transitions/s", "cores": cores, "kind": kind,
+            "ms_per_step": round(dt * 1e3, 3), "steps": steps,
+            "sample": (f"{steps} steps of [reference C++ SumSegmentTree/MinSegmentTree sample+update B=256 @1M + "
+                       f"aten::index gather of 256 Atari transitions from a {rows}-row CPU storage + "
+                       f"{'loop' if gae_fn is gae_torch.loop_gae else 'vec'} GAE [4096,128]] "
+                       f"(gae loop {t_loop * 1e3:.1f} ms, vec {t_vec * 1e3:.1f} ms; faster one used)")}
+
+
+def run_reference(args) -> dict | None:
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return None
+    cpu = cpu_baseline_run(steps=args.steps, warmup=args.warmup)
+    return {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "transitions/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 rows / f32 priorities+GAE",
+            "data": "synthetic",
+            "config": {"workload": "C2 PER sample+update B=256 @1M Atari transitions (56462 B/row) + C3 GAE [4096,128]",
+                       "note": "reference CPU implementation on the host cores; rank 0 only"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        res = run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; rl_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+        res = run_ours(args)
+    if res is not None:
+        print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

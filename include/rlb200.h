@@ -1,0 +1,190 @@
+/*
+ * rlb200.h -- C ABI of the B200-native replay-and-advantage engine (librlb200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of pytorch/rl (TorchRL 0.12) that this
+ * repository accelerates:  ReplayBuffer.sample (PrioritizedSampler segment-tree sample + storage
+ * gather), update_priority (segment-tree write-back) and vec_generalized_advantage_estimate.
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference/torchrl/).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types: raw device pointers, sizes, a CUDA stream handle;
+ *   - every pointer marked [dev] is a device pointer owned by the caller (PyTorch);
+ *     [host] pointers are ordinary host arrays read during the call;
+ *   - the library allocates nothing, never synchronises, never throws: kernels are enqueued on
+ *     `stream` (pass torch.cuda.current_stream().cuda_stream) and the call returns
+ *     RLB_OK or a negative RLB_E* code; rlb_last_error() gives the message for this thread;
+ *   - `dtype`: RLB_F32 or RLB_F64 selects the tree value type, as the reference's
+ *     {Sum,Min}SegmentTreeFp{32,64} do (csrc/pybind.cpp:21-34);
+ *   - a segment tree is the reference's implicit binary heap: `2*capacity` values, leaf i at
+ *     `capacity + i`, node k = op(node 2k, node 2k+1), capacity = smallest power of two
+ *     STRICTLY greater than size (csrc/segment_tree.h:44-48).  The layout is bit-compatible
+ *     with the reference's CUDA tree tensor `values_` (csrc/cuda_segment_tree.h:29-38).
+ *   - there is NO CPU fallback: without a CUDA device every entry point except
+ *     rlb_version / rlb_last_error / rlb_tree_capacity / rlb_*_workspace_bytes fails.
+ */
+#ifndef RLB200_H_
+#define RLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLB_VERSION 100 /* 0.1.0 */
+
+#define RLB_OK 0
+#define RLB_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported dtype ...) */
+#define RLB_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define RLB_ENODEV (-3)   /* no usable CUDA device */
+#define RLB_ELIMIT (-4)   /* argument exceeds a compiled-in limit (e.g. leaves per call) */
+
+#define RLB_F32 0
+#define RLB_F64 1
+
+#define RLB_MAX_LEAVES 24 /* leaves gathered by one rlb_gather launch; callers chunk above this */
+
+/* gather modes (rlb_gather `mode`) */
+#define RLB_GATHER_AUTO 0   /* bulk-DMA (TMA) staging for wide 16-B aligned rows, vector path otherwise */
+#define RLB_GATHER_VECTOR 1 /* force the 128-bit vectorised LDG/STG path for every leaf */
+#define RLB_GATHER_BULK 2   /* force bulk-DMA staging wherever a leaf is eligible */
+
+/* bits of the [dev] int32 status word the kernels OR into (optional, may be NULL) */
+#define RLB_STATUS_INDEX_OOB 1    /* gather: an index was outside [-len, len) and was clamped */
+#define RLB_STATUS_NONPOS_PSUM 2  /* sample: p_sum <= 0  (samplers.py:911-912, CPU-only check there) */
+#define RLB_STATUS_NONPOS_PMIN 4  /* sample: p_min <= 0  (samplers.py:913-914) */
+#define RLB_STATUS_BACKOFF_FAIL 8 /* sample: zero-weight back-off ran below index 0 (samplers.py:940-941) */
+
+typedef void *rlb_stream_t; /* cudaStream_t */
+
+int rlb_version(void);
+const char *rlb_last_error(void);
+/* Number of SMs of the current device (grid sizing is a multiple of this); <0 on error. */
+int rlb_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segment tree  -- replaces the pybind classes {Sum,Min}SegmentTreeFp{32,64} /
+ * Cuda{Sum,Min}SegmentTreeFp{32,64} of torchrl._torchrl
+ * (csrc/segment_tree.h:41-307, csrc/cuda_segment_tree.cu:26-208, csrc/pybind.cpp:21-34).
+ * ------------------------------------------------------------------------------------------- */
+
+/* capacity rule of SegmentTree::SegmentTree (csrc/segment_tree.h:44-48). Pure host arithmetic. */
+int64_t rlb_tree_capacity(int64_t size);
+
+/* values_.assign(2*capacity, identity) (csrc/segment_tree.h:47; cuda_segment_tree.h:34-37).
+ * identity = 0 (sum) / numeric_limits<T>::max() (min). */
+int rlb_tree_fill(void *tree /*[dev] 2*capacity values*/, int64_t capacity, int is_min, int dtype,
+                  rlb_stream_t stream);
+
+/* LoadValues (csrc/segment_tree.h:200-207): leaves [capacity, capacity+size) are already in place;
+ * recompute every internal node bottom-up, node = op(left, right). */
+int rlb_tree_rebuild(void *tree /*[dev]*/, int64_t capacity, int is_min, int dtype, rlb_stream_t stream);
+
+/* Bytes of persistent scratch rlb_tree_update needs for a tree of `size` leaves (one buffer per
+ * sampler, zero-initialised once by the caller, shared by the sum and the min tree). */
+size_t rlb_tree_update_workspace_bytes(int64_t size);
+
+/* SegmentTree::Update, batch form (csrc/segment_tree.h:83-139,216-226; CUDA reference
+ * SetLeavesKernel + RecomputeTree, csrc/cuda_segment_tree.cu:26-49,100-132), applied to the sum
+ * and the min tree of one sampler in the same call (samplers.py:1077-1078).  Semantics: updates
+ * are applied in input order, the LAST duplicate wins; afterwards every ancestor of a touched leaf
+ * equals op(left child, right child) -- bit-identical to the serial reference.  Only touched
+ * ancestors are recomputed.  `value` holds n elements, or one when scalar != 0.
+ * Either tree may be NULL.  `epoch` must be a value never used before with this workspace
+ * (callers pass a running counter starting at 1; on wrap-around clear the workspace). */
+int rlb_tree_update(void *sum_tree /*[dev]*/, void *min_tree /*[dev]*/, int64_t capacity,
+                    const int64_t *index /*[dev] n*/, const void *value /*[dev]*/, int64_t n, int scalar,
+                    int dtype, void *workspace /*[dev]*/, size_t workspace_bytes, uint32_t epoch,
+                    rlb_stream_t stream);
+
+/* SegmentTree::Query, batch form (csrc/segment_tree.h:143-162; QueryKernel
+ * csrc/cuda_segment_tree.cu:51-73): out[i] = op-reduce of leaves [l[i], r[i]).
+ * root_fast_path != 0 reproduces the CPU class (returns the root when l<=0 && r>=size);
+ * 0 reproduces the CUDA reference, which always walks. */
+int rlb_tree_query(const void *tree /*[dev]*/, int64_t size, int64_t capacity, int is_min, int dtype,
+                   const int64_t *l /*[dev] n*/, const int64_t *r /*[dev] n*/, void *out /*[dev] n*/,
+                   int64_t n, int root_fast_path, rlb_stream_t stream);
+
+/* SegmentTree::At, batch form (csrc/segment_tree.h:56-79,210-214; cuda_segment_tree.h:50-60). */
+int rlb_tree_at(const void *tree /*[dev]*/, int64_t capacity, int dtype, const int64_t *index /*[dev] n*/,
+                void *out /*[dev] n*/, int64_t n, rlb_stream_t stream);
+
+/* SumSegmentTree::ScanLowerBound, batch form (csrc/segment_tree.h:249-264,289-294;
+ * ScanLowerBoundKernel csrc/cuda_segment_tree.cu:75-98): first index whose inclusive prefix sum
+ * is >= value; `size` when value > root. */
+int rlb_tree_scan_lower_bound(const void *sum_tree /*[dev]*/, int64_t size, int64_t capacity, int dtype,
+                              const void *value /*[dev] n*/, int64_t *out /*[dev] n*/, int64_t n,
+                              rlb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PrioritizedSampler.sample arithmetic in ONE launch (data/replay_buffers/samplers.py:895-956):
+ *   p_sum = sum.query(0,len); p_min = min.query(0,len); mass = u*p_sum; index = scan_lower_bound(mass)
+ *   index.clamp_max_(len-1); leaf = sum[index]; [CPU semantics: zero-weight back-off :935-943]
+ *   weight = (leaf / p_min) ** -beta
+ * `u` are the uniform draws in [0,1) (the caller keeps torch.rand(B, generator) so the RNG stream
+ * is the reference's, samplers.py:918/923).  cpu_semantics != 0 selects the CPU class behaviour
+ * (root fast path in query, back-off loop); 0 selects the CUDA reference behaviour.
+ * Outputs: index[B] int64, weight[B] fp32 (priority_weight), optional leaf[B] (tree dtype) and
+ * psum_pmin[2] (tree dtype).  fp32 arithmetic is never FMA-contracted. */
+int rlb_per_sample(const void *sum_tree /*[dev]*/, const void *min_tree /*[dev]*/, int64_t size,
+                   int64_t capacity, int dtype, int64_t len, const void *u /*[dev] B, tree dtype*/,
+                   int64_t B, double beta, int cpu_semantics, int64_t *index_out /*[dev] B*/,
+                   float *weight_out /*[dev] B*/, void *leaf_out /*[dev] B or NULL*/,
+                   void *psum_pmin_out /*[dev] 2 or NULL*/, int32_t *status /*[dev] or NULL*/,
+                   rlb_stream_t stream);
+
+/* PrioritizedSampler.update_priority arithmetic (samplers.py:1076-1078) fused with the tree
+ * write: leaf = (priority + eps) ** alpha in fp32 (torch.pow semantics), then rlb_tree_update on
+ * both trees.  index < 0 entries are skipped (MaxValueWriter convention, samplers.py:1040-1052).
+ * If max_priority_out != NULL the maximum RAW priority over the valid entries is atomically folded
+ * into *max_priority_out (max, no reset): with a buffer the caller initialises once to -inf this IS
+ * the reference's running `_max_priority` (samplers.py:1054-1075) without a host round trip.
+ * fp32 trees only. */
+int rlb_per_update(void *sum_tree /*[dev]*/, void *min_tree /*[dev]*/, int64_t capacity,
+                   const int64_t *index /*[dev] n*/, const float *priority /*[dev] n or 1*/, int64_t n,
+                   int scalar, double alpha, double eps, float *leaf_scratch /*[dev] n*/,
+                   float *max_priority_out /*[dev] 1 or NULL*/, void *workspace /*[dev]*/,
+                   size_t workspace_bytes, uint32_t epoch, rlb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Storage gather -- replaces TensorStorage.get for a tensor index
+ * (data/replay_buffers/storages.py:1242-1263: storage[:len][index] per leaf, which bottoms out
+ * in aten::index / vectorized_gather_kernel).  For every leaf k in ONE launch:
+ *     dst[k][b, :] = src[k][index[b], :]        b in [0, B), rows are `row_bytes[k]` bytes,
+ * source rows `src_stride_bytes[k]` apart, destination rows contiguous.  Negative indices wrap
+ * (index + len) as in torch indexing; out-of-range indices set RLB_STATUS_INDEX_OOB in *status
+ * and are clamped (torch raises IndexError; callers that want the exception read the status). */
+int rlb_gather(const void *const *src /*[host] n_leaves [dev] pointers*/,
+               void *const *dst /*[host] n_leaves [dev] pointers*/, const int64_t *row_bytes /*[host]*/,
+               const int64_t *src_stride_bytes /*[host]*/, int n_leaves, const int64_t *index /*[dev] B*/,
+               int64_t B, int64_t len, int mode, int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
+
+/* TensorStorage.set for a tensor cursor (storages.py:1028-1096: storage[cursor] = data per leaf,
+ * aten::index_put_):  dst[k][index[b], :] = src[k][b, :].  Duplicate indices: the last wins only
+ * if the caller passes unique indices (round-robin writers do, writers.py:190-216). */
+int rlb_scatter(const void *const *src /*[host]*/, void *const *dst /*[host]*/,
+                const int64_t *row_bytes /*[host]*/, const int64_t *dst_stride_bytes /*[host]*/, int n_leaves,
+                const int64_t *index /*[dev] B*/, int64_t B, int64_t len, int32_t *status /*[dev] or NULL*/,
+                rlb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generalized advantage estimation -- replaces vec_generalized_advantage_estimate /
+ * generalized_advantage_estimate for scalar gamma, lmbda
+ * (objectives/value/functional.py:270-370 -> _fast_vec_gae :211-267; loop :119-180).
+ * Tensors are contiguous [rows, T, F] (time at dim -2), fp32 (RLB_F32) or fp64 (RLB_F64),
+ * done/terminated are one byte per element (torch.bool).
+ *     delta_t = r_t + gamma*(1-term_t)*v'_t - v_t ;  A_t = delta_t + gammalmbda*(1-done_t)*A_{t+1}
+ *     advantage = A ; value_target = A + v
+ * `gammalmbda` is the caller's fp32 (or fp64) product gamma*lmbda (the reference multiplies two
+ * 0-d tensors, functional.py:249).  One launch, no host sync, forward only. */
+int rlb_gae(const void *state_value /*[dev]*/, const void *next_state_value /*[dev]*/,
+            const void *reward /*[dev]*/, const uint8_t *done /*[dev]*/, const uint8_t *terminated /*[dev]*/,
+            double gamma, double gammalmbda, int64_t rows, int64_t T, int64_t F, int dtype,
+            void *advantage /*[dev]*/, void *value_target /*[dev]*/, rlb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLB200_H_ */

@@ -1,0 +1,217 @@
+// gae.cu -- generalized advantage estimation as ONE discounted reverse-scan kernel (sm_100a).
+//
+// Replaces vec_generalized_advantage_estimate -> _fast_vec_gae (objectives/value/functional.py:211-370):
+// ~15 torch kernels (masked_scatter padding, cumprod filter, conv1d, boolean un-padding) and >= 2 host
+// syncs (value/utils.py:208,283-284) become one launch that reads each input element once and writes
+// each output element once (22 B / element in fp32): an HBM-bandwidth-bound streaming kernel, no
+// contraction, no tensor cores.
+//
+// Maths (the reference loop, functional.py:164-178, is the semantic ground truth):
+//     delta_t = r_t + gamma*(1-term_t)*v'_t - v_t
+//     A_t     = delta_t + c_t * A_{t+1},  c_t = gammalmbda*(1-done_t),  A_T = 0
+// i.e. a suffix scan of the affine maps x -> delta_t + c_t*x under composition
+//     (c1,d1) o (c2,d2) = (c1*c2, d1 + c1*d2).
+// F == 1 layout [rows, T] (time contiguous, functional.py:147-148): one warp per row, each lane owns four
+// consecutive time steps (one 128-bit load per input array), composes them serially, the 32 lane maps
+// are combined with a 5-step shuffle scan (work-efficient variants buy nothing at warp width), and the
+// four local values are then re-derived serially from the lane's incoming value so the result has the
+// accuracy of the serial recurrence.  Rows longer than 128 steps are walked tile by tile from the end
+// with the carry A_{tile end} held in a register.
+// F > 1 layout [rows, T, F]: one thread per (row, feature) column, serial in time, coalesced across
+// features.
+#include "common.cuh"
+
+namespace rlb {
+
+template <typename T>
+struct Vec4 {
+  T v[4];
+};
+
+template <typename T>
+__device__ __forceinline__ Vec4<T> load4(const T *p);
+template <>
+__device__ __forceinline__ Vec4<float> load4<float>(const float *p) {
+  const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+  return {{q.x, q.y, q.z, q.w}};
+}
+template <>
+__device__ __forceinline__ Vec4<double> load4<double>(const double *p) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  return {{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void store4(float *p, const Vec4<float> &x) {
+  __stcs(reinterpret_cast<float4 *>(p), make_float4(x.v[0], x.v[1], x.v[2], x.v[3]));
+}
+__device__ __forceinline__ void store4(double *p, const Vec4<double> &x) {
+  __stcs(reinterpret_cast<double2 *>(p), make_double2(x.v[0], x.v[1]));
+  __stcs(reinterpret_cast<double2 *>(p) + 1, make_double2(x.v[2], x.v[3]));
+}
+
+constexpr int kGaeWarpsPerCta = 8;
+constexpr int kGaeTile = 128;  // time steps per warp iteration (32 lanes x 4)
+
+// VEC: rows are 16-B aligned for T (and 4-B aligned for the flag bytes) and T % 4 == 0.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
+    const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r, const uint8_t *__restrict__ done,
+    const uint8_t *__restrict__ term, T gamma, T gl, int64_t rows, int64_t Tlen, T *__restrict__ adv,
+    T *__restrict__ tgt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)kGaeWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= rows) return;  // whole warps leave together
+  const int64_t base = row * Tlen;
+  const int64_t ntiles = (Tlen + kGaeTile - 1) / kGaeTile;
+  T carry = (T)0;  // A at the first step of the tile processed before (later in time); prev_advantage = 0
+  for (int64_t tile = ntiles - 1; tile >= 0; --tile) {
+    const int64_t t0 = tile * kGaeTile + 4 * lane;  // first of this lane's four steps
+    T d[4], c[4], sv[4];
+    if (VEC && t0 + 4 <= Tlen) {
+      const Vec4<T> qv = load4<T>(v + base + t0);
+      const Vec4<T> qn = load4<T>(nv + base + t0);
+      const Vec4<T> qr = load4<T>(r + base + t0);
+      const uchar4 qd = __ldg(reinterpret_cast<const uchar4 *>(done + base + t0));
+      const uchar4 qt = __ldg(reinterpret_cast<const uchar4 *>(term + base + t0));
+      const uint8_t dd[4] = {qd.x, qd.y, qd.z, qd.w};
+      const uint8_t tt[4] = {qt.x, qt.y, qt.z, qt.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sv[j] = qv.v[j];
+        d[j] = (qr.v[j] + (tt[j] ? (T)0 : gamma) * qn.v[j]) - qv.v[j];
+        c[j] = dd[j] ? (T)0 : gl;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t t = t0 + j;
+        if (t < Tlen) {
+          const T vv = __ldg(v + base + t);
+          sv[j] = vv;
+          d[j] = (__ldg(r + base + t) + (__ldg(term + base + t) ? (T)0 : gamma) * __ldg(nv + base + t)) - vv;
+          c[j] = __ldg(done + base + t) ? (T)0 : gl;
+        } else {  // beyond the row: A = 0 there, contributes nothing
+          sv[j] = (T)0;
+          d[j] = (T)0;
+          c[j] = (T)0;
+        }
+      }
+    }
+    // lane-local composition: A_{t0} = Bq + Cq * A_{t0+4}
+    T Bq = d[3], Cq = c[3];
+#pragma unroll
+    for (int j = 2; j >= 0; --j) {
+      Bq = d[j] + c[j] * Bq;
+      Cq = c[j] * Cq;
+    }
+    // inclusive suffix scan across lanes: afterwards A_{t0(lane)} = Bs + Cs * carry
+    T Bs = Bq, Cs = Cq;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const T Bo = __shfl_down_sync(0xffffffffu, Bs, o);
+      const T Co = __shfl_down_sync(0xffffffffu, Cs, o);
+      if (lane + o < 32) {
+        Bs = Bs + Cs * Bo;
+        Cs = Cs * Co;
+      }
+    }
+    const T a_first = Bs + Cs * carry;
+    // value entering this lane from the right = A at the first step of lane+1 (carry for lane 31)
+    T a_next = __shfl_down_sync(0xffffffffu, a_first, 1);
+    if (lane == 31) a_next = carry;
+    Vec4<T> oa, ot;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      a_next = d[j] + c[j] * a_next;
+      oa.v[j] = a_next;
+      ot.v[j] = a_next + sv[j];  // value_target = advantage + state_value (functional.py:178)
+    }
+    carry = __shfl_sync(0xffffffffu, oa.v[0], 0);
+    if (VEC && t0 + 4 <= Tlen) {
+      store4(adv + base + t0, oa);
+      store4(tgt + base + t0, ot);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (t0 + j < Tlen) {
+          adv[base + t0 + j] = oa.v[j];
+          tgt[base + t0 + j] = ot.v[j];
+        }
+      }
+    }
+  }
+}
+
+// [rows, T, F] with F > 1: thread per (row, f) column; consecutive threads -> consecutive f (coalesced).
+template <typename T>
+__global__ void __launch_bounds__(256) gae_cols_kernel(const T *__restrict__ v, const T *__restrict__ nv,
+                                                       const T *__restrict__ r, const uint8_t *__restrict__ done,
+                                                       const uint8_t *__restrict__ term, T gamma, T gl,
+                                                       int64_t rows, int64_t Tlen, int64_t F, T *__restrict__ adv,
+                                                       T *__restrict__ tgt) {
+  const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (col >= rows * F) return;
+  const int64_t row = col / F, f = col - row * F;
+  const int64_t base = row * Tlen * F + f;
+  T a = (T)0;
+#pragma unroll 4
+  for (int64_t t = Tlen - 1; t >= 0; --t) {
+    const int64_t i = base + t * F;
+    const T vv = __ldg(v + i);
+    const T dlt = (__ldg(r + i) + (__ldg(term + i) ? (T)0 : gamma) * __ldg(nv + i)) - vv;
+    a = dlt + (__ldg(done + i) ? (T)0 : gl) * a;
+    adv[i] = a;
+    tgt[i] = a + vv;
+  }
+}
+
+template <typename T>
+static int gae_impl(const void *v, const void *nv, const void *r, const uint8_t *done, const uint8_t *term,
+                    double gamma, double gl, int64_t rows, int64_t Tlen, int64_t F, void *adv, void *tgt,
+                    cudaStream_t st) {
+  const T *pv = static_cast<const T *>(v), *pn = static_cast<const T *>(nv), *pr = static_cast<const T *>(r);
+  T *pa = static_cast<T *>(adv), *pt = static_cast<T *>(tgt);
+  if (F == 1) {
+    const int64_t blocks = (rows + kGaeWarpsPerCta - 1) / kGaeWarpsPerCta;
+    RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many rows for one launch");
+    auto al = [](const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+    const bool vec = (Tlen % 4 == 0) && al(v, 16) && al(nv, 16) && al(r, 16) && al(adv, 16) && al(tgt, 16) &&
+                     al(done, 4) && al(term, 4);
+    if (vec)
+      gae_rows_kernel<T, true><<<(unsigned)blocks, kGaeWarpsPerCta * 32, 0, st>>>(pv, pn, pr, done, term, (T)gamma,
+                                                                                  (T)gl, rows, Tlen, pa, pt);
+    else
+      gae_rows_kernel<T, false><<<(unsigned)blocks, kGaeWarpsPerCta * 32, 0, st>>>(pv, pn, pr, done, term,
+                                                                                   (T)gamma, (T)gl, rows, Tlen, pa,
+                                                                                   pt);
+    return check_launch("gae_rows_kernel");
+  }
+  const int64_t cols = rows * F;
+  const int64_t blocks = (cols + 255) / 256;
+  RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many columns for one launch");
+  gae_cols_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(pv, pn, pr, done, term, (T)gamma, (T)gl, rows, Tlen, F, pa,
+                                                       pt);
+  return check_launch("gae_cols_kernel");
+}
+
+}  // namespace rlb
+
+using namespace rlb;
+
+extern "C" int rlb_gae(const void *state_value, const void *next_state_value, const void *reward,
+                       const uint8_t *done, const uint8_t *terminated, double gamma, double gammalmbda,
+                       int64_t rows, int64_t T, int64_t F, int dtype, void *advantage, void *value_target,
+                       rlb_stream_t stream) {
+  RLB_REQUIRE(rows >= 0 && T >= 0 && F >= 1, RLB_EINVAL, "rlb_gae: bad shape rows=%lld T=%lld F=%lld",
+              (long long)rows, (long long)T, (long long)F);
+  if (rows == 0 || T == 0) return RLB_OK;
+  RLB_REQUIRE(state_value && next_state_value && reward && done && terminated && advantage && value_target,
+              RLB_EINVAL, "rlb_gae: null pointer");
+  if (dtype == RLB_F32)
+    return gae_impl<float>(state_value, next_state_value, reward, done, terminated, gamma, gammalmbda, rows, T, F,
+                           advantage, value_target, as_stream(stream));
+  if (dtype == RLB_F64)
+    return gae_impl<double>(state_value, next_state_value, reward, done, terminated, gamma, gammalmbda, rows, T, F,
+                            advantage, value_target, as_stream(stream));
+  RLB_REQUIRE(false, RLB_EINVAL, "rlb_gae: unsupported dtype %d", dtype);
+}

@@ -1,0 +1,393 @@
+// gather.cu -- minibatch row gather / scatter for HBM-resident replay storage (sm_100a).
+//
+// Replaces TensorStorage.get / .set for tensor indices (data/replay_buffers/storages.py:1242-1263,
+// 1028-1096), which in the reference is one aten::index (vectorized_gather_kernel) / index_put_ launch
+// PER LEAF plus TensorDict bookkeeping.  Here every leaf of the sampled batch moves in ONE launch:
+//
+//     dst[k][b, :] = src[k][index[b], :]          (gather)      dst[k][index[b], :] = src[k][b, :]   (scatter)
+//
+// A pure byte mover: HBM-bandwidth bound, zero reuse, no tensor cores.  Two roles share the grid:
+//
+//   * bulk-DMA role (CTAs [0, bulk_ctas)) -- wide, 16-B aligned rows (Atari frame stacks: 28 224 B).  The
+//     concatenated output byte space of all bulk leaves is cut into equal contiguous ranges, one per
+//     warp-pipeline (perfect balance even at B = 256, where there are only ~3 rows per SM).  Each
+//     pipeline is driven by ONE elected lane: `cp.async.bulk` global->shared into a ring of 8 KB stages
+//     (completion on an mbarrier), then `cp.async.bulk` shared->global out of the stage; the ring keeps
+//     up to kAhead loads and kStages-kAhead stores in flight per pipeline with no register staging and
+//     no per-byte instructions.  The lanes of the warp prefetch the row indices 32 at a time.
+//   * vector role (remaining CTAs) -- narrow or unaligned leaves (actions, rewards, flags, 1.5 KB
+//     observations): flat (row, vector) units, widest vector the leaf's alignment allows (16/8/4/2/1 B),
+//     4 independent units per thread, streaming cache hints.
+//
+// Index semantics follow torch indexing: negative indices wrap by `len`; out-of-range indices are
+// clamped and reported through the status word (torch would raise IndexError).
+#include "common.cuh"
+
+namespace rlb {
+
+constexpr int kGatherThreads = 128;              // both roles
+constexpr int kPipes = kGatherThreads / 32;      // DMA pipelines (warps) per bulk CTA
+constexpr int kStages = 6;                       // ring depth per pipeline
+constexpr int kAhead = 3;                        // loads kept in flight ahead of the store front
+constexpr uint32_t kChunk = 8192;                // bytes per stage
+constexpr int kVecUnroll = 4;                    // units per thread per tile (vector role)
+constexpr int kTileUnits = kGatherThreads * kVecUnroll;
+constexpr int64_t kBulkMinRowBytes = 4096;       // AUTO mode: rows at least this wide use the DMA role
+
+struct GatherLeaf {
+  const uint8_t *src;
+  uint8_t *dst;
+  int64_t row_bytes;
+  int64_t stride;   // gather: source row stride; scatter: destination row stride
+  int64_t first;    // first 16-B unit (bulk role) / first tile (vector role) of this leaf
+  int64_t units;    // vector role: B * (row_bytes >> vec_log2)
+  uint32_t upr;     // vector role: vectors per row
+  int32_t vec_log2; // vector role: log2(vector bytes)
+  int32_t bulk;     // 1 -> bulk-DMA role
+  int32_t pad_;
+};
+
+struct GatherParams {
+  GatherLeaf leaf[RLB_MAX_LEAVES];
+  const int64_t *index;
+  int64_t B;
+  int64_t len;
+  int32_t *status;
+  int64_t bulk_units;  // total 16-B units over bulk leaves
+  int64_t vec_tiles;   // total tiles over vector leaves
+  int n_leaves;
+  int bulk_ctas;
+};
+
+__device__ __forceinline__ int64_t fix_index(int64_t ix, int64_t len, int32_t *status) {
+  if (ix < 0) ix += len;
+  if (ix < 0 || ix >= len) {
+    if (status) atomicOr(status, RLB_STATUS_INDEX_OOB);
+    ix = ix < 0 ? 0 : len - 1;
+  }
+  return ix;
+}
+
+// ---- vector role -------------------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ V ld_stream(const V *p) {
+  return __ldcs(p);
+}
+template <>
+__device__ __forceinline__ uint8_t ld_stream<uint8_t>(const uint8_t *p) {
+  return *p;
+}
+template <>
+__device__ __forceinline__ uint16_t ld_stream<uint16_t>(const uint16_t *p) {
+  return *p;
+}
+template <typename V>
+__device__ __forceinline__ void st_stream(V *p, V v) {
+  __stcs(p, v);
+}
+template <>
+__device__ __forceinline__ void st_stream<uint8_t>(uint8_t *p, uint8_t v) {
+  *p = v;
+}
+template <>
+__device__ __forceinline__ void st_stream<uint16_t>(uint16_t *p, uint16_t v) {
+  *p = v;
+}
+
+template <typename V, bool SCATTER>
+__device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams &P, int64_t tile_in_leaf) {
+  const int64_t u0 = tile_in_leaf * kTileUnits + threadIdx.x;
+  int64_t b[kVecUnroll], ix[kVecUnroll];
+  uint32_t j[kVecUnroll];
+  bool ok[kVecUnroll];
+#pragma unroll
+  for (int k = 0; k < kVecUnroll; ++k) {
+    const int64_t u = u0 + (int64_t)k * kGatherThreads;
+    ok[k] = u < L.units;
+    if (L.units <= 0xffffffffll) {  // 32-bit divide whenever the leaf's unit space allows it
+      const uint32_t u32 = ok[k] ? (uint32_t)u : 0u;
+      const uint32_t q = u32 / L.upr;
+      b[k] = q;
+      j[k] = u32 - q * L.upr;
+    } else {
+      b[k] = ok[k] ? u / L.upr : 0;
+      j[k] = ok[k] ? (uint32_t)(u - b[k] * L.upr) : 0;
+    }
+    ix[k] = ok[k] ? __ldg(P.index + b[k]) : 0;
+  }
+  V val[kVecUnroll];
+#pragma unroll
+  for (int k = 0; k < kVecUnroll; ++k) {
+    if (ok[k]) {
+      ix[k] = fix_index(ix[k], P.len, P.status);
+      const int64_t srow = SCATTER ? b[k] * L.row_bytes : ix[k] * L.stride;
+      val[k] = ld_stream(reinterpret_cast<const V *>(L.src + srow) + j[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kVecUnroll; ++k) {
+    if (ok[k]) {
+      const int64_t drow = SCATTER ? ix[k] * L.stride : b[k] * L.row_bytes;
+      st_stream(reinterpret_cast<V *>(L.dst + drow) + j[k], val[k]);
+    }
+  }
+}
+
+template <bool SCATTER>
+__device__ __forceinline__ void vector_role(const GatherParams &P, int64_t first_tile, int64_t tile_stride) {
+  for (int64_t tile = first_tile; tile < P.vec_tiles; tile += tile_stride) {
+    int l = -1;
+    for (int k = 0; k < P.n_leaves; ++k) {
+      if (!P.leaf[k].bulk && P.leaf[k].first <= tile) l = k;  // leaves are laid out in increasing `first`
+    }
+    if (l < 0) return;
+    const GatherLeaf &L = P.leaf[l];
+    const int64_t t = tile - L.first;
+    switch (L.vec_log2) {
+      case 4: vec_tile<uint4, SCATTER>(L, P, t); break;
+      case 3: vec_tile<uint2, SCATTER>(L, P, t); break;
+      case 2: vec_tile<uint32_t, SCATTER>(L, P, t); break;
+      case 1: vec_tile<uint16_t, SCATTER>(L, P, t); break;
+      default: vec_tile<uint8_t, SCATTER>(L, P, t); break;
+    }
+  }
+}
+
+// ---- bulk-DMA role -----------------------------------------------------------------------------------
+struct PipeSmem {
+  uint64_t full[kStages];   // mbarriers: stage filled by the g->s bulk copy
+  uint8_t *dst[kStages];    // destination of the piece staged in each slot
+  uint32_t bytes[kStages];
+  uint32_t pad_;
+};
+
+__device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, PipeSmem *ps) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t npipes = (int64_t)P.bulk_ctas * kPipes;
+  const int64_t pipe = (int64_t)blockIdx.x * kPipes + warp;
+  // equal split of the 16-B unit space
+  const int64_t q = P.bulk_units / npipes, rem = P.bulk_units % npipes;
+  int64_t pos = pipe * q + (pipe < rem ? pipe : rem);
+  const int64_t end = pos + q + (pipe < rem ? 1 : 0);
+  if (pos >= end) return;
+  uint8_t *my_ring = ring + (size_t)warp * kStages * kChunk;
+  PipeSmem *my = ps + warp;
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&my->full[s], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  __syncwarp();
+
+  // locate the first piece
+  int l = 0;
+  for (int k = 0; k < P.n_leaves; ++k) {
+    if (P.leaf[k].bulk && P.leaf[k].first <= pos) l = k;
+  }
+  int64_t leaf_end = P.leaf[l].first + P.B * (P.leaf[l].row_bytes >> 4);  // in units
+  int64_t byte_in_leaf = (pos - P.leaf[l].first) << 4;
+  int64_t b = byte_in_leaf / P.leaf[l].row_bytes;
+  int64_t off = byte_in_leaf - b * P.leaf[l].row_bytes;
+  // index window: lane j holds index[win0 + j]
+  int64_t win0 = b;
+  int64_t my_ix = (win0 + lane < P.B) ? __ldg(P.index + win0 + lane) : 0;
+
+  int64_t n_loaded = 0, n_stored = 0;
+  bool more = true;
+  while (more || n_stored < n_loaded) {
+    // ---- keep up to kAhead loads in flight ahead of the store front
+    while (more && n_loaded < n_stored + kAhead) {
+      const GatherLeaf &L = P.leaf[l];
+      if (b >= win0 + 32) {  // warp-uniform: refill the index window
+        win0 = b;
+        my_ix = (win0 + lane < P.B) ? __ldg(P.index + win0 + lane) : 0;
+      }
+      int64_t ix = __shfl_sync(0xffffffffu, my_ix, (int)(b - win0));
+      ix = fix_index(ix, P.len, lane == 0 ? P.status : nullptr);
+      int64_t nbytes = L.row_bytes - off;
+      if (nbytes > (int64_t)kChunk) nbytes = kChunk;
+      const int64_t left = (end - pos) << 4;
+      if (nbytes > left) nbytes = left;
+      const int stage = (int)(n_loaded % kStages);
+      if (lane == 0) {
+        // the slot was last used by piece n_loaded - kStages: its s->g copy must have finished READING
+        // shared memory.  At most kStages - kAhead younger stores may still be pending.
+        if (n_loaded >= kStages) bulk_wait_read<kStages - kAhead>();
+        my->dst[stage] = L.dst + b * L.row_bytes + off;
+        my->bytes[stage] = (uint32_t)nbytes;
+        mbar_arrive_expect_tx(&my->full[stage], (uint32_t)nbytes);
+        bulk_g2s(my_ring + (size_t)stage * kChunk, L.src + ix * L.stride + off, (uint32_t)nbytes, &my->full[stage]);
+      }
+      ++n_loaded;
+      // advance the cursor
+      pos += nbytes >> 4;
+      off += nbytes;
+      if (off == L.row_bytes) {
+        off = 0;
+        ++b;
+      }
+      if (pos >= end) {
+        more = false;
+      } else if (pos >= leaf_end) {  // next bulk leaf
+        int nl = l;
+        for (int k = 0; k < P.n_leaves; ++k) {
+          if (P.leaf[k].bulk && P.leaf[k].first == leaf_end) nl = k;
+        }
+        l = nl;
+        leaf_end = P.leaf[l].first + P.B * (P.leaf[l].row_bytes >> 4);
+        b = 0;
+        off = 0;
+        win0 = 0;
+        my_ix = (lane < P.B) ? __ldg(P.index + lane) : 0;
+      }
+    }
+    // ---- retire the oldest staged piece: wait for its bytes, then DMA it out
+    if (n_stored < n_loaded) {
+      const int stage = (int)(n_stored % kStages);
+      if (lane == 0) {
+        mbar_wait_parity(&my->full[stage], (uint32_t)((n_stored / kStages) & 1));
+        fence_proxy_async_smem();
+        bulk_s2g(my->dst[stage], my_ring + (size_t)stage * kChunk, my->bytes[stage]);
+        bulk_commit();
+      }
+      ++n_stored;
+    }
+  }
+  if (lane == 0) bulk_wait_all();  // all s->g copies complete (and visible) before the CTA retires
+  __syncwarp();
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(kGatherThreads) gather_kernel(const __grid_constant__ GatherParams P) {
+  extern __shared__ __align__(128) uint8_t gsmem[];
+  if (!SCATTER && (int)blockIdx.x < P.bulk_ctas) {
+    PipeSmem *ps = reinterpret_cast<PipeSmem *>(gsmem);
+    uint8_t *ring = gsmem + 1024;  // PipeSmem[kPipes] fits in the first KB; stages stay 128-B aligned
+    bulk_role(P, ring, ps);
+    return;
+  }
+  const int vec_ctas = (int)gridDim.x - P.bulk_ctas;
+  vector_role<SCATTER>(P, (int64_t)blockIdx.x - P.bulk_ctas, vec_ctas);
+}
+
+static_assert(sizeof(PipeSmem) * kPipes <= 1024, "PipeSmem header must fit in 1 KB");
+constexpr size_t kBulkSmemBytes = 1024 + (size_t)kPipes * kStages * kChunk;
+
+static int pick_vec_log2(const void *src, const void *dst, int64_t row_bytes, int64_t stride) {
+  for (int lg = 4; lg > 0; --lg) {
+    const uintptr_t a = uintptr_t(1) << lg;
+    if (reinterpret_cast<uintptr_t>(src) % a == 0 && reinterpret_cast<uintptr_t>(dst) % a == 0 &&
+        row_bytes % (int64_t)a == 0 && stride % (int64_t)a == 0)
+      return lg;
+  }
+  return 0;
+}
+
+template <bool SCATTER>
+static int launch_rows(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *stride,
+                       int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status,
+                       cudaStream_t st, const char *who) {
+  RLB_REQUIRE(n_leaves >= 0 && n_leaves <= RLB_MAX_LEAVES, RLB_ELIMIT, "%s: n_leaves=%d exceeds RLB_MAX_LEAVES=%d",
+              who, n_leaves, RLB_MAX_LEAVES);
+  RLB_REQUIRE(B >= 0 && len >= 0, RLB_EINVAL, "%s: negative B or len", who);
+  if (n_leaves == 0 || B == 0) return RLB_OK;
+  RLB_REQUIRE(len > 0, RLB_EINVAL, "%s: cannot index an empty storage (len == 0)", who);
+  RLB_REQUIRE(src && dst && row_bytes && stride && index, RLB_EINVAL, "%s: null argument", who);
+  const int sms = sm_count();
+  if (sms <= 0) return RLB_ENODEV;
+
+  GatherParams P;
+  memset(&P, 0, sizeof(P));
+  P.index = index;
+  P.B = B;
+  P.len = len;
+  P.status = status;
+  P.n_leaves = n_leaves;
+  int64_t bulk_units = 0, vec_tiles = 0;
+  for (int k = 0; k < n_leaves; ++k) {
+    RLB_REQUIRE(src[k] && dst[k] && row_bytes[k] >= 0 && stride[k] >= row_bytes[k], RLB_EINVAL,
+                "%s: leaf %d has a null pointer, negative row_bytes or stride < row_bytes", who, k);
+    GatherLeaf &L = P.leaf[k];
+    L.src = static_cast<const uint8_t *>(src[k]);
+    L.dst = static_cast<uint8_t *>(dst[k]);
+    L.row_bytes = row_bytes[k];
+    L.stride = stride[k];
+    const int lg = pick_vec_log2(src[k], dst[k], row_bytes[k], stride[k]);
+    const bool eligible = !SCATTER && lg == 4 && row_bytes[k] >= 16;
+    const bool want = (mode == RLB_GATHER_BULK) || (mode == RLB_GATHER_AUTO && row_bytes[k] >= kBulkMinRowBytes);
+    if (row_bytes[k] == 0) {
+      L.bulk = 0;
+      L.first = vec_tiles;
+      L.units = 0;
+      L.upr = 1;
+      L.vec_log2 = 0;
+    } else if (eligible && want) {
+      L.bulk = 1;
+      L.first = bulk_units;
+      bulk_units += B * (row_bytes[k] >> 4);
+    } else {
+      L.bulk = 0;
+      L.vec_log2 = lg;
+      const int64_t upr = row_bytes[k] >> lg;
+      RLB_REQUIRE(upr < (int64_t(1) << 32), RLB_ELIMIT, "%s: leaf %d row too wide for its alignment", who, k);
+      L.upr = (uint32_t)upr;
+      L.units = B * upr;
+      L.first = vec_tiles;
+      vec_tiles += (L.units + kTileUnits - 1) / kTileUnits;
+    }
+  }
+  P.bulk_units = bulk_units;
+  P.vec_tiles = vec_tiles;
+  // grid: one bulk CTA per SM (192 KB of ring each); vector CTAs take SMs of their own when there are few
+  // of them, otherwise they oversubscribe (they need no shared memory when no bulk leaf exists).
+  int bulk_ctas = 0, vec_ctas = 0;
+  if (vec_tiles > 0) {
+    const int64_t cap = (int64_t)sms * (bulk_units > 0 ? 1 : 16);
+    vec_ctas = (int)(vec_tiles < cap ? vec_tiles : cap);
+  }
+  if (bulk_units > 0) {
+    const int64_t bytes = bulk_units << 4;
+    int64_t want_pipes = (bytes + 4095) / 4096;  // at least ~4 KB per pipeline
+    int64_t want_ctas = (want_pipes + kPipes - 1) / kPipes;
+    int avail = sms - (vec_ctas < sms / 4 ? vec_ctas : sms / 4);
+    if (avail < 1) avail = 1;
+    bulk_ctas = (int)(want_ctas < avail ? want_ctas : avail);
+    if (bulk_ctas < 1) bulk_ctas = 1;
+  }
+  P.bulk_ctas = bulk_ctas;
+  const size_t smem = bulk_ctas > 0 ? kBulkSmemBytes : 0;
+  static bool attr_set = false;
+  if (smem && !attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(gather_kernel<SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kBulkSmemBytes),
+                        "cudaFuncSetAttribute(gather_kernel)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  gather_kernel<SCATTER><<<bulk_ctas + vec_ctas, kGatherThreads, smem, st>>>(P);
+  return check_launch(SCATTER ? "gather_kernel<scatter>" : "gather_kernel<gather>");
+}
+
+}  // namespace rlb
+
+using namespace rlb;
+
+extern "C" {
+
+int rlb_gather(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *src_stride_bytes,
+               int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status,
+               rlb_stream_t stream) {
+  RLB_REQUIRE(mode == RLB_GATHER_AUTO || mode == RLB_GATHER_VECTOR || mode == RLB_GATHER_BULK, RLB_EINVAL,
+              "rlb_gather: unknown mode %d", mode);
+  return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, n_leaves, index, B, len, mode, status,
+                            as_stream(stream), "rlb_gather");
+}
+
+int rlb_scatter(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *dst_stride_bytes,
+                int n_leaves, const int64_t *index, int64_t B, int64_t len, int32_t *status, rlb_stream_t stream) {
+  return launch_rows<true>(src, dst, row_bytes, dst_stride_bytes, n_leaves, index, B, len, RLB_GATHER_VECTOR,
+                           status, as_stream(stream), "rlb_scatter");
+}
+
+}  // extern "C"

@@ -1,0 +1,787 @@
+// tree.cu -- HBM-resident sum/min segment trees for prioritized replay (sm_100a).
+//
+// Replaces the reference's CPU tree (csrc/segment_tree.h:41-307) and its correctness-first CUDA port
+// (csrc/cuda_segment_tree.cu:26-208).  The node layout and the value of every node are bit-identical
+// to the reference (node k = op(node 2k, node 2k+1), one fp rounding per node, no FMA contraction), so
+// the indices returned by the prefix-sum descent are exactly the reference's for the same draws.
+// What changes is scheduling:
+//   * sample  -- one launch fuses query(0,len) on both trees, mass = u*p_sum, the lower-bound descent,
+//                clamp, leaf read and the importance weight.  The descent resolves FOUR tree levels per
+//                memory round trip: the 2/4/8/16 descendants of a node sit in four contiguous, 16-B
+//                aligned runs of the heap array, so they are fetched with independent 128-bit loads and
+//                the four comparisons run from registers (5 dependent round trips for a 2^20 tree
+//                instead of 20).
+//   * update  -- last-writer-wins leaf scatter + recomputation of the TOUCHED ancestors only.  Batches
+//                of <= 1024 run in ONE CTA: paths climb level-synchronously, exchanging child values
+//                through a shared-memory hash keyed by parent id (one __syncthreads per level, no
+//                global round trip between levels except the prefetch of untouched siblings); paths
+//                that merge are carried on by a single thread.  Larger batches use a stamp-dedupe
+//                scatter + one sweep launch per level + a single-CTA dense top.
+// These are latency-bound pointer chases over an L2-resident array (16 MB for two 2^20 fp32 trees):
+// no tensor cores, no smem tiling of the tree itself.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace rlb {
+
+// ------------------------------------------------------------------------------------------------
+// fill / rebuild / query / at
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void tree_fill_kernel(T *tree, int64_t n, T v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) tree[i] = v;
+}
+
+template <typename T, bool IsMin>
+__global__ void tree_level_dense_kernel(T *tree, int64_t level_start, int64_t level_count) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < level_count; i += stride) {
+    const int64_t node = level_start + i;
+    tree[node] = tree_op<T, IsMin>(tree[node << 1], tree[(node << 1) | 1]);
+  }
+}
+
+// Dense recomputation of the top of the tree by ONE CTA: loads the W nodes [W, 2W) (W <= 1024, a
+// power of two), reduces pairwise in shared memory and writes every node in [1, W).
+template <typename T, bool IsMin>
+__device__ __forceinline__ void tree_top_dense(T *tree, int W, T *sh) {
+  const int tid = threadIdx.x;
+  if (tid < W) sh[W + tid] = ld_cg(tree + W + tid);
+  __syncthreads();
+  for (int w = W >> 1; w >= 1; w >>= 1) {
+    if (tid < w) {
+      const int node = w + tid;
+      const T v = tree_op<T, IsMin>(sh[node << 1], sh[(node << 1) | 1]);
+      sh[node] = v;
+      tree[node] = v;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) tree_top_kernel(T *sum, T *mn, int W) {
+  __shared__ T sh[2048];
+  if (sum) tree_top_dense<T, false>(sum, W, sh);
+  __syncthreads();
+  if (mn) tree_top_dense<T, true>(mn, W, sh);
+}
+
+// Reduce [l, r) exactly as SegmentTree::Query does (csrc/segment_tree.h:143-162): terms are folded
+// into `ret` bottom-up, left term before right term at each level.
+template <typename T, bool IsMin>
+__device__ __forceinline__ T tree_query_walk(const T *__restrict__ tree, int64_t capacity, int64_t l, int64_t r,
+                                             T identity) {
+  T ret = identity;
+  l |= capacity;
+  r |= capacity;
+  while (l < r) {
+    if (l & 1) ret = tree_op<T, IsMin>(ret, tree[l++]);
+    if (r & 1) ret = tree_op<T, IsMin>(ret, tree[--r]);
+    l >>= 1;
+    r >>= 1;
+  }
+  return ret;
+}
+
+template <typename T, bool IsMin>
+__global__ void tree_query_kernel(const T *__restrict__ tree, int64_t size, int64_t capacity,
+                                  const int64_t *__restrict__ l, const int64_t *__restrict__ r, T *out, int64_t n,
+                                  int root_fast_path, T identity) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t li = l[i], ri = r[i];
+  if (root_fast_path && li <= 0 && ri >= size) {
+    out[i] = tree[1];
+    return;
+  }
+  out[i] = tree_query_walk<T, IsMin>(tree, capacity, li, ri, identity);
+}
+
+template <typename T>
+__global__ void tree_at_kernel(const T *__restrict__ tree, int64_t capacity, const int64_t *__restrict__ index,
+                               T *out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = tree[index[i] | capacity];
+}
+
+// ------------------------------------------------------------------------------------------------
+// lower-bound descent (SumSegmentTree::ScanLowerBound, csrc/segment_tree.h:249-264)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void descend_step(T &cur, int64_t &node, T lvalue) {
+  // `if (current_value > lvalue) { current_value -= lvalue; index |= 1; }` with strict '>'
+  if (cur > lvalue) {
+    cur = sub_rn(cur, lvalue);
+    node |= 1;
+  }
+}
+
+// Generic one-level-per-load descent (any dtype, any remaining depth).
+template <typename T>
+__device__ __forceinline__ int64_t descend_plain(const T *__restrict__ tree, int64_t node, int levels, T &cur) {
+  for (int k = 0; k < levels; ++k) {
+    node <<= 1;
+    descend_step(cur, node, __ldg(tree + node));
+  }
+  return node;
+}
+
+// fp32: four levels per round trip.  From `node`, the left children that the next four comparisons can
+// possibly need are  tree[2n]; tree[4n+{0,2}]; tree[8n+{0,2,4,6}]; tree[16n+{0,2,..,14}]  -- each run is
+// contiguous and 16-B aligned (for n >= 1), so they are fetched as 1 scalar + 1 + 2 + 4 independent
+// LDG.128 and the data-dependent choice is made from registers.  The comparisons/subtractions are the
+// reference's, in the reference's order.
+__device__ __forceinline__ int64_t descend4_f32(const float *__restrict__ tree, int64_t node, float &cur) {
+  const float l1 = __ldg(tree + (node << 1));
+  const float4 q2 = __ldg(reinterpret_cast<const float4 *>(tree + (node << 2)));
+  const float4 q3a = __ldg(reinterpret_cast<const float4 *>(tree + (node << 3)));
+  const float4 q3b = __ldg(reinterpret_cast<const float4 *>(tree + (node << 3) + 4));
+  const float4 q4a = __ldg(reinterpret_cast<const float4 *>(tree + (node << 4)));
+  const float4 q4b = __ldg(reinterpret_cast<const float4 *>(tree + (node << 4) + 4));
+  const float4 q4c = __ldg(reinterpret_cast<const float4 *>(tree + (node << 4) + 8));
+  const float4 q4d = __ldg(reinterpret_cast<const float4 *>(tree + (node << 4) + 12));
+  // level +1
+  int c = 0;
+  if (cur > l1) {
+    cur = sub_rn(cur, l1);
+    c = 1;
+  }
+  // level +2: left child of (2n + c) is tree[4n + 2c]
+  const float l2 = c ? q2.z : q2.x;
+  c <<= 1;
+  if (cur > l2) {
+    cur = sub_rn(cur, l2);
+    c |= 1;
+  }
+  // level +3: left child of (4n + c) is tree[8n + 2c], c in [0,4)
+  float l3 = q3a.x;
+  l3 = (c == 1) ? q3a.z : l3;
+  l3 = (c == 2) ? q3b.x : l3;
+  l3 = (c == 3) ? q3b.z : l3;
+  c <<= 1;
+  if (cur > l3) {
+    cur = sub_rn(cur, l3);
+    c |= 1;
+  }
+  // level +4: left child of (8n + c) is tree[16n + 2c], c in [0,8)
+  float l4 = q4a.x;
+  l4 = (c == 1) ? q4a.z : l4;
+  l4 = (c == 2) ? q4b.x : l4;
+  l4 = (c == 3) ? q4b.z : l4;
+  l4 = (c == 4) ? q4c.x : l4;
+  l4 = (c == 5) ? q4c.z : l4;
+  l4 = (c == 6) ? q4d.x : l4;
+  l4 = (c == 7) ? q4d.z : l4;
+  c <<= 1;
+  if (cur > l4) {
+    cur = sub_rn(cur, l4);
+    c |= 1;
+  }
+  return (node << 4) | c;
+}
+
+template <typename T>
+__device__ __forceinline__ int64_t scan_lower_bound_one(const T *__restrict__ tree, int64_t size, int64_t capacity,
+                                                        int depth, T value, T root) {
+  if (value > root) return size;  // csrc/segment_tree.h:250-252
+  int64_t node = 1;
+  T cur = value;
+  int lev = 0;
+  if constexpr (sizeof(T) == 4) {
+    for (; lev + 4 <= depth; lev += 4) node = descend4_f32(tree, node, cur);
+  }
+  node = descend_plain<T>(tree, node, depth - lev, cur);
+  return node ^ capacity;
+}
+
+template <typename T>
+__global__ void tree_scan_kernel(const T *__restrict__ tree, int64_t size, int64_t capacity, int depth,
+                                 const T *__restrict__ value, int64_t *out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = scan_lower_bound_one<T>(tree, size, capacity, depth, value[i], __ldg(tree + 1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused PrioritizedSampler.sample arithmetic (samplers.py:895-956)
+// ------------------------------------------------------------------------------------------------
+// torch.pow(x, scalar) semantics for fp32 tensors on CUDA (ATen/native/cuda/PowKernel.cu): dedicated
+// kernels for 0.5 / -0.5 / -1, x*x, x*x*x, 1/(x*x) for 2 / 3 / -2, ::pow otherwise; exponent 0 -> 1,
+// exponent 1 -> copy (ATen/native/Pow.cpp).  The exponent is cast to the tensor dtype first.
+__device__ __forceinline__ float pow_like_torch(float x, float y) {
+  if (y == 0.0f) return 1.0f;
+  if (y == 1.0f) return x;
+  if (y == 0.5f) return sqrtf(x);
+  if (y == -0.5f) return rsqrtf(x);
+  if (y == -1.0f) return 1.0f / x;
+  if (y == 2.0f) return mul_rn(x, x);
+  if (y == 3.0f) return mul_rn(mul_rn(x, x), x);
+  if (y == -2.0f) return (float)(1.0 / (double)mul_rn(x, x));
+  return powf(x, y);
+}
+__device__ __forceinline__ double pow_like_torch(double x, double y) {
+  if (y == 0.0) return 1.0;
+  if (y == 1.0) return x;
+  if (y == 0.5) return sqrt(x);
+  if (y == -0.5) return rsqrt(x);
+  if (y == -1.0) return 1.0 / x;
+  if (y == 2.0) return x * x;
+  if (y == 3.0) return x * x * x;
+  if (y == -2.0) return 1.0 / (x * x);
+  return pow(x, y);
+}
+
+// query(0, len) of one tree by one warp.  For l = 0 the walk only ever takes RIGHT terms:
+// level j contributes tree[r_j - 1] iff r_j is odd, with r_j = (capacity + len) >> j, while l_j < r_j
+// (l_j = capacity >> j).  The terms are independent loads (one lane per level), folded in level order
+// by every lane redundantly so the association order is the reference's.
+template <typename T, bool IsMin>
+__device__ __forceinline__ T warp_query_prefix(const T *__restrict__ tree, int64_t capacity, int64_t len,
+                                               T identity) {
+  const int lane = threadIdx.x & 31;
+  T ret = identity;
+  // up to 64 levels in two passes of 32 lanes (capacity < 2^62)
+  for (int base = 0; base < 64; base += 32) {
+    const int j = base + lane;
+    const int64_t lj = (j < 62) ? (capacity >> j) : 0;
+    const int64_t rj = (j < 62) ? ((capacity + len) >> j) : 0;
+    const bool take = (lj < rj) && (rj & 1);
+    const T term = take ? __ldg(tree + (rj - 1)) : identity;
+    const unsigned mask = __ballot_sync(0xffffffffu, take);
+    for (int k = 0; k < 32; ++k) {
+      const T t = __shfl_sync(0xffffffffu, term, k);
+      if ((mask >> k) & 1u) ret = tree_op<T, IsMin>(ret, t);
+    }
+    if ((capacity >> (base + 31)) == 0) break;
+  }
+  return ret;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ sum, const T *__restrict__ mn,
+                                                         int64_t size, int64_t capacity, int depth, int64_t len,
+                                                         const T *__restrict__ u, int64_t B, T neg_beta,
+                                                         int cpu_semantics, int64_t *__restrict__ index_out,
+                                                         float *__restrict__ weight_out, T *leaf_out,
+                                                         T *psum_pmin_out, int32_t *status) {
+  __shared__ T s_p[2];
+  const int warp = threadIdx.x >> 5;
+  if (warp < 2) {
+    // warp 0: p_sum, warp 1: p_min   (samplers.py:901-908)
+    T v;
+    const bool root = cpu_semantics && (len >= size);  // csrc/segment_tree.h:145-147 fast path (l == 0)
+    if (warp == 0) {
+      v = root ? __ldg(sum + 1) : warp_query_prefix<T, false>(sum, capacity, len, (T)0);
+    } else {
+      v = root ? __ldg(mn + 1) : warp_query_prefix<T, true>(mn, capacity, len, Limits<T>::max());
+    }
+    if ((threadIdx.x & 31) == 0) s_p[warp] = v;
+  }
+  __syncthreads();
+  const T p_sum = s_p[0], p_min = s_p[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (psum_pmin_out) {
+      psum_pmin_out[0] = p_sum;
+      psum_pmin_out[1] = p_min;
+    }
+    if (status) {
+      int32_t st = 0;
+      if (!(p_sum > (T)0)) st |= RLB_STATUS_NONPOS_PSUM;
+      if (!(p_min > (T)0)) st |= RLB_STATUS_NONPOS_PMIN;
+      if (st) atomicOr(status, st);
+    }
+  }
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const T mass = mul_rn(u[i], p_sum);  // samplers.py:919 / :923 -- one rounding, never fused downstream
+  int64_t idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1));
+  if (idx > len - 1) idx = len - 1;  // samplers.py:933
+  T leaf = __ldg(sum + (idx | capacity));
+  if (cpu_semantics) {
+    // samplers.py:935-943 (CPU trees only): walk left past zero-priority leaves
+    while (leaf == (T)0) {
+      idx -= 1;
+      if (idx < 0) {
+        if (status) atomicOr(status, RLB_STATUS_BACKOFF_FAIL);
+        idx = 0;
+        break;
+      }
+      leaf = __ldg(sum + (idx | capacity));
+    }
+  }
+  index_out[i] = idx;
+  if (leaf_out) leaf_out[i] = leaf;
+  weight_out[i] = (float)pow_like_torch(leaf / p_min, neg_beta);  // samplers.py:953
+}
+
+// ------------------------------------------------------------------------------------------------
+// update: single-CTA path (n <= 1024)
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kEmptyKey = 0xffffffffu;
+
+template <typename T>
+struct alignas(8) UpdSlot {
+  uint32_t key;  // parent node id (leaf node id for the dedupe round); kEmptyKey = free
+  uint32_t aux;  // levels: bit s set <=> child s deposited; dedupe round: 1 + max input position
+  T s[2];        // sum-tree value of child 0 / 1
+  T m[2];        // min-tree value of child 0 / 1
+};
+
+template <typename T>
+__device__ __forceinline__ uint32_t upd_probe_insert(UpdSlot<T> *tab, uint32_t mask, int log2_slots, uint32_t key,
+                                                     bool &owner) {
+  uint32_t h = (key * 0x9E3779B1u) >> (32 - log2_slots);
+  for (;;) {
+    const uint32_t prev = atomicCAS(&tab[h].key, kEmptyKey, key);
+    if (prev == kEmptyKey) {
+      owner = true;
+      return h;
+    }
+    if (prev == key) {
+      owner = false;
+      return h;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+// One thread per batch item.  Round "-1" elects, per distinct leaf, the item with the largest input
+// position (last-writer-wins, csrc/segment_tree.h:222-226 / cuda_segment_tree.cu:32-37).  Then for each
+// level a carrier thread deposits its node's (sum, min) value in the hash slot of the parent; the
+// thread that created the slot carries the parent upward, combining the two children in (left, right)
+// order; an untouched sibling comes from the (prefetched) global value.  Two tables alternate so a fast
+// thread's inserts for level k+1 never race with a slow thread's read+clear of level k.
+template <typename T>
+__global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, int64_t capacity, int depth,
+                                                               const int64_t *__restrict__ index,
+                                                               const T *__restrict__ value, int n, int scalar,
+                                                               int log2_slots) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  UpdSlot<T> *tab = reinterpret_cast<UpdSlot<T> *>(smem_raw);
+  const uint32_t nslots = 1u << log2_slots;
+  const uint32_t mask = nslots - 1;
+  const int tid = threadIdx.x;
+  for (uint32_t i = tid; i < 2 * nslots; i += blockDim.x) {
+    tab[i].key = kEmptyKey;
+    tab[i].aux = 0;
+  }
+  __syncthreads();
+
+  bool active = false;
+  uint32_t node = 0, slot = 0;
+  T vs = (T)0, vm = (T)0;
+  {
+    // ---- round -1: last-writer-wins election on table 1
+    UpdSlot<T> *t1 = tab + nslots;
+    if (tid < n) {
+      const int64_t ix = index[tid];
+      if (ix >= 0 && ix < capacity) {  // negative = "skip" (MaxValueWriter convention, samplers.py:1040-1052)
+        active = true;
+        node = (uint32_t)(capacity + ix);
+        bool owner;
+        slot = upd_probe_insert(t1, mask, log2_slots, node, owner);
+        atomicMax(&t1[slot].aux, (uint32_t)tid + 1u);
+      }
+    }
+    __syncthreads();
+    if (active) {
+      const uint32_t winner = t1[slot].aux - 1u;
+      if (winner != (uint32_t)tid) {
+        active = false;
+      } else {
+        t1[slot].key = kEmptyKey;
+        t1[slot].aux = 0;
+        const T v = scalar ? value[0] : value[tid];
+        vs = v;
+        vm = v;
+        if (sum) sum[node] = v;
+        if (mn) mn[node] = v;
+      }
+    }
+  }
+
+  for (int k = 0; k < depth; ++k) {
+    UpdSlot<T> *cur = tab + (uint32_t)(k & 1) * nslots;
+    bool owner = false;
+    T sib_s = (T)0, sib_m = (T)0;
+    const uint32_t side = node & 1u;
+    const uint32_t parent = node >> 1;
+    if (active) {
+      // old value of the sibling: only used if nobody in this batch carries it
+      if (sum) sib_s = ld_cg(sum + (node ^ 1u));
+      if (mn) sib_m = ld_cg(mn + (node ^ 1u));
+      slot = upd_probe_insert(cur, mask, log2_slots, parent, owner);
+      cur[slot].s[side] = vs;
+      cur[slot].m[side] = vm;
+      atomicOr(&cur[slot].aux, 1u << side);
+    }
+    __syncthreads();
+    if (active) {
+      if (!owner) {
+        active = false;  // the slot's creator carries the parent
+      } else {
+        const uint32_t other = side ^ 1u;
+        const bool has_other = (cur[slot].aux >> other) & 1u;
+        const T os = has_other ? cur[slot].s[other] : sib_s;
+        const T om = has_other ? cur[slot].m[other] : sib_m;
+        cur[slot].key = kEmptyKey;
+        cur[slot].aux = 0;
+        vs = side ? tree_op<T, false>(os, vs) : tree_op<T, false>(vs, os);
+        vm = side ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+        node = parent;
+        if (sum) sum[node] = vs;
+        if (mn) mn[node] = vm;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// update: general path (any n)
+// ------------------------------------------------------------------------------------------------
+// stamp[leaf] = max over this call's items of (epoch << 32 | position): the item whose position
+// survives is the last writer of that leaf.  The stamp array is persistent; `epoch` strictly increases
+// from call to call so it never needs clearing.
+__global__ void upd_stamp_kernel(unsigned long long *stamp, int64_t capacity, const int64_t *__restrict__ index,
+                                 int64_t n, uint32_t epoch) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t ix = index[i];
+  if (ix < 0 || ix >= capacity) return;
+  atomicMax(stamp + ix, ((unsigned long long)epoch << 32) | (unsigned long long)(uint32_t)i);
+}
+
+template <typename T>
+__global__ void upd_leaf_kernel(T *sum, T *mn, const unsigned long long *__restrict__ stamp, int64_t capacity,
+                                const int64_t *__restrict__ index, const T *__restrict__ value, int64_t n,
+                                int scalar) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t ix = index[i];
+  if (ix < 0 || ix >= capacity) return;
+  if ((uint32_t)(stamp[ix] & 0xffffffffull) != (uint32_t)i) return;  // a later duplicate wins
+  const T v = scalar ? value[0] : value[i];
+  if (sum) sum[capacity + ix] = v;
+  if (mn) mn[capacity + ix] = v;
+}
+
+// Recompute the level-(k+1) ancestor of every item from its two (already final) children.  Items that
+// share an ancestor write the same bits, so the race is benign.
+template <typename T>
+__global__ void upd_sweep_kernel(T *sum, T *mn, int64_t capacity, const int64_t *__restrict__ index, int64_t n,
+                                 int shift) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t ix = index[i];
+  if (ix < 0 || ix >= capacity) return;
+  const int64_t p = (capacity + ix) >> shift;
+  if (sum) sum[p] = tree_op<T, false>(ld_cg(sum + (p << 1)), ld_cg(sum + ((p << 1) | 1)));
+  if (mn) mn[p] = tree_op<T, true>(ld_cg(mn + (p << 1)), ld_cg(mn + ((p << 1) | 1)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused (priority + eps) ** alpha  (samplers.py:1076) + running max of the raw priorities
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  int *ia = reinterpret_cast<int *>(addr);
+  int old = *ia;
+  while (__int_as_float(old) < v) {
+    const int assumed = old;
+    old = atomicCAS(ia, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+
+__global__ void __launch_bounds__(256) per_update_prep_kernel(const int64_t *__restrict__ index,
+                                                              const float *__restrict__ priority, int64_t n,
+                                                              int scalar, float alpha, float eps,
+                                                              float *__restrict__ leaf, float *max_out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float p = -INFINITY;
+  if (i < n) {
+    const float raw = scalar ? priority[0] : priority[i];
+    leaf[i] = pow_like_torch(add_rn(raw, eps), alpha);
+    if (index[i] >= 0) p = raw;
+  }
+  if (max_out) {
+    for (int o = 16; o > 0; o >>= 1) p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
+    __shared__ float sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = sh[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[w]);
+      if (m > -INFINITY) atomic_max_float(max_out, m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int ilog2_i64(int64_t v) {
+  int d = 0;
+  while ((int64_t(1) << d) < v) ++d;
+  return d;
+}
+
+static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <typename T>
+static int tree_fill_impl(void *tree, int64_t capacity, int is_min, cudaStream_t st) {
+  const int64_t n = 2 * capacity;
+  const int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  const int64_t cap_blocks = (int64_t)sm_count() * 8;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  tree_fill_kernel<T><<<(unsigned)blocks, threads, 0, st>>>(static_cast<T *>(tree), n,
+                                                            is_min ? Limits<T>::max() : (T)0);
+  return check_launch("tree_fill_kernel");
+}
+
+template <typename T>
+static int tree_rebuild_impl(void *tree_, int64_t capacity, int is_min, cudaStream_t st) {
+  T *tree = static_cast<T *>(tree_);
+  const int threads = 256;
+  int64_t W = capacity >> 1;  // width of the deepest internal level
+  for (; W >= 1024; W >>= 1) {
+    int64_t blocks = (W + threads - 1) / threads;
+    const int64_t cap_blocks = (int64_t)sm_count() * 16;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    if (is_min)
+      tree_level_dense_kernel<T, true><<<(unsigned)blocks, threads, 0, st>>>(tree, W, W);
+    else
+      tree_level_dense_kernel<T, false><<<(unsigned)blocks, threads, 0, st>>>(tree, W, W);
+    int rc = check_launch("tree_level_dense_kernel");
+    if (rc) return rc;
+  }
+  // nodes [1024, 2048) are final here (for capacity <= 1024 the leaves are): dense top by one CTA
+  const int Wtop = (int)((capacity <= 1024) ? capacity : 1024);
+  if (Wtop >= 2) {
+    tree_top_kernel<T><<<1, 1024, 0, st>>>(is_min ? nullptr : tree, is_min ? tree : nullptr, Wtop);
+    return check_launch("tree_top_kernel");
+  }
+  return RLB_OK;
+}
+
+template <typename T>
+static int tree_update_impl(void *sum_, void *mn_, int64_t capacity, const int64_t *index, const void *value_,
+                            int64_t n, int scalar, void *workspace, size_t workspace_bytes, uint32_t epoch,
+                            cudaStream_t st) {
+  T *sum = static_cast<T *>(sum_);
+  T *mn = static_cast<T *>(mn_);
+  const T *value = static_cast<const T *>(value_);
+  const int depth = ilog2_i64(capacity);
+  if (n <= 1024 && capacity <= (int64_t(1) << 30)) {
+    int threads = (int)((n + 31) / 32 * 32);
+    int log2_slots = 6;
+    while ((1 << log2_slots) < 2 * n) ++log2_slots;
+    const size_t smem = 2 * (size_t(1) << log2_slots) * sizeof(UpdSlot<T>);
+    static bool attr_set = false;
+    if (!attr_set) {
+      int rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                          "cudaFuncSetAttribute(tree_update_cta_kernel)");
+      if (rc) return rc;
+      attr_set = true;
+    }
+    tree_update_cta_kernel<T><<<1, threads, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n, scalar,
+                                                        log2_slots);
+    return check_launch("tree_update_cta_kernel");
+  }
+  // general path
+  RLB_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)capacity * sizeof(unsigned long long),
+              RLB_EINVAL, "rlb_tree_update: n=%lld needs a workspace of rlb_tree_update_workspace_bytes(size)",
+              (long long)n);
+  RLB_REQUIRE(n < (int64_t(1) << 32), RLB_ELIMIT, "rlb_tree_update: n must be < 2^32");
+  unsigned long long *stamp = static_cast<unsigned long long *>(workspace);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  upd_stamp_kernel<<<blocks, threads, 0, st>>>(stamp, capacity, index, n, epoch);
+  int rc = check_launch("upd_stamp_kernel");
+  if (rc) return rc;
+  upd_leaf_kernel<T><<<blocks, threads, 0, st>>>(sum, mn, stamp, capacity, index, value, n, scalar);
+  rc = check_launch("upd_leaf_kernel");
+  if (rc) return rc;
+  // sweep the levels of width >= 1024 (touched ancestors only), then one CTA recomputes the dense top
+  int shift = 1;
+  for (int64_t W = capacity >> 1; W >= 1024; W >>= 1, ++shift) {
+    upd_sweep_kernel<T><<<blocks, threads, 0, st>>>(sum, mn, capacity, index, n, shift);
+    rc = check_launch("upd_sweep_kernel");
+    if (rc) return rc;
+  }
+  const int Wtop = (int)((capacity <= 1024) ? capacity : 1024);
+  if (Wtop >= 2) {
+    tree_top_kernel<T><<<1, 1024, 0, st>>>(sum, mn, Wtop);
+    rc = check_launch("tree_top_kernel");
+  }
+  return rc;
+}
+
+}  // namespace rlb
+
+using namespace rlb;
+
+extern "C" {
+
+int64_t rlb_tree_capacity(int64_t size) {
+  int64_t c = 1;
+  for (; c <= size; c <<= 1) {
+  }
+  return c;
+}
+
+size_t rlb_tree_update_workspace_bytes(int64_t size) {
+  // one 64-bit (epoch, position) stamp per addressable leaf slot; the kernels bound-check against capacity
+  return (size_t)rlb_tree_capacity(size) * sizeof(unsigned long long);
+}
+
+int rlb_tree_fill(void *tree, int64_t capacity, int is_min, int dtype, rlb_stream_t stream) {
+  RLB_REQUIRE(tree && is_pow2(capacity), RLB_EINVAL, "rlb_tree_fill: null tree or capacity not a power of two");
+  if (dtype == RLB_F32) return tree_fill_impl<float>(tree, capacity, is_min, as_stream(stream));
+  if (dtype == RLB_F64) return tree_fill_impl<double>(tree, capacity, is_min, as_stream(stream));
+  RLB_REQUIRE(false, RLB_EINVAL, "rlb_tree_fill: unsupported dtype %d", dtype);
+}
+
+int rlb_tree_rebuild(void *tree, int64_t capacity, int is_min, int dtype, rlb_stream_t stream) {
+  RLB_REQUIRE(tree && is_pow2(capacity), RLB_EINVAL, "rlb_tree_rebuild: null tree or capacity not a power of two");
+  if (dtype == RLB_F32) return tree_rebuild_impl<float>(tree, capacity, is_min, as_stream(stream));
+  if (dtype == RLB_F64) return tree_rebuild_impl<double>(tree, capacity, is_min, as_stream(stream));
+  RLB_REQUIRE(false, RLB_EINVAL, "rlb_tree_rebuild: unsupported dtype %d", dtype);
+}
+
+int rlb_tree_update(void *sum_tree, void *min_tree, int64_t capacity, const int64_t *index, const void *value,
+                    int64_t n, int scalar, int dtype, void *workspace, size_t workspace_bytes, uint32_t epoch,
+                    rlb_stream_t stream) {
+  RLB_REQUIRE((sum_tree || min_tree) && is_pow2(capacity), RLB_EINVAL,
+              "rlb_tree_update: no tree given or capacity not a power of two");
+  RLB_REQUIRE(n >= 0, RLB_EINVAL, "rlb_tree_update: negative n");
+  if (n == 0) return RLB_OK;
+  RLB_REQUIRE(index && value, RLB_EINVAL, "rlb_tree_update: null index/value");
+  if (dtype == RLB_F32)
+    return tree_update_impl<float>(sum_tree, min_tree, capacity, index, value, n, scalar, workspace,
+                                   workspace_bytes, epoch, as_stream(stream));
+  if (dtype == RLB_F64)
+    return tree_update_impl<double>(sum_tree, min_tree, capacity, index, value, n, scalar, workspace,
+                                    workspace_bytes, epoch, as_stream(stream));
+  RLB_REQUIRE(false, RLB_EINVAL, "rlb_tree_update: unsupported dtype %d", dtype);
+}
+
+int rlb_tree_query(const void *tree, int64_t size, int64_t capacity, int is_min, int dtype, const int64_t *l,
+                   const int64_t *r, void *out, int64_t n, int root_fast_path, rlb_stream_t stream) {
+  RLB_REQUIRE(tree && is_pow2(capacity) && n >= 0, RLB_EINVAL, "rlb_tree_query: bad arguments");
+  if (n == 0) return RLB_OK;
+  RLB_REQUIRE(l && r && out, RLB_EINVAL, "rlb_tree_query: null l/r/out");
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == RLB_F32) {
+    if (is_min)
+      tree_query_kernel<float, true><<<blocks, threads, 0, st>>>((const float *)tree, size, capacity, l, r,
+                                                                 (float *)out, n, root_fast_path,
+                                                                 Limits<float>::max());
+    else
+      tree_query_kernel<float, false><<<blocks, threads, 0, st>>>((const float *)tree, size, capacity, l, r,
+                                                                  (float *)out, n, root_fast_path, 0.0f);
+  } else if (dtype == RLB_F64) {
+    if (is_min)
+      tree_query_kernel<double, true><<<blocks, threads, 0, st>>>((const double *)tree, size, capacity, l, r,
+                                                                  (double *)out, n, root_fast_path,
+                                                                  Limits<double>::max());
+    else
+      tree_query_kernel<double, false><<<blocks, threads, 0, st>>>((const double *)tree, size, capacity, l, r,
+                                                                   (double *)out, n, root_fast_path, 0.0);
+  } else {
+    RLB_REQUIRE(false, RLB_EINVAL, "rlb_tree_query: unsupported dtype %d", dtype);
+  }
+  return check_launch("tree_query_kernel");
+}
+
+int rlb_tree_at(const void *tree, int64_t capacity, int dtype, const int64_t *index, void *out, int64_t n,
+                rlb_stream_t stream) {
+  RLB_REQUIRE(tree && is_pow2(capacity) && n >= 0, RLB_EINVAL, "rlb_tree_at: bad arguments");
+  if (n == 0) return RLB_OK;
+  RLB_REQUIRE(index && out, RLB_EINVAL, "rlb_tree_at: null index/out");
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (dtype == RLB_F32)
+    tree_at_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>((const float *)tree, capacity, index,
+                                                                     (float *)out, n);
+  else if (dtype == RLB_F64)
+    tree_at_kernel<double><<<blocks, threads, 0, as_stream(stream)>>>((const double *)tree, capacity, index,
+                                                                      (double *)out, n);
+  else
+    RLB_REQUIRE(false, RLB_EINVAL, "rlb_tree_at: unsupported dtype %d", dtype);
+  return check_launch("tree_at_kernel");
+}
+
+int rlb_tree_scan_lower_bound(const void *sum_tree, int64_t size, int64_t capacity, int dtype, const void *value,
+                              int64_t *out, int64_t n, rlb_stream_t stream) {
+  RLB_REQUIRE(sum_tree && is_pow2(capacity) && n >= 0, RLB_EINVAL, "rlb_tree_scan_lower_bound: bad arguments");
+  if (n == 0) return RLB_OK;
+  RLB_REQUIRE(value && out, RLB_EINVAL, "rlb_tree_scan_lower_bound: null value/out");
+  const int depth = ilog2_i64(capacity);
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (dtype == RLB_F32)
+    tree_scan_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>((const float *)sum_tree, size, capacity,
+                                                                       depth, (const float *)value, out, n);
+  else if (dtype == RLB_F64)
+    tree_scan_kernel<double><<<blocks, threads, 0, as_stream(stream)>>>((const double *)sum_tree, size, capacity,
+                                                                        depth, (const double *)value, out, n);
+  else
+    RLB_REQUIRE(false, RLB_EINVAL, "rlb_tree_scan_lower_bound: unsupported dtype %d", dtype);
+  return check_launch("tree_scan_kernel");
+}
+
+int rlb_per_sample(const void *sum_tree, const void *min_tree, int64_t size, int64_t capacity, int dtype,
+                   int64_t len, const void *u, int64_t B, double beta, int cpu_semantics, int64_t *index_out,
+                   float *weight_out, void *leaf_out, void *psum_pmin_out, int32_t *status, rlb_stream_t stream) {
+  RLB_REQUIRE(sum_tree && min_tree && is_pow2(capacity), RLB_EINVAL, "rlb_per_sample: null tree or bad capacity");
+  RLB_REQUIRE(size > 0 && size < capacity, RLB_EINVAL, "rlb_per_sample: size must be in (0, capacity)");
+  RLB_REQUIRE(len > 0 && len <= size, RLB_EINVAL,
+              "rlb_per_sample: len=%lld outside (0, size=%lld] (Cannot sample from an empty storage.)",
+              (long long)len, (long long)size);
+  RLB_REQUIRE(B >= 0, RLB_EINVAL, "rlb_per_sample: negative batch");
+  if (B == 0) return RLB_OK;
+  RLB_REQUIRE(u && index_out && weight_out, RLB_EINVAL, "rlb_per_sample: null u/index_out/weight_out");
+  const int depth = ilog2_i64(capacity);
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((B + threads - 1) / threads);
+  if (dtype == RLB_F32)
+    per_sample_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(
+        (const float *)sum_tree, (const float *)min_tree, size, capacity, depth, len, (const float *)u, B,
+        (float)(-beta), cpu_semantics, index_out, weight_out, (float *)leaf_out, (float *)psum_pmin_out, status);
+  else if (dtype == RLB_F64)
+    per_sample_kernel<double><<<blocks, threads, 0, as_stream(stream)>>>(
+        (const double *)sum_tree, (const double *)min_tree, size, capacity, depth, len, (const double *)u, B,
+        -beta, cpu_semantics, index_out, weight_out, (double *)leaf_out, (double *)psum_pmin_out, status);
+  else
+    RLB_REQUIRE(false, RLB_EINVAL, "rlb_per_sample: unsupported dtype %d", dtype);
+  return check_launch("per_sample_kernel");
+}
+
+int rlb_per_update(void *sum_tree, void *min_tree, int64_t capacity, const int64_t *index, const float *priority,
+                   int64_t n, int scalar, double alpha, double eps, float *leaf_scratch, float *max_priority_out,
+                   void *workspace, size_t workspace_bytes, uint32_t epoch, rlb_stream_t stream) {
+  RLB_REQUIRE((sum_tree || min_tree) && is_pow2(capacity), RLB_EINVAL, "rlb_per_update: bad tree/capacity");
+  RLB_REQUIRE(n >= 0, RLB_EINVAL, "rlb_per_update: negative n");
+  if (n == 0) return RLB_OK;
+  RLB_REQUIRE(index && priority && leaf_scratch, RLB_EINVAL, "rlb_per_update: null index/priority/leaf_scratch");
+  cudaStream_t st = as_stream(stream);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  per_update_prep_kernel<<<blocks, threads, 0, st>>>(index, priority, n, scalar, (float)alpha, (float)eps,
+                                                     leaf_scratch, max_priority_out);
+  int rc = check_launch("per_update_prep_kernel");
+  if (rc) return rc;
+  return tree_update_impl<float>(sum_tree, min_tree, capacity, index, leaf_scratch, n, /*scalar=*/0, workspace,
+                                 workspace_bytes, epoch, st);
+}
+
+}  // extern "C"

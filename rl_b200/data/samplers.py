@@ -1,0 +1,466 @@
+"""Samplers: the host-side mirror of ``torchrl.data.replay_buffers.samplers`` for the hot path.
+
+    Sampler             abstract contract                       samplers.py:99-171
+    RandomSampler       uniform with replacement                samplers.py:174-218
+    PrioritizedSampler  proportional PER, sum/min segment trees samplers.py:577-1205
+
+``PrioritizedSampler`` keeps the reference's constructor, properties, bookkeeping quirks (double ``pow``
+on default priorities, running max of raw priorities, SURVEY.md 8a') and error messages, but its trees
+live in HBM and its arithmetic is two kernel launches:
+
+    sample           torch.rand(B, generator)  ->  rlb_per_sample   (query x2, mass, descent, clamp, leaf,
+                                                                     importance weight in ONE launch)
+    update_priority  rlb_per_update  ((p+eps)**alpha, running max, last-writer-wins scatter, touched-ancestor
+                                      recomputation of both trees)
+
+``torch.rand`` stays a torch call so the random stream is literally the reference's (samplers.py:918).
+"""
+from __future__ import annotations
+
+import abc
+import json
+from copy import deepcopy
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import ops
+from .segment_tree import MinSegmentTreeFp32, MinSegmentTreeFp64, SumSegmentTreeFp32, SumSegmentTreeFp64
+from .storages import Storage
+from .utils import _is_int, unravel_index
+
+_EMPTY_STORAGE_ERROR = "Cannot sample from an empty storage."
+
+
+class Sampler(abc.ABC):
+    """A generic sampler base class for composable replay buffers (samplers.py:99-171)."""
+
+    _rng: torch.Generator | None = None
+
+    @abc.abstractmethod
+    def sample(self, storage: Storage, batch_size: int) -> tuple[Any, dict]:
+        ...
+
+    def add(self, index: int) -> None:
+        return
+
+    def extend(self, index) -> None:
+        return
+
+    def update_priority(self, index, priority, *, storage: Storage | None = None) -> dict | None:
+        return
+
+    def mark_update(self, index, *, storage: Storage | None = None) -> None:
+        return
+
+    @property
+    def default_priority(self) -> float:
+        return 1.0
+
+    @abc.abstractmethod
+    def state_dict(self) -> dict:
+        ...
+
+    @abc.abstractmethod
+    def load_state_dict(self, state_dict: dict) -> None:
+        ...
+
+    @property
+    def ran_out(self) -> bool:
+        # by default, samplers never run out
+        return False
+
+    @abc.abstractmethod
+    def _empty(self) -> None:
+        ...
+
+    @abc.abstractmethod
+    def dumps(self, path) -> None:
+        ...
+
+    @abc.abstractmethod
+    def loads(self, path) -> None:
+        ...
+
+    @property
+    def _remaining_batches(self) -> int:
+        return torch.iinfo(torch.int64).max
+
+    def __repr__(self) -> str:
+        return f"{self.__class__.__name__}()"
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_rng"] = None
+        return state
+
+
+class RandomSampler(Sampler):
+    """A uniformly random sampler with replacement (samplers.py:174-218)."""
+
+    def sample(self, storage: Storage, batch_size: int) -> tuple[torch.Tensor, dict]:
+        if len(storage) == 0:
+            raise RuntimeError(_EMPTY_STORAGE_ERROR)
+        return storage._rand_given_ndim(batch_size), {}
+
+    def _empty(self) -> None:
+        pass
+
+    def dumps(self, path) -> None:
+        pass
+
+    def loads(self, path) -> None:
+        pass
+
+    def state_dict(self) -> dict:
+        return {}
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        return
+
+
+class PrioritizedSampler(Sampler):
+    r"""Prioritized experience replay sampler (Schaul et al. 2015) -- samplers.py:577-1205.
+
+    :math:`P(i) = p_i^\alpha / \sum_j p_j^\alpha`, importance weight
+    :math:`w_i = (p_i^\alpha / \min_j p_j^\alpha)^{-\beta}`.
+
+    Args:
+        max_capacity (int): maximum capacity of the buffer.
+        alpha (float): prioritisation exponent (0 = uniform).
+        beta (float): importance-sampling exponent.
+        eps (float): added to priorities so that none is zero. Defaults to 1e-8.
+        dtype (torch.dtype): tree dtype, ``torch.float`` (default) or ``torch.double``.
+        reduction (str): how multi-dim priorities are reduced: "max", "min", "median" or "mean".
+        max_priority_within_buffer (bool): track the max priority among the items currently stored
+            instead of the max ever seen.
+        device: device holding the trees.  ``None``: the storage's CUDA device at first use.
+
+    Extra keyword (not in the reference):
+        semantics ("cpu" | "cuda"): which reference tree the sampling arithmetic reproduces when the two
+            differ.  "cpu" (default) = ``SumSegmentTree`` on the host: ``query(0, len)`` returns the root when
+            ``len >= size`` and zero-priority leaves are walked past (samplers.py:935-943); "cuda" = the
+            reference's CUDA port, which always walks the query and has no back-off.
+    """
+
+    def __init__(self, max_capacity: int, alpha: float, beta: float, eps: float = 1e-8,
+                 dtype: torch.dtype = torch.float, reduction: str = "max", max_priority_within_buffer: bool = False,
+                 device=None, *, semantics: str = "cpu") -> None:
+        if alpha < 0:
+            raise ValueError(f"alpha must be greater or equal than 0, got alpha={alpha}")
+        if beta < 0:
+            raise ValueError(f"beta must be greater or equal to 0, got beta={beta}")
+        if semantics not in ("cpu", "cuda"):
+            raise ValueError("semantics must be 'cpu' or 'cuda'")
+        self._max_capacity = int(max_capacity)
+        self._alpha = alpha
+        self._beta = beta
+        self._eps = eps
+        self.reduction = reduction
+        self.dtype = dtype
+        self._max_priority_within_buffer = max_priority_within_buffer
+        self._device = torch.device(device) if device is not None else None
+        self._semantics = semantics
+        self._sum_tree = None
+        self._min_tree = None
+        if self._device is not None:
+            self._init()
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(alpha={self._alpha}, beta={self._beta}, eps={self._eps}, "
+                f"reduction={self.reduction})")
+
+    # ---- properties --------------------------------------------------------------------------------
+    @property
+    def max_size(self) -> int:
+        return self._max_capacity
+
+    @property
+    def device(self) -> torch.device | None:
+        if self._sum_tree is not None:
+            return self._sum_tree.device
+        return self._device
+
+    @property
+    def alpha(self):
+        return self._alpha
+
+    @alpha.setter
+    def alpha(self, value):
+        self._alpha = value
+
+    @property
+    def beta(self):
+        return self._beta
+
+    @beta.setter
+    def beta(self, value):
+        self._beta = value
+
+    def __getstate__(self):
+        import multiprocessing.context as mpc
+
+        if mpc.get_spawning_popen() is not None:
+            raise RuntimeError(
+                f"Samplers of type {type(self)} cannot be shared between processes. "
+                "Use TensorDictPrioritizedReplayBuffer(sync=False) instead: the writer process gets a uniform "
+                "sampler and the learner keeps a local prioritized sampler.")
+        return super().__getstate__()
+
+    # ---- tree lifetime -----------------------------------------------------------------------------
+    def _maybe_init_from_storage(self, storage: Storage | None) -> None:
+        # trees follow the storage's device when no explicit device was given (samplers.py:758-775)
+        if self._sum_tree is not None:
+            return
+        device = self._device
+        if device is None and storage is not None:
+            sd = getattr(storage, "device", None)
+            if sd is not None and sd != "auto":
+                device = torch.device(sd)
+        if device is None:
+            raise RuntimeError(
+                "PrioritizedSampler needs a device for its HBM-resident trees: pass device=... or use it with a "
+                "storage that has one.")
+        self._device = device
+        self._init()
+
+    def _init(self) -> None:
+        if self.dtype in (torch.float, torch.float32):
+            self._sum_tree = SumSegmentTreeFp32(self._max_capacity, self._device)
+            self._min_tree = MinSegmentTreeFp32(self._max_capacity, self._device)
+        elif self.dtype in (torch.double, torch.float64):
+            self._sum_tree = SumSegmentTreeFp64(self._max_capacity, self._device)
+            self._min_tree = MinSegmentTreeFp64(self._max_capacity, self._device)
+        else:
+            raise NotImplementedError(f"dtype {self.dtype} not supported by PrioritizedSampler")
+        dev = self._sum_tree.device
+        # running max of the RAW priorities ever passed to update_priority (samplers.py:1054-1075), kept on
+        # the device so that no call has to synchronise; -inf until the first update.
+        self._max_priority_buf = torch.full((1,), float("-inf"), dtype=torch.float32, device=dev)
+        self._has_max_priority = False
+        self._max_priority_index = None
+        self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._workspace = None
+        self._epoch = 0
+
+    def _empty(self) -> None:
+        if self._device is not None:
+            self._init()
+
+    def _tree_epoch(self) -> int:
+        self._epoch += 1
+        if self._epoch >= 0xFFFFFFFF:
+            if self._workspace is not None:
+                self._workspace.zero_()
+            self._epoch = 1
+        return self._epoch
+
+    def _tree_workspace(self, n: int):
+        if n > 1024 and self._workspace is None:
+            self._workspace = ops.backend().tree_workspace(self._max_capacity, self._sum_tree.device)
+        return self._workspace
+
+    # ---- max-priority bookkeeping ------------------------------------------------------------------
+    @property
+    def _max_priority(self) -> tuple:
+        if not self._has_max_priority:
+            return (None, None)
+        return (self._max_priority_buf[0], self._max_priority_index)
+
+    @property
+    def default_priority(self):
+        # (max_priority + eps) ** alpha, max_priority = 1 before any update (samplers.py:886-893).
+        # NB: mark_update feeds this through update_priority, which applies (. + eps) ** alpha AGAIN.
+        if not self._has_max_priority:
+            return (1 + self._eps) ** self._alpha
+        return (self._max_priority_buf[0] + self._eps) ** self._alpha
+
+    # ---- sample (samplers.py:895-956) --------------------------------------------------------------
+    def sample(self, storage: Storage, batch_size: int) -> tuple[Any, dict]:
+        self._maybe_init_from_storage(storage)
+        length = len(storage)
+        if length == 0:
+            raise RuntimeError(_EMPTY_STORAGE_ERROR)
+        dev = self._sum_tree.device
+        u = torch.rand(batch_size, device=dev, generator=self._rng, dtype=self._sum_tree._dtype)
+        index, weight = ops.backend().per_sample(
+            self._sum_tree.values, self._min_tree.values, self._max_capacity, self._sum_tree.capacity, length, u,
+            self._beta, self._semantics == "cpu", status=self._status)
+        if storage.ndim > 1:
+            index = unravel_index(index, storage.shape)
+        return index, {"priority_weight": weight}
+
+    def check_status(self) -> None:
+        """Synchronise and raise what the CPU reference raises eagerly (samplers.py:910-914,940-941)."""
+        st = int(self._status.item())
+        self._status.zero_()
+        if st & ops.STATUS_NONPOS_PSUM:
+            raise RuntimeError("non-positive p_sum")
+        if st & ops.STATUS_NONPOS_PMIN:
+            raise RuntimeError("non-positive p_min")
+        if st & ops.STATUS_BACKOFF_FAIL:
+            raise RuntimeError("Failed to find a suitable index")
+
+    def add(self, index) -> None:
+        super().add(index)
+        self._maybe_erase_max_priority(index)
+
+    def extend(self, index) -> None:
+        super().extend(index)
+        self._maybe_erase_max_priority(index)
+
+    def _maybe_erase_max_priority(self, index) -> None:
+        # only meaningful with max_priority_within_buffer (samplers.py:840-884): forget the max when the item
+        # that held it is overwritten.  Device-side comparisons would need a sync; like the reference's CUDA
+        # branch (:876-878) we simply drop the max.
+        if not self._max_priority_within_buffer or not self._has_max_priority:
+            return
+        self._has_max_priority = False
+        self._max_priority_buf.fill_(float("-inf"))
+        self._max_priority_index = None
+
+    # ---- update_priority (samplers.py:966-1091) ----------------------------------------------------
+    @torch.no_grad()
+    def update_priority(self, index, priority, *, storage: Storage | None = None) -> None:
+        """Updates the priority of the data pointed by the index.
+
+        Args:
+            index (int or torch.Tensor): indexes of the priorities to be updated.
+            priority (Number or torch.Tensor): new priorities of the indexed elements.
+
+        Keyword Args:
+            storage (Storage, optional): needed to map N-d indices to the trees' flat index.
+        """
+        self._maybe_init_from_storage(storage)
+        dev = self._sum_tree.device
+        priority = torch.as_tensor(priority, device=dev).detach()
+        index = torch.as_tensor(index, dtype=torch.long, device=dev)
+        if priority.numel() > 1 and priority.shape != index.shape:
+            try:
+                priority = priority.reshape(index.shape[:1])
+            except Exception as err:
+                raise RuntimeError(
+                    "priority should be a number or an iterable of the same "
+                    f"length as index. Got priority of shape {priority.shape} and index {index.shape}.") from err
+        elif priority.numel() <= 1:
+            priority = priority.squeeze()
+        if index.ndim == 0:
+            index = index.view(1)
+            if priority.ndim == 0:
+                priority = priority.view(1)
+        if index.ndim > 1:
+            if storage is None:
+                raise RuntimeError(
+                    "storage should be provided to Sampler.update_priority when the storage has more "
+                    "than one dimension.")
+            try:
+                shape = storage.shape
+            except AttributeError:
+                raise AttributeError(
+                    "Could not retrieve the storage shape. If your storage is not a TensorStorage subclass "
+                    "or its shape isn't accessible via the shape attribute, submit an issue on GitHub.")
+            mult = torch.ones(index.shape[-1], dtype=torch.long, device=dev)
+            for d in range(index.shape[-1] - 2, -1, -1):
+                mult[d] = mult[d + 1] * shape[d + 1]
+            index = (index * mult).sum(-1)
+        if index.numel() == 0:
+            return
+        index = index.reshape(-1)
+        priority = priority.reshape(-1)
+        # negative indices (MaxValueWriter's "do not write" marker, :1040-1052) are skipped by the kernel
+        tree_dtype = self._sum_tree._dtype
+        if tree_dtype == torch.float32:
+            priority = priority.to(torch.float32)
+            ops.backend().per_update(self._sum_tree.values, self._min_tree.values, self._sum_tree.capacity, index,
+                                     priority, self._alpha, self._eps, self._max_priority_buf,
+                                     self._tree_workspace(index.numel()), self._tree_epoch())
+        else:
+            valid = index >= 0
+            pmax = torch.where(valid, priority.expand_as(index), priority.new_full((), float("-inf"))).max()
+            self._max_priority_buf.copy_(torch.maximum(self._max_priority_buf[0], pmax.to(torch.float32)).view(1))
+            leaf = torch.pow(priority.to(tree_dtype) + self._eps, self._alpha)
+            ops.backend().tree_update(self._sum_tree.values, self._min_tree.values, self._sum_tree.capacity, index,
+                                      leaf, self._tree_workspace(index.numel()), self._tree_epoch())
+        self._has_max_priority = True
+        if self._max_priority_within_buffer:
+            # O(N) rescan of the leaves, as the reference does (samplers.py:1079-1091) -- one reduction here
+            leaves = self._sum_tree.values[self._sum_tree.capacity:self._sum_tree.capacity + self._max_capacity]
+            maxval, maxidx = leaves.max(0)
+            self._max_priority_buf.copy_(maxval.to(torch.float32).view(1))
+            self._max_priority_index = maxidx
+
+    def mark_update(self, index, *, storage: Storage | None = None) -> None:
+        self.update_priority(index, self.default_priority, storage=storage)
+
+    # ---- (de)serialisation -------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        mp = self._max_priority
+        return {
+            "_alpha": self._alpha,
+            "_beta": self._beta,
+            "_eps": self._eps,
+            "_max_priority": (None if mp[0] is None else float(mp[0]),
+                              None if mp[1] is None else int(mp[1])),
+            "_sum_tree": deepcopy(self._sum_tree),
+            "_min_tree": deepcopy(self._min_tree),
+        }
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        self._alpha = state_dict["_alpha"]
+        self._beta = state_dict["_beta"]
+        self._eps = state_dict["_eps"]
+        st, mt = state_dict["_sum_tree"], state_dict["_min_tree"]
+        if self._sum_tree is None:
+            self._device = st.device
+            self._init()
+        self._sum_tree.load_leaves(st.dump_leaves())
+        self._min_tree.load_leaves(mt.dump_leaves())
+        self._set_max_priority(state_dict["_max_priority"])
+
+    def _set_max_priority(self, mp) -> None:
+        val, idx = mp if mp is not None else (None, None)
+        self._has_max_priority = val is not None
+        self._max_priority_buf.fill_(float("-inf") if val is None else float(val))
+        self._max_priority_index = idx
+
+    def dumps(self, path) -> None:
+        """Same on-disk layout as the reference (samplers.py:1120-1163): the LEAVES of both trees as float64
+        ``sumtree.memmap`` / ``mintree.memmap`` + ``sampler_metadata.json`` -- written with one D2H copy per
+        tree instead of one pybind call per element."""
+        path = Path(path).absolute()
+        path.mkdir(exist_ok=True, parents=True)
+        if self._sum_tree is None:
+            raise RuntimeError("cannot dump a PrioritizedSampler whose trees were never created")
+        for name, tree in (("sumtree.memmap", self._sum_tree), ("mintree.memmap", self._min_tree)):
+            arr = np.memmap(path / name, dtype=np.float64, mode="w+", shape=(self._max_capacity,))
+            arr[:] = tree.dump_leaves().to(torch.float64).cpu().numpy()
+            arr.flush()
+        mp = self._max_priority
+        with open(path / "sampler_metadata.json", "w") as file:
+            json.dump({"_alpha": float(self._alpha), "_beta": float(self._beta), "_eps": float(self._eps),
+                       "_max_priority": [None if mp[0] is None else float(mp[0]),
+                                         None if mp[1] is None else float(mp[1])],
+                       "_max_capacity": float(self._max_capacity)}, file)
+
+    def loads(self, path) -> None:
+        path = Path(path).absolute()
+        with open(path / "sampler_metadata.json") as file:
+            metadata = json.load(file)
+        self._alpha = metadata["_alpha"]
+        self._beta = metadata["_beta"]
+        self._eps = metadata["_eps"]
+        cap = int(metadata["_max_capacity"])
+        if cap != self._max_capacity:
+            raise RuntimeError(
+                f"max capacity of loaded metadata ({cap}) differs from self._max_capacity ({self._max_capacity}).")
+        if self._sum_tree is None:
+            if self._device is None:
+                raise RuntimeError("pass device=... to PrioritizedSampler before loads()")
+            self._init()
+        for name, tree in (("sumtree.memmap", self._sum_tree), ("mintree.memmap", self._min_tree)):
+            arr = np.memmap(path / name, dtype=np.float64, mode="r", shape=(self._max_capacity,))
+            tree.load_leaves(torch.from_numpy(np.ascontiguousarray(arr)))
+        mp = metadata["_max_priority"]
+        self._set_max_priority((mp[0], None if mp[1] is None else int(mp[1])))

@@ -1,0 +1,124 @@
+"""Functional advantage estimators: mirror of ``torchrl.objectives.value.functional`` for GAE.
+
+    generalized_advantage_estimate       functional.py:119-180   (python time loop in the reference)
+    vec_generalized_advantage_estimate   functional.py:270-370   (pad + conv1d in the reference)
+
+Both names resolve to the same single kernel launch (``rlb_gae``, csrc/gae.cu): a warp-level discounted
+reverse scan that reads every input element once and writes every output element once, with no host
+synchronisation.  Signatures, the ``time_dim`` convention, the shape check and its error message are the
+reference's.  Forward only (the reference runs GAE under ``no_grad`` unless ``differentiable=True``).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ... import ops
+
+SHAPE_ERR = "All input tensors (value, reward and done states) must share a unique shape."
+
+__all__ = ["generalized_advantage_estimate", "vec_generalized_advantage_estimate", "gae_scalars"]
+
+
+def gae_scalars(gamma, lmbda, dtype: torch.dtype) -> tuple[float, float]:
+    """(gamma, gamma*lmbda) rounded the way the reference rounds them.
+
+    Tensor arguments (what the GAE module passes, advantages.py:1456-1467) are multiplied as 0-d tensors
+    (functional.py:249), so the product is rounded once in the tensors' dtype; Python numbers are multiplied
+    in double and only cast when they meet a tensor.  Returned as Python floats (exactly representable).
+    Calling this with CUDA tensors synchronises -- the GAE module caches the result instead.
+    """
+    if isinstance(gamma, torch.Tensor) or isinstance(lmbda, torch.Tensor):
+        g = gamma if isinstance(gamma, torch.Tensor) else torch.tensor(gamma)
+        l = lmbda if isinstance(lmbda, torch.Tensor) else torch.tensor(lmbda, device=g.device)
+        if g.numel() > 1 or l.numel() > 1:
+            raise NotImplementedError(
+                "tensor-valued gamma / lmbda (one value per step) are not supported by the B200 GAE kernel yet; "
+                "pass scalars.")
+        gl = (g * l.to(g.device)).to(dtype)
+        return float(g.to(dtype)), float(gl)
+    cast = torch.tensor([float(gamma), float(gamma) * float(lmbda)], dtype=dtype)
+    return float(cast[0]), float(cast[1])
+
+
+def _time_to_minus2(t: torch.Tensor, time_dim: int):
+    """Bring ``time_dim`` to position -2 (functional.py:47-111); returns (tensor, squeeze_back)."""
+    td = time_dim - t.ndim if time_dim >= 0 else time_dim
+    if td < -t.ndim or td >= 0:
+        raise RuntimeError(
+            f"The tensor shape and the time dimension are not compatible: got {t.shape} and time_dim={td}.")
+    if t.ndim >= 2:
+        return t.transpose(td, -2), False
+    if t.ndim == 1 and td == -1:
+        return t.unsqueeze(-1), True
+    raise RuntimeError(f"The tensor shape and the time dimension are not compatible: got {t.shape} and time_dim={td}.")
+
+
+def _gae_impl(gamma, lmbda, state_value, next_state_value, reward, done, terminated, time_dim, scalars=None):
+    if terminated is None:
+        terminated = done
+    if not (next_state_value.shape == state_value.shape == reward.shape == done.shape == terminated.shape):
+        raise RuntimeError(SHAPE_ERR)
+    if state_value.requires_grad or next_state_value.requires_grad or reward.requires_grad:
+        if torch.is_grad_enabled():
+            raise NotImplementedError(
+                "the B200 GAE kernel is forward-only: call it under torch.no_grad() (GAE(differentiable=False), the "
+                "default) or detach the inputs.")
+    dtype = state_value.dtype
+    if dtype not in (torch.float32, torch.float64):
+        raise NotImplementedError(f"GAE kernel supports fp32 / fp64 values, got {dtype}")
+    squeeze = False
+    tensors = [state_value, next_state_value, reward, done, terminated]
+    nd = state_value.ndim
+    td = time_dim - nd if time_dim >= 0 else time_dim  # normalised to a negative index
+    if td != -2 or nd < 2:
+        moved = [_time_to_minus2(t, time_dim) for t in tensors]
+        squeeze = any(s for _, s in moved)
+        tensors = [t for t, _ in moved]
+    v, nv, r, d, tm = tensors
+    shape = v.shape
+    T, F = shape[-2], shape[-1]
+    rows = math.prod(shape[:-2])
+    v = v.detach().contiguous()
+    nv = nv.detach().to(dtype).contiguous()
+    r = r.detach().to(dtype).contiguous()
+    d = d.to(torch.bool).contiguous().view(torch.uint8)
+    tm = tm.to(torch.bool).contiguous().view(torch.uint8)
+    g, gl = scalars if scalars is not None else gae_scalars(gamma, lmbda, dtype)
+    adv, tgt = ops.backend().gae(v, nv, r, d, tm, g, gl, rows, T, F)
+    adv, tgt = adv.view(shape), tgt.view(shape)
+    if squeeze:
+        return adv.squeeze(-1), tgt.squeeze(-1)
+    if td != -2:
+        adv, tgt = adv.transpose(td, -2), tgt.transpose(td, -2)
+    return adv, tgt
+
+
+def vec_generalized_advantage_estimate(gamma, lmbda, state_value: torch.Tensor, next_state_value: torch.Tensor,
+                                       reward: torch.Tensor, done: torch.Tensor,
+                                       terminated: torch.Tensor | None = None, *, time_dim: int = -2):
+    """Vectorized Generalized advantage estimate of a trajectory (https://arxiv.org/pdf/1506.02438.pdf).
+
+    Args:
+        gamma (scalar): exponential mean discount.
+        lmbda (scalar): trajectory discount.
+        state_value (Tensor): value function result with old_state input.
+        next_state_value (Tensor): value function result with new_state input.
+        reward (Tensor): reward of taking actions in the environment.
+        done (Tensor): boolean flag for end of trajectory.
+        terminated (Tensor): boolean flag for the end of episode. Defaults to ``done`` if not provided.
+        time_dim (int): dimension where the time is unrolled. Defaults to -2.
+
+    All tensors (values, reward and done) must have shape ``[*Batch x TimeSteps x *F]``.
+    Returns ``(advantage, value_target)``.
+    """
+    return _gae_impl(gamma, lmbda, state_value, next_state_value, reward, done, terminated, time_dim)
+
+
+def generalized_advantage_estimate(gamma, lmbda, state_value: torch.Tensor, next_state_value: torch.Tensor,
+                                   reward: torch.Tensor, done: torch.Tensor, terminated: torch.Tensor | None = None,
+                                   *, time_dim: int = -2):
+    """Generalized advantage estimate of a trajectory -- same kernel as the vectorized entry point (the
+    reference's python time loop, functional.py:164-178, is what the kernel's recurrence restates)."""
+    return _gae_impl(gamma, lmbda, state_value, next_state_value, reward, done, terminated, time_dim)

@@ -1,0 +1,307 @@
+"""Torch-tensor level entry to the C ABI of librlb200.so (include/rlb200.h).
+
+Everything the host-side mirror of the TorchRL interface (rl_b200.data, rl_b200.objectives) computes
+on the hot path goes through the functions below, which hand raw device pointers and the current
+CUDA stream to the hand-written sm_100a kernels.  There is NO CPU implementation behind them: if the
+shared library is missing, or a tensor is not on a CUDA device, they raise.
+
+The only indirection is ``set_backend`` -- used by the CPU test-suite to plug in an oracle-backed
+emulator (tests/_emul.py) so that the *host logic* (cursors, lengths, key plumbing, error behaviour)
+can be exercised without a GPU.  The product never installs a backend other than ``CudaBackend``.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+from typing import Sequence
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+_SO = _PKG / "librlb200.so"
+
+RLB_F32, RLB_F64 = 0, 1
+GATHER_AUTO, GATHER_VECTOR, GATHER_BULK = 0, 1, 2
+MAX_LEAVES = 24
+STATUS_INDEX_OOB, STATUS_NONPOS_PSUM, STATUS_NONPOS_PMIN, STATUS_BACKOFF_FAIL = 1, 2, 4, 8
+
+_vp, _i64, _i32, _f64, _sz, _u32 = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
+                                    ctypes.c_size_t, ctypes.c_uint32)
+
+_SIGNATURES = {
+    "rlb_version": (ctypes.c_int, []),
+    "rlb_last_error": (ctypes.c_char_p, []),
+    "rlb_device_sm_count": (ctypes.c_int, []),
+    "rlb_tree_capacity": (_i64, [_i64]),
+    "rlb_tree_update_workspace_bytes": (_sz, [_i64]),
+    "rlb_tree_fill": (_i32, [_vp, _i64, _i32, _i32, _vp]),
+    "rlb_tree_rebuild": (_i32, [_vp, _i64, _i32, _i32, _vp]),
+    "rlb_tree_update": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _u32, _vp]),
+    "rlb_tree_query": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "rlb_tree_at": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),
+    "rlb_tree_scan_lower_bound": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
+    "rlb_per_sample": (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _vp, _i64, _f64, _i32, _vp, _vp, _vp, _vp,
+                               _vp, _vp]),
+    "rlb_per_update": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _f64, _f64, _vp, _vp, _vp, _sz, _u32, _vp]),
+    "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
+    "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
+}
+
+
+def exported_symbols() -> list[str]:
+    """Every symbol include/rlb200.h declares (checked against the built library in the CPU tests)."""
+    return sorted(_SIGNATURES)
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the in-tree librlb200.so and declare the prototypes.  Raises if it was never built."""
+    if not _SO.exists():
+        raise RuntimeError(
+            f"{_SO} is missing: the B200 CUDA extension was not built. Run `python -c 'import "
+            "__graft_entry__ as g; g.build()'` (needs nvcc). rl_b200 has no CPU fallback.")
+    L = ctypes.CDLL(str(_SO))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    return L
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return RLB_F32
+    if dt == torch.float64:
+        return RLB_F64
+    raise NotImplementedError(f"dtype {dt} not supported (fp32 / fp64 only)")
+
+
+class CudaBackend:
+    """ctypes binding of librlb200.so; every tensor must live on a CUDA device."""
+
+    name = "cuda"
+
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("rl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        self.L = load_library()
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self.L.rlb_last_error().decode(errors="replace")
+            raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+    @staticmethod
+    def _cuda(*tensors: torch.Tensor) -> torch.device:
+        dev = None
+        for t in tensors:
+            if t is None:
+                continue
+            if not t.is_cuda:
+                raise RuntimeError(
+                    f"rl_b200: expected a CUDA tensor, got device={t.device}; this engine has no CPU path.")
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise RuntimeError(f"rl_b200: tensors on different devices ({dev} vs {t.device})")
+        return dev
+
+    @staticmethod
+    def _stream(dev: torch.device) -> int:
+        return torch.cuda.current_stream(dev).cuda_stream
+
+    @staticmethod
+    def _p(t: torch.Tensor | None) -> int | None:
+        return None if t is None else t.data_ptr()
+
+    class _Guard:
+        """Make `dev` the current CUDA device for the launch if it is not already."""
+
+        def __init__(self, dev):
+            self.ctx = None
+            if dev.index is not None and dev.index != torch.cuda.current_device():
+                self.ctx = torch.cuda.device(dev)
+
+        def __enter__(self):
+            if self.ctx is not None:
+                self.ctx.__enter__()
+
+        def __exit__(self, *a):
+            if self.ctx is not None:
+                self.ctx.__exit__(*a)
+
+    # -- segment tree ------------------------------------------------------------------------------
+    def tree_capacity(self, size: int) -> int:
+        return int(self.L.rlb_tree_capacity(int(size)))
+
+    def tree_new(self, size: int, is_min: bool, dtype: torch.dtype, device) -> torch.Tensor:
+        cap = self.tree_capacity(size)
+        tree = torch.empty(2 * cap, dtype=dtype, device=device)
+        dev = self._cuda(tree)
+        with self._Guard(dev):
+            self._check(self.L.rlb_tree_fill(tree.data_ptr(), cap, int(is_min), _dtype_code(dtype),
+                                             self._stream(dev)), "rlb_tree_fill")
+        return tree
+
+    def tree_workspace(self, size: int, device) -> torch.Tensor:
+        nbytes = int(self.L.rlb_tree_update_workspace_bytes(int(size)))
+        return torch.zeros(nbytes // 8, dtype=torch.int64, device=device)
+
+    def tree_rebuild(self, tree: torch.Tensor, capacity: int, is_min: bool) -> None:
+        dev = self._cuda(tree)
+        with self._Guard(dev):
+            self._check(self.L.rlb_tree_rebuild(tree.data_ptr(), capacity, int(is_min), _dtype_code(tree.dtype),
+                                                self._stream(dev)), "rlb_tree_rebuild")
+
+    def tree_update(self, sum_tree, min_tree, capacity: int, index: torch.Tensor, value: torch.Tensor,
+                    workspace: torch.Tensor | None, epoch: int) -> None:
+        ref = sum_tree if sum_tree is not None else min_tree
+        dev = self._cuda(sum_tree, min_tree, index, value, workspace)
+        if value.dtype != ref.dtype:
+            raise RuntimeError("value dtype must match the tree dtype")  # cuda_segment_tree.cu:163-164
+        if index.dtype != torch.int64:
+            raise RuntimeError("index must be an int64 tensor")  # cuda_segment_tree.cu:161-162
+        n = index.numel()
+        scalar = int(value.numel() == 1)
+        if not scalar and value.numel() != n:
+            raise RuntimeError("value must have one element or as many elements as index")
+        index, value = index.contiguous(), value.contiguous()
+        with self._Guard(dev):
+            self._check(self.L.rlb_tree_update(
+                self._p(sum_tree), self._p(min_tree), capacity, index.data_ptr(), value.data_ptr(), n, scalar,
+                _dtype_code(ref.dtype), self._p(workspace), 0 if workspace is None else workspace.numel() * 8,
+                epoch & 0xFFFFFFFF, self._stream(dev)), "rlb_tree_update")
+
+    def tree_query(self, tree, size: int, capacity: int, is_min: bool, l: torch.Tensor, r: torch.Tensor,
+                   root_fast_path: bool) -> torch.Tensor:
+        dev = self._cuda(tree, l, r)
+        if l.dtype != torch.int64 or r.dtype != torch.int64:
+            raise RuntimeError("l and r must be int64 tensors")  # cuda_segment_tree.cu:176-178
+        lc, rc_ = l.contiguous(), r.contiguous()
+        out = torch.empty(lc.shape, dtype=tree.dtype, device=dev)
+        with self._Guard(dev):
+            self._check(self.L.rlb_tree_query(tree.data_ptr(), size, capacity, int(is_min), _dtype_code(tree.dtype),
+                                              lc.data_ptr(), rc_.data_ptr(), out.data_ptr(), lc.numel(),
+                                              int(root_fast_path), self._stream(dev)), "rlb_tree_query")
+        return out
+
+    def tree_at(self, tree, capacity: int, index: torch.Tensor) -> torch.Tensor:
+        dev = self._cuda(tree, index)
+        ic = index.contiguous()
+        out = torch.empty(ic.shape, dtype=tree.dtype, device=dev)
+        with self._Guard(dev):
+            self._check(self.L.rlb_tree_at(tree.data_ptr(), capacity, _dtype_code(tree.dtype), ic.data_ptr(),
+                                           out.data_ptr(), ic.numel(), self._stream(dev)), "rlb_tree_at")
+        return out
+
+    def tree_scan_lower_bound(self, tree, size: int, capacity: int, value: torch.Tensor) -> torch.Tensor:
+        dev = self._cuda(tree, value)
+        if value.dtype != tree.dtype:
+            raise RuntimeError("value dtype must match the tree dtype")  # cuda_segment_tree.cu:190-192
+        vc = value.contiguous()
+        out = torch.empty(vc.shape, dtype=torch.int64, device=dev)
+        with self._Guard(dev):
+            self._check(self.L.rlb_tree_scan_lower_bound(tree.data_ptr(), size, capacity, _dtype_code(tree.dtype),
+                                                         vc.data_ptr(), out.data_ptr(), vc.numel(),
+                                                         self._stream(dev)), "rlb_tree_scan_lower_bound")
+        return out
+
+    # -- fused sampler arithmetic ------------------------------------------------------------------
+    def per_sample(self, sum_tree, min_tree, size: int, capacity: int, length: int, u: torch.Tensor, beta: float,
+                   cpu_semantics: bool, status: torch.Tensor | None = None, want_aux: bool = False):
+        dev = self._cuda(sum_tree, min_tree, u, status)
+        B = u.numel()
+        u = u.contiguous()
+        index = torch.empty(B, dtype=torch.int64, device=dev)
+        weight = torch.empty(B, dtype=torch.float32, device=dev)
+        leaf = torch.empty(B, dtype=sum_tree.dtype, device=dev) if want_aux else None
+        pp = torch.empty(2, dtype=sum_tree.dtype, device=dev) if want_aux else None
+        with self._Guard(dev):
+            self._check(self.L.rlb_per_sample(
+                sum_tree.data_ptr(), min_tree.data_ptr(), size, capacity, _dtype_code(sum_tree.dtype), length,
+                u.data_ptr(), B, float(beta), int(cpu_semantics), index.data_ptr(), weight.data_ptr(),
+                self._p(leaf), self._p(pp), self._p(status), self._stream(dev)), "rlb_per_sample")
+        if want_aux:
+            return index, weight, leaf, pp
+        return index, weight
+
+    def per_update(self, sum_tree, min_tree, capacity: int, index: torch.Tensor, priority: torch.Tensor,
+                   alpha: float, eps: float, max_out: torch.Tensor | None, workspace, epoch: int) -> None:
+        dev = self._cuda(sum_tree, min_tree, index, priority, max_out, workspace)
+        if priority.dtype != torch.float32 or (sum_tree is not None and sum_tree.dtype != torch.float32):
+            raise NotImplementedError("fused per_update is fp32 only")
+        n = index.numel()
+        scalar = int(priority.numel() == 1)
+        index, priority = index.contiguous(), priority.contiguous()
+        scratch = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        with self._Guard(dev):
+            self._check(self.L.rlb_per_update(
+                self._p(sum_tree), self._p(min_tree), capacity, index.data_ptr(), priority.data_ptr(), n, scalar,
+                float(alpha), float(eps), scratch.data_ptr(), self._p(max_out), self._p(workspace),
+                0 if workspace is None else workspace.numel() * 8, epoch & 0xFFFFFFFF, self._stream(dev)),
+                "rlb_per_update")
+
+    # -- storage rows ------------------------------------------------------------------------------
+    def _rows(self, fn, who, big: Sequence[torch.Tensor], small: Sequence[torch.Tensor], index: torch.Tensor,
+              length: int, status, extra):
+        """big[k] is the [N, ...] storage leaf, small[k] the [B, ...] batch leaf."""
+        dev = self._cuda(index, status, *big, *small)
+        if index.dtype != torch.int64:
+            raise RuntimeError("index must be an int64 tensor")
+        index = index.contiguous()
+        B = index.numel()
+        with self._Guard(dev):
+            for lo in range(0, len(big), MAX_LEAVES):
+                bs, ss = big[lo:lo + MAX_LEAVES], small[lo:lo + MAX_LEAVES]
+                n = len(bs)
+                P, I = ctypes.c_void_p * n, ctypes.c_int64 * n
+                rowb = [s.element_size() * (s.numel() // max(B, 1)) for s in ss]
+                stride = [b.stride(0) * b.element_size() for b in bs]
+                bigp, smallp = P(*[b.data_ptr() for b in bs]), P(*[s.data_ptr() for s in ss])
+                src, dst = (bigp, smallp) if who == "rlb_gather" else (smallp, bigp)
+                self._check(fn(src, dst, I(*rowb), I(*stride), n, index.data_ptr(), B, length, *extra,
+                               self._p(status), self._stream(dev)), who)
+
+    def gather(self, leaves: Sequence[torch.Tensor], index: torch.Tensor, length: int, mode: int = GATHER_AUTO,
+               status: torch.Tensor | None = None) -> list[torch.Tensor]:
+        B = index.numel()
+        for t in leaves:
+            if t.ndim < 1 or (t.ndim > 1 and not t[0].is_contiguous()):
+                raise RuntimeError("storage leaves must be [N, ...] with contiguous rows")
+        outs = [torch.empty((B, *t.shape[1:]), dtype=t.dtype, device=t.device) for t in leaves]
+        if B:
+            self._rows(self.L.rlb_gather, "rlb_gather", leaves, outs, index, length, status, (mode,))
+        return outs
+
+    def scatter(self, leaves: Sequence[torch.Tensor], data: Sequence[torch.Tensor], index: torch.Tensor, length: int,
+                status: torch.Tensor | None = None) -> None:
+        if index.numel():
+            self._rows(self.L.rlb_scatter, "rlb_scatter", leaves, [d.contiguous() for d in data], index, length,
+                       status, ())
+
+    # -- GAE ---------------------------------------------------------------------------------------
+    def gae(self, v, nv, r, done, term, gamma: float, gammalmbda: float, rows: int, T: int, F: int):
+        dev = self._cuda(v, nv, r, done, term)
+        adv, tgt = torch.empty_like(v), torch.empty_like(v)
+        with self._Guard(dev):
+            self._check(self.L.rlb_gae(v.data_ptr(), nv.data_ptr(), r.data_ptr(), done.data_ptr(), term.data_ptr(),
+                                       float(gamma), float(gammalmbda), rows, T, F, _dtype_code(v.dtype),
+                                       adv.data_ptr(), tgt.data_ptr(), self._stream(dev)), "rlb_gae")
+        return adv, tgt
+
+
+_BACKEND = None
+
+
+def backend():
+    """The active backend; created on first use.  Fails loudly without the CUDA extension / a GPU."""
+    global _BACKEND
+    if _BACKEND is None:
+        _BACKEND = CudaBackend()
+    return _BACKEND
+
+
+def set_backend(b) -> None:
+    """TESTS ONLY: install an emulator backend (or None to restore the CUDA one)."""
+    global _BACKEND
+    _BACKEND = b

@@ -1,0 +1,187 @@
+"""TESTS ONLY -- an oracle-backed stand-in for ``rl_b200.ops.CudaBackend``.
+
+Lets the CPU test-suite drive the *host logic* of rl_b200 (cursors, lengths, key plumbing, bookkeeping,
+error behaviour, multi-process sharding) on CPU tensors.  Every method does what the corresponding C-ABI
+entry point is specified to do (include/rlb200.h), computed with the CPU oracle (oracle/) and plain torch
+indexing.  It is never installed by product code and never used on the GPU box: the ``-m gpu`` tests call
+the real library.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import lib as orc_lib
+from oracle import per_oracle as po
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().contiguous().numpy()
+
+
+class OracleBackend:
+    name = "oracle-emulator"
+
+    # ---- segment tree: the heap tensor is kept bit-identical to what the kernels must produce
+    def tree_capacity(self, size: int) -> int:
+        return _capacity(size)
+
+    def tree_new(self, size, is_min, dtype, device):
+        cap = _capacity(size)
+        ident = torch.finfo(dtype).max if is_min else 0.0
+        return torch.full((2 * cap,), ident, dtype=dtype, device="cpu")
+
+    def tree_workspace(self, size, device):
+        return torch.zeros(_capacity(size), dtype=torch.int64)
+
+    def tree_rebuild(self, tree, capacity, is_min):
+        for i in range(capacity - 1, 0, -1):
+            a, b = tree[2 * i], tree[2 * i + 1]
+            tree[i] = torch.minimum(a, b) if is_min else a + b
+
+    def _update_one(self, tree, capacity, is_min, index, value):
+        if tree is None:
+            return
+        idx = index.tolist()
+        vals = value.tolist() if value.numel() > 1 else [value.item()] * len(idx)
+        for i, v in zip(idx, vals):
+            if i < 0:
+                continue
+            node = i + capacity
+            tree[node] = v
+            while node > 1:
+                p = node >> 1
+                a, b = tree[2 * p], tree[2 * p + 1]
+                tree[p] = torch.minimum(a, b) if is_min else a + b
+                node = p
+
+    def tree_update(self, sum_tree, min_tree, capacity, index, value, workspace, epoch):
+        ref = sum_tree if sum_tree is not None else min_tree
+        if value.dtype != ref.dtype:
+            raise RuntimeError("value dtype must match the tree dtype")
+        if index.dtype != torch.int64:
+            raise RuntimeError("index must be an int64 tensor")
+        self._update_one(sum_tree, capacity, False, index.reshape(-1), value.reshape(-1))
+        self._update_one(min_tree, capacity, True, index.reshape(-1), value.reshape(-1))
+
+    def _query1(self, tree, size, capacity, is_min, l, r, root_fast_path):
+        if root_fast_path and l <= 0 and r >= size:
+            return tree[1].clone()
+        ret = torch.tensor(torch.finfo(tree.dtype).max if is_min else 0.0, dtype=tree.dtype)
+        l |= capacity
+        r |= capacity
+        while l < r:
+            if l & 1:
+                ret = torch.minimum(ret, tree[l]) if is_min else ret + tree[l]
+                l += 1
+            if r & 1:
+                r -= 1
+                ret = torch.minimum(ret, tree[r]) if is_min else ret + tree[r]
+            l >>= 1
+            r >>= 1
+        return ret
+
+    def tree_query(self, tree, size, capacity, is_min, l, r, root_fast_path):
+        out = [self._query1(tree, size, capacity, is_min, int(a), int(b), root_fast_path)
+               for a, b in zip(l.reshape(-1).tolist(), r.reshape(-1).tolist())]
+        return torch.stack(out).reshape(l.shape) if out else torch.empty(l.shape, dtype=tree.dtype)
+
+    def tree_at(self, tree, capacity, index):
+        return tree[index + capacity]
+
+    def _scan1(self, tree, size, capacity, value):
+        if value > tree[1]:
+            return size
+        node, cur = 1, value.clone()
+        while node < capacity:
+            node <<= 1
+            if cur > tree[node]:
+                cur = cur - tree[node]
+                node |= 1
+        return node ^ capacity
+
+    def tree_scan_lower_bound(self, tree, size, capacity, value):
+        if value.dtype != tree.dtype:
+            raise RuntimeError("value dtype must match the tree dtype")
+        out = [self._scan1(tree, size, capacity, v) for v in value.reshape(-1)]
+        return torch.tensor(out, dtype=torch.int64).reshape(value.shape)
+
+    # ---- fused sampler arithmetic (restates include/rlb200.h rlb_per_sample / rlb_per_update)
+    def per_sample(self, sum_tree, min_tree, size, capacity, length, u, beta, cpu_semantics, status=None,
+                   want_aux=False):
+        p_sum = self._query1(sum_tree, size, capacity, False, 0, length, bool(cpu_semantics))
+        p_min = self._query1(min_tree, size, capacity, True, 0, length, bool(cpu_semantics))
+        if status is not None:
+            if not p_sum > 0:
+                status |= 2
+            if not p_min > 0:
+                status |= 4
+        mass = u * p_sum
+        index = self.tree_scan_lower_bound(sum_tree, size, capacity, mass)
+        index = index.clamp_max(length - 1)
+        leaf = sum_tree[index + capacity]
+        if cpu_semantics:
+            zero = leaf == 0
+            while zero.any():
+                index = torch.where(zero, index - 1, index)
+                if (index < 0).any():
+                    if status is not None:
+                        status |= 8
+                    index = index.clamp_min(0)
+                    break
+                leaf = sum_tree[index + capacity]
+                zero = leaf == 0
+        weight = torch.pow(leaf / p_min, -beta).to(torch.float32)
+        if want_aux:
+            return index, weight, leaf, torch.stack([p_sum, p_min])
+        return index, weight
+
+    def per_update(self, sum_tree, min_tree, capacity, index, priority, alpha, eps, max_out, workspace, epoch):
+        index = index.reshape(-1)
+        priority = priority.reshape(-1).to(torch.float32)
+        valid = index >= 0
+        if max_out is not None and valid.any():
+            pv = priority.expand_as(index)[valid] if priority.numel() == 1 else priority[valid]
+            max_out.copy_(torch.maximum(max_out, pv.max().view(1)))
+        leaf = torch.pow(priority + eps, alpha)
+        self.tree_update(sum_tree, min_tree, capacity, index, leaf, workspace, epoch)
+
+    # ---- storage rows
+    def gather(self, leaves, index, length, mode=0, status=None):
+        ix = torch.where(index < 0, index + length, index)
+        if ((ix < 0) | (ix >= length)).any():
+            if status is not None:
+                status |= 1
+            ix = ix.clamp(0, length - 1)
+        return [t[ix] for t in leaves]
+
+    def scatter(self, leaves, data, index, length, status=None):
+        ix = torch.where(index < 0, index + length, index)
+        for t, d in zip(leaves, data):
+            t[ix] = d
+
+    # ---- GAE
+    def gae(self, v, nv, r, done, term, gamma, gammalmbda, rows, T, F):
+        L = orc_lib()
+        shape = v.shape
+        if v.dtype == torch.float32:
+            adv = np.empty((rows, T, F), dtype=np.float32)
+            tgt = np.empty_like(adv)
+            a = [np.ascontiguousarray(_np(x)) for x in (v, nv, r, done, term)]
+            L.orc_gae_f32(*[x.ctypes.data for x in a], gamma, gammalmbda, rows, T, F, adv.ctypes.data,
+                          tgt.ctypes.data)
+        else:
+            adv = np.empty((rows, T, F), dtype=np.float64)
+            tgt = np.empty_like(adv)
+            a = [np.ascontiguousarray(_np(x).astype(np.float32)) for x in (v, nv, r)] + \
+                [np.ascontiguousarray(_np(x)) for x in (done, term)]
+            L.orc_gae_f64(*[x.ctypes.data for x in a], gamma, gammalmbda, rows, T, F, adv.ctypes.data,
+                          tgt.ctypes.data)
+        return torch.from_numpy(adv).reshape(shape), torch.from_numpy(tgt).reshape(shape)
+
+
+def _capacity(size: int) -> int:
+    c = 1
+    while c <= size:
+        c <<= 1
+    return c

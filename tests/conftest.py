@@ -52,3 +52,29 @@ def ref_funcs():
     if F is None:
         pytest.skip("/root/reference not present (GPU box)")
     return F
+
+
+@pytest.fixture()
+def emul():
+    """Install the oracle-backed emulator as rl_b200's backend for one CPU host-logic test."""
+    from rl_b200 import ops
+
+    from _emul import OracleBackend
+
+    ops.set_backend(OracleBackend())
+    try:
+        yield
+    finally:
+        ops.set_backend(None)
+
+
+@pytest.fixture(scope="session")
+def cuda_backend():
+    """The real library on a real GPU (-m gpu tests)."""
+    import torch
+
+    from rl_b200 import ops
+
+    assert torch.cuda.is_available()
+    ops.set_backend(None)
+    return ops.backend()

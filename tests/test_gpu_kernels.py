@@ -1,0 +1,392 @@
+"""Parity of the hand-written sm_100a kernels (through the C ABI) against the CPU oracle.
+
+Bars: bit-exact for tree contents, sampled indices and gathered bytes; GAE within rtol=atol=1e-5 of the
+float64 evaluation of the recurrence (and exactly the reference's own tolerance 1e-4 against the golden
+vectors produced by the reference's two fp32 code paths).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import per_oracle as po
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+# ---------------------------------------------------------------------------------------------------- trees
+def _heap_equal(dev_tree, orc_tree):
+    got = dev_tree.values.cpu().numpy()
+    want = orc_tree.values()
+    np.testing.assert_array_equal(got[1:], want[1:])
+
+
+@pytest.mark.parametrize("size", [1, 2, 7, 16, 100, 1000, 1024, 4097, 100_000])
+def test_tree_update_matches_oracle_bitwise(cuda_backend, size):
+    from rl_b200.data.segment_tree import MinSegmentTreeFp32, SumSegmentTreeFp32
+
+    rng = np.random.default_rng(size)
+    ds, dm = SumSegmentTreeFp32(size, dev()), MinSegmentTreeFp32(size, dev())
+    os_, om = po.OracleTree(size, False), po.OracleTree(size, True)
+    assert ds.capacity == os_.capacity
+    _heap_equal(ds, os_)
+    _heap_equal(dm, om)
+    for n in [1, 3, 33, 256, 1000, 1024, 1025, 5000]:
+        idx = rng.integers(0, size, n).astype(np.int64)  # duplicates: last writer must win
+        val = (rng.random(n, dtype=np.float32) * 3 + 1e-3).astype(np.float32)
+        for t in (os_, om):
+            t[idx] = val
+        ti, tv = torch.from_numpy(idx).to(dev()), torch.from_numpy(val).to(dev())
+        ds[ti] = tv
+        dm[ti] = tv
+        _heap_equal(ds, os_)
+        _heap_equal(dm, om)
+    # scalar value overload + negative ("skip") indices
+    idx = rng.integers(0, size, 17).astype(np.int64)
+    os_[idx] = 0.25
+    ds[torch.from_numpy(idx).to(dev())] = torch.tensor(0.25, device=dev())
+    _heap_equal(ds, os_)
+
+
+def test_tree_kat_and_queries(cuda_backend):
+    # test/rb/test_prioritized.py:113-140
+    from rl_b200.data.segment_tree import MinSegmentTreeFp32, SumSegmentTreeFp32
+
+    s, m = SumSegmentTreeFp32(16, dev()), MinSegmentTreeFp32(16, dev())
+    idx = torch.tensor([0, 3, 4, 7, 12, 15], device=dev())
+    val = torch.tensor([1, 2, 4, 8, 16, 32], dtype=torch.float32, device=dev())
+    s[idx] = val
+    m[idx] = val
+    assert s.capacity == 32
+    l = torch.tensor([0, 3, 4, 7], device=dev())
+    r = torch.tensor([16, 8, 13, 16], device=dev())
+    assert s.query(l, r).tolist() == [63, 14, 28, 56]
+    assert m.query(l, r).tolist() == [1, 2, 4, 8]
+    assert s.query(l, r, root_fast_path=False).tolist() == [63, 14, 28, 56]
+    assert s.scan_lower_bound(torch.tensor([0.5, 1.0, 2.9, 7.1, 30.0], device=dev())).tolist() == [0, 0, 3, 7, 12]
+    assert s.scan_lower_bound(64.0) == 16
+    assert s.query(0, 16) == 63.0 and s[3] == 2.0
+    np.testing.assert_array_equal(s[np.array([0, 3, 15])], [1, 2, 32])
+
+
+@pytest.mark.parametrize("size", [5, 1000, 70_000, 1_000_000])
+def test_scan_query_at_match_oracle(cuda_backend, size):
+    from rl_b200.data.segment_tree import MinSegmentTreeFp32, SumSegmentTreeFp32
+
+    rng = np.random.default_rng(size + 1)
+    leaves = (rng.random(size, dtype=np.float32) ** 3 + 1e-6).astype(np.float32)
+    leaves[rng.integers(0, size, max(size // 50, 1))] = 0.0  # some empty slots
+    ds, dm = SumSegmentTreeFp32(size, dev()), MinSegmentTreeFp32(size, dev())
+    os_, om = po.OracleTree(size, False), po.OracleTree(size, True)
+    for t in (os_, om):
+        t.load_leaves(leaves)
+    ds.load_leaves(torch.from_numpy(leaves))
+    dm.load_leaves(torch.from_numpy(leaves))
+    _heap_equal(ds, os_)
+    _heap_equal(dm, om)
+    root = np.float32(os_.query(0, size))
+    mass = (rng.random(20_000, dtype=np.float32) * root * np.float32(1.02)).astype(np.float32)
+    got = ds.scan_lower_bound(torch.from_numpy(mass).to(dev())).cpu().numpy()
+    np.testing.assert_array_equal(got, os_.scan_lower_bound(mass))
+    l = rng.integers(0, size, 300).astype(np.int64)
+    r = np.minimum(l + rng.integers(1, size + 1, 300), size).astype(np.int64)
+    tl, tr = torch.from_numpy(l).to(dev()), torch.from_numpy(r).to(dev())
+    np.testing.assert_array_equal(ds.query(tl, tr).cpu().numpy(), os_.query(l, r))
+    np.testing.assert_array_equal(dm.query(tl, tr).cpu().numpy(), om.query(l, r))
+    np.testing.assert_array_equal(ds.query(tl, tr, root_fast_path=False).cpu().numpy(), os_.query(l, r, walk=True))
+    probe = rng.integers(0, size, 100).astype(np.int64)
+    np.testing.assert_array_equal(ds[torch.from_numpy(probe).to(dev())].cpu().numpy(), os_[probe])
+
+
+def test_tree_fp64(cuda_backend):
+    from rl_b200.data.segment_tree import SumSegmentTreeFp64
+
+    size = 3000
+    rng = np.random.default_rng(0)
+    t = SumSegmentTreeFp64(size, dev())
+    leaves = rng.random(size)
+    t[torch.arange(size, device=dev())] = torch.from_numpy(leaves).to(dev())
+    heap = t.values.cpu().numpy()
+    cap = t.capacity
+    want = np.zeros(2 * cap)
+    want[cap:cap + size] = leaves
+    for i in range(cap - 1, 0, -1):
+        want[i] = want[2 * i] + want[2 * i + 1]
+    np.testing.assert_array_equal(heap[1:], want[1:])
+    mass = rng.random(500) * want[1]
+    got = t.scan_lower_bound(torch.from_numpy(mass).to(dev())).cpu().numpy()
+    ref = []
+    for v in mass:
+        node, cur = 1, v
+        while node < cap:
+            node <<= 1
+            if cur > want[node]:
+                cur -= want[node]
+                node |= 1
+        ref.append(node ^ cap)
+    np.testing.assert_array_equal(got, ref)
+
+
+# ---------------------------------------------------------------------------------------------------- PER sample
+def test_per_sample_golden(cuda_backend):
+    """Committed golden vectors from the compiled reference trees (tests/golden/make_golden.py)."""
+    from rl_b200.data.samplers import PrioritizedSampler
+    from rl_b200.data.storages import Storage
+
+    z = np.load(GOLD / "per_golden.npz")
+    for k in sorted({n.split("/")[0] for n in z.files}):
+        N, filled, B = (int(x) for x in z[f"{k}/meta"])
+        alpha, beta = (float(x) for x in z[f"{k}/ab"])
+        smp = PrioritizedSampler(N, alpha, beta, device=dev())
+        # replay the same writes: default priorities for [0, filled) then the explicit update (with duplicates)
+        smp.mark_update(torch.arange(filled, device=dev()))
+        smp.update_priority(torch.from_numpy(z[f"{k}/upd_index"]).to(dev()),
+                            torch.from_numpy(z[f"{k}/upd_priority"]).to(dev()))
+        got_leaves = smp._sum_tree.dump_leaves().cpu().numpy()
+        # leaves come from powf on the device vs SLEEF pow in the reference: allow 1-ulp, then force identical
+        # leaves so that the index comparison is exact
+        np.testing.assert_allclose(got_leaves, z[f"{k}/leaves"], rtol=3e-7, atol=0)
+        smp._sum_tree.load_leaves(torch.from_numpy(z[f"{k}/leaves"]))
+        min_leaves = z[f"{k}/leaves"].copy()
+        min_leaves[filled:] = np.finfo(np.float32).max
+        smp._min_tree.load_leaves(torch.from_numpy(min_leaves))
+        u = torch.from_numpy(z[f"{k}/u"]).to(dev())
+        idx, w, leaf, pp = cuda_backend.per_sample(smp._sum_tree.values, smp._min_tree.values, N,
+                                                   smp._sum_tree.capacity, filled, u, beta, True, want_aux=True)
+        assert pp[0].item() == z[f"{k}/p_sum"] and pp[1].item() == z[f"{k}/p_min"], k
+        np.testing.assert_array_equal(idx.cpu().numpy(), z[f"{k}/index"])       # index-exact
+        np.testing.assert_allclose(w.cpu().numpy(), z[f"{k}/weight"], rtol=2e-6)  # powf vs SLEEF
+
+
+@pytest.mark.parametrize("size,filled,B", [(16, 16, 64), (1000, 313, 256), (1_000_000, 1_000_000, 256),
+                                           (1_000_000, 400_000, 4096), (3_000_000, 3_000_000, 65536)])
+@pytest.mark.parametrize("cpu_sem", [True, False])
+def test_per_sample_matches_oracle(cuda_backend, size, filled, B, cpu_sem):
+    from rl_b200.data.segment_tree import MinSegmentTreeFp32, SumSegmentTreeFp32
+
+    rng = np.random.default_rng(size + B)
+    leaves = np.zeros(size, dtype=np.float32)
+    leaves[:filled] = ((rng.random(filled, dtype=np.float32) + 1e-8) ** np.float32(0.6)).astype(np.float32)
+    if filled > 100:
+        leaves[rng.integers(0, filled, filled // 100)] = 0.0
+    leaves[0] = 0.5  # u == 0 lands on leaf 0; keep it positive so the CPU back-off loop cannot underflow
+    ds, dm = SumSegmentTreeFp32(size, dev()), MinSegmentTreeFp32(size, dev())
+    os_, om = po.OracleTree(size, False), po.OracleTree(size, True)
+    min_leaves = np.where(np.arange(size) < filled, np.maximum(leaves, np.float32(1e-6)), np.finfo(np.float32).max)
+    min_leaves = min_leaves.astype(np.float32)
+    os_.load_leaves(leaves)
+    om.load_leaves(min_leaves)
+    ds.load_leaves(torch.from_numpy(leaves))
+    dm.load_leaves(torch.from_numpy(min_leaves))
+    u = rng.random(B, dtype=np.float32)
+    u[:3] = [0.0, np.float32(1.0) - np.float32(2 ** -24), 0.5]
+    want_idx, want_w, p_sum, p_min = po.per_sample_c(os_, om, filled, u, 0.4, cpu_checks=cpu_sem,
+                                                     walk_query=not cpu_sem)
+    idx, w, leaf, pp = cuda_backend.per_sample(ds.values, dm.values, size, ds.capacity, filled,
+                                               torch.from_numpy(u).to(dev()), 0.4, cpu_sem, want_aux=True)
+    assert pp[0].item() == p_sum and pp[1].item() == p_min
+    np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
+    np.testing.assert_allclose(w.cpu().numpy(), want_w, rtol=2e-6)
+    # the weight is torch's own CUDA pow on the same operands, bit for bit
+    tw = torch.pow(leaf / pp[1], -0.4)
+    assert torch.equal(tw, w)
+
+
+def test_fused_pow_is_torch_pow(cuda_backend):
+    """(p + eps) ** alpha inside rlb_per_update == torch.pow on the device, bitwise, incl. the special exponents."""
+    from rl_b200.data.samplers import PrioritizedSampler
+
+    N = 50_000
+    g = torch.Generator(device=dev()).manual_seed(0)
+    p = torch.rand(N, device=dev(), generator=g) * 5
+    for alpha in (0.6, 0.7, 0.5, 1.0, 2.0, 0.0, 3.0):
+        smp = PrioritizedSampler(N, alpha, 0.4, device=dev())
+        smp.update_priority(torch.arange(N, device=dev()), p)
+        want = torch.pow(p + 1e-8, alpha)
+        assert torch.equal(smp._sum_tree.dump_leaves(), want), alpha
+        assert smp._max_priority[0].item() == p.max().item()
+
+
+# ---------------------------------------------------------------------------------------------------- gather / scatter
+SHAPES = [((4, 84, 84), torch.uint8), ((), torch.float32), ((1,), torch.int64), ((), torch.bool),
+          ((17,), torch.float32), ((376,), torch.float32), ((3, 5), torch.float16), ((7,), torch.uint8),
+          ((33,), torch.int16), ((2, 3), torch.float64)]
+
+
+def _rand_leaf(n, shape, dtype, g):
+    if dtype in (torch.uint8, torch.int16, torch.int64):
+        return torch.randint(0, 100, (n, *shape), device=dev(), generator=g).to(dtype)
+    if dtype == torch.bool:
+        return torch.rand((n, *shape), device=dev(), generator=g) < 0.5
+    return torch.randn((n, *shape), device=dev(), generator=g).to(dtype)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("N,B", [(50, 1), (300, 7), (5000, 256), (5000, 1024), (20000, 4099)])
+def test_gather_matches_torch_indexing(cuda_backend, mode, N, B):
+    g = torch.Generator(device=dev()).manual_seed(N + B)
+    leaves = [_rand_leaf(N, s, d, g) for s, d in SHAPES]
+    length = N - N // 7
+    idx = torch.randint(-length, length, (B,), device=dev(), generator=g)
+    status = torch.zeros(1, dtype=torch.int32, device=dev())
+    out = cuda_backend.gather(leaves, idx, length, mode=mode, status=status)
+    for leaf, o in zip(leaves, out):
+        assert o.dtype == leaf.dtype and torch.equal(o, leaf[:length][idx])
+    assert status.item() == 0
+    # byte-level C restatement on one leaf
+    np.testing.assert_array_equal(out[0].cpu().numpy(),
+                                  po.gather_rows(leaves[0].cpu().numpy(), idx.cpu().numpy(), length))
+
+
+def test_gather_oob_is_reported(cuda_backend):
+    src = [torch.arange(100, device=dev(), dtype=torch.float32).reshape(50, 2)]
+    status = torch.zeros(1, dtype=torch.int32, device=dev())
+    cuda_backend.gather(src, torch.tensor([0, 49, 50], device=dev()), 50, status=status)
+    assert status.item() & 1
+
+
+def test_gather_strided_rows(cuda_backend):
+    # storage leaf that is a column-slice view: rows are contiguous but the row stride is larger
+    base = torch.randn(1000, 64, device=dev())
+    view = base[:, :32]
+    idx = torch.randint(0, 1000, (300,), device=dev())
+    (o,) = cuda_backend.gather([view], idx, 1000)
+    assert torch.equal(o, view[idx])
+
+
+@pytest.mark.parametrize("B", [256, 4096])
+def test_gather_atari_full_rows(cuda_backend, B):
+    """C2-shaped: the bulk-DMA role on 28 224-byte rows, pixels + next pixels + small leaves in one launch."""
+    N = 20_000
+    g = torch.Generator(device=dev()).manual_seed(B)
+    pix = torch.randint(0, 255, (N, 4, 84, 84), device=dev(), generator=g, dtype=torch.uint8)
+    nxt = torch.randint(0, 255, (N, 4, 84, 84), device=dev(), generator=g, dtype=torch.uint8)
+    act = torch.randint(0, 18, (N, 1), device=dev(), generator=g)
+    rew = torch.randn(N, device=dev(), generator=g)
+    done = torch.rand(N, 1, device=dev(), generator=g) < 0.1
+    leaves = [pix, nxt, act, rew, done]
+    idx = torch.randint(0, N, (B,), device=dev(), generator=g)
+    for mode in (0, 1, 2):
+        out = cuda_backend.gather(leaves, idx, N, mode=mode)
+        for leaf, o in zip(leaves, out):
+            assert torch.equal(o, leaf[idx]), mode
+
+
+def test_scatter_matches_index_put(cuda_backend):
+    g = torch.Generator(device=dev()).manual_seed(3)
+    N, B = 4000, 777
+    leaves = [_rand_leaf(N, s, d, g) for s, d in SHAPES]
+    want = [l.clone() for l in leaves]
+    data = [_rand_leaf(B, s, d, g) for s, d in SHAPES]
+    idx = torch.randperm(N, device=dev(), generator=g)[:B]
+    cuda_backend.scatter(leaves, data, idx, N)
+    for w, d, l in zip(want, data, leaves):
+        w[idx] = d
+        assert torch.equal(w, l)
+
+
+# ---------------------------------------------------------------------------------------------------- GAE
+def _gae_inputs(shape, seed, p=0.05, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    v, nv, r = (torch.randn(*shape, generator=g, dtype=dtype) for _ in range(3))
+    term = torch.rand(*shape, generator=g) < p
+    done = term | (torch.rand(*shape, generator=g) < p)
+    return v, nv, r, done, term
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 5, 1), (3, 200, 1), (7, 3, 3, 1), (64, 128, 1), (9, 131, 1),
+                                   (2, 1000, 1), (4096, 128, 1), (5, 33, 3), (16, 64, 40), (300, 500, 1)])
+@pytest.mark.parametrize("gamma,lmbda", [(0.99, 0.95), (0.5, 0.1)])
+def test_gae_matches_f64_oracle(cuda_backend, shape, gamma, lmbda):
+    from rl_b200.objectives.value import generalized_advantage_estimate, vec_generalized_advantage_estimate
+
+    v, nv, r, done, term = _gae_inputs(shape, sum(shape))
+    g, l = torch.tensor(gamma), torch.tensor(lmbda)
+    fa, ft = po.gae_f64(g, l, v, nv, r, done, term)
+    cu = [x.to(dev()) for x in (v, nv, r, done, term)]
+    a, t = vec_generalized_advantage_estimate(g, l, *cu[:3], done=cu[3], terminated=cu[4])
+    torch.testing.assert_close(a.cpu().double(), fa, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(t.cpu().double(), ft, rtol=1e-5, atol=1e-5)
+    # and against the reference's own fp32 loop semantics (C restatement, bit-exact to the reference)
+    la, lt = po.gae_f32(g, l, v, nv, r, done, term)
+    torch.testing.assert_close(a.cpu(), la, rtol=1e-5, atol=1e-5)
+    a2, t2 = generalized_advantage_estimate(g, l, *cu[:3], done=cu[3], terminated=cu[4])
+    assert torch.equal(a, a2) and torch.equal(t, t2)
+
+
+def test_gae_golden(cuda_backend):
+    from rl_b200.objectives.value import vec_generalized_advantage_estimate
+
+    z = np.load(GOLD / "gae_golden.npz")
+    for k in sorted({n.split("/")[0] for n in z.files}):
+        gt = lambda n: torch.from_numpy(z[f"{k}/{n}"])
+        cu = [gt(n).to(dev()) for n in ("v", "nv", "r", "done", "term")]
+        a, t = vec_generalized_advantage_estimate(gt("gamma"), gt("lmbda"), *cu[:3], done=cu[3], terminated=cu[4])
+        torch.testing.assert_close(a.cpu(), gt("loop_adv"), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(t.cpu(), gt("loop_tgt"), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(a.cpu(), gt("vec_adv"), rtol=1e-4, atol=1e-4)   # the reference's own bar
+        torch.testing.assert_close(t.cpu(), gt("vec_tgt"), rtol=1e-4, atol=1e-4)
+
+
+def test_gae_unaligned_and_time_dim(cuda_backend):
+    from rl_b200.objectives.value import vec_generalized_advantage_estimate
+
+    # a view that is NOT 16-B aligned and whose T is not a multiple of 4 -> scalar path
+    v, nv, r, done, term = _gae_inputs((6, 51, 1), 5)
+    g, l = 0.97, 0.9
+    fa, ft = po.gae_f64(g, l, v, nv, r, done, term)
+    pad = lambda x: torch.cat([x.flatten()[:1], x.flatten()]).to(dev())[1:].view(x.shape)
+    a, t = vec_generalized_advantage_estimate(g, l, pad(v), pad(nv), pad(r), done=pad(done), terminated=pad(term))
+    torch.testing.assert_close(a.cpu().double(), fa, rtol=1e-5, atol=1e-5)
+    # time_dim = -1 on [B, T] inputs and time_dim=0 on [T, B, 1]
+    v2, nv2, r2, d2, t2 = (x.squeeze(-1).to(dev()) for x in (v, nv, r, done, term))
+    a2, tt2 = vec_generalized_advantage_estimate(g, l, v2, nv2, r2, done=d2, terminated=t2, time_dim=-1)
+    assert a2.shape == v2.shape
+    torch.testing.assert_close(a2.cpu().double(), fa.squeeze(-1), rtol=1e-5, atol=1e-5)
+    v3, nv3, r3, d3, t3 = (x.transpose(0, 1).contiguous().to(dev()) for x in (v, nv, r, done, term))
+    a3, _ = vec_generalized_advantage_estimate(g, l, v3, nv3, r3, done=d3, terminated=t3, time_dim=0)
+    torch.testing.assert_close(a3.cpu().double(), fa.transpose(0, 1), rtol=1e-5, atol=1e-5)
+
+
+def test_gae_fp64(cuda_backend):
+    from rl_b200.objectives.value import vec_generalized_advantage_estimate
+
+    v, nv, r, done, term = _gae_inputs((33, 77, 1), 11, dtype=torch.float64)
+    g, l = 0.99, 0.95
+    cu = [x.to(dev()) for x in (v, nv, r, done, term)]
+    a, t = vec_generalized_advantage_estimate(g, l, *cu[:3], done=cu[3], terminated=cu[4])
+    # float64 python loop
+    adv = torch.zeros_like(v)
+    prev = torch.zeros(33, 1, dtype=torch.float64)
+    for s in range(76, -1, -1):
+        delta = r[:, s] + g * (~term[:, s]) * nv[:, s] - v[:, s]
+        prev = delta + g * l * (~done[:, s]) * prev
+        adv[:, s] = prev
+    torch.testing.assert_close(a.cpu(), adv, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(t.cpu(), adv + v, rtol=1e-12, atol=1e-12)
+
+
+def test_successive_traj_gae(cuda_backend):
+    """test/objectives/test_values.py:1775-1857: a rollout with a mid-trajectory `terminated` equals the
+    concatenation of the two halves computed separately."""
+    from rl_b200.objectives.value import vec_generalized_advantage_estimate
+
+    T, cut = 200, 77
+    g = torch.Generator().manual_seed(0)
+    v, nv, r = (torch.randn(1, T, 1, generator=g).to(dev()) for _ in range(3))
+    done = torch.zeros(1, T, 1, dtype=torch.bool, device=dev())
+    done[0, cut - 1] = True
+    done[0, -1] = True
+    a, t = vec_generalized_advantage_estimate(0.99, 0.95, v, nv, r, done=done, terminated=done.clone())
+    a1, t1 = vec_generalized_advantage_estimate(0.99, 0.95, v[:, :cut], nv[:, :cut], r[:, :cut],
+                                                done=done[:, :cut], terminated=done[:, :cut])
+    a2, t2 = vec_generalized_advantage_estimate(0.99, 0.95, v[:, cut:], nv[:, cut:], r[:, cut:],
+                                                done=done[:, cut:], terminated=done[:, cut:])
+    torch.testing.assert_close(a, torch.cat([a1, a2], 1), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(t, torch.cat([t1, t2], 1), rtol=1e-6, atol=1e-6)
