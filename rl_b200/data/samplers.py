@@ -165,6 +165,8 @@ class PrioritizedSampler(Sampler):
         self._semantics = semantics
         self._sum_tree = None
         self._min_tree = None
+        self._has_max_priority = False
+        self._max_priority_index = None
         if self._device is not None:
             self._init()
 
@@ -392,6 +394,7 @@ class PrioritizedSampler(Sampler):
             self._max_priority_index = maxidx
 
     def mark_update(self, index, *, storage: Storage | None = None) -> None:
+        self._maybe_init_from_storage(storage)
         self.update_priority(index, self.default_priority, storage=storage)
 
     # ---- (de)serialisation -------------------------------------------------------------------------

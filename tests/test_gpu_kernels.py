@@ -365,8 +365,8 @@ def test_gae_fp64(cuda_backend):
     adv = torch.zeros_like(v)
     prev = torch.zeros(33, 1, dtype=torch.float64)
     for s in range(76, -1, -1):
-        delta = r[:, s] + g * (~term[:, s]) * nv[:, s] - v[:, s]
-        prev = delta + g * l * (~done[:, s]) * prev
+        delta = r[:, s] + g * (~term[:, s]).double() * nv[:, s] - v[:, s]
+        prev = delta + g * l * (~done[:, s]).double() * prev
         adv[:, s] = prev
     torch.testing.assert_close(a.cpu(), adv, rtol=1e-12, atol=1e-12)
     torch.testing.assert_close(t.cpu(), adv + v, rtol=1e-12, atol=1e-12)
