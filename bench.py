@@ -225,7 +225,7 @@ def kernel_roofline(dev, rb, ring, hbm_peak: float, peak_src: str) -> dict:
 
 def run_ours(args) -> dict:
     from rl_b200 import ops
-    from rl_b200.objectives.value import GAE
+    from rl_b200.graphs import CudaGraphStep
 
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
@@ -236,15 +236,16 @@ def run_ours(args) -> dict:
 
         dist.init_process_group("nccl", device_id=dev)
     be = ops.backend()
-    rb, g = build_buffer(dev, CAPACITY, seed=rank)
-    ring = gae_ring(dev, GAE_ROWS, GAE_T, g)
-    td_err = torch.rand(BATCH, device=dev, generator=g)
-    gae_scalars = (float(torch.tensor(GAMMA)), float(torch.tensor(GAMMA) * torch.tensor(LMBDA)))
-    gather_bufs = None
+    gbatch = BATCH * world
     if distributed:
-        from rl_b200.data.sharded import ShardedBatchGather
-
-        gather_bufs = ShardedBatchGather(dev, world)
+        rb, g = build_sharded(dev, CAPACITY, world, rank)
+    else:
+        rb, g = build_buffer(dev, CAPACITY, seed=rank)
+    ring = gae_ring(dev, GAE_ROWS, GAE_T, g)
+    ring8 = [(v, nv, r, d.view(torch.uint8), t.view(torch.uint8)) for v, nv, r, d, t in ring]
+    R = len(ring)
+    td_err = torch.rand(gbatch, device=dev, generator=g)
+    gs = (float(torch.tensor(GAMMA)), float(torch.tensor(GAMMA) * torch.tensor(LMBDA)))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -252,65 +253,114 @@ def run_ours(args) -> dict:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step(i: int):
-        batch = rb.sample()
-        if gather_bufs is not None:
-            batch = gather_bufs.all_gather(batch)
-        rb.update_priority(batch.get("index")[:BATCH] if gather_bufs is None else gather_bufs.local_index, td_err)
-        v, nv, r, d, t = ring[i % len(ring)]
-        a, tg = be.gae(v, nv, r, d.view(torch.uint8), t.view(torch.uint8), *gae_scalars, GAE_ROWS, GAE_T, 1)
-        return batch, a, tg
+    def make_step(slot: int):
+        v, nv, r, d8, t8 = ring8[slot]
 
-    # ---- device-resident timing (value)
+        def step():
+            batch = rb.sample()                                   # rand -> per_sample -> gather [-> all-gather]
+            rb.update_priority(batch.get("index"), td_err)         # fused pow + tree write-back
+            a, tg = be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
+            return batch, a, tg
+
+        return step
+
+    steps = [make_step(i) for i in range(R)]
+
+    # ---- (1) eager: every call goes through the Python API
     clocks = ClockSampler(local) if rank == 0 else None
-    ms = timed(step, args.steps, args.warmup, sync_all)
+    ms_eager = timed(lambda i: steps[i % R](), args.steps, args.warmup, sync_all)
+
+    # ---- (2) the same steps captured once into CUDA graphs (one per GAE input set) and replayed
+    graphs, graph_err = None, None
+    try:
+        gen = rb.sampler._rng
+        graphs = [CudaGraphStep(st, generators=[gen], warmup=1) for st in steps]
+        ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
+    except Exception as err:  # e.g. a collective that cannot be captured
+        graph_err = f"{type(err).__name__}: {err}"[:200]
+        graphs, ms_graph = None, None
     clk = clocks.stop() if clocks else None
 
-    # ---- sub-metrics, same method
+    # ---- sub-metrics (eager, same method)
     ms_sample = timed(lambda i: rb.sample(), args.steps, 3, sync_all)
-    ms_update = timed(lambda i: rb.update_priority(torch.randint(0, CAPACITY, (BATCH,), device=dev), td_err),
-                      args.steps, 3, sync_all)
+    idx_pool = [torch.randint(0, CAPACITY * world, (gbatch,), device=dev, generator=g) for _ in range(8)]
+    ms_update = timed(lambda i: rb.update_priority(idx_pool[i % 8], td_err), args.steps, 3, sync_all)
 
     def gae_only(i):
-        v, nv, r, d, t = ring[i % len(ring)]
-        be.gae(v, nv, r, d.view(torch.uint8), t.view(torch.uint8), *gae_scalars, GAE_ROWS, GAE_T, 1)
+        v, nv, r, d8, t8 = ring8[i % R]
+        be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
 
     ms_gae = timed(gae_only, args.steps, 3, sync_all)
 
-    # ---- end to end with HOST buffers: H2D of the step's inputs, D2H of the step's results, every step
+    # ---- (3) end to end with HOST buffers: H2D of the step's inputs and D2H of the step's results every step.
+    # Two independent lanes (stream + pinned buffers + device staging) alternate so that one step's D2H overlaps
+    # the next step's H2D and compute (PCIe is full duplex); every step still synchronises on its own results.
     pin = lambda t: t.cpu().pin_memory()
-    host_in = [tuple(pin(x) for x in s) for s in ring[:2]]
-    host_td = pin(td_err)
-    dev_in = [torch.empty_like(x) for x in ring[0]]
-    dev_td = torch.empty_like(td_err)
     sample0 = rb.sample()
-    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in sample0.items(True, True)}
-    host_adv = torch.empty(GAE_ROWS, GAE_T, 1).pin_memory()
-    host_tgt = torch.empty(GAE_ROWS, GAE_T, 1).pin_memory()
-    h2d = sum(x.numel() * x.element_size() for x in host_in[0]) + host_td.numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in host_out.values()) + 2 * host_adv.numel() * 4
+    out_keys = list(sample0.keys(True, True))
+    lanes = []
+    for lane in range(2):
+        s = torch.cuda.Stream(dev)
+        host_in = tuple(pin(x) for x in ring[lane])
+        lanes.append({
+            "stream": s, "host_in": host_in, "host_td": pin(td_err),
+            "dev_in": [torch.empty_like(x) for x in ring[lane]], "dev_td": torch.empty_like(td_err),
+            "host_out": {k: torch.empty(sample0.get(k).shape, dtype=sample0.get(k).dtype).pin_memory() for k in out_keys},
+            "host_adv": torch.empty(GAE_ROWS, GAE_T, 1).pin_memory(), "host_tgt": torch.empty(GAE_ROWS, GAE_T, 1).pin_memory(),
+            "done": torch.cuda.Event(),
+        })
+    h2d = sum(x.numel() * x.element_size() for x in lanes[0]["host_in"]) + td_err.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in lanes[0]["host_out"].values()) + 2 * GAE_ROWS * GAE_T * 4
+
+    def e2e_body(L):
+        for dst, src in zip(L["dev_in"], L["host_in"]):
+            dst.copy_(src, non_blocking=True)
+        L["dev_td"].copy_(L["host_td"], non_blocking=True)
+        batch = rb.sample()
+        rb.update_priority(batch.get("index"), L["dev_td"])
+        di = L["dev_in"]
+        a, tg = be.gae(di[0], di[1], di[2], di[3].view(torch.uint8), di[4].view(torch.uint8), gs[0], gs[1],
+                       GAE_ROWS, GAE_T, 1)
+        for k, hv in L["host_out"].items():
+            hv.copy_(batch.get(k), non_blocking=True)
+        L["host_adv"].copy_(a, non_blocking=True)
+        L["host_tgt"].copy_(tg, non_blocking=True)
 
     def e2e_step(i: int):
-        for dst, src in zip(dev_in, host_in[i % 2]):
-            dst.copy_(src, non_blocking=True)
-        dev_td.copy_(host_td, non_blocking=True)
-        batch = rb.sample()
-        rb.update_priority(batch.get("index"), dev_td)
-        a, tg = be.gae(dev_in[0], dev_in[1], dev_in[2], dev_in[3].view(torch.uint8), dev_in[4].view(torch.uint8),
-                       *gae_scalars, GAE_ROWS, GAE_T, 1)
-        for k, hv in host_out.items():
-            hv.copy_(batch.get(k), non_blocking=True)
-        host_adv.copy_(a, non_blocking=True)
-        host_tgt.copy_(tg, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller needs the results on the host
+        L = lanes[i % 2]
+        L["done"].synchronize()            # the caller consumed this lane's previous results
+        with torch.cuda.stream(L["stream"]):
+            e2e_body(L)
+            L["done"].record()
 
-    ms_e2e = timed(e2e_step, args.steps, args.warmup, sync_all)
+    def timed_e2e(steps_, warmup_):
+        for i in range(warmup_):
+            e2e_step(i)
+        sync_all()
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for L in lanes:
+            L["stream"].wait_event(e0)
+        for i in range(steps_):
+            e2e_step(warmup_ + i)
+        for L in lanes:
+            cur.wait_stream(L["stream"])
+        e1.record(cur)
+        sync_all()
+        return e0.elapsed_time(e1) / steps_
+
+    ms_e2e = timed_e2e(args.steps, args.warmup)
 
     # ---- max over ranks
+    vals = [ms_eager, ms_graph if ms_graph is not None else -1.0, ms_e2e, ms_sample, ms_update, ms_gae]
     if distributed:
-        t = torch.tensor([ms, ms_e2e, ms_sample, ms_update, ms_gae], device=dev)
+        t = torch.tensor(vals, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_sample, ms_update, ms_gae = t.tolist()
+        vals = t.tolist()
+    ms_eager, ms_graph, ms_e2e, ms_sample, ms_update, ms_gae = vals
+    if ms_graph is not None and ms_graph <= 0:
+        ms_graph = None
 
     hbm_peak, peak_src = peaks()
     result = None
@@ -318,21 +368,29 @@ def run_ours(args) -> dict:
         roof = kernel_roofline(dev, rb, ring, hbm_peak, peak_src) if world == 1 else None
         cpu = cpu_baseline_run(steps=None) if world == 1 else None
         per_step = TRANSITIONS_PER_STEP * world
+        ms = ms_graph if ms_graph is not None else ms_eager
+        n_leaves = len(rb.storage._leaves)
         result = {
             "metric": METRIC, "value": round(per_step / (ms * 1e-3), 1), "unit": "transitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 rows / f32 priorities+GAE", "data": "synthetic",
-            "config": {"workload": "C2 PER sample+update B=256 @1M Atari transitions (56462 B/row) + C3 GAE [4096,128]",
+            "config": {"workload": f"C2 PER sample+update B=256 @1M Atari transitions ({n_leaves} leaves) + C3 GAE [4096,128]",
                        "capacity_per_gpu": CAPACITY, "batch_per_gpu": BATCH, "gae_shape": [GAE_ROWS, GAE_T, 1],
                        "alpha": ALPHA, "beta": BETA, "gamma": GAMMA, "lmbda": LMBDA,
+                       "launch": "cuda_graph replay of the public-API step" if ms_graph is not None else "eager python API",
                        "parallelism": f"capacity-sharded x{world}, 1 all-gather/sample" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (56 GB storage, random rows; GAE inputs rotate through >160 MB)"},
             "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5)},
-            "gpu_launches": 5 * args.steps,
-            "breakdown": {"sample_us": round(ms_sample * 1e3, 2), "update_priority_us": round(ms_update * 1e3, 2),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5),
+                    "note": "eager python API, pinned host buffers, two lanes alternate so D2H overlaps the next H2D"},
+            "gpu_launches": (5 if world == 1 else 9) * args.steps,
+            "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
+                          "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),
+                          "graph_error": graph_err,
+                          "eager_value": round(per_step / (ms_eager * 1e-3), 1),
+                          "sample_us": round(ms_sample * 1e3, 2), "update_priority_us": round(ms_update * 1e3, 2),
                           "gae_us": round(ms_gae * 1e3, 2),
-                          "sample_transitions_per_s": round(BATCH * world / (ms_sample * 1e-3), 1),
+                          "sample_transitions_per_s": round(gbatch / (ms_sample * 1e-3), 1),
                           "gae_transitions_per_s": round(GAE_ROWS * GAE_T * world / (ms_gae * 1e-3), 1)},
             "clocks": clk,
         }
@@ -346,6 +404,28 @@ def run_ours(args) -> dict:
     return result
 
 
+def build_sharded(dev, capacity_per_rank: int, world: int, rank: int):
+    """One 1M shard per rank of a capacity-sharded buffer (weak scaling), filled with synthetic transitions."""
+    from rl_b200.data import TensorDict
+    from rl_b200.data.sharded import ShardedPrioritizedReplayBuffer
+
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    rb = ShardedPrioritizedReplayBuffer(alpha=ALPHA, beta=BETA, capacity=capacity_per_rank * world,
+                                        batch_size=BATCH * world, device=dev, generator=g)
+    chunk = 50_000
+    for lo in range(0, capacity_per_rank, chunk):
+        n = min(chunk, capacity_per_rank - lo)
+        rb.extend(TensorDict({
+            "pixels": torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+            "action": torch.randint(0, 18, (n, 1), device=dev, generator=g),
+            "next": {"pixels": torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+                     "reward": torch.randn(n, device=dev, generator=g),
+                     "done": torch.rand(n, 1, device=dev, generator=g) < 0.01,
+                     "terminated": torch.rand(n, 1, device=dev, generator=g) < 0.01},
+            "td_error": torch.rand(n, device=dev, generator=g)}, [n]))
+    return rb, g
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 def cpu_baseline_run(steps: int | None, warmup: int = 2) -> dict:
     """The reference's own CPU path on the host cores: compiled reference segment trees (oracle/_ref/cpu) under
@@ -356,7 +436,6 @@ def cpu_baseline_run(steps: int | None, warmup: int = 2) -> dict:
     from oracle.ref_loader import reference_trees
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     factory = reference_trees("cpu")
     kind = "reference" if factory is not None else "port"
     smp = po.OraclePrioritizedSampler(CAPACITY, ALPHA, BETA, tree_factory=factory)
@@ -380,16 +459,31 @@ def cpu_baseline_run(steps: int | None, warmup: int = 2) -> dict:
             fn()
         return (time.perf_counter() - t0) / n
 
+    # give the reference the thread count it runs fastest with (many-core hosts oversubscribe the small ops of
+    # the GAE code paths; aten::index parallelises over rows): tuned per phase on the bounded sample
+    cands = sorted({c for c in (1, 4, 8, 16, 32, 64, cores) if c <= cores})
+    ridx0 = torch.randint(0, rows, (BATCH,), generator=g)
+    best_gae, best_gather = (None, None, 1e9), (None, 1e9)
     with torch.no_grad():
-        t_loop = t_of(lambda: gae_torch.loop_gae(gm, lm, v, nv, r, done, term), 3)
-        t_vec = t_of(lambda: gae_torch.vec_gae(gm, lm, v, nv, r, done, term), 3)
-    gae_fn = gae_torch.loop_gae if t_loop <= t_vec else gae_torch.vec_gae
+        for c in cands:
+            torch.set_num_threads(c)
+            for name, fn in (("loop", gae_torch.loop_gae), ("vec", gae_torch.vec_gae)):
+                t = t_of(lambda: fn(gm, lm, v, nv, r, done, term), 2)
+                if t < best_gae[2]:
+                    best_gae = (name, c, t)
+            t = t_of(lambda: {k: x[ridx0] for k, x in store.items()}, 3)
+            if t < best_gather[1]:
+                best_gather = (c, t)
+    gae_fn = gae_torch.loop_gae if best_gae[0] == "loop" else gae_torch.vec_gae
+    t_loop = t_vec = best_gae[2]
 
     def step():
+        torch.set_num_threads(best_gather[0])
         idx, w = smp.sample(CAPACITY, BATCH, generator=g)
         ridx = idx % rows  # bounded storage: same number of random 28 KB rows touched
         batch = {k: x[ridx] for k, x in store.items()}
         smp.update_priority(idx, td)
+        torch.set_num_threads(best_gae[1])
         with torch.no_grad():
             a, t = gae_fn(gm, lm, v, nv, r, done, term)
         return batch, a, t
@@ -403,12 +497,14 @@ def cpu_baseline_run(steps: int | None, warmup: int = 2) -> dict:
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": round(TRANSITIONS_PER_STEP / dt, 1), "unit": "transitions/s", "cores": cores, "kind": kind,
+    return {"value": round(TRANSITIONS_PER_STEP / dt, 1), "unit": "transitions/s",
+            "cores": max(best_gather[0], best_gae[1]), "host_cores": cores, "kind": kind,
             "ms_per_step": round(dt * 1e3, 3), "steps": steps,
-            "sample": (f"{steps} steps of [reference C++ SumSegmentTree/MinSegmentTree sample+update B=256 @1M + "
-                       f"aten::index gather of 256 Atari transitions from a {rows}-row CPU storage + "
-                       f"{'loop' if gae_fn is gae_torch.loop_gae else 'vec'} GAE [4096,128]] "
-                       f"(gae loop {t_loop * 1e3:.1f} ms, vec {t_vec * 1e3:.1f} ms; faster one used)")}
+            "sample": (f"{steps} steps of [reference C++ SumSegmentTree/MinSegmentTree sample+update B=256 @1M "
+                       f"(single-threaded by construction) + aten::index gather of 256 Atari transitions from a "
+                       f"{rows}-row CPU storage ({best_gather[0]} threads, {best_gather[1] * 1e3:.2f} ms) + "
+                       f"{best_gae[0]} GAE [4096,128] ({best_gae[1]} threads, {best_gae[2] * 1e3:.1f} ms)]; thread "
+                       f"counts are the fastest of {cands} for each phase")}
 
 
 def run_reference(args) -> dict | None:

@@ -144,7 +144,7 @@ int rlb_per_sample(const void *sum_tree /*[dev]*/, const void *min_tree /*[dev]*
  * fp32 trees only. */
 int rlb_per_update(void *sum_tree /*[dev]*/, void *min_tree /*[dev]*/, int64_t capacity,
                    const int64_t *index /*[dev] n*/, const float *priority /*[dev] n or 1*/, int64_t n,
-                   int scalar, double alpha, double eps, float *leaf_scratch /*[dev] n*/,
+                   int scalar, double alpha, double eps, float *leaf_scratch /*[dev] n; may be NULL when n <= 1024*/,
                    float *max_priority_out /*[dev] 1 or NULL*/, void *workspace /*[dev]*/,
                    size_t workspace_bytes, uint32_t epoch, rlb_stream_t stream);
 
@@ -153,13 +153,16 @@ int rlb_per_update(void *sum_tree /*[dev]*/, void *min_tree /*[dev]*/, int64_t c
  * (data/replay_buffers/storages.py:1242-1263: storage[:len][index] per leaf, which bottoms out
  * in aten::index / vectorized_gather_kernel).  For every leaf k in ONE launch:
  *     dst[k][b, :] = src[k][index[b], :]        b in [0, B), rows are `row_bytes[k]` bytes,
- * source rows `src_stride_bytes[k]` apart, destination rows contiguous.  Negative indices wrap
+ * source rows `src_stride_bytes[k]` apart, destination rows `dst_stride_bytes[k]` apart (NULL =
+ * contiguous; a stride lets every leaf land in its column of one packed [B, row] buffer, e.g. the
+ * send buffer of the sharded buffer's all-gather, with no staging copy).  Negative indices wrap
  * (index + len) as in torch indexing; out-of-range indices set RLB_STATUS_INDEX_OOB in *status
  * and are clamped (torch raises IndexError; callers that want the exception read the status). */
 int rlb_gather(const void *const *src /*[host] n_leaves [dev] pointers*/,
                void *const *dst /*[host] n_leaves [dev] pointers*/, const int64_t *row_bytes /*[host]*/,
-               const int64_t *src_stride_bytes /*[host]*/, int n_leaves, const int64_t *index /*[dev] B*/,
-               int64_t B, int64_t len, int mode, int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
+               const int64_t *src_stride_bytes /*[host]*/, const int64_t *dst_stride_bytes /*[host] or NULL*/,
+               int n_leaves, const int64_t *index /*[dev] B*/, int64_t B, int64_t len, int mode,
+               int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
 
 /* TensorStorage.set for a tensor cursor (storages.py:1028-1096: storage[cursor] = data per leaf,
  * aten::index_put_):  dst[k][index[b], :] = src[k][b, :].  Duplicate indices: the last wins only

@@ -39,6 +39,7 @@ struct GatherLeaf {
   uint8_t *dst;
   int64_t row_bytes;
   int64_t stride;   // gather: source row stride; scatter: destination row stride
+  int64_t ostride;  // row stride of the OTHER (batch-ordered) side: gather dst / scatter src
   int64_t first;    // first 16-B unit (bulk role) / first tile (vector role) of this leaf
   int64_t units;    // vector role: B * (row_bytes >> vec_log2)
   uint32_t upr;     // vector role: vectors per row
@@ -120,14 +121,14 @@ __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams
   for (int k = 0; k < kVecUnroll; ++k) {
     if (ok[k]) {
       ix[k] = fix_index(ix[k], P.len, P.status);
-      const int64_t srow = SCATTER ? b[k] * L.row_bytes : ix[k] * L.stride;
+      const int64_t srow = SCATTER ? b[k] * L.ostride : ix[k] * L.stride;
       val[k] = ld_stream(reinterpret_cast<const V *>(L.src + srow) + j[k]);
     }
   }
 #pragma unroll
   for (int k = 0; k < kVecUnroll; ++k) {
     if (ok[k]) {
-      const int64_t drow = SCATTER ? ix[k] * L.stride : b[k] * L.row_bytes;
+      const int64_t drow = SCATTER ? ix[k] * L.stride : b[k] * L.ostride;
       st_stream(reinterpret_cast<V *>(L.dst + drow) + j[k], val[k]);
     }
   }
@@ -214,7 +215,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
         // the slot was last used by piece n_loaded - kStages: its s->g copy must have finished READING
         // shared memory.  At most kStages - kAhead younger stores may still be pending.
         if (n_loaded >= kStages) bulk_wait_read<kStages - kAhead>();
-        my->dst[stage] = L.dst + b * L.row_bytes + off;
+        my->dst[stage] = L.dst + b * L.ostride + off;
         my->bytes[stage] = (uint32_t)nbytes;
         mbar_arrive_expect_tx(&my->full[stage], (uint32_t)nbytes);
         bulk_g2s(my_ring + (size_t)stage * kChunk, L.src + ix * L.stride + off, (uint32_t)nbytes, &my->full[stage]);
@@ -274,11 +275,11 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const __grid_con
 static_assert(sizeof(PipeSmem) * kPipes <= 1024, "PipeSmem header must fit in 1 KB");
 constexpr size_t kBulkSmemBytes = 1024 + (size_t)kPipes * kStages * kChunk;
 
-static int pick_vec_log2(const void *src, const void *dst, int64_t row_bytes, int64_t stride) {
+static int pick_vec_log2(const void *src, const void *dst, int64_t row_bytes, int64_t stride, int64_t ostride) {
   for (int lg = 4; lg > 0; --lg) {
     const uintptr_t a = uintptr_t(1) << lg;
     if (reinterpret_cast<uintptr_t>(src) % a == 0 && reinterpret_cast<uintptr_t>(dst) % a == 0 &&
-        row_bytes % (int64_t)a == 0 && stride % (int64_t)a == 0)
+        row_bytes % (int64_t)a == 0 && stride % (int64_t)a == 0 && ostride % (int64_t)a == 0)
       return lg;
   }
   return 0;
@@ -286,7 +287,7 @@ static int pick_vec_log2(const void *src, const void *dst, int64_t row_bytes, in
 
 template <bool SCATTER>
 static int launch_rows(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *stride,
-                       int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status,
+                       const int64_t *ostride, int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status,
                        cudaStream_t st, const char *who) {
   RLB_REQUIRE(n_leaves >= 0 && n_leaves <= RLB_MAX_LEAVES, RLB_ELIMIT, "%s: n_leaves=%d exceeds RLB_MAX_LEAVES=%d",
               who, n_leaves, RLB_MAX_LEAVES);
@@ -313,7 +314,9 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
     L.dst = static_cast<uint8_t *>(dst[k]);
     L.row_bytes = row_bytes[k];
     L.stride = stride[k];
-    const int lg = pick_vec_log2(src[k], dst[k], row_bytes[k], stride[k]);
+    L.ostride = ostride ? ostride[k] : row_bytes[k];
+    RLB_REQUIRE(L.ostride >= row_bytes[k], RLB_EINVAL, "%s: leaf %d batch-side stride < row_bytes", who, k);
+    const int lg = pick_vec_log2(src[k], dst[k], row_bytes[k], stride[k], L.ostride);
     const bool eligible = !SCATTER && lg == 4 && row_bytes[k] >= 16;
     const bool want = (mode == RLB_GATHER_BULK) || (mode == RLB_GATHER_AUTO && row_bytes[k] >= kBulkMinRowBytes);
     if (row_bytes[k] == 0) {
@@ -376,18 +379,18 @@ using namespace rlb;
 extern "C" {
 
 int rlb_gather(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *src_stride_bytes,
-               int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status,
-               rlb_stream_t stream) {
+               const int64_t *dst_stride_bytes, int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode,
+               int32_t *status, rlb_stream_t stream) {
   RLB_REQUIRE(mode == RLB_GATHER_AUTO || mode == RLB_GATHER_VECTOR || mode == RLB_GATHER_BULK, RLB_EINVAL,
               "rlb_gather: unknown mode %d", mode);
-  return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, n_leaves, index, B, len, mode, status,
-                            as_stream(stream), "rlb_gather");
+  return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, dst_stride_bytes, n_leaves, index, B, len, mode,
+                            status, as_stream(stream), "rlb_gather");
 }
 
 int rlb_scatter(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *dst_stride_bytes,
                 int n_leaves, const int64_t *index, int64_t B, int64_t len, int32_t *status, rlb_stream_t stream) {
-  return launch_rows<true>(src, dst, row_bytes, dst_stride_bytes, n_leaves, index, B, len, RLB_GATHER_VECTOR,
-                           status, as_stream(stream), "rlb_scatter");
+  return launch_rows<true>(src, dst, row_bytes, dst_stride_bytes, nullptr, n_leaves, index, B, len,
+                           RLB_GATHER_VECTOR, status, as_stream(stream), "rlb_scatter");
 }
 
 }  // extern "C"

@@ -109,6 +109,32 @@ __global__ void tree_at_kernel(const T *__restrict__ tree, int64_t capacity, con
   if (i < n) out[i] = tree[index[i] | capacity];
 }
 
+// torch.pow(x, scalar) semantics for fp32 tensors on CUDA (ATen/native/cuda/PowKernel.cu): dedicated
+// kernels for 0.5 / -0.5 / -1, x*x, x*x*x, 1/(x*x) for 2 / 3 / -2, ::pow otherwise; exponent 0 -> 1,
+// exponent 1 -> copy (ATen/native/Pow.cpp).  The exponent is cast to the tensor dtype first.
+__device__ __forceinline__ float pow_like_torch(float x, float y) {
+  if (y == 0.0f) return 1.0f;
+  if (y == 1.0f) return x;
+  if (y == 0.5f) return sqrtf(x);
+  if (y == -0.5f) return rsqrtf(x);
+  if (y == -1.0f) return 1.0f / x;
+  if (y == 2.0f) return mul_rn(x, x);
+  if (y == 3.0f) return mul_rn(mul_rn(x, x), x);
+  if (y == -2.0f) return (float)(1.0 / (double)mul_rn(x, x));
+  return powf(x, y);
+}
+__device__ __forceinline__ double pow_like_torch(double x, double y) {
+  if (y == 0.0) return 1.0;
+  if (y == 1.0) return x;
+  if (y == 0.5) return sqrt(x);
+  if (y == -0.5) return rsqrt(x);
+  if (y == -1.0) return 1.0 / x;
+  if (y == 2.0) return x * x;
+  if (y == 3.0) return x * x * x;
+  if (y == -2.0) return 1.0 / (x * x);
+  return pow(x, y);
+}
+
 // ------------------------------------------------------------------------------------------------
 // lower-bound descent (SumSegmentTree::ScanLowerBound, csrc/segment_tree.h:249-264)
 // ------------------------------------------------------------------------------------------------
@@ -210,32 +236,6 @@ __global__ void tree_scan_kernel(const T *__restrict__ tree, int64_t size, int64
 // ------------------------------------------------------------------------------------------------
 // fused PrioritizedSampler.sample arithmetic (samplers.py:895-956)
 // ------------------------------------------------------------------------------------------------
-// torch.pow(x, scalar) semantics for fp32 tensors on CUDA (ATen/native/cuda/PowKernel.cu): dedicated
-// kernels for 0.5 / -0.5 / -1, x*x, x*x*x, 1/(x*x) for 2 / 3 / -2, ::pow otherwise; exponent 0 -> 1,
-// exponent 1 -> copy (ATen/native/Pow.cpp).  The exponent is cast to the tensor dtype first.
-__device__ __forceinline__ float pow_like_torch(float x, float y) {
-  if (y == 0.0f) return 1.0f;
-  if (y == 1.0f) return x;
-  if (y == 0.5f) return sqrtf(x);
-  if (y == -0.5f) return rsqrtf(x);
-  if (y == -1.0f) return 1.0f / x;
-  if (y == 2.0f) return mul_rn(x, x);
-  if (y == 3.0f) return mul_rn(mul_rn(x, x), x);
-  if (y == -2.0f) return (float)(1.0 / (double)mul_rn(x, x));
-  return powf(x, y);
-}
-__device__ __forceinline__ double pow_like_torch(double x, double y) {
-  if (y == 0.0) return 1.0;
-  if (y == 1.0) return x;
-  if (y == 0.5) return sqrt(x);
-  if (y == -0.5) return rsqrt(x);
-  if (y == -1.0) return 1.0 / x;
-  if (y == 2.0) return x * x;
-  if (y == 3.0) return x * x * x;
-  if (y == -2.0) return 1.0 / (x * x);
-  return pow(x, y);
-}
-
 // query(0, len) of one tree by one warp.  For l = 0 the walk only ever takes RIGHT terms:
 // level j contributes tree[r_j - 1] iff r_j is odd, with r_j = (capacity + len) >> j, while l_j < r_j
 // (l_j = capacity >> j).  The terms are independent loads (one lane per level), folded in level order
@@ -271,6 +271,8 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
                                                          T *psum_pmin_out, int32_t *status) {
   __shared__ T s_p[2];
   const int warp = threadIdx.x >> 5;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const T ui = (i < B) ? __ldg(u + i) : (T)0;  // in flight while warps 0/1 resolve p_sum / p_min
   if (warp < 2) {
     // warp 0: p_sum, warp 1: p_min   (samplers.py:901-908)
     T v;
@@ -296,9 +298,8 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
       if (st) atomicOr(status, st);
     }
   }
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= B) return;
-  const T mass = mul_rn(u[i], p_sum);  // samplers.py:919 / :923 -- one rounding, never fused downstream
+  const T mass = mul_rn(ui, p_sum);  // samplers.py:919 / :923 -- one rounding, never fused downstream
   int64_t idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1));
   if (idx > len - 1) idx = len - 1;  // samplers.py:933
   T leaf = __ldg(sum + (idx | capacity));
@@ -354,39 +355,78 @@ __device__ __forceinline__ uint32_t upd_probe_insert(UpdSlot<T> *tab, uint32_t m
 // position (last-writer-wins, csrc/segment_tree.h:222-226 / cuda_segment_tree.cu:32-37).  Then for each
 // level a carrier thread deposits its node's (sum, min) value in the hash slot of the parent; the
 // thread that created the slot carries the parent upward, combining the two children in (left, right)
-// order; an untouched sibling comes from the (prefetched) global value.  Two tables alternate so a fast
-// thread's inserts for level k+1 never race with a slow thread's read+clear of level k.
-template <typename T>
+// order; an untouched sibling comes from its global value.  Those sibling reads are the only global
+// round trips on the critical path, so every path's siblings are pulled into L2 up front
+// (prefetch.global.L2, fire and forget) and each level's sibling is loaded one level ahead of its use.
+// Two tables alternate so a fast thread's inserts for level k+1 never race with a slow thread's
+// read+clear of level k.
+// FUSED (fp32): `value` holds RAW priorities; the leaf is (p + eps) ** alpha (samplers.py:1076, torch.pow
+// semantics) and the maximum raw priority of the valid items is folded into *max_out.
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  int *ia = reinterpret_cast<int *>(addr);
+  int old = *ia;
+  while (__int_as_float(old) < v) {
+    const int assumed = old;
+    old = atomicCAS(ia, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+
+template <typename T, bool FUSED>
 __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, int64_t capacity, int depth,
                                                                const int64_t *__restrict__ index,
                                                                const T *__restrict__ value, int n, int scalar,
-                                                               int log2_slots) {
+                                                               int log2_slots, float alpha, float eps,
+                                                               float *max_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   UpdSlot<T> *tab = reinterpret_cast<UpdSlot<T> *>(smem_raw);
   const uint32_t nslots = 1u << log2_slots;
   const uint32_t mask = nslots - 1;
   const int tid = threadIdx.x;
+
+  // ---- my item; start pulling its whole path's siblings into L2 before anything else
+  bool active = false;
+  uint32_t leafnode = 0;
+  T raw = (T)0;
+  if (tid < n) {
+    const int64_t ix = index[tid];
+    if (ix >= 0 && ix < capacity) {  // negative = "skip" (MaxValueWriter convention, samplers.py:1040-1052)
+      active = true;
+      leafnode = (uint32_t)(capacity + ix);
+      for (int k = 0; k < depth; ++k) {
+        const uint32_t sib = (leafnode >> k) ^ 1u;
+        if (sum) prefetch_l2(sum + sib);
+        if (mn) prefetch_l2(mn + sib);
+      }
+      raw = scalar ? value[0] : value[tid];
+    }
+  }
+  if constexpr (FUSED) {
+    if (max_out) {
+      float p = active ? (float)raw : -INFINITY;
+      for (int o = 16; o > 0; o >>= 1) p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
+      if ((tid & 31) == 0 && p > -INFINITY) atomic_max_float(max_out, p);
+    }
+  }
   for (uint32_t i = tid; i < 2 * nslots; i += blockDim.x) {
     tab[i].key = kEmptyKey;
     tab[i].aux = 0;
   }
   __syncthreads();
 
-  bool active = false;
-  uint32_t node = 0, slot = 0;
+  uint32_t node = leafnode, slot = 0;
   T vs = (T)0, vm = (T)0;
   {
     // ---- round -1: last-writer-wins election on table 1
     UpdSlot<T> *t1 = tab + nslots;
-    if (tid < n) {
-      const int64_t ix = index[tid];
-      if (ix >= 0 && ix < capacity) {  // negative = "skip" (MaxValueWriter convention, samplers.py:1040-1052)
-        active = true;
-        node = (uint32_t)(capacity + ix);
-        bool owner;
-        slot = upd_probe_insert(t1, mask, log2_slots, node, owner);
-        atomicMax(&t1[slot].aux, (uint32_t)tid + 1u);
-      }
+    if (active) {
+      bool owner;
+      slot = upd_probe_insert(t1, mask, log2_slots, node, owner);
+      atomicMax(&t1[slot].aux, (uint32_t)tid + 1u);
     }
     __syncthreads();
     if (active) {
@@ -396,7 +436,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       } else {
         t1[slot].key = kEmptyKey;
         t1[slot].aux = 0;
-        const T v = scalar ? value[0] : value[tid];
+        T v = raw;
+        if constexpr (FUSED) v = (T)pow_like_torch(add_rn((float)raw, eps), alpha);
         vs = v;
         vm = v;
         if (sum) sum[node] = v;
@@ -405,16 +446,23 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     }
   }
 
+  // sibling of my node at level 0, loaded ahead of use; later levels are loaded one level ahead
+  T sib_s = (T)0, sib_m = (T)0;
+  if (active) {
+    if (sum) sib_s = ld_cg(sum + (node ^ 1u));
+    if (mn) sib_m = ld_cg(mn + (node ^ 1u));
+  }
   for (int k = 0; k < depth; ++k) {
     UpdSlot<T> *cur = tab + (uint32_t)(k & 1) * nslots;
     bool owner = false;
-    T sib_s = (T)0, sib_m = (T)0;
     const uint32_t side = node & 1u;
     const uint32_t parent = node >> 1;
+    T nxt_s = (T)0, nxt_m = (T)0;
     if (active) {
-      // old value of the sibling: only used if nobody in this batch carries it
-      if (sum) sib_s = ld_cg(sum + (node ^ 1u));
-      if (mn) sib_m = ld_cg(mn + (node ^ 1u));
+      if (k + 1 < depth) {  // old value of the parent's sibling: only used if nobody in this batch carries it
+        if (sum) nxt_s = ld_cg(sum + (parent ^ 1u));
+        if (mn) nxt_m = ld_cg(mn + (parent ^ 1u));
+      }
       slot = upd_probe_insert(cur, mask, log2_slots, parent, owner);
       cur[slot].s[side] = vs;
       cur[slot].m[side] = vm;
@@ -436,6 +484,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         node = parent;
         if (sum) sum[node] = vs;
         if (mn) mn[node] = vm;
+        sib_s = nxt_s;
+        sib_m = nxt_m;
       }
     }
   }
@@ -487,16 +537,6 @@ __global__ void upd_sweep_kernel(T *sum, T *mn, int64_t capacity, const int64_t 
 // ------------------------------------------------------------------------------------------------
 // fused (priority + eps) ** alpha  (samplers.py:1076) + running max of the raw priorities
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
-  int *ia = reinterpret_cast<int *>(addr);
-  int old = *ia;
-  while (__int_as_float(old) < v) {
-    const int assumed = old;
-    old = atomicCAS(ia, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
-}
-
 __global__ void __launch_bounds__(256) per_update_prep_kernel(const int64_t *__restrict__ index,
                                                               const float *__restrict__ priority, int64_t n,
                                                               int scalar, float alpha, float eps,
@@ -569,30 +609,47 @@ static int tree_rebuild_impl(void *tree_, int64_t capacity, int is_min, cudaStre
   return RLB_OK;
 }
 
+struct FusedPow {
+  bool on = false;
+  float alpha = 0.f, eps = 0.f;
+  float *max_out = nullptr;
+};
+
+template <typename T, bool FUSED>
+static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const int64_t *index, const T *value,
+                             int64_t n, int scalar, const FusedPow &fp, cudaStream_t st) {
+  const int threads = (int)((n + 31) / 32 * 32);
+  int log2_slots = 6;
+  while ((1 << log2_slots) < 2 * n) ++log2_slots;
+  const size_t smem = 2 * (size_t(1) << log2_slots) * sizeof(UpdSlot<T>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T, FUSED>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                        "cudaFuncSetAttribute(tree_update_cta_kernel)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  tree_update_cta_kernel<T, FUSED><<<1, threads, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n, scalar,
+                                                             log2_slots, fp.alpha, fp.eps, fp.max_out);
+  return check_launch("tree_update_cta_kernel");
+}
+
+constexpr int64_t kUpdateCtaMax = 1024;  // batch sizes handled by the single-CTA kernel
+
 template <typename T>
 static int tree_update_impl(void *sum_, void *mn_, int64_t capacity, const int64_t *index, const void *value_,
                             int64_t n, int scalar, void *workspace, size_t workspace_bytes, uint32_t epoch,
-                            cudaStream_t st) {
+                            cudaStream_t st, const FusedPow &fp = FusedPow()) {
   T *sum = static_cast<T *>(sum_);
   T *mn = static_cast<T *>(mn_);
   const T *value = static_cast<const T *>(value_);
   const int depth = ilog2_i64(capacity);
-  if (n <= 1024 && capacity <= (int64_t(1) << 30)) {
-    int threads = (int)((n + 31) / 32 * 32);
-    int log2_slots = 6;
-    while ((1 << log2_slots) < 2 * n) ++log2_slots;
-    const size_t smem = 2 * (size_t(1) << log2_slots) * sizeof(UpdSlot<T>);
-    static bool attr_set = false;
-    if (!attr_set) {
-      int rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                          "cudaFuncSetAttribute(tree_update_cta_kernel)");
-      if (rc) return rc;
-      attr_set = true;
+  if (n <= kUpdateCtaMax && capacity <= (int64_t(1) << 30)) {
+    if constexpr (sizeof(T) == 4) {
+      if (fp.on) return launch_update_cta<T, true>(sum, mn, capacity, depth, index, value, n, scalar, fp, st);
     }
-    tree_update_cta_kernel<T><<<1, threads, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n, scalar,
-                                                        log2_slots);
-    return check_launch("tree_update_cta_kernel");
+    return launch_update_cta<T, false>(sum, mn, capacity, depth, index, value, n, scalar, fp, st);
   }
   // general path
   RLB_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)capacity * sizeof(unsigned long long),
@@ -772,8 +829,19 @@ int rlb_per_update(void *sum_tree, void *min_tree, int64_t capacity, const int64
   RLB_REQUIRE((sum_tree || min_tree) && is_pow2(capacity), RLB_EINVAL, "rlb_per_update: bad tree/capacity");
   RLB_REQUIRE(n >= 0, RLB_EINVAL, "rlb_per_update: negative n");
   if (n == 0) return RLB_OK;
-  RLB_REQUIRE(index && priority && leaf_scratch, RLB_EINVAL, "rlb_per_update: null index/priority/leaf_scratch");
+  RLB_REQUIRE(index && priority, RLB_EINVAL, "rlb_per_update: null index/priority");
+  RLB_REQUIRE(leaf_scratch || n <= kUpdateCtaMax, RLB_EINVAL, "rlb_per_update: n > 1024 needs leaf_scratch[n]");
   cudaStream_t st = as_stream(stream);
+  if (n <= kUpdateCtaMax && capacity <= (int64_t(1) << 30)) {
+    // one launch: pow, running max, election, leaf write and the climb all happen inside the CTA kernel
+    FusedPow fp;
+    fp.on = true;
+    fp.alpha = (float)alpha;
+    fp.eps = (float)eps;
+    fp.max_out = max_priority_out;
+    return tree_update_impl<float>(sum_tree, min_tree, capacity, index, priority, n, scalar, workspace,
+                                   workspace_bytes, epoch, st, fp);
+  }
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   per_update_prep_kernel<<<blocks, threads, 0, st>>>(index, priority, n, scalar, (float)alpha, (float)eps,

@@ -260,6 +260,10 @@ class PrioritizedSampler(Sampler):
         return self._epoch
 
     def _tree_workspace(self, n: int):
+        if n > 1024 and self._sum_tree.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(
+                "update_priority with more than 1024 entries uses an epoch-stamped scatter that cannot be replayed "
+                "from a CUDA graph; split the batch or run it outside the graph.")
         if n > 1024 and self._workspace is None:
             self._workspace = ops.backend().tree_workspace(self._max_capacity, self._sum_tree.device)
         return self._workspace
@@ -464,6 +468,6 @@ class PrioritizedSampler(Sampler):
             self._init()
         for name, tree in (("sumtree.memmap", self._sum_tree), ("mintree.memmap", self._min_tree)):
             arr = np.memmap(path / name, dtype=np.float64, mode="r", shape=(self._max_capacity,))
-            tree.load_leaves(torch.from_numpy(np.ascontiguousarray(arr)))
+            tree.load_leaves(torch.from_numpy(np.array(arr)))
         mp = metadata["_max_priority"]
         self._set_max_priority((mp[0], None if mp[1] is None else int(mp[1])))

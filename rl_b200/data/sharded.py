@@ -1,0 +1,184 @@
+"""Capacity-sharded prioritized replay over the GPUs of one box.
+
+The reference has no sharded / collective replay buffer (its nearest analogue is ``SamplerEnsemble`` with
+``sample_from_all=True``, samplers.py:3111-3118: equal quotas per sub-buffer).  Here slots
+``[r*N/W, (r+1)*N/W)`` live on rank ``r`` with their own sum/min trees; ``sample(B)`` draws ``B/W`` rows on
+every rank and assembles the global minibatch with ONE all-gather over NVLink:
+
+  * the local gather kernel writes every leaf of the local draw straight into its column of a packed
+    ``[B/W, row]`` send buffer (``rlb_gather`` with destination strides) -- no staging copy;
+  * the same rows carry the global index, the leaf priority ``p_i`` and the shard's ``(S_r, m_r)``
+    (sum and min of its priorities), so importance weights can be finalised identically on every rank after
+    the gather, normalised over the WHOLE buffer as the reference normalises over its single buffer:
+        w_i = ((p_i / S_r) / min_r'(m_r' / S_r')) ** -beta          (W = 1  ->  (p_i / p_min) ** -beta)
+  * ``torch.distributed.all_gather_into_tensor`` (NCCL) moves ``B/W * row`` bytes per rank; leaves of the
+    returned batch are strided views into the receive buffer.
+
+``update_priority`` takes GLOBAL indices (replicated on every rank, or any subset): each rank rewrites the
+ones it owns and skips the rest inside the kernel (negative local index) -- no collective, no sync.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import ops
+from .replay_buffers import TensorDictPrioritizedReplayBuffer
+from .storages import LazyTensorStorage, flatten_data, unflatten_data
+from .tensordict_lite import is_tensor_collection
+
+
+def _align(x: int, a: int) -> int:
+    return -(-x // a) * a
+
+
+class _PackedLayout:
+    """Column layout of one packed transition row: every storage leaf + (global index, p_i, S_r, m_r)."""
+
+    def __init__(self, leaves):
+        order = sorted(range(len(leaves)), key=lambda k: -leaves[k][0].numel() * leaves[k].element_size())
+        off = 0
+        self.cols = [None] * len(leaves)
+        for k in order:
+            t = leaves[k]
+            nbytes = t[0].numel() * t.element_size()
+            a = 16 if nbytes >= 16 else max(t.element_size(), 1)
+            off = _align(off, a)
+            self.cols[k] = (off, nbytes, t.dtype, tuple(t.shape[1:]))
+            off += nbytes
+        off = _align(off, 8)
+        self.meta = off            # int64 global index | f32 p_i | f32 S_r | f32 m_r | pad
+        off += 8 + 4 + 4 + 4
+        self.row = _align(off, 16)
+
+    def leaf_views(self, buf: torch.Tensor) -> list[torch.Tensor]:
+        """buf: uint8 [rows, self.row] -> one strided [rows, *shape] view per leaf."""
+        rows = buf.shape[0]
+        out = []
+        for off, nbytes, dtype, shape in self.cols:
+            col = buf[:, off:off + nbytes]
+            v = col.view(dtype) if dtype != torch.uint8 else col
+            out.append(v.view(rows, *shape) if shape else v.view(rows))
+        return out
+
+    def meta_views(self, buf: torch.Tensor):
+        m = self.meta
+        return (buf[:, m:m + 8].view(torch.int64).view(-1), buf[:, m + 8:m + 12].view(torch.float32).view(-1),
+                buf[:, m + 12:m + 16].view(torch.float32).view(-1), buf[:, m + 16:m + 20].view(torch.float32).view(-1))
+
+
+class ShardedPrioritizedReplayBuffer:
+    """One shard of a capacity-sharded ``TensorDictPrioritizedReplayBuffer`` per rank.
+
+    Keyword Args:
+        alpha, beta, eps, priority_key: as :class:`TensorDictPrioritizedReplayBuffer`.
+        capacity (int): GLOBAL capacity; every rank holds ``ceil(capacity / world_size)`` slots.
+        batch_size (int): GLOBAL batch size of :meth:`sample` (must be divisible by the world size).
+        device: this rank's device.
+        generator: this rank's random generator (seed it with ``seed + rank``).
+        process_group: defaults to the global group; ``None`` with an uninitialised torch.distributed runs as a
+            single shard (world size 1).
+    """
+
+    def __init__(self, *, alpha: float, beta: float, capacity: int, eps: float = 1e-8, priority_key: str = "td_error",
+                 batch_size: int | None = None, device="cuda", generator=None, process_group=None):
+        import torch.distributed as dist
+
+        self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = process_group
+        self.world = self._dist.get_world_size(process_group) if self._dist else 1
+        self.rank = self._dist.get_rank(process_group) if self._dist else 0
+        self.capacity = int(capacity)
+        self.shard_capacity = -(-self.capacity // self.world)
+        if batch_size is not None and batch_size % self.world:
+            raise ValueError(f"batch_size={batch_size} must be divisible by the world size {self.world}")
+        self._batch_size = batch_size
+        self.device = torch.device(device)
+        self.local = TensorDictPrioritizedReplayBuffer(
+            alpha=alpha, beta=beta, eps=eps, priority_key=priority_key,
+            storage=LazyTensorStorage(self.shard_capacity, device=self.device),
+            batch_size=None if batch_size is None else batch_size // self.world, generator=generator)
+        self._layout = None
+        self.local_index = None  # local indices of this rank's last draw
+
+    # ---- writes: every rank feeds its own shard (data-parallel collectors) --------------------------------
+    def extend(self, data) -> torch.Tensor:
+        """Writes ``data`` into this rank's shard; returns the GLOBAL indices of the written slots."""
+        local = self.local.extend(data)
+        return local + self.rank * self.shard_capacity
+
+    def __len__(self) -> int:
+        return len(self.local)
+
+    @property
+    def sampler(self):
+        return self.local.sampler
+
+    @property
+    def storage(self):
+        return self.local.storage
+
+    # ---- sample --------------------------------------------------------------------------------------
+    def sample(self, batch_size: int | None = None):
+        if batch_size is None:
+            batch_size = self._batch_size
+        if batch_size is None:
+            raise RuntimeError("batch_size not specified.")
+        if batch_size % self.world:
+            raise ValueError(f"batch_size={batch_size} must be divisible by the world size {self.world}")
+        b_loc = batch_size // self.world
+        st, smp = self.local.storage, self.local.sampler
+        smp._maybe_init_from_storage(st)
+        length = len(st)
+        if length == 0:
+            raise RuntimeError("Cannot sample from an empty storage.")
+        be = ops.backend()
+        dev = smp._sum_tree.device
+        with self.local._replay_lock:
+            u = torch.rand(b_loc, device=dev, generator=smp._rng, dtype=smp._sum_tree._dtype)
+            idx, _, leaf, pp = be.per_sample(smp._sum_tree.values, smp._min_tree.values, smp._max_capacity,
+                                             smp._sum_tree.capacity, length, u, smp._beta, smp._semantics == "cpu",
+                                             status=smp._status, want_aux=True)
+            if self._layout is None:
+                self._layout = _PackedLayout(st._leaves)
+            lay = self._layout
+            send = torch.empty((b_loc, lay.row), dtype=torch.uint8, device=dev)
+            be.gather(st._leaves, idx, length, out=lay.leaf_views(send))
+        gidx, pi, S, m = lay.meta_views(send)
+        gidx.copy_(idx + self.rank * self.shard_capacity)
+        pi.copy_(leaf)
+        S.copy_(pp[0].expand(b_loc))
+        m.copy_(pp[1].expand(b_loc))
+        self.local_index = idx
+        if self.world > 1:
+            recv = torch.empty((batch_size, lay.row), dtype=torch.uint8, device=dev)
+            self._dist.all_gather_into_tensor(recv, send, group=self.group)  # the ONE collective of sample()
+        else:
+            recv = send
+        leaves = lay.leaf_views(recv)
+        gidx, pi, S, m = lay.meta_views(recv)
+        batch = unflatten_data(leaves, st._spec, (batch_size,))
+        # importance weights normalised over the whole (sharded) buffer; identical on every rank
+        ratio = pi / S
+        weight = torch.pow(ratio / (m / S).min(), -smp._beta)
+        if is_tensor_collection(batch):
+            batch.set("index", gidx)
+            batch.set("priority_weight", weight)
+            return batch
+        return batch, {"index": gidx, "priority_weight": weight}
+
+    # ---- priority write-back ---------------------------------------------------------------------------
+    def update_priority(self, index: torch.Tensor, priority) -> None:
+        """``index`` holds GLOBAL indices; entries owned by other ranks are skipped inside the kernel."""
+        index = torch.as_tensor(index, dtype=torch.long, device=self.device)
+        lo = self.rank * self.shard_capacity
+        local = index - lo
+        local = torch.where((local >= 0) & (local < self.shard_capacity), local, local.new_full((), -1))
+        self.local.update_priority(local, priority)
+
+    def update_tensordict_priority(self, data) -> None:
+        priority = data.get(self.local.priority_key)
+        if priority.ndim > 1:
+            priority = priority.reshape(priority.shape[0], -1).max(dim=1)[0]
+        self.update_priority(data.get("index"), priority)

@@ -47,6 +47,8 @@ def unflatten_data(leaves: Sequence[torch.Tensor], spec: tuple, batch_size) -> A
         return leaves[0]
     if kind == "td":
         cls = spec[2]
+        if cls is TensorDict:
+            return TensorDict._from_leaves(spec[1], leaves, batch_size)
         try:
             out = cls({}, batch_size=list(batch_size))
         except Exception:  # a foreign TensorDictBase subclass we cannot construct
@@ -314,6 +316,7 @@ class TensorStorage(Storage):
         self._storage = storage
         self._leaves: list | None = None
         self._spec = None
+        self._plan = None
         self._last_cursor = None
         self._status = None
         if storage is not None:
@@ -322,6 +325,7 @@ class TensorStorage(Storage):
     # ---- layout ------------------------------------------------------------------------------------
     def _bind(self, storage) -> None:
         self._leaves, self._spec = flatten_data(storage)
+        self._plan = None
         self._total_shape_value = torch.Size(self._leaves[0].shape[: self.ndim])
         if self.ndim > 1:
             self.max_size = self._total_shape_value.numel()
@@ -481,17 +485,21 @@ class TensorStorage(Storage):
             out = be.gather(leaves, lin.reshape(-1), length, status=self._status)
             out = [o.reshape(*lin.shape, *o.shape[1:]) for o in out]
             return unflatten_data(out, self._spec, lin.shape)
-        index = torch.as_tensor(index)
-        if index.dtype == torch.bool:
-            index = index.nonzero().squeeze(-1)
-        index = index.to(device=self._leaves[0].device, dtype=torch.long)
+        if not (isinstance(index, torch.Tensor) and index.dtype == torch.int64 and index.device == self._leaves[0].device):
+            index = torch.as_tensor(index)
+            if index.dtype == torch.bool:
+                index = index.nonzero().squeeze(-1)
+            index = index.to(device=self._leaves[0].device, dtype=torch.long)
         if self.ndim > 1:
             # a 1-d tensor index on a multi-dim storage selects whole dim-0 slabs: plain torch indexing
             out = [leaf[:n0][index] for leaf in self._leaves]
             return unflatten_data(out, self._spec, out[0].shape[: index.ndim + self.ndim - 1])
-        out = be.gather(self._leaves, index.reshape(-1), n0, status=self._status)
-        if index.ndim != 1:
-            out = [o.reshape(*index.shape, *o.shape[1:]) for o in out]
+        if self._plan is None:
+            self._plan = be.gather_plan(self._leaves)
+        if index.ndim == 1:
+            return unflatten_data(self._plan.run(index, n0, status=self._status), self._spec, index.shape)
+        out = self._plan.run(index.reshape(-1), n0, status=self._status)
+        out = [o.reshape(*index.shape, *o.shape[1:]) for o in out]
         return unflatten_data(out, self._spec, index.shape)
 
     def enable_index_check(self, enabled: bool = True) -> None:

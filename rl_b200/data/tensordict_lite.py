@@ -38,6 +38,28 @@ class TensorDict:
         for k, v in (source or {}).items():
             self.set(k, v)
 
+    @classmethod
+    def _from_leaves(cls, keys, leaves, batch_size) -> "TensorDict":
+        """Trusted fast constructor: nested keys (str | tuple) + leaves that already share `batch_size`."""
+        out = cls.__new__(cls)
+        out._data = {}
+        out._device = None
+        out._batch_size = batch_size if isinstance(batch_size, torch.Size) else torch.Size(batch_size)
+        for k, v in zip(keys, leaves):
+            if isinstance(k, str):
+                out._data[k] = v
+                continue
+            node = out
+            for part in k[:-1]:
+                nxt = node._data.get(part)
+                if nxt is None:
+                    nxt = cls.__new__(cls)
+                    nxt._data, nxt._device, nxt._batch_size = {}, None, out._batch_size
+                    node._data[part] = nxt
+                node = nxt
+            node._data[k[-1]] = v
+        return out
+
     # ---- metadata
     @property
     def batch_size(self) -> torch.Size:

@@ -43,7 +43,7 @@ _SIGNATURES = {
     "rlb_per_sample": (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _vp, _i64, _f64, _i32, _vp, _vp, _vp, _vp,
                                _vp, _vp]),
     "rlb_per_update": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _f64, _f64, _vp, _vp, _vp, _sz, _u32, _vp]),
-    "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
 }
@@ -233,18 +233,18 @@ class CudaBackend:
         n = index.numel()
         scalar = int(priority.numel() == 1)
         index, priority = index.contiguous(), priority.contiguous()
-        scratch = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        scratch = torch.empty(n, dtype=torch.float32, device=dev) if n > 1024 else None
         with self._Guard(dev):
             self._check(self.L.rlb_per_update(
                 self._p(sum_tree), self._p(min_tree), capacity, index.data_ptr(), priority.data_ptr(), n, scalar,
-                float(alpha), float(eps), scratch.data_ptr(), self._p(max_out), self._p(workspace),
+                float(alpha), float(eps), self._p(scratch), self._p(max_out), self._p(workspace),
                 0 if workspace is None else workspace.numel() * 8, epoch & 0xFFFFFFFF, self._stream(dev)),
                 "rlb_per_update")
 
     # -- storage rows ------------------------------------------------------------------------------
-    def _rows(self, fn, who, big: Sequence[torch.Tensor], small: Sequence[torch.Tensor], index: torch.Tensor,
-              length: int, status, extra):
-        """big[k] is the [N, ...] storage leaf, small[k] the [B, ...] batch leaf."""
+    def _rows(self, who, big: Sequence[torch.Tensor], small: Sequence[torch.Tensor], index: torch.Tensor,
+              length: int, status, mode: int = GATHER_AUTO):
+        """big[k] is the [N, ...] storage leaf, small[k] the [B, ...] batch leaf (rows may be strided)."""
         dev = self._cuda(index, status, *big, *small)
         if index.dtype != torch.int64:
             raise RuntimeError("index must be an int64 tensor")
@@ -255,29 +255,40 @@ class CudaBackend:
                 bs, ss = big[lo:lo + MAX_LEAVES], small[lo:lo + MAX_LEAVES]
                 n = len(bs)
                 P, I = ctypes.c_void_p * n, ctypes.c_int64 * n
-                rowb = [s.element_size() * (s.numel() // max(B, 1)) for s in ss]
-                stride = [b.stride(0) * b.element_size() for b in bs]
+                rowb = I(*[b.element_size() * (b[0].numel() if b.ndim > 1 else 1) for b in bs])
+                bstride = I(*[b.stride(0) * b.element_size() for b in bs])
+                sstride = I(*[(s.stride(0) if s.ndim > 0 and s.shape[0] > 1 else (s[0].numel() if s.ndim > 1 else 1))
+                              * s.element_size() for s in ss])
                 bigp, smallp = P(*[b.data_ptr() for b in bs]), P(*[s.data_ptr() for s in ss])
-                src, dst = (bigp, smallp) if who == "rlb_gather" else (smallp, bigp)
-                self._check(fn(src, dst, I(*rowb), I(*stride), n, index.data_ptr(), B, length, *extra,
-                               self._p(status), self._stream(dev)), who)
+                if who == "rlb_gather":
+                    rc = self.L.rlb_gather(bigp, smallp, rowb, bstride, sstride, n, index.data_ptr(), B, length, mode,
+                                           self._p(status), self._stream(dev))
+                else:
+                    rc = self.L.rlb_scatter(smallp, bigp, rowb, bstride, n, index.data_ptr(), B, length,
+                                            self._p(status), self._stream(dev))
+                self._check(rc, who)
+
+    @staticmethod
+    def _check_rows(t: torch.Tensor) -> None:
+        if t.ndim < 1 or (t.ndim > 1 and t.shape[0] > 0 and not t[0].is_contiguous()):
+            raise RuntimeError("leaves must be [N, ...] tensors whose rows are contiguous")
 
     def gather(self, leaves: Sequence[torch.Tensor], index: torch.Tensor, length: int, mode: int = GATHER_AUTO,
-               status: torch.Tensor | None = None) -> list[torch.Tensor]:
-        B = index.numel()
-        for t in leaves:
-            if t.ndim < 1 or (t.ndim > 1 and not t[0].is_contiguous()):
-                raise RuntimeError("storage leaves must be [N, ...] with contiguous rows")
-        outs = [torch.empty((B, *t.shape[1:]), dtype=t.dtype, device=t.device) for t in leaves]
-        if B:
-            self._rows(self.L.rlb_gather, "rlb_gather", leaves, outs, index, length, status, (mode,))
-        return outs
+               status: torch.Tensor | None = None, out: Sequence[torch.Tensor] | None = None) -> list[torch.Tensor]:
+        """out[k][b] = leaves[k][index[b]].  `out` may be given (rows may be strided views into a packed buffer)."""
+        return self.gather_plan(leaves).run(index, length, mode=mode, status=status, out=out)
+
+    def gather_plan(self, leaves: Sequence[torch.Tensor]) -> "GatherPlan":
+        """Pre-marshalled source side of rlb_gather for a fixed set of storage leaves (pointers, row sizes and
+        strides do not change between samples); storages cache it."""
+        return GatherPlan(self, leaves)
 
     def scatter(self, leaves: Sequence[torch.Tensor], data: Sequence[torch.Tensor], index: torch.Tensor, length: int,
                 status: torch.Tensor | None = None) -> None:
         if index.numel():
-            self._rows(self.L.rlb_scatter, "rlb_scatter", leaves, [d.contiguous() for d in data], index, length,
-                       status, ())
+            for t in leaves:
+                self._check_rows(t)
+            self._rows("rlb_scatter", leaves, [d.contiguous() for d in data], index, length, status)
 
     # -- GAE ---------------------------------------------------------------------------------------
     def gae(self, v, nv, r, done, term, gamma: float, gammalmbda: float, rows: int, T: int, F: int):
@@ -288,6 +299,61 @@ class CudaBackend:
                                        float(gamma), float(gammalmbda), rows, T, F, _dtype_code(v.dtype),
                                        adv.data_ptr(), tgt.data_ptr(), self._stream(dev)), "rlb_gae")
         return adv, tgt
+
+
+class GatherPlan:
+    """Source-side arguments of ``rlb_gather`` marshalled once for a set of [N, ...] leaves."""
+
+    def __init__(self, be: CudaBackend, leaves: Sequence[torch.Tensor]):
+        self.be = be
+        self.leaves = list(leaves)
+        for t in self.leaves:
+            be._check_rows(t)
+        self.dev = be._cuda(*self.leaves)
+        self.tails = [tuple(t.shape[1:]) for t in self.leaves]
+        self.dtypes = [t.dtype for t in self.leaves]
+        self.chunks = []
+        for lo in range(0, len(self.leaves), MAX_LEAVES):
+            ts = self.leaves[lo:lo + MAX_LEAVES]
+            n = len(ts)
+            P, I = ctypes.c_void_p * n, ctypes.c_int64 * n
+            rowb = [t.element_size() * (t[0].numel() if t.ndim > 1 else 1) for t in ts]
+            self.chunks.append((lo, n, P, P(*[t.data_ptr() for t in ts]), I(*rowb),
+                                I(*[t.stride(0) * t.element_size() for t in ts]), I))
+
+    def run(self, index: torch.Tensor, length: int, mode: int = GATHER_AUTO, status: torch.Tensor | None = None,
+            out: Sequence[torch.Tensor] | None = None) -> list[torch.Tensor]:
+        be = self.be
+        if not index.is_cuda or index.device != self.dev:
+            raise RuntimeError(f"rl_b200: index must live on {self.dev}, got {index.device}; there is no CPU path.")
+        if index.dtype != torch.int64:
+            raise RuntimeError("index must be an int64 tensor")
+        if not index.is_contiguous():
+            index = index.contiguous()
+        B = index.numel()
+        dev = self.dev
+        strided = out is not None
+        if out is None:
+            out = [torch.empty((B, *tail), dtype=dt, device=dev) for tail, dt in zip(self.tails, self.dtypes)]
+        else:
+            for o, tail, dt in zip(out, self.tails, self.dtypes):
+                be._check_rows(o)
+                if tuple(o.shape) != (B, *tail) or o.dtype != dt or o.device != dev:
+                    raise RuntimeError("gather: `out` leaf has the wrong shape, dtype or device")
+        if B == 0:
+            return list(out)
+        stream = be._stream(dev)
+        with be._Guard(dev):
+            for lo, n, P, srcp, rowb, sstride, I in self.chunks:
+                outs = out[lo:lo + n]
+                dstp = P(*[o.data_ptr() for o in outs])
+                dstride = None
+                if strided:
+                    dstride = I(*[(o.stride(0) if B > 1 else (o[0].numel() if o.ndim > 1 else 1)) * o.element_size()
+                                  for o in outs])
+                be._check(be.L.rlb_gather(srcp, dstp, rowb, sstride, dstride, n, index.data_ptr(), B, length, mode,
+                                          be._p(status), stream), "rlb_gather")
+        return list(out)
 
 
 _BACKEND = None

@@ -147,13 +147,27 @@ class OracleBackend:
         self.tree_update(sum_tree, min_tree, capacity, index, leaf, workspace, epoch)
 
     # ---- storage rows
-    def gather(self, leaves, index, length, mode=0, status=None):
+    def gather(self, leaves, index, length, mode=0, status=None, out=None):
         ix = torch.where(index < 0, index + length, index)
         if ((ix < 0) | (ix >= length)).any():
             if status is not None:
                 status |= 1
             ix = ix.clamp(0, length - 1)
-        return [t[ix] for t in leaves]
+        res = [t[ix] for t in leaves]
+        if out is not None:
+            for o, r in zip(out, res):
+                o.copy_(r)
+            return list(out)
+        return res
+
+    def gather_plan(self, leaves):
+        be = self
+
+        class _Plan:
+            def run(self, index, length, mode=0, status=None, out=None):
+                return be.gather(leaves, index, length, mode=mode, status=status, out=out)
+
+        return _Plan()
 
     def scatter(self, leaves, data, index, length, status=None):
         ix = torch.where(index < 0, index + length, index)

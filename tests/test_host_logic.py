@@ -1,0 +1,358 @@
+"""Host-side logic of the TorchRL-facing mirror (cursors, lengths, key plumbing, bookkeeping quirks, error
+behaviour), exercised on CPU with the oracle-backed emulator standing in for the CUDA library
+(tests/_emul.py).  The arithmetic itself is checked on the GPU in tests/test_gpu_kernels.py; here the
+expected values come from the compiled reference trees / the restated reference glue (oracle/)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import per_oracle as po
+from rl_b200 import ops
+from rl_b200.data import (LazyTensorStorage, ListStorage, PrioritizedReplayBuffer, PrioritizedSampler, RandomSampler,
+                          ReplayBuffer, RoundRobinWriter, TensorDict, TensorDictPrioritizedReplayBuffer,
+                          TensorDictReplayBuffer, TensorStorage)
+from rl_b200.objectives.value import GAE, vec_generalized_advantage_estimate
+
+
+# ------------------------------------------------------------------------------------------- C1 plumbing
+def test_config1_liststorage_randomsampler_cartpole():
+    """BASELINE configs[0]: ListStorage + RandomSampler, 10k cap, CartPole-shaped, batch 32, CPU.  Pure host
+    plumbing -- no kernel is involved, so it runs without any backend."""
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(0)
+    rb = ReplayBuffer(storage=ListStorage(10_000), sampler=RandomSampler(), batch_size=32, generator=g)
+    items = [TensorDict({"obs": torch.randn(4), "action": torch.randint(0, 2, (1,))}, []) for _ in range(500)]
+    for it in items[:10]:
+        rb.add(it)
+    idx = rb.extend(items[10:])
+    assert len(rb) == 500 and idx.tolist() == list(range(10, 500))
+    batch, info = rb.sample(return_info=True)
+    assert batch.batch_size == torch.Size([32])
+    assert batch.get("obs").shape == (32, 4) and batch.get("action").dtype == torch.int64
+    want = torch.stack([items[i].get("obs") for i in info["index"].tolist()])
+    assert torch.equal(batch.get("obs"), want)
+    # same generator state => same indices (test/rb/test_rb_core.py:113-131 style)
+    g.manual_seed(5)
+    a = rb.sample(return_info=True)[1]["index"]
+    g.manual_seed(5)
+    b = rb.sample(return_info=True)[1]["index"]
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="batch_size not specified"):
+        ReplayBuffer(storage=ListStorage(10)).sample()
+    with pytest.raises(RuntimeError, match="Cannot sample from an empty storage"):
+        ReplayBuffer(storage=ListStorage(10), batch_size=2).sample()
+
+
+def test_liststorage_semantics():
+    st = ListStorage(3)
+    st.set(0, "a")
+    st.set(1, "b")
+    with pytest.raises(RuntimeError, match="more than one item away"):
+        st.set(3, "d")
+    st.set(2, "c")
+    with pytest.raises(RuntimeError, match="maximum capacity"):
+        st.set(3, "d")
+    assert st.get([0, 2]) == ["a", "c"] and st.get(torch.tensor([1])) == ["b"] and len(st) == 3
+    rb = ReplayBuffer(storage=ListStorage(5), batch_size=2)
+    rb.extend(list(range(7)))  # wraps round-robin
+    assert rb.storage._storage == [5, 6, 2, 3, 4]
+
+
+def test_no_cpu_fallback_in_product_path():
+    """Without the emulator a tensor-index read of a TensorStorage must fail loudly on this GPU-less box."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ops.set_backend(None)
+    st = TensorStorage(torch.arange(10.0))
+    assert st.get(3) == 3.0  # views need no kernel
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        st.get(torch.tensor([1, 2]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PrioritizedSampler(10, 0.6, 0.4, device="cpu")
+
+
+# ------------------------------------------------------------------------------------------- storages / writers
+def test_lazy_tensor_storage_bookkeeping(emul):
+    st = LazyTensorStorage(10, device="cpu")
+    assert len(st) == 0 and not st.initialized
+    with pytest.raises(RuntimeError, match="non-initialized"):
+        st.get(0)
+    w = RoundRobinWriter()
+    w.register_storage(st)
+    data = TensorDict({"a": torch.arange(6.0).reshape(6, 1), "n": {"b": torch.arange(6)}}, [6])
+    idx = w.extend(data)
+    assert idx.tolist() == list(range(6)) and len(st) == 6 and w._cursor == 6 and w._write_count == 6
+    assert st.shape == torch.Size([6]) and not st._is_full
+    idx = w.extend(data)  # wraps: 6..9, 0, 1  -> scatter path
+    assert idx.tolist() == [6, 7, 8, 9, 0, 1] and len(st) == 10 and w._cursor == 2 and st._is_full
+    got = st.get(torch.tensor([0, 1, 2, 6, 9]))
+    assert got.get(("n", "b")).tolist() == [4, 5, 2, 0, 3]
+    assert got.batch_size == torch.Size([5])
+    assert st.get(slice(0, 3)).get("a").squeeze(-1).tolist() == [4.0, 5.0, 2.0]
+    assert st[7].get(("n", "b")).item() == 1
+    # negative indices wrap by len (torch indexing semantics)
+    assert st.get(torch.tensor([-1])).get(("n", "b")).item() == 3
+    st._empty()
+    assert len(st) == 0
+    # pytree (tuple) storage and plain tensors
+    st2 = LazyTensorStorage(8, device="cpu")
+    rb = ReplayBuffer(storage=st2, batch_size=4)
+    rb.extend((torch.arange(5), torch.arange(5.0).unsqueeze(-1)))
+    out = rb[torch.tensor([4, 0])]
+    assert isinstance(out, tuple) and out[0].tolist() == [4, 0] and out[1].shape == (2, 1)
+    st3 = TensorStorage(torch.arange(12.0).reshape(6, 2))
+    assert len(st3) == 6 and torch.equal(st3.get(torch.tensor([5, 0])), torch.tensor([[10.0, 11.0], [0.0, 1.0]]))
+    with pytest.raises(ValueError, match="max-size and the storage shape mismatch"):
+        TensorStorage(torch.zeros(4), max_size=5)
+
+
+def test_shared_storage_prioritized_sampler(emul):
+    """test/rb/test_rb_core.py:577-601: a second buffer on the same storage sees the writes (mark_update)."""
+    n = 100
+    storage = LazyTensorStorage(n, device="cpu")
+    writer = RoundRobinWriter()
+    rb0 = ReplayBuffer(storage=storage, writer=writer, sampler=RandomSampler(), batch_size=10)
+    rb1 = ReplayBuffer(storage=storage, writer=writer, sampler=PrioritizedSampler(max_capacity=n, alpha=0.7, beta=1.1),
+                       batch_size=10)
+    rb0.extend(TensorDict({"a": torch.arange(50)}, [50]))
+    assert len(rb0) == 50 and len(storage) == 50 and len(rb1) == 50
+    rb0.sample()
+    rb1.sample()
+    assert rb1._sampler._sum_tree.query(0, 10) == 10
+    assert rb1._sampler._sum_tree.query(0, 50) == 50
+    assert rb1._sampler._sum_tree.query(0, 70) == 50
+
+
+# ------------------------------------------------------------------------------------------- PER glue vs reference
+def _oracle_sampler(N, alpha, beta, ref_cpu=True):
+    from oracle.ref_loader import reference_trees
+
+    f = reference_trees("cpu") if ref_cpu else None
+    return po.OraclePrioritizedSampler(N, alpha, beta, tree_factory=f)
+
+
+def test_prioritized_buffer_matches_reference_glue(emul, ref_cpu):
+    """extend (default priorities + td_error write-back), sample under a fixed seed, update_tensordict_priority:
+    indices, weights and tree leaves equal the reference sampler glue over the compiled reference trees."""
+    N, B = 2000, 128
+    alpha, beta = 0.6, 0.4
+    g = torch.Generator().manual_seed(3)
+    rb = TensorDictPrioritizedReplayBuffer(alpha=alpha, beta=beta, storage=LazyTensorStorage(N, device="cpu"),
+                                           batch_size=B, generator=g)
+    ref = _oracle_sampler(N, alpha, beta)
+    gd = torch.Generator().manual_seed(11)
+    for n in (700, 900, 650):  # the last one wraps around
+        td_err = torch.rand(n, generator=gd) * 3
+        data = TensorDict({"obs": torch.randn(n, 4, generator=gd), "td_error": td_err}, [n])
+        cur = rb.writer._cursor
+        idx = rb.extend(data)
+        want_idx = torch.arange(cur, cur + n) % N
+        assert torch.equal(idx, want_idx) and torch.equal(data.get("index"), want_idx)
+        ref.mark_update(want_idx)               # writer -> mark_update            (writers.py:232-235)
+        ref.update_priority(want_idx, td_err)   # then the td_error of the new data (replay_buffers.py:1903-1907)
+    smp = rb.sampler
+    np.testing.assert_array_equal(smp._sum_tree.dump_leaves().numpy(), ref._sum_tree[np.arange(N)])
+    np.testing.assert_array_equal(smp._min_tree.dump_leaves().numpy(), ref._min_tree[np.arange(N)])
+    assert float(smp._max_priority[0]) == float(ref._max_priority)
+    assert float(smp.default_priority) == float(ref.default_priority)
+    for _ in range(3):
+        state = g.get_state()
+        sample = rb.sample()
+        g2 = torch.Generator()
+        g2.set_state(state)
+        want_idx, want_w = ref.sample(len(rb), B, generator=g2)
+        assert torch.equal(sample.get("index"), want_idx)
+        assert torch.equal(sample.get("priority_weight"), want_w)
+        assert torch.equal(sample.get("obs"), rb.storage.get(slice(None)).get("obs")[want_idx])
+        new_td = torch.rand(B, generator=gd) * 2
+        sample.set("td_error", new_td)
+        rb.update_tensordict_priority(sample)
+        ref.update_priority(want_idx, new_td)
+        np.testing.assert_array_equal(smp._sum_tree.values.numpy()[1:2], [np.float32(ref._sum_tree.query(0, N))])
+
+
+def test_double_pow_quirk_and_default_priority(emul):
+    rb = ReplayBuffer(storage=LazyTensorStorage(8, device="cpu"),
+                      sampler=PrioritizedSampler(8, alpha=0.6, beta=0.4), batch_size=2)
+    assert rb.sampler.default_priority == (1 + 1e-8) ** 0.6
+    idx = rb.extend(torch.arange(2.0))
+    rb.update_priority(idx[:1], torch.tensor([4.0]))
+    rb.extend(torch.arange(1.0))  # new item gets ((4+eps)^a + eps)^a, not (4+eps)^a   (SURVEY 8a')
+    leaves = rb.sampler._sum_tree.dump_leaves()
+    np.testing.assert_allclose(leaves[[0, 2]].numpy(), [2.29740, 1.64718], rtol=1e-5)
+    assert float(rb.sampler._max_priority[0]) == 4.0
+
+
+def test_prb_update_max_priority(emul):
+    """test/rb/test_samplers.py:1152-1188 (value part; the argmax index is only kept with
+    max_priority_within_buffer=True, like the reference's CUDA branch)."""
+    for within in (True, False):
+        rb = ReplayBuffer(storage=LazyTensorStorage(11, device="cpu"),
+                          sampler=PrioritizedSampler(max_capacity=11, alpha=1.0, beta=1.0,
+                                                     max_priority_within_buffer=within))
+        for data in torch.arange(20):
+            idx = rb.add(data)
+            rb.update_priority(idx, 21 - data)
+            if data <= 10 or not within:
+                assert rb.sampler._max_priority[0] == 21
+            else:
+                leaves = rb.sampler._sum_tree.dump_leaves()
+                assert rb.sampler._max_priority[0] == leaves.max()
+                assert rb.sampler._max_priority[1] == leaves.argmax()
+        idx = rb.extend(torch.arange(10))
+        rb.update_priority(idx, 12)
+        assert rb.sampler._max_priority[0] == (12 if within else 21)
+
+
+def test_priority_weight_formula(emul):
+    """test/rb/test_prioritized.py:278-338: priority_weight == ((p+eps)^alpha / min)^(-beta), obs == index."""
+    size, B, alpha, beta, eps = 64, 16, 0.7, 0.5, 1e-8
+    pr = torch.linspace(0.1, 2.0, size)
+    tree_p = (pr + eps).pow(alpha)
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(size, device="cpu"),
+                                sampler=PrioritizedSampler(size, alpha, beta, eps, device="cpu"), batch_size=B,
+                                priority_key="td_error")
+    rb.extend(TensorDict({"obs": torch.arange(size), "td_error": pr}, [size]))
+    for _ in range(8):
+        s = rb.sample()
+        i = s.get("index")
+        torch.testing.assert_close(s.get("obs"), i)
+        torch.testing.assert_close(s.get("td_error"), pr[i])
+        torch.testing.assert_close(s.get("priority_weight"), (tree_p[i] / tree_p.min()).pow(-beta))
+
+
+def test_prb_rng(emul):
+    """test/rb/test_rb_core.py:113-131: same generator state => identical PER sample."""
+    g = torch.Generator().manual_seed(0)
+    rb = PrioritizedReplayBuffer(alpha=0.7, beta=0.9, storage=LazyTensorStorage(50, device="cpu"), batch_size=8,
+                                 generator=g)
+    rb.extend(torch.arange(50.0))
+    rb.update_priority(torch.arange(50), torch.rand(50))
+    st = g.get_state()
+    a = rb.sample()
+    b = rb.sample()
+    g.set_state(st)
+    c = rb.sample()
+    assert torch.equal(a, c) and not torch.equal(a, b)
+
+
+def test_update_priority_shapes_and_negative_index(emul):
+    smp = PrioritizedSampler(16, 1.0, 1.0, device="cpu")
+    smp.update_priority(torch.arange(4), 2.0)                       # scalar priority
+    smp.update_priority(3, torch.tensor(5.0))                        # int index, 0-d priority
+    smp.update_priority(torch.tensor([5, -1, 6]), torch.tensor([1.0, 100.0, 3.0]))  # -1 = skip
+    leaves = smp._sum_tree.dump_leaves()
+    assert leaves[:7].tolist() == pytest.approx([2, 2, 2, 5, 0, 1, 3], rel=1e-6)
+    assert float(smp._max_priority[0]) == 5.0   # the skipped 100 must not count
+    with pytest.raises(RuntimeError, match="priority should be a number or an iterable"):
+        smp.update_priority(torch.arange(4), torch.ones(3))
+    with pytest.raises(ValueError, match="alpha must be greater or equal than 0"):
+        PrioritizedSampler(4, -1.0, 1.0)
+    with pytest.raises(ValueError, match="beta must be greater or equal to 0"):
+        PrioritizedSampler(4, 1.0, -1.0)
+
+
+def test_sampler_dumps_loads_reference_layout(emul, tmp_path):
+    """On-disk layout of samplers.py:1120-1204: float64 leaves memmaps + json metadata."""
+    smp = PrioritizedSampler(37, 0.6, 0.4, device="cpu")
+    smp.update_priority(torch.arange(30), torch.rand(30) + 0.1)
+    smp.dumps(tmp_path / "s")
+    mm = np.memmap(tmp_path / "s" / "sumtree.memmap", dtype=np.float64, mode="r", shape=(37,))
+    np.testing.assert_array_equal(np.asarray(mm), smp._sum_tree.dump_leaves().double().numpy())
+    other = PrioritizedSampler(37, 0.1, 0.1, device="cpu")
+    other.loads(tmp_path / "s")
+    assert torch.equal(other._sum_tree.values[1:], smp._sum_tree.values[1:])
+    assert torch.equal(other._min_tree.values[1:], smp._min_tree.values[1:])
+    assert other.alpha == 0.6 and float(other._max_priority[0]) == float(smp._max_priority[0])
+    sd = smp.state_dict()
+    third = PrioritizedSampler(37, 0.6, 0.4, device="cpu")
+    third.load_state_dict(sd)
+    assert torch.equal(third._sum_tree.values[1:], smp._sum_tree.values[1:])
+
+
+def test_buffer_dumps_loads(emul, tmp_path):
+    g = torch.Generator().manual_seed(1)
+    mk = lambda: TensorDictPrioritizedReplayBuffer(alpha=0.6, beta=0.4, storage=LazyTensorStorage(20, device="cpu"),
+                                                   batch_size=5, generator=torch.Generator().manual_seed(1))
+    rb = mk()
+    rb.extend(TensorDict({"x": torch.randn(13, 3, generator=g), "td_error": torch.rand(13, generator=g)}, [13]))
+    rb.dumps(tmp_path / "rb")
+    rb2 = mk()
+    rb2.extend(TensorDict({"x": torch.zeros(1, 3), "td_error": torch.zeros(1)}, [1]))  # initialise the layout
+    rb2.loads(tmp_path / "rb")
+    assert len(rb2) == 13 and rb2.writer._cursor == 13
+    a, b = rb.sample(), rb2.sample()
+    assert torch.equal(a.get("index"), b.get("index")) and torch.equal(a.get("x"), b.get("x"))
+
+
+# ------------------------------------------------------------------------------------------- GAE plumbing
+def _gae_td(B, T, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    term = torch.rand(B, T, 1, generator=g) < 0.05
+    return TensorDict({
+        "state_value": torch.randn(B, T, 1, generator=g),
+        "next": {"state_value": torch.randn(B, T, 1, generator=g), "reward": torch.randn(B, T, 1, generator=g),
+                 "done": term | (torch.rand(B, T, 1, generator=g) < 0.05), "terminated": term},
+    }, [B, T])
+
+
+def test_gae_module_keys_and_values(emul, ref_funcs):
+    td = _gae_td(5, 40)
+    mod = GAE(gamma=0.99, lmbda=0.95, value_network=None)
+    out = mod(td)
+    assert out is td and td.get("advantage").shape == (5, 40, 1)
+    ra, rt = ref_funcs.generalized_advantage_estimate(
+        mod.gamma, mod.lmbda, td.get("state_value"), td.get(("next", "state_value")), td.get(("next", "reward")),
+        done=td.get(("next", "done")), terminated=td.get(("next", "terminated")))
+    assert torch.equal(td.get("advantage"), ra) and torch.equal(td.get("value_target"), rt)
+    # custom keys, average_gae, skip_existing
+    mod2 = GAE(gamma=0.9, lmbda=0.8, value_network=None, average_gae=True, skip_existing=True)
+    mod2.set_keys(advantage="adv", value_target=("tgt", "v"))
+    td2 = _gae_td(3, 17, 1)
+    mod2(td2)
+    assert abs(td2.get("adv").mean()) < 1e-5 and td2.get(("tgt", "v")).shape == (3, 17, 1)
+    before = td2.get("adv").clone()
+    td2.set(("next", "reward"), torch.zeros(3, 17, 1))
+    mod2(td2)  # skip_existing: untouched
+    assert torch.equal(td2.get("adv"), before)
+    with pytest.raises(ValueError, match="is missing, and no value network was provided"):
+        GAE(gamma=0.9, lmbda=0.9, value_network=None)(TensorDict({"next": {"reward": torch.zeros(2, 3, 1),
+                                                                        "done": torch.zeros(2, 3, 1, dtype=torch.bool)}},
+                                                                 [2, 3]))
+    with pytest.raises(NotImplementedError):
+        GAE(gamma=0.9, lmbda=0.9, value_network=None, differentiable=True)
+    # a critic callable is invoked on the data and on data["next"]
+    calls = []
+
+    def critic(t):
+        calls.append(1)
+        t.set("state_value", torch.ones(*t.batch_size, 1))
+
+    td3 = _gae_td(2, 6, 2)
+    GAE(gamma=0.99, lmbda=0.95, value_network=critic)(td3)
+    assert len(calls) == 2 and td3.get("value_target").shape == (2, 6, 1)
+
+
+def test_gae_functional_errors_and_time_dim(emul, ref_funcs):
+    v = torch.randn(4, 9, 1)
+    with pytest.raises(RuntimeError, match="must share a unique shape"):
+        vec_generalized_advantage_estimate(0.9, 0.9, v, v[:, :8], v, torch.zeros(4, 9, 1, dtype=torch.bool))
+    with pytest.raises(NotImplementedError, match="tensor-valued gamma"):
+        vec_generalized_advantage_estimate(torch.full((4, 9, 1), 0.9), 0.9, v, v, v,
+                                           torch.zeros(4, 9, 1, dtype=torch.bool))
+    g = torch.Generator().manual_seed(0)
+    v, nv, r = (torch.randn(6, 11, generator=g) for _ in range(3))
+    done = torch.rand(6, 11, generator=g) < 0.1
+    a, t = vec_generalized_advantage_estimate(0.99, 0.95, v, nv, r, done=done, time_dim=-1)
+    ra, rt = ref_funcs.generalized_advantage_estimate(0.99, 0.95, v, nv, r, done=done, time_dim=-1)
+    assert a.shape == (6, 11) and torch.equal(a, ra) and torch.equal(t, rt)
+    a, t = vec_generalized_advantage_estimate(0.99, 0.95, v.t().unsqueeze(-1), nv.t().unsqueeze(-1),
+                                              r.t().unsqueeze(-1), done=done.t().unsqueeze(-1), time_dim=0)
+    assert a.shape == (11, 6, 1) and torch.equal(a.squeeze(-1).t(), ra)
+    # python-float vs tensor gamma/lmbda are rounded the way the reference rounds them
+    from rl_b200.objectives.value.functional import gae_scalars
+
+    gm, gl = gae_scalars(torch.tensor(0.99), torch.tensor(0.95), torch.float32)
+    assert gl == float(torch.tensor(0.99) * torch.tensor(0.95))
+    gm2, gl2 = gae_scalars(0.99, 0.95, torch.float32)
+    assert gl2 == float(torch.tensor(0.99 * 0.95, dtype=torch.float32))

@@ -1,0 +1,124 @@
+"""world_size-2 (gloo, CPU) tests of the capacity-sharded buffer's host logic: per-rank draws are index-exact
+against the reference sampler glue on that shard, the gathered batch is the rank-order concatenation, weights
+are identical on every rank, and priority write-back only touches the owning shard."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from _emul import OracleBackend
+        from oracle import per_oracle as po
+        from rl_b200 import ops
+        from rl_b200.data import TensorDict
+        from rl_b200.data.sharded import ShardedPrioritizedReplayBuffer
+
+        ops.set_backend(OracleBackend())
+        cap, B, alpha, beta = 1000, 64, 0.6, 0.4
+        g = torch.Generator().manual_seed(100 + rank)
+        rb = ShardedPrioritizedReplayBuffer(alpha=alpha, beta=beta, capacity=cap, batch_size=B, device="cpu",
+                                            generator=g)
+        assert rb.shard_capacity == 500 and rb.world == world
+        gd = torch.Generator().manual_seed(7 + rank)
+        n = 300 + 50 * rank
+        data = TensorDict({"obs": torch.randn(n, 3, generator=gd), "frame": torch.randint(0, 255, (n, 2, 4), dtype=torch.uint8, generator=gd),
+                           "flag": torch.rand(n, 1, generator=gd) < 0.5, "td_error": torch.rand(n, generator=gd) * 2}, [n])
+        gidx = rb.extend(data)
+        assert gidx.tolist() == list(range(rank * 500, rank * 500 + n))
+        # reference glue on this shard
+        ref = po.OraclePrioritizedSampler(500, alpha, beta)
+        ref.mark_update(torch.arange(n))
+        ref.update_priority(torch.arange(n), data.get("td_error"))
+        state = g.get_state()
+        batch = rb.sample()
+        g2 = torch.Generator()
+        g2.set_state(state)
+        want_local, _ = ref.sample(n, B // world, generator=g2)
+        assert torch.equal(rb.local_index, want_local)                       # index-exact per shard
+        mine = {"index": want_local + rank * 500, "obs": data.get("obs")[want_local],
+                "frame": data.get("frame")[want_local], "flag": data.get("flag")[want_local],
+                "p": torch.as_tensor(ref._sum_tree[want_local.numpy()]),
+                "S": torch.tensor(ref._sum_tree.query(0, n)), "m": torch.tensor(ref._min_tree.query(0, n))}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        for key in ("index", "obs", "frame", "flag"):                          # rank-order concatenation
+            assert torch.equal(batch.get(key), torch.cat([e[key] for e in everyone])), key
+        assert batch.get("frame").dtype == torch.uint8 and batch.get("flag").dtype == torch.bool
+        p = torch.cat([e["p"] for e in everyone])
+        S = torch.cat([e["S"].expand(B // world) for e in everyone])
+        mn = min(float(e["m"] / e["S"]) for e in everyone)
+        want_w = torch.pow((p / S) / mn, -beta)
+        torch.testing.assert_close(batch.get("priority_weight"), want_w, rtol=1e-6, atol=0)
+        ws = [None] * world
+        dist.all_gather_object(ws, batch.get("priority_weight"))
+        assert all(torch.equal(ws[0], w) for w in ws)                          # identical on every rank
+        # write-back with GLOBAL indices: only the owner changes
+        before = rb.sampler._sum_tree.dump_leaves().clone()
+        new_p = torch.full((B,), 5.0)
+        rb.update_priority(batch.get("index"), new_p)
+        after = rb.sampler._sum_tree.dump_leaves()
+        own = (batch.get("index") // 500) == rank
+        touched = torch.zeros(500, dtype=torch.bool)
+        touched[(batch.get("index")[own] - rank * 500)] = True
+        assert torch.equal(after[~touched], before[~touched])
+        assert torch.allclose(after[touched], torch.tensor(5.0 + 1e-8) ** alpha)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()))
+
+
+def test_sharded_two_ranks_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
+def test_sharded_single_process(emul):
+    """World size 1: the sharded buffer degenerates to the plain prioritized buffer (weights = (p/p_min)^-beta)."""
+    from rl_b200.data import LazyTensorStorage, TensorDict, TensorDictPrioritizedReplayBuffer
+    from rl_b200.data.sharded import ShardedPrioritizedReplayBuffer
+
+    mk = lambda: torch.Generator().manual_seed(5)
+    data = TensorDict({"x": torch.randn(200, 5), "td_error": torch.rand(200)}, [200])
+    a = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=256, batch_size=32, device="cpu", generator=mk())
+    b = TensorDictPrioritizedReplayBuffer(alpha=0.6, beta=0.4, storage=LazyTensorStorage(256, device="cpu"),
+                                          batch_size=32, generator=mk())
+    a.extend(data.clone())
+    b.extend(data.clone())
+    sa, sb = a.sample(), b.sample()
+    assert torch.equal(sa.get("index"), sb.get("index")) and torch.equal(sa.get("x"), sb.get("x"))
+    torch.testing.assert_close(sa.get("priority_weight"), sb.get("priority_weight"), rtol=1e-6, atol=0)
