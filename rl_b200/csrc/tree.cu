@@ -323,49 +323,19 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
 // ------------------------------------------------------------------------------------------------
 // update: single-CTA path (n <= 1024)
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kEmptyKey = 0xffffffffu;
-
-template <typename T>
-struct alignas(8) UpdSlot {
-  uint32_t key;  // parent node id (leaf node id for the dedupe round); kEmptyKey = free
-  uint32_t aux;  // levels: bit s set <=> child s deposited; dedupe round: 1 + max input position
-  T s[2];        // sum-tree value of child 0 / 1
-  T m[2];        // min-tree value of child 0 / 1
-};
-
-template <typename T>
-__device__ __forceinline__ uint32_t upd_probe_insert(UpdSlot<T> *tab, uint32_t mask, int log2_slots, uint32_t key,
-                                                     bool &owner) {
-  uint32_t h = (key * 0x9E3779B1u) >> (32 - log2_slots);
-  for (;;) {
-    const uint32_t prev = atomicCAS(&tab[h].key, kEmptyKey, key);
-    if (prev == kEmptyKey) {
-      owner = true;
-      return h;
-    }
-    if (prev == key) {
-      owner = false;
-      return h;
-    }
-    h = (h + 1) & mask;
-  }
-}
-
-// One thread per batch item.  Round "-1" elects, per distinct leaf, the item with the largest input
-// position (last-writer-wins, csrc/segment_tree.h:222-226 / cuda_segment_tree.cu:32-37).  Then for each
-// level a carrier thread deposits its node's (sum, min) value in the hash slot of the parent; the
-// thread that created the slot carries the parent upward, combining the two children in (left, right)
-// order; an untouched sibling comes from its global value.  Those sibling reads are the only global
-// round trips on the critical path, so every path's siblings are pulled into L2 up front
-// (prefetch.global.L2, fire and forget) and each level's sibling is loaded one level ahead of its use.
-// Two tables alternate so a fast thread's inserts for level k+1 never race with a slow thread's
-// read+clear of level k.
+// Sorted-merge climb.  The batch is sorted by leaf (bitonic, in shared memory; ties broken so that the
+// LAST input position comes first and wins -- csrc/segment_tree.h:222-226 / cuda_segment_tree.cu:32-37)
+// and compacted to the m distinct leaves.  Item j's root path coincides with its left neighbour's from
+// level L_j = bitlength(key_j ^ key_{j-1}) upwards, so j carries its own nodes for levels < L_j and then
+// hands its value to the group on its left.  Below the merge levels every sibling is untouched by the
+// batch, so its OLD global value is what the reference's serial update would read: all of them (<= 2 x
+// depth per item) are fetched up front with 4-byte cp.async straight into shared memory -- ONE memory
+// round trip for the whole batch -- and the level loop itself touches only registers and shared memory:
+// per level a living item combines (left, right) from {its value, a deposited partner value, a prefetched
+// sibling}, writes the parent to the global tree and, if it merges at the next level, deposits the
+// value for its left group.  One __syncthreads per level, ~15 instructions per item per level.
 // FUSED (fp32): `value` holds RAW priorities; the leaf is (p + eps) ** alpha (samplers.py:1076, torch.pow
 // semantics) and the maximum raw priority of the valid items is folded into *max_out.
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
 __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
   int *ia = reinterpret_cast<int *>(addr);
   int old = *ia;
@@ -376,118 +346,173 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
   }
 }
 
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "n"(sizeof(T))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename T>
+__host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
+  // skey u64[np] | ukey u32[np] | nxt i32[np] | Lsm i32[np] | sraw T[np] | uval T[np] | dep_s,dep_m T[np] each
+  // | sib_s, sib_m T[depth*np] each
+  return (size_t)np * (8 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (4 + 2 * (size_t)depth);
+}
+
 template <typename T, bool FUSED>
 __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, int64_t capacity, int depth,
                                                                const int64_t *__restrict__ index,
                                                                const T *__restrict__ value, int n, int scalar,
-                                                               int log2_slots, float alpha, float eps,
-                                                               float *max_out) {
+                                                               float alpha, float eps, float *max_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  UpdSlot<T> *tab = reinterpret_cast<UpdSlot<T> *>(smem_raw);
-  const uint32_t nslots = 1u << log2_slots;
-  const uint32_t mask = nslots - 1;
+  const int NP = blockDim.x;  // power of two >= n
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
+  uint32_t *ukey = reinterpret_cast<uint32_t *>(skey + NP);
+  int *nxt = reinterpret_cast<int *>(ukey + NP);
+  int *Lsm = nxt + NP;
+  T *sraw = reinterpret_cast<T *>(Lsm + NP);
+  T *uval = sraw + NP;
+  T *dep_s = uval + NP;
+  T *dep_m = dep_s + NP;
+  T *sib_s = dep_m + NP;
+  T *sib_m = sib_s + (size_t)depth * NP;
+  __shared__ int warp_cnt[32];
+  __shared__ int s_total;
 
-  // ---- my item; start pulling its whole path's siblings into L2 before anything else
-  bool active = false;
-  uint32_t leafnode = 0;
+  // ---- 1. keys: (leaf node id, reversed input position) -- ascending sort puts the last writer first
+  unsigned long long key = ~0ull;
   T raw = (T)0;
+  bool valid = false;
   if (tid < n) {
     const int64_t ix = index[tid];
     if (ix >= 0 && ix < capacity) {  // negative = "skip" (MaxValueWriter convention, samplers.py:1040-1052)
-      active = true;
-      leafnode = (uint32_t)(capacity + ix);
-      for (int k = 0; k < depth; ++k) {
-        const uint32_t sib = (leafnode >> k) ^ 1u;
-        if (sum) prefetch_l2(sum + sib);
-        if (mn) prefetch_l2(mn + sib);
-      }
+      valid = true;
+      key = ((unsigned long long)(capacity + ix) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)tid);
       raw = scalar ? value[0] : value[tid];
     }
   }
   if constexpr (FUSED) {
     if (max_out) {
-      float p = active ? (float)raw : -INFINITY;
+      float p = valid ? (float)raw : -INFINITY;
       for (int o = 16; o > 0; o >>= 1) p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
-      if ((tid & 31) == 0 && p > -INFINITY) atomic_max_float(max_out, p);
+      if (lane == 0 && p > -INFINITY) atomic_max_float(max_out, p);
     }
   }
-  for (uint32_t i = tid; i < 2 * nslots; i += blockDim.x) {
-    tab[i].key = kEmptyKey;
-    tab[i].aux = 0;
-  }
+  skey[tid] = key;
+  sraw[tid] = raw;
   __syncthreads();
 
-  uint32_t node = leafnode, slot = 0;
-  T vs = (T)0, vm = (T)0;
-  {
-    // ---- round -1: last-writer-wins election on table 1
-    UpdSlot<T> *t1 = tab + nslots;
-    if (active) {
-      bool owner;
-      slot = upd_probe_insert(t1, mask, log2_slots, node, owner);
-      atomicMax(&t1[slot].aux, (uint32_t)tid + 1u);
-    }
-    __syncthreads();
-    if (active) {
-      const uint32_t winner = t1[slot].aux - 1u;
-      if (winner != (uint32_t)tid) {
-        active = false;
-      } else {
-        t1[slot].key = kEmptyKey;
-        t1[slot].aux = 0;
-        T v = raw;
-        if constexpr (FUSED) v = (T)pow_like_torch(add_rn((float)raw, eps), alpha);
-        vs = v;
-        vm = v;
-        if (sum) sum[node] = v;
-        if (mn) mn[node] = v;
+  // ---- 2. bitonic sort of NP keys
+  for (int k = 2; k <= NP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int partner = tid ^ j;
+      if (partner > tid) {
+        const unsigned long long a = skey[tid], b = skey[partner];
+        const bool up = (tid & k) == 0;
+        if ((a > b) == up) {
+          skey[tid] = b;
+          skey[partner] = a;
+        }
       }
+      __syncthreads();
     }
   }
 
-  // sibling of my node at level 0, loaded ahead of use; later levels are loaded one level ahead
-  T sib_s = (T)0, sib_m = (T)0;
-  if (active) {
-    if (sum) sib_s = ld_cg(sum + (node ^ 1u));
-    if (mn) sib_m = ld_cg(mn + (node ^ 1u));
+  // ---- 3. distinct leaves: head of each run of equal leaf ids, compacted by a block-wide exclusive scan
+  const unsigned long long mykey = skey[tid];
+  const uint32_t myleaf = (uint32_t)(mykey >> 32);
+  const bool head = (mykey != ~0ull) && (tid == 0 || (uint32_t)(skey[tid - 1] >> 32) != myleaf);
+  const unsigned bal = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = NP >> 5;
+    int c = (lane < nw) ? warp_cnt[lane] : 0;
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane < nw) warp_cnt[lane] = incl - c;
+    if (lane == 31) s_total = incl;
   }
-  for (int k = 0; k < depth; ++k) {
-    UpdSlot<T> *cur = tab + (uint32_t)(k & 1) * nslots;
-    bool owner = false;
-    const uint32_t side = node & 1u;
-    const uint32_t parent = node >> 1;
-    T nxt_s = (T)0, nxt_m = (T)0;
-    if (active) {
-      if (k + 1 < depth) {  // old value of the parent's sibling: only used if nobody in this batch carries it
-        if (sum) nxt_s = ld_cg(sum + (parent ^ 1u));
-        if (mn) nxt_m = ld_cg(mn + (parent ^ 1u));
+  __syncthreads();
+  if (head) {
+    const int u = warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
+    ukey[u] = myleaf;
+    uval[u] = sraw[0xffffffffu - (uint32_t)(mykey & 0xffffffffull)];
+  }
+  __syncthreads();
+  const int m = s_total;
+
+  // ---- 4. per distinct leaf: merge level, leaf write, sibling prefetch, first deposit
+  bool alive = tid < m;
+  uint32_t leafnode = 0;
+  int L = 0, my_next = -1;
+  T vs = (T)0, vm = (T)0;
+  if (alive) {
+    leafnode = ukey[tid];
+    T v = uval[tid];
+    if constexpr (FUSED) v = (T)pow_like_torch(add_rn((float)v, eps), alpha);
+    vs = v;
+    vm = v;
+    L = (tid == 0) ? depth + 1 : 32 - __clz(leafnode ^ ukey[tid - 1]);
+    Lsm[tid] = L;
+    my_next = (tid + 1 < m) ? tid + 1 : -1;
+    nxt[tid] = my_next;
+    if (sum) sum[leafnode] = v;
+    if (mn) mn[leafnode] = v;
+    // siblings are needed for levels l with l + 1 < L (while this item still carries its own node)
+    const int lim = (L - 1 < depth) ? L - 1 : depth;
+    for (int l = 0; l < lim; ++l) {
+      const uint32_t sib = (leafnode >> l) ^ 1u;
+      if (sum) cp_async_elem(sib_s + (size_t)l * NP + tid, sum + sib);
+      if (mn) cp_async_elem(sib_m + (size_t)l * NP + tid, mn + sib);
+    }
+    if (L == 1) {  // merges with its left neighbour already at level 1: hand over the leaf value
+      dep_s[tid] = vs;
+      dep_m[tid] = vm;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- 5. climb
+  for (int l = 0; l < depth; ++l) {
+    if (alive) {
+      if (L == l + 1) {
+        alive = false;  // my level-l value was deposited; the group on my left carries the parent
+      } else {
+        const uint32_t node = leafnode >> l;
+        T os, om;
+        bool from_partner = false;
+        if ((node & 1u) == 0u && my_next >= 0 && Lsm[my_next] == l + 1) {
+          os = dep_s[my_next];  // touched right sibling: value deposited by the item that merges into me
+          om = dep_m[my_next];
+          my_next = nxt[my_next];
+          nxt[tid] = my_next;
+          from_partner = true;
+        }
+        if (!from_partner) {
+          os = sum ? sib_s[(size_t)l * NP + tid] : (T)0;
+          om = mn ? sib_m[(size_t)l * NP + tid] : (T)0;
+        }
+        // node = op(left child, right child)
+        vs = (node & 1u) ? tree_op<T, false>(os, vs) : tree_op<T, false>(vs, os);
+        vm = (node & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+        const uint32_t parent = node >> 1;
+        if (sum) sum[parent] = vs;
+        if (mn) mn[parent] = vm;
+        if (L == l + 2) {  // I merge into my left group at the next level: deposit the value just computed
+          dep_s[tid] = vs;
+          dep_m[tid] = vm;
+        }
       }
-      slot = upd_probe_insert(cur, mask, log2_slots, parent, owner);
-      cur[slot].s[side] = vs;
-      cur[slot].m[side] = vm;
-      atomicOr(&cur[slot].aux, 1u << side);
     }
     __syncthreads();
-    if (active) {
-      if (!owner) {
-        active = false;  // the slot's creator carries the parent
-      } else {
-        const uint32_t other = side ^ 1u;
-        const bool has_other = (cur[slot].aux >> other) & 1u;
-        const T os = has_other ? cur[slot].s[other] : sib_s;
-        const T om = has_other ? cur[slot].m[other] : sib_m;
-        cur[slot].key = kEmptyKey;
-        cur[slot].aux = 0;
-        vs = side ? tree_op<T, false>(os, vs) : tree_op<T, false>(vs, os);
-        vm = side ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
-        node = parent;
-        if (sum) sum[node] = vs;
-        if (mn) mn[node] = vm;
-        sib_s = nxt_s;
-        sib_m = nxt_m;
-      }
-    }
   }
 }
 
@@ -609,6 +634,8 @@ static int tree_rebuild_impl(void *tree_, int64_t capacity, int is_min, cudaStre
   return RLB_OK;
 }
 
+constexpr int kUpdateSmemLimit = 224 * 1024;  // dynamic shared memory the single-CTA update may use
+
 struct FusedPow {
   bool on = false;
   float alpha = 0.f, eps = 0.f;
@@ -618,24 +645,30 @@ struct FusedPow {
 template <typename T, bool FUSED>
 static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const int64_t *index, const T *value,
                              int64_t n, int scalar, const FusedPow &fp, cudaStream_t st) {
-  const int threads = (int)((n + 31) / 32 * 32);
-  int log2_slots = 6;
-  while ((1 << log2_slots) < 2 * n) ++log2_slots;
-  const size_t smem = 2 * (size_t(1) << log2_slots) * sizeof(UpdSlot<T>);
+  int np = 32;
+  while (np < n) np <<= 1;
+  const size_t smem = upd_smem_bytes<T>(np, depth);
   static bool attr_set = false;
   if (!attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T, FUSED>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmemLimit),
                         "cudaFuncSetAttribute(tree_update_cta_kernel)");
     if (rc) return rc;
     attr_set = true;
   }
-  tree_update_cta_kernel<T, FUSED><<<1, threads, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n, scalar,
-                                                             log2_slots, fp.alpha, fp.eps, fp.max_out);
+  tree_update_cta_kernel<T, FUSED><<<1, np, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n, scalar,
+                                                        fp.alpha, fp.eps, fp.max_out);
   return check_launch("tree_update_cta_kernel");
 }
 
-constexpr int64_t kUpdateCtaMax = 1024;  // batch sizes handled by the single-CTA kernel
+template <typename T>
+static bool update_fits_cta(int64_t n, int64_t capacity, int depth) {
+  if (n > 1024 || capacity > (int64_t(1) << 30)) return false;
+  int np = 32;
+  while (np < n) np <<= 1;
+  return upd_smem_bytes<T>(np, depth) <= (size_t)kUpdateSmemLimit;
+}
+
 
 template <typename T>
 static int tree_update_impl(void *sum_, void *mn_, int64_t capacity, const int64_t *index, const void *value_,
@@ -645,7 +678,7 @@ static int tree_update_impl(void *sum_, void *mn_, int64_t capacity, const int64
   T *mn = static_cast<T *>(mn_);
   const T *value = static_cast<const T *>(value_);
   const int depth = ilog2_i64(capacity);
-  if (n <= kUpdateCtaMax && capacity <= (int64_t(1) << 30)) {
+  if (update_fits_cta<T>(n, capacity, depth)) {
     if constexpr (sizeof(T) == 4) {
       if (fp.on) return launch_update_cta<T, true>(sum, mn, capacity, depth, index, value, n, scalar, fp, st);
     }
@@ -830,9 +863,10 @@ int rlb_per_update(void *sum_tree, void *min_tree, int64_t capacity, const int64
   RLB_REQUIRE(n >= 0, RLB_EINVAL, "rlb_per_update: negative n");
   if (n == 0) return RLB_OK;
   RLB_REQUIRE(index && priority, RLB_EINVAL, "rlb_per_update: null index/priority");
-  RLB_REQUIRE(leaf_scratch || n <= kUpdateCtaMax, RLB_EINVAL, "rlb_per_update: n > 1024 needs leaf_scratch[n]");
+  RLB_REQUIRE(leaf_scratch || update_fits_cta<float>(n, capacity, ilog2_i64(capacity)), RLB_EINVAL,
+              "rlb_per_update: this batch size needs leaf_scratch[n]");
   cudaStream_t st = as_stream(stream);
-  if (n <= kUpdateCtaMax && capacity <= (int64_t(1) << 30)) {
+  if (update_fits_cta<float>(n, capacity, ilog2_i64(capacity))) {
     // one launch: pow, running max, election, leaf write and the climb all happen inside the CTA kernel
     FusedPow fp;
     fp.on = true;
