@@ -82,8 +82,9 @@ int rlb_tree_fill(void *tree /*[dev] 2*capacity values*/, int64_t capacity, int 
  * recompute every internal node bottom-up, node = op(left, right). */
 int rlb_tree_rebuild(void *tree /*[dev]*/, int64_t capacity, int is_min, int dtype, rlb_stream_t stream);
 
-/* Bytes of persistent scratch rlb_tree_update needs for a tree of `size` leaves (one buffer per
- * sampler, zero-initialised once by the caller, shared by the sum and the min tree). */
+/* Bytes of persistent scratch rlb_tree_update / rlb_per_update need for a tree of `size` leaves (one
+ * buffer per sampler, zero-initialised ONCE by the caller, shared by the sum and the min tree; calls
+ * that share a workspace must be stream-ordered). */
 size_t rlb_tree_update_workspace_bytes(int64_t size);
 
 /* SegmentTree::Update, batch form (csrc/segment_tree.h:83-139,216-226; CUDA reference

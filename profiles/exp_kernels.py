@@ -39,7 +39,7 @@ def make(parts):
                 outs.append(plan.run(idx, N))
             if "update" in parts:
                 be.per_update(smp._sum_tree.values, smp._min_tree.values, smp._sum_tree.capacity, idx, td_err, 0.6, 1e-8,
-                              smp._max_priority_buf, None, 1)
+                              smp._max_priority_buf, smp._tree_workspace(B), 1)
             if "gae" in parts:
                 v, nv, r, d8, t8 = ring8[slot]
                 outs.append(be.gae(v, nv, r, d8, t8, 0.99, 0.9405, bench.GAE_ROWS, bench.GAE_T, 1))

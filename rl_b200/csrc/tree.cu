@@ -321,19 +321,24 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------------
-// update: single-CTA path (n <= 1024)
+// update: batches of <= 1024 in ONE launch
 // ------------------------------------------------------------------------------------------------
 // Sorted-merge climb.  The batch is sorted by leaf (bitonic, in shared memory; ties broken so that the
 // LAST input position comes first and wins -- csrc/segment_tree.h:222-226 / cuda_segment_tree.cu:32-37)
 // and compacted to the m distinct leaves.  Item j's root path coincides with its left neighbour's from
 // level L_j = bitlength(key_j ^ key_{j-1}) upwards, so j carries its own nodes for levels < L_j and then
 // hands its value to the group on its left.  Below the merge levels every sibling is untouched by the
-// batch, so its OLD global value is what the reference's serial update would read: all of them (<= 2 x
-// depth per item) are fetched up front with 4-byte cp.async straight into shared memory -- ONE memory
-// round trip for the whole batch -- and the level loop itself touches only registers and shared memory:
-// per level a living item combines (left, right) from {its value, a deposited partner value, a prefetched
-// sibling}, writes the parent to the global tree and, if it merges at the next level, deposits the
-// value for its left group.  One __syncthreads per level, ~15 instructions per item per level.
+// batch, so its OLD global value is what the reference's serial update would read.
+//
+// Those sibling reads are 2 x depth scattered 4-byte loads per item -- ~10k sectors for a batch of 256 on
+// a 2^20 tree -- and a single SM's L1 moves only about one sector wavefront every ~2 cycles, which made
+// them the whole cost of earlier single-CTA versions (ncu: 20k of 28k cycles).  So the launch has TWO
+// phases: (A) a grid of CTAs spread over the chip reads every (item, level) sibling of both trees and
+// writes it, coalesced, to a scratch tile; the last CTA to finish (atomic ticket) alone continues with
+// (B): it pulls the scratch tile into shared memory with coalesced 16-byte cp.async, sorts, compacts and
+// climbs level-synchronously touching only registers and shared memory: per level a living item combines
+// (left, right) from {its value, a deposited partner value, a prefetched sibling}, writes the parent to
+// the global tree and, if it merges at the next level, deposits the value for its left group.
 // FUSED (fp32): `value` holds RAW priorities; the leaf is (p + eps) ** alpha (samplers.py:1076, torch.pow
 // semantics) and the maximum raw priority of the valid items is folded into *max_out.
 __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
@@ -346,41 +351,82 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
   }
 }
 
-template <typename T>
-__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "n"(sizeof(T))
-               : "memory");
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+constexpr size_t kUpdCtrlBytes = 1024;                 // ticket counter lives at the start of the workspace
+constexpr size_t kUpdScratchBytes = (size_t(1) << 20) - kUpdCtrlBytes;
+constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // stamps of the general path start here
+
 template <typename T>
 __host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
-  // skey u64[np] | ukey u32[np] | nxt i32[np] | Lsm i32[np] | sraw T[np] | uval T[np] | dep_s,dep_m T[np] each
+  // skey u64[np] | ukey u32[np] | upos u32[np] | nxt i32[np] | Lsm i32[np] | sraw T[np] | dep_s,dep_m T[np] each
   // | sib_s, sib_m T[depth*np] each
-  return (size_t)np * (8 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (4 + 2 * (size_t)depth);
+  return (size_t)np * (8 + 4 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (3 + 2 * (size_t)depth);
 }
 
 template <typename T, bool FUSED>
 __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, int64_t capacity, int depth,
                                                                const int64_t *__restrict__ index,
                                                                const T *__restrict__ value, int n, int scalar,
-                                                               float alpha, float eps, float *max_out) {
+                                                               float alpha, float eps, float *max_out,
+                                                               int *ticket, T *scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NP = blockDim.x;  // power of two >= n
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
-  uint32_t *ukey = reinterpret_cast<uint32_t *>(skey + NP);
-  int *nxt = reinterpret_cast<int *>(ukey + NP);
-  int *Lsm = nxt + NP;
-  T *sraw = reinterpret_cast<T *>(Lsm + NP);
-  T *uval = sraw + NP;
-  T *dep_s = uval + NP;
-  T *dep_m = dep_s + NP;
-  T *sib_s = dep_m + NP;
-  T *sib_m = sib_s + (size_t)depth * NP;
   __shared__ int warp_cnt[32];
   __shared__ int s_total;
+  __shared__ int s_last;
+
+  // ---- phase A (all CTAs): scratch[t][l][i] = tree_t[((capacity + index[i]) >> l) ^ 1]
+  {
+    const int64_t per_tree = (int64_t)depth * NP;
+    const int64_t total = 2 * per_tree;
+    for (int64_t e = (int64_t)blockIdx.x * NP + tid; e < total; e += (int64_t)gridDim.x * NP) {
+      const int t = (int)(e / per_tree);
+      const int64_t rem = e - (int64_t)t * per_tree;
+      const int l = (int)(rem / NP);
+      const int i = (int)(rem - (int64_t)l * NP);
+      const T *tree = t ? mn : sum;
+      T v = (T)0;
+      if (tree && i < n) {
+        const int64_t ix = __ldg(index + i);
+        if (ix >= 0 && ix < capacity) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+      }
+      scratch[e] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(ticket, 1);
+      s_last = (prev == (int)gridDim.x - 1);
+      if (s_last) *ticket = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+  }
+
+  // ---- phase B (last CTA only)
+  unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
+  uint32_t *ukey = reinterpret_cast<uint32_t *>(skey + NP);
+  uint32_t *upos = ukey + NP;
+  int *nxt = reinterpret_cast<int *>(upos + NP);
+  int *Lsm = nxt + NP;
+  T *sraw = reinterpret_cast<T *>(Lsm + NP);
+  T *dep_s = sraw + NP;
+  T *dep_m = dep_s + NP;
+  T *sib = dep_m + NP;  // [2][depth][NP], indexed by ORIGINAL input position
+  {
+    // coalesced 16-byte async copies of the whole scratch tile (lands while we sort)
+    const size_t bytes = 2 * (size_t)depth * NP * sizeof(T);
+    const unsigned char *g = reinterpret_cast<const unsigned char *>(scratch);
+    unsigned char *d = reinterpret_cast<unsigned char *>(sib);
+    for (size_t off = (size_t)tid * 16; off < bytes; off += (size_t)NP * 16) cp_async16(d + off, g + off);
+  }
 
   // ---- 1. keys: (leaf node id, reversed input position) -- ascending sort puts the last writer first
   unsigned long long key = ~0ull;
@@ -443,19 +489,21 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   if (head) {
     const int u = warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
     ukey[u] = myleaf;
-    uval[u] = sraw[0xffffffffu - (uint32_t)(mykey & 0xffffffffull)];
+    upos[u] = 0xffffffffu - (uint32_t)(mykey & 0xffffffffull);
   }
+  cp_async_wait_all();
   __syncthreads();
   const int m = s_total;
 
-  // ---- 4. per distinct leaf: merge level, leaf write, sibling prefetch, first deposit
+  // ---- 4. per distinct leaf: merge level, leaf write, first deposit
   bool alive = tid < m;
-  uint32_t leafnode = 0;
+  uint32_t leafnode = 0, pos = 0;
   int L = 0, my_next = -1;
   T vs = (T)0, vm = (T)0;
   if (alive) {
     leafnode = ukey[tid];
-    T v = uval[tid];
+    pos = upos[tid];
+    T v = sraw[pos];
     if constexpr (FUSED) v = (T)pow_like_torch(add_rn((float)v, eps), alpha);
     vs = v;
     vm = v;
@@ -465,22 +513,16 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     nxt[tid] = my_next;
     if (sum) sum[leafnode] = v;
     if (mn) mn[leafnode] = v;
-    // siblings are needed for levels l with l + 1 < L (while this item still carries its own node)
-    const int lim = (L - 1 < depth) ? L - 1 : depth;
-    for (int l = 0; l < lim; ++l) {
-      const uint32_t sib = (leafnode >> l) ^ 1u;
-      if (sum) cp_async_elem(sib_s + (size_t)l * NP + tid, sum + sib);
-      if (mn) cp_async_elem(sib_m + (size_t)l * NP + tid, mn + sib);
-    }
     if (L == 1) {  // merges with its left neighbour already at level 1: hand over the leaf value
       dep_s[tid] = vs;
       dep_m[tid] = vm;
     }
   }
-  cp_async_wait_all();
   __syncthreads();
 
   // ---- 5. climb
+  const T *sib_s = sib + pos;
+  const T *sib_m = sib + (size_t)depth * NP + pos;
   for (int l = 0; l < depth; ++l) {
     if (alive) {
       if (L == l + 1) {
@@ -488,17 +530,14 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       } else {
         const uint32_t node = leafnode >> l;
         T os, om;
-        bool from_partner = false;
         if ((node & 1u) == 0u && my_next >= 0 && Lsm[my_next] == l + 1) {
           os = dep_s[my_next];  // touched right sibling: value deposited by the item that merges into me
           om = dep_m[my_next];
           my_next = nxt[my_next];
           nxt[tid] = my_next;
-          from_partner = true;
-        }
-        if (!from_partner) {
-          os = sum ? sib_s[(size_t)l * NP + tid] : (T)0;
-          om = mn ? sib_m[(size_t)l * NP + tid] : (T)0;
+        } else {
+          os = sib_s[(size_t)l * NP];  // untouched sibling: its old global value
+          om = sib_m[(size_t)l * NP];
         }
         // node = op(left child, right child)
         vs = (node & 1u) ? tree_op<T, false>(os, vs) : tree_op<T, false>(vs, os);
@@ -644,7 +683,7 @@ struct FusedPow {
 
 template <typename T, bool FUSED>
 static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const int64_t *index, const T *value,
-                             int64_t n, int scalar, const FusedPow &fp, cudaStream_t st) {
+                             int64_t n, int scalar, const FusedPow &fp, void *workspace, cudaStream_t st) {
   int np = 32;
   while (np < n) np <<= 1;
   const size_t smem = upd_smem_bytes<T>(np, depth);
@@ -656,8 +695,16 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
     if (rc) return rc;
     attr_set = true;
   }
-  tree_update_cta_kernel<T, FUSED><<<1, np, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n, scalar,
-                                                        fp.alpha, fp.eps, fp.max_out);
+  // phase A grid: ~4 scattered sibling reads per thread, at most one CTA per SM
+  int64_t grid = (2 * (int64_t)depth * np + 4 * (int64_t)np - 1) / (4 * (int64_t)np);
+  const int sms = sm_count();
+  if (grid > sms) grid = sms;
+  if (grid < 1) grid = 1;
+  int *ticket = static_cast<int *>(workspace);
+  T *scratch = reinterpret_cast<T *>(static_cast<unsigned char *>(workspace) + kUpdCtrlBytes);
+  tree_update_cta_kernel<T, FUSED><<<(unsigned)grid, np, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n,
+                                                                    scalar, fp.alpha, fp.eps, fp.max_out, ticket,
+                                                                    scratch);
   return check_launch("tree_update_cta_kernel");
 }
 
@@ -666,7 +713,8 @@ static bool update_fits_cta(int64_t n, int64_t capacity, int depth) {
   if (n > 1024 || capacity > (int64_t(1) << 30)) return false;
   int np = 32;
   while (np < n) np <<= 1;
-  return upd_smem_bytes<T>(np, depth) <= (size_t)kUpdateSmemLimit;
+  return upd_smem_bytes<T>(np, depth) <= (size_t)kUpdateSmemLimit &&
+         2 * (size_t)depth * np * sizeof(T) <= kUpdScratchBytes;
 }
 
 
@@ -678,18 +726,18 @@ static int tree_update_impl(void *sum_, void *mn_, int64_t capacity, const int64
   T *mn = static_cast<T *>(mn_);
   const T *value = static_cast<const T *>(value_);
   const int depth = ilog2_i64(capacity);
+  RLB_REQUIRE(workspace != nullptr && workspace_bytes >= kUpdWorkspaceHead + (size_t)capacity * sizeof(unsigned long long),
+              RLB_EINVAL, "rlb_tree_update: needs a zero-initialised workspace of rlb_tree_update_workspace_bytes(size)");
   if (update_fits_cta<T>(n, capacity, depth)) {
     if constexpr (sizeof(T) == 4) {
-      if (fp.on) return launch_update_cta<T, true>(sum, mn, capacity, depth, index, value, n, scalar, fp, st);
+      if (fp.on)
+        return launch_update_cta<T, true>(sum, mn, capacity, depth, index, value, n, scalar, fp, workspace, st);
     }
-    return launch_update_cta<T, false>(sum, mn, capacity, depth, index, value, n, scalar, fp, st);
+    return launch_update_cta<T, false>(sum, mn, capacity, depth, index, value, n, scalar, fp, workspace, st);
   }
   // general path
-  RLB_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)capacity * sizeof(unsigned long long),
-              RLB_EINVAL, "rlb_tree_update: n=%lld needs a workspace of rlb_tree_update_workspace_bytes(size)",
-              (long long)n);
-  RLB_REQUIRE(n < (int64_t(1) << 32), RLB_ELIMIT, "rlb_tree_update: n must be < 2^32");
-  unsigned long long *stamp = static_cast<unsigned long long *>(workspace);
+  unsigned long long *stamp =
+      reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(workspace) + kUpdWorkspaceHead);
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   upd_stamp_kernel<<<blocks, threads, 0, st>>>(stamp, capacity, index, n, epoch);
@@ -727,8 +775,9 @@ int64_t rlb_tree_capacity(int64_t size) {
 }
 
 size_t rlb_tree_update_workspace_bytes(int64_t size) {
-  // one 64-bit (epoch, position) stamp per addressable leaf slot; the kernels bound-check against capacity
-  return (size_t)rlb_tree_capacity(size) * sizeof(unsigned long long);
+  // 1 MB head (launch ticket + the sibling scratch tile of the <=1024 path) followed by one 64-bit
+  // (epoch, position) stamp per addressable leaf slot for larger batches
+  return rlb::kUpdWorkspaceHead + (size_t)rlb_tree_capacity(size) * sizeof(unsigned long long);
 }
 
 int rlb_tree_fill(void *tree, int64_t capacity, int is_min, int dtype, rlb_stream_t stream) {

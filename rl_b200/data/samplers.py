@@ -264,7 +264,7 @@ class PrioritizedSampler(Sampler):
             raise RuntimeError(
                 "update_priority with more than 1024 entries uses an epoch-stamped scatter that cannot be replayed "
                 "from a CUDA graph; split the batch or run it outside the graph.")
-        if n > 1024 and self._workspace is None:
+        if self._workspace is None:  # ticket + sibling scratch (<= 1024 items) and stamps (larger batches)
             self._workspace = ops.backend().tree_workspace(self._max_capacity, self._sum_tree.device)
         return self._workspace
 

@@ -35,7 +35,7 @@ class _DeviceSegmentTree:
         be = ops.backend()
         self._capacity = be.tree_capacity(size)
         self._values = be.tree_new(size, self._is_min, self._dtype, self._device)
-        self._workspace = None  # persistent (epoch, position) stamps, allocated on the first large update
+        self._workspace = None  # persistent update scratch (ticket, sibling tile, stamps), allocated on first update
         self._epoch = 0
 
     # ---- properties --------------------------------------------------------------------------------
@@ -87,7 +87,7 @@ class _DeviceSegmentTree:
         return self._epoch
 
     def _ensure_workspace(self, n: int):
-        if n > 1024 and self._workspace is None:
+        if self._workspace is None:
             self._workspace = ops.backend().tree_workspace(self._size, self.device)
         return self._workspace
 

@@ -47,7 +47,7 @@ def test_host_only_entry_points(so):
     for size, cap in [(1, 2), (2, 4), (15, 16), (16, 32), (1000, 1024), (1024, 2048), (1_000_000, 1 << 20),
                       (1_250_000, 1 << 21), (6_250_000, 1 << 23)]:
         assert L.rlb_tree_capacity(size) == cap
-    assert L.rlb_tree_update_workspace_bytes(1000) == 1024 * 8
+    assert L.rlb_tree_update_workspace_bytes(1000) == (1 << 20) + 1024 * 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
