@@ -1,0 +1,26 @@
+"""clock64() stamps at the phase boundaries of the single-launch update kernel (profiling aid)."""
+import ctypes, sys
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from rl_b200 import ops
+from rl_b200.data import PrioritizedSampler
+dev = torch.device("cuda", 0)
+be = ops.backend()
+be.L.rlb_debug_set_tick_buffer.argtypes = [ctypes.c_void_p]
+N = 1_000_000
+for B in (256, 1024):
+    smp = PrioritizedSampler(N, 0.6, 0.4, device=dev)
+    smp.update_priority(torch.arange(N, device=dev), torch.rand(N, device=dev))
+    ticks = torch.zeros(8, dtype=torch.int64, device=dev)
+    be.L.rlb_debug_set_tick_buffer(ticks.data_ptr())
+    for it in range(4):
+        idx = torch.randint(0, N, (B,), device=dev)
+        p = torch.rand(B, device=dev)
+        torch.cuda.synchronize()
+        smp.update_priority(idx, p)
+        torch.cuda.synchronize()
+        t = ticks.tolist()
+        d = [t[i + 1] - t[i] for i in range(6)]
+        print(f"B={B} it={it}: phaseA+ticket {d[0]}  keys {d[1]}  sort {d[2]}  compact+cpwait {d[3]}  init {d[4]}  climb {d[5]}  total {t[6]-t[0]} cycles")
+    be.L.rlb_debug_set_tick_buffer(None)

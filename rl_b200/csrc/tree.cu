@@ -213,13 +213,15 @@ __device__ __forceinline__ int64_t descend4_f32(const float *__restrict__ tree, 
 
 template <typename T>
 __device__ __forceinline__ int64_t scan_lower_bound_one(const T *__restrict__ tree, int64_t size, int64_t capacity,
-                                                        int depth, T value, T root) {
+                                                        int depth, T value, T root, bool speculative = true) {
   if (value > root) return size;  // csrc/segment_tree.h:250-252
   int64_t node = 1;
   T cur = value;
   int lev = 0;
   if constexpr (sizeof(T) == 4) {
-    for (; lev + 4 <= depth; lev += 4) node = descend4_f32(tree, node, cur);
+    if (speculative) {
+      for (; lev + 4 <= depth; lev += 4) node = descend4_f32(tree, node, cur);
+    }
   }
   node = descend_plain<T>(tree, node, depth - lev, cur);
   return node ^ capacity;
@@ -262,27 +264,31 @@ __device__ __forceinline__ T warp_query_prefix(const T *__restrict__ tree, int64
   return ret;
 }
 
+// Small batches are latency-bound (one dependent round trip per descent step) and use the 4-level speculative
+// descent; large batches are bound by L1 sector wavefronts (every lane chases its own path) and use the plain
+// one-load-per-level descent: half the wavefronts, with the latency hidden by occupancy.
 template <typename T>
 __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ sum, const T *__restrict__ mn,
                                                          int64_t size, int64_t capacity, int depth, int64_t len,
                                                          const T *__restrict__ u, int64_t B, T neg_beta,
-                                                         int cpu_semantics, int64_t *__restrict__ index_out,
+                                                         int cpu_semantics, int speculative,
+                                                         int64_t *__restrict__ index_out,
                                                          float *__restrict__ weight_out, T *leaf_out,
                                                          T *psum_pmin_out, int32_t *status) {
   __shared__ T s_p[2];
   const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const T ui = (i < B) ? __ldg(u + i) : (T)0;  // in flight while warps 0/1 resolve p_sum / p_min
-  if (warp < 2) {
-    // warp 0: p_sum, warp 1: p_min   (samplers.py:901-908)
-    T v;
-    const bool root = cpu_semantics && (len >= size);  // csrc/segment_tree.h:145-147 fast path (l == 0)
-    if (warp == 0) {
-      v = root ? __ldg(sum + 1) : warp_query_prefix<T, false>(sum, capacity, len, (T)0);
-    } else {
-      v = root ? __ldg(mn + 1) : warp_query_prefix<T, true>(mn, capacity, len, Limits<T>::max());
-    }
-    if ((threadIdx.x & 31) == 0) s_p[warp] = v;
+  const T ui = (i < B) ? __ldg(u + i) : (T)0;  // in flight while p_sum / p_min are resolved
+  // p_sum by warp 0, p_min by warp 1 (or both by warp 0 in single-warp CTAs)   (samplers.py:901-908)
+  const bool root = cpu_semantics && (len >= size);  // csrc/segment_tree.h:145-147 fast path (l == 0)
+  if (warp == 0) {
+    const T v = root ? __ldg(sum + 1) : warp_query_prefix<T, false>(sum, capacity, len, (T)0);
+    if ((threadIdx.x & 31) == 0) s_p[0] = v;
+  }
+  if (warp == (nwarps > 1 ? 1 : 0)) {
+    const T v = root ? __ldg(mn + 1) : warp_query_prefix<T, true>(mn, capacity, len, Limits<T>::max());
+    if ((threadIdx.x & 31) == 0) s_p[1] = v;
   }
   __syncthreads();
   const T p_sum = s_p[0], p_min = s_p[1];
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   }
   if (i >= B) return;
   const T mass = mul_rn(ui, p_sum);  // samplers.py:919 / :923 -- one rounding, never fused downstream
-  int64_t idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1));
+  int64_t idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1), speculative != 0);
   if (idx > len - 1) idx = len - 1;  // samplers.py:933
   T leaf = __ldg(sum + (idx | capacity));
   if (cpu_semantics) {
@@ -362,9 +368,29 @@ constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // stamps of the general 
 
 template <typename T>
 __host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
-  // skey u64[np] | ukey u32[np] | upos u32[np] | nxt i32[np] | Lsm i32[np] | sraw T[np] | dep_s,dep_m T[np] each
+  // xbuf u64[2*np] | ukey u32[np] | upos u32[np] | nxt i32[np] | Lsm i32[np] | sraw T[np] | dep_s,dep_m T[np] each
   // | sib_s, sib_m T[depth*np] each
-  return (size_t)np * (8 + 4 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (3 + 2 * (size_t)depth);
+  return (size_t)np * (16 + 4 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (3 + 2 * (size_t)depth);
+}
+
+#define RLB_TICK(k)                                                   \
+  do {                                                                \
+    if (dbg && threadIdx.x == 0) dbg[(k)] = (long long)clock64();     \
+  } while (0)
+
+// max of floats through one fire-and-forget reduction: non-negative values order like their int bits, negative
+// ones like their reversed unsigned bits (the buffer starts at -inf = 0xff800000, below / above all of them).
+__device__ __forceinline__ void red_max_float(float *addr, float v) {
+  if (v >= 0.0f)
+    atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int lane_mask) {
+  const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, lane_mask);
+  const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), lane_mask);
+  return ((unsigned long long)hi << 32) | lo;
 }
 
 template <typename T, bool FUSED>
@@ -372,7 +398,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
                                                                const int64_t *__restrict__ index,
                                                                const T *__restrict__ value, int n, int scalar,
                                                                float alpha, float eps, float *max_out,
-                                                               int *ticket, T *scratch) {
+                                                               int *ticket, T *__restrict__ scratch,
+                                                               long long *dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NP = blockDim.x;  // power of two >= n
   const int tid = threadIdx.x;
@@ -381,19 +408,31 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   __shared__ int s_total;
   __shared__ int s_last;
 
-  // ---- phase A (all CTAs): scratch[t][l][i] = tree_t[((capacity + index[i]) >> l) ^ 1]
+  const long long t_start = dbg ? (long long)clock64() : 0;  // stamps are taken by the CTA that runs phase B
+  // my own item (every CTA loads it: phase A needs the indices anyway, the last CTA needs the values)
+  bool valid = false;
+  int64_t my_ix = -1;
+  T raw = (T)0;
+  if (tid < n) {
+    my_ix = __ldg(index + tid);
+    valid = (my_ix >= 0 && my_ix < capacity);  // negative = "skip" (MaxValueWriter convention, samplers.py:1040-1052)
+    raw = scalar ? __ldg(value) : __ldg(value + tid);
+  }
+
+  // ---- phase A (all CTAs): scratch[t][l][i] = tree_t[((capacity + index[i]) >> l) ^ 1], one element per
+  // thread per pass (the grid is sized so that there is normally a single pass)
   {
-    const int64_t per_tree = (int64_t)depth * NP;
-    const int64_t total = 2 * per_tree;
-    for (int64_t e = (int64_t)blockIdx.x * NP + tid; e < total; e += (int64_t)gridDim.x * NP) {
-      const int t = (int)(e / per_tree);
-      const int64_t rem = e - (int64_t)t * per_tree;
-      const int l = (int)(rem / NP);
-      const int i = (int)(rem - (int64_t)l * NP);
+    const uint32_t per_tree = (uint32_t)depth * (uint32_t)NP;
+    const uint32_t total = 2u * per_tree;
+    for (uint32_t e = blockIdx.x * (uint32_t)NP + tid; e < total; e += gridDim.x * (uint32_t)NP) {
+      const uint32_t t = e >= per_tree;
+      const uint32_t rem = e - t * per_tree;
+      const uint32_t l = rem / (uint32_t)NP;
+      const uint32_t i = rem - l * (uint32_t)NP;  // == tid
       const T *tree = t ? mn : sum;
       T v = (T)0;
-      if (tree && i < n) {
-        const int64_t ix = __ldg(index + i);
+      if (tree && i < (uint32_t)n) {
+        const int64_t ix = (i == (uint32_t)tid) ? my_ix : __ldg(index + i);
         if (ix >= 0 && ix < capacity) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
       }
       scratch[e] = v;
@@ -409,17 +448,19 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     if (!s_last) return;
     __threadfence();
   }
+  if (dbg && threadIdx.x == 0) dbg[0] = t_start;
+  RLB_TICK(1);
 
   // ---- phase B (last CTA only)
-  unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
-  uint32_t *ukey = reinterpret_cast<uint32_t *>(skey + NP);
+  unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
+  uint32_t *ukey = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);
   uint32_t *upos = ukey + NP;
   int *nxt = reinterpret_cast<int *>(upos + NP);
   int *Lsm = nxt + NP;
   T *sraw = reinterpret_cast<T *>(Lsm + NP);
   T *dep_s = sraw + NP;
   T *dep_m = dep_s + NP;
-  T *sib = dep_m + NP;  // [2][depth][NP], indexed by ORIGINAL input position
+  T *sib = dep_m + NP;  // [2][depth][NP], indexed by ORIGINAL input position; reused as the output staging tile
   {
     // coalesced 16-byte async copies of the whole scratch tile (lands while we sort)
     const size_t bytes = 2 * (size_t)depth * NP * sizeof(T);
@@ -430,47 +471,52 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
 
   // ---- 1. keys: (leaf node id, reversed input position) -- ascending sort puts the last writer first
   unsigned long long key = ~0ull;
-  T raw = (T)0;
-  bool valid = false;
-  if (tid < n) {
-    const int64_t ix = index[tid];
-    if (ix >= 0 && ix < capacity) {  // negative = "skip" (MaxValueWriter convention, samplers.py:1040-1052)
-      valid = true;
-      key = ((unsigned long long)(capacity + ix) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)tid);
-      raw = scalar ? value[0] : value[tid];
-    }
-  }
+  if (valid) key = ((unsigned long long)(capacity + my_ix) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)tid);
   if constexpr (FUSED) {
     if (max_out) {
       float p = valid ? (float)raw : -INFINITY;
       for (int o = 16; o > 0; o >>= 1) p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
-      if (lane == 0 && p > -INFINITY) atomic_max_float(max_out, p);
+      if (lane == 0 && p > -INFINITY) red_max_float(max_out, p);
     }
   }
-  skey[tid] = key;
   sraw[tid] = raw;
-  __syncthreads();
+  RLB_TICK(2);
 
-  // ---- 2. bitonic sort of NP keys
-  for (int k = 2; k <= NP; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const int partner = tid ^ j;
-      if (partner > tid) {
-        const unsigned long long a = skey[tid], b = skey[partner];
-        const bool up = (tid & k) == 0;
-        if ((a > b) == up) {
-          skey[tid] = b;
-          skey[partner] = a;
+  // ---- 2. bitonic sort of NP keys, one key per thread: strides < 32 with warp shuffles, larger strides through
+  // double-buffered shared memory (one barrier per such step)
+  {
+    int flip = 0;
+    for (int k = 2; k <= NP; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        unsigned long long other;
+        if (j >= 32) {
+          unsigned long long *buf = xbuf + flip * NP;
+          buf[tid] = key;
+          __syncthreads();
+          other = buf[tid ^ j];
+          flip ^= 1;
+        } else {
+          other = shfl_xor_u64(key, j);
         }
+        const bool up = (tid & k) == 0;      // this block of k sorts ascending
+        const bool lower = (tid & j) == 0;   // I hold the lower position of the pair
+        const bool take_min = (lower == up);
+        const bool other_less = other < key;
+        key = (take_min == other_less) ? other : key;
       }
-      __syncthreads();
     }
   }
+  RLB_TICK(3);
 
   // ---- 3. distinct leaves: head of each run of equal leaf ids, compacted by a block-wide exclusive scan
-  const unsigned long long mykey = skey[tid];
-  const uint32_t myleaf = (uint32_t)(mykey >> 32);
-  const bool head = (mykey != ~0ull) && (tid == 0 || (uint32_t)(skey[tid - 1] >> 32) != myleaf);
+  const uint32_t myleaf = (uint32_t)(key >> 32);
+  {
+    unsigned long long *buf = xbuf;  // both exchange buffers are free again after one more barrier
+    __syncthreads();
+    buf[tid] = key;
+    __syncthreads();
+  }
+  const bool head = (key != ~0ull) && (tid == 0 || (uint32_t)(xbuf[tid - 1] >> 32) != myleaf);
   const unsigned bal = __ballot_sync(0xffffffffu, head);
   if (lane == 0) warp_cnt[warp] = __popc(bal);
   __syncthreads();
@@ -489,17 +535,18 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   if (head) {
     const int u = warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
     ukey[u] = myleaf;
-    upos[u] = 0xffffffffu - (uint32_t)(mykey & 0xffffffffull);
+    upos[u] = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
   }
   cp_async_wait_all();
   __syncthreads();
+  RLB_TICK(4);
   const int m = s_total;
 
-  // ---- 4. per distinct leaf: merge level, leaf write, first deposit
+  // ---- 4. per distinct leaf: merge level, first deposit
   bool alive = tid < m;
   uint32_t leafnode = 0, pos = 0;
   int L = 0, my_next = -1;
-  T vs = (T)0, vm = (T)0;
+  T vs = (T)0, vm = (T)0, leaf_v = (T)0;
   if (alive) {
     leafnode = ukey[tid];
     pos = upos[tid];
@@ -507,28 +554,34 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     if constexpr (FUSED) v = (T)pow_like_torch(add_rn((float)v, eps), alpha);
     vs = v;
     vm = v;
+    leaf_v = v;
     L = (tid == 0) ? depth + 1 : 32 - __clz(leafnode ^ ukey[tid - 1]);
     Lsm[tid] = L;
     my_next = (tid + 1 < m) ? tid + 1 : -1;
     nxt[tid] = my_next;
-    if (sum) sum[leafnode] = v;
-    if (mn) mn[leafnode] = v;
     if (L == 1) {  // merges with its left neighbour already at level 1: hand over the leaf value
       dep_s[tid] = vs;
       dep_m[tid] = vm;
     }
   }
   __syncthreads();
+  RLB_TICK(5);
 
-  // ---- 5. climb
-  const T *sib_s = sib + pos;
-  const T *sib_m = sib + (size_t)depth * NP + pos;
+  // ---- 5. climb.  Nothing but registers and shared memory inside the loop: the parent computed at level l
+  // overwrites the (consumed) sibling slot [l][pos] and is flushed to the global trees afterwards -- a global
+  // store before a barrier would make every level wait for its L2 acknowledgement.  (An event-driven variant
+  // that folds untouched-sibling levels lazily was 3x slower: lanes of a warp have their events at different
+  // levels, so the lazy loops serialise under SIMT.)
+  T *io_s = sib + pos;
+  T *io_m = sib + (size_t)depth * NP + pos;
+  int levels_done = 0;
   for (int l = 0; l < depth; ++l) {
     if (alive) {
       if (L == l + 1) {
         alive = false;  // my level-l value was deposited; the group on my left carries the parent
       } else {
         const uint32_t node = leafnode >> l;
+        const uint32_t off = (uint32_t)l * (uint32_t)NP;
         T os, om;
         if ((node & 1u) == 0u && my_next >= 0 && Lsm[my_next] == l + 1) {
           os = dep_s[my_next];  // touched right sibling: value deposited by the item that merges into me
@@ -536,15 +589,14 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
           my_next = nxt[my_next];
           nxt[tid] = my_next;
         } else {
-          os = sib_s[(size_t)l * NP];  // untouched sibling: its old global value
-          om = sib_m[(size_t)l * NP];
+          os = io_s[off];  // untouched sibling: its old global value
+          om = io_m[off];
         }
-        // node = op(left child, right child)
-        vs = (node & 1u) ? tree_op<T, false>(os, vs) : tree_op<T, false>(vs, os);
+        vs = tree_op<T, false>(vs, os);  // IEEE addition commutes: operand order is immaterial for the sum
         vm = (node & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
-        const uint32_t parent = node >> 1;
-        if (sum) sum[parent] = vs;
-        if (mn) mn[parent] = vm;
+        io_s[off] = vs;  // value of node (leafnode >> (l + 1))
+        io_m[off] = vm;
+        levels_done = l + 1;
         if (L == l + 2) {  // I merge into my left group at the next level: deposit the value just computed
           dep_s[tid] = vs;
           dep_m[tid] = vm;
@@ -553,6 +605,19 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     }
     __syncthreads();
   }
+  RLB_TICK(6);
+
+  // ---- 6. flush: leaf + every ancestor this item carried (each touched node is written exactly once)
+  if (tid < m) {
+    if (sum) sum[leafnode] = leaf_v;
+    if (mn) mn[leafnode] = leaf_v;
+    for (int l = 0; l < levels_done; ++l) {
+      const uint32_t parent = leafnode >> (l + 1);
+      if (sum) sum[parent] = io_s[(size_t)l * NP];
+      if (mn) mn[parent] = io_m[(size_t)l * NP];
+    }
+  }
+  RLB_TICK(7);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -675,6 +740,8 @@ static int tree_rebuild_impl(void *tree_, int64_t capacity, int is_min, cudaStre
 
 constexpr int kUpdateSmemLimit = 224 * 1024;  // dynamic shared memory the single-CTA update may use
 
+long long *g_debug_ticks = nullptr;  // set by rlb_debug_set_tick_buffer (profiling only)
+
 struct FusedPow {
   bool on = false;
   float alpha = 0.f, eps = 0.f;
@@ -695,8 +762,8 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
     if (rc) return rc;
     attr_set = true;
   }
-  // phase A grid: ~4 scattered sibling reads per thread, at most one CTA per SM
-  int64_t grid = (2 * (int64_t)depth * np + 4 * (int64_t)np - 1) / (4 * (int64_t)np);
+  // phase A grid: one scattered sibling read per thread (2 * depth CTAs), at most one CTA per SM
+  int64_t grid = 2 * (int64_t)depth;
   const int sms = sm_count();
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
@@ -704,7 +771,7 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   T *scratch = reinterpret_cast<T *>(static_cast<unsigned char *>(workspace) + kUpdCtrlBytes);
   tree_update_cta_kernel<T, FUSED><<<(unsigned)grid, np, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n,
                                                                     scalar, fp.alpha, fp.eps, fp.max_out, ticket,
-                                                                    scratch);
+                                                                    scratch, g_debug_ticks);
   return check_launch("tree_update_cta_kernel");
 }
 
@@ -766,6 +833,10 @@ static int tree_update_impl(void *sum_, void *mn_, int64_t capacity, const int64
 using namespace rlb;
 
 extern "C" {
+
+/* profiling aid (not part of the public header): device buffer of >= 8 int64 that the single-launch update
+ * kernel fills with clock64() stamps at its phase boundaries; NULL disables. */
+void rlb_debug_set_tick_buffer(void *p) { rlb::g_debug_ticks = static_cast<long long *>(p); }
 
 int64_t rlb_tree_capacity(int64_t size) {
   int64_t c = 1;
@@ -890,16 +961,20 @@ int rlb_per_sample(const void *sum_tree, const void *min_tree, int64_t size, int
   if (B == 0) return RLB_OK;
   RLB_REQUIRE(u && index_out && weight_out, RLB_EINVAL, "rlb_per_sample: null u/index_out/weight_out");
   const int depth = ilog2_i64(capacity);
+  const int sms = sm_count();
+  const int speculative = B <= (int64_t)sms * 64;          // latency-bound regime: 4 levels per round trip
   const int threads = 128;
   const unsigned blocks = (unsigned)((B + threads - 1) / threads);
   if (dtype == RLB_F32)
     per_sample_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(
         (const float *)sum_tree, (const float *)min_tree, size, capacity, depth, len, (const float *)u, B,
-        (float)(-beta), cpu_semantics, index_out, weight_out, (float *)leaf_out, (float *)psum_pmin_out, status);
+        (float)(-beta), cpu_semantics, speculative, index_out, weight_out, (float *)leaf_out,
+        (float *)psum_pmin_out, status);
   else if (dtype == RLB_F64)
     per_sample_kernel<double><<<blocks, threads, 0, as_stream(stream)>>>(
         (const double *)sum_tree, (const double *)min_tree, size, capacity, depth, len, (const double *)u, B,
-        -beta, cpu_semantics, index_out, weight_out, (double *)leaf_out, (double *)psum_pmin_out, status);
+        -beta, cpu_semantics, speculative, index_out, weight_out, (double *)leaf_out, (double *)psum_pmin_out,
+        status);
   else
     RLB_REQUIRE(false, RLB_EINVAL, "rlb_per_sample: unsupported dtype %d", dtype);
   return check_launch("per_sample_kernel");
