@@ -253,22 +253,53 @@ def run_ours(args) -> dict:
             dist.barrier()
             torch.cuda.synchronize()
 
+    side_gae, side_upd = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    smp = rb.sampler
+    smp.record_index_event = True
+
     def make_step(slot: int):
         v, nv, r, d8, t8 = ring8[slot]
 
         def step():
-            batch = rb.sample()                                   # rand -> per_sample -> gather [-> all-gather]
-            rb.update_priority(batch.get("index"), td_err)         # fused pow + tree write-back
+            # three independent chains of the same step run on three streams (fork / join with events):
+            #   main      rand -> per_sample -> gather [-> all-gather]
+            #   side_upd  update_priority(index): needs the sampled indices only, overlaps the gather
+            #   side_gae  GAE of this step's rollout: independent of the replay path
+            main = torch.cuda.current_stream(dev)
+            side_gae.wait_stream(main)
+            with torch.cuda.stream(side_gae):
+                a, tg = be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
+            batch = rb.sample()
+            index = batch.get("index")
+            if distributed:
+                side_upd.wait_stream(main)           # global indices exist only after the all-gather
+            else:
+                side_upd.wait_event(smp.index_ready)
+            with torch.cuda.stream(side_upd):
+                rb.update_priority(index, td_err)    # fused pow + tree write-back
+            main.wait_stream(side_upd)
+            main.wait_stream(side_gae)
+            return batch, a, tg
+
+        return step
+
+    def make_eager_step(slot: int):
+        v, nv, r, d8, t8 = ring8[slot]
+
+        def step():  # the plain single-stream call sequence a Python training loop would issue
+            batch = rb.sample()
+            rb.update_priority(batch.get("index"), td_err)
             a, tg = be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
             return batch, a, tg
 
         return step
 
     steps = [make_step(i) for i in range(R)]
+    eager_steps = [make_eager_step(i) for i in range(R)]
 
     # ---- (1) eager: every call goes through the Python API
     clocks = ClockSampler(local) if rank == 0 else None
-    ms_eager = timed(lambda i: steps[i % R](), args.steps, args.warmup, sync_all)
+    ms_eager = timed(lambda i: eager_steps[i % R](), args.steps, args.warmup, sync_all)
 
     # ---- (2) the same steps captured once into CUDA graphs (one per GAE input set) and replayed
     graphs, graph_err = None, None

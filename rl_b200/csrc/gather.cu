@@ -27,7 +27,7 @@ namespace rlb {
 
 constexpr int kGatherThreads = 128;              // both roles
 constexpr int kPipes = kGatherThreads / 32;      // DMA pipelines (warps) per bulk CTA
-constexpr int kStages = 6;                       // ring depth per pipeline
+constexpr int kStages = 5;                       // ring depth per pipeline (161 KB/CTA: leaves room for a co-resident update CTA)
 constexpr int kAhead = 3;                        // loads kept in flight ahead of the store front
 constexpr uint32_t kChunk = 8192;                // bytes per stage
 constexpr int kVecUnroll = 4;                    // units per thread per tile (vector role)
@@ -365,6 +365,12 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
     int rc = check_cuda(cudaFuncSetAttribute(gather_kernel<SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kBulkSmemBytes),
                         "cudaFuncSetAttribute(gather_kernel)");
+    if (rc) return rc;
+    // ask for the largest shared-memory carveout so that a CTA of another kernel (the priority update runs
+    // concurrently on a side stream) can still become resident next to a 161 KB gather CTA
+    rc = check_cuda(cudaFuncSetAttribute(gather_kernel<SCATTER>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared),
+                    "cudaFuncSetAttribute(gather_kernel, carveout)");
     if (rc) return rc;
     attr_set = true;
   }

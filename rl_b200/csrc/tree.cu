@@ -760,6 +760,11 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmemLimit),
                         "cudaFuncSetAttribute(tree_update_cta_kernel)");
     if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T, FUSED>,
+                                         cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared),
+                    "cudaFuncSetAttribute(tree_update_cta_kernel, carveout)");
+    if (rc) return rc;
     attr_set = true;
   }
   // phase A grid: one scattered sibling read per thread (2 * depth CTAs), at most one CTA per SM

@@ -165,6 +165,11 @@ class PrioritizedSampler(Sampler):
         self._semantics = semantics
         self._sum_tree = None
         self._min_tree = None
+        #: when set to True, ``sample`` records ``index_ready`` (a CUDA event) right after the tree kernel, so work
+        #: that only needs the sampled indices -- typically ``update_priority`` on a side stream -- can overlap
+        #: with the storage gather that follows on the sampling stream.
+        self.record_index_event = False
+        self.index_ready = None
         self._has_max_priority = False
         self._max_priority_index = None
         if self._device is not None:
@@ -294,6 +299,10 @@ class PrioritizedSampler(Sampler):
         index, weight = ops.backend().per_sample(
             self._sum_tree.values, self._min_tree.values, self._max_capacity, self._sum_tree.capacity, length, u,
             self._beta, self._semantics == "cpu", status=self._status)
+        if self.record_index_event and dev.type == "cuda":
+            if self.index_ready is None:
+                self.index_ready = torch.cuda.Event()
+            self.index_ready.record(torch.cuda.current_stream(dev))
         if storage.ndim > 1:
             index = unravel_index(index, storage.shape)
         return index, {"priority_weight": weight}
