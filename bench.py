@@ -301,13 +301,38 @@ def run_ours(args) -> dict:
     clocks = ClockSampler(local) if rank == 0 else None
     ms_eager = timed(lambda i: eager_steps[i % R](), args.steps, args.warmup, sync_all)
 
-    # ---- (2) the same steps captured once into CUDA graphs (one per GAE input set) and replayed
-    graphs, graph_err = None, None
+    # ---- (2) the same steps captured once into CUDA graphs (one per GAE input set) and replayed.  With N > 1 the
+    # NCCL all-gather is issued eagerly between two captured halves: [local draw into the send buffer] and
+    # [weights + priority write-back + GAE].
+    graphs, graph_err, ms_graph = None, None, None
     try:
         gen = rb.sampler._rng
-        graphs = [CudaGraphStep(st, generators=[gen], warmup=1) for st in steps]
-        ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
-    except Exception as err:  # e.g. a collective that cannot be captured
+        if not distributed:
+            graphs = [CudaGraphStep(st, generators=[gen], warmup=1) for st in steps]
+            ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
+        else:
+            draw = CudaGraphStep(lambda: rb.local_draw(static_buffers=True), generators=[gen], warmup=1)
+
+            def make_tail(slot: int):
+                v, nv, r, d8, t8 = ring8[slot]
+
+                def tail():
+                    batch = rb.finalize()
+                    rb.update_priority(batch.get("index"), td_err)
+                    return batch, be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
+
+                return tail
+
+            rb.exchange()
+            tails = [CudaGraphStep(make_tail(i), warmup=1) for i in range(R)]
+
+            def graph_step(i):
+                draw()
+                rb.exchange()
+                return tails[i % R]()
+
+            ms_graph = timed(graph_step, args.steps, args.warmup, sync_all)
+    except Exception as err:
         graph_err = f"{type(err).__name__}: {err}"[:200]
         graphs, ms_graph = None, None
     clk = clocks.stop() if clocks else None
@@ -408,7 +433,7 @@ def run_ours(args) -> dict:
             "config": {"workload": f"C2 PER sample+update B=256 @1M Atari transitions ({n_leaves} leaves) + C3 GAE [4096,128]",
                        "capacity_per_gpu": CAPACITY, "batch_per_gpu": BATCH, "gae_shape": [GAE_ROWS, GAE_T, 1],
                        "alpha": ALPHA, "beta": BETA, "gamma": GAMMA, "lmbda": LMBDA,
-                       "launch": "cuda_graph replay of the public-API step" if ms_graph is not None else "eager python API",
+                       "launch": ("cuda_graph replay of the public-API step" + (" (NCCL all-gather eager between two graphs)" if world > 1 else "")) if ms_graph is not None else "eager python API",
                        "parallelism": f"capacity-sharded x{world}, 1 all-gather/sample" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (56 GB storage, random rows; GAE inputs rotate through >160 MB)"},
             "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
@@ -553,6 +578,20 @@ def run_reference(args) -> dict | None:
             "e2e": {"value": cpu["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def _watchdog(seconds: float) -> None:
+    """A hung collective must not hang the caller: after `seconds` the process prints what it knows and exits."""
+    def fire():
+        rank = int(os.environ.get("RANK", 0))
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "error": f"bench.py watchdog fired after {seconds:.0f} s",
+                              "n_gpus": int(os.environ.get("WORLD_SIZE", 1))}), flush=True)
+        os._exit(3)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -562,6 +601,7 @@ def main() -> None:
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    _watchdog(float(os.environ.get("RLB_BENCH_TIMEOUT", "840")))
     if args.impl == "reference":
         res = run_reference(args)
     else:

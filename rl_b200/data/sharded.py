@@ -100,6 +100,9 @@ class ShardedPrioritizedReplayBuffer:
             storage=LazyTensorStorage(self.shard_capacity, device=self.device),
             batch_size=None if batch_size is None else batch_size // self.world, generator=generator)
         self._layout = None
+        self._static = None
+        self._send = self._recv = None
+        self._bs = None
         self.local_index = None  # local indices of this rank's last draw
 
     # ---- writes: every rank feeds its own shard (data-parallel collectors) --------------------------------
@@ -120,13 +123,24 @@ class ShardedPrioritizedReplayBuffer:
         return self.local.storage
 
     # ---- sample --------------------------------------------------------------------------------------
-    def sample(self, batch_size: int | None = None):
+    # sample() = local_draw() -> exchange() -> finalize().  The three stages are public so that a training step can
+    # capture the two compute stages in CUDA graphs and issue the collective eagerly in between.
+    def _resolve_batch(self, batch_size):
         if batch_size is None:
             batch_size = self._batch_size
         if batch_size is None:
             raise RuntimeError("batch_size not specified.")
         if batch_size % self.world:
             raise ValueError(f"batch_size={batch_size} must be divisible by the world size {self.world}")
+        return batch_size
+
+    def local_draw(self, batch_size: int | None = None, *, static_buffers: bool = False) -> torch.Tensor:
+        """Draw ``batch_size / world`` rows from this shard straight into the packed send buffer (returned).
+
+        ``static_buffers=True`` reuses one send / receive buffer pair across calls (needed under CUDA-graph capture;
+        the returned batch is then overwritten by the next sample).
+        """
+        batch_size = self._resolve_batch(batch_size)
         b_loc = batch_size // self.world
         st, smp = self.local.storage, self.local.sampler
         smp._maybe_init_from_storage(st)
@@ -135,15 +149,22 @@ class ShardedPrioritizedReplayBuffer:
             raise RuntimeError("Cannot sample from an empty storage.")
         be = ops.backend()
         dev = smp._sum_tree.device
+        if self._layout is None:
+            self._layout = _PackedLayout(st._leaves)
+        lay = self._layout
+        if static_buffers:
+            if self._static is None or self._static[0].shape[0] != b_loc:
+                self._static = (torch.empty((b_loc, lay.row), dtype=torch.uint8, device=dev),
+                                torch.empty((batch_size, lay.row), dtype=torch.uint8, device=dev))
+            send, recv = self._static
+        else:
+            send = torch.empty((b_loc, lay.row), dtype=torch.uint8, device=dev)
+            recv = torch.empty((batch_size, lay.row), dtype=torch.uint8, device=dev) if self.world > 1 else send
         with self.local._replay_lock:
             u = torch.rand(b_loc, device=dev, generator=smp._rng, dtype=smp._sum_tree._dtype)
             idx, _, leaf, pp = be.per_sample(smp._sum_tree.values, smp._min_tree.values, smp._max_capacity,
                                              smp._sum_tree.capacity, length, u, smp._beta, smp._semantics == "cpu",
                                              status=smp._status, want_aux=True)
-            if self._layout is None:
-                self._layout = _PackedLayout(st._leaves)
-            lay = self._layout
-            send = torch.empty((b_loc, lay.row), dtype=torch.uint8, device=dev)
             be.gather(st._leaves, idx, length, out=lay.leaf_views(send))
         gidx, pi, S, m = lay.meta_views(send)
         gidx.copy_(idx + self.rank * self.shard_capacity)
@@ -151,22 +172,33 @@ class ShardedPrioritizedReplayBuffer:
         S.copy_(pp[0].expand(b_loc))
         m.copy_(pp[1].expand(b_loc))
         self.local_index = idx
+        self._send, self._recv, self._bs = send, recv, batch_size
+        return send
+
+    def exchange(self) -> torch.Tensor:
+        """The ONE collective of sample(): all-gather the packed local draws (NCCL over NVLink)."""
         if self.world > 1:
-            recv = torch.empty((batch_size, lay.row), dtype=torch.uint8, device=dev)
-            self._dist.all_gather_into_tensor(recv, send, group=self.group)  # the ONE collective of sample()
-        else:
-            recv = send
+            self._dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        return self._recv
+
+    def finalize(self):
+        """Views of the gathered buffer as the global batch + importance weights over the whole sharded buffer."""
+        lay, recv, smp = self._layout, self._recv, self.local.sampler
         leaves = lay.leaf_views(recv)
         gidx, pi, S, m = lay.meta_views(recv)
-        batch = unflatten_data(leaves, st._spec, (batch_size,))
-        # importance weights normalised over the whole (sharded) buffer; identical on every rank
+        batch = unflatten_data(leaves, self.local.storage._spec, (self._bs,))
         ratio = pi / S
-        weight = torch.pow(ratio / (m / S).min(), -smp._beta)
+        weight = torch.pow(ratio / (m / S).min(), -smp._beta)  # identical on every rank
         if is_tensor_collection(batch):
             batch.set("index", gidx)
             batch.set("priority_weight", weight)
             return batch
         return batch, {"index": gidx, "priority_weight": weight}
+
+    def sample(self, batch_size: int | None = None):
+        self.local_draw(batch_size)
+        self.exchange()
+        return self.finalize()
 
     # ---- priority write-back ---------------------------------------------------------------------------
     def update_priority(self, index: torch.Tensor, priority) -> None:
