@@ -64,6 +64,13 @@ const char *rlb_last_error(void);
 /* Number of SMs of the current device (grid sizing is a multiple of this); <0 on error. */
 int rlb_device_sm_count(void);
 
+/* Keep [ptr, ptr+bytes) (the sampler's sum+min trees: 16 MB for 1M slots) resident in the 126 MB L2 for
+ * kernels subsequently launched on (or captured from) `stream`: sets the persisting-L2 carve-out and the
+ * stream's access-policy window (hit = persisting, miss = streaming).  The 29 MB that every sampled batch
+ * streams through L2 otherwise evicts the lower tree levels between steps.  ptr == NULL clears the window.
+ * Returns > 0 (MiB set aside + 1) on success, 0 when the device has no persisting L2, < 0 on error. */
+int rlb_l2_persist(const void *ptr, size_t bytes, rlb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Segment tree  -- replaces the pybind classes {Sum,Min}SegmentTreeFp{32,64} /
  * Cuda{Sum,Min}SegmentTreeFp{32,64} of torchrl._torchrl

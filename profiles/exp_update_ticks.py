@@ -12,7 +12,7 @@ N = 1_000_000
 for B in (256, 1024):
     smp = PrioritizedSampler(N, 0.6, 0.4, device=dev)
     smp.update_priority(torch.arange(N, device=dev), torch.rand(N, device=dev))
-    ticks = torch.zeros(8, dtype=torch.int64, device=dev)
+    ticks = torch.zeros(16, dtype=torch.int64, device=dev)
     be.L.rlb_debug_set_tick_buffer(ticks.data_ptr())
     for it in range(4):
         idx = torch.randint(0, N, (B,), device=dev)
@@ -21,6 +21,12 @@ for B in (256, 1024):
         smp.update_priority(idx, p)
         torch.cuda.synchronize()
         t = ticks.tolist()
-        d = [t[i + 1] - t[i] for i in range(6)]
-        print(f"B={B} it={it}: phaseA+ticket {d[0]}  keys {d[1]}  sort {d[2]}  compact+cpwait {d[3]}  init {d[4]}  climb {d[5]}  total {t[6]-t[0]} cycles")
+        d = [t[i + 1] - t[i] for i in range(7)]
+        print(f"UPD B={B} it={it}: phaseA+ticket {d[0]}  keys {d[1]}  sort {d[2]}  compact+cpwait {d[3]}  init {d[4]}  climb {d[5]}  flush-issue {d[6]}  total {t[7]-t[0]} cycles")
+        u = torch.rand(B, device=dev)
+        torch.cuda.synchronize()
+        be.per_sample(smp._sum_tree.values, smp._min_tree.values, N, smp._sum_tree.capacity, N, u, 0.4, True)
+        torch.cuda.synchronize()
+        t = ticks.tolist()
+        print(f"SMP B={B} it={it}: psum+sync {t[9]-t[8]}  descent {t[10]-t[9]}  leaf+pow+store {t[11]-t[10]}  total {t[11]-t[8]} cycles")
     be.L.rlb_debug_set_tick_buffer(None)

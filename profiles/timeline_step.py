@@ -22,6 +22,9 @@ td_err = torch.rand(bench.BATCH, device=dev, generator=g)
 smp = rb.sampler
 smp.record_index_event = True
 side_gae, side_upd = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+import os
+if os.environ.get('RLB_PIN_L2') == '1':
+    print('pin_l2 ->', smp.pin_l2(), smp.pin_l2(side_upd))
 
 
 def step():
@@ -60,3 +63,11 @@ evs.sort(key=lambda e: e.time_range.start)
 t0 = evs[0].time_range.start
 for e in evs:
     print(f"{e.time_range.start - t0:9.2f} -> {e.time_range.end - t0:9.2f} us  ({e.time_range.end - e.time_range.start:6.2f})  {e.name[:70]}")
+from collections import defaultdict
+agg = defaultdict(list)
+for e in evs:
+    agg[e.name[:50]].append(e.time_range.end - e.time_range.start)
+for k, v in agg.items():
+    print(f"AVG {sum(v)/len(v):7.2f} us x{len(v):2d}  {k}")
+span = evs[-1].time_range.end - evs[0].time_range.start
+print(f"SPAN {span:.1f} us for 6 steps")

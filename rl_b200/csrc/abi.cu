@@ -50,4 +50,39 @@ const char *rlb_last_error(void) { return rlb::g_err; }
 
 int rlb_device_sm_count(void) { return rlb::sm_count(); }
 
+int rlb_l2_persist(const void *ptr, size_t bytes, rlb_stream_t stream) {
+  using namespace rlb;
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  int max_persist = 0, max_window = 0;
+  rc = check_cuda(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev),
+                  "cudaDeviceGetAttribute(MaxPersistingL2CacheSize)");
+  if (rc) return rc;
+  rc = check_cuda(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev),
+                  "cudaDeviceGetAttribute(MaxAccessPolicyWindowSize)");
+  if (rc) return rc;
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (ptr == nullptr || bytes == 0 || max_persist <= 0 || max_window <= 0) {
+    attr.accessPolicyWindow.num_bytes = 0;  // clears the window
+    check_cuda(cudaStreamSetAttribute(as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr),
+               "cudaStreamSetAttribute(clear)");
+    return 0;
+  }
+  size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+  rc = check_cuda(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want), "cudaDeviceSetLimit(PersistingL2)");
+  if (rc) return rc;
+  const size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+  attr.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
+  attr.accessPolicyWindow.num_bytes = win;
+  attr.accessPolicyWindow.hitRatio = want >= win ? 1.0f : (float)want / (float)win;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  rc = check_cuda(cudaStreamSetAttribute(as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr),
+                  "cudaStreamSetAttribute(AccessPolicyWindow)");
+  if (rc) return rc;
+  return (int)(want >> 20) + 1;  // > 0: MiB of L2 set aside (+1)
+}
+
 }  // extern "C"

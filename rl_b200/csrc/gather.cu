@@ -174,6 +174,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
   if (pos >= end) return;
   uint8_t *my_ring = ring + (size_t)warp * kStages * kChunk;
   PipeSmem *my = ps + warp;
+  const uint64_t policy = l2_policy_evict_first();
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&my->full[s], 1);
     fence_mbar_init();
@@ -218,7 +219,8 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
         my->dst[stage] = L.dst + b * L.ostride + off;
         my->bytes[stage] = (uint32_t)nbytes;
         mbar_arrive_expect_tx(&my->full[stage], (uint32_t)nbytes);
-        bulk_g2s(my_ring + (size_t)stage * kChunk, L.src + ix * L.stride + off, (uint32_t)nbytes, &my->full[stage]);
+        bulk_g2s_hint(my_ring + (size_t)stage * kChunk, L.src + ix * L.stride + off, (uint32_t)nbytes,
+                      &my->full[stage], policy);
       }
       ++n_loaded;
       // advance the cursor

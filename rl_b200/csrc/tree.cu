@@ -25,6 +25,8 @@
 
 namespace rlb {
 
+long long *g_debug_ticks = nullptr;  // set by rlb_debug_set_tick_buffer (profiling only)
+
 // ------------------------------------------------------------------------------------------------
 // fill / rebuild / query / at
 // ------------------------------------------------------------------------------------------------
@@ -264,21 +266,27 @@ __device__ __forceinline__ T warp_query_prefix(const T *__restrict__ tree, int64
   return ret;
 }
 
-// Small batches are latency-bound (one dependent round trip per descent step) and use the 4-level speculative
-// descent; large batches are bound by L1 sector wavefronts (every lane chases its own path) and use the plain
-// one-load-per-level descent: half the wavefronts, with the latency hidden by occupancy.
+// Every lane chases its own root-to-leaf path, so each warp-level load touches 32 different lines and one SM's L1
+// retires only about one such sector wavefront every ~2 cycles: with 128 samples per SM a 4-level round costs
+// 2.6k cycles instead of one ~1k-cycle round trip (clock64-instrumented, profiles/README.md).  Small batches are
+// therefore SPREAD: `spc` samples per 32-thread CTA, chosen so that the grid covers ~2 CTAs per SM (B=256 -> one
+// sample per CTA on 256 CTAs), and use the 4-level speculative descent (latency-bound).  Large batches fill
+// 128-thread CTAs and use the plain one-load-per-level descent: half the wavefronts, latency hidden by occupancy.
 template <typename T>
 __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ sum, const T *__restrict__ mn,
                                                          int64_t size, int64_t capacity, int depth, int64_t len,
                                                          const T *__restrict__ u, int64_t B, T neg_beta,
-                                                         int cpu_semantics, int speculative,
+                                                         int cpu_semantics, int speculative, int spc,
                                                          int64_t *__restrict__ index_out,
                                                          float *__restrict__ weight_out, T *leaf_out,
-                                                         T *psum_pmin_out, int32_t *status) {
+                                                         T *psum_pmin_out, int32_t *status, long long *dbg) {
   __shared__ T s_p[2];
+  if (dbg && (blockIdx.x != 0 || threadIdx.x != 0)) dbg = nullptr;
+  if (dbg) dbg[8] = (long long)clock64();
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool lane_on = (int)threadIdx.x < spc;  // spc == blockDim.x for full CTAs
+  const int64_t i = lane_on ? blockIdx.x * (int64_t)spc + threadIdx.x : B;
   const T ui = (i < B) ? __ldg(u + i) : (T)0;  // in flight while p_sum / p_min are resolved
   // p_sum by warp 0, p_min by warp 1 (or both by warp 0 in single-warp CTAs)   (samplers.py:901-908)
   const bool root = cpu_semantics && (len >= size);  // csrc/segment_tree.h:145-147 fast path (l == 0)
@@ -305,9 +313,11 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
     }
   }
   if (i >= B) return;
+  if (dbg) dbg[9] = (long long)clock64();
   const T mass = mul_rn(ui, p_sum);  // samplers.py:919 / :923 -- one rounding, never fused downstream
   int64_t idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1), speculative != 0);
   if (idx > len - 1) idx = len - 1;  // samplers.py:933
+  if (dbg) dbg[10] = (long long)clock64() + (idx & 0);
   T leaf = __ldg(sum + (idx | capacity));
   if (cpu_semantics) {
     // samplers.py:935-943 (CPU trees only): walk left past zero-priority leaves
@@ -323,7 +333,9 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   }
   index_out[i] = idx;
   if (leaf_out) leaf_out[i] = leaf;
-  weight_out[i] = (float)pow_like_torch(leaf / p_min, neg_beta);  // samplers.py:953
+  const float w = (float)pow_like_torch(leaf / p_min, neg_beta);  // samplers.py:953
+  weight_out[i] = w;
+  if (dbg) dbg[11] = (long long)clock64() + (w > 1e30f ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -740,8 +752,6 @@ static int tree_rebuild_impl(void *tree_, int64_t capacity, int is_min, cudaStre
 
 constexpr int kUpdateSmemLimit = 224 * 1024;  // dynamic shared memory the single-CTA update may use
 
-long long *g_debug_ticks = nullptr;  // set by rlb_debug_set_tick_buffer (profiling only)
-
 struct FusedPow {
   bool on = false;
   float alpha = 0.f, eps = 0.f;
@@ -967,19 +977,25 @@ int rlb_per_sample(const void *sum_tree, const void *min_tree, int64_t size, int
   RLB_REQUIRE(u && index_out && weight_out, RLB_EINVAL, "rlb_per_sample: null u/index_out/weight_out");
   const int depth = ilog2_i64(capacity);
   const int sms = sm_count();
-  const int speculative = B <= (int64_t)sms * 64;          // latency-bound regime: 4 levels per round trip
-  const int threads = 128;
-  const unsigned blocks = (unsigned)((B + threads - 1) / threads);
+  const int speculative = B <= (int64_t)sms * 64;  // latency-bound regime: 4 levels per round trip
+  int threads = 128, spc = 128;
+  if (speculative) {  // spread: ~2 single-warp CTAs per SM, each with as few samples as that allows
+    threads = 32;
+    spc = (int)((B + 2 * (int64_t)sms - 1) / (2 * (int64_t)sms));
+    if (spc < 1) spc = 1;
+    if (spc > 32) spc = 32;
+  }
+  const unsigned blocks = (unsigned)((B + spc - 1) / spc);
   if (dtype == RLB_F32)
     per_sample_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(
         (const float *)sum_tree, (const float *)min_tree, size, capacity, depth, len, (const float *)u, B,
-        (float)(-beta), cpu_semantics, speculative, index_out, weight_out, (float *)leaf_out,
-        (float *)psum_pmin_out, status);
+        (float)(-beta), cpu_semantics, speculative, spc, index_out, weight_out, (float *)leaf_out,
+        (float *)psum_pmin_out, status, g_debug_ticks);
   else if (dtype == RLB_F64)
     per_sample_kernel<double><<<blocks, threads, 0, as_stream(stream)>>>(
         (const double *)sum_tree, (const double *)min_tree, size, capacity, depth, len, (const double *)u, B,
-        -beta, cpu_semantics, speculative, index_out, weight_out, (double *)leaf_out, (double *)psum_pmin_out,
-        status);
+        -beta, cpu_semantics, speculative, spc, index_out, weight_out, (double *)leaf_out, (double *)psum_pmin_out,
+        status, g_debug_ticks);
   else
     RLB_REQUIRE(false, RLB_EINVAL, "rlb_per_sample: unsupported dtype %d", dtype);
   return check_launch("per_sample_kernel");

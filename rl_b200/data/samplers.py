@@ -235,13 +235,16 @@ class PrioritizedSampler(Sampler):
 
     def _init(self) -> None:
         if self.dtype in (torch.float, torch.float32):
-            self._sum_tree = SumSegmentTreeFp32(self._max_capacity, self._device)
-            self._min_tree = MinSegmentTreeFp32(self._max_capacity, self._device)
+            sum_cls, min_cls, dt = SumSegmentTreeFp32, MinSegmentTreeFp32, torch.float32
         elif self.dtype in (torch.double, torch.float64):
-            self._sum_tree = SumSegmentTreeFp64(self._max_capacity, self._device)
-            self._min_tree = MinSegmentTreeFp64(self._max_capacity, self._device)
+            sum_cls, min_cls, dt = SumSegmentTreeFp64, MinSegmentTreeFp64, torch.float64
         else:
             raise NotImplementedError(f"dtype {self.dtype} not supported by PrioritizedSampler")
+        # both heaps live in ONE allocation so that a single L2 access-policy window can keep them resident
+        cap2 = 2 * ops.backend().tree_capacity(self._max_capacity)
+        self._tree_buf = torch.empty(2 * cap2, dtype=dt, device=self._device)
+        self._sum_tree = sum_cls(self._max_capacity, self._device, out=self._tree_buf[:cap2])
+        self._min_tree = min_cls(self._max_capacity, self._device, out=self._tree_buf[cap2:])
         dev = self._sum_tree.device
         # running max of the RAW priorities ever passed to update_priority (samplers.py:1054-1075), kept on
         # the device so that no call has to synchronise; -inf until the first update.
@@ -255,6 +258,13 @@ class PrioritizedSampler(Sampler):
     def _empty(self) -> None:
         if self._device is not None:
             self._init()
+
+    def pin_l2(self, stream=None) -> int:
+        """Keep both trees resident in L2 for kernels launched on / captured from ``stream`` (default: the current
+        stream).  Returns the MiB set aside (+1), or 0 when the device has no persisting L2."""
+        if self._sum_tree is None:
+            raise RuntimeError("the trees do not exist yet (no device known)")
+        return ops.backend().l2_persist(self._tree_buf, stream)
 
     def _tree_epoch(self) -> int:
         self._epoch += 1

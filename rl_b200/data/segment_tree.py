@@ -26,7 +26,7 @@ class _DeviceSegmentTree:
     _is_min = False
     _dtype = torch.float32
 
-    def __init__(self, size: int, device="cuda"):
+    def __init__(self, size: int, device="cuda", *, out: torch.Tensor | None = None):
         size = int(size)
         if size <= 0:
             raise ValueError("segment tree size must be positive")
@@ -34,7 +34,7 @@ class _DeviceSegmentTree:
         self._device = torch.device(device)
         be = ops.backend()
         self._capacity = be.tree_capacity(size)
-        self._values = be.tree_new(size, self._is_min, self._dtype, self._device)
+        self._values = be.tree_new(size, self._is_min, self._dtype, self._device, out=out)
         self._workspace = None  # persistent update scratch (ticket, sibling tile, stamps), allocated on first update
         self._epoch = 0
 

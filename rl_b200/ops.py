@@ -32,6 +32,7 @@ _SIGNATURES = {
     "rlb_version": (ctypes.c_int, []),
     "rlb_last_error": (ctypes.c_char_p, []),
     "rlb_device_sm_count": (ctypes.c_int, []),
+    "rlb_l2_persist": (_i32, [_vp, _sz, _vp]),
     "rlb_tree_capacity": (_i64, [_i64]),
     "rlb_tree_update_workspace_bytes": (_sz, [_i64]),
     "rlb_tree_fill": (_i32, [_vp, _i64, _i32, _i32, _vp]),
@@ -130,13 +131,28 @@ class CudaBackend:
             if self.ctx is not None:
                 self.ctx.__exit__(*a)
 
+    def l2_persist(self, tensor: torch.Tensor | None, stream: "torch.cuda.Stream | None" = None) -> int:
+        """Ask for `tensor`'s bytes to stay L2-resident for kernels launched on `stream` (default: current)."""
+        if tensor is None:
+            s = (stream or torch.cuda.current_stream()).cuda_stream
+            return int(self.L.rlb_l2_persist(None, 0, s))
+        dev = self._cuda(tensor)
+        s = (stream or torch.cuda.current_stream(dev)).cuda_stream
+        with self._Guard(dev):
+            rc = int(self.L.rlb_l2_persist(tensor.data_ptr(), tensor.numel() * tensor.element_size(), s))
+        if rc < 0:
+            self._check(rc, "rlb_l2_persist")
+        return rc
+
     # -- segment tree ------------------------------------------------------------------------------
     def tree_capacity(self, size: int) -> int:
         return int(self.L.rlb_tree_capacity(int(size)))
 
-    def tree_new(self, size: int, is_min: bool, dtype: torch.dtype, device) -> torch.Tensor:
+    def tree_new(self, size: int, is_min: bool, dtype: torch.dtype, device, out: torch.Tensor | None = None) -> torch.Tensor:
         cap = self.tree_capacity(size)
-        tree = torch.empty(2 * cap, dtype=dtype, device=device)
+        tree = torch.empty(2 * cap, dtype=dtype, device=device) if out is None else out
+        if tree.numel() != 2 * cap or tree.dtype != dtype or not tree.is_contiguous():
+            raise RuntimeError("tree_new: `out` must be a contiguous tensor of 2*capacity elements of the tree dtype")
         dev = self._cuda(tree)
         with self._Guard(dev):
             self._check(self.L.rlb_tree_fill(tree.data_ptr(), cap, int(is_min), _dtype_code(dtype),

@@ -26,9 +26,14 @@ class OracleBackend:
     def tree_capacity(self, size: int) -> int:
         return _capacity(size)
 
-    def tree_new(self, size, is_min, dtype, device):
+    def l2_persist(self, tensor, stream=None):
+        return 0
+
+    def tree_new(self, size, is_min, dtype, device, out=None):
         cap = _capacity(size)
         ident = torch.finfo(dtype).max if is_min else 0.0
+        if out is not None:
+            return out.fill_(ident)
         return torch.full((2 * cap,), ident, dtype=dtype, device="cpu")
 
     def tree_workspace(self, size, device):
