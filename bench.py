@@ -182,22 +182,24 @@ def kernel_roofline(dev, rb, ring, hbm_peak: float, peak_src: str) -> dict:
                "achieved": round(alg / us / 1e3, 1), "peak": hbm_peak, "unit": "GB/s",
                "frac": round(alg / us / 1e3 / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
                "algorithmic_bytes": alg, "us_per_launch": round(us, 3)}
-        # the same kernel at the reference benchmark's own batch size (65 536 rows, pixels only would be 1.8 GB:
-        # use 16 384 full transitions = 1.85 GB moved) -- the steady-state figure
-        big = torch.randint(0, len(st), (16384,), device=dev, generator=g)
-        for _ in range(2):
+        # the same kernel over a batch sweep (single launches, cold rows): fixed cost + streaming rate
+        sweep = {}
+        for bb in (1024, 4096, 16384):
+            big = torch.randint(0, len(st), (bb,), device=dev, generator=g)
+            for _ in range(2):
+                o = be.gather(st._leaves, big, len(st))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
             o = be.gather(st._leaves, big, len(st))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        o = be.gather(st._leaves, big, len(st))
-        e1.record(stream)
-        stream.synchronize()
-        del o
-        us_big = e0.elapsed_time(e1) * 1e3
-        alg_big = 16384 * row_bytes * 2 + 16384 * 8
-        out["steady_state_B16384"] = {"achieved": round(alg_big / us_big / 1e3, 1),
-                                      "frac": round(alg_big / us_big / 1e3 / hbm_peak, 4),
-                                      "us_per_launch": round(us_big, 1)}
+            e1.record(stream)
+            stream.synchronize()
+            del o
+            us_b = e0.elapsed_time(e1) * 1e3
+            alg_b = bb * row_bytes * 2 + bb * 8
+            sweep[f"B{bb}"] = {"achieved": round(alg_b / us_b / 1e3, 1), "frac": round(alg_b / us_b / 1e3 / hbm_peak, 4),
+                               "us_per_launch": round(us_b, 1)}
+        out["batch_sweep"] = sweep
+        out["steady_state_B16384"] = sweep["B16384"]
         # GAE kernel, same method
         v, nv, r, d, t = ring[0]
         graph2 = torch.cuda.CUDAGraph()
@@ -349,18 +351,19 @@ def run_ours(args) -> dict:
     ms_gae = timed(gae_only, args.steps, 3, sync_all)
 
     # ---- (3) end to end with HOST buffers: H2D of the step's inputs and D2H of the step's results every step.
-    # Two independent lanes (stream + pinned buffers + device staging) alternate so that one step's D2H overlaps
-    # the next step's H2D and compute (PCIe is full duplex); every step still synchronises on its own results.
+    # Three independent lanes (stream + pinned buffers + device staging) rotate so that one step's D2H overlaps
+    # the next steps' H2D and compute (PCIe is full duplex); every step still synchronises on its own results.
     pin = lambda t: t.cpu().pin_memory()
     sample0 = rb.sample()
     out_keys = list(sample0.keys(True, True))
     lanes = []
-    for lane in range(2):
+    n_lanes = 3
+    for lane in range(n_lanes):
         s = torch.cuda.Stream(dev)
-        host_in = tuple(pin(x) for x in ring[lane])
+        host_in = tuple(pin(x) for x in ring[lane % R])
         lanes.append({
             "stream": s, "host_in": host_in, "host_td": pin(td_err),
-            "dev_in": [torch.empty_like(x) for x in ring[lane]], "dev_td": torch.empty_like(td_err),
+            "dev_in": [torch.empty_like(x) for x in ring[lane % R]], "dev_td": torch.empty_like(td_err),
             "host_out": {k: torch.empty(sample0.get(k).shape, dtype=sample0.get(k).dtype).pin_memory() for k in out_keys},
             "host_adv": torch.empty(GAE_ROWS, GAE_T, 1).pin_memory(), "host_tgt": torch.empty(GAE_ROWS, GAE_T, 1).pin_memory(),
             "done": torch.cuda.Event(),
@@ -383,7 +386,7 @@ def run_ours(args) -> dict:
         L["host_tgt"].copy_(tg, non_blocking=True)
 
     def e2e_step(i: int):
-        L = lanes[i % 2]
+        L = lanes[i % n_lanes]
         L["done"].synchronize()            # the caller consumed this lane's previous results
         with torch.cuda.stream(L["stream"]):
             e2e_body(L)
@@ -438,7 +441,7 @@ def run_ours(args) -> dict:
                        "l2": "inputs larger than L2 (56 GB storage, random rows; GAE inputs rotate through >160 MB)"},
             "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5),
-                    "note": "eager python API, pinned host buffers, two lanes alternate so D2H overlaps the next H2D"},
+                    "note": "eager python API, pinned host buffers, three lanes rotate so D2H overlaps the next steps' H2D + compute"},
             "gpu_launches": (5 if world == 1 else 9) * args.steps,
             "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
                           "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),

@@ -25,11 +25,25 @@
 
 namespace rlb {
 
-constexpr int kGatherThreads = 128;              // both roles
-constexpr int kPipes = kGatherThreads / 32;      // DMA pipelines (warps) per bulk CTA
-constexpr int kStages = 5;                       // ring depth per pipeline (161 KB/CTA: leaves room for a co-resident update CTA)
-constexpr int kAhead = 3;                        // loads kept in flight ahead of the store front
-constexpr uint32_t kChunk = 8192;                // bytes per stage
+// tunables (overridable at build time for the sweeps recorded in profiles/README.md)
+#ifndef RLB_GATHER_PIPES
+#define RLB_GATHER_PIPES 4
+#endif
+#ifndef RLB_GATHER_STAGES
+#define RLB_GATHER_STAGES 5
+#endif
+#ifndef RLB_GATHER_AHEAD
+#define RLB_GATHER_AHEAD 3
+#endif
+#ifndef RLB_GATHER_CHUNK
+#define RLB_GATHER_CHUNK 8192
+#endif
+constexpr int kPipes = RLB_GATHER_PIPES;         // DMA pipelines (warps) per bulk CTA
+constexpr int kGatherThreads = 32 * kPipes;      // both roles
+constexpr int kStages = RLB_GATHER_STAGES;       // ring depth per pipeline (5 x 8 KB x 4 = 161 KB/CTA: leaves room
+                                                 // for a co-resident priority-update CTA)
+constexpr int kAhead = RLB_GATHER_AHEAD;         // loads kept in flight ahead of the store front
+constexpr uint32_t kChunk = RLB_GATHER_CHUNK;    // bytes per stage
 constexpr int kVecUnroll = 4;                    // units per thread per tile (vector role)
 constexpr int kTileUnits = kGatherThreads * kVecUnroll;
 constexpr int64_t kBulkMinRowBytes = 4096;       // AUTO mode: rows at least this wide use the DMA role
@@ -162,6 +176,8 @@ struct PipeSmem {
   uint32_t pad_;
 };
 
+constexpr size_t kPipeHeaderBytes = (sizeof(PipeSmem) * kPipes + 1023) / 1024 * 1024;
+
 __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, PipeSmem *ps) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const __grid_con
   extern __shared__ __align__(128) uint8_t gsmem[];
   if (!SCATTER && (int)blockIdx.x < P.bulk_ctas) {
     PipeSmem *ps = reinterpret_cast<PipeSmem *>(gsmem);
-    uint8_t *ring = gsmem + 1024;  // PipeSmem[kPipes] fits in the first KB; stages stay 128-B aligned
+    uint8_t *ring = gsmem + kPipeHeaderBytes;  // PipeSmem[kPipes] header; stages stay 128-B aligned
     bulk_role(P, ring, ps);
     return;
   }
@@ -274,8 +290,9 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const __grid_con
   vector_role<SCATTER>(P, (int64_t)blockIdx.x - P.bulk_ctas, vec_ctas);
 }
 
-static_assert(sizeof(PipeSmem) * kPipes <= 1024, "PipeSmem header must fit in 1 KB");
-constexpr size_t kBulkSmemBytes = 1024 + (size_t)kPipes * kStages * kChunk;
+constexpr size_t kBulkSmemBytes = kPipeHeaderBytes + (size_t)kPipes * kStages * kChunk;
+static_assert(kBulkSmemBytes <= 227 * 1024, "bulk ring exceeds the shared memory of an SM");
+static_assert(kAhead >= 1 && kAhead < kStages, "need 1 <= kAhead < kStages");
 
 static int pick_vec_log2(const void *src, const void *dst, int64_t row_bytes, int64_t stride, int64_t ostride) {
   for (int lg = 4; lg > 0; --lg) {

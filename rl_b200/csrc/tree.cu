@@ -164,7 +164,8 @@ __device__ __forceinline__ int64_t descend_plain(const T *__restrict__ tree, int
 // contiguous and 16-B aligned (for n >= 1), so they are fetched as 1 scalar + 1 + 2 + 4 independent
 // LDG.128 and the data-dependent choice is made from registers.  The comparisons/subtractions are the
 // reference's, in the reference's order.
-__device__ __forceinline__ int64_t descend4_f32(const float *__restrict__ tree, int64_t node, float &cur) {
+__device__ __forceinline__ int64_t descend4_f32(const float *__restrict__ tree, int64_t node, float &cur,
+                                                float &landed) {
   const float l1 = __ldg(tree + (node << 1));
   const float4 q2 = __ldg(reinterpret_cast<const float4 *>(tree + (node << 2)));
   const float4 q3a = __ldg(reinterpret_cast<const float4 *>(tree + (node << 3)));
@@ -210,6 +211,11 @@ __device__ __forceinline__ int64_t descend4_f32(const float *__restrict__ tree, 
     cur = sub_rn(cur, l4);
     c |= 1;
   }
+  // value of the node we end on (tree[16n + c]): it is one of the 16 floats already in registers, so when this
+  // round reaches the leaves the caller needs no further load for the leaf priority
+  const float4 qq = (c < 8) ? ((c < 4) ? q4a : q4b) : ((c < 12) ? q4c : q4d);
+  const int e = c & 3;
+  landed = (e == 0) ? qq.x : (e == 1) ? qq.y : (e == 2) ? qq.z : qq.w;
   return (node << 4) | c;
 }
 
@@ -222,7 +228,8 @@ __device__ __forceinline__ int64_t scan_lower_bound_one(const T *__restrict__ tr
   int lev = 0;
   if constexpr (sizeof(T) == 4) {
     if (speculative) {
-      for (; lev + 4 <= depth; lev += 4) node = descend4_f32(tree, node, cur);
+      float landed;
+      for (; lev + 4 <= depth; lev += 4) node = descend4_f32(tree, node, cur, landed);
     }
   }
   node = descend_plain<T>(tree, node, depth - lev, cur);
@@ -280,14 +287,27 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
                                                          int64_t *__restrict__ index_out,
                                                          float *__restrict__ weight_out, T *leaf_out,
                                                          T *psum_pmin_out, int32_t *status, long long *dbg) {
+  constexpr int kTopLevels = 9;  // nodes 1..511 of the sum tree are staged in shared memory: 8 descent steps
   __shared__ T s_p[2];
+  __shared__ T s_top[1 << kTopLevels];
   if (dbg && (blockIdx.x != 0 || threadIdx.x != 0)) dbg = nullptr;
   if (dbg) dbg[8] = (long long)clock64();
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const bool lane_on = (int)threadIdx.x < spc;  // spc == blockDim.x for full CTAs
   const int64_t i = lane_on ? blockIdx.x * (int64_t)spc + threadIdx.x : B;
-  const T ui = (i < B) ? __ldg(u + i) : (T)0;  // in flight while p_sum / p_min are resolved
+  // ---- round 0: every load below is independent -- the draw, both roots (or the prefix walks) and the top of the tree
+  const T ui = (i < B) ? __ldg(u + i) : (T)0;
+  const bool use_top = speculative && depth >= kTopLevels && sizeof(T) == 4;
+  if (use_top) {
+    for (int k = threadIdx.x * 4; k < (1 << kTopLevels); k += blockDim.x * 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4 *>(sum + k));  // coalesced; slot 0 is never read
+      s_top[k] = (T)q.x;
+      s_top[k + 1] = (T)q.y;
+      s_top[k + 2] = (T)q.z;
+      s_top[k + 3] = (T)q.w;
+    }
+  }
   // p_sum by warp 0, p_min by warp 1 (or both by warp 0 in single-warp CTAs)   (samplers.py:901-908)
   const bool root = cpu_semantics && (len >= size);  // csrc/segment_tree.h:145-147 fast path (l == 0)
   if (warp == 0) {
@@ -315,10 +335,43 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   if (i >= B) return;
   if (dbg) dbg[9] = (long long)clock64();
   const T mass = mul_rn(ui, p_sum);  // samplers.py:919 / :923 -- one rounding, never fused downstream
-  int64_t idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1), speculative != 0);
-  if (idx > len - 1) idx = len - 1;  // samplers.py:933
+  int64_t idx;
+  T leaf;
+  bool have_leaf = false;
+  if constexpr (sizeof(T) == 4) {
+    if (use_top) {
+      // ScanLowerBound (csrc/segment_tree.h:249-264): 8 steps from shared memory, then 4 levels per round trip
+      const T rootv = s_top[1];
+      if (mass > rootv) {
+        idx = size;
+      } else {
+        int64_t node = 1;
+        T cur = mass;
+#pragma unroll
+        for (int k = 0; k < kTopLevels - 1; ++k) {
+          node <<= 1;
+          descend_step(cur, node, s_top[node]);
+        }
+        int lev = kTopLevels - 1;
+        float landed = 0.f;
+        for (; lev + 4 <= depth; lev += 4) node = descend4_f32(sum, node, cur, landed);
+        have_leaf = (lev == depth) && (depth > kTopLevels - 1);
+        node = descend_plain<T>(sum, node, depth - lev, cur);
+        idx = node ^ capacity;
+        leaf = landed;
+      }
+    } else {
+      idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1), speculative != 0);
+    }
+  } else {
+    idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1), speculative != 0);
+  }
+  if (idx > len - 1) {  // samplers.py:933
+    idx = len - 1;
+    have_leaf = false;
+  }
   if (dbg) dbg[10] = (long long)clock64() + (idx & 0);
-  T leaf = __ldg(sum + (idx | capacity));
+  if (!have_leaf) leaf = __ldg(sum + (idx | capacity));
   if (cpu_semantics) {
     // samplers.py:935-943 (CPU trees only): walk left past zero-priority leaves
     while (leaf == (T)0) {
