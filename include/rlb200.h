@@ -149,12 +149,15 @@ int rlb_per_sample(const void *sum_tree /*[dev]*/, const void *min_tree /*[dev]*
  * If max_priority_out != NULL the maximum RAW priority over the valid entries is atomically folded
  * into *max_priority_out (max, no reset): with a buffer the caller initialises once to -inf this IS
  * the reference's running `_max_priority` (samplers.py:1054-1075) without a host round trip.
- * fp32 trees only. */
+ * fp32 trees only.  `index_base` is subtracted from every index and entries outside
+ * [0, index_limit) are skipped (index_limit < 0 means capacity): a rank of the capacity-sharded buffer
+ * passes GLOBAL indices with base = rank * shard_capacity and rewrites only what it owns. */
 int rlb_per_update(void *sum_tree /*[dev]*/, void *min_tree /*[dev]*/, int64_t capacity,
                    const int64_t *index /*[dev] n*/, const float *priority /*[dev] n or 1*/, int64_t n,
                    int scalar, double alpha, double eps, float *leaf_scratch /*[dev] n; may be NULL when n <= 1024*/,
                    float *max_priority_out /*[dev] 1 or NULL*/, void *workspace /*[dev]*/,
-                   size_t workspace_bytes, uint32_t epoch, rlb_stream_t stream);
+                   size_t workspace_bytes, uint32_t epoch, int64_t index_base, int64_t index_limit,
+                   rlb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Storage gather -- replaces TensorStorage.get for a tensor index
@@ -179,6 +182,20 @@ int rlb_scatter(const void *const *src /*[host]*/, void *const *dst /*[host]*/,
                 const int64_t *row_bytes /*[host]*/, const int64_t *dst_stride_bytes /*[host]*/, int n_leaves,
                 const int64_t *index /*[dev] B*/, int64_t B, int64_t len, int32_t *status /*[dev] or NULL*/,
                 rlb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sharded minibatch trailer (new; the reference has no sharded buffer -- SURVEY.md section 8e).  A packed
+ * minibatch row ends with  int64 global_index | f32 p_i | f32 S_r | f32 m_r  at byte `meta_offset`
+ * (8-byte aligned).  rlb_shard_pack fills the trailer of the B local rows from rlb_per_sample's outputs
+ * (index + index_base, leaf, psum_pmin); rlb_shard_weights reads the trailers of the B gathered rows and
+ * writes  w_i = ((p_i/S_r) / min_b(m_b/S_b)) ** -beta  (= samplers.py:945-953 for one shard) plus,
+ * optionally, a contiguous copy of the global indices. */
+int rlb_shard_pack(void *rows /*[dev] B x row_bytes*/, int64_t row_bytes, int64_t meta_offset,
+                   const int64_t *index /*[dev] B*/, const float *leaf /*[dev] B*/,
+                   const float *psum_pmin /*[dev] 2*/, int64_t index_base, int64_t B, rlb_stream_t stream);
+int rlb_shard_weights(const void *rows /*[dev] B x row_bytes*/, int64_t row_bytes, int64_t meta_offset, int64_t B,
+                      double beta, float *weight_out /*[dev] B*/, int64_t *index_out /*[dev] B or NULL*/,
+                      rlb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Generalized advantage estimation -- replaces vec_generalized_advantage_estimate /

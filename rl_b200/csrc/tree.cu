@@ -433,9 +433,8 @@ constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // stamps of the general 
 
 template <typename T>
 __host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
-  // xbuf u64[2*np] | ukey u32[np] | upos u32[np] | nxt i32[np] | Lsm i32[np] | sraw T[np] | dep_s,dep_m T[np] each
-  // | sib_s, sib_m T[depth*np] each
-  return (size_t)np * (16 + 4 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (3 + 2 * (size_t)depth);
+  // xbuf u64[2*np] | ukey u32[np] | upos u32[np] | sraw T[np] | sib_s, sib_m T[depth*np] each
+  return (size_t)np * (16 + 4 + 4) + (size_t)np * sizeof(T) * (1 + 2 * (size_t)depth);
 }
 
 #define RLB_TICK(k)                                                   \
@@ -464,7 +463,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
                                                                const T *__restrict__ value, int n, int scalar,
                                                                float alpha, float eps, float *max_out,
                                                                int *ticket, T *__restrict__ scratch,
-                                                               long long *dbg) {
+                                                               long long *dbg, int64_t index_base,
+                                                               int64_t index_limit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NP = blockDim.x;  // power of two >= n
   const int tid = threadIdx.x;
@@ -479,8 +479,10 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   int64_t my_ix = -1;
   T raw = (T)0;
   if (tid < n) {
-    my_ix = __ldg(index + tid);
-    valid = (my_ix >= 0 && my_ix < capacity);  // negative = "skip" (MaxValueWriter convention, samplers.py:1040-1052)
+    // index_base maps GLOBAL indices of a sharded buffer onto this shard; entries that fall outside
+    // [0, index_limit) are skipped, like the negative "do not write" markers of samplers.py:1040-1052
+    my_ix = __ldg(index + tid) - index_base;
+    valid = (my_ix >= 0 && my_ix < index_limit);
     raw = scalar ? __ldg(value) : __ldg(value + tid);
   }
 
@@ -497,8 +499,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       const T *tree = t ? mn : sum;
       T v = (T)0;
       if (tree && i < (uint32_t)n) {
-        const int64_t ix = (i == (uint32_t)tid) ? my_ix : __ldg(index + i);
-        if (ix >= 0 && ix < capacity) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+        const int64_t ix = (i == (uint32_t)tid) ? my_ix : __ldg(index + i) - index_base;
+        if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
       }
       scratch[e] = v;
     }
@@ -520,12 +522,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
   uint32_t *ukey = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);
   uint32_t *upos = ukey + NP;
-  int *nxt = reinterpret_cast<int *>(upos + NP);
-  int *Lsm = nxt + NP;
-  T *sraw = reinterpret_cast<T *>(Lsm + NP);
-  T *dep_s = sraw + NP;
-  T *dep_m = dep_s + NP;
-  T *sib = dep_m + NP;  // [2][depth][NP], indexed by ORIGINAL input position; reused as the output staging tile
+  T *sraw = reinterpret_cast<T *>(upos + NP);
+  T *sib = sraw + NP;  // [2][depth][NP], indexed by ORIGINAL input position; reused as the output staging tile
   {
     // coalesced 16-byte async copies of the whole scratch tile (lands while we sort)
     const size_t bytes = 2 * (size_t)depth * NP * sizeof(T);
@@ -534,9 +532,18 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     for (size_t off = (size_t)tid * 16; off < bytes; off += (size_t)NP * 16) cp_async16(d + off, g + off);
   }
 
-  // ---- 1. keys: (leaf node id, reversed input position) -- ascending sort puts the last writer first
+  // ---- 1. keys: (leaf node id, reversed input position) -- ascending sort puts the last writer first.  When
+  // both fit in 32 bits (trees up to 2^21 slots with 1024-item batches) the whole sort runs on 32-bit keys.
+  const int pos_bits = 31 - __clz(NP);  // log2(NP)
+  const bool key32 = (depth + 1 + pos_bits) <= 32;
   unsigned long long key = ~0ull;
-  if (valid) key = ((unsigned long long)(capacity + my_ix) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)tid);
+  if (valid) {
+    const unsigned long long leaf = (unsigned long long)(capacity + my_ix);
+    const unsigned long long rpos = (unsigned long long)(NP - 1 - tid);
+    key = key32 ? ((leaf << pos_bits) | rpos) : ((leaf << 32) | rpos);
+  } else if (key32) {
+    key = 0xffffffffull;
+  }
   if constexpr (FUSED) {
     if (max_out) {
       float p = valid ? (float)raw : -INFINITY;
@@ -549,7 +556,28 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
 
   // ---- 2. bitonic sort of NP keys, one key per thread: strides < 32 with warp shuffles, larger strides through
   // double-buffered shared memory (one barrier per such step)
-  {
+  if (key32) {
+    uint32_t k32 = (uint32_t)key;
+    uint32_t *xb32 = reinterpret_cast<uint32_t *>(xbuf);
+    int flip = 0;
+    for (int k = 2; k <= NP; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        uint32_t other;
+        if (j >= 32) {
+          uint32_t *buf = xb32 + flip * NP;
+          buf[tid] = k32;
+          __syncthreads();
+          other = buf[tid ^ j];
+          flip ^= 1;
+        } else {
+          other = __shfl_xor_sync(0xffffffffu, k32, j);
+        }
+        const bool take_min = (((tid & j) == 0) == ((tid & k) == 0));
+        k32 = (take_min == (other < k32)) ? other : k32;
+      }
+    }
+    key = k32;
+  } else {
     int flip = 0;
     for (int k = 2; k <= NP; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
@@ -563,25 +591,25 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         } else {
           other = shfl_xor_u64(key, j);
         }
-        const bool up = (tid & k) == 0;      // this block of k sorts ascending
-        const bool lower = (tid & j) == 0;   // I hold the lower position of the pair
-        const bool take_min = (lower == up);
-        const bool other_less = other < key;
-        key = (take_min == other_less) ? other : key;
+        const bool take_min = (((tid & j) == 0) == ((tid & k) == 0));
+        key = (take_min == (other < key)) ? other : key;
       }
     }
   }
   RLB_TICK(3);
 
   // ---- 3. distinct leaves: head of each run of equal leaf ids, compacted by a block-wide exclusive scan
-  const uint32_t myleaf = (uint32_t)(key >> 32);
+  const bool key_valid = key32 ? ((uint32_t)key != 0xffffffffu) : (key != ~0ull);
+  const uint32_t myleaf = key32 ? ((uint32_t)key >> pos_bits) : (uint32_t)(key >> 32);
+  const uint32_t mypos = (uint32_t)(NP - 1) - (uint32_t)(key & (unsigned long long)(NP - 1));
   {
-    unsigned long long *buf = xbuf;  // both exchange buffers are free again after one more barrier
+    uint32_t *buf = reinterpret_cast<uint32_t *>(xbuf);  // both exchange buffers are free again after a barrier
     __syncthreads();
-    buf[tid] = key;
+    buf[tid] = key_valid ? myleaf : 0xffffffffu;
     __syncthreads();
   }
-  const bool head = (key != ~0ull) && (tid == 0 || (uint32_t)(xbuf[tid - 1] >> 32) != myleaf);
+  const uint32_t *sorted_leaf = reinterpret_cast<const uint32_t *>(xbuf);
+  const bool head = key_valid && (tid == 0 || sorted_leaf[tid - 1] != myleaf);
   const unsigned bal = __ballot_sync(0xffffffffu, head);
   if (lane == 0) warp_cnt[warp] = __popc(bal);
   __syncthreads();
@@ -600,18 +628,23 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   if (head) {
     const int u = warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
     ukey[u] = myleaf;
-    upos[u] = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
+    upos[u] = mypos;
   }
   cp_async_wait_all();
   __syncthreads();
   RLB_TICK(4);
   const int m = s_total;
 
-  // ---- 4. per distinct leaf: merge level, first deposit
+  // ---- 4. per distinct leaf j: merge level L_j, and WHERE its hand-over goes.  The group j merges into at level
+  // L_j is led by the leftmost item sharing the prefix key_j >> L_j (a lower bound in the sorted keys); that
+  // leader consumes, at iteration L_j - 1, the slot [L_j - 1][pos_leader] of the sibling tile -- which until then
+  // holds the OLD value of exactly the node j carries.  So j simply overwrites that slot with the new value:
+  // the leader's loop body is the same whether its sibling was touched or not.
   bool alive = tid < m;
   uint32_t leafnode = 0, pos = 0;
-  int L = 0, my_next = -1;
+  int L = 0;
   T vs = (T)0, vm = (T)0, leaf_v = (T)0;
+  T *hand_s = nullptr, *hand_m = nullptr;
   if (alive) {
     leafnode = ukey[tid];
     pos = upos[tid];
@@ -621,12 +654,20 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     vm = v;
     leaf_v = v;
     L = (tid == 0) ? depth + 1 : 32 - __clz(leafnode ^ ukey[tid - 1]);
-    Lsm[tid] = L;
-    my_next = (tid + 1 < m) ? tid + 1 : -1;
-    nxt[tid] = my_next;
-    if (L == 1) {  // merges with its left neighbour already at level 1: hand over the leaf value
-      dep_s[tid] = vs;
-      dep_m[tid] = vm;
+    if (tid > 0) {
+      const uint32_t prefix = leafnode >> L;
+      int lo = 0, hi = tid;  // first index in [0, tid) whose key has this prefix
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((ukey[mid] >> L) < prefix) lo = mid + 1; else hi = mid;
+      }
+      const uint32_t lead_pos = upos[lo];
+      hand_s = sib + (size_t)(L - 1) * NP + lead_pos;
+      hand_m = sib + (size_t)depth * NP + (size_t)(L - 1) * NP + lead_pos;
+      if (L == 1) {  // sibling leaves: hand the leaf value over before the first iteration
+        *hand_s = vs;
+        *hand_m = vm;
+      }
     }
   }
   __syncthreads();
@@ -634,37 +675,25 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
 
   // ---- 5. climb.  Nothing but registers and shared memory inside the loop: the parent computed at level l
   // overwrites the (consumed) sibling slot [l][pos] and is flushed to the global trees afterwards -- a global
-  // store before a barrier would make every level wait for its L2 acknowledgement.  (An event-driven variant
-  // that folds untouched-sibling levels lazily was 3x slower: lanes of a warp have their events at different
-  // levels, so the lazy loops serialise under SIMT.)
+  // store before a barrier would make every level wait for its L2 acknowledgement.
   T *io_s = sib + pos;
   T *io_m = sib + (size_t)depth * NP + pos;
   int levels_done = 0;
   for (int l = 0; l < depth; ++l) {
     if (alive) {
       if (L == l + 1) {
-        alive = false;  // my level-l value was deposited; the group on my left carries the parent
+        alive = false;  // my level-l value was handed over; the leader of the group on my left carries the parent
       } else {
-        const uint32_t node = leafnode >> l;
         const uint32_t off = (uint32_t)l * (uint32_t)NP;
-        T os, om;
-        if ((node & 1u) == 0u && my_next >= 0 && Lsm[my_next] == l + 1) {
-          os = dep_s[my_next];  // touched right sibling: value deposited by the item that merges into me
-          om = dep_m[my_next];
-          my_next = nxt[my_next];
-          nxt[tid] = my_next;
-        } else {
-          os = io_s[off];  // untouched sibling: its old global value
-          om = io_m[off];
-        }
-        vs = tree_op<T, false>(vs, os);  // IEEE addition commutes: operand order is immaterial for the sum
-        vm = (node & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+        const T os = io_s[off], om = io_m[off];  // sibling: old global value, or the value handed over to me
+        vs = tree_op<T, false>(vs, os);          // IEEE addition commutes: operand order is immaterial
+        vm = ((leafnode >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
         io_s[off] = vs;  // value of node (leafnode >> (l + 1))
         io_m[off] = vm;
         levels_done = l + 1;
-        if (L == l + 2) {  // I merge into my left group at the next level: deposit the value just computed
-          dep_s[tid] = vs;
-          dep_m[tid] = vm;
+        if (L == l + 2) {  // I merge at the next level: hand the value just computed to the leader
+          *hand_s = vs;
+          *hand_m = vm;
         }
       }
     }
@@ -692,22 +721,22 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
 // survives is the last writer of that leaf.  The stamp array is persistent; `epoch` strictly increases
 // from call to call so it never needs clearing.
 __global__ void upd_stamp_kernel(unsigned long long *stamp, int64_t capacity, const int64_t *__restrict__ index,
-                                 int64_t n, uint32_t epoch) {
+                                 int64_t n, uint32_t epoch, int64_t index_base, int64_t index_limit) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t ix = index[i];
-  if (ix < 0 || ix >= capacity) return;
+  const int64_t ix = index[i] - index_base;
+  if (ix < 0 || ix >= index_limit) return;
   atomicMax(stamp + ix, ((unsigned long long)epoch << 32) | (unsigned long long)(uint32_t)i);
 }
 
 template <typename T>
 __global__ void upd_leaf_kernel(T *sum, T *mn, const unsigned long long *__restrict__ stamp, int64_t capacity,
                                 const int64_t *__restrict__ index, const T *__restrict__ value, int64_t n,
-                                int scalar) {
+                                int scalar, int64_t index_base, int64_t index_limit) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t ix = index[i];
-  if (ix < 0 || ix >= capacity) return;
+  const int64_t ix = index[i] - index_base;
+  if (ix < 0 || ix >= index_limit) return;
   if ((uint32_t)(stamp[ix] & 0xffffffffull) != (uint32_t)i) return;  // a later duplicate wins
   const T v = scalar ? value[0] : value[i];
   if (sum) sum[capacity + ix] = v;
@@ -718,11 +747,11 @@ __global__ void upd_leaf_kernel(T *sum, T *mn, const unsigned long long *__restr
 // share an ancestor write the same bits, so the race is benign.
 template <typename T>
 __global__ void upd_sweep_kernel(T *sum, T *mn, int64_t capacity, const int64_t *__restrict__ index, int64_t n,
-                                 int shift) {
+                                 int shift, int64_t index_base, int64_t index_limit) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t ix = index[i];
-  if (ix < 0 || ix >= capacity) return;
+  const int64_t ix = index[i] - index_base;
+  if (ix < 0 || ix >= index_limit) return;
   const int64_t p = (capacity + ix) >> shift;
   if (sum) sum[p] = tree_op<T, false>(ld_cg(sum + (p << 1)), ld_cg(sum + ((p << 1) | 1)));
   if (mn) mn[p] = tree_op<T, true>(ld_cg(mn + (p << 1)), ld_cg(mn + ((p << 1) | 1)));
@@ -734,13 +763,15 @@ __global__ void upd_sweep_kernel(T *sum, T *mn, int64_t capacity, const int64_t 
 __global__ void __launch_bounds__(256) per_update_prep_kernel(const int64_t *__restrict__ index,
                                                               const float *__restrict__ priority, int64_t n,
                                                               int scalar, float alpha, float eps,
-                                                              float *__restrict__ leaf, float *max_out) {
+                                                              float *__restrict__ leaf, float *max_out,
+                                                              int64_t index_base, int64_t index_limit) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   float p = -INFINITY;
   if (i < n) {
     const float raw = scalar ? priority[0] : priority[i];
     leaf[i] = pow_like_torch(add_rn(raw, eps), alpha);
-    if (index[i] >= 0) p = raw;
+    const int64_t ix = index[i] - index_base;
+    if (ix >= 0 && ix < index_limit) p = raw;
   }
   if (max_out) {
     for (int o = 16; o > 0; o >>= 1) p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
@@ -809,6 +840,8 @@ struct FusedPow {
   bool on = false;
   float alpha = 0.f, eps = 0.f;
   float *max_out = nullptr;
+  int64_t index_base = 0;    // subtracted from every index (global -> shard-local)
+  int64_t index_limit = -1;  // valid local indices are [0, index_limit); -1 = capacity
 };
 
 template <typename T, bool FUSED>
@@ -839,7 +872,8 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   T *scratch = reinterpret_cast<T *>(static_cast<unsigned char *>(workspace) + kUpdCtrlBytes);
   tree_update_cta_kernel<T, FUSED><<<(unsigned)grid, np, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n,
                                                                     scalar, fp.alpha, fp.eps, fp.max_out, ticket,
-                                                                    scratch, g_debug_ticks);
+                                                                    scratch, g_debug_ticks, fp.index_base,
+                                                                    fp.index_limit < 0 ? capacity : fp.index_limit);
   return check_launch("tree_update_cta_kernel");
 }
 
@@ -875,16 +909,17 @@ static int tree_update_impl(void *sum_, void *mn_, int64_t capacity, const int64
       reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(workspace) + kUpdWorkspaceHead);
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-  upd_stamp_kernel<<<blocks, threads, 0, st>>>(stamp, capacity, index, n, epoch);
+  const int64_t ibase = fp.index_base, ilimit = fp.index_limit < 0 ? capacity : fp.index_limit;
+  upd_stamp_kernel<<<blocks, threads, 0, st>>>(stamp, capacity, index, n, epoch, ibase, ilimit);
   int rc = check_launch("upd_stamp_kernel");
   if (rc) return rc;
-  upd_leaf_kernel<T><<<blocks, threads, 0, st>>>(sum, mn, stamp, capacity, index, value, n, scalar);
+  upd_leaf_kernel<T><<<blocks, threads, 0, st>>>(sum, mn, stamp, capacity, index, value, n, scalar, ibase, ilimit);
   rc = check_launch("upd_leaf_kernel");
   if (rc) return rc;
   // sweep the levels of width >= 1024 (touched ancestors only), then one CTA recomputes the dense top
   int shift = 1;
   for (int64_t W = capacity >> 1; W >= 1024; W >>= 1, ++shift) {
-    upd_sweep_kernel<T><<<blocks, threads, 0, st>>>(sum, mn, capacity, index, n, shift);
+    upd_sweep_kernel<T><<<blocks, threads, 0, st>>>(sum, mn, capacity, index, n, shift, ibase, ilimit);
     rc = check_launch("upd_sweep_kernel");
     if (rc) return rc;
   }
@@ -1056,7 +1091,8 @@ int rlb_per_sample(const void *sum_tree, const void *min_tree, int64_t size, int
 
 int rlb_per_update(void *sum_tree, void *min_tree, int64_t capacity, const int64_t *index, const float *priority,
                    int64_t n, int scalar, double alpha, double eps, float *leaf_scratch, float *max_priority_out,
-                   void *workspace, size_t workspace_bytes, uint32_t epoch, rlb_stream_t stream) {
+                   void *workspace, size_t workspace_bytes, uint32_t epoch, int64_t index_base, int64_t index_limit,
+                   rlb_stream_t stream) {
   RLB_REQUIRE((sum_tree || min_tree) && is_pow2(capacity), RLB_EINVAL, "rlb_per_update: bad tree/capacity");
   RLB_REQUIRE(n >= 0, RLB_EINVAL, "rlb_per_update: negative n");
   if (n == 0) return RLB_OK;
@@ -1071,17 +1107,23 @@ int rlb_per_update(void *sum_tree, void *min_tree, int64_t capacity, const int64
     fp.alpha = (float)alpha;
     fp.eps = (float)eps;
     fp.max_out = max_priority_out;
+    fp.index_base = index_base;
+    fp.index_limit = index_limit;
     return tree_update_impl<float>(sum_tree, min_tree, capacity, index, priority, n, scalar, workspace,
                                    workspace_bytes, epoch, st, fp);
   }
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   per_update_prep_kernel<<<blocks, threads, 0, st>>>(index, priority, n, scalar, (float)alpha, (float)eps,
-                                                     leaf_scratch, max_priority_out);
+                                                     leaf_scratch, max_priority_out, index_base,
+                                                     index_limit < 0 ? capacity : index_limit);
   int rc = check_launch("per_update_prep_kernel");
   if (rc) return rc;
+  FusedPow plain;  // pow already applied; only the index mapping is forwarded
+  plain.index_base = index_base;
+  plain.index_limit = index_limit;
   return tree_update_impl<float>(sum_tree, min_tree, capacity, index, leaf_scratch, n, /*scalar=*/0, workspace,
-                                 workspace_bytes, epoch, st);
+                                 workspace_bytes, epoch, st, plain);
 }
 
 }  // extern "C"

@@ -348,7 +348,8 @@ class PrioritizedSampler(Sampler):
 
     # ---- update_priority (samplers.py:966-1091) ----------------------------------------------------
     @torch.no_grad()
-    def update_priority(self, index, priority, *, storage: Storage | None = None) -> None:
+    def update_priority(self, index, priority, *, storage: Storage | None = None, index_base: int = 0,
+                        index_limit: int = -1) -> None:
         """Updates the priority of the data pointed by the index.
 
         Args:
@@ -357,6 +358,9 @@ class PrioritizedSampler(Sampler):
 
         Keyword Args:
             storage (Storage, optional): needed to map N-d indices to the trees' flat index.
+            index_base, index_limit (int): (not in the reference) ``index_base`` is subtracted from every index
+                and results outside ``[0, index_limit)`` are skipped inside the kernel -- how a shard of the
+                capacity-sharded buffer consumes GLOBAL indices without a host round trip.
         """
         self._maybe_init_from_storage(storage)
         dev = self._sum_tree.device
@@ -400,8 +404,12 @@ class PrioritizedSampler(Sampler):
             priority = priority.to(torch.float32)
             ops.backend().per_update(self._sum_tree.values, self._min_tree.values, self._sum_tree.capacity, index,
                                      priority, self._alpha, self._eps, self._max_priority_buf,
-                                     self._tree_workspace(index.numel()), self._tree_epoch())
+                                     self._tree_workspace(index.numel()), self._tree_epoch(), index_base, index_limit)
         else:
+            if index_base or index_limit >= 0:
+                index = index - index_base
+                lim = self._sum_tree.capacity if index_limit < 0 else index_limit
+                index = torch.where((index >= 0) & (index < lim), index, index.new_full((), -1))
             valid = index >= 0
             pmax = torch.where(valid, priority.expand_as(index), priority.new_full((), float("-inf"))).max()
             self._max_priority_buf.copy_(torch.maximum(self._max_priority_buf[0], pmax.to(torch.float32)).view(1))

@@ -166,11 +166,7 @@ class ShardedPrioritizedReplayBuffer:
                                              smp._sum_tree.capacity, length, u, smp._beta, smp._semantics == "cpu",
                                              status=smp._status, want_aux=True)
             be.gather(st._leaves, idx, length, out=lay.leaf_views(send))
-        gidx, pi, S, m = lay.meta_views(send)
-        gidx.copy_(idx + self.rank * self.shard_capacity)
-        pi.copy_(leaf)
-        S.copy_(pp[0].expand(b_loc))
-        m.copy_(pp[1].expand(b_loc))
+            be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity)  # trailer: 1 launch
         self.local_index = idx
         self._send, self._recv, self._bs = send, recv, batch_size
         return send
@@ -185,10 +181,8 @@ class ShardedPrioritizedReplayBuffer:
         """Views of the gathered buffer as the global batch + importance weights over the whole sharded buffer."""
         lay, recv, smp = self._layout, self._recv, self.local.sampler
         leaves = lay.leaf_views(recv)
-        gidx, pi, S, m = lay.meta_views(recv)
         batch = unflatten_data(leaves, self.local.storage._spec, (self._bs,))
-        ratio = pi / S
-        weight = torch.pow(ratio / (m / S).min(), -smp._beta)  # identical on every rank
+        weight, gidx = ops.backend().shard_weights(recv, lay.meta, smp._beta)  # identical on every rank
         if is_tensor_collection(batch):
             batch.set("index", gidx)
             batch.set("priority_weight", weight)
@@ -204,10 +198,9 @@ class ShardedPrioritizedReplayBuffer:
     def update_priority(self, index: torch.Tensor, priority) -> None:
         """``index`` holds GLOBAL indices; entries owned by other ranks are skipped inside the kernel."""
         index = torch.as_tensor(index, dtype=torch.long, device=self.device)
-        lo = self.rank * self.shard_capacity
-        local = index - lo
-        local = torch.where((local >= 0) & (local < self.shard_capacity), local, local.new_full((), -1))
-        self.local.update_priority(local, priority)
+        self.local.sampler.update_priority(index, priority, storage=self.local.storage,
+                                           index_base=self.rank * self.shard_capacity,
+                                           index_limit=self.shard_capacity)
 
     def update_tensordict_priority(self, data) -> None:
         priority = data.get(self.local.priority_key)

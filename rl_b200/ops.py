@@ -43,7 +43,10 @@ _SIGNATURES = {
     "rlb_tree_scan_lower_bound": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
     "rlb_per_sample": (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _vp, _i64, _f64, _i32, _vp, _vp, _vp, _vp,
                                _vp, _vp]),
-    "rlb_per_update": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _f64, _f64, _vp, _vp, _vp, _sz, _u32, _vp]),
+    "rlb_per_update": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _f64, _f64, _vp, _vp, _vp, _sz, _u32, _i64, _i64,
+                               _vp]),
+    "rlb_shard_pack": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "rlb_shard_weights": (_i32, [_vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp]),
     "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
@@ -242,7 +245,8 @@ class CudaBackend:
         return index, weight
 
     def per_update(self, sum_tree, min_tree, capacity: int, index: torch.Tensor, priority: torch.Tensor,
-                   alpha: float, eps: float, max_out: torch.Tensor | None, workspace, epoch: int) -> None:
+                   alpha: float, eps: float, max_out: torch.Tensor | None, workspace, epoch: int,
+                   index_base: int = 0, index_limit: int = -1) -> None:
         dev = self._cuda(sum_tree, min_tree, index, priority, max_out, workspace)
         if priority.dtype != torch.float32 or (sum_tree is not None and sum_tree.dtype != torch.float32):
             raise NotImplementedError("fused per_update is fp32 only")
@@ -254,8 +258,27 @@ class CudaBackend:
             self._check(self.L.rlb_per_update(
                 self._p(sum_tree), self._p(min_tree), capacity, index.data_ptr(), priority.data_ptr(), n, scalar,
                 float(alpha), float(eps), self._p(scratch), self._p(max_out), self._p(workspace),
-                0 if workspace is None else workspace.numel() * 8, epoch & 0xFFFFFFFF, self._stream(dev)),
-                "rlb_per_update")
+                0 if workspace is None else workspace.numel() * 8, epoch & 0xFFFFFFFF, int(index_base),
+                int(index_limit), self._stream(dev)), "rlb_per_update")
+
+    # -- sharded minibatch trailer -----------------------------------------------------------------
+    def shard_pack(self, rows: torch.Tensor, meta_offset: int, index, leaf, psum_pmin, index_base: int) -> None:
+        dev = self._cuda(rows, index, leaf, psum_pmin)
+        with self._Guard(dev):
+            self._check(self.L.rlb_shard_pack(rows.data_ptr(), rows.stride(0), meta_offset, index.data_ptr(),
+                                              leaf.data_ptr(), psum_pmin.data_ptr(), int(index_base), rows.shape[0],
+                                              self._stream(dev)), "rlb_shard_pack")
+
+    def shard_weights(self, rows: torch.Tensor, meta_offset: int, beta: float):
+        dev = self._cuda(rows)
+        B = rows.shape[0]
+        weight = torch.empty(B, dtype=torch.float32, device=dev)
+        gidx = torch.empty(B, dtype=torch.int64, device=dev)
+        with self._Guard(dev):
+            self._check(self.L.rlb_shard_weights(rows.data_ptr(), rows.stride(0), meta_offset, B, float(beta),
+                                                 weight.data_ptr(), gidx.data_ptr(), self._stream(dev)),
+                        "rlb_shard_weights")
+        return weight, gidx
 
     # -- storage rows ------------------------------------------------------------------------------
     def _rows(self, who, big: Sequence[torch.Tensor], small: Sequence[torch.Tensor], index: torch.Tensor,

@@ -141,8 +141,11 @@ class OracleBackend:
             return index, weight, leaf, torch.stack([p_sum, p_min])
         return index, weight
 
-    def per_update(self, sum_tree, min_tree, capacity, index, priority, alpha, eps, max_out, workspace, epoch):
-        index = index.reshape(-1)
+    def per_update(self, sum_tree, min_tree, capacity, index, priority, alpha, eps, max_out, workspace, epoch,
+                   index_base=0, index_limit=-1):
+        index = index.reshape(-1) - index_base
+        limit = capacity if index_limit < 0 else index_limit
+        index = torch.where((index >= 0) & (index < limit), index, torch.full_like(index, -1))
         priority = priority.reshape(-1).to(torch.float32)
         valid = index >= 0
         if max_out is not None and valid.any():
@@ -150,6 +153,22 @@ class OracleBackend:
             max_out.copy_(torch.maximum(max_out, pv.max().view(1)))
         leaf = torch.pow(priority + eps, alpha)
         self.tree_update(sum_tree, min_tree, capacity, index, leaf, workspace, epoch)
+
+    # ---- sharded minibatch trailer
+    def shard_pack(self, rows, meta_offset, index, leaf, psum_pmin, index_base):
+        m = meta_offset
+        rows[:, m:m + 8].view(torch.int64).view(-1).copy_(index + index_base)
+        rows[:, m + 8:m + 12].view(torch.float32).view(-1).copy_(leaf)
+        rows[:, m + 12:m + 16].view(torch.float32).view(-1).copy_(psum_pmin[0].expand(rows.shape[0]))
+        rows[:, m + 16:m + 20].view(torch.float32).view(-1).copy_(psum_pmin[1].expand(rows.shape[0]))
+
+    def shard_weights(self, rows, meta_offset, beta):
+        m = meta_offset
+        gidx = rows[:, m:m + 8].view(torch.int64).view(-1).clone()
+        p = rows[:, m + 8:m + 12].view(torch.float32).view(-1)
+        S = rows[:, m + 12:m + 16].view(torch.float32).view(-1)
+        mn = rows[:, m + 16:m + 20].view(torch.float32).view(-1)
+        return torch.pow((p / S) / (mn / S).min(), -beta), gidx
 
     # ---- storage rows
     def gather(self, leaves, index, length, mode=0, status=None, out=None):
