@@ -177,24 +177,34 @@ def kernel_roofline(dev, rb, ring, hbm_peak: float, peak_src: str) -> dict:
         us = sorted(ms)[len(ms) // 2] * 1e3
         row_bytes = sum(l[0].numel() * l.element_size() for l in st._leaves)  # every stored leaf, per transition
         alg = BATCH * row_bytes * 2 + BATCH * 8
+        traffic = None
+        tf = ROOT / "profiles" / "traffic_r1.json"
+        if tf.exists():  # from the committed `ncu --set full` capture (profiles/ncu_full_r1.csv), per launch
+            tj = json.loads(tf.read_text())["gather_kernel_B256"]
+            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
         out = {"bound": "hbm", "kernel": f"gather_kernel<gather> (rlb_gather, {len(st._leaves)} leaves, B=256)",
                "row_bytes": row_bytes,
                "achieved": round(alg / us / 1e3, 1), "peak": hbm_peak, "unit": "GB/s",
-               "frac": round(alg / us / 1e3 / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+               "frac": round(alg / us / 1e3 / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                "algorithmic_bytes": alg, "us_per_launch": round(us, 3)}
-        # the same kernel over a batch sweep (single launches, cold rows): fixed cost + streaming rate
+        # the same kernel over a batch sweep (graph-replayed launches on cold rows): fixed cost + streaming rate
         sweep = {}
-        for bb in (1024, 4096, 16384):
-            big = torch.randint(0, len(st), (bb,), device=dev, generator=g)
-            for _ in range(2):
-                o = be.gather(st._leaves, big, len(st))
+        for bb, reps in ((1024, 8), (4096, 4), (16384, 2)):
+            idx_b = [torch.randint(0, len(st), (bb,), device=dev, generator=g) for _ in range(reps)]
+            be.gather(st._leaves, idx_b[0], len(st))
+            stream.synchronize()
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, stream=stream):
+                keep = [be.gather(st._leaves, ix, len(st)) for ix in idx_b]
+            gb.replay()
+            stream.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            o = be.gather(st._leaves, big, len(st))
+            gb.replay()
             e1.record(stream)
             stream.synchronize()
-            del o
-            us_b = e0.elapsed_time(e1) * 1e3
+            del keep, gb
+            us_b = e0.elapsed_time(e1) * 1e3 / reps
             alg_b = bb * row_bytes * 2 + bb * 8
             sweep[f"B{bb}"] = {"achieved": round(alg_b / us_b / 1e3, 1), "frac": round(alg_b / us_b / 1e3 / hbm_peak, 4),
                                "us_per_launch": round(us_b, 1)}
