@@ -433,8 +433,8 @@ constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // stamps of the general 
 
 template <typename T>
 __host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
-  // xbuf u64[2*np] | ukey u32[np] | upos u32[np] | sraw T[np] | sib_s, sib_m T[depth*np] each
-  return (size_t)np * (16 + 4 + 4) + (size_t)np * sizeof(T) * (1 + 2 * (size_t)depth);
+  // xbuf u64[2*np] | ukey u32[np] | upos u32[np] | Lw i32[np] | sraw T[np] | lv T[np] | sib_s, sib_m T[depth*np] each
+  return (size_t)np * (16 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (2 + 2 * (size_t)depth);
 }
 
 #define RLB_TICK(k)                                                   \
@@ -464,21 +464,28 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
                                                                float alpha, float eps, float *max_out,
                                                                int *ticket, T *__restrict__ scratch,
                                                                long long *dbg, int64_t index_base,
-                                                               int64_t index_limit) {
+                                                               int64_t index_limit, int NP) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NP = blockDim.x;  // power of two >= n
+  // NP (a power of two >= n) compute threads; when the block has 2*NP threads the upper half are WRITER warps
+  // that stream finished node values to the global trees while the compute warps are still climbing
   const int tid = threadIdx.x;
+  const bool has_writers = (int)blockDim.x == 2 * NP;
   const int lane = tid & 31, warp = tid >> 5;
   __shared__ int warp_cnt[32];
   __shared__ int s_total;
   __shared__ int s_last;
+  __shared__ __align__(8) uint64_t s_level_done[33];  // mbarriers: [l] = level l is final, [32] = item info is final
+  if (has_writers && tid == 0) {
+    for (int k = 0; k < 33; ++k) mbar_init(&s_level_done[k], 1);
+    fence_mbar_init();
+  }
 
   const long long t_start = dbg ? (long long)clock64() : 0;  // stamps are taken by the CTA that runs phase B
   // my own item (every CTA loads it: phase A needs the indices anyway, the last CTA needs the values)
   bool valid = false;
   int64_t my_ix = -1;
   T raw = (T)0;
-  if (tid < n) {
+  if (tid < n && tid < NP) {
     // index_base maps GLOBAL indices of a sharded buffer onto this shard; entries that fall outside
     // [0, index_limit) are skipped, like the negative "do not write" markers of samplers.py:1040-1052
     my_ix = __ldg(index + tid) - index_base;
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   {
     const uint32_t per_tree = (uint32_t)depth * (uint32_t)NP;
     const uint32_t total = 2u * per_tree;
-    for (uint32_t e = blockIdx.x * (uint32_t)NP + tid; e < total; e += gridDim.x * (uint32_t)NP) {
+    for (uint32_t e = blockIdx.x * (uint32_t)NP + tid; tid < NP && e < total; e += gridDim.x * (uint32_t)NP) {
       const uint32_t t = e >= per_tree;
       const uint32_t rem = e - t * per_tree;
       const uint32_t l = rem / (uint32_t)NP;
@@ -522,8 +529,37 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
   uint32_t *ukey = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);
   uint32_t *upos = ukey + NP;
-  T *sraw = reinterpret_cast<T *>(upos + NP);
-  T *sib = sraw + NP;  // [2][depth][NP], indexed by ORIGINAL input position; reused as the output staging tile
+  int *Lw = reinterpret_cast<int *>(upos + NP);  // merge level of each distinct leaf (for the writer warps)
+  T *sraw = reinterpret_cast<T *>(Lw + NP);
+  T *lv = sraw + NP;   // leaf value of each distinct leaf (for the writer warps)
+  T *sib = lv + NP;    // [2][depth][NP], indexed by ORIGINAL input position; reused as the output staging tile
+  if (tid >= NP) {
+    // ---- writer warps: wait until a level is final, then scatter it.  Their stores drain on their own
+    // barriers, never on the compute warps' one.
+    const int w = tid - NP;
+    mbar_wait_parity(&s_level_done[32], 0);
+    const int mm = s_total;
+    uint32_t wleaf = 0, wpos = 0;
+    int wL = 0;
+    if (w < mm) {
+      wleaf = ukey[w];
+      wpos = upos[w];
+      wL = Lw[w];
+      const T v = lv[w];
+      if (sum) sum[wleaf] = v;
+      if (mn) mn[wleaf] = v;
+    }
+    for (int l = 0; l < depth; ++l) {
+      mbar_wait_parity(&s_level_done[l], 0);
+      if (w < mm && wL > l + 1) {  // item w carried node (wleaf >> (l + 1))
+        const uint32_t parent = wleaf >> (l + 1);
+        if (sum) sum[parent] = sib[(size_t)l * NP + wpos];
+        if (mn) mn[parent] = sib[(size_t)depth * NP + (size_t)l * NP + wpos];
+      }
+    }
+    return;
+  }
+  auto compute_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(NP) : "memory"); };
   {
     // coalesced 16-byte async copies of the whole scratch tile (lands while we sort)
     const size_t bytes = 2 * (size_t)depth * NP * sizeof(T);
@@ -566,7 +602,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         if (j >= 32) {
           uint32_t *buf = xb32 + flip * NP;
           buf[tid] = k32;
-          __syncthreads();
+          compute_sync();
           other = buf[tid ^ j];
           flip ^= 1;
         } else {
@@ -585,7 +621,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         if (j >= 32) {
           unsigned long long *buf = xbuf + flip * NP;
           buf[tid] = key;
-          __syncthreads();
+          compute_sync();
           other = buf[tid ^ j];
           flip ^= 1;
         } else {
@@ -604,15 +640,15 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   const uint32_t mypos = (uint32_t)(NP - 1) - (uint32_t)(key & (unsigned long long)(NP - 1));
   {
     uint32_t *buf = reinterpret_cast<uint32_t *>(xbuf);  // both exchange buffers are free again after a barrier
-    __syncthreads();
+    compute_sync();
     buf[tid] = key_valid ? myleaf : 0xffffffffu;
-    __syncthreads();
+    compute_sync();
   }
   const uint32_t *sorted_leaf = reinterpret_cast<const uint32_t *>(xbuf);
   const bool head = key_valid && (tid == 0 || sorted_leaf[tid - 1] != myleaf);
   const unsigned bal = __ballot_sync(0xffffffffu, head);
   if (lane == 0) warp_cnt[warp] = __popc(bal);
-  __syncthreads();
+  compute_sync();
   if (warp == 0) {
     const int nw = NP >> 5;
     int c = (lane < nw) ? warp_cnt[lane] : 0;
@@ -624,14 +660,14 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     if (lane < nw) warp_cnt[lane] = incl - c;
     if (lane == 31) s_total = incl;
   }
-  __syncthreads();
+  compute_sync();
   if (head) {
     const int u = warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
     ukey[u] = myleaf;
     upos[u] = mypos;
   }
   cp_async_wait_all();
-  __syncthreads();
+  compute_sync();
   RLB_TICK(4);
   const int m = s_total;
 
@@ -654,6 +690,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     vm = v;
     leaf_v = v;
     L = (tid == 0) ? depth + 1 : 32 - __clz(leafnode ^ ukey[tid - 1]);
+    Lw[tid] = L;
+    lv[tid] = v;
     if (tid > 0) {
       const uint32_t prefix = leafnode >> L;
       int lo = 0, hi = tid;  // first index in [0, tid) whose key has this prefix
@@ -670,7 +708,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
     }
   }
-  __syncthreads();
+  compute_sync();
+  if (has_writers && tid == 0) mbar_arrive(&s_level_done[32]);  // item info (ukey/upos/Lw/lv/s_total) is final
   RLB_TICK(5);
 
   // ---- 5. climb.  Nothing but registers and shared memory inside the loop: the parent computed at level l
@@ -697,12 +736,13 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         }
       }
     }
-    __syncthreads();
+    compute_sync();
+    if (has_writers && tid == 0) mbar_arrive(&s_level_done[l]);  // level l of the staging tile is final
   }
   RLB_TICK(6);
 
-  // ---- 6. flush: leaf + every ancestor this item carried (each touched node is written exactly once)
-  if (tid < m) {
+  // ---- 6. flush (only when there are no writer warps): leaf + every ancestor this item carried
+  if (!has_writers && tid < m) {
     if (sum) sum[leafnode] = leaf_v;
     if (mn) mn[leafnode] = leaf_v;
     for (int l = 0; l < levels_done; ++l) {
@@ -870,10 +910,10 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   if (grid < 1) grid = 1;
   int *ticket = static_cast<int *>(workspace);
   T *scratch = reinterpret_cast<T *>(static_cast<unsigned char *>(workspace) + kUpdCtrlBytes);
-  tree_update_cta_kernel<T, FUSED><<<(unsigned)grid, np, smem, st>>>(sum, mn, capacity, depth, index, value, (int)n,
-                                                                    scalar, fp.alpha, fp.eps, fp.max_out, ticket,
-                                                                    scratch, g_debug_ticks, fp.index_base,
-                                                                    fp.index_limit < 0 ? capacity : fp.index_limit);
+  const int threads = (np <= 512 && depth <= 32) ? 2 * np : np;  // room for the writer warps?
+  tree_update_cta_kernel<T, FUSED><<<(unsigned)grid, threads, smem, st>>>(
+      sum, mn, capacity, depth, index, value, (int)n, scalar, fp.alpha, fp.eps, fp.max_out, ticket, scratch,
+      g_debug_ticks, fp.index_base, fp.index_limit < 0 ? capacity : fp.index_limit, np);
   return check_launch("tree_update_cta_kernel");
 }
 
