@@ -136,6 +136,7 @@ def gae_ring(dev, rows: int, T: int, g, min_bytes: int = 160 << 20):
     """Input sets for GAE whose total footprint exceeds L2 so that every call reads cold data."""
     per = rows * T * 14
     n = max(2, -(-min_bytes // per))
+    n += n % 2  # even: the sharded buffer alternates its two receive buffers from one step to the next
     ring = []
     for _ in range(n):
         v, nv, r = (torch.randn(rows, T, 1, device=dev, generator=g) for _ in range(3))
@@ -322,6 +323,29 @@ def run_ours(args) -> dict:
         if not distributed:
             graphs = [CudaGraphStep(st, generators=[gen], warmup=1) for st in steps]
             ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
+        elif rb._use_nvlink(dev):
+            # sharded + NVLink transport: the gather kernel itself broadcasts the rows into every rank's receive
+            # buffer and a signal-pad barrier closes the exchange -- no NCCL call, so the WHOLE step is one graph.
+            # Receive buffers are double-buffered: slot i uses buffer i % 2 (R is even), fixed at capture time.
+            def make_dist_step(slot: int):
+                v, nv, r, d8, t8 = ring8[slot]
+
+                def step():
+                    main = torch.cuda.current_stream(dev)
+                    side_gae.wait_stream(main)
+                    with torch.cuda.stream(side_gae):
+                        a, tg = be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
+                    rb.local_draw()
+                    rb.exchange()
+                    batch = rb.finalize()
+                    rb.update_priority(batch.get("index"), td_err)
+                    main.wait_stream(side_gae)
+                    return batch, a, tg
+
+                return step
+
+            graphs = [CudaGraphStep(make_dist_step(i), generators=[gen], warmup=2) for i in range(R)]  # 3 calls/slot
+            ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
         else:
             draw = CudaGraphStep(lambda: rb.local_draw(static_buffers=True), generators=[gen], warmup=1)
 
@@ -432,6 +456,10 @@ def run_ours(args) -> dict:
         ms_graph = None
 
     hbm_peak, peak_src = peaks()
+    transport = None
+    if distributed:
+        transport = ("gather kernel broadcasts over NVLink peer memory + signal-pad barrier" if rb._symm not in (None, False)
+                     else "NCCL all-gather issued eagerly between two graphs")
     result = None
     if rank == 0:
         roof = kernel_roofline(dev, rb, ring, hbm_peak, peak_src) if world == 1 else None
@@ -446,8 +474,8 @@ def run_ours(args) -> dict:
             "config": {"workload": f"C2 PER sample+update B=256 @1M Atari transitions ({n_leaves} leaves) + C3 GAE [4096,128]",
                        "capacity_per_gpu": CAPACITY, "batch_per_gpu": BATCH, "gae_shape": [GAE_ROWS, GAE_T, 1],
                        "alpha": ALPHA, "beta": BETA, "gamma": GAMMA, "lmbda": LMBDA,
-                       "launch": ("cuda_graph replay of the public-API step" + (" (NCCL all-gather eager between two graphs)" if world > 1 else "")) if ms_graph is not None else "eager python API",
-                       "parallelism": f"capacity-sharded x{world}, 1 all-gather/sample" if world > 1 else "single GPU",
+                       "launch": ("cuda_graph replay of the public-API step" + (f" ({transport})" if world > 1 else "")) if ms_graph is not None else "eager python API",
+                       "parallelism": f"capacity-sharded x{world}, {transport}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (56 GB storage, random rows; GAE inputs rotate through >160 MB)"},
             "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5),

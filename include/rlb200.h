@@ -45,6 +45,7 @@ extern "C" {
 #define RLB_F64 1
 
 #define RLB_MAX_LEAVES 24 /* leaves gathered by one rlb_gather launch; callers chunk above this */
+#define RLB_MAX_PEERS 16  /* destinations (local + NVLink peers) one launch can broadcast to */
 
 /* gather modes (rlb_gather `mode`) */
 #define RLB_GATHER_AUTO 0   /* bulk-DMA (TMA) staging for wide 16-B aligned rows, vector path otherwise */
@@ -166,13 +167,17 @@ int rlb_per_update(void *sum_tree /*[dev]*/, void *min_tree /*[dev]*/, int64_t c
  *     dst[k][b, :] = src[k][index[b], :]        b in [0, B), rows are `row_bytes[k]` bytes,
  * source rows `src_stride_bytes[k]` apart, destination rows `dst_stride_bytes[k]` apart (NULL =
  * contiguous; a stride lets every leaf land in its column of one packed [B, row] buffer, e.g. the
- * send buffer of the sharded buffer's all-gather, with no staging copy).  Negative indices wrap
+ * send buffer of the sharded buffer's all-gather, with no staging copy).  With n_peers > 0 every destination
+ * byte is written to dst + peer_delta[p] for each p (16-B aligned byte offsets; include 0 for the local
+ * copy): passing the offsets of the peers' symmetric receive buffers (NVLink peer memory) makes the gather
+ * kernel broadcast the rows itself -- gather + all-gather fused in one launch.  Negative indices wrap
  * (index + len) as in torch indexing; out-of-range indices set RLB_STATUS_INDEX_OOB in *status
  * and are clamped (torch raises IndexError; callers that want the exception read the status). */
 int rlb_gather(const void *const *src /*[host] n_leaves [dev] pointers*/,
                void *const *dst /*[host] n_leaves [dev] pointers*/, const int64_t *row_bytes /*[host]*/,
                const int64_t *src_stride_bytes /*[host]*/, const int64_t *dst_stride_bytes /*[host] or NULL*/,
-               int n_leaves, const int64_t *index /*[dev] B*/, int64_t B, int64_t len, int mode,
+               const int64_t *peer_delta /*[host] n_peers or NULL*/, int n_peers, int n_leaves,
+               const int64_t *index /*[dev] B*/, int64_t B, int64_t len, int mode,
                int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
 
 /* TensorStorage.set for a tensor cursor (storages.py:1028-1096: storage[cursor] = data per leaf,
@@ -192,7 +197,8 @@ int rlb_scatter(const void *const *src /*[host]*/, void *const *dst /*[host]*/,
  * optionally, a contiguous copy of the global indices. */
 int rlb_shard_pack(void *rows /*[dev] B x row_bytes*/, int64_t row_bytes, int64_t meta_offset,
                    const int64_t *index /*[dev] B*/, const float *leaf /*[dev] B*/,
-                   const float *psum_pmin /*[dev] 2*/, int64_t index_base, int64_t B, rlb_stream_t stream);
+                   const float *psum_pmin /*[dev] 2*/, int64_t index_base, int64_t B,
+                   const int64_t *peer_delta /*[host] or NULL*/, int n_peers, rlb_stream_t stream);
 int rlb_shard_weights(const void *rows /*[dev] B x row_bytes*/, int64_t row_bytes, int64_t meta_offset, int64_t B,
                       double beta, float *weight_out /*[dev] B*/, int64_t *index_out /*[dev] B or NULL*/,
                       rlb_stream_t stream);

@@ -64,6 +64,12 @@ struct GatherLeaf {
 
 struct GatherParams {
   GatherLeaf leaf[RLB_MAX_LEAVES];
+  // every destination byte is written to dst + peer_delta[p] for p < n_peers: delta 0 is the local buffer, the
+  // others are the same location of the symmetric receive buffer on peer GPUs (NVLink peer memory), so the
+  // gathered rows are broadcast by the gather kernel itself -- no separate all-gather
+  int64_t peer_delta[RLB_MAX_PEERS];
+  int n_peers;
+  int pad0_;
   const int64_t *index;
   int64_t B;
   int64_t len;
@@ -143,7 +149,8 @@ __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams
   for (int k = 0; k < kVecUnroll; ++k) {
     if (ok[k]) {
       const int64_t drow = SCATTER ? ix[k] * L.stride : b[k] * L.ostride;
-      st_stream(reinterpret_cast<V *>(L.dst + drow) + j[k], val[k]);
+      for (int p = 0; p < P.n_peers; ++p)
+        st_stream(reinterpret_cast<V *>(L.dst + P.peer_delta[p] + drow) + j[k], val[k]);
     }
   }
 }
@@ -267,7 +274,8 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
       if (lane == 0) {
         mbar_wait_parity(&my->full[stage], (uint32_t)((n_stored / kStages) & 1));
         fence_proxy_async_smem();
-        bulk_s2g(my->dst[stage], my_ring + (size_t)stage * kChunk, my->bytes[stage]);
+        for (int p = 0; p < P.n_peers; ++p)  // local buffer and, when sharded, every peer's receive buffer
+          bulk_s2g(my->dst[stage] + P.peer_delta[p], my_ring + (size_t)stage * kChunk, my->bytes[stage]);
         bulk_commit();
       }
       ++n_stored;
@@ -306,7 +314,7 @@ static int pick_vec_log2(const void *src, const void *dst, int64_t row_bytes, in
 
 template <bool SCATTER>
 static int launch_rows(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *stride,
-                       const int64_t *ostride, int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status,
+                       const int64_t *ostride, const int64_t *peer_delta, int n_peers, int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status,
                        cudaStream_t st, const char *who) {
   RLB_REQUIRE(n_leaves >= 0 && n_leaves <= RLB_MAX_LEAVES, RLB_ELIMIT, "%s: n_leaves=%d exceeds RLB_MAX_LEAVES=%d",
               who, n_leaves, RLB_MAX_LEAVES);
@@ -317,8 +325,15 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
   const int sms = sm_count();
   if (sms <= 0) return RLB_ENODEV;
 
+  RLB_REQUIRE(n_peers >= 0 && n_peers <= RLB_MAX_PEERS && (n_peers == 0 || peer_delta), RLB_ELIMIT,
+              "%s: n_peers=%d outside [0, %d] or null peer_delta", who, n_peers, RLB_MAX_PEERS);
   GatherParams P;
   memset(&P, 0, sizeof(P));
+  P.n_peers = n_peers > 0 ? n_peers : 1;  // no peer list = the local buffer only
+  for (int p = 0; p < n_peers; ++p) {
+    RLB_REQUIRE(peer_delta[p] % 16 == 0, RLB_EINVAL, "%s: peer_delta[%d] is not 16-byte aligned", who, p);
+    P.peer_delta[p] = peer_delta[p];
+  }
   P.index = index;
   P.B = B;
   P.len = len;
@@ -404,17 +419,17 @@ using namespace rlb;
 extern "C" {
 
 int rlb_gather(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *src_stride_bytes,
-               const int64_t *dst_stride_bytes, int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode,
-               int32_t *status, rlb_stream_t stream) {
+               const int64_t *dst_stride_bytes, const int64_t *peer_delta, int n_peers, int n_leaves,
+               const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status, rlb_stream_t stream) {
   RLB_REQUIRE(mode == RLB_GATHER_AUTO || mode == RLB_GATHER_VECTOR || mode == RLB_GATHER_BULK, RLB_EINVAL,
               "rlb_gather: unknown mode %d", mode);
-  return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, dst_stride_bytes, n_leaves, index, B, len, mode,
-                            status, as_stream(stream), "rlb_gather");
+  return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, dst_stride_bytes, peer_delta, n_peers, n_leaves,
+                            index, B, len, mode, status, as_stream(stream), "rlb_gather");
 }
 
 int rlb_scatter(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *dst_stride_bytes,
                 int n_leaves, const int64_t *index, int64_t B, int64_t len, int32_t *status, rlb_stream_t stream) {
-  return launch_rows<true>(src, dst, row_bytes, dst_stride_bytes, nullptr, n_leaves, index, B, len,
+  return launch_rows<true>(src, dst, row_bytes, dst_stride_bytes, nullptr, nullptr, 0, n_leaves, index, B, len,
                            RLB_GATHER_VECTOR, status, as_stream(stream), "rlb_scatter");
 }
 

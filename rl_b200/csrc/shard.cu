@@ -8,6 +8,7 @@
 // which is the reference formula (samplers.py:945-953) when there is a single shard.  Both are latency-sized
 // (B <= a few thousand rows); neither touches the row payload.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -25,17 +26,26 @@ __device__ __forceinline__ float pow_like_torch_f(float x, float y) {
   return powf(x, y);
 }
 
+struct PeerList {
+  int64_t delta[RLB_MAX_PEERS];
+  int n;
+};
+
 __global__ void shard_pack_kernel(uint8_t *rows, int64_t row_bytes, int64_t meta_off, const int64_t *__restrict__ index,
                                   const float *__restrict__ leaf, const float *__restrict__ psum_pmin,
-                                  int64_t index_base, int64_t B) {
+                                  int64_t index_base, int64_t B, const PeerList peers) {
   const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (b >= B) return;
-  uint8_t *m = rows + b * row_bytes + meta_off;  // 8-byte aligned by construction of the layout
-  *reinterpret_cast<int64_t *>(m) = index[b] + index_base;
-  float *f = reinterpret_cast<float *>(m + 8);
-  f[0] = leaf[b];
-  f[1] = psum_pmin[0];
-  f[2] = psum_pmin[1];
+  const int64_t gi = index[b] + index_base;
+  const float p = leaf[b], S = psum_pmin[0], mn = psum_pmin[1];
+  for (int q = 0; q < peers.n; ++q) {  // the local rows and the same rows of every peer's receive buffer
+    uint8_t *m = rows + peers.delta[q] + b * row_bytes + meta_off;  // 8-byte aligned by construction of the layout
+    *reinterpret_cast<int64_t *>(m) = gi;
+    float *f = reinterpret_cast<float *>(m + 8);
+    f[0] = p;
+    f[1] = S;
+    f[2] = mn;
+  }
 }
 
 // one CTA: pass 1 reduces min_b(m_b / S_b) over all gathered rows, pass 2 writes the weights (and a contiguous
@@ -76,14 +86,21 @@ using namespace rlb;
 extern "C" {
 
 int rlb_shard_pack(void *rows, int64_t row_bytes, int64_t meta_offset, const int64_t *index, const float *leaf,
-                   const float *psum_pmin, int64_t index_base, int64_t B, rlb_stream_t stream) {
+                   const float *psum_pmin, int64_t index_base, int64_t B, const int64_t *peer_delta, int n_peers,
+                   rlb_stream_t stream) {
   RLB_REQUIRE(B >= 0 && row_bytes > 0 && meta_offset >= 0 && meta_offset + 20 <= row_bytes && meta_offset % 8 == 0,
               RLB_EINVAL, "rlb_shard_pack: bad layout");
   if (B == 0) return RLB_OK;
   RLB_REQUIRE(rows && index && leaf && psum_pmin, RLB_EINVAL, "rlb_shard_pack: null pointer");
+  RLB_REQUIRE(n_peers >= 0 && n_peers <= RLB_MAX_PEERS && (n_peers == 0 || peer_delta), RLB_ELIMIT,
+              "rlb_shard_pack: bad peer list");
+  PeerList peers;
+  memset(&peers, 0, sizeof(peers));
+  peers.n = n_peers > 0 ? n_peers : 1;
+  for (int p = 0; p < n_peers; ++p) peers.delta[p] = peer_delta[p];
   const int threads = 128;
   shard_pack_kernel<<<(unsigned)((B + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
-      static_cast<uint8_t *>(rows), row_bytes, meta_offset, index, leaf, psum_pmin, index_base, B);
+      static_cast<uint8_t *>(rows), row_bytes, meta_offset, index, leaf, psum_pmin, index_base, B, peers);
   return check_launch("shard_pack_kernel");
 }
 

@@ -11,8 +11,15 @@ every rank and assembles the global minibatch with ONE all-gather over NVLink:
     (sum and min of its priorities), so importance weights can be finalised identically on every rank after
     the gather, normalised over the WHOLE buffer as the reference normalises over its single buffer:
         w_i = ((p_i / S_r) / min_r'(m_r' / S_r')) ** -beta          (W = 1  ->  (p_i / p_min) ** -beta)
-  * ``torch.distributed.all_gather_into_tensor`` (NCCL) moves ``B/W * row`` bytes per rank; leaves of the
-    returned batch are strided views into the receive buffer.
+  * transport "nvlink" (default on CUDA when torch's symmetric memory is available): the receive buffers of all
+    ranks are ONE symmetric allocation (``torch.distributed._symmetric_memory``), so every rank knows the
+    address of its rows in every peer's buffer and the gather kernel's shared-memory stages are stored W times
+    -- once locally, W-1 times through NVLink peer memory.  Gather and all-gather are the SAME launch
+    (``rlb_gather`` with ``peer_delta``); a signal-pad barrier (one tiny kernel) closes the exchange, and the
+    whole step is capturable in a CUDA graph.  Receive buffers are double-buffered: a returned batch stays valid
+    until the second next ``sample()``.
+  * transport "nccl": ``torch.distributed.all_gather_into_tensor`` moves ``B/W * row`` bytes per rank (also the
+    CPU/gloo test path).  Either way the leaves of the returned batch are strided views into the receive buffer.
 
 ``update_priority`` takes GLOBAL indices (replicated on every rank, or any subset): each rank rewrites the
 ones it owns and skips the rest inside the kernel (negative local index) -- no collective, no sync.
@@ -27,6 +34,10 @@ from .. import ops
 from .replay_buffers import TensorDictPrioritizedReplayBuffer
 from .storages import LazyTensorStorage, flatten_data, unflatten_data
 from .tensordict_lite import is_tensor_collection
+
+
+class _NoSymmetricMemory(RuntimeError):
+    pass
 
 
 def _align(x: int, a: int) -> int:
@@ -82,7 +93,8 @@ class ShardedPrioritizedReplayBuffer:
     """
 
     def __init__(self, *, alpha: float, beta: float, capacity: int, eps: float = 1e-8, priority_key: str = "td_error",
-                 batch_size: int | None = None, device="cuda", generator=None, process_group=None):
+                 batch_size: int | None = None, device="cuda", generator=None, process_group=None,
+                 transport: str = "auto"):
         import torch.distributed as dist
 
         self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
@@ -99,6 +111,11 @@ class ShardedPrioritizedReplayBuffer:
             alpha=alpha, beta=beta, eps=eps, priority_key=priority_key,
             storage=LazyTensorStorage(self.shard_capacity, device=self.device),
             batch_size=None if batch_size is None else batch_size // self.world, generator=generator)
+        if transport not in ("auto", "nvlink", "nccl"):
+            raise ValueError("transport must be 'auto', 'nvlink' or 'nccl'")
+        self.transport = transport
+        self._symm = None        # (symmetric double buffer, handle, peer byte offsets)
+        self._parity = 0
         self._layout = None
         self._static = None
         self._send = self._recv = None
@@ -152,7 +169,18 @@ class ShardedPrioritizedReplayBuffer:
         if self._layout is None:
             self._layout = _PackedLayout(st._leaves)
         lay = self._layout
-        if static_buffers:
+        peers = None
+        nv = None
+        if self._use_nvlink(dev):
+            try:
+                nv = self._symmetric_buffers(batch_size, dev)
+            except _NoSymmetricMemory:
+                nv = None
+        if nv is not None:
+            buf, hdl, peers = nv
+            recv = buf[self._parity]
+            send = recv[self.rank * b_loc:(self.rank + 1) * b_loc]  # my rows inside the gathered batch
+        elif static_buffers:
             if self._static is None or self._static[0].shape[0] != b_loc:
                 self._static = (torch.empty((b_loc, lay.row), dtype=torch.uint8, device=dev),
                                 torch.empty((batch_size, lay.row), dtype=torch.uint8, device=dev))
@@ -165,17 +193,54 @@ class ShardedPrioritizedReplayBuffer:
             idx, _, leaf, pp = be.per_sample(smp._sum_tree.values, smp._min_tree.values, smp._max_capacity,
                                              smp._sum_tree.capacity, length, u, smp._beta, smp._semantics == "cpu",
                                              status=smp._status, want_aux=True)
-            be.gather(st._leaves, idx, length, out=lay.leaf_views(send))
-            be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity)  # trailer: 1 launch
+            # with `peers` the rows are written into every rank's receive buffer by this very launch
+            be.gather(st._leaves, idx, length, out=lay.leaf_views(send), peer_delta=peers)
+            be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity, peer_delta=peers)
         self.local_index = idx
         self._send, self._recv, self._bs = send, recv, batch_size
         return send
 
     def exchange(self) -> torch.Tensor:
-        """The ONE collective of sample(): all-gather the packed local draws (NCCL over NVLink)."""
+        """Close the exchange of sample().  nvlink: the rows are already on their way into every peer's buffer; a
+        signal-pad barrier (one small kernel, stream-ordered) waits until everybody's have landed.  nccl: the ONE
+        collective, an all-gather of the packed local draws."""
         if self.world > 1:
-            self._dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+            if self._symm is not None and self._recv.data_ptr() == self._symm[0][self._parity].data_ptr():
+                self._symm[1].barrier(channel=self._parity)
+                self._parity ^= 1  # the next draw fills the other buffer; this one stays valid meanwhile
+            else:
+                self._dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
         return self._recv
+
+    def _use_nvlink(self, dev) -> bool:
+        if self.world == 1 or dev.type != "cuda" or self.transport == "nccl":
+            return False
+        if self._symm is False:
+            return False
+        return True
+
+    def _symmetric_buffers(self, batch_size: int, dev):
+        """[2, B, row] symmetric receive buffer + the byte offsets from MY buffer to every rank's (0 for myself)."""
+        if self._symm is not None and self._symm is not False and self._symm[0].shape[1] == batch_size:
+            return self._symm
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            buf = symm_mem.empty((2, batch_size, self._layout.row), dtype=torch.uint8, device=dev)
+            hdl = symm_mem.rendezvous(buf, group=self.group if self.group is not None else self._dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            peers = [p - ptrs[self.rank] for p in ptrs]
+            if any(d % 16 for d in peers):
+                raise RuntimeError("symmetric buffers are not 16-byte aligned relative to each other")
+            self._symm = (buf, hdl, peers)
+            self._parity = 0
+        except Exception:
+            if self.transport == "nvlink":
+                raise
+            self._symm = False  # fall back to the NCCL all-gather for good
+            raise _NoSymmetricMemory()
+        return self._symm
+
 
     def finalize(self):
         """Views of the gathered buffer as the global batch + importance weights over the whole sharded buffer."""

@@ -45,9 +45,9 @@ _SIGNATURES = {
                                _vp, _vp]),
     "rlb_per_update": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _f64, _f64, _vp, _vp, _vp, _sz, _u32, _i64, _i64,
                                _vp]),
-    "rlb_shard_pack": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "rlb_shard_pack": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp]),
     "rlb_shard_weights": (_i32, [_vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp]),
-    "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
 }
@@ -262,12 +262,15 @@ class CudaBackend:
                 int(index_limit), self._stream(dev)), "rlb_per_update")
 
     # -- sharded minibatch trailer -----------------------------------------------------------------
-    def shard_pack(self, rows: torch.Tensor, meta_offset: int, index, leaf, psum_pmin, index_base: int) -> None:
+    def shard_pack(self, rows: torch.Tensor, meta_offset: int, index, leaf, psum_pmin, index_base: int,
+                   peer_delta: Sequence[int] | None = None) -> None:
         dev = self._cuda(rows, index, leaf, psum_pmin)
+        n_peers = 0 if peer_delta is None else len(peer_delta)
+        peers = (ctypes.c_int64 * n_peers)(*peer_delta) if n_peers else None
         with self._Guard(dev):
             self._check(self.L.rlb_shard_pack(rows.data_ptr(), rows.stride(0), meta_offset, index.data_ptr(),
                                               leaf.data_ptr(), psum_pmin.data_ptr(), int(index_base), rows.shape[0],
-                                              self._stream(dev)), "rlb_shard_pack")
+                                              peers, n_peers, self._stream(dev)), "rlb_shard_pack")
 
     def shard_weights(self, rows: torch.Tensor, meta_offset: int, beta: float):
         dev = self._cuda(rows)
@@ -300,8 +303,8 @@ class CudaBackend:
                               * s.element_size() for s in ss])
                 bigp, smallp = P(*[b.data_ptr() for b in bs]), P(*[s.data_ptr() for s in ss])
                 if who == "rlb_gather":
-                    rc = self.L.rlb_gather(bigp, smallp, rowb, bstride, sstride, n, index.data_ptr(), B, length, mode,
-                                           self._p(status), self._stream(dev))
+                    rc = self.L.rlb_gather(bigp, smallp, rowb, bstride, sstride, None, 0, n, index.data_ptr(), B, length,
+                                           mode, self._p(status), self._stream(dev))
                 else:
                     rc = self.L.rlb_scatter(smallp, bigp, rowb, bstride, n, index.data_ptr(), B, length,
                                             self._p(status), self._stream(dev))
@@ -313,9 +316,11 @@ class CudaBackend:
             raise RuntimeError("leaves must be [N, ...] tensors whose rows are contiguous")
 
     def gather(self, leaves: Sequence[torch.Tensor], index: torch.Tensor, length: int, mode: int = GATHER_AUTO,
-               status: torch.Tensor | None = None, out: Sequence[torch.Tensor] | None = None) -> list[torch.Tensor]:
-        """out[k][b] = leaves[k][index[b]].  `out` may be given (rows may be strided views into a packed buffer)."""
-        return self.gather_plan(leaves).run(index, length, mode=mode, status=status, out=out)
+               status: torch.Tensor | None = None, out: Sequence[torch.Tensor] | None = None,
+               peer_delta: Sequence[int] | None = None) -> list[torch.Tensor]:
+        """out[k][b] = leaves[k][index[b]].  `out` may be given (rows may be strided views into a packed buffer);
+        `peer_delta` (byte offsets, including 0) replicates every written byte into NVLink peer buffers."""
+        return self.gather_plan(leaves).run(index, length, mode=mode, status=status, out=out, peer_delta=peer_delta)
 
     def gather_plan(self, leaves: Sequence[torch.Tensor]) -> "GatherPlan":
         """Pre-marshalled source side of rlb_gather for a fixed set of storage leaves (pointers, row sizes and
@@ -361,8 +366,10 @@ class GatherPlan:
                                 I(*[t.stride(0) * t.element_size() for t in ts]), I))
 
     def run(self, index: torch.Tensor, length: int, mode: int = GATHER_AUTO, status: torch.Tensor | None = None,
-            out: Sequence[torch.Tensor] | None = None) -> list[torch.Tensor]:
+            out: Sequence[torch.Tensor] | None = None, peer_delta: Sequence[int] | None = None) -> list[torch.Tensor]:
         be = self.be
+        n_peers = 0 if peer_delta is None else len(peer_delta)
+        peers = (ctypes.c_int64 * n_peers)(*peer_delta) if n_peers else None
         if not index.is_cuda or index.device != self.dev:
             raise RuntimeError(f"rl_b200: index must live on {self.dev}, got {index.device}; there is no CPU path.")
         if index.dtype != torch.int64:
@@ -390,8 +397,8 @@ class GatherPlan:
                 if strided:
                     dstride = I(*[(o.stride(0) if B > 1 else (o[0].numel() if o.ndim > 1 else 1)) * o.element_size()
                                   for o in outs])
-                be._check(be.L.rlb_gather(srcp, dstp, rowb, sstride, dstride, n, index.data_ptr(), B, length, mode,
-                                          be._p(status), stream), "rlb_gather")
+                be._check(be.L.rlb_gather(srcp, dstp, rowb, sstride, dstride, peers, n_peers, n, index.data_ptr(), B,
+                                          length, mode, be._p(status), stream), "rlb_gather")
         return list(out)
 
 

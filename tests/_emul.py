@@ -155,7 +155,7 @@ class OracleBackend:
         self.tree_update(sum_tree, min_tree, capacity, index, leaf, workspace, epoch)
 
     # ---- sharded minibatch trailer
-    def shard_pack(self, rows, meta_offset, index, leaf, psum_pmin, index_base):
+    def shard_pack(self, rows, meta_offset, index, leaf, psum_pmin, index_base, peer_delta=None):
         m = meta_offset
         rows[:, m:m + 8].view(torch.int64).view(-1).copy_(index + index_base)
         rows[:, m + 8:m + 12].view(torch.float32).view(-1).copy_(leaf)
@@ -171,7 +171,7 @@ class OracleBackend:
         return torch.pow((p / S) / (mn / S).min(), -beta), gidx
 
     # ---- storage rows
-    def gather(self, leaves, index, length, mode=0, status=None, out=None):
+    def gather(self, leaves, index, length, mode=0, status=None, out=None, peer_delta=None):
         ix = torch.where(index < 0, index + length, index)
         if ((ix < 0) | (ix >= length)).any():
             if status is not None:
@@ -188,7 +188,7 @@ class OracleBackend:
         be = self
 
         class _Plan:
-            def run(self, index, length, mode=0, status=None, out=None):
+            def run(self, index, length, mode=0, status=None, out=None, peer_delta=None):
                 return be.gather(leaves, index, length, mode=mode, status=status, out=out)
 
         return _Plan()
