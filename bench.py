@@ -369,8 +369,20 @@ def run_ours(args) -> dict:
 
             ms_graph = timed(graph_step, args.steps, args.warmup, sync_all)
     except Exception as err:
-        graph_err = f"{type(err).__name__}: {err}"[:200]
+        import traceback
+
+        graph_err = f"{type(err).__name__}: {err}"[:300]
+        print(f"[bench rank {rank}] CUDA-graph path failed, falling back to eager: {graph_err}\n"
+              + "".join(traceback.format_exc().splitlines(True)[-6:]), file=sys.stderr, flush=True)
         graphs, ms_graph = None, None
+        # a capture that died half-way leaves the generator in capture mode: give the sampler a fresh one
+        torch.cuda.synchronize()
+        fresh = torch.Generator(device=dev).manual_seed(4242 + rank)
+        if hasattr(rb, "local"):
+            rb.local.set_rng(fresh)
+        else:
+            rb.set_rng(fresh)
+        g = fresh
     clk = clocks.stop() if clocks else None
 
     # ---- sub-metrics (eager, same method)
@@ -391,7 +403,9 @@ def run_ours(args) -> dict:
     sample0 = rb.sample()
     out_keys = list(sample0.keys(True, True))
     lanes = []
-    n_lanes = 3
+    # N > 1: one lane -- the sharded buffer's two receive buffers are overwritten by the PEERS' next-but-one draw,
+    # which is only ordered against work on the sampling stream
+    n_lanes = 1 if distributed else 3
     for lane in range(n_lanes):
         s = torch.cuda.Stream(dev)
         host_in = tuple(pin(x) for x in ring[lane % R])
@@ -479,7 +493,7 @@ def run_ours(args) -> dict:
                        "l2": "inputs larger than L2 (56 GB storage, random rows; GAE inputs rotate through >160 MB)"},
             "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5),
-                    "note": "eager python API, pinned host buffers, three lanes rotate so D2H overlaps the next steps' H2D + compute"},
+                    "note": f"eager python API, pinned host buffers, {n_lanes} lane(s): with several lanes D2H overlaps the next steps' H2D + compute"},
             "gpu_launches": (5 if world == 1 else 9) * args.steps,
             "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
                           "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),

@@ -275,10 +275,6 @@ class PrioritizedSampler(Sampler):
         return self._epoch
 
     def _tree_workspace(self, n: int):
-        if n > 1024 and self._sum_tree.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
-            raise RuntimeError(
-                "update_priority with more than 1024 entries uses an epoch-stamped scatter that cannot be replayed "
-                "from a CUDA graph; split the batch or run it outside the graph.")
         if self._workspace is None:  # ticket + sibling scratch (<= 1024 items) and stamps (larger batches)
             self._workspace = ops.backend().tree_workspace(self._max_capacity, self._sum_tree.device)
         return self._workspace
@@ -402,9 +398,17 @@ class PrioritizedSampler(Sampler):
         tree_dtype = self._sum_tree._dtype
         if tree_dtype == torch.float32:
             priority = priority.to(torch.float32)
-            ops.backend().per_update(self._sum_tree.values, self._min_tree.values, self._sum_tree.capacity, index,
-                                     priority, self._alpha, self._eps, self._max_priority_buf,
-                                     self._tree_workspace(index.numel()), self._tree_epoch(), index_base, index_limit)
+            n = index.numel()
+            # batches above 1024 use an epoch-stamped scatter whose epoch would be frozen into a captured graph;
+            # under capture they are applied as consecutive chunks of <= 1024 instead (input order is preserved, so
+            # "the last duplicate wins" still holds across chunks)
+            step = 1024 if (n > 1024 and dev.type == "cuda" and torch.cuda.is_current_stream_capturing()) else n
+            for lo in range(0, n, step):
+                pr = priority if priority.numel() == 1 else priority[lo:lo + step]
+                ops.backend().per_update(self._sum_tree.values, self._min_tree.values, self._sum_tree.capacity,
+                                         index[lo:lo + step], pr, self._alpha, self._eps, self._max_priority_buf,
+                                         self._tree_workspace(min(step, n - lo)), self._tree_epoch(), index_base,
+                                         index_limit)
         else:
             if index_base or index_limit >= 0:
                 index = index - index_base

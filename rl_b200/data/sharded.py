@@ -114,6 +114,7 @@ class ShardedPrioritizedReplayBuffer:
         if transport not in ("auto", "nvlink", "nccl"):
             raise ValueError("transport must be 'auto', 'nvlink' or 'nccl'")
         self.transport = transport
+        self._last_gidx = None
         self._symm = None        # (symmetric double buffer, handle, peer byte offsets)
         self._parity = 0
         self._layout = None
@@ -248,6 +249,7 @@ class ShardedPrioritizedReplayBuffer:
         leaves = lay.leaf_views(recv)
         batch = unflatten_data(leaves, self.local.storage._spec, (self._bs,))
         weight, gidx = ops.backend().shard_weights(recv, lay.meta, smp._beta)  # identical on every rank
+        self._last_gidx = gidx
         if is_tensor_collection(batch):
             batch.set("index", gidx)
             batch.set("priority_weight", weight)
@@ -263,6 +265,15 @@ class ShardedPrioritizedReplayBuffer:
     def update_priority(self, index: torch.Tensor, priority) -> None:
         """``index`` holds GLOBAL indices; entries owned by other ranks are skipped inside the kernel."""
         index = torch.as_tensor(index, dtype=torch.long, device=self.device)
+        if index is self._last_gidx and self._bs is not None:
+            # the index vector of the batch sample() just returned: rows [rank*B/W, (rank+1)*B/W) are exactly the
+            # draws from this shard, every other row belongs to another rank -- no need to scan them
+            b_loc = self._bs // self.world
+            lo = self.rank * b_loc
+            priority = torch.as_tensor(priority, device=self.device)
+            if priority.numel() > 1:
+                priority = priority.reshape(-1)[lo:lo + b_loc]
+            index = index[lo:lo + b_loc]
         self.local.sampler.update_priority(index, priority, storage=self.local.storage,
                                            index_base=self.rank * self.shard_capacity,
                                            index_limit=self.shard_capacity)
