@@ -402,6 +402,9 @@ def run_ours(args) -> dict:
     pin = lambda t: t.cpu().pin_memory()
     sample0 = rb.sample()
     out_keys = list(sample0.keys(True, True))
+    # N > 1: every rank delivers ITS rows of the gathered batch to the host (the job as a whole lands the global
+    # minibatch in host memory once), plus its own GAE outputs
+    own = slice(rank * BATCH, (rank + 1) * BATCH) if distributed else slice(None)
     lanes = []
     # N > 1: one lane -- the sharded buffer's two receive buffers are overwritten by the PEERS' next-but-one draw,
     # which is only ordered against work on the sampling stream
@@ -412,7 +415,8 @@ def run_ours(args) -> dict:
         lanes.append({
             "stream": s, "host_in": host_in, "host_td": pin(td_err),
             "dev_in": [torch.empty_like(x) for x in ring[lane % R]], "dev_td": torch.empty_like(td_err),
-            "host_out": {k: torch.empty(sample0.get(k).shape, dtype=sample0.get(k).dtype).pin_memory() for k in out_keys},
+            "host_out": {k: torch.empty(sample0.get(k)[own].shape, dtype=sample0.get(k).dtype).pin_memory()
+                         for k in out_keys},
             "host_adv": torch.empty(GAE_ROWS, GAE_T, 1).pin_memory(), "host_tgt": torch.empty(GAE_ROWS, GAE_T, 1).pin_memory(),
             "done": torch.cuda.Event(),
         })
@@ -429,7 +433,7 @@ def run_ours(args) -> dict:
         a, tg = be.gae(di[0], di[1], di[2], di[3].view(torch.uint8), di[4].view(torch.uint8), gs[0], gs[1],
                        GAE_ROWS, GAE_T, 1)
         for k, hv in L["host_out"].items():
-            hv.copy_(batch.get(k), non_blocking=True)
+            hv.copy_(batch.get(k)[own], non_blocking=True)
         L["host_adv"].copy_(a, non_blocking=True)
         L["host_tgt"].copy_(tg, non_blocking=True)
 

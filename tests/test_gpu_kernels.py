@@ -390,3 +390,63 @@ def test_successive_traj_gae(cuda_backend):
                                                 done=done[:, cut:], terminated=done[:, cut:])
     torch.testing.assert_close(a, torch.cat([a1, a2], 1), rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(t, torch.cat([t1, t2], 1), rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------- peer broadcast
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gather_peer_replication_single_gpu(cuda_backend, mode):
+    """rlb_gather / rlb_shard_pack with peer_delta: every destination byte also lands at dst + delta[p].  On one
+    GPU the 'peers' are three slices of one buffer (the multi-GPU run, tests/mgpu_check.py, passes the offsets of the
+    NVLink symmetric receive buffers instead)."""
+    from rl_b200.data.sharded import _PackedLayout
+
+    N, B = 5000, 96
+    g = torch.Generator(device=dev()).manual_seed(4)
+    leaves = [torch.randint(0, 255, (N, 4, 84, 84), dtype=torch.uint8, device=dev(), generator=g),
+              torch.randn(N, 17, device=dev(), generator=g), torch.randint(0, 9, (N, 1), device=dev(), generator=g),
+              torch.rand(N, 1, device=dev(), generator=g) < 0.5]
+    lay = _PackedLayout(leaves)
+    buf = torch.zeros((3, B, lay.row), dtype=torch.uint8, device=dev())
+    step = B * lay.row
+    idx = torch.randint(0, N, (B,), device=dev(), generator=g)
+    cuda_backend.gather(leaves, idx, N, mode=mode, out=lay.leaf_views(buf[0]), peer_delta=[0, step, 2 * step])
+    leaf_p = torch.rand(B, device=dev(), generator=g)
+    pp = torch.tensor([3.5, 0.25], device=dev())
+    cuda_backend.shard_pack(buf[0], lay.meta, idx, leaf_p, pp, 1000, peer_delta=[0, step, 2 * step])
+    for c in range(3):
+        for leaf, view in zip(leaves, lay.leaf_views(buf[c])):
+            assert torch.equal(view, leaf[idx]), c
+        gi, p, S, m = lay.meta_views(buf[c])
+        assert torch.equal(gi, idx + 1000) and torch.equal(p, leaf_p)
+        assert torch.all(S == 3.5) and torch.all(m == 0.25)
+    assert torch.equal(buf[0], buf[1]) and torch.equal(buf[0], buf[2])
+    w, gidx = cuda_backend.shard_weights(buf[1], lay.meta, 0.4)
+    torch.testing.assert_close(w, torch.pow((leaf_p / 3.5) / (0.25 / 3.5), -0.4), rtol=1e-6, atol=0)
+    assert torch.equal(gidx, idx + 1000)
+
+
+def test_update_priority_chunked_under_capture(cuda_backend):
+    """More than 1024 priorities inside a CUDA graph: applied as <=1024-item chunks, same heap as the eager call."""
+    from rl_b200.data import PrioritizedSampler
+
+    N, n = 100_000, 3000
+    g = torch.Generator(device=dev()).manual_seed(8)
+    idx = torch.randint(0, N, (n,), device=dev(), generator=g)
+    idx[::7] = idx[0]  # duplicates across chunk boundaries: the last one must win
+    pr = torch.rand(n, device=dev(), generator=g) + 0.1
+    a, b = PrioritizedSampler(N, 0.6, 0.4, device=dev()), PrioritizedSampler(N, 0.6, 0.4, device=dev())
+    for s in (a, b):
+        s.update_priority(torch.arange(N, device=dev()), torch.ones(N, device=dev()))
+    a.update_priority(idx, pr)  # eager: stamp-dedupe general path
+    s_ = torch.cuda.Stream(dev())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s_):
+        b.update_priority(idx[:8], pr[:8])  # lazy init outside capture
+        b.update_priority(idx[:8], torch.ones(8, device=dev()))
+        s_.synchronize()
+        with torch.cuda.graph(graph, stream=s_):
+            b.update_priority(idx, pr)
+        graph.replay()
+        s_.synchronize()
+    assert torch.equal(a._sum_tree.values[1:], b._sum_tree.values[1:])
+    assert torch.equal(a._min_tree.values[1:], b._min_tree.values[1:])
