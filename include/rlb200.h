@@ -218,6 +218,18 @@ int rlb_gae(const void *state_value /*[dev]*/, const void *next_state_value /*[d
             double gamma, double gammalmbda, int64_t rows, int64_t T, int64_t F, int dtype,
             void *advantage /*[dev]*/, void *value_target /*[dev]*/, rlb_stream_t stream);
 
+/* TD(lambda) / TD(1) return -- replaces vec_td_lambda_return_estimate / td_lambda_return_estimate and (lmbda = 1)
+ * vec_td1_return_estimate / td1_return_estimate for scalar gamma, lmbda
+ * (objectives/value/functional.py:790-899, 993-1210, 464-570, 648-707).  Same reverse scan as rlb_gae:
+ *     nv_t = (1-term_t)*v'_t ;  G_t = r_t + gamma*((1-lmbda)*nv_t + lmbda*G'_{t+1}),
+ *     G'_{t+1} = nv_t where done_t or t = T-1 (bootstrap at the end of the window), else G_{t+1}.
+ * The caller passes gammalmbda = gamma*lmbda and one_minus_lmbda rounded as the reference's tensor ops round
+ * them (functional.py:1034-1046). */
+int rlb_td_lambda_return(const void *next_state_value /*[dev]*/, const void *reward /*[dev]*/,
+                         const uint8_t *done /*[dev]*/, const uint8_t *terminated /*[dev]*/, double gamma,
+                         double gammalmbda, double one_minus_lmbda, int64_t rows, int64_t T, int64_t F, int dtype,
+                         void *returns /*[dev]*/, rlb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

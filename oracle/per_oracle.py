@@ -288,3 +288,25 @@ def _gae(gamma, lmbda, v, nv, r, done, term, f64: bool):
         L.orc_gae_f32(_ptr(v_), _ptr(nv_), _ptr(r_), _ptr(d_), _ptr(t_), float(g32), gl, rows, T, F,
                       _ptr(adv), _ptr(tgt))
     return torch.from_numpy(adv), torch.from_numpy(tgt)
+
+
+def td_lambda(gamma, lmbda, next_state_value, reward, done, terminated=None, f64: bool = False):
+    """TD(lambda) return (functional.py:790-899, scalar gamma/lmbda) through the C oracle; fp32 (reference op order)
+    or float64 evaluation of the same recurrence on the fp32 inputs with the fp32-rounded gamma / lmbda."""
+    L = lib()
+    if terminated is None:
+        terminated = done
+    shape = tuple(reward.shape)
+    T, F = shape[-2], shape[-1]
+    rows = int(np.prod(shape[:-2], dtype=np.int64)) if len(shape) > 2 else 1
+    g32 = float(torch.as_tensor(gamma, dtype=torch.float32))
+    l32 = float(torch.as_tensor(lmbda, dtype=torch.float32))
+    c = lambda t, dt: np.ascontiguousarray(t.detach().cpu().numpy().astype(dt, copy=False))
+    nv_, r_, d_, t_ = c(next_state_value, np.float32), c(reward, np.float32), c(done, np.uint8), c(terminated, np.uint8)
+    if f64:
+        out = np.empty(shape, dtype=np.float64)
+        L.orc_td_lambda_f64(_ptr(nv_), _ptr(r_), _ptr(d_), _ptr(t_), g32, l32, rows, T, F, _ptr(out))
+    else:
+        out = np.empty(shape, dtype=np.float32)
+        L.orc_td_lambda_f32(_ptr(nv_), _ptr(r_), _ptr(d_), _ptr(t_), g32, l32, rows, T, F, _ptr(out))
+    return torch.from_numpy(out)

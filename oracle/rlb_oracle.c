@@ -246,6 +246,55 @@ void orc_gae_f64(const float *v, const float *nv, const float *r, const uint8_t 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * TD(lambda) return  (objectives/value/functional.py:790-899, rolling branch, scalar gamma / lmbda;
+ * lmbda = 1 is TD(1), functional.py:464-570 / 648-707):
+ *   nv_t = v'_t * not_terminated_t                                                  :850-853
+ *   g = nv_{T-1}; for t = T-1 .. 0:  g = g*(1-done_t) + nv_t*done_t                 :888-894
+ *                                    g = ret_t = r_t + gamma*((1-lmbda)*nv_t + lmbda*g)   :895-897
+ * ---------------------------------------------------------------------------------------- */
+void orc_td_lambda_f32(const float *nv, const float *r, const uint8_t *done, const uint8_t *term, float gamma,
+                       float lmbda, int64_t rows, int64_t T, int64_t F, float *ret) {
+  const float oml = 1.0f - lmbda;
+  for (int64_t b = 0; b < rows; ++b) {
+    for (int64_t f = 0; f < F; ++f) {
+      const int64_t last = (b * T + (T - 1)) * F + f;
+      float g = nv[last] * (float)(term[last] ? 0 : 1);
+      for (int64_t t = T - 1; t >= 0; --t) {
+        const int64_t i = (b * T + t) * F + f;
+        const float nvt = nv[i] * (float)(term[i] ? 0 : 1);
+        const float dn = (float)(done[i] ? 1 : 0);
+        const float g1 = g * (1.0f - dn);
+        const float g2 = nvt * dn;
+        g = g1 + g2;
+        const float a = oml * nvt;
+        const float bb = lmbda * g;
+        const float s = a + bb;
+        const float gs = gamma * s;
+        g = r[i] + gs;
+        ret[i] = g;
+      }
+    }
+  }
+}
+
+void orc_td_lambda_f64(const float *nv, const float *r, const uint8_t *done, const uint8_t *term, double gamma,
+                       double lmbda, int64_t rows, int64_t T, int64_t F, double *ret) {
+  for (int64_t b = 0; b < rows; ++b) {
+    for (int64_t f = 0; f < F; ++f) {
+      const int64_t last = (b * T + (T - 1)) * F + f;
+      double g = term[last] ? 0.0 : (double)nv[last];
+      for (int64_t t = T - 1; t >= 0; --t) {
+        const int64_t i = (b * T + t) * F + f;
+        const double nvt = term[i] ? 0.0 : (double)nv[i];
+        if (done[i]) g = nvt;
+        g = (double)r[i] + gamma * ((1.0 - lmbda) * nvt + lmbda * g);
+        ret[i] = g;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Storage gather  (data/replay_buffers/storages.py:1242-1263): storage[:len][index] per leaf,
  * i.e. a row copy out[b,:] = src[index[b],:].  The arithmetic lives in torch (aten::index); this
  * byte-level restatement exists so the C-ABI gather can be checked without torch semantics in

@@ -19,6 +19,11 @@
 // with the carry A_{tile end} held in a register.
 // F > 1 layout [rows, T, F]: one thread per (row, feature) column, serial in time, coalesced across
 // features.
+//
+// The same scan serves the sibling estimators: MODE 1 = TD(lambda) / TD(1) returns
+// (functional.py:843-899, scalar gamma / lmbda):  G_t = r_t + gamma*((1-lmbda)*nv_t + lmbda*G'_{t+1}),
+// nv_t = (1-term_t)*v'_t, G' = nv_t where done_t (or at the last step) -- i.e. the affine map
+//     d_t = r_t + gamma*nv_t*(done_t ? 1 : 1-lmbda),   c_t = done_t ? 0 : gamma*lmbda.
 #include "common.cuh"
 
 namespace rlb {
@@ -53,10 +58,26 @@ constexpr int kGaeWarpsPerCta = 8;
 constexpr int kGaeTile = 128;  // time steps per warp iteration (32 lanes x 4)
 
 // VEC: rows are 16-B aligned for T (and 4-B aligned for the flag bytes) and T % 4 == 0.
-template <typename T, bool VEC>
+// MODE 0: GAE (outputs advantage and value_target; needs v).  MODE 1: TD(lambda) return (output `adv` only; `v`
+// and `tgt` are unused, `oml` = 1 - lmbda).
+template <typename T, int MODE>
+__device__ __forceinline__ void scan_coeffs(T vv, T nvv, T rr, bool dn, bool tm, bool last, T gamma, T gl, T oml,
+                                            T &d, T &c) {
+  if constexpr (MODE == 0) {
+    d = (rr + (tm ? (T)0 : gamma) * nvv) - vv;
+    c = dn ? (T)0 : gl;
+  } else {
+    const bool cut = dn || last;
+    const T nvt = tm ? (T)0 : nvv;
+    d = rr + (nvt * gamma) * (cut ? (T)1 : oml);
+    c = cut ? (T)0 : gl;
+  }
+}
+
+template <typename T, bool VEC, int MODE>
 __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
     const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r, const uint8_t *__restrict__ done,
-    const uint8_t *__restrict__ term, T gamma, T gl, int64_t rows, int64_t Tlen, T *__restrict__ adv,
+    const uint8_t *__restrict__ term, T gamma, T gl, T oml, int64_t rows, int64_t Tlen, T *__restrict__ adv,
     T *__restrict__ tgt) {
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)kGaeWarpsPerCta + (threadIdx.x >> 5);
@@ -68,7 +89,8 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
     const int64_t t0 = tile * kGaeTile + 4 * lane;  // first of this lane's four steps
     T d[4], c[4], sv[4];
     if (VEC && t0 + 4 <= Tlen) {
-      const Vec4<T> qv = load4<T>(v + base + t0);
+      Vec4<T> qv = {{(T)0, (T)0, (T)0, (T)0}};
+      if constexpr (MODE == 0) qv = load4<T>(v + base + t0);
       const Vec4<T> qn = load4<T>(nv + base + t0);
       const Vec4<T> qr = load4<T>(r + base + t0);
       const uchar4 qd = __ldg(reinterpret_cast<const uchar4 *>(done + base + t0));
@@ -78,18 +100,18 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         sv[j] = qv.v[j];
-        d[j] = (qr.v[j] + (tt[j] ? (T)0 : gamma) * qn.v[j]) - qv.v[j];
-        c[j] = dd[j] ? (T)0 : gl;
+        scan_coeffs<T, MODE>(qv.v[j], qn.v[j], qr.v[j], dd[j] != 0, tt[j] != 0, t0 + j == Tlen - 1, gamma, gl, oml,
+                             d[j], c[j]);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int64_t t = t0 + j;
         if (t < Tlen) {
-          const T vv = __ldg(v + base + t);
+          const T vv = (MODE == 0) ? __ldg(v + base + t) : (T)0;
           sv[j] = vv;
-          d[j] = (__ldg(r + base + t) + (__ldg(term + base + t) ? (T)0 : gamma) * __ldg(nv + base + t)) - vv;
-          c[j] = __ldg(done + base + t) ? (T)0 : gl;
+          scan_coeffs<T, MODE>(vv, __ldg(nv + base + t), __ldg(r + base + t), __ldg(done + base + t) != 0,
+                               __ldg(term + base + t) != 0, t == Tlen - 1, gamma, gl, oml, d[j], c[j]);
         } else {  // beyond the row: A = 0 there, contributes nothing
           sv[j] = (T)0;
           d[j] = (T)0;
@@ -129,13 +151,13 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
     carry = __shfl_sync(0xffffffffu, oa.v[0], 0);
     if (VEC && t0 + 4 <= Tlen) {
       store4(adv + base + t0, oa);
-      store4(tgt + base + t0, ot);
+      if constexpr (MODE == 0) store4(tgt + base + t0, ot);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (t0 + j < Tlen) {
           adv[base + t0 + j] = oa.v[j];
-          tgt[base + t0 + j] = ot.v[j];
+          if constexpr (MODE == 0) tgt[base + t0 + j] = ot.v[j];
         }
       }
     }
@@ -143,10 +165,10 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
 }
 
 // [rows, T, F] with F > 1: thread per (row, f) column; consecutive threads -> consecutive f (coalesced).
-template <typename T>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(256) gae_cols_kernel(const T *__restrict__ v, const T *__restrict__ nv,
                                                        const T *__restrict__ r, const uint8_t *__restrict__ done,
-                                                       const uint8_t *__restrict__ term, T gamma, T gl,
+                                                       const uint8_t *__restrict__ term, T gamma, T gl, T oml,
                                                        int64_t rows, int64_t Tlen, int64_t F, T *__restrict__ adv,
                                                        T *__restrict__ tgt) {
   const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -157,40 +179,41 @@ __global__ void __launch_bounds__(256) gae_cols_kernel(const T *__restrict__ v, 
 #pragma unroll 4
   for (int64_t t = Tlen - 1; t >= 0; --t) {
     const int64_t i = base + t * F;
-    const T vv = __ldg(v + i);
-    const T dlt = (__ldg(r + i) + (__ldg(term + i) ? (T)0 : gamma) * __ldg(nv + i)) - vv;
-    a = dlt + (__ldg(done + i) ? (T)0 : gl) * a;
+    const T vv = (MODE == 0) ? __ldg(v + i) : (T)0;
+    T dlt, cc;
+    scan_coeffs<T, MODE>(vv, __ldg(nv + i), __ldg(r + i), __ldg(done + i) != 0, __ldg(term + i) != 0, t == Tlen - 1,
+                         gamma, gl, oml, dlt, cc);
+    a = dlt + cc * a;
     adv[i] = a;
-    tgt[i] = a + vv;
+    if constexpr (MODE == 0) tgt[i] = a + vv;
   }
 }
 
-template <typename T>
+template <typename T, int MODE>
 static int gae_impl(const void *v, const void *nv, const void *r, const uint8_t *done, const uint8_t *term,
-                    double gamma, double gl, int64_t rows, int64_t Tlen, int64_t F, void *adv, void *tgt,
+                    double gamma, double gl, double oml, int64_t rows, int64_t Tlen, int64_t F, void *adv, void *tgt,
                     cudaStream_t st) {
   const T *pv = static_cast<const T *>(v), *pn = static_cast<const T *>(nv), *pr = static_cast<const T *>(r);
   T *pa = static_cast<T *>(adv), *pt = static_cast<T *>(tgt);
   if (F == 1) {
     const int64_t blocks = (rows + kGaeWarpsPerCta - 1) / kGaeWarpsPerCta;
     RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many rows for one launch");
-    auto al = [](const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+    auto al = [](const void *p, uintptr_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
     const bool vec = (Tlen % 4 == 0) && al(v, 16) && al(nv, 16) && al(r, 16) && al(adv, 16) && al(tgt, 16) &&
                      al(done, 4) && al(term, 4);
     if (vec)
-      gae_rows_kernel<T, true><<<(unsigned)blocks, kGaeWarpsPerCta * 32, 0, st>>>(pv, pn, pr, done, term, (T)gamma,
-                                                                                  (T)gl, rows, Tlen, pa, pt);
+      gae_rows_kernel<T, true, MODE><<<(unsigned)blocks, kGaeWarpsPerCta * 32, 0, st>>>(
+          pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt);
     else
-      gae_rows_kernel<T, false><<<(unsigned)blocks, kGaeWarpsPerCta * 32, 0, st>>>(pv, pn, pr, done, term,
-                                                                                   (T)gamma, (T)gl, rows, Tlen, pa,
-                                                                                   pt);
+      gae_rows_kernel<T, false, MODE><<<(unsigned)blocks, kGaeWarpsPerCta * 32, 0, st>>>(
+          pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt);
     return check_launch("gae_rows_kernel");
   }
   const int64_t cols = rows * F;
   const int64_t blocks = (cols + 255) / 256;
   RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many columns for one launch");
-  gae_cols_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(pv, pn, pr, done, term, (T)gamma, (T)gl, rows, Tlen, F, pa,
-                                                       pt);
+  gae_cols_kernel<T, MODE><<<(unsigned)blocks, 256, 0, st>>>(pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows,
+                                                             Tlen, F, pa, pt);
   return check_launch("gae_cols_kernel");
 }
 
@@ -208,10 +231,28 @@ extern "C" int rlb_gae(const void *state_value, const void *next_state_value, co
   RLB_REQUIRE(state_value && next_state_value && reward && done && terminated && advantage && value_target,
               RLB_EINVAL, "rlb_gae: null pointer");
   if (dtype == RLB_F32)
-    return gae_impl<float>(state_value, next_state_value, reward, done, terminated, gamma, gammalmbda, rows, T, F,
-                           advantage, value_target, as_stream(stream));
+    return gae_impl<float, 0>(state_value, next_state_value, reward, done, terminated, gamma, gammalmbda, 0.0, rows, T,
+                              F, advantage, value_target, as_stream(stream));
   if (dtype == RLB_F64)
-    return gae_impl<double>(state_value, next_state_value, reward, done, terminated, gamma, gammalmbda, rows, T, F,
-                            advantage, value_target, as_stream(stream));
+    return gae_impl<double, 0>(state_value, next_state_value, reward, done, terminated, gamma, gammalmbda, 0.0, rows,
+                               T, F, advantage, value_target, as_stream(stream));
   RLB_REQUIRE(false, RLB_EINVAL, "rlb_gae: unsupported dtype %d", dtype);
+}
+
+extern "C" int rlb_td_lambda_return(const void *next_state_value, const void *reward, const uint8_t *done,
+                                    const uint8_t *terminated, double gamma, double gammalmbda,
+                                    double one_minus_lmbda, int64_t rows, int64_t T, int64_t F, int dtype,
+                                    void *returns, rlb_stream_t stream) {
+  RLB_REQUIRE(rows >= 0 && T >= 0 && F >= 1, RLB_EINVAL, "rlb_td_lambda_return: bad shape rows=%lld T=%lld F=%lld",
+              (long long)rows, (long long)T, (long long)F);
+  if (rows == 0 || T == 0) return RLB_OK;
+  RLB_REQUIRE(next_state_value && reward && done && terminated && returns, RLB_EINVAL,
+              "rlb_td_lambda_return: null pointer");
+  if (dtype == RLB_F32)
+    return gae_impl<float, 1>(nullptr, next_state_value, reward, done, terminated, gamma, gammalmbda, one_minus_lmbda,
+                              rows, T, F, returns, nullptr, as_stream(stream));
+  if (dtype == RLB_F64)
+    return gae_impl<double, 1>(nullptr, next_state_value, reward, done, terminated, gamma, gammalmbda,
+                               one_minus_lmbda, rows, T, F, returns, nullptr, as_stream(stream));
+  RLB_REQUIRE(false, RLB_EINVAL, "rlb_td_lambda_return: unsupported dtype %d", dtype);
 }

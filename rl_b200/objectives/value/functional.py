@@ -2,6 +2,9 @@
 
     generalized_advantage_estimate       functional.py:119-180   (python time loop in the reference)
     vec_generalized_advantage_estimate   functional.py:270-370   (pad + conv1d in the reference)
+    td_lambda_return_estimate / vec_...  functional.py:790-899, 1056-1210   (+ the *_advantage_estimate forms)
+    td1_return_estimate / vec_...        functional.py:464-570, 648-707     (TD(lambda) with lmbda = 1)
+    td0_return_estimate / advantage      functional.py:378-457              (elementwise, no scan)
 
 Both names resolve to the same single kernel launch (``rlb_gae``, csrc/gae.cu): a warp-level discounted
 reverse scan that reads every input element once and writes every output element once, with no host
@@ -18,7 +21,13 @@ from ... import ops
 
 SHAPE_ERR = "All input tensors (value, reward and done states) must share a unique shape."
 
-__all__ = ["generalized_advantage_estimate", "vec_generalized_advantage_estimate", "gae_scalars"]
+__all__ = [
+    "generalized_advantage_estimate", "vec_generalized_advantage_estimate", "gae_scalars",
+    "td0_return_estimate", "td0_advantage_estimate",
+    "td1_return_estimate", "vec_td1_return_estimate", "td1_advantage_estimate", "vec_td1_advantage_estimate",
+    "td_lambda_return_estimate", "vec_td_lambda_return_estimate", "td_lambda_advantage_estimate",
+    "vec_td_lambda_advantage_estimate",
+]
 
 
 def gae_scalars(gamma, lmbda, dtype: torch.dtype) -> tuple[float, float]:
@@ -122,3 +131,149 @@ def generalized_advantage_estimate(gamma, lmbda, state_value: torch.Tensor, next
     """Generalized advantage estimate of a trajectory -- same kernel as the vectorized entry point (the
     reference's python time loop, functional.py:164-178, is what the kernel's recurrence restates)."""
     return _gae_impl(gamma, lmbda, state_value, next_state_value, reward, done, terminated, time_dim)
+
+
+########################################################################
+# TD(0), TD(1), TD(lambda)  -- SURVEY.md section 8(f)-2: the same reverse scan with other coefficients
+# --------------------------------------------------------------------------------------------------
+
+
+def td0_return_estimate(gamma, next_state_value: torch.Tensor, reward: torch.Tensor,
+                        terminated: torch.Tensor | None = None, *, done: torch.Tensor | None = None) -> torch.Tensor:
+    """TD(0) discounted return estimate ``r + gamma * (1 - terminated) * v'`` (functional.py:418-457).
+    Elementwise -- there is nothing to scan, so it stays one fused torch expression as in the reference."""
+    if done is not None and terminated is None:
+        terminated = done.clone()
+    if not (next_state_value.shape == reward.shape == terminated.shape):
+        raise RuntimeError(SHAPE_ERR)
+    return reward + gamma * (~terminated).int() * next_state_value
+
+
+def td0_advantage_estimate(gamma, state_value, next_state_value, reward, done, terminated=None) -> torch.Tensor:
+    """TD(0) advantage estimate (functional.py:378-415)."""
+    if terminated is None:
+        terminated = done.clone()
+    if not (next_state_value.shape == state_value.shape == reward.shape == done.shape == terminated.shape):
+        raise RuntimeError(SHAPE_ERR)
+    return td0_return_estimate(gamma, next_state_value, reward, terminated) - state_value
+
+
+def _td_lambda_scalars(gamma, lmbda, dtype):
+    """(gamma, gamma*lmbda, 1-lmbda) rounded like the tensor ops of _fast_td_lambda_return_estimate
+    (functional.py:1031-1046): every factor lives in the value dtype."""
+    for x in (gamma, lmbda):
+        if isinstance(x, torch.Tensor) and x.numel() > 1:
+            raise NotImplementedError(
+                "tensor-valued gamma / lmbda (one value per step) are not supported by the B200 scan kernel yet; "
+                "pass scalars.")
+    g = torch.as_tensor(gamma).detach().to("cpu", dtype).reshape(())
+    l = torch.as_tensor(lmbda).detach().to("cpu", dtype).reshape(())
+    return float(g), float(g * l), float(1 - l)
+
+
+def _td_lambda_impl(gamma, lmbda, next_state_value, reward, done, terminated, rolling_gamma, time_dim):
+    if terminated is None:
+        terminated = done
+    if not (next_state_value.shape == reward.shape == done.shape == terminated.shape):
+        raise RuntimeError(SHAPE_ERR)
+    if rolling_gamma is not None and not rolling_gamma:
+        raise RuntimeError("rolling_gamma=False is expected only with time-sensitive gamma or lambda values")
+    if (next_state_value.requires_grad or reward.requires_grad) and torch.is_grad_enabled():
+        raise NotImplementedError("the B200 scan kernel is forward-only: call it under torch.no_grad().")
+    dtype = next_state_value.dtype
+    if dtype not in (torch.float32, torch.float64):
+        raise NotImplementedError(f"TD(lambda) kernel supports fp32 / fp64 values, got {dtype}")
+    squeeze = False
+    tensors = [next_state_value, reward, done, terminated]
+    nd = next_state_value.ndim
+    td = time_dim - nd if time_dim >= 0 else time_dim
+    if td != -2 or nd < 2:
+        moved = [_time_to_minus2(t, time_dim) for t in tensors]
+        squeeze = any(sq for _, sq in moved)
+        tensors = [t for t, _ in moved]
+    nv, r, d, tm = tensors
+    shape = nv.shape
+    T, F = shape[-2], shape[-1]
+    rows = math.prod(shape[:-2])
+    nv = nv.detach().contiguous()
+    r = r.detach().to(dtype).contiguous()
+    d = d.to(torch.bool).contiguous().view(torch.uint8)
+    tm = tm.to(torch.bool).contiguous().view(torch.uint8)
+    g, gl, oml = _td_lambda_scalars(gamma, lmbda, dtype)
+    ret = ops.backend().td_lambda_return(nv, r, d, tm, g, gl, oml, rows, T, F).view(shape)
+    if squeeze:
+        return ret.squeeze(-1)
+    if td != -2:
+        ret = ret.transpose(td, -2)
+    return ret
+
+
+def vec_td_lambda_return_estimate(gamma, lmbda, next_state_value: torch.Tensor, reward: torch.Tensor,
+                                  done: torch.Tensor, terminated: torch.Tensor | None = None,
+                                  rolling_gamma: bool | None = None, *, time_dim: int = -2) -> torch.Tensor:
+    r"""Vectorized TD(:math:`\lambda`) return estimate (functional.py:1056-1210; scalar ``gamma`` / ``lmbda``).
+
+    Args:
+        gamma (scalar): exponential mean discount.
+        lmbda (scalar): trajectory discount.
+        next_state_value (Tensor): value function result with new_state input.
+        reward (Tensor): reward of taking actions in the environment.
+        done (Tensor): boolean flag for end of trajectory.
+        terminated (Tensor): boolean flag for the end of episode. Defaults to ``done`` if not provided.
+        rolling_gamma (bool, optional): only meaningful for tensor-valued gamma; must be ``None`` / ``True`` here.
+        time_dim (int): dimension where the time is unrolled. Defaults to -2.
+
+    All tensors (values, reward and done) must have shape ``[*Batch x TimeSteps x *F]``.
+    """
+    return _td_lambda_impl(gamma, lmbda, next_state_value, reward, done, terminated, rolling_gamma, time_dim)
+
+
+def td_lambda_return_estimate(gamma, lmbda, next_state_value, reward, done, terminated=None, rolling_gamma=None, *,
+                              time_dim: int = -2) -> torch.Tensor:
+    r"""TD(:math:`\lambda`) return estimate (functional.py:790-899) -- same kernel as the vectorized entry point."""
+    return _td_lambda_impl(gamma, lmbda, next_state_value, reward, done, terminated, rolling_gamma, time_dim)
+
+
+def _td_lambda_adv(gamma, lmbda, state_value, next_state_value, reward, done, terminated, rolling_gamma, time_dim):
+    if terminated is None:
+        terminated = done
+    if not (next_state_value.shape == state_value.shape == reward.shape == done.shape == terminated.shape):
+        raise RuntimeError(SHAPE_ERR)
+    return _td_lambda_impl(gamma, lmbda, next_state_value, reward, done, terminated, rolling_gamma,
+                           time_dim) - state_value
+
+
+def vec_td_lambda_advantage_estimate(gamma, lmbda, state_value, next_state_value, reward, done, terminated=None,
+                                     rolling_gamma=None, time_dim: int = -2) -> torch.Tensor:
+    r"""Vectorized TD(:math:`\lambda`) advantage estimate: returns - state_value (functional.py:1213-1294)."""
+    return _td_lambda_adv(gamma, lmbda, state_value, next_state_value, reward, done, terminated, rolling_gamma, time_dim)
+
+
+def td_lambda_advantage_estimate(gamma, lmbda, state_value, next_state_value, reward, done, terminated=None,
+                                 rolling_gamma=None, time_dim: int = -2) -> torch.Tensor:
+    r"""TD(:math:`\lambda`) advantage estimate (functional.py:913-990)."""
+    return _td_lambda_adv(gamma, lmbda, state_value, next_state_value, reward, done, terminated, rolling_gamma, time_dim)
+
+
+def vec_td1_return_estimate(gamma, next_state_value, reward, done, terminated=None, rolling_gamma=None,
+                            time_dim: int = -2) -> torch.Tensor:
+    """Vectorized TD(1) return estimate = TD(lambda) with lmbda = 1 (functional.py:648-707)."""
+    return _td_lambda_impl(gamma, 1, next_state_value, reward, done, terminated, rolling_gamma, time_dim)
+
+
+def td1_return_estimate(gamma, next_state_value, reward, done, terminated=None, rolling_gamma=None,
+                        time_dim: int = -2) -> torch.Tensor:
+    """TD(1) return estimate (functional.py:464-570) -- same kernel as the vectorized entry point."""
+    return _td_lambda_impl(gamma, 1, next_state_value, reward, done, terminated, rolling_gamma, time_dim)
+
+
+def vec_td1_advantage_estimate(gamma, state_value, next_state_value, reward, done, terminated=None, rolling_gamma=None,
+                               time_dim: int = -2) -> torch.Tensor:
+    """Vectorized TD(1) advantage estimate (functional.py:710-787)."""
+    return _td_lambda_adv(gamma, 1, state_value, next_state_value, reward, done, terminated, rolling_gamma, time_dim)
+
+
+def td1_advantage_estimate(gamma, state_value, next_state_value, reward, done, terminated=None, rolling_gamma=None,
+                           time_dim: int = -2) -> torch.Tensor:
+    """TD(1) advantage estimate (functional.py:572-645)."""
+    return _td_lambda_adv(gamma, 1, state_value, next_state_value, reward, done, terminated, rolling_gamma, time_dim)

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "rlb_td_lambda_return": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp]),
 }
 
 
@@ -343,6 +344,17 @@ class CudaBackend:
                                        float(gamma), float(gammalmbda), rows, T, F, _dtype_code(v.dtype),
                                        adv.data_ptr(), tgt.data_ptr(), self._stream(dev)), "rlb_gae")
         return adv, tgt
+
+    def td_lambda_return(self, nv, r, done, term, gamma: float, gammalmbda: float, one_minus_lmbda: float, rows: int,
+                         T: int, F: int):
+        dev = self._cuda(nv, r, done, term)
+        ret = torch.empty_like(nv)
+        with self._Guard(dev):
+            self._check(self.L.rlb_td_lambda_return(nv.data_ptr(), r.data_ptr(), done.data_ptr(), term.data_ptr(),
+                                                    float(gamma), float(gammalmbda), float(one_minus_lmbda), rows, T, F,
+                                                    _dtype_code(nv.dtype), ret.data_ptr(), self._stream(dev)),
+                        "rlb_td_lambda_return")
+        return ret
 
 
 class GatherPlan:

@@ -218,6 +218,11 @@ class OracleBackend:
         return torch.from_numpy(adv).reshape(shape), torch.from_numpy(tgt).reshape(shape)
 
 
+    def td_lambda_return(self, nv, r, done, term, gamma, gammalmbda, one_minus_lmbda, rows, T, F):
+        lmbda = 1.0 - one_minus_lmbda
+        return po.td_lambda(gamma, lmbda, nv, r, done.bool(), term.bool(), f64=(nv.dtype == torch.float64)).to(nv.dtype)
+
+
 def _capacity(size: int) -> int:
     c = 1
     while c <= size:

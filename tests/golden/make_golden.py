@@ -49,6 +49,24 @@ def gae_cases():
     np.savez_compressed(OUT / "gae_golden.npz", **out)
 
 
+def td_cases():
+    F = reference_functionals()
+    out = {}
+    cases = {"lam95": ((16, 128, 1), 0.99, 0.95, 0.05), "td1": ((8, 64, 1), 0.97, 1.0, 0.1),
+             "odd": ((5, 37, 1), 0.9, 0.5, 0.2), "multi_f": ((4, 25, 3), 0.99, 0.9, 0.1)}
+    for i, (name, (shape, gamma, lmbda, p)) in enumerate(cases.items()):
+        g = torch.Generator().manual_seed(300 + i)
+        nv, r = (torch.randn(*shape, generator=g) for _ in range(2))
+        term = torch.rand(*shape, generator=g) < p
+        done = term | (torch.rand(*shape, generator=g) < p)
+        loop = F.td_lambda_return_estimate(gamma, lmbda, nv, r, done=done, terminated=term)
+        vec = F.vec_td_lambda_return_estimate(gamma, lmbda, nv, r, done=done, terminated=term)
+        for k, t in dict(gamma=torch.tensor(gamma), lmbda=torch.tensor(lmbda), nv=nv, r=r, done=done, term=term,
+                         loop=loop, vec=vec).items():
+            out[f"{name}/{k}"] = t.numpy()
+    np.savez_compressed(OUT / "td_lambda_golden.npz", **out)
+
+
 def per_cases():
     assert reference_ext("cpu") is not None
     out = {}
@@ -80,6 +98,7 @@ def per_cases():
 
 if __name__ == "__main__":
     gae_cases()
+    td_cases()
     per_cases()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

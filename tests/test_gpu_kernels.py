@@ -450,3 +450,34 @@ def test_update_priority_chunked_under_capture(cuda_backend):
         s_.synchronize()
     assert torch.equal(a._sum_tree.values[1:], b._sum_tree.values[1:])
     assert torch.equal(a._min_tree.values[1:], b._min_tree.values[1:])
+
+
+# ---------------------------------------------------------------------------------------------------- TD(lambda)
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 200, 1), (9, 131, 1), (4096, 128, 1), (5, 33, 3), (2, 1000, 1)])
+@pytest.mark.parametrize("gamma,lmbda", [(0.99, 0.95), (0.97, 1.0), (0.9, 0.0)])
+def test_td_lambda_matches_f64_oracle(cuda_backend, shape, gamma, lmbda):
+    from rl_b200.objectives.value import td1_return_estimate, vec_td_lambda_advantage_estimate, vec_td_lambda_return_estimate
+
+    v, nv, r, done, term = _gae_inputs(shape, sum(shape) + 1)
+    f64 = po.td_lambda(gamma, lmbda, nv, r, done, term, f64=True)
+    loop = po.td_lambda(gamma, lmbda, nv, r, done, term)           # bit-equal to the reference loop
+    cu = [x.to(dev()) for x in (v, nv, r, done, term)]
+    got = vec_td_lambda_return_estimate(gamma, lmbda, cu[1], cu[2], cu[3], cu[4])
+    torch.testing.assert_close(got.cpu().double(), f64, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(got.cpu(), loop, rtol=1e-5, atol=1e-5)
+    adv = vec_td_lambda_advantage_estimate(gamma, lmbda, cu[0], cu[1], cu[2], cu[3], cu[4])
+    assert torch.equal(adv, got - cu[0])
+    if lmbda == 1.0:
+        assert torch.equal(td1_return_estimate(gamma, cu[1], cu[2], cu[3], cu[4]), got)
+
+
+def test_td_lambda_golden(cuda_backend):
+    from rl_b200.objectives.value import vec_td_lambda_return_estimate
+
+    z = np.load(GOLD / "td_lambda_golden.npz")
+    for k in sorted({n.split("/")[0] for n in z.files}):
+        gt = lambda n: torch.from_numpy(z[f"{k}/{n}"])
+        got = vec_td_lambda_return_estimate(float(gt("gamma")), float(gt("lmbda")), gt("nv").to(dev()), gt("r").to(dev()),
+                                            gt("done").to(dev()), gt("term").to(dev()))
+        torch.testing.assert_close(got.cpu(), gt("loop"), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(got.cpu(), gt("vec"), rtol=1e-4, atol=1e-4)   # the reference's own bar

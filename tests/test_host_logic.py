@@ -356,3 +356,35 @@ def test_gae_functional_errors_and_time_dim(emul, ref_funcs):
     assert gl == float(torch.tensor(0.99) * torch.tensor(0.95))
     gm2, gl2 = gae_scalars(0.99, 0.95, torch.float32)
     assert gl2 == float(torch.tensor(0.99 * 0.95, dtype=torch.float32))
+
+
+def test_td_estimators_plumbing(emul, ref_funcs):
+    """TD(0)/TD(1)/TD(lambda) functionals: signatures, shape errors, time_dim, advantage = return - value."""
+    from rl_b200.objectives.value import (td0_advantage_estimate, td0_return_estimate, td1_return_estimate,
+                                          td_lambda_advantage_estimate, vec_td1_advantage_estimate,
+                                          vec_td_lambda_return_estimate)
+
+    g = torch.Generator().manual_seed(0)
+    v, nv, r = (torch.randn(4, 12, 1, generator=g) for _ in range(3))
+    term = torch.rand(4, 12, 1, generator=g) < 0.1
+    done = term | (torch.rand(4, 12, 1, generator=g) < 0.1)
+    ref = ref_funcs.td_lambda_return_estimate(0.99, 0.9, nv, r, done=done, terminated=term)
+    got = vec_td_lambda_return_estimate(0.99, 0.9, nv, r, done, term)
+    assert torch.equal(got, ref)      # the emulator runs the C restatement, bit-equal to the reference loop
+    adv = td_lambda_advantage_estimate(0.99, 0.9, v, nv, r, done, term)
+    assert torch.equal(adv, ref - v)
+    ref1 = ref_funcs.td1_return_estimate(0.99, nv, r, done=done, terminated=term)
+    torch.testing.assert_close(td1_return_estimate(0.99, nv, r, done, term), ref1, rtol=1e-5, atol=1e-5)
+    assert torch.equal(vec_td1_advantage_estimate(0.99, v, nv, r, done, term), td1_return_estimate(0.99, nv, r, done, term) - v)
+    assert torch.equal(td0_return_estimate(0.99, nv, r, term), ref_funcs.td0_return_estimate(0.99, nv, r, term))
+    assert torch.equal(td0_advantage_estimate(0.99, v, nv, r, done, term),
+                       ref_funcs.td0_advantage_estimate(0.99, v, nv, r, done, term))
+    got_t = vec_td_lambda_return_estimate(0.99, 0.9, nv.squeeze(-1), r.squeeze(-1), done.squeeze(-1), term.squeeze(-1),
+                                          time_dim=-1)
+    assert torch.equal(got_t, ref.squeeze(-1))
+    with pytest.raises(RuntimeError, match="must share a unique shape"):
+        vec_td_lambda_return_estimate(0.99, 0.9, nv, r[:, :5], done, term)
+    with pytest.raises(NotImplementedError, match="tensor-valued"):
+        vec_td_lambda_return_estimate(torch.full((4, 12, 1), 0.9), 0.9, nv, r, done, term)
+    with pytest.raises(RuntimeError, match="rolling_gamma=False"):
+        vec_td_lambda_return_estimate(0.99, 0.9, nv, r, done, term, rolling_gamma=False)

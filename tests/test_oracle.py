@@ -175,3 +175,30 @@ def test_gather_oracle_is_torch_indexing():
     assert np.array_equal(out, torch.from_numpy(src)[:60][torch.from_numpy(idx)].numpy())
     with pytest.raises(IndexError):
         po.gather_rows(src, np.array([60]), 60)
+
+
+# --------------------------------------------------------------------------- TD(lambda) / TD(1)
+@pytest.mark.parametrize("shape", [(1, 5, 1), (3, 100, 1), (4, 17, 5), (2, 3, 7, 1)])
+@pytest.mark.parametrize("gamma,lmbda", [(0.99, 0.95), (0.9, 1.0), (0.5, 0.0)])
+def test_td_lambda_c_oracle_is_reference_loop(ref_funcs, shape, gamma, lmbda):
+    v, nv, r, done, term = _gae_inputs(shape, 3)
+    ref = ref_funcs.td_lambda_return_estimate(gamma, lmbda, nv, r, done=done, terminated=term)
+    got = po.td_lambda(gamma, lmbda, nv, r, done, term)
+    assert torch.equal(got, ref)                                   # bit-exact: same op order, no FMA
+    f64 = po.td_lambda(gamma, lmbda, nv, r, done, term, f64=True)
+    torch.testing.assert_close(ref.double(), f64, rtol=1e-5, atol=1e-5)
+    if lmbda == 1.0:                                                # TD(1) loop (functional.py:464-570) agrees
+        td1 = ref_funcs.td1_return_estimate(gamma, nv, r, done=done, terminated=term)
+        torch.testing.assert_close(td1.double(), f64, rtol=1e-5, atol=1e-5)
+
+
+def test_td_lambda_golden_fixture():
+    from pathlib import Path
+
+    z = np.load(Path(__file__).parent / "golden" / "td_lambda_golden.npz")
+    for k in sorted({n.split("/")[0] for n in z.files}):
+        gt = lambda n: torch.from_numpy(z[f"{k}/{n}"])
+        got = po.td_lambda(gt("gamma"), gt("lmbda"), gt("nv"), gt("r"), gt("done"), gt("term"))
+        assert torch.equal(got, gt("loop")), k
+        f64 = po.td_lambda(gt("gamma"), gt("lmbda"), gt("nv"), gt("r"), gt("done"), gt("term"), f64=True)
+        torch.testing.assert_close(gt("vec").double(), f64, rtol=1e-4, atol=1e-4)
