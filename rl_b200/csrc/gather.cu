@@ -394,7 +394,10 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
   }
   P.bulk_ctas = bulk_ctas;
   const size_t smem = bulk_ctas > 0 ? kBulkSmemBytes : 0;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // function attributes are per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool &attr_set = attr_set_dev[cur_dev & 63];
   if (smem && !attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(gather_kernel<SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kBulkSmemBytes),

@@ -890,7 +890,10 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   int np = 32;
   while (np < n) np <<= 1;
   const size_t smem = upd_smem_bytes<T>(np, depth);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // function attributes are per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool &attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T, FUSED>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmemLimit),

@@ -331,9 +331,11 @@ class CudaBackend:
     def scatter(self, leaves: Sequence[torch.Tensor], data: Sequence[torch.Tensor], index: torch.Tensor, length: int,
                 status: torch.Tensor | None = None) -> None:
         if index.numel():
-            for t in leaves:
+            pairs = [(t, d.contiguous()) for t, d in zip(leaves, data) if t.numel() > 0 and d.numel() > 0]
+            for t, _ in pairs:
                 self._check_rows(t)
-            self._rows("rlb_scatter", leaves, [d.contiguous() for d in data], index, length, status)
+            if pairs:
+                self._rows("rlb_scatter", [t for t, _ in pairs], [d for _, d in pairs], index, length, status)
 
     # -- GAE ---------------------------------------------------------------------------------------
     def gae(self, v, nv, r, done, term, gamma: float, gammalmbda: float, rows: int, T: int, F: int):
@@ -369,12 +371,15 @@ class GatherPlan:
         self.tails = [tuple(t.shape[1:]) for t in self.leaves]
         self.dtypes = [t.dtype for t in self.leaves]
         self.chunks = []
-        for lo in range(0, len(self.leaves), MAX_LEAVES):
-            ts = self.leaves[lo:lo + MAX_LEAVES]
+        # leaves whose rows hold no bytes (a zero-sized feature dim) have nothing to move and no device pointer
+        live = [k for k, t in enumerate(self.leaves) if t.numel() > 0]
+        for lo in range(0, len(live), MAX_LEAVES):
+            ks = live[lo:lo + MAX_LEAVES]
+            ts = [self.leaves[k] for k in ks]
             n = len(ts)
             P, I = ctypes.c_void_p * n, ctypes.c_int64 * n
             rowb = [t.element_size() * (t[0].numel() if t.ndim > 1 else 1) for t in ts]
-            self.chunks.append((lo, n, P, P(*[t.data_ptr() for t in ts]), I(*rowb),
+            self.chunks.append((ks, n, P, P(*[t.data_ptr() for t in ts]), I(*rowb),
                                 I(*[t.stride(0) * t.element_size() for t in ts]), I))
 
     def run(self, index: torch.Tensor, length: int, mode: int = GATHER_AUTO, status: torch.Tensor | None = None,
@@ -400,10 +405,12 @@ class GatherPlan:
                     raise RuntimeError("gather: `out` leaf has the wrong shape, dtype or device")
         if B == 0:
             return list(out)
+        if length <= 0:
+            raise RuntimeError("rl_b200: cannot index an empty storage (len == 0)")
         stream = be._stream(dev)
         with be._Guard(dev):
-            for lo, n, P, srcp, rowb, sstride, I in self.chunks:
-                outs = out[lo:lo + n]
+            for ks, n, P, srcp, rowb, sstride, I in self.chunks:
+                outs = [out[k] for k in ks]
                 dstp = P(*[o.data_ptr() for o in outs])
                 dstride = None
                 if strided:

@@ -481,3 +481,37 @@ def test_td_lambda_golden(cuda_backend):
                                             gt("done").to(dev()), gt("term").to(dev()))
         torch.testing.assert_close(got.cpu(), gt("loop"), rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(got.cpu(), gt("vec"), rtol=1e-4, atol=1e-4)   # the reference's own bar
+
+
+# ---------------------------------------------------------------------------------------------------- edge cases
+def test_empty_and_degenerate_inputs(cuda_backend):
+    """Empty batches / rows / time axes are no-ops that return correctly shaped empties; arguments are validated."""
+    from rl_b200.data import PrioritizedSampler
+    from rl_b200.data.segment_tree import SumSegmentTreeFp32
+    from rl_b200.objectives.value import vec_generalized_advantage_estimate, vec_td_lambda_return_estimate
+
+    src = [torch.randn(10, 3, device=dev()), torch.zeros(10, 0, device=dev())]          # a zero-width leaf too
+    out = cuda_backend.gather(src, torch.empty(0, dtype=torch.long, device=dev()), 10)
+    assert out[0].shape == (0, 3) and out[1].shape == (0, 0)
+    out = cuda_backend.gather(src, torch.tensor([9, 0], device=dev()), 10)
+    assert torch.equal(out[0], src[0][[9, 0]]) and out[1].shape == (2, 0)
+    with pytest.raises(RuntimeError, match="empty storage"):
+        cuda_backend.gather(src, torch.tensor([0], device=dev()), 0)
+    t = SumSegmentTreeFp32(8, dev())
+    t[torch.empty(0, dtype=torch.long, device=dev())] = torch.empty(0, device=dev())    # n == 0
+    assert t.query(0, 8) == 0.0
+    assert t.scan_lower_bound(torch.empty(0, device=dev())).shape == (0,)
+    smp = PrioritizedSampler(8, 0.6, 0.4, device=dev())
+    smp.update_priority(torch.tensor([-1, -1], device=dev()), torch.tensor([3.0, 4.0], device=dev()))  # all skipped
+    assert smp._sum_tree.query(0, 8) == 0.0 and float(smp._max_priority_buf) == float("-inf")
+    e = torch.empty(0, 5, 1, device=dev())
+    a, tg = vec_generalized_advantage_estimate(0.9, 0.9, e, e, e, done=e.bool())
+    assert a.shape == (0, 5, 1) and tg.shape == (0, 5, 1)
+    e = torch.empty(3, 0, 1, device=dev())
+    assert vec_td_lambda_return_estimate(0.9, 0.9, e, e, e.bool()).shape == (3, 0, 1)
+    with pytest.raises(RuntimeError, match="expected a CUDA tensor|no CPU path"):
+        cuda_backend.gather([torch.randn(4, 2)], torch.tensor([0]), 4)
+    # single-element tree / batch, capacity rule for a power-of-two size
+    one = SumSegmentTreeFp32(1, dev())
+    one[torch.tensor([0], device=dev())] = torch.tensor([2.5], device=dev())
+    assert one.capacity == 2 and one.query(0, 1) == 2.5 and one.scan_lower_bound(1.0) == 0
