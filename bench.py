@@ -488,9 +488,10 @@ def run_ours(args) -> dict:
         result = {
             "metric": METRIC, "value": round(per_step / (ms * 1e-3), 1), "unit": "transitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8 rows / f32 priorities+GAE", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C2 PER sample+update B=256 @1M Atari transitions ({n_leaves} leaves) + C3 GAE [4096,128]",
                        "capacity_per_gpu": CAPACITY, "batch_per_gpu": BATCH, "gae_shape": [GAE_ROWS, GAE_T, 1],
+                       "arithmetic": "fp32 priorities / trees / GAE, byte-exact u8 row moves, int64 indices",
                        "alpha": ALPHA, "beta": BETA, "gamma": GAMMA, "lmbda": LMBDA,
                        "launch": ("cuda_graph replay of the public-API step" + (f" ({transport})" if world > 1 else "")) if ms_graph is not None else "eager python API",
                        "parallelism": f"capacity-sharded x{world}, {transport}" if world > 1 else "single GPU",
@@ -498,7 +499,7 @@ def run_ours(args) -> dict:
             "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5),
                     "note": f"eager python API, pinned host buffers, {n_lanes} lane(s): with several lanes D2H overlaps the next steps' H2D + compute"},
-            "gpu_launches": (5 if world == 1 else 9) * args.steps,
+            "gpu_launches": (4 if world == 1 else 6) * args.steps,  # ours per step: per_sample, gather, update, gae [+ pack, weights]
             "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
                           "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),
                           "graph_error": graph_err,
@@ -629,7 +630,7 @@ def run_reference(args) -> dict | None:
     cpu = cpu_baseline_run(steps=args.steps, warmup=args.warmup)
     return {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "transitions/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 rows / f32 priorities+GAE",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "C2 PER sample+update B=256 @1M Atari transitions (56462 B/row) + C3 GAE [4096,128]",
                        "note": "reference CPU implementation on the host cores; rank 0 only"},

@@ -2,6 +2,7 @@
 
     Sampler             abstract contract                       samplers.py:99-171
     RandomSampler       uniform with replacement                samplers.py:174-218
+    SamplerWithoutReplacement  permutation sweeps (PPO epochs)  samplers.py:221-362
     PrioritizedSampler  proportional PER, sum/min segment trees samplers.py:577-1205
 
 ``PrioritizedSampler`` keeps the reference's constructor, properties, bookkeeping quirks (double ``pow``
@@ -119,6 +120,107 @@ class RandomSampler(Sampler):
 
     def load_state_dict(self, state_dict: dict) -> None:
         return
+
+
+class SamplerWithoutReplacement(Sampler):
+    """A data-consuming sampler: consecutive batches never share an item until the storage has been swept
+    (samplers.py:221-362; PPO minibatching, sota-implementations/ppo/ppo_atari.py:83-91).
+
+    Args:
+        drop_last (bool, optional): if ``True`` an incomplete last batch is dropped (``ran_out`` turns true when the
+            remaining indices cannot fill a batch). Defaults to ``False``: the last batch of a sweep may be short.
+        shuffle (bool, optional): if ``False`` items come in storage order. Defaults to ``True``.
+
+    A fresh permutation (``torch.randperm(len, generator)`` on the storage device -- the reference's RNG call) is drawn
+    whenever the storage length changes or the previous one is exhausted.  Index generation is a handful of tiny
+    torch ops per sweep; the bytes are moved by the storage's gather kernel.
+    """
+
+    def __init__(self, drop_last: bool = False, shuffle: bool = True):
+        self._sample_list = None
+        self.len_storage = 0
+        self.drop_last = drop_last
+        self._ran_out = False
+        self.shuffle = shuffle
+        self._remaining = torch.iinfo(torch.int64).max
+
+    @property
+    def _remaining_batches(self) -> int:
+        return self._remaining
+
+    def _count_remaining(self, batch_size: int) -> None:
+        n = self._sample_list.numel()
+        self._remaining = n // batch_size if self.drop_last else -(n // -batch_size)
+
+    def _new_order(self, storage, len_storage: int, batch_size: int) -> None:
+        device = self._sample_list.device if storage is None else getattr(storage, "device", None)
+        if device == "auto":
+            device = None
+        if self.shuffle:
+            self._sample_list = torch.randperm(len_storage, device=device, generator=self._rng)
+        else:
+            self._sample_list = torch.arange(len_storage, device=device)
+        self._count_remaining(batch_size)
+
+    def sample(self, storage: Storage, batch_size: int) -> tuple[Any, dict]:
+        len_storage = len(storage)
+        if len_storage == 0:
+            raise RuntimeError(_EMPTY_STORAGE_ERROR)
+        if self.len_storage != len_storage or self._sample_list is None:
+            self._new_order(storage, len_storage, batch_size)
+        if len_storage < batch_size and self.drop_last:
+            raise ValueError(
+                f"The batch size ({batch_size}) is greater than the storage capacity ({len_storage}). "
+                "This makes it impossible to return a sample without repeating indices. "
+                "Consider changing the sampler class or turn the 'drop_last' argument to False.")
+        self.len_storage = len_storage
+        index = self._sample_list[:batch_size]
+        self._sample_list = self._sample_list[batch_size:]
+        self._count_remaining(batch_size)
+        left = self._sample_list.shape[0]
+        if left == 0 or (self.drop_last and left < batch_size):
+            self.ran_out = True  # read by ReplayBuffer.__iter__ as the end of the sweep
+            self._new_order(None, len_storage, batch_size)
+        else:
+            self.ran_out = False
+        if storage.ndim > 1:
+            index = unravel_index(index, storage.shape)
+        return index, {}
+
+    @property
+    def ran_out(self) -> bool:
+        return self._ran_out
+
+    @ran_out.setter
+    def ran_out(self, value: bool) -> None:
+        self._ran_out = value
+
+    def _empty(self) -> None:
+        self._sample_list = None
+        self.len_storage = 0
+        self._ran_out = False
+
+    def state_dict(self) -> dict:
+        return {"len_storage": self.len_storage, "_sample_list": self._sample_list, "drop_last": self.drop_last,
+                "_ran_out": self._ran_out}
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        self.len_storage = state_dict["len_storage"]
+        self._sample_list = state_dict["_sample_list"]
+        self.drop_last = state_dict["drop_last"]
+        self._ran_out = state_dict["_ran_out"]
+
+    def dumps(self, path) -> None:
+        path = Path(path)
+        path.mkdir(exist_ok=True, parents=True)
+        torch.save(self.state_dict(), path / "sampler_state.pt")
+
+    def loads(self, path) -> None:
+        self.load_state_dict(torch.load(Path(path) / "sampler_state.pt", weights_only=False))
+
+    def __repr__(self) -> str:
+        perc = len(self._sample_list) / self.len_storage * 100 if self._sample_list is not None else 0.0
+        return f"{self.__class__.__name__}({perc: 4.4f}% sampled)"
 
 
 class PrioritizedSampler(Sampler):

@@ -388,3 +388,33 @@ def test_td_estimators_plumbing(emul, ref_funcs):
         vec_td_lambda_return_estimate(torch.full((4, 12, 1), 0.9), 0.9, nv, r, done, term)
     with pytest.raises(RuntimeError, match="rolling_gamma=False"):
         vec_td_lambda_return_estimate(0.99, 0.9, nv, r, done, term, rolling_gamma=False)
+
+
+@pytest.mark.parametrize("drop_last", [True, False])
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_sampler_without_replacement(emul, drop_last, shuffle):
+    """samplers.py:221-362 / test/rb/test_samplers.py: every item once per sweep, ran_out ends __iter__,
+    a PPO-style epoch loop over GAE output runs through the same buffer."""
+    from rl_b200.data import SamplerWithoutReplacement
+
+    n, B = 23, 5
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(n, device="cpu"),
+                                sampler=SamplerWithoutReplacement(drop_last=drop_last, shuffle=shuffle), batch_size=B,
+                                generator=torch.Generator().manual_seed(0))
+    td = _gae_td(1, n)
+    GAE(gamma=0.99, lmbda=0.95, value_network=None)(td)
+    rb.extend(td.reshape(n))
+    for epoch in range(2):
+        seen = [b.get("index") for b in rb]
+        flat = torch.cat(seen)
+        if drop_last:
+            assert len(seen) == n // B and all(s.numel() == B for s in seen) and flat.unique().numel() == flat.numel()
+        else:
+            assert len(seen) == -(n // -B) and sorted(flat.tolist()) == list(range(n))
+        if not shuffle:
+            assert flat.tolist() == list(range(flat.numel()))
+    b = rb.sample()
+    assert torch.equal(b.get("advantage"), td.get("advantage").reshape(n, 1)[b.get("index")])
+    with pytest.raises(ValueError, match="greater than the storage capacity"):
+        ReplayBuffer(storage=LazyTensorStorage(3, device="cpu"), sampler=SamplerWithoutReplacement(drop_last=True),
+                     batch_size=8)._sampler.sample(type("S", (), {"__len__": lambda s: 3, "ndim": 1, "device": "cpu"})(), 8)
