@@ -230,6 +230,12 @@ int rlb_td_lambda_return(const void *next_state_value /*[dev]*/, const void *rew
                          double gammalmbda, double one_minus_lmbda, int64_t rows, int64_t T, int64_t F, int dtype,
                          void *returns /*[dev]*/, rlb_stream_t stream);
 
+/* The bare reverse scan  out_t = d_t + c_t * out_{t+1}  (out_T = 0) over contiguous [rows, T, F] coefficient
+ * tensors.  V-trace (vtrace_advantage_estimate, functional.py:1297-1382: vs_minus_v) and GAE with per-step
+ * gamma / lmbda tensors (functional.py:317-370, rolling) are this scan after an elementwise prologue. */
+int rlb_affine_scan(const void *d /*[dev]*/, const void *c /*[dev]*/, int64_t rows, int64_t T, int64_t F, int dtype,
+                    void *out /*[dev]*/, rlb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

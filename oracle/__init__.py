@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
     L.orc_gae_f64.argtypes = [vp, vp, vp, vp, vp, c_f64, c_f64, c_i64, c_i64, c_i64, vp, vp]
     L.orc_td_lambda_f32.argtypes = [vp, vp, vp, vp, c_f32, c_f32, c_i64, c_i64, c_i64, vp]
     L.orc_td_lambda_f64.argtypes = [vp, vp, vp, vp, c_f64, c_f64, c_i64, c_i64, c_i64, vp]
+    L.orc_affine_scan_f32.argtypes = [vp, vp, c_i64, c_i64, c_i64, vp]
+    L.orc_affine_scan_f64.argtypes = [vp, vp, c_i64, c_i64, c_i64, vp]
     L.orc_gather_rows.restype = c_int
     L.orc_gather_rows.argtypes = [vp, c_i64, c_i64, c_i64, vp, c_i64, vp]
     _LIB = L

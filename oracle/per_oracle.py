@@ -310,3 +310,51 @@ def td_lambda(gamma, lmbda, next_state_value, reward, done, terminated=None, f64
         out = np.empty(shape, dtype=np.float32)
         L.orc_td_lambda_f32(_ptr(nv_), _ptr(r_), _ptr(d_), _ptr(t_), g32, l32, rows, T, F, _ptr(out))
     return torch.from_numpy(out)
+
+
+def affine_scan(d: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """out_t = d_t + c_t * out_{t+1} along dim -2 of [*B, T, F] tensors, through the C oracle (dtype of ``d``)."""
+    L = lib()
+    shape = tuple(d.shape)
+    T, F = shape[-2], shape[-1]
+    rows = int(np.prod(shape[:-2], dtype=np.int64)) if len(shape) > 2 else 1
+    dt = np.float64 if d.dtype == torch.float64 else np.float32
+    d_ = np.ascontiguousarray(d.detach().cpu().numpy().astype(dt, copy=False))
+    c_ = np.ascontiguousarray(torch.broadcast_to(c, d.shape).detach().cpu().numpy().astype(dt, copy=False))
+    out = np.empty(shape, dtype=dt)
+    (L.orc_affine_scan_f64 if dt == np.float64 else L.orc_affine_scan_f32)(_ptr(d_), _ptr(c_), rows, T, F, _ptr(out))
+    return torch.from_numpy(out)
+
+
+def vtrace(gamma, log_pi, log_mu, state_value, next_state_value, reward, done, terminated=None, rho_thresh=1.0,
+           c_thresh=1.0):
+    """V-trace (vtrace_advantage_estimate, functional.py:1297-1382), time at dim -2: the reference's elementwise
+    prologue / epilogue as CPU tensor ops in its order, its python time loop (:1360-1368) through the C scan."""
+    rho_thresh = torch.as_tensor(rho_thresh)
+    c_thresh = torch.as_tensor(c_thresh)
+    not_done = (~done).int()
+    not_terminated = not_done if terminated is None else (~terminated).int()
+    done_discounts = gamma * not_done
+    terminated_discounts = gamma * not_terminated
+    rho = (log_pi - log_mu).exp()
+    clipped_rho = rho.clamp_max(rho_thresh)
+    deltas = clipped_rho * (reward + terminated_discounts * next_state_value - state_value)
+    clipped_c = rho.clamp_max(c_thresh)
+    vs_minus_v = affine_scan(deltas, done_discounts * clipped_c)
+    vs = vs_minus_v + state_value
+    vs_t_plus_1 = torch.cat([vs[..., 1:, :], next_state_value[..., -1:, :]], dim=-2)
+    advantages = clipped_rho * (reward + terminated_discounts * vs_t_plus_1 - state_value)
+    return advantages, vs
+
+
+def gae_per_step(gamma, lmbda, state_value, next_state_value, reward, done, terminated=None):
+    """GAE with tensor-valued gamma / lmbda (functional.py:317-370), time at dim -2, as the recurrence the rolled
+    cumprod tensor (value/utils.py:130-181) unrolls to:  A_t = td0_t + not_done_t*gamma_t*lmbda_t * A_{t+1}."""
+    if terminated is None:
+        terminated = done
+    dtype = state_value.dtype
+    value = gamma * lmbda
+    gammalmbdas = (~done).to(dtype) * value
+    td0 = reward + (~terminated).to(dtype) * gamma * next_state_value - state_value
+    adv = affine_scan(td0, gammalmbdas)
+    return adv, adv + state_value

@@ -294,6 +294,39 @@ void orc_td_lambda_f64(const float *nv, const float *r, const uint8_t *done, con
   }
 }
 
+/* ----------------------------------------------------------------------------------------
+ * The bare reverse scan  out_t = d_t + c_t * out_{t+1},  out_T = 0.  This is the python loop of
+ * vtrace_advantage_estimate (functional.py:1360-1368: `delta_t + discount_t * c_t * vs_minus_v[-1]`, with
+ * c = discount_t * c_t formed first, as python evaluates it) and the recurrence that the rolled gamma tensor of
+ * vec_generalized_advantage_estimate (functional.py:317-370, value/utils.py:130-181) unrolls to.
+ * Product and sum are rounded separately, as torch's elementwise ops do.
+ * ---------------------------------------------------------------------------------------- */
+void orc_affine_scan_f32(const float *d, const float *c, int64_t rows, int64_t T, int64_t F, float *out) {
+  for (int64_t b = 0; b < rows; ++b)
+    for (int64_t f = 0; f < F; ++f) {
+      float a = 0.0f;
+      for (int64_t t = T - 1; t >= 0; --t) {
+        const int64_t i = (b * T + t) * F + f;
+        const float m = c[i] * a;
+        a = d[i] + m;
+        out[i] = a;
+      }
+    }
+}
+
+void orc_affine_scan_f64(const double *d, const double *c, int64_t rows, int64_t T, int64_t F, double *out) {
+  for (int64_t b = 0; b < rows; ++b)
+    for (int64_t f = 0; f < F; ++f) {
+      double a = 0.0;
+      for (int64_t t = T - 1; t >= 0; --t) {
+        const int64_t i = (b * T + t) * F + f;
+        const double m = c[i] * a;
+        a = d[i] + m;
+        out[i] = a;
+      }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Storage gather  (data/replay_buffers/storages.py:1242-1263): storage[:len][index] per leaf,
  * i.e. a row copy out[b,:] = src[index[b],:].  The arithmetic lives in torch (aten::index); this

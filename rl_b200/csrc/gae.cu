@@ -24,6 +24,9 @@
 // (functional.py:843-899, scalar gamma / lmbda):  G_t = r_t + gamma*((1-lmbda)*nv_t + lmbda*G'_{t+1}),
 // nv_t = (1-term_t)*v'_t, G' = nv_t where done_t (or at the last step) -- i.e. the affine map
 //     d_t = r_t + gamma*nv_t*(done_t ? 1 : 1-lmbda),   c_t = done_t ? 0 : gamma*lmbda.
+// MODE 2 = the bare scan  A_t = d_t + c_t*A_{t+1}  over caller-supplied coefficient tensors: V-trace
+// (functional.py:1297-1382) and GAE with per-step gamma / lmbda tensors (functional.py:317-370) reduce to it after an
+// elementwise prologue, without the [B, T, T] gamma tensor of value/utils.py:130-181.
 #include "common.cuh"
 
 namespace rlb {
@@ -66,6 +69,9 @@ __device__ __forceinline__ void scan_coeffs(T vv, T nvv, T rr, bool dn, bool tm,
   if constexpr (MODE == 0) {
     d = (rr + (tm ? (T)0 : gamma) * nvv) - vv;
     c = dn ? (T)0 : gl;
+  } else if constexpr (MODE == 2) {
+    d = rr;   // `r` carries d_t
+    c = nvv;  // `nv` carries c_t
   } else {
     const bool cut = dn || last;
     const T nvt = tm ? (T)0 : nvv;
@@ -93,8 +99,11 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
       if constexpr (MODE == 0) qv = load4<T>(v + base + t0);
       const Vec4<T> qn = load4<T>(nv + base + t0);
       const Vec4<T> qr = load4<T>(r + base + t0);
-      const uchar4 qd = __ldg(reinterpret_cast<const uchar4 *>(done + base + t0));
-      const uchar4 qt = __ldg(reinterpret_cast<const uchar4 *>(term + base + t0));
+      uchar4 qd = make_uchar4(0, 0, 0, 0), qt = make_uchar4(0, 0, 0, 0);
+      if constexpr (MODE != 2) {
+        qd = __ldg(reinterpret_cast<const uchar4 *>(done + base + t0));
+        qt = __ldg(reinterpret_cast<const uchar4 *>(term + base + t0));
+      }
       const uint8_t dd[4] = {qd.x, qd.y, qd.z, qd.w};
       const uint8_t tt[4] = {qt.x, qt.y, qt.z, qt.w};
 #pragma unroll
@@ -110,8 +119,10 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
         if (t < Tlen) {
           const T vv = (MODE == 0) ? __ldg(v + base + t) : (T)0;
           sv[j] = vv;
-          scan_coeffs<T, MODE>(vv, __ldg(nv + base + t), __ldg(r + base + t), __ldg(done + base + t) != 0,
-                               __ldg(term + base + t) != 0, t == Tlen - 1, gamma, gl, oml, d[j], c[j]);
+          const bool dn = (MODE != 2) ? (__ldg(done + base + t) != 0) : false;
+          const bool tm = (MODE != 2) ? (__ldg(term + base + t) != 0) : false;
+          scan_coeffs<T, MODE>(vv, __ldg(nv + base + t), __ldg(r + base + t), dn, tm, t == Tlen - 1, gamma, gl, oml,
+                               d[j], c[j]);
         } else {  // beyond the row: A = 0 there, contributes nothing
           sv[j] = (T)0;
           d[j] = (T)0;
@@ -181,8 +192,9 @@ __global__ void __launch_bounds__(256) gae_cols_kernel(const T *__restrict__ v, 
     const int64_t i = base + t * F;
     const T vv = (MODE == 0) ? __ldg(v + i) : (T)0;
     T dlt, cc;
-    scan_coeffs<T, MODE>(vv, __ldg(nv + i), __ldg(r + i), __ldg(done + i) != 0, __ldg(term + i) != 0, t == Tlen - 1,
-                         gamma, gl, oml, dlt, cc);
+    const bool dn = (MODE != 2) ? (__ldg(done + i) != 0) : false;
+    const bool tm = (MODE != 2) ? (__ldg(term + i) != 0) : false;
+    scan_coeffs<T, MODE>(vv, __ldg(nv + i), __ldg(r + i), dn, tm, t == Tlen - 1, gamma, gl, oml, dlt, cc);
     a = dlt + cc * a;
     adv[i] = a;
     if constexpr (MODE == 0) tgt[i] = a + vv;
@@ -255,4 +267,19 @@ extern "C" int rlb_td_lambda_return(const void *next_state_value, const void *re
     return gae_impl<double, 1>(nullptr, next_state_value, reward, done, terminated, gamma, gammalmbda,
                                one_minus_lmbda, rows, T, F, returns, nullptr, as_stream(stream));
   RLB_REQUIRE(false, RLB_EINVAL, "rlb_td_lambda_return: unsupported dtype %d", dtype);
+}
+
+extern "C" int rlb_affine_scan(const void *d, const void *c, int64_t rows, int64_t T, int64_t F, int dtype, void *out,
+                               rlb_stream_t stream) {
+  RLB_REQUIRE(rows >= 0 && T >= 0 && F >= 1, RLB_EINVAL, "rlb_affine_scan: bad shape rows=%lld T=%lld F=%lld",
+              (long long)rows, (long long)T, (long long)F);
+  if (rows == 0 || T == 0) return RLB_OK;
+  RLB_REQUIRE(d && c && out, RLB_EINVAL, "rlb_affine_scan: null pointer");
+  if (dtype == RLB_F32)
+    return gae_impl<float, 2>(nullptr, c, d, nullptr, nullptr, 0.0, 0.0, 0.0, rows, T, F, out, nullptr,
+                              as_stream(stream));
+  if (dtype == RLB_F64)
+    return gae_impl<double, 2>(nullptr, c, d, nullptr, nullptr, 0.0, 0.0, 0.0, rows, T, F, out, nullptr,
+                               as_stream(stream));
+  RLB_REQUIRE(false, RLB_EINVAL, "rlb_affine_scan: unsupported dtype %d", dtype);
 }

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "rlb_td_lambda_return": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp]),
+    "rlb_affine_scan": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
 }
 
 
@@ -357,6 +358,14 @@ class CudaBackend:
                                                     _dtype_code(nv.dtype), ret.data_ptr(), self._stream(dev)),
                         "rlb_td_lambda_return")
         return ret
+
+    def affine_scan(self, d, c, rows: int, T: int, F: int):
+        dev = self._cuda(d, c)
+        out = torch.empty_like(d)
+        with self._Guard(dev):
+            self._check(self.L.rlb_affine_scan(d.data_ptr(), c.data_ptr(), rows, T, F, _dtype_code(d.dtype),
+                                               out.data_ptr(), self._stream(dev)), "rlb_affine_scan")
+        return out
 
 
 class GatherPlan:

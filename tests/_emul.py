@@ -223,6 +223,10 @@ class OracleBackend:
         return po.td_lambda(gamma, lmbda, nv, r, done.bool(), term.bool(), f64=(nv.dtype == torch.float64)).to(nv.dtype)
 
 
+    def affine_scan(self, d, c, rows, T, F):
+        return po.affine_scan(d.reshape(rows, T, F), c.reshape(rows, T, F)).reshape(d.shape)
+
+
 def _capacity(size: int) -> int:
     c = 1
     while c <= size:

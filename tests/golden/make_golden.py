@@ -67,6 +67,31 @@ def td_cases():
     np.savez_compressed(OUT / "td_lambda_golden.npz", **out)
 
 
+def scan_cases():
+    """vtrace_golden.npz: the reference's vtrace_advantage_estimate (functional.py:1297-1382) and
+    vec_generalized_advantage_estimate with per-step gamma / lmbda tensors (functional.py:317-370), and reward2go."""
+    F = reference_functionals()
+    out = {}
+    cases = {"impala": ((16, 80, 1), 0.99, 0.05, 1.0, 1.0), "clip": ((4, 33, 1), 0.9, 0.2, 0.7, 1.3),
+             "multi_f": ((3, 20, 2), 0.97, 0.1, 1.0, 0.9), "nd": ((2, 3, 40, 1), 0.99, 0.05, 1.0, 1.0)}
+    for i, (name, (shape, gamma, p, rho_t, c_t)) in enumerate(cases.items()):
+        g = torch.Generator().manual_seed(400 + i)
+        v, nv, r = (torch.randn(*shape, generator=g) for _ in range(3))
+        log_pi, log_mu = (0.5 * torch.randn(*shape, generator=g) - 1 for _ in range(2))
+        term = torch.rand(*shape, generator=g) < p
+        done = term | (torch.rand(*shape, generator=g) < p)
+        adv, vs = F.vtrace_advantage_estimate(gamma, log_pi, log_mu, v, nv, r, done, term, rho_t, c_t)
+        gammas = 0.9 + 0.1 * torch.rand(*shape, generator=g)
+        lmbdas = 0.8 + 0.2 * torch.rand(*shape, generator=g)
+        ga, gt = F.vec_generalized_advantage_estimate(gammas, lmbdas, v, nv, r, done=done, terminated=term)
+        r2g = F.reward2go(r, done, gamma)                                     # functional.py:1385-1460
+        for k, t in dict(gamma=torch.tensor(gamma), rho_thresh=torch.tensor(rho_t), c_thresh=torch.tensor(c_t), v=v,
+                         nv=nv, r=r, log_pi=log_pi, log_mu=log_mu, done=done, term=term, adv=adv, vs=vs,
+                         gammas=gammas, lmbdas=lmbdas, gae_adv=ga, gae_tgt=gt, r2g=r2g).items():
+            out[f"{name}/{k}"] = t.numpy()
+    np.savez_compressed(OUT / "vtrace_golden.npz", **out)
+
+
 def per_cases():
     assert reference_ext("cpu") is not None
     out = {}
@@ -99,6 +124,7 @@ def per_cases():
 if __name__ == "__main__":
     gae_cases()
     td_cases()
+    scan_cases()
     per_cases()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -337,9 +337,10 @@ def test_gae_functional_errors_and_time_dim(emul, ref_funcs):
     v = torch.randn(4, 9, 1)
     with pytest.raises(RuntimeError, match="must share a unique shape"):
         vec_generalized_advantage_estimate(0.9, 0.9, v, v[:, :8], v, torch.zeros(4, 9, 1, dtype=torch.bool))
-    with pytest.raises(NotImplementedError, match="tensor-valued gamma"):
-        vec_generalized_advantage_estimate(torch.full((4, 9, 1), 0.9), 0.9, v, v, v,
-                                           torch.zeros(4, 9, 1, dtype=torch.bool))
+    nd = torch.zeros(4, 9, 1, dtype=torch.bool)          # a constant per-step gamma tensor == the scalar path
+    a_t, _ = vec_generalized_advantage_estimate(torch.full((4, 9, 1), 0.9), 0.9, v, v, v, nd)
+    a_s, _ = vec_generalized_advantage_estimate(0.9, 0.9, v, v, v, nd)
+    torch.testing.assert_close(a_t, a_s, rtol=1e-5, atol=1e-5)
     g = torch.Generator().manual_seed(0)
     v, nv, r = (torch.randn(6, 11, generator=g) for _ in range(3))
     done = torch.rand(6, 11, generator=g) < 0.1
@@ -388,6 +389,66 @@ def test_td_estimators_plumbing(emul, ref_funcs):
         vec_td_lambda_return_estimate(torch.full((4, 12, 1), 0.9), 0.9, nv, r, done, term)
     with pytest.raises(RuntimeError, match="rolling_gamma=False"):
         vec_td_lambda_return_estimate(0.99, 0.9, nv, r, done, term, rolling_gamma=False)
+
+
+def test_vtrace_and_per_step_gae_plumbing(emul, ref_funcs):
+    """vtrace_advantage_estimate / tensor-valued gamma, lmbda: signature, time_dim, shape errors, values."""
+    from rl_b200.objectives.value import vec_generalized_advantage_estimate, vtrace_advantage_estimate
+
+    g = torch.Generator().manual_seed(1)
+    shape = (4, 12, 1)
+    v, nv, r, lp, lm = (torch.randn(*shape, generator=g) for _ in range(5))
+    term = torch.rand(*shape, generator=g) < 0.1
+    done = term | (torch.rand(*shape, generator=g) < 0.1)
+    ref = ref_funcs.vtrace_advantage_estimate(0.99, lp, lm, v, nv, r, done, term, 1.0, 0.9)
+    got = vtrace_advantage_estimate(0.99, lp, lm, v, nv, r, done, term, 1.0, 0.9)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])     # emulator = C scan, same op order
+    ref = ref_funcs.vtrace_advantage_estimate(0.99, lp, lm, v, nv, r, done, rho_thresh=torch.tensor(0.5))
+    got = vtrace_advantage_estimate(0.99, lp, lm, v, nv, r, done, rho_thresh=torch.tensor(0.5))
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    sq = lambda t: t.squeeze(-1)
+    ref_t = ref_funcs.vtrace_advantage_estimate(0.99, sq(lp), sq(lm), sq(v), sq(nv), sq(r), sq(done), sq(term),
+                                                time_dim=-1)
+    got_t = vtrace_advantage_estimate(0.99, sq(lp), sq(lm), sq(v), sq(nv), sq(r), sq(done), sq(term), time_dim=-1)
+    assert got_t[0].shape == ref_t[0].shape == (4, 12)
+    assert torch.equal(got_t[0], ref_t[0]) and torch.equal(got_t[1], ref_t[1])
+    with pytest.raises(RuntimeError, match="must share a unique shape"):
+        vtrace_advantage_estimate(0.99, lp, lm, v, nv, r[:, :5], done, term)
+
+    gammas = 0.9 + 0.1 * torch.rand(*shape, generator=g)
+    lmbdas = 0.8 + 0.2 * torch.rand(*shape, generator=g)
+    ref = ref_funcs.vec_generalized_advantage_estimate(gammas, lmbdas, v, nv, r, done=done, terminated=term)
+    got = vec_generalized_advantage_estimate(gammas, lmbdas, v, nv, r, done, term)
+    torch.testing.assert_close(got[0], ref[0], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(got[1], ref[1], rtol=1e-4, atol=1e-4)
+    ref = ref_funcs.vec_generalized_advantage_estimate(gammas, 0.95, v, nv, r, done=done, terminated=term)
+    got = vec_generalized_advantage_estimate(gammas, 0.95, v, nv, r, done, term)     # tensor gamma, scalar lmbda
+    torch.testing.assert_close(got[0], ref[0], rtol=1e-4, atol=1e-4)
+    ref_t = ref_funcs.vec_generalized_advantage_estimate(sq(gammas), sq(lmbdas), sq(v), sq(nv), sq(r), done=sq(done),
+                                                         terminated=sq(term), time_dim=-1)
+    got_t = vec_generalized_advantage_estimate(sq(gammas), sq(lmbdas), sq(v), sq(nv), sq(r), sq(done), sq(term),
+                                               time_dim=-1)
+    assert got_t[0].shape == ref_t[0].shape
+    torch.testing.assert_close(got_t[0], ref_t[0], rtol=1e-4, atol=1e-4)
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        vec_generalized_advantage_estimate(gammas.requires_grad_(), lmbdas, v, nv, r, done, term)
+
+    from rl_b200.objectives.value import reward2go
+    for shp, tdim in [((4, 20, 1), -2), ((4, 20, 3), -2), ((2, 3, 20, 1), -2), ((20, 2), -2), ((5, 20), -1),
+                      ((4, 20, 1), 1)]:
+        rr = torch.randn(*shp, generator=g)
+        dd = torch.rand(*shp, generator=g) < 0.15
+        ref = ref_funcs.reward2go(rr, dd, 0.97, time_dim=tdim)
+        got = reward2go(rr, dd, 0.97, time_dim=tdim)
+        assert got.shape == ref.shape == rr.shape
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    ones, dn = torch.ones(1, 10), torch.zeros(1, 10, dtype=torch.bool)       # the docstring example, :1408-1422
+    dn[:, [3, 7]] = True
+    torch.testing.assert_close(reward2go(ones, dn, 0.99, time_dim=-1).flatten(),
+                               torch.tensor([3.9404, 2.9701, 1.99, 1.0, 3.9404, 2.9701, 1.99, 1.0, 1.99, 1.0]),
+                               rtol=1e-4, atol=1e-4)
+    with pytest.raises(ValueError, match="must share the same shape"):
+        reward2go(ones, dn[:, :5], 0.99)
 
 
 @pytest.mark.parametrize("drop_last", [True, False])

@@ -202,3 +202,42 @@ def test_td_lambda_golden_fixture():
         assert torch.equal(got, gt("loop")), k
         f64 = po.td_lambda(gt("gamma"), gt("lmbda"), gt("nv"), gt("r"), gt("done"), gt("term"), f64=True)
         torch.testing.assert_close(gt("vec").double(), f64, rtol=1e-4, atol=1e-4)
+
+
+def test_vtrace_golden_fixture():
+    """The scan oracle against the reference's V-trace loop (bit-equal: same ops in the same order) and its
+    per-step-gamma GAE (cumprod + conv in the reference, recurrence here: the reference's own 1e-4 bar)."""
+    from pathlib import Path
+
+    z = np.load(Path(__file__).parent / "golden" / "vtrace_golden.npz")
+    names = sorted({n.split("/")[0] for n in z.files})
+    assert len(names) == 4
+    for k in names:
+        gt = lambda n: torch.from_numpy(z[f"{k}/{n}"])
+        adv, vs = po.vtrace(float(gt("gamma")), gt("log_pi"), gt("log_mu"), gt("v"), gt("nv"), gt("r"), gt("done"),
+                            gt("term"), float(gt("rho_thresh")), float(gt("c_thresh")))
+        assert torch.equal(vs, gt("vs")), k
+        assert torch.equal(adv, gt("adv")), k
+        ga, gtg = po.gae_per_step(gt("gammas"), gt("lmbdas"), gt("v"), gt("nv"), gt("r"), gt("done"), gt("term"))
+        torch.testing.assert_close(ga, gt("gae_adv"), rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(gtg, gt("gae_tgt"), rtol=1e-4, atol=1e-4)
+        r2g = po.affine_scan(gt("r"), (~gt("done")).float() * float(gt("gamma")))       # reward2go, :1385-1460
+        torch.testing.assert_close(r2g, gt("r2g"), rtol=1e-5, atol=1e-5)
+        # the recurrence in float64 agrees with the fp32 one far inside the bar
+        ga64, _ = po.gae_per_step(gt("gammas").double(), gt("lmbdas").double(), gt("v").double(), gt("nv").double(),
+                                  gt("r").double(), gt("done"), gt("term"))
+        torch.testing.assert_close(ga.double(), ga64, rtol=1e-5, atol=1e-5)
+
+
+def test_vtrace_oracle_matches_live_reference(ref_funcs):
+    g = torch.Generator().manual_seed(5)
+    shape = (3, 17, 2)
+    v, nv, r, lp, lm = (torch.randn(*shape, generator=g) for _ in range(5))
+    term = torch.rand(*shape, generator=g) < 0.1
+    done = term | (torch.rand(*shape, generator=g) < 0.1)
+    ref = ref_funcs.vtrace_advantage_estimate(0.95, lp, lm, v, nv, r, done, term, 0.8, 1.2)
+    got = po.vtrace(0.95, lp, lm, v, nv, r, done, term, 0.8, 1.2)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    ref = ref_funcs.vtrace_advantage_estimate(0.95, lp, lm, v, nv, r, done)       # terminated=None
+    got = po.vtrace(0.95, lp, lm, v, nv, r, done)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
