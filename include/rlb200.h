@@ -230,6 +230,35 @@ int rlb_td_lambda_return(const void *next_state_value /*[dev]*/, const void *rew
                          double gammalmbda, double one_minus_lmbda, int64_t rows, int64_t T, int64_t F, int dtype,
                          void *returns /*[dev]*/, rlb_stream_t stream);
 
+/* ---- write path ------------------------------------------------------------------------
+ * RoundRobinWriter.extend (writers.py:190-216) writes the slots (cursor + arange(n)) % max_size and gives all of them
+ * the sampler's default priority (writers.py:232-235 -> samplers.py:1093-1096).  For such a modular RANGE the tree
+ * update needs no sort / merge: see csrc/tree_range.cuh.
+ *
+ * mode RLB_RANGE_VALUE    *value (tree dtype) is the leaf value as is.
+ *      RLB_RANGE_PRIORITY *value (fp32) is a raw priority: leaf = (p + eps) ** alpha; *max_priority <- max(., p).
+ *      RLB_RANGE_DEFAULT  p = has_max ? (*max_priority + eps) ** alpha : first_default   (samplers.py:886-893), then
+ *                         as RLB_RANGE_PRIORITY -- the whole of PrioritizedSampler.mark_update for a writer batch.
+ * ticket: one zero-initialised 32-bit word the kernel leaves at zero (RLB_RANGE_DEFAULT only).  n <= modulo. */
+#define RLB_RANGE_VALUE 0
+#define RLB_RANGE_PRIORITY 1
+#define RLB_RANGE_DEFAULT 2
+int rlb_tree_update_range(void *sum_tree /*[dev]*/, void *min_tree /*[dev]*/, int64_t capacity, int dtype,
+                          int64_t start, int64_t n, int64_t modulo, int mode, const void *value /*[dev] scalar*/,
+                          double alpha, double eps, double first_default, int has_max,
+                          float *max_priority /*[dev]*/, uint32_t *ticket /*[dev]*/, rlb_stream_t stream);
+
+/* TensorStorage.set for a writer batch (storages.py:1028-1096) fused with the range update above, ONE launch:
+ * dst[k][(cursor + b) % max_size, :] = src[k][b, :] for every leaf k (src_stride_bytes NULL = packed rows) and the trees
+ * as rlb_tree_update_range(start = cursor, modulo = max_size).  sum_tree == min_tree == NULL: rows only;
+ * n_leaves == 0: trees only. */
+int rlb_extend(const void *const *src /*[host] of [dev]*/, void *const *dst /*[host] of [dev]*/,
+               const int64_t *row_bytes /*[host]*/, const int64_t *dst_stride_bytes /*[host]*/,
+               const int64_t *src_stride_bytes /*[host] or NULL*/, int n_leaves, int64_t cursor, int64_t n,
+               int64_t max_size, void *sum_tree /*[dev]*/, void *min_tree /*[dev]*/, int64_t capacity, int dtype,
+               int mode, const void *value /*[dev] scalar*/, double alpha, double eps, double first_default,
+               int has_max, float *max_priority /*[dev]*/, uint32_t *ticket /*[dev]*/, rlb_stream_t stream);
+
 /* The bare reverse scan  out_t = d_t + c_t * out_{t+1}  (out_T = 0) over contiguous [rows, T, F] coefficient
  * tensors.  V-trace (vtrace_advantage_estimate, functional.py:1297-1382: vs_minus_v) and GAE with per-step
  * gamma / lmbda tensors (functional.py:317-370, rolling) are this scan after an elementwise prologue. */

@@ -24,7 +24,7 @@ def needs_build() -> bool:
     if not SO.exists():
         return True
     t = SO.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", ROOT / "include" / "rlb200.h"]
+    deps = [CSRC / s for s in SOURCES] + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "rlb200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -22,6 +22,7 @@
 // Index semantics follow torch indexing: negative indices wrap by `len`; out-of-range indices are
 // clamped and reported through the status word (torch would raise IndexError).
 #include "common.cuh"
+#include "tree_range.cuh"
 
 namespace rlb {
 
@@ -70,7 +71,8 @@ struct GatherParams {
   int64_t peer_delta[RLB_MAX_PEERS];
   int n_peers;
   int pad0_;
-  const int64_t *index;
+  const int64_t *index;  // null: the implicit modular range  (ibase + b) % len  (the writer's cursor; B <= len)
+  int64_t ibase;
   int64_t B;
   int64_t len;
   int32_t *status;
@@ -87,6 +89,12 @@ __device__ __forceinline__ int64_t fix_index(int64_t ix, int64_t len, int32_t *s
     ix = ix < 0 ? 0 : len - 1;
   }
   return ix;
+}
+
+__device__ __forceinline__ int64_t load_index(const GatherParams &P, int64_t b) {
+  if (P.index) return __ldg(P.index + b);
+  const int64_t ix = P.ibase + b;
+  return ix >= P.len ? ix - P.len : ix;
 }
 
 // ---- vector role -------------------------------------------------------------------------------------
@@ -134,7 +142,7 @@ __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams
       b[k] = ok[k] ? u / L.upr : 0;
       j[k] = ok[k] ? (uint32_t)(u - b[k] * L.upr) : 0;
     }
-    ix[k] = ok[k] ? __ldg(P.index + b[k]) : 0;
+    ix[k] = ok[k] ? load_index(P, b[k]) : 0;
   }
   V val[kVecUnroll];
 #pragma unroll
@@ -185,11 +193,12 @@ struct PipeSmem {
 
 constexpr size_t kPipeHeaderBytes = (sizeof(PipeSmem) * kPipes + 1023) / 1024 * 1024;
 
-__device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, PipeSmem *ps) {
+template <bool SCATTER>
+__device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, PipeSmem *ps, int cta) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t npipes = (int64_t)P.bulk_ctas * kPipes;
-  const int64_t pipe = (int64_t)blockIdx.x * kPipes + warp;
+  const int64_t pipe = (int64_t)cta * kPipes + warp;
   // equal split of the 16-B unit space
   const int64_t q = P.bulk_units / npipes, rem = P.bulk_units % npipes;
   int64_t pos = pipe * q + (pipe < rem ? pipe : rem);
@@ -216,7 +225,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
   int64_t off = byte_in_leaf - b * P.leaf[l].row_bytes;
   // index window: lane j holds index[win0 + j]
   int64_t win0 = b;
-  int64_t my_ix = (win0 + lane < P.B) ? __ldg(P.index + win0 + lane) : 0;
+  int64_t my_ix = (win0 + lane < P.B) ? load_index(P, win0 + lane) : 0;
 
   int64_t n_loaded = 0, n_stored = 0;
   bool more = true;
@@ -226,7 +235,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
       const GatherLeaf &L = P.leaf[l];
       if (b >= win0 + 32) {  // warp-uniform: refill the index window
         win0 = b;
-        my_ix = (win0 + lane < P.B) ? __ldg(P.index + win0 + lane) : 0;
+        my_ix = (win0 + lane < P.B) ? load_index(P, win0 + lane) : 0;
       }
       int64_t ix = __shfl_sync(0xffffffffu, my_ix, (int)(b - win0));
       ix = fix_index(ix, P.len, lane == 0 ? P.status : nullptr);
@@ -239,11 +248,11 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
         // the slot was last used by piece n_loaded - kStages: its s->g copy must have finished READING
         // shared memory.  At most kStages - kAhead younger stores may still be pending.
         if (n_loaded >= kStages) bulk_wait_read<kStages - kAhead>();
-        my->dst[stage] = L.dst + b * L.ostride + off;
+        my->dst[stage] = L.dst + (SCATTER ? ix * L.stride : b * L.ostride) + off;
         my->bytes[stage] = (uint32_t)nbytes;
         mbar_arrive_expect_tx(&my->full[stage], (uint32_t)nbytes);
-        bulk_g2s_hint(my_ring + (size_t)stage * kChunk, L.src + ix * L.stride + off, (uint32_t)nbytes,
-                      &my->full[stage], policy);
+        bulk_g2s_hint(my_ring + (size_t)stage * kChunk, L.src + (SCATTER ? b * L.ostride : ix * L.stride) + off,
+                      (uint32_t)nbytes, &my->full[stage], policy);
       }
       ++n_loaded;
       // advance the cursor
@@ -265,7 +274,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
         b = 0;
         off = 0;
         win0 = 0;
-        my_ix = (lane < P.B) ? __ldg(P.index + lane) : 0;
+        my_ix = (lane < P.B) ? load_index(P, lane) : 0;
       }
     }
     // ---- retire the oldest staged piece: wait for its bytes, then DMA it out
@@ -288,14 +297,36 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
 template <bool SCATTER>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const __grid_constant__ GatherParams P) {
   extern __shared__ __align__(128) uint8_t gsmem[];
-  if (!SCATTER && (int)blockIdx.x < P.bulk_ctas) {
+  if ((int)blockIdx.x < P.bulk_ctas) {
     PipeSmem *ps = reinterpret_cast<PipeSmem *>(gsmem);
     uint8_t *ring = gsmem + kPipeHeaderBytes;  // PipeSmem[kPipes] header; stages stay 128-B aligned
-    bulk_role(P, ring, ps);
+    bulk_role<SCATTER>(P, ring, ps, (int)blockIdx.x);
     return;
   }
   const int vec_ctas = (int)gridDim.x - P.bulk_ctas;
   vector_role<SCATTER>(P, (int64_t)blockIdx.x - P.bulk_ctas, vec_ctas);
+}
+
+// The fused write path: TensorStorage.set of a writer batch (storages.py:1028-1096) and the
+// default-priority update of the same slots (writers.py:232-235 -> samplers.py:1093-1096) in ONE launch.  CTAs
+// [0, row_ctas) move the rows (scatter with the implicit modular index), the last range_ctas CTAs write the trees
+// (tree_range.cuh).  The two halves touch disjoint memory and never wait for each other.
+template <typename T>
+__global__ void __launch_bounds__(kRangeThreads) extend_kernel(const __grid_constant__ GatherParams P,
+                                                                const __grid_constant__ RangeParams R,
+                                                                int tree_ctas) {
+  extern __shared__ __align__(128) uint8_t gsmem[];
+  if ((int)blockIdx.x < tree_ctas) {
+    range_role<T>(R, (int)blockIdx.x, tree_ctas);
+    return;
+  }
+  if (threadIdx.x >= kGatherThreads) return;  // the row roles are written for kGatherThreads threads
+  const int cta = (int)blockIdx.x - tree_ctas, row_ctas = (int)gridDim.x - tree_ctas;
+  if (cta < P.bulk_ctas) {
+    bulk_role<true>(P, gsmem + kPipeHeaderBytes, reinterpret_cast<PipeSmem *>(gsmem), cta);
+    return;
+  }
+  vector_role<true>(P, (int64_t)cta - P.bulk_ctas, row_ctas - P.bulk_ctas);
 }
 
 constexpr size_t kBulkSmemBytes = kPipeHeaderBytes + (size_t)kPipes * kStages * kChunk;
@@ -312,22 +343,19 @@ static int pick_vec_log2(const void *src, const void *dst, int64_t row_bytes, in
   return 0;
 }
 
+// Fills the kernel parameters and the CTA split (bulk_ctas in P, vec_ctas returned).  `index` may be null for the
+// implicit modular range starting at `ibase` (write path).
 template <bool SCATTER>
-static int launch_rows(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *stride,
-                       const int64_t *ostride, const int64_t *peer_delta, int n_peers, int n_leaves, const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status,
-                       cudaStream_t st, const char *who) {
-  RLB_REQUIRE(n_leaves >= 0 && n_leaves <= RLB_MAX_LEAVES, RLB_ELIMIT, "%s: n_leaves=%d exceeds RLB_MAX_LEAVES=%d",
-              who, n_leaves, RLB_MAX_LEAVES);
-  RLB_REQUIRE(B >= 0 && len >= 0, RLB_EINVAL, "%s: negative B or len", who);
-  if (n_leaves == 0 || B == 0) return RLB_OK;
-  RLB_REQUIRE(len > 0, RLB_EINVAL, "%s: cannot index an empty storage (len == 0)", who);
-  RLB_REQUIRE(src && dst && row_bytes && stride && index, RLB_EINVAL, "%s: null argument", who);
+static int plan_rows(GatherParams &P, int &vec_ctas_out, const void *const *src, void *const *dst,
+                     const int64_t *row_bytes, const int64_t *stride, const int64_t *ostride,
+                     const int64_t *peer_delta, int n_peers, int n_leaves, const int64_t *index, int64_t ibase,
+                     int64_t B, int64_t len, int mode, int32_t *status, const char *who, int reserved_sms = 0) {
+  RLB_REQUIRE(src && dst && row_bytes && stride, RLB_EINVAL, "%s: null argument", who);
   const int sms = sm_count();
   if (sms <= 0) return RLB_ENODEV;
 
   RLB_REQUIRE(n_peers >= 0 && n_peers <= RLB_MAX_PEERS && (n_peers == 0 || peer_delta), RLB_ELIMIT,
               "%s: n_peers=%d outside [0, %d] or null peer_delta", who, n_peers, RLB_MAX_PEERS);
-  GatherParams P;
   memset(&P, 0, sizeof(P));
   P.n_peers = n_peers > 0 ? n_peers : 1;  // no peer list = the local buffer only
   for (int p = 0; p < n_peers; ++p) {
@@ -335,6 +363,7 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
     P.peer_delta[p] = peer_delta[p];
   }
   P.index = index;
+  P.ibase = ibase;
   P.B = B;
   P.len = len;
   P.status = status;
@@ -351,7 +380,7 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
     L.ostride = ostride ? ostride[k] : row_bytes[k];
     RLB_REQUIRE(L.ostride >= row_bytes[k], RLB_EINVAL, "%s: leaf %d batch-side stride < row_bytes", who, k);
     const int lg = pick_vec_log2(src[k], dst[k], row_bytes[k], stride[k], L.ostride);
-    const bool eligible = !SCATTER && lg == 4 && row_bytes[k] >= 16;
+    const bool eligible = lg == 4 && row_bytes[k] >= 16;  // (rlb_scatter asks for the vector role)
     const bool want = (mode == RLB_GATHER_BULK) || (mode == RLB_GATHER_AUTO && row_bytes[k] >= kBulkMinRowBytes);
     if (row_bytes[k] == 0) {
       L.bulk = 0;
@@ -387,32 +416,69 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
     const int64_t bytes = bulk_units << 4;
     int64_t want_pipes = (bytes + 4095) / 4096;  // at least ~4 KB per pipeline
     int64_t want_ctas = (want_pipes + kPipes - 1) / kPipes;
-    int avail = sms - (vec_ctas < sms / 4 ? vec_ctas : sms / 4);
+    int avail = sms - reserved_sms - (vec_ctas < sms / 4 ? vec_ctas : sms / 4);
     if (avail < 1) avail = 1;
     bulk_ctas = (int)(want_ctas < avail ? want_ctas : avail);
     if (bulk_ctas < 1) bulk_ctas = 1;
   }
   P.bulk_ctas = bulk_ctas;
-  const size_t smem = bulk_ctas > 0 ? kBulkSmemBytes : 0;
-  static bool attr_set_dev[64] = {};  // function attributes are per device
+  vec_ctas_out = vec_ctas;
+  return RLB_OK;
+}
+
+// dynamic shared memory opt-in, once per (kernel, device)
+template <typename K>
+static int allow_bulk_smem(K kernel, bool *attr_set_dev, const char *name) {
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   bool &attr_set = attr_set_dev[cur_dev & 63];
-  if (smem && !attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(gather_kernel<SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kBulkSmemBytes),
-                        "cudaFuncSetAttribute(gather_kernel)");
-    if (rc) return rc;
-    // ask for the largest shared-memory carveout so that a CTA of another kernel (the priority update runs
-    // concurrently on a side stream) can still become resident next to a 161 KB gather CTA
-    rc = check_cuda(cudaFuncSetAttribute(gather_kernel<SCATTER>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared),
-                    "cudaFuncSetAttribute(gather_kernel, carveout)");
-    if (rc) return rc;
-    attr_set = true;
-  }
-  gather_kernel<SCATTER><<<bulk_ctas + vec_ctas, kGatherThreads, smem, st>>>(P);
+  if (attr_set) return RLB_OK;
+  int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkSmemBytes),
+                      name);
+  if (rc) return rc;
+  // ask for the largest shared-memory carveout so that a CTA of another kernel (the priority update runs
+  // concurrently on a side stream) can still become resident next to a 161 KB gather CTA
+  rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared),
+                  name);
+  if (rc) return rc;
+  attr_set = true;
+  return RLB_OK;
+}
+
+template <bool SCATTER>
+static int launch_rows(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *stride,
+                       const int64_t *ostride, const int64_t *peer_delta, int n_peers, int n_leaves,
+                       const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status, cudaStream_t st,
+                       const char *who) {
+  RLB_REQUIRE(n_leaves >= 0 && n_leaves <= RLB_MAX_LEAVES, RLB_ELIMIT, "%s: n_leaves=%d exceeds RLB_MAX_LEAVES=%d",
+              who, n_leaves, RLB_MAX_LEAVES);
+  RLB_REQUIRE(B >= 0 && len >= 0, RLB_EINVAL, "%s: negative B or len", who);
+  if (n_leaves == 0 || B == 0) return RLB_OK;
+  RLB_REQUIRE(len > 0, RLB_EINVAL, "%s: cannot index an empty storage (len == 0)", who);
+  RLB_REQUIRE(index, RLB_EINVAL, "%s: null argument", who);
+  GatherParams P;
+  int vec_ctas = 0;
+  int rc = plan_rows<SCATTER>(P, vec_ctas, src, dst, row_bytes, stride, ostride, peer_delta, n_peers, n_leaves, index,
+                              0, B, len, mode, status, who);
+  if (rc) return rc;
+  const size_t smem = P.bulk_ctas > 0 ? kBulkSmemBytes : 0;
+  static bool attr_set_dev[64] = {};  // function attributes are per device
+  if (smem && (rc = allow_bulk_smem(gather_kernel<SCATTER>, attr_set_dev, "cudaFuncSetAttribute(gather_kernel)")))
+    return rc;
+  gather_kernel<SCATTER><<<P.bulk_ctas + vec_ctas, kGatherThreads, smem, st>>>(P);
   return check_launch(SCATTER ? "gather_kernel<scatter>" : "gather_kernel<gather>");
+}
+
+template <typename T>
+static int launch_extend(const GatherParams &P, int row_ctas, const RangeParams &R, int tree_ctas,
+                         cudaStream_t st) {
+  const size_t smem = P.bulk_ctas > 0 ? kBulkSmemBytes : 0;
+  static bool attr_set_dev[64] = {};
+  int rc;
+  if (smem && (rc = allow_bulk_smem(extend_kernel<T>, attr_set_dev, "cudaFuncSetAttribute(extend_kernel)"))) return rc;
+  extend_kernel<T><<<tree_ctas + row_ctas, kRangeThreads, smem, st>>>(P, R, tree_ctas);
+  return check_launch("extend_kernel");
 }
 
 }  // namespace rlb
@@ -434,6 +500,41 @@ int rlb_scatter(const void *const *src, void *const *dst, const int64_t *row_byt
                 int n_leaves, const int64_t *index, int64_t B, int64_t len, int32_t *status, rlb_stream_t stream) {
   return launch_rows<true>(src, dst, row_bytes, dst_stride_bytes, nullptr, nullptr, 0, n_leaves, index, B, len,
                            RLB_GATHER_VECTOR, status, as_stream(stream), "rlb_scatter");
+}
+
+int rlb_extend(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *dst_stride_bytes,
+               const int64_t *src_stride_bytes, int n_leaves, int64_t cursor, int64_t n, int64_t max_size,
+               void *sum_tree, void *min_tree, int64_t capacity, int dtype, int mode, const void *value, double alpha,
+               double eps, double first_default, int has_max, float *max_priority, uint32_t *ticket,
+               rlb_stream_t stream) {
+  RLB_REQUIRE(n_leaves >= 0 && n_leaves <= RLB_MAX_LEAVES, RLB_ELIMIT, "rlb_extend: n_leaves=%d exceeds %d",
+              n_leaves, RLB_MAX_LEAVES);
+  RLB_REQUIRE(max_size > 0 && cursor >= 0 && cursor < max_size && n >= 0 && n <= max_size, RLB_EINVAL,
+              "rlb_extend: cursor=%lld n=%lld outside max_size=%lld", (long long)cursor, (long long)n,
+              (long long)max_size);
+  if (n == 0) return RLB_OK;
+  const bool trees = sum_tree || min_tree;
+  RLB_REQUIRE(trees || n_leaves > 0, RLB_EINVAL, "rlb_extend: nothing to write");
+  RangeParams R;
+  memset(&R, 0, sizeof(R));
+  int tree_ctas = 0, rc;
+  if (trees) {
+    rc = range_params(R, "rlb_extend", sum_tree, min_tree, capacity, dtype, cursor, n, max_size, mode, value, alpha,
+                      eps, first_default, has_max, max_priority, ticket);
+    if (rc) return rc;
+    tree_ctas = range_ctas(n);
+    if (tree_ctas > 8) tree_ctas = 8;  // the movers need the SMs; 2048 threads write the closed-form nodes fast enough
+  }
+  GatherParams P;
+  memset(&P, 0, sizeof(P));
+  int vec_ctas = 0;
+  if (n_leaves > 0 &&
+      (rc = plan_rows<true>(P, vec_ctas, src, dst, row_bytes, dst_stride_bytes, src_stride_bytes, nullptr, 0, n_leaves,
+                            nullptr, cursor, n, max_size, RLB_GATHER_AUTO, nullptr, "rlb_extend", tree_ctas)))
+    return rc;
+  const int row_ctas = P.bulk_ctas + vec_ctas;
+  if (trees && dtype == RLB_F64) return launch_extend<double>(P, row_ctas, R, tree_ctas, as_stream(stream));
+  return launch_extend<float>(P, row_ctas, R, tree_ctas, as_stream(stream));
 }
 
 }  // extern "C"

@@ -22,6 +22,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tree_range.cuh"
 
 namespace rlb {
 
@@ -109,32 +110,6 @@ __global__ void tree_at_kernel(const T *__restrict__ tree, int64_t capacity, con
                                T *out, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = tree[index[i] | capacity];
-}
-
-// torch.pow(x, scalar) semantics for fp32 tensors on CUDA (ATen/native/cuda/PowKernel.cu): dedicated
-// kernels for 0.5 / -0.5 / -1, x*x, x*x*x, 1/(x*x) for 2 / 3 / -2, ::pow otherwise; exponent 0 -> 1,
-// exponent 1 -> copy (ATen/native/Pow.cpp).  The exponent is cast to the tensor dtype first.
-__device__ __forceinline__ float pow_like_torch(float x, float y) {
-  if (y == 0.0f) return 1.0f;
-  if (y == 1.0f) return x;
-  if (y == 0.5f) return sqrtf(x);
-  if (y == -0.5f) return rsqrtf(x);
-  if (y == -1.0f) return 1.0f / x;
-  if (y == 2.0f) return mul_rn(x, x);
-  if (y == 3.0f) return mul_rn(mul_rn(x, x), x);
-  if (y == -2.0f) return (float)(1.0 / (double)mul_rn(x, x));
-  return powf(x, y);
-}
-__device__ __forceinline__ double pow_like_torch(double x, double y) {
-  if (y == 0.0) return 1.0;
-  if (y == 1.0) return x;
-  if (y == 0.5) return sqrt(x);
-  if (y == -0.5) return rsqrt(x);
-  if (y == -1.0) return 1.0 / x;
-  if (y == 2.0) return x * x;
-  if (y == 3.0) return x * x * x;
-  if (y == -2.0) return 1.0 / (x * x);
-  return pow(x, y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -441,15 +416,6 @@ __host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
   do {                                                                \
     if (dbg && threadIdx.x == 0) dbg[(k)] = (long long)clock64();     \
   } while (0)
-
-// max of floats through one fire-and-forget reduction: non-negative values order like their int bits, negative
-// ones like their reversed unsigned bits (the buffer starts at -inf = 0xff800000, below / above all of them).
-__device__ __forceinline__ void red_max_float(float *addr, float v) {
-  if (v >= 0.0f)
-    atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
-  else
-    atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
-}
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int lane_mask) {
   const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, lane_mask);
@@ -974,6 +940,15 @@ static int tree_update_impl(void *sum_, void *mn_, int64_t capacity, const int64
   return rc;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// contiguous-range priority write (tree_range.cuh)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kRangeThreads) tree_range_kernel(const __grid_constant__ RangeParams R) {
+  range_role<T>(R, (int)blockIdx.x, (int)gridDim.x);
+}
+
 }  // namespace rlb
 
 using namespace rlb;
@@ -1167,6 +1142,22 @@ int rlb_per_update(void *sum_tree, void *min_tree, int64_t capacity, const int64
   plain.index_limit = index_limit;
   return tree_update_impl<float>(sum_tree, min_tree, capacity, index, leaf_scratch, n, /*scalar=*/0, workspace,
                                  workspace_bytes, epoch, st, plain);
+}
+
+int rlb_tree_update_range(void *sum_tree, void *min_tree, int64_t capacity, int dtype, int64_t start, int64_t n,
+                          int64_t modulo, int mode, const void *value, double alpha, double eps, double first_default,
+                          int has_max, float *max_priority, uint32_t *ticket, rlb_stream_t stream) {
+  if (n == 0) return RLB_OK;
+  RangeParams R;
+  int rc = range_params(R, "rlb_tree_update_range", sum_tree, min_tree, capacity, dtype, start, n, modulo, mode, value,
+                        alpha, eps, first_default, has_max, max_priority, ticket);
+  if (rc) return rc;
+  const int ctas = range_ctas(n);
+  if (dtype == RLB_F32)
+    tree_range_kernel<float><<<ctas, kRangeThreads, 0, as_stream(stream)>>>(R);
+  else
+    tree_range_kernel<double><<<ctas, kRangeThreads, 0, as_stream(stream)>>>(R);
+  return check_launch("tree_range_kernel");
 }
 
 }  // extern "C"

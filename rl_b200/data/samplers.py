@@ -355,6 +355,7 @@ class PrioritizedSampler(Sampler):
         self._max_priority_index = None
         self._status = torch.zeros(1, dtype=torch.int32, device=dev)
         self._workspace = None
+        self._range_ticket = None
         self._epoch = 0
 
     def _empty(self) -> None:
@@ -533,6 +534,32 @@ class PrioritizedSampler(Sampler):
     def mark_update(self, index, *, storage: Storage | None = None) -> None:
         self._maybe_init_from_storage(storage)
         self.update_priority(index, self.default_priority, storage=storage)
+
+    def _range_update(self, modulo: int, *, storage: Storage | None = None):
+        """``mark_update`` of a writer batch -- slots (cursor + arange(n)) % modulo -- as kernel arguments
+        (``ops.RangeUpdate``): default priority, its second pow, the running max and the tree write all happen in the
+        range kernel (csrc/tree_range.cuh), alone (``mark_update_range``) or fused with the row write
+        (``rlb_extend``).  ``None`` when this sampler needs the general path (fp64 trees, whose default priority is
+        computed in double, or the O(N) max rescan of ``max_priority_within_buffer``)."""
+        self._maybe_init_from_storage(storage)
+        if self._max_priority_within_buffer or self._sum_tree._dtype != torch.float32 or modulo > self._max_capacity:
+            return None
+        if self._range_ticket is None:
+            self._range_ticket = torch.zeros(1, dtype=torch.int32, device=self._sum_tree.device)
+        rng = ops.RangeUpdate(self._sum_tree.values, self._min_tree.values, self._sum_tree.capacity,
+                              ops.RANGE_DEFAULT, alpha=self._alpha, eps=self._eps,
+                              first_default=(1 + self._eps) ** self._alpha, has_max=self._has_max_priority,
+                              max_buf=self._max_priority_buf, ticket=self._range_ticket)
+        self._has_max_priority = True   # the kernel about to be launched publishes the new running max
+        return rng
+
+    def mark_update_range(self, start: int, n: int, modulo: int, *, storage: Storage | None = None) -> None:
+        """``mark_update(arange(start, start + n) % modulo)`` in one small launch (not in the reference API)."""
+        rng = self._range_update(modulo, storage=storage)
+        if rng is None:
+            dev = self._sum_tree.device
+            return self.mark_update(torch.arange(start, start + n, device=dev) % modulo, storage=storage)
+        ops.backend().tree_update_range(rng, start, n, modulo)
 
     # ---- (de)serialisation -------------------------------------------------------------------------
     def state_dict(self) -> dict:

@@ -397,7 +397,9 @@ class TensorStorage(Storage):
             datum = datum.to(device=store.device, dtype=store.dtype, non_blocking=True)
         return datum
 
-    def set(self, cursor, data, *, set_cursor: bool = True):
+    def _leaves_for_write(self, cursor, data, set_cursor: bool) -> list:
+        """Bookkeeping shared by every write: stacks lists, moves the fill level, allocates on first use and
+        returns the data leaves in storage order."""
         if set_cursor:
             self._last_cursor = cursor
         if isinstance(data, list):
@@ -423,21 +425,44 @@ class TensorStorage(Storage):
                 self._init(data[0])
             else:
                 self._init(pytree.tree_map(lambda x: x[0], data))
+        if is_tensor_collection(data) and self._spec[0] == "td":
+            # read by the storage's own keys: extra keys (e.g. the writer's "index") that the storage does not
+            # hold are dropped, missing keys are an error -- the reference's locked-storage behaviour
+            # (storages.py:1070-1072)
+            leaves = []
+            for k in self._spec[1]:
+                v = data.get(k, None)
+                if v is None:
+                    raise KeyError(f"key {k} of the storage is missing from the data written to it")
+                leaves.append(v)
+            return leaves
         leaves, _ = flatten_data(data)
         if len(leaves) != len(self._leaves):
-            if is_tensor_collection(data) and self._spec[0] == "td":
-                # extra keys (e.g. the writer's "index") that the storage does not hold are dropped, missing
-                # keys are an error -- the reference's locked-storage behaviour (storages.py:1070-1072)
-                leaves = []
-                for k in self._spec[1]:
-                    v = data.get(k, None)
-                    if v is None:
-                        raise KeyError(f"key {k} of the storage is missing from the data written to it")
-                    leaves.append(v)
-            else:
-                raise RuntimeError("the data written to the storage does not match its tree structure")
-        elif is_tensor_collection(data) and self._spec[0] == "td":
-            leaves = [data.get(k) for k in self._spec[1]]
+            raise RuntimeError("the data written to the storage does not match its tree structure")
+        return leaves
+
+    def _fits_range(self, n: int, data) -> bool:
+        """Whether a writer batch of ``n`` items can take ``_extend_range``."""
+        return self.ndim == 1 and 0 < n <= self.max_size and (
+            is_tensor_collection(data) or isinstance(data, (torch.Tensor, dict, tuple, list)))
+
+    def _extend_range(self, cursor: int, n: int, data, trees=None) -> None:
+        """The writer's batch -- rows (cursor + arange(n)) % max_size -- in ONE launch, together with the sampler's
+        default-priority write when ``trees`` (an ``ops.RangeUpdate``) is given: ``rlb_extend``, the fused form of
+        storages.py:1028-1096 + samplers.py:1093-1096."""
+        max0 = self.max_size
+        index = slice(cursor, cursor + n) if cursor + n <= max0 else (torch.arange(cursor, cursor + n) % max0)
+        leaves = self._leaves_for_write(index, data, True)
+        stores = self._leaves
+        cast = [self._cast(d, s) for d, s in zip(leaves, stores)]
+        for d, s in zip(cast, stores):
+            if d.shape[0] != n or d.shape[1:] != s.shape[1:]:
+                raise RuntimeError(f"cannot write data of shape {tuple(d.shape)} into storage rows {tuple(s.shape[1:])}")
+        ops.backend().extend(stores, [d if d.is_contiguous() or d.ndim == 1 or d[0].is_contiguous() else d.contiguous()
+                                      for d in cast], cursor, n, max0, trees)
+
+    def set(self, cursor, data, *, set_cursor: bool = True):
+        leaves = self._leaves_for_write(cursor, data, set_cursor)
         if _is_int(cursor) or isinstance(cursor, slice):
             for datum, store in zip(leaves, self._leaves):
                 store[cursor] = self._cast(datum, store)

@@ -17,6 +17,10 @@ NestedKey = Any  # str | tuple[str, ...]
 
 
 def _norm_key(key: NestedKey) -> tuple:
+    if type(key) is str:
+        return (key,)
+    if type(key) is tuple and key and all(type(k) is str for k in key):
+        return key
     if isinstance(key, str):
         return (key,)
     if isinstance(key, tuple) and all(isinstance(k, str) for k in key) and key:
@@ -89,8 +93,10 @@ class TensorDict:
     def device(self):
         if self._device is not None:
             return self._device
-        for _, v in self.items(True, True):
-            return v.device
+        for v in self._data.values():       # the first leaf decides; no key list is built
+            d = v.device
+            if d is not None:
+                return d
         return None
 
     @property
@@ -133,6 +139,10 @@ class TensorDict:
 
 
     def get(self, key: NestedKey, default=...):
+        if type(key) is str:                # flat key: one dict probe
+            v = self._data.get(key)
+            if v is not None:
+                return v
         node: Any = self
         for k in _norm_key(key):
             if not isinstance(node, TensorDict) or k not in node._data:
@@ -167,8 +177,15 @@ class TensorDict:
         return out
 
     def items(self, include_nested: bool = False, leaves_only: bool = False) -> Iterator:
-        for k in self.keys(include_nested, leaves_only):
-            yield k, self.get(k)
+        for k, v in self._data.items():
+            if isinstance(v, TensorDict):
+                if not leaves_only:
+                    yield k, v
+                if include_nested:
+                    for sk, sv in v.items(True, leaves_only):
+                        yield (k, *((sk,) if type(sk) is str else sk)), sv
+            else:
+                yield k, v
 
     def values(self, include_nested: bool = False, leaves_only: bool = False) -> Iterator:
         for _, v in self.items(include_nested, leaves_only):

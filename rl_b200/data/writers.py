@@ -150,14 +150,41 @@ class RoundRobinWriter(Writer):
             raise RuntimeError(f"Expected at least one element in extend. Got {data=}")
         device = data.device if hasattr(data, "device") else None
         max0 = self._storage._max_size_along_dim0(batched_data=data)
-        index = torch.arange(cur, cur + n, dtype=torch.long, device=device) % max0
+        index = torch.arange(cur, cur + n, dtype=torch.long, device=device)
+        if cur + n > max0:
+            index = index % max0
         self._cursor = (cur + n) % max0
         self._write_count += n
         self._stamp(data, index)
+        if self._extend_fused(cur, n, max0, data, index):
+            return index
         self._storage.set(slice(cur, cur + n) if cur + n <= max0 else index, data)
         index = self._replicate_index(index)
         self._mark_update_entities(index)
         return index
+
+    def _extend_fused(self, cur: int, n: int, max0: int, data, index) -> bool:
+        """Rows and default priorities of the batch in one launch (``TensorStorage._extend_range``): a writer batch is
+        always the modular slot range (cur + arange(n)) % max0, for which neither the row write nor the tree update
+        needs the index tensor.  The first attached buffer whose sampler accepts the range form rides in the row
+        kernel; every other attached buffer is told through ``mark_update`` as usual."""
+        storage = self._storage
+        if not hasattr(storage, "_extend_range") or not storage._fits_range(n, data):
+            return False
+        ents = list(storage._attached_entities_iter())
+        trees, fused_ent = None, None
+        for ent in ents:
+            make = getattr(getattr(ent, "_sampler", None), "_range_update", None)
+            if make is not None:
+                trees = make(max0, storage=storage)
+                if trees is not None:
+                    fused_ent = ent
+                    break
+        storage._extend_range(cur, n, data, trees)
+        for ent in ents:
+            if ent is not fused_ent:
+                ent.mark_update(index)
+        return True
 
     def __repr__(self) -> str:
         full = self._storage._is_full if self._storage is not None else None

@@ -52,6 +52,10 @@ _SIGNATURES = {
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "rlb_td_lambda_return": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "rlb_affine_scan": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
+    "rlb_tree_update_range": (_i32, [_vp, _vp, _i64, _i32, _i64, _i64, _i64, _i32, _vp, _f64, _f64, _f64, _i32, _vp,
+                                     _vp, _vp]),
+    "rlb_extend": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _f64,
+                          _f64, _f64, _i32, _vp, _vp, _vp]),
 }
 
 
@@ -314,7 +318,7 @@ class CudaBackend:
 
     @staticmethod
     def _check_rows(t: torch.Tensor) -> None:
-        if t.ndim < 1 or (t.ndim > 1 and t.shape[0] > 0 and not t[0].is_contiguous()):
+        if t.ndim < 1 or (t.ndim > 1 and t.shape[0] > 0 and not t.is_contiguous() and not t[0].is_contiguous()):
             raise RuntimeError("leaves must be [N, ...] tensors whose rows are contiguous")
 
     def gather(self, leaves: Sequence[torch.Tensor], index: torch.Tensor, length: int, mode: int = GATHER_AUTO,
@@ -337,6 +341,45 @@ class CudaBackend:
                 self._check_rows(t)
             if pairs:
                 self._rows("rlb_scatter", [t for t, _ in pairs], [d for _, d in pairs], index, length, status)
+
+    # -- write path --------------------------------------------------------------------------------
+    def tree_update_range(self, rng: "RangeUpdate", start: int, n: int, modulo: int) -> None:
+        """Priority write of the slots (start + arange(n)) % modulo (``rlb_tree_update_range``)."""
+        dev = self._cuda(rng.sum, rng.mn, rng.value, rng.max_buf, rng.ticket)
+        with self._Guard(dev):
+            self._check(self.L.rlb_tree_update_range(
+                self._p(rng.sum), self._p(rng.mn), rng.capacity, rng.dtype_code, start, n, modulo, rng.mode,
+                self._p(rng.value), rng.alpha, rng.eps, rng.first_default, int(rng.has_max), self._p(rng.max_buf),
+                self._p(rng.ticket), self._stream(dev)), "rlb_tree_update_range")
+
+    def extend(self, stores: Sequence[torch.Tensor], data: Sequence[torch.Tensor], cursor: int, n: int,
+               max_size: int, rng: "RangeUpdate | None" = None) -> None:
+        """stores[k][(cursor + b) % max_size] = data[k][b] for every leaf and, with ``rng``, the priority write of the
+        same slots -- one launch (``rlb_extend``; more than RLB_MAX_LEAVES leaves take one launch per group)."""
+        pairs = [(t, d) for t, d in zip(stores, data) if t.numel() > 0 and d.numel() > 0]
+        for t, d in pairs:
+            self._check_rows(t)
+            self._check_rows(d)
+        extra = () if rng is None else (rng.sum, rng.mn, rng.value, rng.max_buf, rng.ticket)
+        dev = self._cuda(*extra, *[t for t, _ in pairs], *[d for _, d in pairs])
+        with self._Guard(dev):
+            groups = [pairs[lo:lo + MAX_LEAVES] for lo in range(0, len(pairs), MAX_LEAVES)] or [[]]
+            for gi, grp in enumerate(groups):
+                k = len(grp)
+                P, I = ctypes.c_void_p * max(k, 1), ctypes.c_int64 * max(k, 1)
+                rowb = I(*[t.element_size() * (t[0].numel() if t.ndim > 1 else 1) for t, _ in grp])
+                dstride = I(*[t.stride(0) * t.element_size() for t, _ in grp])
+                sstride = I(*[(d.stride(0) if d.shape[0] > 1 else (d[0].numel() if d.ndim > 1 else 1))
+                              * d.element_size() for _, d in grp])
+                r = rng if gi == 0 else None     # the trees ride with the first group
+                self._check(self.L.rlb_extend(
+                    P(*[d.data_ptr() for _, d in grp]), P(*[t.data_ptr() for t, _ in grp]), rowb, dstride, sstride,
+                    k, cursor, n, max_size,
+                    self._p(r.sum) if r else None, self._p(r.mn) if r else None, r.capacity if r else 0,
+                    r.dtype_code if r else 0, r.mode if r else 0, self._p(r.value) if r else None,
+                    r.alpha if r else 0.0, r.eps if r else 0.0, r.first_default if r else 0.0,
+                    int(r.has_max) if r else 0, self._p(r.max_buf) if r else None,
+                    self._p(r.ticket) if r else None, self._stream(dev)), "rlb_extend")
 
     # -- GAE ---------------------------------------------------------------------------------------
     def gae(self, v, nv, r, done, term, gamma: float, gammalmbda: float, rows: int, T: int, F: int):
@@ -366,6 +409,23 @@ class CudaBackend:
             self._check(self.L.rlb_affine_scan(d.data_ptr(), c.data_ptr(), rows, T, F, _dtype_code(d.dtype),
                                                out.data_ptr(), self._stream(dev)), "rlb_affine_scan")
         return out
+
+
+RANGE_VALUE, RANGE_PRIORITY, RANGE_DEFAULT = 0, 1, 2
+
+
+class RangeUpdate:
+    """Tree-side arguments of ``rlb_tree_update_range`` / ``rlb_extend`` (see include/rlb200.h)."""
+
+    __slots__ = ("sum", "mn", "capacity", "dtype_code", "mode", "value", "alpha", "eps", "first_default", "has_max",
+                 "max_buf", "ticket")
+
+    def __init__(self, sum, mn, capacity, mode, value=None, alpha=1.0, eps=0.0, first_default=1.0, has_max=False,
+                 max_buf=None, ticket=None):
+        self.sum, self.mn, self.capacity, self.mode, self.value = sum, mn, int(capacity), int(mode), value
+        self.dtype_code = _dtype_code((sum if sum is not None else mn).dtype)
+        self.alpha, self.eps, self.first_default = float(alpha), float(eps), float(first_default)
+        self.has_max, self.max_buf, self.ticket = bool(has_max), max_buf, ticket
 
 
 class GatherPlan:

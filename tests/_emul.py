@@ -154,6 +154,27 @@ class OracleBackend:
         leaf = torch.pow(priority + eps, alpha)
         self.tree_update(sum_tree, min_tree, capacity, index, leaf, workspace, epoch)
 
+    # ---- write path: what the reference does for a writer batch, index by index
+    def tree_update_range(self, rng, start, n, modulo):
+        index = torch.arange(start, start + n) % modulo
+        if rng.mode == 0:
+            return self.tree_update(rng.sum, rng.mn, rng.capacity, index, rng.value.reshape(1), None, 0)
+        if rng.mode == 1:
+            p = rng.value.reshape(()).to(torch.float32)
+        elif rng.has_max:
+            p = (rng.max_buf[0] + rng.eps) ** rng.alpha                     # samplers.py:886-893
+        else:
+            p = torch.as_tensor(rng.first_default, dtype=torch.float32)
+        self.per_update(rng.sum, rng.mn, rng.capacity, index, p, rng.alpha, rng.eps, rng.max_buf, None, 0)
+
+    def extend(self, stores, data, cursor, n, max_size, rng=None):
+        index = torch.arange(cursor, cursor + n) % max_size
+        for t, d in zip(stores, data):
+            if t.numel() and d.numel():
+                t[index] = d
+        if rng is not None:
+            self.tree_update_range(rng, cursor, n, max_size)
+
     # ---- sharded minibatch trailer
     def shard_pack(self, rows, meta_offset, index, leaf, psum_pmin, index_base, peer_delta=None):
         m = meta_offset

@@ -54,6 +54,113 @@ def test_tree_update_matches_oracle_bitwise(cuda_backend, size):
     _heap_equal(ds, os_)
 
 
+@pytest.mark.parametrize("size", [1, 2, 7, 16, 1000, 4097, 100_000, 1_000_000])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_tree_update_range_matches_oracle_bitwise(cuda_backend, size, dtype):
+    """rlb_tree_update_range (closed-form fill + boundary chain) against the reference's index-by-index update: whole
+    heaps bit-equal, for plain / wrapping / full / single-slot ranges on top of random earlier contents."""
+    from rl_b200 import ops
+    from rl_b200.data.segment_tree import (MinSegmentTreeFp32, MinSegmentTreeFp64, SumSegmentTreeFp32,
+                                           SumSegmentTreeFp64)
+
+    f64 = dtype == torch.float64
+    rng = np.random.default_rng(size + f64)
+    ds = (SumSegmentTreeFp64 if f64 else SumSegmentTreeFp32)(size, dev())
+    dm = (MinSegmentTreeFp64 if f64 else MinSegmentTreeFp32)(size, dev())
+    npdt = np.float64 if f64 else np.float32
+
+    class NpTree:
+        """fp64 has no compiled reference here: every node an update touches ends as op(children)
+        (segment_tree.h:83-139), so the heap is rebuilt level by level from the leaves; untouched nodes keep the
+        identity, which op(identity, identity) reproduces."""
+
+        def __init__(self, is_min):
+            self.is_min = is_min
+            self.h = np.full(2 * ds.capacity, np.finfo(np.float64).max if is_min else 0.0)
+
+        def __setitem__(self, ix, v):
+            cap = ds.capacity
+            self.h[cap + ix] = v
+            w = cap // 2
+            while w >= 1:
+                a, b = self.h[2 * w:4 * w:2], self.h[2 * w + 1:4 * w:2]
+                self.h[w:2 * w] = np.minimum(a, b) if self.is_min else a + b
+                w //= 2
+
+        def values(self):
+            return self.h
+
+    os_, om = (NpTree(False), NpTree(True)) if f64 else (po.OracleTree(size, False), po.OracleTree(size, True))
+    n0 = min(size, 5000)
+    idx = rng.integers(0, size, n0).astype(np.int64)
+    val = (rng.random(n0) * 3 + 1e-3).astype(npdt)
+    for t in (os_, om):
+        t[idx] = val
+    ds[torch.from_numpy(idx).to(dev())] = torch.from_numpy(val).to(dev())
+    dm[torch.from_numpy(idx).to(dev())] = torch.from_numpy(val).to(dev())
+    cases = [(0, 1), (size - 1, 1), (0, size), (size // 2, size), (size // 3, max(1, size // 2)), (size - 1, 2),
+             (0, max(1, size - 1)), (size // 2, max(1, size // 2 + 1))]
+    cases += [(int(rng.integers(0, size)), int(rng.integers(1, size + 1))) for _ in range(6)]
+    for start, n in cases:
+        n = min(n, size)
+        v = npdt(rng.random() * 2 + 1e-3)
+        ix = (start + np.arange(n, dtype=np.int64)) % size
+        for t in (os_, om):
+            t[ix] = v
+        value = torch.tensor(v, dtype=dtype, device=dev())
+        cuda_backend.tree_update_range(ops.RangeUpdate(ds.values, dm.values, ds.capacity, ops.RANGE_VALUE, value),
+                                       start, n, size)
+        _heap_equal(ds, os_)
+        _heap_equal(dm, om)
+    # a single tree (the segment-tree classes' own use)
+    cuda_backend.tree_update_range(ops.RangeUpdate(ds.values, None, ds.capacity, ops.RANGE_VALUE,
+                                                   torch.tensor(0.5, dtype=dtype, device=dev())), 0, size, size)
+    os_[np.arange(size, dtype=np.int64)] = npdt(0.5)
+    _heap_equal(ds, os_)
+    _heap_equal(dm, om)
+
+
+@pytest.mark.parametrize("alpha", [0.6, 0.5, 1.0])
+def test_range_default_priority_matches_oracle_sampler(cuda_backend, alpha):
+    """mark_update of writer batches through the range kernel (default priority computed in the kernel, double pow,
+    running max through the ticket) == the restated reference sampler, leaf for leaf, across many extends."""
+    from rl_b200.data import PrioritizedSampler
+
+    N = 5000
+    smp = PrioritizedSampler(N, alpha, 0.4, device=dev())
+    orc = po.OraclePrioritizedSampler(N, alpha, 0.4)
+    rng = np.random.default_rng(3)
+    cursor = 0
+    for it in range(12):
+        n = int(rng.integers(1, 3000))
+        smp.mark_update_range(cursor, n, N)
+        orc.mark_update(torch.arange(cursor, cursor + n) % N)
+        cursor = (cursor + n) % N
+        got_s, got_m = smp._sum_tree.values.cpu().numpy(), smp._min_tree.values.cpu().numpy()
+        if alpha == 1.0:            # no transcendental: the CPU restatement is exact.  (torch's CPU sqrt / pow are not
+                                    # correctly rounded -- 0.7 % of fp32 inputs differ from IEEE sqrt -- so for any
+                                    # other alpha CPU and CUDA leaves differ by an ulp in the reference itself)
+            np.testing.assert_array_equal(got_s[1:], orc._sum_tree.values()[1:])
+            np.testing.assert_array_equal(got_m[1:], orc._min_tree.values()[1:])
+            assert float(smp._max_priority_buf[0]) == float(torch.as_tensor(orc._max_priority, dtype=torch.float32))
+        else:                       # CUDA powf vs glibc powf: leaves agree to an ulp, the heap is exact for ITS leaves
+            cap = smp._sum_tree.capacity
+            np.testing.assert_allclose(got_s[cap:cap + N], orc._sum_tree.values()[cap:cap + N], rtol=1e-6)
+            ts, tm = po.OracleTree(N, False), po.OracleTree(N, True)
+            ts.load_leaves(got_s[cap:cap + N])
+            tm.load_leaves(got_m[cap:cap + N])
+            np.testing.assert_array_equal(got_s[1:], ts.values()[1:])
+            np.testing.assert_array_equal(got_m[1:], tm.values()[1:])
+            np.testing.assert_allclose(float(smp._max_priority_buf[0]), float(orc._max_priority), rtol=1e-6)
+        if it % 3 == 2:       # raise / keep the running max so that the default priority moves
+            k = int(rng.integers(1, 200))
+            idx = torch.from_numpy(rng.integers(0, N, k))
+            pr = torch.from_numpy((rng.random(k) * (it + 1)).astype(np.float32))
+            smp.update_priority(idx.to(dev()), pr.to(dev()))
+            orc.update_priority(idx, pr)
+    assert int(smp._range_ticket.item()) == 0
+
+
 def test_tree_kat_and_queries(cuda_backend):
     # test/rb/test_prioritized.py:113-140
     from rl_b200.data.segment_tree import MinSegmentTreeFp32, SumSegmentTreeFp32
