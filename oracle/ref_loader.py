@@ -63,8 +63,9 @@ def reference_functionals(root: str = "/root/reference"):
     base = Path(root) / "torchrl" / "objectives" / "value"
     if not base.exists():
         return None
-    if "tensordict" not in sys.modules:
-        td, tdu = types.ModuleType("tensordict"), types.ModuleType("tensordict.utils")
+    td = sys.modules.setdefault("tensordict", types.ModuleType("tensordict"))
+    tdu = sys.modules.setdefault("tensordict.utils", types.ModuleType("tensordict.utils"))
+    if not hasattr(td, "TensorDictBase") or not hasattr(tdu, "expand_right"):
 
         class TensorDictBase:  # isinstance() target only
             pass
@@ -75,7 +76,6 @@ def reference_functionals(root: str = "/root/reference"):
             return t.expand(shape)
 
         td.TensorDictBase, tdu.expand_right, td.utils = TensorDictBase, expand_right, tdu
-        sys.modules.update({"tensordict": td, "tensordict.utils": tdu})
     for n in ("torchrl", "torchrl.objectives", "torchrl.objectives.value"):
         if n not in sys.modules:
             m = types.ModuleType(n)
@@ -92,3 +92,125 @@ def reference_functionals(root: str = "/root/reference"):
     _load("torchrl.objectives.value.utils", base / "utils.py")
     _FUNCS = _load("torchrl.objectives.value.functional", base / "functional.py")
     return _FUNCS
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the reference's samplers module, UNMODIFIED, imported by path
+# ----------------------------------------------------------------------------------------------------------
+_SAMPLERS = None
+
+
+class StubTD:
+    """The few TensorDict operations torchrl/data/replay_buffers/samplers.py performs on storage contents: nested-key
+    ``get`` / ``[key]``, row indexing, ``keys(include_nested=True)``.  Flat dict keyed by tuples."""
+
+    def __init__(self, data: dict):
+        self._d = {(k,) if isinstance(k, str) else tuple(k): v for k, v in data.items()}
+
+    @staticmethod
+    def _k(key):
+        return (key,) if isinstance(key, str) else tuple(key)
+
+    def keys(self, include_nested=False, leaves_only=False):
+        return [k[0] if len(k) == 1 else k for k in self._d]
+
+    def get(self, key, default=...):
+        k = self._k(key)
+        if k in self._d:
+            return self._d[k]
+        if default is ...:
+            raise KeyError(key)
+        return default
+
+    def __getitem__(self, item):
+        if isinstance(item, str) or (isinstance(item, tuple) and item and all(isinstance(i, str) for i in item)):
+            return self.get(item)
+        return StubTD({k: v[item] for k, v in self._d.items()})
+
+
+def reference_samplers(root: str = "/root/reference"):
+    """Import torchrl/data/replay_buffers/samplers.py by path, with stub modules for what it imports at module level
+    (tensordict, pyvers, torchrl._utils, the storages module) and the COMPILED reference trees as ``torchrl._torchrl``.
+    Returns a namespace with the module (``.mod``) and ``make_storage(data: dict, length, max_size, last_cursor)`` that
+    builds the minimal ``TensorStorage`` the samplers need.  DEV CONTAINER ONLY (None when /root/reference is absent).
+    """
+    global _SAMPLERS
+    if _SAMPLERS is not None:
+        return _SAMPLERS
+    path = Path(root) / "torchrl" / "data" / "replay_buffers" / "samplers.py"
+    if not path.exists():
+        return None
+    import logging
+
+    import torch
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            if not hasattr(m, k):
+                setattr(m, k, v)
+        return m
+
+    def implement_for(*a, **k):          # pyvers: version-gated overloads; the last definition wins, as at import
+        return lambda fn: fn
+
+    def _replace_last(key, new):         # torchrl/_utils.py: replace the last element of a (nested) key
+        return new if isinstance(key, str) else (*key[:-1], new)
+
+    class Storage:                       # isinstance() targets + the attributes the samplers read
+        ndim = 1
+
+    class StorageEnsemble(Storage):
+        pass
+
+    class TensorStorage(Storage):
+        def __init__(self, data: dict, length: int, max_size: int, last_cursor=None):
+            self._storage = StubTD(data)
+            self._len, self.max_size, self._last_cursor = int(length), int(max_size), last_cursor
+            self.device = next(iter(data.values())).device
+
+        def __len__(self):
+            return self._len
+
+        @property
+        def _is_full(self):
+            return self._len == self.max_size
+
+        @property
+        def shape(self):
+            return torch.Size([self.max_size])
+
+        def __getitem__(self, index):
+            if isinstance(index, slice) and index == slice(None):
+                return StubTD({k: v[: self._len] for k, v in self._storage._d.items()})
+            if isinstance(index, tuple) and len(index) == 1:
+                index = index[0]
+            return self._storage[index]
+
+    mod("pyvers", implement_for=implement_for)
+    td = mod("tensordict", is_tensor_collection=lambda x: isinstance(x, StubTD), MemoryMappedTensor=type("MMT", (), {}),
+             TensorDict=StubTD)
+    tdu = mod("tensordict.utils", NestedKey=object)
+    td.utils = tdu
+    for n in ("torchrl", "torchrl.data", "torchrl.data.replay_buffers"):
+        mod(n)
+    mod("torchrl._extension", EXTENSION_WARNING="")
+    mod("torchrl._utils", _replace_last=_replace_last, logger=logging.getLogger("torchrl"), rl_warnings=lambda: False)
+    mod("torchrl.data.replay_buffers.storages", Storage=Storage, StorageEnsemble=StorageEnsemble,
+        TensorStorage=TensorStorage)
+    mod("torchrl.data.replay_buffers.utils", _auto_device=lambda: torch.device("cpu"),
+        _is_int=lambda i: isinstance(i, int) or (isinstance(i, torch.Tensor) and i.ndim == 0 and not i.is_floating_point()),
+        unravel_index=lambda index, shape: torch.unravel_index(index, shape))
+    ext = reference_ext("cpu")
+    if ext is not None:
+        sys.modules["torchrl._torchrl"] = ext
+    spec = importlib.util.spec_from_file_location("torchrl.data.replay_buffers.samplers", path)
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["torchrl.data.replay_buffers.samplers"] = m
+    spec.loader.exec_module(m)
+    _SAMPLERS = types.SimpleNamespace(mod=m, make_storage=TensorStorage, StubTD=StubTD)
+    return _SAMPLERS

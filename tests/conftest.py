@@ -54,6 +54,17 @@ def ref_funcs():
     return F
 
 
+@pytest.fixture(scope="session")
+def ref_samplers():
+    """The reference's samplers module, unmodified, under stub imports (dev container only)."""
+    from oracle.ref_loader import reference_samplers
+
+    R = reference_samplers()
+    if R is None:
+        pytest.skip("/root/reference not present (GPU box)")
+    return R
+
+
 @pytest.fixture()
 def emul():
     """Install the oracle-backed emulator as rl_b200's backend for one CPU host-logic test."""

@@ -109,6 +109,44 @@ def test_sampler_glue_matches_reference_tree(ref_cpu):
     np.testing.assert_array_equal(wc, wa.numpy())
 
 
+@pytest.mark.parametrize("alpha,beta", [(0.6, 0.4), (0.7, 0.5), (1.0, 1.0)])
+def test_sampler_restatement_equals_live_reference_sampler(ref_samplers, alpha, beta):
+    """The REAL torchrl PrioritizedSampler (samplers.py imported unmodified, on the compiled reference trees) against
+    oracle.OraclePrioritizedSampler through the same life cycle: writer marks, TD-error write-backs with duplicates and
+    negative ("skip") indices, scalar priorities, draws from one CPU generator.  Indices, weights, default priority and
+    the running max agree exactly -- this pins the restatement every GPU parity test leans on."""
+    N = 1000
+    ref = ref_samplers.mod.PrioritizedSampler(N, alpha, beta)
+    st = ref_samplers.make_storage({"obs": torch.zeros(N)}, 0, N)
+    orc = po.OraclePrioritizedSampler(N, alpha, beta)
+    g = torch.Generator().manual_seed(11)
+    ref._rng = torch.Generator().manual_seed(5)
+    og = torch.Generator().manual_seed(5)
+    filled = 0
+    for it in range(8):
+        n = int(torch.randint(1, 300, (), generator=g))
+        idx = (filled + torch.arange(n)) % N
+        filled = min(N, filled + n)
+        st._len = filled
+        ref.mark_update(idx, storage=st)
+        orc.mark_update(idx)
+        k = int(torch.randint(1, 200, (), generator=g))
+        ix = torch.randint(0, filled, (k,), generator=g)
+        ix[::17] = -1
+        pr = torch.rand(k, generator=g) * (it + 1)
+        ref.update_priority(ix, pr, storage=st)
+        orc.update_priority(ix, pr)
+        if it % 3 == 0:
+            ref.update_priority(ix[:5].clamp_min(0), 0.25, storage=st)
+            orc.update_priority(ix[:5].clamp_min(0), 0.25)
+        assert float(ref.default_priority) == float(orc.default_priority)
+        assert float(ref._max_priority[0]) == float(orc._max_priority)
+        ri, rinfo = ref.sample(st, 64)
+        oi, ow = orc.sample(filled, 64, generator=og)
+        assert torch.equal(ri, oi)
+        assert torch.equal(rinfo["priority_weight"], ow)
+
+
 def test_double_pow_quirk():
     # SURVEY 8(a'): mark_update passes the already-powered default priority through update_priority
     s = po.OraclePrioritizedSampler(8, alpha=0.6, beta=0.4)
