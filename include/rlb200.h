@@ -259,6 +259,35 @@ int rlb_extend(const void *const *src /*[host] of [dev]*/, void *const *dst /*[h
                int mode, const void *value /*[dev] scalar*/, double alpha, double eps, double first_default,
                int has_max, float *max_priority /*[dev]*/, uint32_t *ticket /*[dev]*/, rlb_stream_t stream);
 
+/* ---- trajectory slices -------------------------------------------------------------------
+ * SliceSampler for 1-d storages (samplers.py:1207-2300).
+ *
+ * rlb_traj_table: the (start, stop, length) table of the trajectories stored in a ring of L slots
+ * (_find_start_stop_traj :1652-1706, _end_to_start_stop :1708-1743).  signal: RLB_TRAJ_END = L end-of-trajectory bytes,
+ * RLB_TRAJ_ID = L int64 trajectory ids (an end is where the id changes; at capacity the ring closes on slot 0).  Not at
+ * capacity the last slot always ends a trajectory; at capacity slot `cursor` (the last one written, -1 = unknown) does,
+ * and slot L-1 when there is no end at all.  Entries are ordered by stop.  counts[0] = number of trajectories,
+ * counts[1] = how many are at least min_len long; filter != 0 keeps only those in the table (strict_length, :1993-2010).
+ * start / stop / length need room for L entries.  workspace: rlb_traj_table_workspace_bytes(L) bytes, zeroed once.
+ *
+ * rlb_slice_index: _get_index :2058-2215 with span = False.  Slice s takes trajectory traj_draw[s] (the output of
+ * torch.randint(n_traj, ...)) and starts floor(u[s] * (len - seq + 1)) steps into it (fp32 product, as torch.rand() *
+ * int64 tensor); index = (start + step) % storage_length; truncated marks the last real step of every slice.
+ * variable != 0: slices of trajectories shorter than seq_length are shortened (strict_length = False, :2033-2037); then
+ * pad_output pads them to seq_length by repeating the last real index and writes mask, otherwise slice s is written at
+ * out_offset[s] (exclusive cumsum of seq_out, obtained by a first call with index_out == NULL). */
+#define RLB_TRAJ_END 0
+#define RLB_TRAJ_ID 1
+size_t rlb_traj_table_workspace_bytes(int64_t L);
+int rlb_traj_table(const void *signal /*[dev]*/, int kind, int64_t L, int at_capacity, int64_t cursor, int64_t min_len,
+                   int filter, int64_t *start /*[dev]*/, int64_t *stop /*[dev]*/, int64_t *length /*[dev]*/,
+                   int64_t *counts /*[dev] 2*/, void *workspace /*[dev]*/, size_t workspace_bytes, rlb_stream_t stream);
+int rlb_slice_index(const int64_t *start /*[dev]*/, const int64_t *length /*[dev]*/, int64_t n_traj,
+                    const int64_t *traj_draw /*[dev]*/, const float *u /*[dev]*/, int64_t num_slices, int64_t seq_length,
+                    int64_t storage_length, int variable, int pad_output, const int64_t *out_offset /*[dev] or NULL*/,
+                    int64_t *index_out /*[dev] or NULL*/, uint8_t *truncated_out /*[dev] or NULL*/,
+                    uint8_t *mask_out /*[dev] or NULL*/, int64_t *seq_out /*[dev] or NULL*/, rlb_stream_t stream);
+
 /* The bare reverse scan  out_t = d_t + c_t * out_{t+1}  (out_T = 0) over contiguous [rows, T, F] coefficient
  * tensors.  V-trace (vtrace_advantage_estimate, functional.py:1297-1382: vs_minus_v) and GAE with per-step
  * gamma / lmbda tensors (functional.py:317-370, rolling) are this scan after an elementwise prologue. */

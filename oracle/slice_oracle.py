@@ -1,0 +1,90 @@
+"""TEST INFRASTRUCTURE -- CPU restatement of the reference's SliceSampler arithmetic for 1-d storages.
+
+Follows torchrl/data/replay_buffers/samplers.py (SliceSampler):
+    traj_table    _find_start_stop_traj :1652-1706  +  _end_to_start_stop :1708-1743
+    slice_index   _sample_slices :1973-2056  +  _get_index :2058-2215  (span = False)
+with the random draws passed in explicitly (``traj_draw`` = the output of ``torch.randint(maxval, (num_slices,))``,
+``u`` = the output of ``torch.rand(num_slices)``; the reference makes exactly these two calls in this order, :1987-1990 and
+:2099-2102), so that a CUDA run can be checked against it with the draws its own generator produced.
+Pinned against the unmodified reference (tests/test_oracle.py: patched RNG calls) and tests/golden/slice_golden.npz.
+Never imported by the product.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def traj_table(*, end=None, trajectory=None, at_capacity: bool, cursor=None):
+    """(start, stop, length) int64 arrays, one entry per trajectory in the ring, ordered by stop position."""
+    if trajectory is not None:
+        t = np.asarray(trajectory)
+        L = t.shape[0]
+        end = np.empty(L, dtype=bool)
+        end[:-1] = t[:-1] != t[1:]                                   # :1666
+        end[-1] = (t[-1] != t[0]) if at_capacity else True           # :1667-1670
+    else:
+        end = np.array(end, dtype=bool).reshape(-1).copy()
+        L = end.shape[0]
+        if not at_capacity:
+            end[L - 1] = True                                        # :1675-1677
+    if at_capacity:
+        if cursor is not None:
+            end[int(cursor)] = True                                  # :1683-1699: the last written slot closes a trajectory
+        if not end.any():
+            end[L - 1] = True                                        # :1700-1703
+    stop = np.nonzero(end)[0].astype(np.int64)                       # :1717
+    start = (np.roll(stop, 1) + 1) % L                               # :1720-1738 (1-d: the start is the previous stop + 1)
+    length = stop - start + 1                                        # :1739
+    length[length <= 0] += L                                         # :1740
+    return start, stop, length
+
+
+def valid_trajectories(start, stop, length, seq_length: int, strict_length: bool):
+    """The trajectories `traj_idx` indexes (:1993-2010): with strict_length those at least seq_length long."""
+    if strict_length and (length < seq_length).any():
+        keep = length >= seq_length
+        if not keep.any():
+            raise RuntimeError("Did not find a single trajectory with sufficient length")
+        return start[keep], stop[keep], length[keep]
+    return start, stop, length
+
+
+def slice_index(start, length, *, seq_length: int, num_slices: int, storage_length: int, traj_draw, u,
+                strict_length: bool = True, pad_output: bool = False):
+    """index int64[n_out], truncated bool[n_out], mask bool[n_out] | None, per-slice lengths int64[num_slices].
+
+    ``start`` / ``length`` are the (already filtered) trajectories; ``traj_draw`` in [0, len(start))."""
+    traj = np.asarray(traj_draw, dtype=np.int64)
+    u = np.asarray(u, dtype=np.float32)
+    lens = np.asarray(length, dtype=np.int64)[traj]
+    if (not strict_length) and (np.asarray(length) < seq_length).any():
+        seq = np.minimum(lens, seq_length)                           # :2037
+        variable = True
+    else:
+        seq = np.full(num_slices, seq_length, dtype=np.int64)
+        variable = False
+    end_point = lens - seq + 1                                       # :2072-2074, span[1] False
+    # torch.rand(fp32) * int64 tensor -> fp32 product, floor, cast (:2099-2102)
+    rel = np.floor(u * end_point.astype(np.float32)).astype(np.int64)
+    starts = np.asarray(start, dtype=np.int64)[traj] + rel           # :2120-2126
+    if variable and pad_output:
+        T = seq_length
+        ar = np.arange(T, dtype=np.int64)
+        real = ar[None, :] < seq[:, None]                            # :2147-2148
+        full = starts[:, None] + ar[None, :]
+        last = starts + np.maximum(seq - 1, 0)
+        full = np.where(real, full, last[:, None]) % storage_length  # :2151-2158
+        index = full.reshape(-1)
+        mask = real.reshape(-1)
+        truncated = np.zeros(num_slices * T, dtype=bool)
+        truncated[np.arange(num_slices) * T + np.maximum(seq - 1, 0)] = True      # :2178-2183
+        return index, truncated, mask, seq
+    if variable:
+        index = np.concatenate([s + np.arange(n, dtype=np.int64) for s, n in zip(starts, seq)]) % storage_length
+        truncated = np.zeros(index.shape[0], dtype=bool)
+        truncated[np.cumsum(seq) - 1] = True                         # :2187
+        return index, truncated, None, seq
+    index = ((starts[:, None] + np.arange(seq_length, dtype=np.int64)[None, :]) % storage_length).reshape(-1)
+    truncated = np.zeros(num_slices * seq_length, dtype=bool)
+    truncated.reshape(num_slices, seq_length)[:, -1] = True          # :2185
+    return index, truncated, None, seq

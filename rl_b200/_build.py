@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 SO = PKG / "librlb200.so"
-SOURCES = ["abi.cu", "tree.cu", "gae.cu", "gather.cu", "shard.cu"]
+SOURCES = ["abi.cu", "tree.cu", "gae.cu", "gather.cu", "shard.cu", "slice.cu"]
 
 
 def nvcc_path() -> str:

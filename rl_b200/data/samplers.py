@@ -4,6 +4,7 @@
     RandomSampler       uniform with replacement                samplers.py:174-218
     SamplerWithoutReplacement  permutation sweeps (PPO epochs)  samplers.py:221-362
     PrioritizedSampler  proportional PER, sum/min segment trees samplers.py:577-1205
+    SliceSampler        trajectory slices of a ring of steps    samplers.py:1207-2300 (1-d storages, span=False)
 
 ``PrioritizedSampler`` keeps the reference's constructor, properties, bookkeeping quirks (double ``pow``
 on default priorities, running max of raw priorities, SURVEY.md 8a') and error messages, but its trees
@@ -221,6 +222,256 @@ class SamplerWithoutReplacement(Sampler):
     def __repr__(self) -> str:
         perc = len(self._sample_list) / self.len_storage * 100 if self._sample_list is not None else 0.0
         return f"{self.__class__.__name__}({perc: 4.4f}% sampled)"
+
+
+class SliceSampler(Sampler):
+    """Samples slices of data along the first dimension, given start and stop signals (samplers.py:1207-2300).
+
+    Keyword Args:
+        num_slices (int): the number of slices to be sampled; the batch size must be divisible by it. Exclusive with
+            ``slice_len``.
+        slice_len (int): the length of the slices to be sampled; the batch size must be divisible by it.
+        end_key (NestedKey, optional): the key indicating the end of a trajectory. Defaults to ``("next", "done")``.
+        traj_key (NestedKey, optional): the key indicating the trajectories. When neither key is given,
+            ``("collector", "traj_ids")`` then ``"episode"`` are looked up in the storage, then ``end_key`` is used.
+        ends (torch.Tensor, optional): a 1d boolean tensor with the end-of-trajectory signals (needs ``cache_values``).
+        trajectories (torch.Tensor, optional): a 1d integer tensor with the trajectory ids (needs ``cache_values``).
+        cache_values (bool, optional): keep the trajectory table until the buffer is written to. Defaults to ``False``.
+        truncated_key (NestedKey, optional): if not ``None``, the last step of every slice is marked truncated (and done)
+            in the info written into the sample. Defaults to ``("next", "truncated")``.
+        strict_length (bool, optional): if ``False``, trajectories shorter than the slice length are sampled whole and
+            the batch may be shorter than asked. Defaults to ``True`` (they are never sampled).
+        pad_output (bool, optional): with ``strict_length=False``, pad short slices to the slice length by repeating
+            their last step and return ``("collector", "mask")``.
+        span, compile, use_gpu: accepted for signature compatibility; ``span`` must be falsy, the other two have no
+            effect (everything already runs on the storage's device).
+
+    One-dimensional storages only.  Both halves of the reference's index arithmetic are kernels: ``rlb_traj_table``
+    (trajectory boundaries of the ring; the reference's nonzero / roll / boolean-index sequence, :1652-1743, :1993-2010)
+    and ``rlb_slice_index`` (slice expansion, :2058-2215).  The two random draws are the reference's own calls
+    (``torch.randint(n_trajectories, (num_slices,))`` then ``torch.rand(num_slices)``), so a seeded generator yields the
+    reference's slices.  Like the reference, building the table reads two counters back (one sync); with
+    ``cache_values=True`` that happens once per write instead of once per sample.
+    """
+
+    def __init__(self, *, num_slices: int | None = None, slice_len: int | None = None, end_key=None, traj_key=None,
+                 ends: torch.Tensor | None = None, trajectories: torch.Tensor | None = None,
+                 cache_values: bool = False, truncated_key=("next", "truncated"), strict_length: bool = True,
+                 pad_output: bool = False, compile=False, span=False, use_gpu=False):
+        self.num_slices, self.slice_len = num_slices, slice_len
+        self.end_key, self.traj_key = end_key, traj_key
+        self.truncated_key = truncated_key
+        self.cache_values = cache_values
+        self.strict_length = strict_length
+        if pad_output and strict_length:
+            raise ValueError(
+                "pad_output=True is incompatible with strict_length=True: padding only happens when short trajectories "
+                "are kept, which requires strict_length=False.")
+        self.pad_output = pad_output
+        if isinstance(span, (bool, int)):
+            span = (span, span)
+        if any(span):
+            raise NotImplementedError("SliceSampler(span=...) is not supported by the B200 slice kernels")
+        self.span = span
+        self._cache: dict = {}
+        self._given = None          # (signal tensor, by_id) passed to the constructor
+        self._fetch_traj, self._traj_key_auto = True, False
+        if trajectories is not None or ends is not None:
+            what = "trajectories" if trajectories is not None else "ends"
+            if traj_key is not None or end_key:
+                raise RuntimeError(f"`{what}` and `end_key` or `traj_key` are exclusive arguments.")
+            if trajectories is not None and ends is not None:
+                raise RuntimeError("trajectories and ends are exclusive arguments.")
+            if not cache_values:
+                raise RuntimeError(f"To be used, {what} requires `cache_values` to be set to `True`.")
+            sig = trajectories if trajectories is not None else ends
+            if sig.ndim != 1:
+                raise NotImplementedError("SliceSampler supports 1-d storages only")
+            self._given = (sig, trajectories is not None)
+        else:
+            if traj_key is not None:
+                self._fetch_traj = True
+            elif end_key is not None:
+                self._fetch_traj = False
+            else:
+                self._traj_key_auto = True
+            self.end_key = end_key if end_key is not None else ("next", "done")
+        if not ((num_slices is None) ^ (slice_len is None)):
+            raise TypeError("Either num_slices or slice_len must be not None, and not both. "
+                            f"Got num_slices={num_slices} and slice_len={slice_len}.")
+        self._table_buf = self._counts = self._workspace = None
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(num_slices={self.num_slices}, slice_len={self.slice_len}, "
+                f"end_key={self.end_key}, traj_key={self.traj_key}, truncated_key={self.truncated_key}, "
+                f"strict_length={self.strict_length}, pad_output={self.pad_output})")
+
+    def extend(self, index) -> None:
+        super().extend(index)
+        if self._given is None:
+            self._cache.clear()
+
+    def add(self, index) -> None:
+        super().add(index)
+        if self._given is None:
+            self._cache.clear()
+
+    def _empty(self) -> None:
+        self._cache.clear()
+
+    def dumps(self, path) -> None:   # no-op: the table is derived from the storage
+        ...
+
+    def loads(self, path) -> None:
+        ...
+
+    def state_dict(self) -> dict:
+        return {}
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        ...
+
+    # ---- trajectory table ---------------------------------------------------------------------------
+    def _resolve_traj_key(self, contents) -> None:
+        # samplers.py:1798-1864: prefer what collectors write, then "episode", then reconstruct from end_key
+        self._traj_key_auto = False
+        keys = set(contents.keys(True, True)) if hasattr(contents, "keys") else set()
+        if ("collector", "traj_ids") in keys:
+            self.traj_key, self._fetch_traj = ("collector", "traj_ids"), True
+        elif "episode" in keys:
+            self.traj_key, self._fetch_traj = "episode", True
+        else:
+            self._fetch_traj = False
+
+    def _signal(self, storage):
+        """(signal tensor over the filled slots, by_id, at_capacity, cursor)."""
+        if self._given is not None:   # the reference assumes a full storage here (:1565-1586)
+            sig, by_id = self._given
+            return sig.to(storage.device) if hasattr(storage, "device") else sig, by_id, True, -1
+        try:
+            contents = storage[:]
+        except Exception:
+            raise RuntimeError("Could not get a tensordict out of the storage, which is required for SliceSampler to "
+                               "compute the trajectories.")
+        if self._traj_key_auto:
+            self._resolve_traj_key(contents)
+        sig = None
+        for attempt in range(2):
+            key = self.traj_key if self._fetch_traj else self.end_key
+            try:
+                sig = contents.get(key)
+                break
+            except (KeyError, AttributeError):
+                if attempt or (not self._fetch_traj and self.traj_key is None):
+                    raise KeyError(f"SliceSampler could not find {key!r} in the storage")
+                self._fetch_traj = not self._fetch_traj      # fall back to the other signal (:1893-1927)
+        sig = sig.squeeze() if sig.ndim > 1 else sig
+        if sig.ndim != 1:
+            raise NotImplementedError(
+                f"SliceSampler on the B200 engine supports 1-d storages; got a signal of shape {tuple(sig.shape)}")
+        cursor = getattr(storage, "_last_cursor", None)
+        if isinstance(cursor, slice):
+            cursor = cursor.stop - 1
+        elif isinstance(cursor, range):
+            cursor = cursor[-1]
+        elif isinstance(cursor, torch.Tensor):
+            cursor = int(cursor.reshape(-1)[-1])
+        return sig[:len(storage)], self._fetch_traj, bool(storage._is_full), -1 if cursor is None else int(cursor)
+
+    def _table(self, storage, seq_length: int):
+        """(table int64 [3, L] = start / stop / length rows, n_trajectories, n_long_enough)."""
+        key = ("table", seq_length)
+        if self.cache_values and key in self._cache:
+            return self._cache[key]
+        sig, by_id, at_capacity, cursor = self._signal(storage)
+        L = sig.shape[0]
+        if L == 0:
+            raise RuntimeError(_EMPTY_STORAGE_ERROR)
+        dev = sig.device
+        be = ops.backend()
+        if self._table_buf is None or self._table_buf.shape[1] < L or self._table_buf.device != dev:
+            size = max(L, getattr(storage, "max_size", L))
+            self._table_buf = torch.empty((3, size), dtype=torch.int64, device=dev)
+            self._counts = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._workspace = be.traj_workspace(size, dev)
+        table = self._table_buf if not self.cache_values else torch.empty_like(self._table_buf)
+        be.traj_table(sig, by_id, L, at_capacity, cursor, seq_length, self.strict_length, table, self._counts,
+                      self._workspace)
+        n_all, n_long = (int(c) for c in self._counts.tolist())      # the one synchronisation of a table build
+        out = (table, n_all, n_long)
+        if self.cache_values:
+            self._cache[key] = out
+        return out
+
+    def _adjusted_batch_size(self, batch_size: int) -> tuple[int, int]:
+        if self.num_slices is not None:
+            if batch_size % self.num_slices != 0:
+                raise RuntimeError("The batch-size must be divisible by the number of slices, got "
+                                   f"batch_size={batch_size} and num_slices={self.num_slices}.")
+            return batch_size // self.num_slices, self.num_slices
+        if batch_size % self.slice_len != 0:
+            raise RuntimeError("The batch-size must be divisible by the slice length, got "
+                               f"batch_size={batch_size} and slice_len={self.slice_len}.")
+        return self.slice_len, batch_size // self.slice_len
+
+    # ---- sample (samplers.py:1947-2215) -------------------------------------------------------------
+    def sample(self, storage: Storage, batch_size: int) -> tuple[Any, dict]:
+        if storage.ndim != 1:
+            raise NotImplementedError("SliceSampler on the B200 engine supports 1-d storages only")
+        seq_length, num_slices = self._adjusted_batch_size(batch_size)
+        table, n_all, n_long = self._table(storage, seq_length)
+        if self.strict_length:
+            if n_long == 0:
+                raise RuntimeError("Did not find a single trajectory with sufficient length "
+                                   f"(required={seq_length}, trajectories={n_all}).")
+            n_traj, variable = n_long, False
+        else:
+            n_traj, variable = n_all, n_long < n_all
+        dev = table.device
+        traj = torch.randint(n_traj, (num_slices,), device=dev, generator=self._rng)        # :1987-1990
+        u = torch.rand(num_slices, device=dev, generator=self._rng)                          # :2099-2102
+        be = ops.backend()
+        storage_length = storage.shape[0]
+        args = (table[0], table[2], n_traj, traj, u, seq_length, storage_length)
+        if variable and not self.pad_output:
+            seq = be.slice_index(*args, variable=True, want_index=False)[3]
+            ends_at = seq.cumsum(0)
+            total = int(ends_at[-1])                                                         # data-dependent batch size
+            index, truncated, mask, seq = be.slice_index(*args, variable=True, out_offset=ends_at - seq, total=total)
+            slice_starts = ends_at - seq
+        else:
+            index, truncated, mask, seq = be.slice_index(*args, variable=variable, pad_output=self.pad_output)
+            slice_starts = None
+        info: dict = {}
+        if mask is not None:
+            info[("collector", "mask")] = mask
+        contents = storage[:] if hasattr(storage, "get") else None
+        get = (lambda k: contents.get(k, None)) if contents is not None and hasattr(contents, "get") else (lambda k: None)
+        if self.truncated_key is not None:
+            done_key = _replace_last(self.truncated_key, "done")
+            terminated_key = _replace_last(self.truncated_key, "terminated")
+            wanted = {"done": get(done_key), "terminated": get(terminated_key), "is_init": get("is_init")}
+        else:
+            wanted = {"is_init": get("is_init")}
+        have = {k: v for k, v in wanted.items() if v is not None}
+        rows = dict(zip(have, be.gather(list(have.values()), index, len(storage)))) if have else {}
+        if self.truncated_key is not None:
+            done = rows.get("done")
+            info[self.truncated_key] = truncated
+            info[done_key] = truncated.clone() if done is None else done.reshape(truncated.shape) | truncated
+            term = rows.get("terminated")
+            info[terminated_key] = torch.zeros_like(truncated) if term is None else term
+        if "is_init" in rows:   # every slice start is an init for recurrent modules (:2217-2268)
+            marker = torch.zeros_like(rows["is_init"])
+            if slice_starts is None:
+                slice_starts = torch.arange(num_slices, device=dev) * seq_length
+            marker[slice_starts] = True
+            info["is_init"] = marker | rows["is_init"]
+        return (index,), info
+
+
+def _replace_last(key, new: str):
+    return new if isinstance(key, str) else (*key[:-1], new)
 
 
 class PrioritizedSampler(Sampler):

@@ -52,6 +52,9 @@ _SIGNATURES = {
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "rlb_td_lambda_return": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "rlb_affine_scan": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
+    "rlb_traj_table_workspace_bytes": (_sz, [_i64]),
+    "rlb_traj_table": (_i32, [_vp, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rlb_slice_index": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rlb_tree_update_range": (_i32, [_vp, _vp, _i64, _i32, _i64, _i64, _i64, _i32, _vp, _f64, _f64, _f64, _i32, _vp,
                                      _vp, _vp]),
     "rlb_extend": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _f64,
@@ -380,6 +383,49 @@ class CudaBackend:
                     r.alpha if r else 0.0, r.eps if r else 0.0, r.first_default if r else 0.0,
                     int(r.has_max) if r else 0, self._p(r.max_buf) if r else None,
                     self._p(r.ticket) if r else None, self._stream(dev)), "rlb_extend")
+
+    # -- trajectory slices -------------------------------------------------------------------------
+    def traj_workspace(self, L: int, device) -> torch.Tensor:
+        n = int(self.L.rlb_traj_table_workspace_bytes(int(L)))
+        return torch.zeros((n + 7) // 8, dtype=torch.int64, device=device)
+
+    def traj_table(self, signal: torch.Tensor, by_id: bool, L: int, at_capacity: bool, cursor: int, min_len: int,
+                   keep_long_only: bool, table: torch.Tensor, counts: torch.Tensor, workspace: torch.Tensor) -> None:
+        """table: int64 [3, >= L] (start, stop, length rows), counts: int64 [2]; see rlb_traj_table."""
+        dev = self._cuda(signal, table, counts, workspace)
+        if by_id:
+            if signal.dtype != torch.int64:
+                signal = signal.to(torch.int64)
+        elif signal.dtype != torch.uint8:
+            signal = signal.view(torch.uint8) if signal.dtype == torch.bool else (signal != 0).view(torch.uint8)
+        signal = signal.contiguous()
+        if signal.numel() < L or table.shape[1] < L or not table.is_contiguous():
+            raise RuntimeError("traj_table: signal / table shorter than the storage")
+        with self._Guard(dev):
+            self._check(self.L.rlb_traj_table(signal.data_ptr(), 1 if by_id else 0, L, int(at_capacity), cursor, min_len,
+                                              int(keep_long_only), table[0].data_ptr(), table[1].data_ptr(),
+                                              table[2].data_ptr(), counts.data_ptr(), workspace.data_ptr(),
+                                              workspace.numel() * 8, self._stream(dev)), "rlb_traj_table")
+
+    def slice_index(self, start, length, n_traj: int, traj_draw, u, seq_length: int, storage_length: int,
+                    variable: bool = False, pad_output: bool = False, out_offset=None, total: int | None = None,
+                    want_index: bool = True):
+        """Returns (index int64[n], truncated bool[n, 1], mask bool[n] | None, seq int64[num_slices])."""
+        dev = self._cuda(start, length, traj_draw, u, out_offset)
+        S = traj_draw.numel()
+        seq = torch.empty(S, dtype=torch.int64, device=dev)
+        index = trunc = mask = None
+        if want_index:
+            n = S * seq_length if (not variable or pad_output) else int(total)
+            index = torch.empty(n, dtype=torch.int64, device=dev)
+            trunc = torch.empty((n, 1), dtype=torch.bool, device=dev)
+            mask = torch.empty(n, dtype=torch.bool, device=dev) if (variable and pad_output) else None
+        with self._Guard(dev):
+            self._check(self.L.rlb_slice_index(start.data_ptr(), length.data_ptr(), n_traj, traj_draw.data_ptr(),
+                                               u.data_ptr(), S, seq_length, storage_length, int(variable),
+                                               int(pad_output), self._p(out_offset), self._p(index), self._p(trunc),
+                                               self._p(mask), seq.data_ptr(), self._stream(dev)), "rlb_slice_index")
+        return index, trunc, mask, seq
 
     # -- GAE ---------------------------------------------------------------------------------------
     def gae(self, v, nv, r, done, term, gamma: float, gammalmbda: float, rows: int, T: int, F: int):

@@ -175,6 +175,38 @@ class OracleBackend:
         if rng is not None:
             self.tree_update_range(rng, cursor, n, max_size)
 
+    # ---- trajectory slices: the restated reference arithmetic (oracle/slice_oracle.py)
+    def traj_workspace(self, L, device):
+        return torch.zeros(1, dtype=torch.int64)
+
+    def traj_table(self, signal, by_id, L, at_capacity, cursor, min_len, keep_long_only, table, counts, workspace):
+        from oracle import slice_oracle as so
+
+        sig = signal.reshape(-1)[:L].numpy()
+        cur = None if cursor < 0 else cursor
+        start, stop, length = (so.traj_table(trajectory=sig, at_capacity=at_capacity, cursor=cur) if by_id
+                               else so.traj_table(end=sig, at_capacity=at_capacity, cursor=cur))
+        long_enough = length >= min_len
+        counts[0], counts[1] = len(start), int(long_enough.sum())
+        if keep_long_only:
+            start, stop, length = start[long_enough], stop[long_enough], length[long_enough]
+        for row, a in zip(table, (start, stop, length)):
+            row[:len(a)] = torch.from_numpy(a)
+
+    def slice_index(self, start, length, n_traj, traj_draw, u, seq_length, storage_length, variable=False,
+                    pad_output=False, out_offset=None, total=None, want_index=True):
+        from oracle import slice_oracle as so
+
+        idx, tr, mask, seq = so.slice_index(start[:n_traj].numpy(), length[:n_traj].numpy(), seq_length=seq_length,
+                                            num_slices=traj_draw.numel(), storage_length=storage_length,
+                                            traj_draw=traj_draw.numpy(), u=u.numpy(), strict_length=not variable,
+                                            pad_output=pad_output)
+        seq = torch.from_numpy(np.asarray(seq))
+        if not want_index:
+            return None, None, None, seq
+        return (torch.from_numpy(idx), torch.from_numpy(tr).reshape(-1, 1),
+                None if mask is None else torch.from_numpy(mask), seq)
+
     # ---- sharded minibatch trailer
     def shard_pack(self, rows, meta_offset, index, leaf, psum_pmin, index_base, peer_delta=None):
         m = meta_offset

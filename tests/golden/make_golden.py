@@ -92,6 +92,42 @@ def scan_cases():
     np.savez_compressed(OUT / "vtrace_golden.npz", **out)
 
 
+def slice_cases():
+    """slice_golden.npz: the reference's SliceSampler (samplers.py:1207-2300, imported unmodified under stub deps) on 1-d
+    storages: the trajectory table it derives, the two random draws it makes and the index / truncated / mask it returns."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from _slice_cases import _ref_slice_run, _slice_cases
+    from oracle.ref_loader import reference_samplers
+
+    R = reference_samplers()
+    out = {}
+    for name, (kwargs, data, length, max_size, last_cursor, batch_size) in _slice_cases().items():
+        index, info, rec = _ref_slice_run(R, kwargs, data, length, max_size, last_cursor, batch_size, seed=7)
+        smp = R.mod.SliceSampler(**kwargs)
+        st = R.make_storage(data, length, max_size, last_cursor)
+        start, stop, lens = smp._get_stop_and_length(st)
+        by_traj = kwargs.get("traj_key") is not None
+        sig = data[kwargs["traj_key"]] if by_traj else data[("next", "done")]
+        if kwargs.get("num_slices") is not None:
+            num_slices, seq = kwargs["num_slices"], batch_size // kwargs["num_slices"]
+        else:
+            seq, num_slices = kwargs["slice_len"], batch_size // kwargs["slice_len"]
+        cursor = -1 if last_cursor is None else int(last_cursor[-1] if isinstance(last_cursor, torch.Tensor) else last_cursor)
+        out[f"{name}/meta"] = np.array([length, max_size, cursor, seq, num_slices, kwargs.get("strict_length", True),
+                                        kwargs.get("pad_output", False), by_traj], dtype=np.int64)
+        out[f"{name}/signal"] = sig.reshape(-1).numpy()
+        out[f"{name}/stored_done"] = data.get(("next", "done"), torch.zeros(max_size, 1, dtype=torch.bool)).reshape(-1).numpy()
+        out[f"{name}/table"] = np.stack([start[:, 0].numpy(), stop[:, 0].numpy(), lens.numpy()])
+        out[f"{name}/traj_draw"] = rec["traj"].numpy()
+        out[f"{name}/u"] = rec["u"].numpy()
+        out[f"{name}/index"] = index.numpy()
+        out[f"{name}/truncated"] = info[("next", "truncated")].reshape(-1).numpy()
+        out[f"{name}/done"] = info[("next", "done")].reshape(-1).numpy()
+        if ("collector", "mask") in info:
+            out[f"{name}/mask"] = info[("collector", "mask")].numpy()
+    np.savez_compressed(OUT / "slice_golden.npz", **out)
+
+
 def per_cases():
     assert reference_ext("cpu") is not None
     out = {}
@@ -125,6 +161,7 @@ if __name__ == "__main__":
     gae_cases()
     td_cases()
     scan_cases()
+    slice_cases()
     per_cases()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

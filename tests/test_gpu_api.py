@@ -291,3 +291,49 @@ def test_extend_rows_only_and_non_prioritized_buffers(cuda_backend):
         full = rb.storage.get(slice(None))
         for k in data:
             assert torch.equal(full.get(k), ref[k][:len(rb)]), (it, k)
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_slice_sampler_buffer_on_device(cuda_backend, strict):
+    """TensorDictReplayBuffer + SliceSampler on the GPU: the slices are the oracle's for the draws of the buffer's own
+    CUDA generator, rows come from the sampled slots, done = stored done | truncated; cache_values survives sampling and
+    is dropped by a write; a wrapped ring keeps trajectories that cross the end of the storage."""
+    from oracle import slice_oracle as so
+    from rl_b200.data import LazyTensorStorage, SliceSampler, TensorDict, TensorDictReplayBuffer
+
+    L, S, T = 50_000, 32, 16
+    g = torch.Generator(device=dev()).manual_seed(5)
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device=dev()), batch_size=S * T, generator=g,
+                                sampler=SliceSampler(num_slices=S, end_key=("next", "done"), strict_length=strict,
+                                                     cache_values=True))
+    rng = np.random.default_rng(1)
+    written = 0
+    for n in (30_000, 15_000, 12_000):                # the third batch wraps around
+        done = torch.from_numpy(rng.random(n) < 0.04).reshape(n, 1)
+        rb.extend(TensorDict({"obs": torch.arange(written, written + n, dtype=torch.float32, device=dev()).reshape(n, 1),
+                              ("next", "done"): done.to(dev())}, [n]))
+        written += n
+        full = rb.storage.get(slice(None))
+        stored_done = full.get(("next", "done")).reshape(-1).cpu().numpy()
+        filled = len(rb)
+        cursor = rb.storage._last_cursor
+        cursor = cursor.stop - 1 if isinstance(cursor, slice) else int(cursor.reshape(-1)[-1])
+        start, stop, length = so.traj_table(end=stored_done, at_capacity=filled == L, cursor=cursor)
+        variable = (not strict) and bool((length < T).any())
+        vs, _, vl = so.valid_trajectories(start, stop, length, T, strict)
+        for _ in range(2):
+            state = g.get_state()
+            batch = rb.sample()
+            g.set_state(state)
+            traj = torch.randint(len(vs), (S,), device=dev(), generator=g)
+            u = torch.rand(S, device=dev(), generator=g)
+            oi, otr, _, _ = so.slice_index(vs, vl, seq_length=T, num_slices=S, storage_length=L,
+                                           traj_draw=traj.cpu().numpy(), u=u.cpu().numpy(), strict_length=strict)
+            idx = batch.get("index").reshape(-1)
+            np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+            assert variable == (len(oi) != S * T)
+            np.testing.assert_array_equal(batch.get(("next", "truncated")).reshape(-1).cpu().numpy(), otr)
+            np.testing.assert_array_equal(batch.get(("next", "done")).reshape(-1).cpu().numpy(), stored_done[oi] | otr)
+            assert torch.equal(batch.get("obs"), full.get("obs")[idx])
+        assert rb.sampler._cache
+    assert rb.storage._is_full

@@ -638,6 +638,98 @@ def test_vtrace_and_per_step_gae_golden(cuda_backend):
             torch.testing.assert_close(vs_t, vs.squeeze(-1), rtol=1e-5, atol=1e-5)
 
 
+# ---------------------------------------------------------------------------------------------------- trajectory slices
+@pytest.mark.parametrize("L", [1, 2, 7, 2048, 2049, 5000, 100_000, 1_000_003])
+@pytest.mark.parametrize("by_id", [False, True])
+def test_traj_table_matches_oracle(cuda_backend, L, by_id):
+    """rlb_traj_table (tile scan with last-CTA prefix, emit, compaction) against the restated reference
+    (_find_start_stop_traj / _end_to_start_stop): every table row and both counters, bit-exact, over densities from
+    "no end at all" to "every slot ends", partial and full rings, with and without the cursor rule and the length filter."""
+    from oracle import slice_oracle as so
+
+    rng = np.random.default_rng(L + by_id)
+    table = torch.empty((3, L), dtype=torch.int64, device=dev())
+    counts = torch.zeros(2, dtype=torch.int64, device=dev())
+    ws = cuda_backend.traj_workspace(L, dev())
+    for density in [0.0, 0.002, 0.05, 0.6, 1.0]:
+        for at_capacity in (False, True):
+            for cursor in (-1, int(rng.integers(0, L))):
+                if by_id:
+                    sig = np.cumsum(rng.random(L) < density).astype(np.int64) + 5
+                    kw = dict(trajectory=sig)
+                else:
+                    sig = rng.random(L) < density
+                    kw = dict(end=sig)
+                start, stop, length = so.traj_table(at_capacity=at_capacity, cursor=None if cursor < 0 else cursor, **kw)
+                for min_len, keep in ((0, False), (4, False), (4, True), (L + 1, True)):
+                    cuda_backend.traj_table(torch.from_numpy(sig).to(dev()), by_id, L, at_capacity, cursor, min_len, keep,
+                                            table, counts, ws)
+                    long_enough = length >= min_len
+                    assert counts.tolist() == [len(start), int(long_enough.sum())]
+                    sel = long_enough if keep else slice(None)
+                    want = np.stack([start[sel], stop[sel], length[sel]])
+                    np.testing.assert_array_equal(table[:, :want.shape[1]].cpu().numpy(), want)
+    assert int(ws.view(torch.int32)[:2].abs().sum()) == 0        # both tickets are back at zero
+
+
+def test_slice_index_golden_and_large(cuda_backend):
+    """rlb_slice_index with the draws the reference made (tests/golden/slice_golden.npz, produced by the unmodified
+    SliceSampler): index / truncated / mask bit-equal; then BASELINE-scale shapes against the oracle."""
+    from oracle import slice_oracle as so
+
+    z = np.load(GOLD / "slice_golden.npz")
+    for k in sorted({n.split("/")[0] for n in z.files}):
+        gt = lambda n: z[f"{k}/{n}"]
+        length, max_size, cursor, seq, num_slices, strict, pad, by_id = (int(x) for x in gt("meta"))
+        sig = torch.from_numpy(gt("signal")[:length]).to(dev())
+        table = torch.empty((3, max_size), dtype=torch.int64, device=dev())
+        counts = torch.zeros(2, dtype=torch.int64, device=dev())
+        cuda_backend.traj_table(sig, bool(by_id), length, length == max_size, cursor, seq, bool(strict), table, counts,
+                                cuda_backend.traj_workspace(max_size, dev()))
+        n_all, n_long = counts.tolist()
+        assert n_all == gt("table").shape[1]
+        if not strict:
+            np.testing.assert_array_equal(table[:, :n_all].cpu().numpy(), gt("table"))
+        n_traj, variable = (n_long, False) if strict else (n_all, n_long < n_all)
+        traj, u = torch.from_numpy(gt("traj_draw")).to(dev()), torch.from_numpy(gt("u")).to(dev())
+        args = (table[0], table[2], n_traj, traj, u, seq, max_size)
+        if variable and not pad:
+            sq = cuda_backend.slice_index(*args, variable=True, want_index=False)[3]
+            ends_at = sq.cumsum(0)
+            index, trunc, mask, _ = cuda_backend.slice_index(*args, variable=True, out_offset=ends_at - sq,
+                                                             total=int(ends_at[-1]))
+        else:
+            index, trunc, mask, _ = cuda_backend.slice_index(*args, variable=variable, pad_output=bool(pad))
+        np.testing.assert_array_equal(index.cpu().numpy(), gt("index"))
+        np.testing.assert_array_equal(trunc.cpu().numpy().reshape(-1), gt("truncated"))
+        if pad:
+            np.testing.assert_array_equal(mask.cpu().numpy(), gt("mask"))
+    # 10M-slot ring, 4096 slices of 64 steps
+    L, S, T = 10_000_000, 4096, 64
+    rng = np.random.default_rng(0)
+    end = rng.random(L) < 1 / 300
+    start, stop, length = so.traj_table(end=end, at_capacity=True, cursor=None)
+    ks, _, kl = so.valid_trajectories(start, stop, length, T, True)
+    table = torch.empty((3, L), dtype=torch.int64, device=dev())
+    counts = torch.zeros(2, dtype=torch.int64, device=dev())
+    cuda_backend.traj_table(torch.from_numpy(end).to(dev()), False, L, True, -1, T, True, table, counts,
+                            cuda_backend.traj_workspace(L, dev()))
+    assert counts.tolist() == [len(start), len(ks)]
+    np.testing.assert_array_equal(table[0, :len(ks)].cpu().numpy(), ks)
+    g = torch.Generator(device=dev()).manual_seed(0)
+    traj = torch.randint(len(ks), (S,), device=dev(), generator=g)
+    u = torch.rand(S, device=dev(), generator=g)
+    index, trunc, _, _ = cuda_backend.slice_index(table[0], table[2], len(ks), traj, u, T, L)
+    oi, otr, _, _ = so.slice_index(ks, kl, seq_length=T, num_slices=S, storage_length=L, traj_draw=traj.cpu().numpy(),
+                                   u=u.cpu().numpy())
+    np.testing.assert_array_equal(index.cpu().numpy(), oi)
+    np.testing.assert_array_equal(trunc.cpu().numpy().reshape(-1), otr)
+    # size-independent property: every slice is S consecutive ring slots inside ONE trajectory
+    ix = index.view(S, T).cpu().numpy()
+    assert ((ix[:, 1:] - ix[:, :-1]) % L == 1).all()
+    assert not end[ix[:, :-1]].any()
+
+
 # ---------------------------------------------------------------------------------------------------- edge cases
 def test_empty_and_degenerate_inputs(cuda_backend):
     """Empty batches / rows / time axes are no-ops that return correctly shaped empties; arguments are validated."""

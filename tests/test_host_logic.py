@@ -479,3 +479,68 @@ def test_sampler_without_replacement(emul, drop_last, shuffle):
     with pytest.raises(ValueError, match="greater than the storage capacity"):
         ReplayBuffer(storage=LazyTensorStorage(3, device="cpu"), sampler=SamplerWithoutReplacement(drop_last=True),
                      batch_size=8)._sampler.sample(type("S", (), {"__len__": lambda s: 3, "ndim": 1, "device": "cpu"})(), 8)
+
+
+@pytest.mark.parametrize("case", ["end_full", "end_partial", "traj_full", "strict_filter", "loose_variable", "loose_padded",
+                                  "with_terminated", "no_end_full"])
+def test_slice_sampler_equals_live_reference(emul, ref_samplers, case):
+    """rl_b200 SliceSampler inside a TensorDictReplayBuffer (kernels emulated by the oracle) against the UNMODIFIED
+    reference sampler on the same contents with the same CPU generator seed: same slices, same info, same rows."""
+    from _slice_cases import _slice_cases
+    from rl_b200.data import SliceSampler
+
+    kwargs, data, length, max_size, last_cursor, batch_size = _slice_cases()[case]
+    td = TensorDict({k: v[:length] for k, v in data.items()}, [length])
+    td.set("obs", torch.arange(length, dtype=torch.float32).unsqueeze(-1))
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(max_size, device="cpu"), sampler=SliceSampler(**kwargs),
+                                batch_size=batch_size, generator=torch.Generator().manual_seed(3))
+    rb.extend(td)
+    ref = ref_samplers.mod.SliceSampler(**kwargs)
+    ref._rng = torch.Generator().manual_seed(3)
+    cursor = rb.storage._last_cursor
+    st = ref_samplers.make_storage({**{k: v for k, v in data.items()}, "obs": td.get("obs") if length == max_size else
+                                    torch.cat([td.get("obs"), torch.zeros(max_size - length, 1)])}, length, max_size,
+                                   range(cursor.start, cursor.stop) if isinstance(cursor, slice) else cursor)
+    for _ in range(3):
+        want_index, want_info = ref.sample(st, batch_size)
+        got = rb.sample()
+        assert torch.equal(got.get("index").reshape(-1), want_index[0])
+        for k, v in want_info.items():
+            assert torch.equal(got.get(k).reshape(v.shape), v), k
+        assert torch.equal(got.get("obs").reshape(-1), want_index[0].float())     # the rows are the indexed rows
+
+
+def test_slice_sampler_contract(emul):
+    from rl_b200.data import SliceSampler
+
+    with pytest.raises(TypeError, match="Either num_slices or slice_len"):
+        SliceSampler()
+    with pytest.raises(ValueError, match="pad_output=True is incompatible"):
+        SliceSampler(num_slices=2, pad_output=True)
+    with pytest.raises(NotImplementedError, match="span"):
+        SliceSampler(num_slices=2, span=True)
+    with pytest.raises(RuntimeError, match="requires `cache_values`"):
+        SliceSampler(num_slices=2, ends=torch.zeros(10, dtype=torch.bool))
+    L = 60
+    done = torch.zeros(L, 1, dtype=torch.bool)
+    done[[9, 29, 59]] = True
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device="cpu"), batch_size=12,
+                                sampler=SliceSampler(num_slices=3, end_key=("next", "done"), cache_values=True))
+    rb.extend(TensorDict({("next", "done"): done, "t": torch.arange(L)}, [L]))
+    b = rb.sample()
+    t = b.get("t").reshape(3, 4)
+    assert (t[:, 1:] - t[:, :-1] == 1).all()                      # consecutive steps of one trajectory
+    assert b.get(("next", "truncated")).reshape(3, 4)[:, -1].all()
+    assert ("table", 4) in rb.sampler._cache
+    rb.extend(TensorDict({("next", "done"): done[:5], "t": torch.arange(5)}, [5]))
+    assert not rb.sampler._cache                                  # a write drops the cached table
+    with pytest.raises(RuntimeError, match="divisible by the number of slices"):
+        rb.sample(10)
+    with pytest.raises(RuntimeError, match="sufficient length"):
+        rb.sample(3 * 40)
+    # ends= given up front: the table never depends on the storage contents
+    rb2 = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device="cpu"), batch_size=8,
+                                 sampler=SliceSampler(slice_len=4, ends=done.squeeze(-1), cache_values=True))
+    rb2.extend(TensorDict({"t": torch.arange(L)}, [L]))
+    t = rb2.sample().get("t").reshape(2, 4)
+    assert (t[:, 1:] - t[:, :-1] == 1).all()

@@ -279,3 +279,49 @@ def test_vtrace_oracle_matches_live_reference(ref_funcs):
     ref = ref_funcs.vtrace_advantage_estimate(0.95, lp, lm, v, nv, r, done)       # terminated=None
     got = po.vtrace(0.95, lp, lm, v, nv, r, done)
     assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+
+
+# ------------------------------------------------------------------------------------------ SliceSampler
+from _slice_cases import _oracle_slice, _ref_slice_run, _slice_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("case", sorted(_slice_cases()))
+def test_slice_oracle_equals_live_reference(ref_samplers, case):
+    kwargs, data, length, max_size, last_cursor, batch_size = _slice_cases()[case]
+    for seed in range(4):
+        index, info, rec = _ref_slice_run(ref_samplers, kwargs, data, length, max_size, last_cursor, batch_size, seed)
+        oi, otr, omask, _ = _oracle_slice(kwargs, data, length, max_size, last_cursor, batch_size, rec)
+        np.testing.assert_array_equal(index.numpy(), oi)
+        np.testing.assert_array_equal(info[("next", "truncated")].numpy().reshape(-1), otr)
+        stored_done = data[("next", "done")][oi].numpy().reshape(-1) if ("next", "done") in data else np.zeros_like(otr)
+        np.testing.assert_array_equal(info[("next", "done")].numpy().reshape(-1), stored_done | otr)
+        if omask is not None:
+            np.testing.assert_array_equal(info[("collector", "mask")].numpy(), omask)
+        else:
+            assert ("collector", "mask") not in info
+
+
+def test_slice_golden_fixture():
+    """tests/golden/slice_golden.npz (made by the unmodified reference) against the restatement -- runs anywhere."""
+    from pathlib import Path
+
+    from oracle import slice_oracle as so
+
+    z = np.load(Path(__file__).parent / "golden" / "slice_golden.npz")
+    names = sorted({n.split("/")[0] for n in z.files})
+    assert len(names) >= 11
+    for k in names:
+        gt = lambda n: z[f"{k}/{n}"]
+        length, max_size, cursor, seq, num_slices, strict, pad, by_traj = (int(x) for x in gt("meta"))
+        sig = gt("signal")[:length]
+        kw = dict(at_capacity=length == max_size, cursor=None if cursor < 0 else cursor)
+        start, stop, lens = so.traj_table(trajectory=sig, **kw) if by_traj else so.traj_table(end=sig, **kw)
+        np.testing.assert_array_equal(np.stack([start, stop, lens]), gt("table"))
+        start, stop, lens = so.valid_trajectories(start, stop, lens, seq, bool(strict))
+        oi, otr, omask, _ = so.slice_index(start, lens, seq_length=seq, num_slices=num_slices, storage_length=max_size,
+                                           traj_draw=gt("traj_draw"), u=gt("u"), strict_length=bool(strict),
+                                           pad_output=bool(pad))
+        np.testing.assert_array_equal(oi, gt("index"))
+        np.testing.assert_array_equal(otr, gt("truncated"))
+        if pad:
+            np.testing.assert_array_equal(omask, gt("mask"))
