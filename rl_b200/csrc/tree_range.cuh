@@ -9,8 +9,9 @@
 //     These ~2n nodes are plain coalesced stores, spread over as many CTAs as the caller gives the role;
 //   * every other ancestor of a written leaf is an ancestor of one of the (at most four) boundary leaves of the (at
 //     most two, when the range wraps) pieces: <= 4 nodes per level.  Their values form one serial chain from the
-//     leaves to the root,  node = op(child0, child1),  where a child is a closed-form node, the chain's previous node,
-//     or an UNTOUCHED node whose old value was prefetched (all 8 * depth candidates in one parallel round trip).
+//     leaves to the root,  node = op(child0, child1),  where a child is a closed-form node, a node the chain produced
+//     one level below, or an UNTOUCHED node whose old value was prefetched (all <= 8 * depth of them in one parallel
+//     round trip, by the 4 x depth threads that each own one (boundary leaf, level) pair).
 //
 // Neither part waits for the other (the chain never reads a node the fill writes), so there is no grid-wide sync.
 // The default priority itself ((max_priority + eps) ** alpha, samplers.py:886-893), its second pow (the reference's
@@ -139,84 +140,70 @@ __device__ __forceinline__ void range_role(const RangeParams &R, int cta, int nc
       c = add_rn(c, c);
     }
   }
-  if (cta != 0 || tid >= 32) return;
-  // ---- boundary chain: ONE warp, lane = level - 1.  Which nodes exist and where each child comes from depends only on
-  // the range, so every lane works that out for its own level (and loads the untouched children) in parallel; only
-  // the values are serial, handed from lane to lane with one shuffle round per level.
-  const unsigned full = 0xffffffffu;
-  const int l = tid + 1;
-  const bool lvl_ok = l <= R.depth;
-  int64_t node[4], below[4];
-  bool act[4], bact[4];
+  if (cta != 0) return;
+  // ---- boundary chain (CTA 0, 4 warps): warp k = boundary leaf k, lane = level - 1.  Whether a thread's node exists,
+  // and which of its children are closed-form, depends only on the range, so every thread works that out (and loads
+  // the untouched children) in parallel; only the values are serial: one shared-memory exchange + barrier per level.
+  __shared__ long long x_node[2][4];  // nodes produced at the previous / current level (-1: none)
+  __shared__ T x_sum[2][4], x_min[2][4];
+  const int k = tid >> 5, l = (tid & 31) + 1;
+  const bool mine = k < 4 && l <= R.depth && R.e[(k & 3) >> 1] > R.s[(k & 3) >> 1];
+  int64_t node = -1;
+  bool act = false;
+  T imm_s[2] = {(T)0, (T)0}, imm_m[2] = {(T)0, (T)0};
+  bool closed[2] = {false, false};
+  if (mine) {
+    const int64_t edge = R.capacity + range_edge_leaf(R, k);
+    node = edge >> l;
+    act = !range_covers(R, node, l);
+    for (int j = 0; j < k; ++j)  // boundary leaves sharing this ancestor: the lower warp keeps it
+      if (R.e[j >> 1] > R.s[j >> 1] && ((R.capacity + range_edge_leaf(R, j)) >> l) == node) act = false;
+    if (act) {
+      const T cst = scale_pow2(v, l - 1);  // closed-form sum one level below (v + v, 2v + 2v, ... are exact)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool rv = R.e[k >> 1] > R.s[k >> 1];
-    const int64_t edge = rv ? R.capacity + range_edge_leaf(R, k) : 0;
-    node[k] = edge >> l;
-    below[k] = edge >> (l - 1);
-    act[k] = lvl_ok && rv && !range_covers(R, node[k], l);
-    bact[k] = lvl_ok && l > 1 && rv && !range_covers(R, below[k], l - 1);
-#pragma unroll
-    for (int j = 0; j < k; ++j) {  // boundary leaves sharing an ancestor: the lower candidate keeps it
-      if (act[j] && node[j] == node[k]) act[k] = false;
-      if (bact[j] && below[j] == below[k]) bact[k] = false;
-    }
-  }
-  const T cst = scale_pow2(v, l - 1);  // closed-form sum one level below (v + v, 2v + 2v, ... are exact)
-  int src[4][2];                       // >= 0: candidate of the level below that produces this child
-  T imm_s[4][2], imm_m[4][2];          // otherwise: closed form or the untouched node's value
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int64_t child = (node[k] << 1) | ch;
-      src[k][ch] = -1;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (bact[j] && below[j] == child) src[k][ch] = j;
-      imm_s[k][ch] = cst;
-      imm_m[k][ch] = v;
-      if (act[k] && src[k][ch] < 0 && !range_covers(R, child, l - 1)) {
-        imm_s[k][ch] = sum ? ld_cg(sum + child) : (T)0;
-        imm_m[k][ch] = mn ? ld_cg(mn + child) : (T)0;
+      for (int ch = 0; ch < 2; ++ch) {
+        const int64_t child = (node << 1) | ch;
+        closed[ch] = range_covers(R, child, l - 1);
+        imm_s[ch] = closed[ch] ? cst : (sum ? ld_cg(sum + child) : (T)0);  // (an untouched node unless the level
+        imm_m[ch] = closed[ch] ? v : (mn ? ld_cg(mn + child) : (T)0);      //  below produced it: resolved in the loop)
       }
     }
   }
-  T ps[4] = {(T)0, (T)0, (T)0, (T)0}, pm[4] = {(T)0, (T)0, (T)0, (T)0};
+  if (tid < 8) x_node[tid >> 2][tid & 3] = -1;
+  __syncthreads();
+  T out_s = (T)0, out_m = (T)0;
   for (int step = 1; step <= R.depth; ++step) {
-    T qs[4], qm[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      qs[j] = __shfl_up_sync(full, ps[j], 1);
-      qm[j] = __shfl_up_sync(full, pm[j], 1);
-    }
-    if (l == step) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
+    const int cur = step & 1, prv = cur ^ 1;
+    if (k < 4 && l == step) {
+      if (act) {
         T cs[2], cm[2];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-          cs[ch] = imm_s[k][ch];
-          cm[ch] = imm_m[k][ch];
+          const int64_t child = (node << 1) | ch;
+          cs[ch] = imm_s[ch];
+          cm[ch] = imm_m[ch];
+          if (!closed[ch]) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (src[k][ch] == j) {
-              cs[ch] = qs[j];
-              cm[ch] = qm[j];
+            for (int j = 0; j < 4; ++j) {
+              if (x_node[prv][j] == child) {
+                cs[ch] = x_sum[prv][j];
+                cm[ch] = x_min[prv][j];
+              }
             }
           }
         }
-        ps[k] = tree_op<T, false>(cs[0], cs[1]);
-        pm[k] = tree_op<T, true>(cm[0], cm[1]);
+        out_s = tree_op<T, false>(cs[0], cs[1]);
+        out_m = tree_op<T, true>(cm[0], cm[1]);
+        x_sum[cur][k] = out_s;
+        x_min[cur][k] = out_m;
       }
+      x_node[cur][k] = act ? node : -1;
     }
+    __syncthreads();
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (act[k]) {
-      if (sum) sum[node[k]] = ps[k];
-      if (mn) mn[node[k]] = pm[k];
-    }
+  if (act) {
+    if (sum) sum[node] = out_s;
+    if (mn) mn[node] = out_m;
   }
 }
 
