@@ -236,6 +236,49 @@ def kernel_roofline(dev, rb, ring, hbm_peak: float, peak_src: str) -> dict:
     return out
 
 
+def write_path_probe(dev, rb, g, hbm_peak: float) -> dict | None:
+    """SURVEY 8(f)-1 beside the headline: rb.extend of 1024 Atari transitions (rows + default priorities, one rlb_extend
+    launch), ten consecutive writer batches captured in one CUDA graph and replayed.  Never fatal to the bench."""
+    try:
+        from rl_b200.data import TensorDict
+
+        n = 1024
+        td = TensorDict({
+            "pixels": torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+            "action": torch.randint(0, 18, (n, 1), device=dev, generator=g),
+            "next": {"pixels": torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+                     "reward": torch.randn(n, device=dev, generator=g),
+                     "done": torch.zeros(n, 1, dtype=torch.bool, device=dev),
+                     "terminated": torch.zeros(n, 1, dtype=torch.bool, device=dev)},
+            "td_error": torch.rand(n, device=dev, generator=g),
+        }, [n])
+        row = sum(l[0].numel() * l.element_size() for l in rb.storage._leaves if l is not None)
+        rb.extend(td, update_priority=False)
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(dev)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(gr, stream=side):
+                for _ in range(10):
+                    rb.extend(td, update_priority=False)
+        torch.cuda.synchronize(dev)
+        for _ in range(3):
+            gr.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a.record()
+        for _ in range(20):
+            gr.replay()
+        b.record()
+        torch.cuda.synchronize(dev)
+        us = a.elapsed_time(b) * 1e3 / 200
+        gbs = 2 * n * row / us / 1e3
+        return {"extend_n": n, "extend_us": round(us, 2), "extend_GBps": round(gbs, 1), "extend_frac_of_hbm": round(gbs / hbm_peak, 3),
+                "extend_transitions_per_s": round(n / (us * 1e-6), 1), "row_bytes": row}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_ours(args) -> dict:
     from rl_b200 import ops
     from rl_b200.graphs import CudaGraphStep
@@ -514,6 +557,8 @@ def run_ours(args) -> dict:
             result["roofline"] = roof
         if cpu:
             result["cpu_baseline"] = cpu
+        if world == 1:
+            result["breakdown"]["write_path"] = write_path_probe(dev, rb, g, hbm_peak)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
