@@ -288,6 +288,14 @@ int rlb_slice_index(const int64_t *start /*[dev]*/, const int64_t *length /*[dev
                     int64_t *index_out /*[dev] or NULL*/, uint8_t *truncated_out /*[dev] or NULL*/,
                     uint8_t *mask_out /*[dev] or NULL*/, int64_t *seq_out /*[dev] or NULL*/, rlb_stream_t stream);
 
+/* PrioritizedSliceSampler (samplers.py:2575-3028): a slice must not start within the last seq_length - 1 steps of its
+ * trajectory.  The reference zeroes those leaves in the sum tree before each draw and restores them (:2854-2918); here the
+ * draw uses a masked copy of the leaves: this call zeroes leaves[(stop[k] - j) mod ring_length], j < min(length[k],
+ * seq_length - 1), for every trajectory k of an rlb_traj_table (unfiltered); rlb_tree_rebuild + rlb_per_sample follow. */
+int rlb_slice_mask_starts(void *leaves /*[dev] the copy's leaf level: tree + capacity*/, int dtype,
+                          const int64_t *stop /*[dev]*/, const int64_t *length /*[dev]*/, int64_t n_traj,
+                          int64_t seq_length, int64_t ring_length, rlb_stream_t stream);
+
 /* The bare reverse scan  out_t = d_t + c_t * out_{t+1}  (out_T = 0) over contiguous [rows, T, F] coefficient
  * tensors.  V-trace (vtrace_advantage_estimate, functional.py:1297-1382: vs_minus_v) and GAE with per-step
  * gamma / lmbda tensors (functional.py:317-370, rolling) are this scan after an elementwise prologue. */

@@ -181,8 +181,16 @@ def reference_samplers(root: str = "/root/reference"):
             return self._len == self.max_size
 
         @property
-        def shape(self):
+        def _total_shape(self):
             return torch.Size([self.max_size])
+
+        @property
+        def _len_along_dim0(self):
+            return self._len
+
+        @property
+        def shape(self):          # truncated to the fill level, as TensorStorage.shape (storages.py:856-863)
+            return torch.Size([self.max_size if self._is_full else self._len])
 
         def __getitem__(self, index):
             if isinstance(index, slice) and index == slice(None):

@@ -88,3 +88,40 @@ def slice_index(start, length, *, seq_length: int, num_slices: int, storage_leng
     truncated = np.zeros(num_slices * seq_length, dtype=bool)
     truncated.reshape(num_slices, seq_length)[:, -1] = True          # :2185
     return index, truncated, None, seq
+
+
+def invalid_starts(stop, length, seq_length: int, ring_length: int):
+    """PrioritizedSliceSampler._preceding_stop_idx (:2854-2888, strict_length=True, span=False): the slots a slice of
+    ``seq_length`` steps must not start at -- the last ``seq_length - 1`` steps of every trajectory (all of a shorter one).
+    The reference lists them through a left-padded index matrix in "trajectory order" coordinates and shifts by the first
+    start when the ring is full; in storage coordinates that is simply ``stop - j`` (mod ring) for j < min(len, seq - 1).
+    Order: trajectory by trajectory, ascending within each, like the reference's boolean-mask read-out."""
+    out = []
+    for sp, ln in zip(np.asarray(stop, dtype=np.int64), np.asarray(length, dtype=np.int64)):
+        m = int(min(ln, seq_length - 1))
+        out.append((sp - np.arange(m - 1, -1, -1, dtype=np.int64)) % ring_length)
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+
+
+def prioritized_slice_sample(orc_sampler, start, stop, length, *, seq_length: int, num_slices: int, storage_len: int,
+                             u):
+    """PrioritizedSliceSampler.sample (:2890-3004) on an oracle.per_oracle.OraclePrioritizedSampler: zero the invalid
+    starts in the sum tree (:2910-2912), draw ``num_slices`` starts like PrioritizedSampler.sample (:2915-2917), restore
+    (:2918), expand (:2963-2966) and repeat the weights (:2969-2971).
+    Returns (index int64[S*T], weight fp32[S*T], truncated bool[S*T], starts int64[S])."""
+    bad = invalid_starts(stop, length, seq_length, storage_len)
+    tree = orc_sampler._sum_tree
+    vals = np.array(tree[bad], dtype=np.float32)
+    tree[bad] = np.zeros(len(bad), dtype=np.float32)
+    try:
+        import torch
+
+        starts, w = orc_sampler.sample(storage_len, num_slices, u=torch.as_tensor(np.asarray(u)))
+    finally:
+        tree[bad] = vals
+    starts = starts.numpy().astype(np.int64)
+    index = ((starts[:, None] + np.arange(seq_length, dtype=np.int64)[None, :]) % storage_len).reshape(-1)
+    weight = np.repeat(w.numpy(), seq_length)
+    truncated = np.zeros(num_slices * seq_length, dtype=bool)
+    truncated.reshape(num_slices, seq_length)[:, -1] = True
+    return index, weight, truncated, starts

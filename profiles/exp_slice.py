@@ -66,5 +66,30 @@ def main():
         del table, end, ids
 
 
+def buffers():
+    """rb.sample() through the public API: SliceSampler and PrioritizedSliceSampler on a 1M-slot ring, 32 slices x 64 steps
+    of Atari-shaped frames (28 KB rows), trajectory table cached between writes."""
+    from rl_b200.data import (LazyTensorStorage, PrioritizedSliceSampler, SliceSampler, TensorDict,
+                              TensorDictReplayBuffer)
+
+    L, S, T = 300_000, 32, 64
+    g = torch.Generator(device=dev).manual_seed(1)
+    for name, smp in (("SliceSampler", SliceSampler(num_slices=S, end_key=("next", "done"), cache_values=True)),
+                      ("PrioritizedSliceSampler", PrioritizedSliceSampler(L, 0.6, 0.4, num_slices=S,
+                                                                          end_key=("next", "done"), cache_values=True))):
+        rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device=dev), sampler=smp, batch_size=S * T, generator=g)
+        for lo in range(0, L, 50_000):
+            n = 50_000
+            rb.extend(TensorDict({"pixels": torch.randint(0, 255, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+                                  ("next", "done"): torch.rand(n, 1, device=dev, generator=g) < 0.005}, [n]))
+        rb.sample()
+        t = timed(rb.sample, 100)
+        bytes_ = 2 * S * T * 28225
+        print(f"{name:24s} rb.sample() {S}x{T} steps of 28 KB: {t:7.1f} us eager ({bytes_ / t / 1e3:6.0f} GB/s of rows, "
+              f"{S * T / t:5.1f} M steps/s)")
+        del rb
+
+
 if __name__ == "__main__":
     main()
+    buffers()

@@ -337,6 +337,27 @@ __global__ void __launch_bounds__(128) slice_index_kernel(const SliceParams P) {
   }
 }
 
+// ---- prioritized slices: starts that would run past the end of their trajectory get zero mass ------------------
+// PrioritizedSliceSampler zeroes them in the sum tree before every draw and restores them afterwards
+// (samplers.py:2854-2888, 2910-2918: two tree updates of n_traj * (seq - 1) items per sample).  Here the sampler draws
+// from a masked COPY of the leaves: this kernel zeroes the last min(len, seq - 1) leaves of every trajectory in the copy
+// (one warp per trajectory), rlb_tree_rebuild turns it into a tree, and the draw is the ordinary rlb_per_sample.
+template <typename T>
+__global__ void __launch_bounds__(128) slice_mask_starts_kernel(T *leaves, const int64_t *stop, const int64_t *length,
+                                                                 int64_t n_traj, int64_t seq_length,
+                                                                 int64_t ring_length) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= n_traj) return;
+  const int64_t sp = __ldg(stop + k), len = __ldg(length + k);
+  const int64_t m = len < seq_length - 1 ? len : seq_length - 1;
+  for (int64_t j = lane; j < m; j += 32) {
+    int64_t i = sp - j;
+    if (i < 0) i += ring_length;
+    leaves[i] = (T)0;
+  }
+}
+
 }  // namespace rlb
 
 using namespace rlb;
@@ -427,6 +448,24 @@ int rlb_slice_index(const int64_t *start, const int64_t *length, int64_t n_traj,
   const int wpb = 4;
   slice_index_kernel<<<(unsigned)((num_slices + wpb - 1) / wpb), 32 * wpb, 0, as_stream(stream)>>>(P);
   return check_launch("slice_index_kernel");
+}
+
+int rlb_slice_mask_starts(void *leaves, int dtype, const int64_t *stop, const int64_t *length, int64_t n_traj,
+                          int64_t seq_length, int64_t ring_length, rlb_stream_t stream) {
+  RLB_REQUIRE(n_traj >= 0 && seq_length > 0 && ring_length > 0, RLB_EINVAL, "rlb_slice_mask_starts: bad sizes");
+  if (n_traj == 0 || seq_length == 1) return RLB_OK;
+  RLB_REQUIRE(leaves && stop && length, RLB_EINVAL, "rlb_slice_mask_starts: null argument");
+  const int wpb = 4;
+  const unsigned blocks = (unsigned)((n_traj + wpb - 1) / wpb);
+  if (dtype == RLB_F32)
+    slice_mask_starts_kernel<float><<<blocks, 32 * wpb, 0, as_stream(stream)>>>((float *)leaves, stop, length, n_traj,
+                                                                              seq_length, ring_length);
+  else if (dtype == RLB_F64)
+    slice_mask_starts_kernel<double><<<blocks, 32 * wpb, 0, as_stream(stream)>>>((double *)leaves, stop, length, n_traj,
+                                                                               seq_length, ring_length);
+  else
+    RLB_REQUIRE(false, RLB_EINVAL, "rlb_slice_mask_starts: unsupported dtype %d", dtype);
+  return check_launch("slice_mask_starts_kernel");
 }
 
 }  // extern "C"

@@ -1,7 +1,8 @@
 """rl_b200.data -- mirror of ``torchrl.data``'s replay-buffer surface for the B200 hot path."""
 from .replay_buffers import (PrioritizedReplayBuffer, ReplayBuffer, TensorDictPrioritizedReplayBuffer,
                              TensorDictReplayBuffer)
-from .samplers import PrioritizedSampler, RandomSampler, Sampler, SamplerWithoutReplacement, SliceSampler
+from .samplers import (PrioritizedSampler, PrioritizedSliceSampler, RandomSampler, Sampler, SamplerWithoutReplacement,
+                       SliceSampler)
 from .segment_tree import (MinSegmentTreeFp32, MinSegmentTreeFp64, SumSegmentTreeFp32, SumSegmentTreeFp64)
 from .storages import LazyTensorStorage, ListStorage, Storage, TensorStorage
 from .tensordict_lite import TensorDict, is_tensor_collection
@@ -9,7 +10,7 @@ from .writers import RoundRobinWriter, TensorDictRoundRobinWriter, Writer
 
 __all__ = [
     "ReplayBuffer", "PrioritizedReplayBuffer", "TensorDictReplayBuffer", "TensorDictPrioritizedReplayBuffer",
-    "Sampler", "RandomSampler", "SamplerWithoutReplacement", "SliceSampler", "PrioritizedSampler", "Storage", "ListStorage", "TensorStorage",
+    "Sampler", "RandomSampler", "SamplerWithoutReplacement", "SliceSampler", "PrioritizedSliceSampler", "PrioritizedSampler", "Storage", "ListStorage", "TensorStorage",
     "LazyTensorStorage", "Writer", "RoundRobinWriter", "TensorDictRoundRobinWriter", "TensorDict",
     "is_tensor_collection", "SumSegmentTreeFp32", "SumSegmentTreeFp64", "MinSegmentTreeFp32", "MinSegmentTreeFp64",
 ]

@@ -299,7 +299,7 @@ class SliceSampler(Sampler):
         if not ((num_slices is None) ^ (slice_len is None)):
             raise TypeError("Either num_slices or slice_len must be not None, and not both. "
                             f"Got num_slices={num_slices} and slice_len={slice_len}.")
-        self._table_buf = self._counts = self._workspace = None
+        self._traj_buf = self._traj_counts = self._traj_ws = None
 
     def __repr__(self) -> str:
         return (f"{self.__class__.__name__}(num_slices={self.num_slices}, slice_len={self.slice_len}, "
@@ -389,15 +389,15 @@ class SliceSampler(Sampler):
             raise RuntimeError(_EMPTY_STORAGE_ERROR)
         dev = sig.device
         be = ops.backend()
-        if self._table_buf is None or self._table_buf.shape[1] < L or self._table_buf.device != dev:
+        if self._traj_buf is None or self._traj_buf.shape[1] < L or self._traj_buf.device != dev:
             size = max(L, getattr(storage, "max_size", L))
-            self._table_buf = torch.empty((3, size), dtype=torch.int64, device=dev)
-            self._counts = torch.zeros(2, dtype=torch.int64, device=dev)
-            self._workspace = be.traj_workspace(size, dev)
-        table = self._table_buf if not self.cache_values else torch.empty_like(self._table_buf)
-        be.traj_table(sig, by_id, L, at_capacity, cursor, seq_length, self.strict_length, table, self._counts,
-                      self._workspace)
-        n_all, n_long = (int(c) for c in self._counts.tolist())      # the one synchronisation of a table build
+            self._traj_buf = torch.empty((3, size), dtype=torch.int64, device=dev)
+            self._traj_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._traj_ws = be.traj_workspace(size, dev)
+        table = self._traj_buf if not self.cache_values else torch.empty_like(self._traj_buf)
+        be.traj_table(sig, by_id, L, at_capacity, cursor, seq_length, self.strict_length, table, self._traj_counts,
+                      self._traj_ws)
+        n_all, n_long = (int(c) for c in self._traj_counts.tolist())      # the one synchronisation of a table build
         out = (table, n_all, n_long)
         if self.cache_values:
             self._cache[key] = out
@@ -882,3 +882,114 @@ class PrioritizedSampler(Sampler):
             tree.load_leaves(torch.from_numpy(np.array(arr)))
         mp = metadata["_max_priority"]
         self._set_max_priority((mp[0], None if mp[1] is None else int(mp[1])))
+
+
+class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):
+    """Samples slices of data along the first dimension with prioritized START steps (samplers.py:2575-3028).
+
+    The start of every slice is drawn with probability proportional to its priority among the steps from which a whole
+    slice fits inside the trajectory; the slice then runs ``slice_len`` steps forward and every step carries the start's
+    importance weight.  Constructor arguments are those of :class:`PrioritizedSampler` followed by the keyword arguments
+    of :class:`SliceSampler` (``strict_length=True`` and ``span=False`` only; 1-d storages).
+
+    The reference forbids bad starts by zeroing their leaves in the sum tree before each draw and writing them back
+    afterwards -- two tree updates of ``n_trajectories * (slice_len - 1)`` items per sample, done index by index on the
+    host (:2910-2918).  Here the draw comes from a masked copy: one device copy of the sum tree's leaves,
+    ``rlb_slice_mask_starts`` (zero the last ``slice_len - 1`` leaves of every trajectory of the ``rlb_traj_table``),
+    ``rlb_tree_rebuild`` and the ordinary ``rlb_per_sample`` with the untouched min tree.  A tree built from the masked
+    leaves has, node for node, the values the reference's zero-and-recompute produces, so the sampled starts are the
+    reference's for the same uniform draws.
+    """
+
+    def __init__(self, max_capacity: int, alpha: float, beta: float, eps: float = 1e-8,
+                 dtype: torch.dtype = torch.float, reduction: str = "max", *, num_slices: int | None = None,
+                 slice_len: int | None = None, end_key=None, traj_key=None, ends: torch.Tensor | None = None,
+                 trajectories: torch.Tensor | None = None, cache_values: bool = False,
+                 truncated_key=("next", "truncated"), strict_length: bool = True, compile=False, span=False,
+                 max_priority_within_buffer: bool = False, device=None, semantics: str = "cpu"):
+        if not strict_length:
+            raise NotImplementedError("PrioritizedSliceSampler(strict_length=False) is not supported by the B200 engine")
+        SliceSampler.__init__(self, num_slices=num_slices, slice_len=slice_len, end_key=end_key, traj_key=traj_key,
+                              cache_values=cache_values, truncated_key=truncated_key, strict_length=strict_length,
+                              ends=ends, trajectories=trajectories, compile=compile, span=span)
+        PrioritizedSampler.__init__(self, max_capacity=max_capacity, alpha=alpha, beta=beta, eps=eps, dtype=dtype,
+                                    reduction=reduction, max_priority_within_buffer=max_priority_within_buffer,
+                                    device=device, semantics=semantics)
+        self._masked = None
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(num_slices={self.num_slices}, slice_len={self.slice_len}, "
+                f"end_key={self.end_key}, traj_key={self.traj_key}, truncated_key={self.truncated_key}, "
+                f"strict_length={self.strict_length}, alpha={self._alpha}, beta={self._beta}, eps={self._eps})")
+
+    # the priority bookkeeping is PrioritizedSampler's, the table cache SliceSampler's
+    def mark_update(self, index, *, storage: Storage | None = None) -> None:
+        return PrioritizedSampler.mark_update(self, index, storage=storage)
+
+    # add / extend: SliceSampler's (drop the cached table), which chain to PrioritizedSampler's through super()
+
+    def _empty(self) -> None:
+        SliceSampler._empty(self)
+        PrioritizedSampler._empty(self)
+
+    def dumps(self, path) -> None:
+        PrioritizedSampler.dumps(self, path)
+
+    def loads(self, path) -> None:
+        PrioritizedSampler.loads(self, path)
+
+    def state_dict(self) -> dict:
+        return PrioritizedSampler.state_dict(self)
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        PrioritizedSampler.load_state_dict(self, state_dict)
+
+    def sample(self, storage: Storage, batch_size: int) -> tuple[Any, dict]:
+        if storage.ndim != 1:
+            raise NotImplementedError("PrioritizedSliceSampler on the B200 engine supports 1-d storages only")
+        self._maybe_init_from_storage(storage)
+        length = len(storage)
+        if length == 0:
+            raise RuntimeError(_EMPTY_STORAGE_ERROR)
+        seq_length, num_slices = self._adjusted_batch_size(batch_size)
+        # every trajectory of the ring (no length filter: short ones are masked out whole)
+        keep, self.strict_length = self.strict_length, False
+        try:
+            table, n_all, _ = self._table(storage, seq_length)
+        finally:
+            self.strict_length = keep
+        be = ops.backend()
+        st, mt = self._sum_tree, self._min_tree
+        if self._masked is None or self._masked.shape != st.values.shape:
+            self._masked = torch.empty_like(st.values)
+        cap = st.capacity
+        self._masked[cap:].copy_(st.values[cap:])                                        # :2910 (vals = tree[idx])
+        be.slice_mask_starts(self._masked, cap, table[1], table[2], n_all, seq_length, storage.shape[0])   # :2911
+        be.tree_rebuild(self._masked, cap, False)
+        dev = st.device
+        u = torch.rand(num_slices, device=dev, generator=self._rng, dtype=st._dtype)       # PrioritizedSampler.sample
+        starts, weight = be.per_sample(self._masked, mt.values, self._max_capacity, cap, length, u, self._beta,
+                                       self._semantics == "cpu", status=self._status)
+        if self.record_index_event and dev.type == "cuda":
+            if self.index_ready is None:
+                self.index_ready = torch.cuda.Event()
+            self.index_ready.record(torch.cuda.current_stream(dev))
+        steps = torch.arange(seq_length, device=dev)
+        index = ((starts.unsqueeze(1) + steps) % storage.shape[0]).reshape(-1)            # :2963-2966
+        info: dict = {"priority_weight": weight.repeat_interleave(seq_length)}            # :2969-2971
+        if self.truncated_key is not None:
+            done_key = _replace_last(self.truncated_key, "done")
+            terminated_key = _replace_last(self.truncated_key, "terminated")
+            truncated = torch.zeros((num_slices, seq_length), dtype=torch.bool, device=dev)
+            truncated[:, -1] = True
+            truncated = truncated.reshape(-1, 1)
+            contents = storage[:]
+            have = {k: v for k, v in (("done", contents.get(done_key, None)),
+                                      ("terminated", contents.get(terminated_key, None))) if v is not None}
+            rows = dict(zip(have, be.gather(list(have.values()), index, length))) if have else {}
+            info[self.truncated_key] = truncated
+            done = rows.get("done")
+            info[done_key] = truncated.clone() if done is None else done.reshape(truncated.shape) | truncated
+            term = rows.get("terminated")
+            info[terminated_key] = torch.zeros_like(truncated) if term is None else term
+        return (index,), info

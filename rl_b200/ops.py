@@ -55,6 +55,7 @@ _SIGNATURES = {
     "rlb_traj_table_workspace_bytes": (_sz, [_i64]),
     "rlb_traj_table": (_i32, [_vp, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rlb_slice_index": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rlb_slice_mask_starts": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
     "rlb_tree_update_range": (_i32, [_vp, _vp, _i64, _i32, _i64, _i64, _i64, _i32, _vp, _f64, _f64, _f64, _i32, _vp,
                                      _vp, _vp]),
     "rlb_extend": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _f64,
@@ -426,6 +427,17 @@ class CudaBackend:
                                                int(pad_output), self._p(out_offset), self._p(index), self._p(trunc),
                                                self._p(mask), seq.data_ptr(), self._stream(dev)), "rlb_slice_index")
         return index, trunc, mask, seq
+
+    def slice_mask_starts(self, masked_tree: torch.Tensor, capacity: int, stop, length, n_traj: int, seq_length: int,
+                          ring_length: int) -> None:
+        """Zero, in the LEAF level of ``masked_tree`` (a copy of a sum tree), the starts from which a slice of
+        ``seq_length`` steps would leave its trajectory (``rlb_slice_mask_starts``)."""
+        dev = self._cuda(masked_tree, stop, length)
+        leaves = masked_tree[capacity:]
+        with self._Guard(dev):
+            self._check(self.L.rlb_slice_mask_starts(leaves.data_ptr(), _dtype_code(masked_tree.dtype), stop.data_ptr(),
+                                                     length.data_ptr(), n_traj, seq_length, ring_length,
+                                                     self._stream(dev)), "rlb_slice_mask_starts")
 
     # -- GAE ---------------------------------------------------------------------------------------
     def gae(self, v, nv, r, done, term, gamma: float, gammalmbda: float, rows: int, T: int, F: int):

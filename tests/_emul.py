@@ -207,6 +207,12 @@ class OracleBackend:
         return (torch.from_numpy(idx), torch.from_numpy(tr).reshape(-1, 1),
                 None if mask is None else torch.from_numpy(mask), seq)
 
+    def slice_mask_starts(self, masked_tree, capacity, stop, length, n_traj, seq_length, ring_length):
+        from oracle import slice_oracle as so
+
+        bad = so.invalid_starts(stop[:n_traj].numpy(), length[:n_traj].numpy(), seq_length, ring_length)
+        masked_tree[capacity + torch.from_numpy(bad)] = 0
+
     # ---- sharded minibatch trailer
     def shard_pack(self, rows, meta_offset, index, leaf, psum_pmin, index_base, peer_delta=None):
         m = meta_offset

@@ -79,3 +79,40 @@ def _oracle_slice(kwargs, data, length, max_size, last_cursor, batch_size, rec):
     return so.slice_index(start, lens, seq_length=seq, num_slices=num_slices, storage_length=max_size,
                           traj_draw=rec["traj"].numpy(), u=rec["u"].numpy(), strict_length=strict,
                           pad_output=kwargs.get("pad_output", False))
+
+
+def _pslice_scenarios():
+    """(L, filled, num_slices, seq_length, seed) for PrioritizedSliceSampler."""
+    return {"full_small": (60, 60, 4, 5, 0), "full": (400, 400, 8, 10, 1), "partial": (400, 250, 8, 10, 2),
+            "short_slices": (400, 400, 6, 3, 3), "long_slices": (1000, 1000, 4, 40, 4)}
+
+
+def _ref_pslice_run(R, L, filled, S, T, seed, draws=3):
+    """Run the unmodified PrioritizedSliceSampler; returns done flags, the sum/min leaves it sampled from and, per draw,
+    (u, index, weight, truncated)."""
+    from unittest import mock
+
+    m = R.mod
+    g = torch.Generator().manual_seed(seed)
+    done = torch.rand(L, 1, generator=g) < 0.06
+    st = R.make_storage({("next", "done"): done}, filled, L, None)
+    ref = m.PrioritizedSliceSampler(L, 0.7, 0.9, num_slices=S, end_key=("next", "done"))
+    ref._rng = torch.Generator().manual_seed(seed + 100)
+    ref.mark_update(torch.arange(filled), storage=st)
+    ref.update_priority(torch.arange(filled), torch.rand(filled, generator=g) * 3, storage=st)
+    sum_leaves = np.array([ref._sum_tree[i] for i in range(L)], dtype=np.float32)
+    min_leaves = np.array([ref._min_tree[i] for i in range(L)], dtype=np.float32)
+    out = []
+    real = torch.rand
+    for _ in range(draws):
+        rec = {}
+
+        def rand(*a, **k):
+            rec["u"] = real(*a, **k)
+            return rec["u"]
+
+        with mock.patch.object(m.torch, "rand", rand):
+            idx, info = ref.sample(st, S * T)
+        out.append((rec["u"].numpy(), idx[0].numpy(), info["priority_weight"].numpy(),
+                    info[("next", "truncated")].numpy().reshape(-1)))
+    return done.reshape(-1).numpy(), sum_leaves, min_leaves, out

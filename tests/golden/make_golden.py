@@ -128,6 +128,25 @@ def slice_cases():
     np.savez_compressed(OUT / "slice_golden.npz", **out)
 
 
+def pslice_cases():
+    """pslice_golden.npz: the reference's PrioritizedSliceSampler (samplers.py:2575-3028, unmodified, on the compiled
+    reference trees): the leaves it drew from, its uniform draws, and the slices / per-step weights it returned."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from _slice_cases import _pslice_scenarios, _ref_pslice_run
+    from oracle.ref_loader import reference_samplers
+
+    R = reference_samplers()
+    out = {}
+    for name, (L, filled, S, T, seed) in _pslice_scenarios().items():
+        done, sl, ml, draws = _ref_pslice_run(R, L, filled, S, T, seed)
+        out[f"{name}/meta"] = np.array([L, filled, S, T], dtype=np.int64)
+        out[f"{name}/done"], out[f"{name}/sum_leaves"], out[f"{name}/min_leaves"] = done, sl, ml
+        out[f"{name}/u"] = np.stack([d[0] for d in draws])
+        out[f"{name}/index"] = np.stack([d[1] for d in draws])
+        out[f"{name}/weight"] = np.stack([d[2] for d in draws])
+    np.savez_compressed(OUT / "pslice_golden.npz", **out)
+
+
 def per_cases():
     assert reference_ext("cpu") is not None
     out = {}
@@ -162,6 +181,7 @@ if __name__ == "__main__":
     td_cases()
     scan_cases()
     slice_cases()
+    pslice_cases()
     per_cases()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

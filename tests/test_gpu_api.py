@@ -337,3 +337,47 @@ def test_slice_sampler_buffer_on_device(cuda_backend, strict):
             assert torch.equal(batch.get("obs"), full.get("obs")[idx])
         assert rb.sampler._cache
     assert rb.storage._is_full
+
+
+def test_prioritized_slice_sampler_buffer_on_device(cuda_backend):
+    """TensorDictReplayBuffer + PrioritizedSliceSampler on the GPU at a 1M-slot ring: starts are the oracle's for the
+    draws of the buffer's CUDA generator and the device's own leaves; slices stay inside one trajectory; every step
+    carries its start's weight; the true priorities are untouched by sampling."""
+    from oracle import slice_oracle as so
+    from rl_b200.data import LazyTensorStorage, PrioritizedSliceSampler, TensorDict, TensorDictReplayBuffer
+
+    L, S, T = 1_000_000, 64, 32
+    g = torch.Generator(device=dev()).manual_seed(9)
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device=dev()), batch_size=S * T, generator=g,
+                                sampler=PrioritizedSliceSampler(L, 0.6, 0.4, num_slices=S, end_key=("next", "done"),
+                                                                cache_values=True))
+    rng = np.random.default_rng(2)
+    for n in (600_000, 400_000, 123_456):             # fills the ring, then wraps
+        done = torch.from_numpy(rng.random(n) < 0.01).reshape(n, 1).to(dev())
+        rb.extend(TensorDict({"t": torch.arange(n, device=dev()).reshape(n, 1), ("next", "done"): done}, [n]))
+        filled = len(rb)
+        ix = torch.from_numpy(rng.integers(0, filled, 50_000)).to(dev())
+        rb.update_priority(ix, torch.rand(50_000, device=dev(), generator=g) * 4)
+        before = rb.sampler._sum_tree.values.clone()
+        os_, om = _oracle_from(rb.sampler, L)
+        orc = po.OraclePrioritizedSampler(L, 0.6, 0.4)
+        orc._sum_tree, orc._min_tree = os_, om
+        stored_done = rb.storage.get(slice(None)).get(("next", "done")).reshape(-1).cpu().numpy()
+        cursor = rb.storage._last_cursor
+        cursor = cursor.stop - 1 if isinstance(cursor, slice) else int(cursor.reshape(-1)[-1])
+        start, stop, length = so.traj_table(end=stored_done, at_capacity=filled == L, cursor=cursor)
+        for _ in range(2):
+            state = g.get_state()
+            batch = rb.sample()
+            g.set_state(state)
+            u = torch.rand(S, device=dev(), generator=g)
+            oi, ow, otr, _ = so.prioritized_slice_sample(orc, start, stop, length, seq_length=T, num_slices=S,
+                                                         storage_len=filled, u=u.cpu().numpy())
+            idx = batch.get("index").reshape(-1).cpu().numpy()
+            np.testing.assert_array_equal(idx, oi)
+            np.testing.assert_allclose(batch.get("priority_weight").cpu().numpy(), ow, rtol=2e-6)
+            np.testing.assert_array_equal(batch.get(("next", "truncated")).reshape(-1).cpu().numpy(), otr)
+            assert not stored_done[idx.reshape(S, T)[:, :-1]].any()          # no slice crosses a trajectory end
+            w = batch.get("priority_weight").reshape(S, T)
+            assert (w == w[:, :1]).all()
+        assert torch.equal(rb.sampler._sum_tree.values, before)

@@ -730,6 +730,43 @@ def test_slice_index_golden_and_large(cuda_backend):
     assert not end[ix[:, :-1]].any()
 
 
+def test_prioritized_slice_golden(cuda_backend):
+    """PrioritizedSliceSampler's draw on the device -- masked copy of the leaves (rlb_slice_mask_starts), rebuild, the
+    ordinary PER sample -- with the leaves and uniform draws of the unmodified reference (tests/golden/pslice_golden.npz):
+    the masked heap is, node for node, the reference's zero-and-recompute tree, and the sampled starts are its starts."""
+    from oracle import slice_oracle as so
+    from rl_b200.data import PrioritizedSliceSampler
+
+    z = np.load(GOLD / "pslice_golden.npz")
+    for k in sorted({n.split("/")[0] for n in z.files}):
+        gt = lambda n: z[f"{k}/{n}"]
+        L, filled, S, T = (int(x) for x in gt("meta"))
+        smp = PrioritizedSliceSampler(L, 0.7, 0.9, num_slices=S, end_key=("next", "done"), device=dev())
+        smp._sum_tree.load_leaves(torch.from_numpy(gt("sum_leaves")).to(dev()))
+        smp._min_tree.load_leaves(torch.from_numpy(gt("min_leaves")).to(dev()))
+        cap = smp._sum_tree.capacity
+        done = torch.from_numpy(gt("done")[:filled]).to(dev())
+        table = torch.empty((3, L), dtype=torch.int64, device=dev())
+        counts = torch.zeros(2, dtype=torch.int64, device=dev())
+        cuda_backend.traj_table(done, False, filled, filled == L, -1, T, False, table, counts,
+                                cuda_backend.traj_workspace(L, dev()))
+        n_all = int(counts[0])
+        masked = smp._sum_tree.values.clone()
+        cuda_backend.slice_mask_starts(masked, cap, table[1], table[2], n_all, T, filled)
+        cuda_backend.tree_rebuild(masked, cap, False)
+        start, stop, length = so.traj_table(end=gt("done")[:filled], at_capacity=filled == L, cursor=None)
+        ot = po.OracleTree(L, False)
+        leaves = gt("sum_leaves").copy()
+        leaves[so.invalid_starts(stop, length, T, filled)] = 0
+        ot.load_leaves(leaves)
+        np.testing.assert_array_equal(masked.cpu().numpy()[1:], ot.values()[1:])
+        for d in range(gt("u").shape[0]):
+            u = torch.from_numpy(gt("u")[d]).to(dev())
+            starts, w = cuda_backend.per_sample(masked, smp._min_tree.values, L, cap, filled, u, 0.9, True)
+            np.testing.assert_array_equal(starts.cpu().numpy(), gt("index")[d].reshape(S, T)[:, 0])
+            np.testing.assert_allclose(w.cpu().numpy(), gt("weight")[d].reshape(S, T)[:, 0], rtol=2e-6)
+
+
 # ---------------------------------------------------------------------------------------------------- edge cases
 def test_empty_and_degenerate_inputs(cuda_backend):
     """Empty batches / rows / time axes are no-ops that return correctly shaped empties; arguments are validated."""

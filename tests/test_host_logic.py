@@ -544,3 +544,43 @@ def test_slice_sampler_contract(emul):
     rb2.extend(TensorDict({"t": torch.arange(L)}, [L]))
     t = rb2.sample().get("t").reshape(2, 4)
     assert (t[:, 1:] - t[:, :-1] == 1).all()
+
+
+@pytest.mark.parametrize("filled", [400, 250])
+def test_prioritized_slice_sampler_equals_live_reference(emul, ref_samplers, filled):
+    """PrioritizedSliceSampler in a TensorDictReplayBuffer (kernels emulated) against the UNMODIFIED reference class:
+    same starts, slices, per-step weights and flags for the same CPU generator seed, through writes, TD-error
+    write-backs and repeated draws."""
+    from rl_b200.data import PrioritizedSliceSampler
+
+    L, S, T = 400, 8, 10
+    g = torch.Generator().manual_seed(0)
+    done = torch.rand(L, 1, generator=g) < 0.06
+    kw = dict(num_slices=S, end_key=("next", "done"))
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device="cpu"), batch_size=S * T,
+                                sampler=PrioritizedSliceSampler(L, 0.7, 0.9, **kw),
+                                generator=torch.Generator().manual_seed(2), priority_key="td_error")
+    ref = ref_samplers.mod.PrioritizedSliceSampler(L, 0.7, 0.9, **kw)
+    ref._rng = torch.Generator().manual_seed(2)
+    obs = torch.arange(L, dtype=torch.float32).unsqueeze(-1)
+    rb.extend(TensorDict({("next", "done"): done[:filled], "obs": obs[:filled]}, [filled]))
+    st = ref_samplers.make_storage({("next", "done"): done, "obs": obs}, filled, L, range(0, filled))   # _last_cursor
+    ref.mark_update(torch.arange(filled), storage=st)
+    for rep in range(4):
+        ix = torch.randint(0, filled, (50,), generator=g)
+        pr = torch.rand(50, generator=g) * 3
+        rb.update_priority(ix, pr)
+        ref.update_priority(ix, pr, storage=st)
+        want_index, want_info = ref.sample(st, S * T)
+        got = rb.sample()
+        assert torch.equal(got.get("index").reshape(-1), want_index[0])
+        assert torch.equal(got.get("priority_weight").reshape(-1), want_info["priority_weight"])
+        for k in (("next", "truncated"), ("next", "done"), ("next", "terminated")):
+            assert torch.equal(got.get(k).reshape(-1), want_info[k].reshape(-1)), k
+        t = got.get("obs").reshape(S, T)
+        assert (t[:, 1:] - t[:, :-1] == 1).all() and not done[:filled][got.get("index").reshape(S, T)[:, :-1]].any()
+    # the true priorities were never altered by sampling
+    orc_leaves = torch.tensor([ref._sum_tree[i] for i in range(filled)])
+    assert torch.equal(rb.sampler._sum_tree.dump_leaves()[:filled].cpu(), orc_leaves)
+    with pytest.raises(NotImplementedError, match="strict_length=False"):
+        PrioritizedSliceSampler(L, 0.7, 0.9, num_slices=2, strict_length=False)

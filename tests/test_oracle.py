@@ -282,7 +282,8 @@ def test_vtrace_oracle_matches_live_reference(ref_funcs):
 
 
 # ------------------------------------------------------------------------------------------ SliceSampler
-from _slice_cases import _oracle_slice, _ref_slice_run, _slice_cases  # noqa: E402
+from _slice_cases import (_oracle_slice, _pslice_scenarios, _ref_pslice_run, _ref_slice_run,  # noqa: E402
+                          _slice_cases)
 
 
 @pytest.mark.parametrize("case", sorted(_slice_cases()))
@@ -325,3 +326,39 @@ def test_slice_golden_fixture():
         np.testing.assert_array_equal(otr, gt("truncated"))
         if pad:
             np.testing.assert_array_equal(omask, gt("mask"))
+
+
+def _oracle_pslice(done, sum_leaves, min_leaves, L, filled, S, T, u):
+    from oracle import slice_oracle as so
+
+    orc = po.OraclePrioritizedSampler(L, 0.7, 0.9)
+    orc._sum_tree.load_leaves(sum_leaves)
+    orc._min_tree.load_leaves(min_leaves)
+    start, stop, length = so.traj_table(end=done[:filled], at_capacity=filled == L, cursor=None)
+    return so.prioritized_slice_sample(orc, start, stop, length, seq_length=T, num_slices=S, storage_len=filled, u=u)
+
+
+@pytest.mark.parametrize("name", sorted(_pslice_scenarios()))
+def test_prioritized_slice_oracle_equals_live_reference(ref_samplers, name):
+    L, filled, S, T, seed = _pslice_scenarios()[name]
+    done, sl, ml, draws = _ref_pslice_run(ref_samplers, L, filled, S, T, seed)
+    for u, index, weight, truncated in draws:
+        oi, ow, otr, _ = _oracle_pslice(done, sl, ml, L, filled, S, T, u)
+        np.testing.assert_array_equal(oi, index)
+        np.testing.assert_array_equal(ow, weight)
+        np.testing.assert_array_equal(otr, truncated)
+
+
+def test_prioritized_slice_golden_fixture():
+    from pathlib import Path
+
+    z = np.load(Path(__file__).parent / "golden" / "pslice_golden.npz")
+    names = sorted({n.split("/")[0] for n in z.files})
+    assert len(names) == len(_pslice_scenarios())
+    for k in names:
+        gt = lambda n: z[f"{k}/{n}"]
+        L, filled, S, T = (int(x) for x in gt("meta"))
+        for d in range(gt("u").shape[0]):
+            oi, ow, otr, _ = _oracle_pslice(gt("done"), gt("sum_leaves"), gt("min_leaves"), L, filled, S, T, gt("u")[d])
+            np.testing.assert_array_equal(oi, gt("index")[d])
+            np.testing.assert_array_equal(ow, gt("weight")[d])
