@@ -2,7 +2,7 @@
 from .replay_buffers import (PrioritizedReplayBuffer, ReplayBuffer, TensorDictPrioritizedReplayBuffer,
                              TensorDictReplayBuffer)
 from .samplers import (PrioritizedSampler, PrioritizedSliceSampler, RandomSampler, Sampler, SamplerWithoutReplacement,
-                       SliceSampler)
+                       SliceSampler, SliceSamplerWithoutReplacement)
 from .segment_tree import (MinSegmentTreeFp32, MinSegmentTreeFp64, SumSegmentTreeFp32, SumSegmentTreeFp64)
 from .storages import LazyTensorStorage, ListStorage, Storage, TensorStorage
 from .tensordict_lite import TensorDict, is_tensor_collection
@@ -10,7 +10,7 @@ from .writers import RoundRobinWriter, TensorDictRoundRobinWriter, Writer
 
 __all__ = [
     "ReplayBuffer", "PrioritizedReplayBuffer", "TensorDictReplayBuffer", "TensorDictPrioritizedReplayBuffer",
-    "Sampler", "RandomSampler", "SamplerWithoutReplacement", "SliceSampler", "PrioritizedSliceSampler", "PrioritizedSampler", "Storage", "ListStorage", "TensorStorage",
+    "Sampler", "RandomSampler", "SamplerWithoutReplacement", "SliceSampler", "SliceSamplerWithoutReplacement", "PrioritizedSliceSampler", "PrioritizedSampler", "Storage", "ListStorage", "TensorStorage",
     "LazyTensorStorage", "Writer", "RoundRobinWriter", "TensorDictRoundRobinWriter", "TensorDict",
     "is_tensor_collection", "SumSegmentTreeFp32", "SumSegmentTreeFp64", "MinSegmentTreeFp32", "MinSegmentTreeFp64",
 ]

@@ -163,8 +163,11 @@ class SamplerWithoutReplacement(Sampler):
             self._sample_list = torch.arange(len_storage, device=device)
         self._count_remaining(batch_size)
 
+    def _storage_len(self, storage) -> int:
+        return len(storage)
+
     def sample(self, storage: Storage, batch_size: int) -> tuple[Any, dict]:
-        len_storage = len(storage)
+        len_storage = self._storage_len(storage)
         if len_storage == 0:
             raise RuntimeError(_EMPTY_STORAGE_ERROR)
         if self.len_storage != len_storage or self._sample_list is None:
@@ -403,6 +406,16 @@ class SliceSampler(Sampler):
             self._cache[key] = out
         return out
 
+    def _plan(self, storage, seq_length: int, num_slices: int):
+        """(table, n_trajectories a slice may come from, variable-length flag, trajectory ids or None = draw them)."""
+        table, n_all, n_long = self._table(storage, seq_length)
+        if self.strict_length:
+            if n_long == 0:
+                raise RuntimeError("Did not find a single trajectory with sufficient length "
+                                   f"(required={seq_length}, trajectories={n_all}).")
+            return table, n_long, False, None
+        return table, n_all, n_long < n_all, None
+
     def _adjusted_batch_size(self, batch_size: int) -> tuple[int, int]:
         if self.num_slices is not None:
             if batch_size % self.num_slices != 0:
@@ -419,16 +432,11 @@ class SliceSampler(Sampler):
         if storage.ndim != 1:
             raise NotImplementedError("SliceSampler on the B200 engine supports 1-d storages only")
         seq_length, num_slices = self._adjusted_batch_size(batch_size)
-        table, n_all, n_long = self._table(storage, seq_length)
-        if self.strict_length:
-            if n_long == 0:
-                raise RuntimeError("Did not find a single trajectory with sufficient length "
-                                   f"(required={seq_length}, trajectories={n_all}).")
-            n_traj, variable = n_long, False
-        else:
-            n_traj, variable = n_all, n_long < n_all
+        table, n_traj, variable, traj = self._plan(storage, seq_length, num_slices)
         dev = table.device
-        traj = torch.randint(n_traj, (num_slices,), device=dev, generator=self._rng)        # :1987-1990
+        if traj is None:
+            traj = torch.randint(n_traj, (num_slices,), device=dev, generator=self._rng)    # :1987-1990
+        num_slices = traj.numel()
         u = torch.rand(num_slices, device=dev, generator=self._rng)                          # :2099-2102
         be = ops.backend()
         storage_length = storage.shape[0]
@@ -882,6 +890,77 @@ class PrioritizedSampler(Sampler):
             tree.load_leaves(torch.from_numpy(np.array(arr)))
         mp = metadata["_max_priority"]
         self._set_max_priority((mp[0], None if mp[1] is None else int(mp[1])))
+
+
+class SliceSamplerWithoutReplacement(SliceSampler, SamplerWithoutReplacement):
+    """Samples slices of data along the first dimension, without replacement over TRAJECTORIES (samplers.py:2303-2573).
+
+    Every sweep visits each stored trajectory once (``torch.randperm(n_trajectories, generator)``, or storage order with
+    ``shuffle=False``); the position of the slice inside its trajectory is still drawn uniformly.  Keyword arguments are
+    those of :class:`SliceSampler` (``cache_values`` is always on, as in the reference) plus ``drop_last`` / ``shuffle`` of
+    :class:`SamplerWithoutReplacement`.  With ``strict_length`` the trajectories of a batch that are too short are
+    dropped from it, so a batch may hold fewer slices than asked (:2010-2025).
+    """
+
+    def __init__(self, *, num_slices: int | None = None, slice_len: int | None = None, drop_last: bool = False,
+                 end_key=None, traj_key=None, ends: torch.Tensor | None = None, trajectories: torch.Tensor | None = None,
+                 truncated_key=("next", "truncated"), strict_length: bool = True, shuffle: bool = True, compile=False,
+                 use_gpu=False):
+        SliceSampler.__init__(self, num_slices=num_slices, slice_len=slice_len, end_key=end_key, traj_key=traj_key,
+                              cache_values=True, truncated_key=truncated_key, strict_length=strict_length, ends=ends,
+                              trajectories=trajectories, compile=compile, use_gpu=use_gpu)
+        SamplerWithoutReplacement.__init__(self, drop_last=drop_last, shuffle=shuffle)
+        self._storage_len_buffer = 0
+
+    def __repr__(self) -> str:
+        perc = len(self._sample_list) / self.len_storage * 100 if self._sample_list is not None and self.len_storage else 0
+        return (f"{self.__class__.__name__}(num_slices={self.num_slices}, slice_len={self.slice_len}, "
+                f"end_key={self.end_key}, traj_key={self.traj_key}, truncated_key={self.truncated_key}, "
+                f"strict_length={self.strict_length},{perc}% sampled)")
+
+    def _empty(self) -> None:
+        self._cache = {}
+        SamplerWithoutReplacement._empty(self)
+
+    def _storage_len(self, storage) -> int:
+        return self._storage_len_buffer      # the sweep is over trajectories, not steps
+
+    def state_dict(self) -> dict:
+        return SamplerWithoutReplacement.state_dict(self)
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        SamplerWithoutReplacement.load_state_dict(self, state_dict)
+
+    def dumps(self, path) -> None:
+        SamplerWithoutReplacement.dumps(self, path)
+
+    def loads(self, path) -> None:
+        SamplerWithoutReplacement.loads(self, path)
+
+    def _plan(self, storage, seq_length: int, num_slices: int):
+        keep, self.strict_length = self.strict_length, False          # the sweep is over ALL trajectories of the ring
+        try:
+            table, n_all, n_long = self._table(storage, seq_length)
+        finally:
+            self.strict_length = keep
+        self._storage_len_buffer = n_all
+        traj, _ = SamplerWithoutReplacement.sample(self, storage, num_slices)           # :2540-2541
+        if not self.strict_length:
+            return table, n_all, n_long < n_all, traj
+        if n_long == n_all:
+            return table, n_all, False, traj
+        if n_long == 0:
+            raise RuntimeError("Did not find a single trajectory with sufficient length "
+                               f"(required={seq_length}, trajectories={n_all}).")
+        # drop the short trajectories of this batch and renumber the others within the long-enough ones (:2010-2025)
+        valid = table[2, :n_all] >= seq_length
+        picked = torch.zeros(n_all, dtype=torch.bool, device=valid.device)
+        picked[traj] = True
+        traj = picked[valid].nonzero().squeeze(-1)
+        if not traj.numel():
+            raise RuntimeError("None of the provided indices pointed to a trajectory of sufficient length. Consider "
+                               "using strict_length=False for the sampler instead.")
+        return table[:, :n_all][:, valid].contiguous(), n_long, False, traj
 
 
 class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):

@@ -381,3 +381,42 @@ def test_prioritized_slice_sampler_buffer_on_device(cuda_backend):
             w = batch.get("priority_weight").reshape(S, T)
             assert (w == w[:, :1]).all()
         assert torch.equal(rb.sampler._sum_tree.values, before)
+
+
+def test_slice_sampler_without_replacement_on_device(cuda_backend):
+    """A sweep of SliceSamplerWithoutReplacement on the GPU visits every stored trajectory exactly once (slices lie in
+    distinct trajectories until ran_out), slices are consecutive steps, and shuffle=False walks the ring in order."""
+    from oracle import slice_oracle as so
+    from rl_b200.data import LazyTensorStorage, SliceSamplerWithoutReplacement, TensorDict, TensorDictReplayBuffer
+
+    L, S, T = 20_000, 8, 4
+    rng = np.random.default_rng(4)
+    done = rng.random(L) < 0.02
+    done[::37] = False
+    length = so.traj_table(end=done, at_capacity=True, cursor=L - 1)[2]
+    for shuffle in (True, False):
+        rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device=dev()), batch_size=S * T,
+                                    generator=torch.Generator(device=dev()).manual_seed(0),
+                                    sampler=SliceSamplerWithoutReplacement(num_slices=S, end_key=("next", "done"),
+                                                                           shuffle=shuffle, strict_length=False))
+        rb.extend(TensorDict({"t": torch.arange(L, device=dev()).reshape(L, 1),
+                              ("next", "done"): torch.from_numpy(done).reshape(L, 1).to(dev())}, [L]))
+        start, stop, _ = so.traj_table(end=done, at_capacity=True, cursor=L - 1)
+        owner = np.empty(L, dtype=np.int64)                       # slot -> trajectory id
+        for k, (s0, e0) in enumerate(zip(start, stop)):
+            if s0 <= e0:
+                owner[s0:e0 + 1] = k
+            else:
+                owner[s0:] = k
+                owner[:e0 + 1] = k
+        seen = []
+        for _ in range(10_000):
+            b = rb.sample()
+            first = b.get("index").reshape(-1)[b.get(("next", "truncated")).reshape(-1).roll(1)].cpu().numpy()
+            seen.extend(owner[first].tolist())
+            if rb.sampler.ran_out:
+                break
+        assert sorted(seen) == list(range(len(start)))           # each trajectory exactly once per sweep
+        if not shuffle:
+            assert seen == list(range(len(start)))
+    assert (length > 0).all()

@@ -584,3 +584,41 @@ def test_prioritized_slice_sampler_equals_live_reference(emul, ref_samplers, fil
     assert torch.equal(rb.sampler._sum_tree.dump_leaves()[:filled].cpu(), orc_leaves)
     with pytest.raises(NotImplementedError, match="strict_length=False"):
         PrioritizedSliceSampler(L, 0.7, 0.9, num_slices=2, strict_length=False)
+
+
+@pytest.mark.parametrize("case", ["end_full", "strict_filter", "loose_variable", "traj_partial"])
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_slice_sampler_without_replacement_equals_live_reference(emul, ref_samplers, case, shuffle):
+    """SliceSamplerWithoutReplacement against the UNMODIFIED reference class, same CPU generator: a full sweep over the
+    trajectories and into the next one -- same slices, same ran_out sequence."""
+    from _slice_cases import _slice_cases
+    from rl_b200.data import SliceSamplerWithoutReplacement
+
+    kwargs, data, length, max_size, last_cursor, batch_size = _slice_cases()[case]
+    kwargs = {k: v for k, v in kwargs.items() if k != "pad_output"}
+    td = TensorDict({k: v[:length] for k, v in data.items()}, [length])
+    td.set("obs", torch.arange(length, dtype=torch.float32).unsqueeze(-1))
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(max_size, device="cpu"), batch_size=batch_size,
+                                sampler=SliceSamplerWithoutReplacement(shuffle=shuffle, **kwargs),
+                                generator=torch.Generator().manual_seed(4))
+    rb.extend(td)
+    ref = ref_samplers.mod.SliceSamplerWithoutReplacement(shuffle=shuffle, **kwargs)
+    ref._rng = torch.Generator().manual_seed(4)
+    cursor = rb.storage._last_cursor
+    st = ref_samplers.make_storage({k: v for k, v in data.items()}, length, max_size,
+                                   range(cursor.start, cursor.stop) if isinstance(cursor, slice) else cursor)
+    raised = 0
+    for _ in range(12):
+        try:
+            want_index, want_info = ref.sample(st, batch_size)
+        except RuntimeError as err:      # a batch of trajectories that are all too short: the reference gives up, so do we
+            assert "sufficient length" in str(err)
+            with pytest.raises(RuntimeError, match="sufficient length"):
+                rb.sample()
+            raised += 1
+            continue
+        got = rb.sample()
+        assert torch.equal(got.get("index").reshape(-1), want_index[0])
+        assert torch.equal(got.get(("next", "truncated")).reshape(-1), want_info[("next", "truncated")].reshape(-1))
+        assert rb.sampler.ran_out == ref.ran_out
+        assert torch.equal(got.get("obs").reshape(-1), want_index[0].float())
