@@ -16,7 +16,8 @@ import torch
 from torch import nn
 
 from ...data.tensordict_lite import is_tensor_collection
-from .functional import _gae_impl, gae_scalars
+from .functional import (_gae_impl, gae_scalars, td0_return_estimate, vec_td1_return_estimate,
+                         vec_td_lambda_return_estimate)
 
 
 @dataclass
@@ -147,8 +148,7 @@ class GAE(nn.Module):
                 and tensordict.get(tk.value_target, None) is not None:
             return tensordict
         reward = tensordict.get(_nk("next", tk.reward))
-        if tensordict.get(tk.steps_to_next_obs, None) is not None:
-            raise NotImplementedError("n-step gamma ** steps_to_next_obs needs per-step discounts (tensor gamma)")
+        steps = tensordict.get(tk.steps_to_next_obs, None)
         value, next_value = self._values(tensordict, params, target_params)
         done = tensordict.get(_nk("next", tk.done))
         terminated = tensordict.get(_nk("next", tk.terminated), None)
@@ -159,8 +159,15 @@ class GAE(nn.Module):
             reward = reward + self.gamma.to(reward.device) * value * truncated
             terminated = done
         td = self._get_time_dim(time_dim, tensordict)
-        adv, value_target = _gae_impl(None, None, value, next_value, reward, done, terminated, td,
-                                      scalars=self._scalars(value.dtype))
+        if steps is not None:
+            # n-step transitions: gamma ** steps_to_next_obs, one discount per step (advantages.py:1576-1578) --
+            # the per-step form of the scan (rlb_affine_scan)
+            gamma = self.gamma.to(reward.device) ** steps.view_as(reward)
+            adv, value_target = _gae_impl(gamma, self.lmbda.to(reward.device), value, next_value, reward, done,
+                                          terminated, td)
+        else:
+            adv, value_target = _gae_impl(None, None, value, next_value, reward, done, terminated, td,
+                                          scalars=self._scalars(value.dtype))
         if self.average_gae:
             loc = adv.mean()
             scale = adv.std().clamp_min(1e-4)
@@ -185,3 +192,109 @@ class GAE(nn.Module):
                                     done if terminated is None else terminated, td,
                                     scalars=self._scalars(value.dtype))
         return value_target
+
+
+class _ReturnEstimator(GAE):
+    """Shared plumbing of the TD(0) / TD(1) / TD(lambda) estimator modules (advantages.py:622-1336): same keys, same
+    ``forward`` (``value_target = value_estimate(...)``, ``advantage = value_target - value``), a different return."""
+
+    def __init__(self, *, gamma, lmbda=1.0, value_network=None, average_rewards: bool = False,
+                 differentiable: bool = False, vectorized: bool | None = None, skip_existing: bool | None = None,
+                 advantage_key=None, value_target_key=None, value_key=None, shifted: bool = False, device=None,
+                 time_dim: int | None = None, deactivate_vmap: bool = False, value_chunk_size: int | None = None):
+        super().__init__(gamma=gamma, lmbda=lmbda, value_network=value_network, differentiable=differentiable,
+                         vectorized=vectorized, skip_existing=skip_existing, advantage_key=advantage_key,
+                         value_target_key=value_target_key, value_key=value_key, shifted=shifted, device=device,
+                         time_dim=time_dim)
+        self.average_rewards = average_rewards
+
+    def _return(self, gamma, next_value, reward, done, terminated, time_dim):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def value_estimate(self, tensordict, params=None, target_params=None, next_value=None, time_dim: int | None = None,
+                       **kwargs):
+        tk = self.tensor_keys
+        reward = tensordict.get(_nk("next", tk.reward))
+        gamma = self.gamma.to(reward.device)
+        steps = tensordict.get(tk.steps_to_next_obs, None)
+        if steps is not None:
+            gamma = gamma ** steps.view_as(reward)
+        else:
+            gamma = float(self._scalars(reward.dtype)[0])
+        if self.average_rewards:
+            reward = reward - reward.mean()
+            reward = reward / reward.std().clamp_min(self._reward_std_floor)
+            tensordict.set(_nk("next", tk.reward), reward)    # the rewards are updated in place, like the reference
+        if next_value is None:
+            _, next_value = self._values(tensordict, params, target_params)
+        done = tensordict.get(_nk("next", tk.done))
+        terminated = tensordict.get(_nk("next", tk.terminated), None)
+        if terminated is None:
+            terminated = done
+        return self._return(gamma, next_value, reward, done, terminated, self._get_time_dim(time_dim, tensordict))
+
+    _reward_std_floor = 1e-4
+
+    @torch.no_grad()
+    def forward(self, tensordict, *, params=None, target_params=None, time_dim: int | None = None):
+        if not is_tensor_collection(tensordict):
+            raise TypeError(f"{type(self).__name__}.forward expects a TensorDict-like input")
+        if tensordict.batch_dims < 1:
+            raise RuntimeError("Expected input tensordict to have at least one dimensions, got"
+                               f"tensordict.batch_size = {tensordict.batch_size}")
+        tk = self.tensor_keys
+        if self.skip_existing and tensordict.get(tk.advantage, None) is not None \
+                and tensordict.get(tk.value_target, None) is not None:
+            return tensordict
+        value, next_value = self._values(tensordict, params, target_params)
+        value_target = self.value_estimate(tensordict, next_value=next_value, time_dim=time_dim)
+        tensordict.set(tk.advantage, value_target - value)
+        tensordict.set(tk.value_target, value_target)
+        return tensordict
+
+
+class TD0Estimator(_ReturnEstimator):
+    """Temporal Difference (TD(0)) estimate of advantage function, AKA bootstrapped temporal difference or 1-step return
+    (advantages.py:622-841): ``value_target = reward + gamma * not_terminated * next_value`` (elementwise)."""
+
+    _reward_std_floor = 1e-5
+
+    def __init__(self, *, gamma, value_network=None, **kwargs):
+        super().__init__(gamma=gamma, value_network=value_network, **kwargs)
+
+    def _return(self, gamma, next_value, reward, done, terminated, time_dim):
+        return td0_return_estimate(gamma=gamma, next_state_value=next_value, reward=reward, terminated=terminated,
+                                   done=done)
+
+
+class TD1Estimator(_ReturnEstimator):
+    r""":math:`\infty`-Temporal Difference (TD(1)) estimate of advantage function (advantages.py:844-1071): the
+    discounted return bootstrapped at trajectory ends -- the TD(lambda) scan kernel with lambda = 1."""
+
+    def __init__(self, *, gamma, value_network=None, **kwargs):
+        super().__init__(gamma=gamma, value_network=value_network, **kwargs)
+
+    def _return(self, gamma, next_value, reward, done, terminated, time_dim):
+        if isinstance(gamma, torch.Tensor):
+            raise NotImplementedError("TD1Estimator with steps_to_next_obs (per-step gamma) is not supported")
+        return vec_td1_return_estimate(gamma, next_value, reward, done=done, terminated=terminated, time_dim=time_dim)
+
+
+class TDLambdaEstimator(_ReturnEstimator):
+    r"""TD(:math:`\lambda`) estimate of advantage function (advantages.py:1074-1336): one ``rlb_td_lambda_return``
+    launch whichever ``vectorized`` says."""
+
+    def __init__(self, *, gamma, lmbda, value_network=None, **kwargs):
+        super().__init__(gamma=gamma, lmbda=lmbda, value_network=value_network, **kwargs)
+
+    def _return(self, gamma, next_value, reward, done, terminated, time_dim):
+        if isinstance(gamma, torch.Tensor):
+            raise NotImplementedError("TDLambdaEstimator with steps_to_next_obs (per-step gamma) is not supported")
+        return vec_td_lambda_return_estimate(gamma, self._lmbda_host(), next_value, reward, done=done, terminated=terminated,
+                                             time_dim=time_dim)
+
+    def _lmbda_host(self) -> float:
+        if "lmbda" not in self._scalar_cache:           # one host read, at first use
+            self._scalar_cache["lmbda"] = float(self.lmbda.cpu())
+        return self._scalar_cache["lmbda"]

@@ -622,3 +622,60 @@ def test_slice_sampler_without_replacement_equals_live_reference(emul, ref_sampl
         assert torch.equal(got.get(("next", "truncated")).reshape(-1), want_info[("next", "truncated")].reshape(-1))
         assert rb.sampler.ran_out == ref.ran_out
         assert torch.equal(got.get("obs").reshape(-1), want_index[0].float())
+
+
+def test_td_estimator_modules_and_nstep_gae(emul, ref_funcs):
+    """TD0Estimator / TD1Estimator / TDLambdaEstimator (advantages.py:622-1336) write value_target = the functional's
+    return and advantage = value_target - value; GAE with steps_to_next_obs uses gamma ** steps per step (:1576-1578)."""
+    from rl_b200.objectives.value import GAE, TD0Estimator, TD1Estimator, TDLambdaEstimator
+
+    g = torch.Generator().manual_seed(0)
+    B, T = 6, 20
+    v, nv, r = (torch.randn(B, T, 1, generator=g) for _ in range(3))
+    term = torch.rand(B, T, 1, generator=g) < 0.05
+    done = term | (torch.rand(B, T, 1, generator=g) < 0.05)
+
+    def make():
+        return TensorDict({"state_value": v.clone(), "next": {"state_value": nv.clone(), "reward": r.clone(),
+                                                              "done": done.clone(), "terminated": term.clone()}}, [B, T])
+
+    td = TDLambdaEstimator(gamma=0.98, lmbda=0.9, value_network=None)(make())
+    want = ref_funcs.td_lambda_return_estimate(0.98, 0.9, nv, r, done=done, terminated=term)
+    torch.testing.assert_close(td.get("value_target"), want, rtol=1e-5, atol=1e-5)
+    assert torch.equal(td.get("advantage"), td.get("value_target") - v)
+    td = TD1Estimator(gamma=0.98, value_network=None)(make())
+    torch.testing.assert_close(td.get("value_target"), ref_funcs.td1_return_estimate(0.98, nv, r, done=done, terminated=term),
+                               rtol=1e-5, atol=1e-5)
+    td = TD0Estimator(gamma=0.98, value_network=None)(make())
+    torch.testing.assert_close(td.get("value_target"), ref_funcs.td0_return_estimate(0.98, nv, r, term))
+    est = TDLambdaEstimator(gamma=0.98, lmbda=0.9, value_network=None, advantage_key="adv", value_target_key="ret",
+                            average_rewards=True)
+    td = est(make())
+    assert "adv" in td.keys() and "ret" in td.keys() and est.out_keys == ["adv", "ret"]
+    rn = (r - r.mean()) / r.std().clamp_min(1e-4)
+    torch.testing.assert_close(td.get(("next", "reward")), rn)           # rewards are normalised in place, as upstream
+    torch.testing.assert_close(td.get("ret"), ref_funcs.td_lambda_return_estimate(0.98, 0.9, nv, rn, done=done, terminated=term),
+                               rtol=1e-5, atol=1e-5)
+    # critic given: called on the data and on its "next"
+    calls = []
+
+    def critic(t):
+        calls.append(1)
+        t.set("state_value", t.get("obs") * 2)
+
+    data = make()
+    data.set("obs", v.clone())
+    data.get("next").set("obs", nv.clone())
+    td = TD0Estimator(gamma=0.9, value_network=critic)(data)
+    assert len(calls) == 2
+    torch.testing.assert_close(td.get("value_target"), r + 0.9 * (~term).int() * (nv * 2))
+    # n-step transitions
+    data = make()
+    steps = torch.randint(1, 4, (B, T, 1), generator=g)
+    data.set("steps_to_next_obs", steps)
+    out = GAE(gamma=0.97, lmbda=0.9, value_network=None)(data)
+    gam = torch.tensor(0.97) ** steps
+    want_adv, want_tgt = ref_funcs.vec_generalized_advantage_estimate(gam, torch.tensor(0.9), v, nv, r, done=done,
+                                                                      terminated=term)
+    torch.testing.assert_close(out.get("advantage"), want_adv, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out.get("value_target"), want_tgt, rtol=1e-4, atol=1e-4)
