@@ -17,10 +17,12 @@ never leave the device.
 """
 from __future__ import annotations
 
+import collections
 import contextlib
 import json
 import threading
 import warnings
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Any, Callable
 
@@ -70,8 +72,11 @@ class ReplayBuffer:
         batch_size (int): default batch size of :meth:`sample`.
         dim_extend (int): which dim of the data ``extend`` iterates over (defaults to ``storage.ndim - 1``).
         generator (torch.Generator): random generator shared by storage, sampler and writer.
-        pin_memory, prefetch, transform, shared, compilable, delayed_init: accepted for signature
-            compatibility; anything but the default raises ``NotImplementedError`` (off the hot path).
+        prefetch (int, optional): number of next batches prepared by a thread pool (replay_buffers.py:340-341,
+            1155-1164).  With an HBM-resident buffer every launch is already asynchronous, so this only hides the
+            python / launch latency of ``_sample``; worker threads launch on their own current stream.
+        pin_memory, transform, shared, compilable, delayed_init: accepted for signature compatibility; anything but
+            the default raises ``NotImplementedError`` (off the hot path).
     """
 
     def __init__(self, *, storage=None, sampler=None, writer=None, collate_fn: Callable | None = None,
@@ -79,7 +84,7 @@ class ReplayBuffer:
                  batch_size: int | None = None, dim_extend: int | None = None, checkpointer=None,
                  generator: torch.Generator | None = None, shared: bool = False, compilable: bool | None = None,
                  delayed_init: bool | None = None) -> None:
-        for name, val in (("prefetch", prefetch), ("transform", transform), ("transform_factory", transform_factory),
+        for name, val in (("transform", transform), ("transform_factory", transform_factory),
                           ("shared", shared), ("pin_memory", pin_memory), ("delayed_init", delayed_init)):
             if val:
                 raise NotImplementedError(
@@ -87,6 +92,11 @@ class ReplayBuffer:
         if dim_extend is not None and dim_extend < 0:
             raise ValueError("dim_extend must be a positive value.")
         self._batch_size = batch_size
+        self._prefetch = bool(prefetch)
+        self._prefetch_cap = prefetch or 0
+        self._prefetch_queue = collections.deque()
+        self._prefetch_executor = ThreadPoolExecutor(max_workers=self._prefetch_cap) if self._prefetch else None
+        self._futures_lock = threading.RLock()
         self._replay_lock = threading.RLock()
         self._write_lock = contextlib.nullcontext()
         self.shared = False
@@ -274,7 +284,14 @@ class ReplayBuffer:
                 "batch_size not specified. You can specify the batch_size when constructing the replay buffer, "
                 "or pass it to the sample method. Refer to the ReplayBuffer documentation for a proper usage of "
                 "the batch-size arguments.")
-        data, info = self._sample(batch_size)
+        if not self._prefetch:
+            data, info = self._sample(batch_size)
+        else:
+            with self._futures_lock:
+                while (len(self._prefetch_queue) < min(self._sampler._remaining_batches, self._prefetch_cap)
+                       and not self._sampler.ran_out) or not len(self._prefetch_queue):
+                    self._prefetch_queue.append(self._prefetch_executor.submit(self._sample, batch_size))
+                data, info = self._prefetch_queue.popleft().result()
         if return_info:
             dev = getattr(self.storage, "device", None)
             if dev is not None and dev != "auto":

@@ -679,3 +679,23 @@ def test_td_estimator_modules_and_nstep_gae(emul, ref_funcs):
                                                                       terminated=term)
     torch.testing.assert_close(out.get("advantage"), want_adv, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(out.get("value_target"), want_tgt, rtol=1e-4, atol=1e-4)
+
+
+def test_prefetch_thread_pool(emul):
+    """ReplayBuffer(prefetch=k) (replay_buffers.py:340-341, 1155-1164): batches come from a queue fed by worker threads;
+    a without-replacement sweep still yields every item exactly once and stops at ran_out."""
+    from rl_b200.data import SamplerWithoutReplacement
+
+    n = 40
+    rb = TensorDictPrioritizedReplayBuffer(alpha=0.6, beta=0.4, storage=LazyTensorStorage(n, device="cpu"), batch_size=8,
+                                           prefetch=2, generator=torch.Generator().manual_seed(0))
+    rb.extend(TensorDict({"obs": torch.arange(n, dtype=torch.float32).unsqueeze(-1), "td_error": torch.rand(n)}, [n]))
+    for _ in range(6):
+        b = rb.sample()
+        assert torch.equal(b.get("obs").reshape(-1), b.get("index").reshape(-1).float())
+        assert 1 <= len(rb._prefetch_queue) <= 2                       # the queue is topped up behind the consumer
+    rb2 = TensorDictReplayBuffer(storage=LazyTensorStorage(n, device="cpu"), batch_size=8, prefetch=3,
+                                 sampler=SamplerWithoutReplacement(), generator=torch.Generator().manual_seed(0))
+    rb2.extend(TensorDict({"obs": torch.arange(n, dtype=torch.float32).unsqueeze(-1)}, [n]))
+    seen = torch.cat([rb2.sample().get("index").reshape(-1) for _ in range(5)])
+    assert sorted(seen.tolist()) == list(range(n))
