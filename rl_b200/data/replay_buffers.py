@@ -8,7 +8,7 @@
 Same constructor keywords, method names, locking (one RLock around sampler + storage access), info
 packing and error messages for the calls on the hot path: ``add / extend / sample / update_priority /
 update_tensordict_priority / mark_update / empty / set_rng / state_dict / dumps / loads``.  Orchestration
-features that are not on the path (transforms, prefetch threads, shared-memory multiprocessing, ensembles,
+features that are not on the path (transforms, shared-memory multiprocessing, ensembles,
 remote / Ray buffers) are out of scope -- see DESIGN.md.
 
 With a CUDA ``LazyTensorStorage`` and a ``PrioritizedSampler`` a ``sample()`` is three launches --
