@@ -91,10 +91,15 @@ __device__ __forceinline__ int64_t fix_index(int64_t ix, int64_t len, int32_t *s
   return ix;
 }
 
+// IMPLICIT (write path only): no index array, slot = (ibase + b) mod len
+template <bool IMPLICIT>
 __device__ __forceinline__ int64_t load_index(const GatherParams &P, int64_t b) {
-  if (P.index) return __ldg(P.index + b);
-  const int64_t ix = P.ibase + b;
-  return ix >= P.len ? ix - P.len : ix;
+  if constexpr (!IMPLICIT) {
+    return __ldg(P.index + b);
+  } else {
+    const int64_t ix = P.ibase + b;
+    return ix >= P.len ? ix - P.len : ix;
+  }
 }
 
 // ---- vector role -------------------------------------------------------------------------------------
@@ -123,7 +128,7 @@ __device__ __forceinline__ void st_stream<uint16_t>(uint16_t *p, uint16_t v) {
   *p = v;
 }
 
-template <typename V, bool SCATTER>
+template <typename V, bool SCATTER, bool IMPLICIT>
 __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams &P, int64_t tile_in_leaf) {
   const int64_t u0 = tile_in_leaf * kTileUnits + threadIdx.x;
   int64_t b[kVecUnroll], ix[kVecUnroll];
@@ -142,7 +147,7 @@ __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams
       b[k] = ok[k] ? u / L.upr : 0;
       j[k] = ok[k] ? (uint32_t)(u - b[k] * L.upr) : 0;
     }
-    ix[k] = ok[k] ? load_index(P, b[k]) : 0;
+    ix[k] = ok[k] ? load_index<IMPLICIT>(P, b[k]) : 0;
   }
   V val[kVecUnroll];
 #pragma unroll
@@ -163,7 +168,7 @@ __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams
   }
 }
 
-template <bool SCATTER>
+template <bool SCATTER, bool IMPLICIT = false>
 __device__ __forceinline__ void vector_role(const GatherParams &P, int64_t first_tile, int64_t tile_stride) {
   for (int64_t tile = first_tile; tile < P.vec_tiles; tile += tile_stride) {
     int l = -1;
@@ -174,11 +179,11 @@ __device__ __forceinline__ void vector_role(const GatherParams &P, int64_t first
     const GatherLeaf &L = P.leaf[l];
     const int64_t t = tile - L.first;
     switch (L.vec_log2) {
-      case 4: vec_tile<uint4, SCATTER>(L, P, t); break;
-      case 3: vec_tile<uint2, SCATTER>(L, P, t); break;
-      case 2: vec_tile<uint32_t, SCATTER>(L, P, t); break;
-      case 1: vec_tile<uint16_t, SCATTER>(L, P, t); break;
-      default: vec_tile<uint8_t, SCATTER>(L, P, t); break;
+      case 4: vec_tile<uint4, SCATTER, IMPLICIT>(L, P, t); break;
+      case 3: vec_tile<uint2, SCATTER, IMPLICIT>(L, P, t); break;
+      case 2: vec_tile<uint32_t, SCATTER, IMPLICIT>(L, P, t); break;
+      case 1: vec_tile<uint16_t, SCATTER, IMPLICIT>(L, P, t); break;
+      default: vec_tile<uint8_t, SCATTER, IMPLICIT>(L, P, t); break;
     }
   }
 }
@@ -193,7 +198,7 @@ struct PipeSmem {
 
 constexpr size_t kPipeHeaderBytes = (sizeof(PipeSmem) * kPipes + 1023) / 1024 * 1024;
 
-template <bool SCATTER>
+template <bool SCATTER, bool IMPLICIT = false>
 __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, PipeSmem *ps, int cta) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -225,7 +230,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
   int64_t off = byte_in_leaf - b * P.leaf[l].row_bytes;
   // index window: lane j holds index[win0 + j]
   int64_t win0 = b;
-  int64_t my_ix = (win0 + lane < P.B) ? load_index(P, win0 + lane) : 0;
+  int64_t my_ix = (win0 + lane < P.B) ? load_index<IMPLICIT>(P, win0 + lane) : 0;
 
   int64_t n_loaded = 0, n_stored = 0;
   bool more = true;
@@ -235,7 +240,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
       const GatherLeaf &L = P.leaf[l];
       if (b >= win0 + 32) {  // warp-uniform: refill the index window
         win0 = b;
-        my_ix = (win0 + lane < P.B) ? load_index(P, win0 + lane) : 0;
+        my_ix = (win0 + lane < P.B) ? load_index<IMPLICIT>(P, win0 + lane) : 0;
       }
       int64_t ix = __shfl_sync(0xffffffffu, my_ix, (int)(b - win0));
       ix = fix_index(ix, P.len, lane == 0 ? P.status : nullptr);
@@ -274,7 +279,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
         b = 0;
         off = 0;
         win0 = 0;
-        my_ix = (lane < P.B) ? load_index(P, lane) : 0;
+        my_ix = (lane < P.B) ? load_index<IMPLICIT>(P, lane) : 0;
       }
     }
     // ---- retire the oldest staged piece: wait for its bytes, then DMA it out
@@ -323,10 +328,10 @@ __global__ void __launch_bounds__(kRangeThreads) extend_kernel(const __grid_cons
   if (threadIdx.x >= kGatherThreads) return;  // the row roles are written for kGatherThreads threads
   const int cta = (int)blockIdx.x - tree_ctas, row_ctas = (int)gridDim.x - tree_ctas;
   if (cta < P.bulk_ctas) {
-    bulk_role<true>(P, gsmem + kPipeHeaderBytes, reinterpret_cast<PipeSmem *>(gsmem), cta);
+    bulk_role<true, true>(P, gsmem + kPipeHeaderBytes, reinterpret_cast<PipeSmem *>(gsmem), cta);
     return;
   }
-  vector_role<true>(P, (int64_t)cta - P.bulk_ctas, row_ctas - P.bulk_ctas);
+  vector_role<true, true>(P, (int64_t)cta - P.bulk_ctas, row_ctas - P.bulk_ctas);
 }
 
 constexpr size_t kBulkSmemBytes = kPipeHeaderBytes + (size_t)kPipes * kStages * kChunk;
