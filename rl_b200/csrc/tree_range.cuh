@@ -111,7 +111,10 @@ __device__ __forceinline__ void range_role(const RangeParams &R, int cta, int nc
     if (R.mode == kRangePriority) {
       p = __ldg(static_cast<const float *>(R.value));
     } else {
-      p = R.has_max ? pow_like_torch(add_rn(ld_cg(R.max_buf), R.eps), R.alpha) : R.first_default;
+      // "no priority seen yet" is decided on the device (the running max is still -inf), not by the host's flag, so
+      // that a launch captured in a CUDA graph stays right when it is replayed after priorities have arrived
+      const float mx = ld_cg(R.max_buf);
+      p = (R.has_max && mx > -INFINITY) ? pow_like_torch(add_rn(mx, R.eps), R.alpha) : R.first_default;
     }
     v = (T)pow_like_torch(add_rn(p, R.eps), R.alpha);
     if (R.max_buf && tid == 0) {  // publish the new running max once every CTA has read the old one

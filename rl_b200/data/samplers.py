@@ -652,9 +652,13 @@ class PrioritizedSampler(Sampler):
     def default_priority(self):
         # (max_priority + eps) ** alpha, max_priority = 1 before any update (samplers.py:886-893).
         # NB: mark_update feeds this through update_priority, which applies (. + eps) ** alpha AGAIN.
+        first = (1 + self._eps) ** self._alpha
         if not self._has_max_priority:
-            return (1 + self._eps) ** self._alpha
-        return (self._max_priority_buf[0] + self._eps) ** self._alpha
+            return first
+        mx = self._max_priority_buf[0]
+        # (the running max is still -inf if every index of the updates so far was a "skip" marker: the reference
+        # returns early then and keeps max_priority = None, samplers.py:1040-1052)
+        return torch.where(mx > float("-inf"), (mx + self._eps) ** self._alpha, mx.new_full((), first))
 
     # ---- sample (samplers.py:895-956) --------------------------------------------------------------
     def sample(self, storage: Storage, batch_size: int) -> tuple[Any, dict]:
@@ -805,9 +809,10 @@ class PrioritizedSampler(Sampler):
             return None
         if self._range_ticket is None:
             self._range_ticket = torch.zeros(1, dtype=torch.int32, device=self._sum_tree.device)
+        # has_max=True: the kernel itself checks whether the running max is still -inf (no priority seen yet)
         rng = ops.RangeUpdate(self._sum_tree.values, self._min_tree.values, self._sum_tree.capacity,
                               ops.RANGE_DEFAULT, alpha=self._alpha, eps=self._eps,
-                              first_default=(1 + self._eps) ** self._alpha, has_max=self._has_max_priority,
+                              first_default=(1 + self._eps) ** self._alpha, has_max=True,
                               max_buf=self._max_priority_buf, ticket=self._range_ticket)
         self._has_max_priority = True   # the kernel about to be launched publishes the new running max
         return rng

@@ -161,7 +161,7 @@ class OracleBackend:
             return self.tree_update(rng.sum, rng.mn, rng.capacity, index, rng.value.reshape(1), None, 0)
         if rng.mode == 1:
             p = rng.value.reshape(()).to(torch.float32)
-        elif rng.has_max:
+        elif rng.has_max and bool(rng.max_buf[0] > float("-inf")):
             p = (rng.max_buf[0] + rng.eps) ** rng.alpha                     # samplers.py:886-893
         else:
             p = torch.as_tensor(rng.first_default, dtype=torch.float32)

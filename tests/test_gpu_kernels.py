@@ -161,6 +161,36 @@ def test_range_default_priority_matches_oracle_sampler(cuda_backend, alpha):
     assert int(smp._range_ticket.item()) == 0
 
 
+def test_range_default_follows_the_running_max_on_replay(cuda_backend):
+    """The range kernel decides "no priority seen yet" on the device: a launch captured before any priority exists
+    gives the initial default, and the SAME graph replayed after a write-back gives (max + eps) ** alpha; updates made of
+    "skip" markers only leave the max unset, as in the reference."""
+    from rl_b200.data import PrioritizedSampler
+
+    N = 1000
+    smp = PrioritizedSampler(N, 1.0, 0.4, device=dev())
+    smp.update_priority(torch.tensor([-1, -1], device=dev()), torch.tensor([3.0, 4.0], device=dev()))   # skips only
+    side = torch.cuda.Stream(dev())
+    gr = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(gr, stream=side):
+            smp.mark_update_range(0, 100, N)
+    gr.replay()
+    torch.cuda.synchronize()
+    eps = np.float32(1e-8)
+    first = np.float32(np.float32(1 + 1e-8) + eps)
+    leaves = smp._sum_tree.dump_leaves().cpu().numpy()
+    assert (leaves[:100] == first).all() and (leaves[100:] == 0).all()
+    smp.update_priority(torch.tensor([5], device=dev()), torch.tensor([7.0], device=dev()))
+    gr.replay()
+    torch.cuda.synchronize()
+    leaves = smp._sum_tree.dump_leaves().cpu().numpy()
+    want = np.float32(np.float32(np.float32(7.0) + eps) + eps)
+    assert (leaves[:100] == want).all()
+    assert float(smp._max_priority_buf[0]) == float(np.float32(np.float32(7.0) + eps))   # the default itself is a raw priority
+
+
 def test_tree_kat_and_queries(cuda_backend):
     # test/rb/test_prioritized.py:113-140
     from rl_b200.data.segment_tree import MinSegmentTreeFp32, SumSegmentTreeFp32

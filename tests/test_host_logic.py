@@ -699,3 +699,22 @@ def test_prefetch_thread_pool(emul):
     rb2.extend(TensorDict({"obs": torch.arange(n, dtype=torch.float32).unsqueeze(-1)}, [n]))
     seen = torch.cat([rb2.sample().get("index").reshape(-1) for _ in range(5)])
     assert sorted(seen.tolist()) == list(range(n))
+
+
+def test_default_priority_after_skip_only_update(emul):
+    """update_priority with only negative ("skip") indices leaves max_priority unset in the reference (samplers.py:1040-1052):
+    the next writer batch still gets the initial default priority, through both write paths."""
+    from rl_b200.data import PrioritizedSampler
+
+    orc = po.OraclePrioritizedSampler(50, 0.6, 0.4)
+    orc.update_priority(torch.tensor([-1, -1]), torch.tensor([3.0, 4.0]))
+    orc.mark_update(torch.arange(10))
+    for fused in (True, False):
+        smp = PrioritizedSampler(50, 0.6, 0.4, device="cpu")
+        smp.update_priority(torch.tensor([-1, -1]), torch.tensor([3.0, 4.0]))
+        if fused:
+            smp.mark_update_range(0, 10, 50)
+        else:
+            smp.mark_update(torch.arange(10))
+        np.testing.assert_array_equal(smp._sum_tree.values.numpy()[1:], orc._sum_tree.values()[1:])
+        assert float(smp._max_priority_buf[0]) == float(orc._max_priority)
