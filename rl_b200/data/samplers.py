@@ -531,6 +531,12 @@ class PrioritizedSampler(Sampler):
         #: with the storage gather that follows on the sampling stream.
         self.record_index_event = False
         self.index_ready = None
+        #: when set to True, each ``sample`` also draws the uniforms of the NEXT one (same generator calls, same order)
+        #: so that the RNG kernel is not the first thing a sample has to wait for; only worth it for captured /
+        #: multi-stream steps, and only if nothing else consumes the generator between two samples.
+        self.predraw = False
+        self._u_next = None
+        self._u_ready = 0
         self._has_max_priority = False
         self._max_priority_index = None
         if self._device is not None:
@@ -667,10 +673,15 @@ class PrioritizedSampler(Sampler):
         if length == 0:
             raise RuntimeError(_EMPTY_STORAGE_ERROR)
         dev = self._sum_tree.device
-        u = torch.rand(batch_size, device=dev, generator=self._rng, dtype=self._sum_tree._dtype)
+        u = self._draw(batch_size, dev)
         index, weight = ops.backend().per_sample(
             self._sum_tree.values, self._min_tree.values, self._max_capacity, self._sum_tree.capacity, length, u,
             self._beta, self._semantics == "cpu", status=self._status)
+        if self.predraw:
+            # the NEXT call's uniforms, drawn now: the same torch.rand calls in the same order, but off the critical
+            # path of the next sample (it only has to wait for the priority write-back, not for an RNG kernel first)
+            torch.rand(batch_size, device=dev, generator=self._rng, dtype=u.dtype, out=self._u_next)
+            self._u_ready = batch_size
         if self.record_index_event and dev.type == "cuda":
             if self.index_ready is None:
                 self.index_ready = torch.cuda.Event()
@@ -678,6 +689,22 @@ class PrioritizedSampler(Sampler):
         if storage.ndim > 1:
             index = unravel_index(index, storage.shape)
         return index, {"priority_weight": weight}
+
+    def _draw(self, batch_size: int, dev) -> torch.Tensor:
+        """``torch.rand(batch_size, generator)`` -- the reference's call (samplers.py:918) -- or, with ``predraw``, the
+        values that call produced at the end of the previous ``sample``.  The buffer is persistent so that a captured
+        step reads and refills the same memory on every replay."""
+        dtype = self._sum_tree._dtype
+        if not self.predraw:
+            return torch.rand(batch_size, device=dev, generator=self._rng, dtype=dtype)
+        if self._u_next is None or self._u_next.numel() != batch_size or self._u_next.device != dev:
+            self._u_next = torch.empty(batch_size, device=dev, dtype=dtype)
+            self._u_ready = 0
+        if self._u_ready != batch_size:      # first call, or another batch size: draw now
+            torch.rand(batch_size, device=dev, generator=self._rng, dtype=dtype, out=self._u_next)
+        # ONE buffer: the sample kernel reads it, the refill that follows on the same stream overwrites it (stream
+        # order keeps the two apart), and a captured step therefore reads what its previous replay drew
+        return self._u_next
 
     def check_status(self) -> None:
         """Synchronise and raise what the CPU reference raises eagerly (samplers.py:910-914,940-941)."""

@@ -420,3 +420,53 @@ def test_slice_sampler_without_replacement_on_device(cuda_backend):
         if not shuffle:
             assert seen == list(range(len(start)))
     assert (length > 0).all()
+
+
+def test_predraw_same_stream_eager_and_graph(cuda_backend):
+    """PrioritizedSampler.predraw: (1) eager, the sampled indices are those of the plain sampler for the same seed;
+    (2) captured, every replay consumes what the previous replay drew -- index-exact against the oracle for the uniforms
+    the generator produced one step earlier -- and replays keep producing fresh batches."""
+    from rl_b200.data import LazyTensorStorage, TensorDict, TensorDictPrioritizedReplayBuffer
+    from rl_b200.graphs import CudaGraphStep
+
+    N, B = 20_000, 64
+
+    def make(predraw, seed=4):
+        g = torch.Generator(device=dev()).manual_seed(seed)
+        rb = TensorDictPrioritizedReplayBuffer(alpha=0.7, beta=0.5, storage=LazyTensorStorage(N, device=dev()),
+                                               batch_size=B, generator=g)
+        rb.sampler.predraw = predraw
+        dg = torch.Generator(device=dev()).manual_seed(11)
+        rb.extend(TensorDict({"x": torch.randn(N, 8, device=dev(), generator=dg),
+                              "td_error": torch.rand(N, device=dev(), generator=dg)}, [N]))
+        return rb, g
+
+    plain, _ = make(False)
+    early, _ = make(True)
+    td = torch.rand(B, device=dev(), generator=torch.Generator(device=dev()).manual_seed(2))
+    for _ in range(5):
+        a, b = plain.sample(), early.sample()
+        assert torch.equal(a.get("index"), b.get("index"))
+        plain.update_priority(a.get("index"), td)
+        early.update_priority(b.get("index"), td)
+
+    rb, g = make(True, seed=9)
+
+    def step():
+        batch = rb.sample()
+        rb.update_priority(batch.get("index"), td)
+        return batch
+
+    graphed = CudaGraphStep(step, generators=[g], warmup=2)
+    seen = []
+    for it in range(4):
+        os_, om = _oracle_from(rb.sampler, N)
+        u = rb.sampler._u_next.clone()                   # drawn by the previous call / replay
+        batch = graphed()
+        torch.cuda.synchronize()
+        idx = batch.get("index").clone()
+        want_idx, _, _, _ = po.per_sample_c(os_, om, N, u.cpu().numpy(), 0.5)
+        np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
+        assert not torch.equal(rb.sampler._u_next, u)    # and the replay refilled the buffer for the next one
+        seen.append(idx)
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])

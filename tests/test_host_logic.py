@@ -718,3 +718,22 @@ def test_default_priority_after_skip_only_update(emul):
             smp.mark_update(torch.arange(10))
         np.testing.assert_array_equal(smp._sum_tree.values.numpy()[1:], orc._sum_tree.values()[1:])
         assert float(smp._max_priority_buf[0]) == float(orc._max_priority)
+
+
+def test_predraw_keeps_the_random_stream(emul):
+    """PrioritizedSampler.predraw draws each sample's uniforms one call early: same torch.rand calls in the same order,
+    so the sampled indices are those of the plain sampler for the same seed."""
+    def run(predraw):
+        rb = TensorDictPrioritizedReplayBuffer(alpha=0.6, beta=0.4, storage=LazyTensorStorage(200, device="cpu"),
+                                               batch_size=16, generator=torch.Generator().manual_seed(3))
+        rb.sampler.predraw = predraw
+        rb.extend(TensorDict({"obs": torch.arange(200.0).unsqueeze(-1),
+                              "td_error": torch.rand(200, generator=torch.Generator().manual_seed(1))}, [200]))
+        out = []
+        for i in range(5):
+            b = rb.sample()
+            out.append(b.get("index").clone())
+            rb.update_priority(b.get("index"), torch.full((16,), float(i + 1)))
+        return torch.stack(out)
+
+    assert torch.equal(run(False), run(True))
