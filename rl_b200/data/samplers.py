@@ -31,7 +31,7 @@ import torch
 from .. import ops
 from .segment_tree import MinSegmentTreeFp32, MinSegmentTreeFp64, SumSegmentTreeFp32, SumSegmentTreeFp64
 from .storages import Storage
-from .utils import _is_int, unravel_index
+from .utils import unravel_index
 
 _EMPTY_STORAGE_ERROR = "Cannot sample from an empty storage."
 

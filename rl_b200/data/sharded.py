@@ -26,13 +26,12 @@ ones it owns and skips the rest inside the kernel (negative local index) -- no c
 """
 from __future__ import annotations
 
-import math
 
 import torch
 
 from .. import ops
 from .replay_buffers import TensorDictPrioritizedReplayBuffer
-from .storages import LazyTensorStorage, flatten_data, unflatten_data
+from .storages import LazyTensorStorage, unflatten_data
 from .tensordict_lite import is_tensor_collection
 
 
