@@ -275,7 +275,9 @@ int rlb_extend(const void *const *src /*[host] of [dev]*/, void *const *dst /*[h
  * int64 tensor); index = (start + step) % storage_length; truncated marks the last real step of every slice.
  * variable != 0: slices of trajectories shorter than seq_length are shortened (strict_length = False, :2033-2037); then
  * pad_output pads them to seq_length by repeating the last real index and writes mask, otherwise slice s is written at
- * out_offset[s] (exclusive cumsum of seq_out, obtained by a first call with index_out == NULL). */
+ * out_offset[s] (exclusive cumsum of seq_out, obtained by a first call with index_out == NULL).
+ * done_src / term_src: the storage's one-byte-per-slot done / terminated flags; done_out = done_src[index] | truncated and
+ * term_out = term_src[index] (zero / truncated alone when a source is NULL) -- the info of samplers.py:2190-2205. */
 #define RLB_TRAJ_END 0
 #define RLB_TRAJ_ID 1
 size_t rlb_traj_table_workspace_bytes(int64_t L);
@@ -286,7 +288,9 @@ int rlb_slice_index(const int64_t *start /*[dev]*/, const int64_t *length /*[dev
                     const int64_t *traj_draw /*[dev]*/, const float *u /*[dev]*/, int64_t num_slices, int64_t seq_length,
                     int64_t storage_length, int variable, int pad_output, const int64_t *out_offset /*[dev] or NULL*/,
                     int64_t *index_out /*[dev] or NULL*/, uint8_t *truncated_out /*[dev] or NULL*/,
-                    uint8_t *mask_out /*[dev] or NULL*/, int64_t *seq_out /*[dev] or NULL*/, rlb_stream_t stream);
+                    uint8_t *mask_out /*[dev] or NULL*/, int64_t *seq_out /*[dev] or NULL*/,
+                    const uint8_t *done_src /*[dev] or NULL*/, const uint8_t *term_src /*[dev] or NULL*/,
+                    uint8_t *done_out /*[dev] or NULL*/, uint8_t *term_out /*[dev] or NULL*/, rlb_stream_t stream);
 
 /* PrioritizedSliceSampler (samplers.py:2575-3028): a slice must not start within the last seq_length - 1 steps of its
  * trajectory.  The reference zeroes those leaves in the sum tree before each draw and restores them (:2854-2918); here the

@@ -302,6 +302,10 @@ struct SliceParams {
   int variable, pad_output;
   int64_t *index_out, *seq_out;
   uint8_t *truncated_out, *mask_out;
+  // optional: the stored one-byte done / terminated flags of the sampled slots, so that the info the sampler returns
+  // (done | truncated, terminated; samplers.py:2190-2205) needs no second gather
+  const uint8_t *done_src, *term_src;
+  uint8_t *done_out, *term_out;
 };
 
 // one warp per slice
@@ -332,7 +336,10 @@ __global__ void __launch_bounds__(128) slice_index_kernel(const SliceParams P) {
     ix %= P.storage_length;
     if (ix < 0) ix += P.storage_length;
     P.index_out[off + j] = ix;
-    if (P.truncated_out) P.truncated_out[off + j] = (j == last_real) ? 1 : 0;   // :2178-2187
+    const uint8_t trunc = (j == last_real) ? 1 : 0;                              // :2178-2187
+    if (P.truncated_out) P.truncated_out[off + j] = trunc;
+    if (P.done_out) P.done_out[off + j] = (P.done_src && __ldg(P.done_src + ix)) ? 1 : trunc;
+    if (P.term_out) P.term_out[off + j] = (P.term_src && __ldg(P.term_src + ix)) ? 1 : 0;
     if (padded && P.mask_out) P.mask_out[off + j] = real ? 1 : 0;
   }
 }
@@ -420,7 +427,8 @@ int rlb_traj_table(const void *signal, int kind, int64_t L, int at_capacity, int
 int rlb_slice_index(const int64_t *start, const int64_t *length, int64_t n_traj, const int64_t *traj_draw,
                     const float *u, int64_t num_slices, int64_t seq_length, int64_t storage_length, int variable,
                     int pad_output, const int64_t *out_offset, int64_t *index_out, uint8_t *truncated_out,
-                    uint8_t *mask_out, int64_t *seq_out, rlb_stream_t stream) {
+                    uint8_t *mask_out, int64_t *seq_out, const uint8_t *done_src, const uint8_t *term_src,
+                    uint8_t *done_out, uint8_t *term_out, rlb_stream_t stream) {
   RLB_REQUIRE(num_slices >= 0 && seq_length > 0 && storage_length > 0 && n_traj > 0, RLB_EINVAL,
               "rlb_slice_index: bad sizes (num_slices=%lld seq_length=%lld storage_length=%lld n_traj=%lld)",
               (long long)num_slices, (long long)seq_length, (long long)storage_length, (long long)n_traj);
@@ -445,6 +453,10 @@ int rlb_slice_index(const int64_t *start, const int64_t *length, int64_t n_traj,
   P.seq_out = seq_out;
   P.truncated_out = truncated_out;
   P.mask_out = mask_out;
+  P.done_src = done_src;
+  P.term_src = term_src;
+  P.done_out = done_out;
+  P.term_out = term_out;
   const int wpb = 4;
   slice_index_kernel<<<(unsigned)((num_slices + wpb - 1) / wpb), 32 * wpb, 0, as_stream(stream)>>>(P);
   return check_launch("slice_index_kernel");

@@ -441,40 +441,48 @@ class SliceSampler(Sampler):
         be = ops.backend()
         storage_length = storage.shape[0]
         args = (table[0], table[2], n_traj, traj, u, seq_length, storage_length)
+        # the stored done / terminated flags of the sampled steps ride in the same launch when they are one byte per slot
+        contents = storage[:] if hasattr(storage, "get") else None
+        get = (lambda k: contents.get(k, None)) if contents is not None and hasattr(contents, "get") else (lambda k: None)
+        done_all = term_all = None
+        if self.truncated_key is not None:
+            done_key = _replace_last(self.truncated_key, "done")
+            terminated_key = _replace_last(self.truncated_key, "terminated")
+            done_all, term_all = get(done_key), get(terminated_key)
+        one_byte = lambda t: t is None or (t.element_size() == 1 and t.numel() == t.shape[0] and t.is_contiguous())
+        fused = self.truncated_key is not None and one_byte(done_all) and one_byte(term_all)
+        kw = dict(flags=(done_all, term_all)) if fused else {}
         if variable and not self.pad_output:
             seq = be.slice_index(*args, variable=True, want_index=False)[3]
             ends_at = seq.cumsum(0)
             total = int(ends_at[-1])                                                         # data-dependent batch size
-            index, truncated, mask, seq = be.slice_index(*args, variable=True, out_offset=ends_at - seq, total=total)
+            out = be.slice_index(*args, variable=True, out_offset=ends_at - seq, total=total, **kw)
             slice_starts = ends_at - seq
         else:
-            index, truncated, mask, seq = be.slice_index(*args, variable=variable, pad_output=self.pad_output)
+            out = be.slice_index(*args, variable=variable, pad_output=self.pad_output, **kw)
             slice_starts = None
+        index, truncated, mask = out[0], out[1], out[2]
         info: dict = {}
         if mask is not None:
             info[("collector", "mask")] = mask
-        contents = storage[:] if hasattr(storage, "get") else None
-        get = (lambda k: contents.get(k, None)) if contents is not None and hasattr(contents, "get") else (lambda k: None)
+        is_init_all = get("is_init")
         if self.truncated_key is not None:
-            done_key = _replace_last(self.truncated_key, "done")
-            terminated_key = _replace_last(self.truncated_key, "terminated")
-            wanted = {"done": get(done_key), "terminated": get(terminated_key), "is_init": get("is_init")}
-        else:
-            wanted = {"is_init": get("is_init")}
-        have = {k: v for k, v in wanted.items() if v is not None}
-        rows = dict(zip(have, be.gather(list(have.values()), index, len(storage)))) if have else {}
-        if self.truncated_key is not None:
-            done = rows.get("done")
             info[self.truncated_key] = truncated
-            info[done_key] = truncated.clone() if done is None else done.reshape(truncated.shape) | truncated
-            term = rows.get("terminated")
-            info[terminated_key] = torch.zeros_like(truncated) if term is None else term
-        if "is_init" in rows:   # every slice start is an init for recurrent modules (:2217-2268)
-            marker = torch.zeros_like(rows["is_init"])
+            if fused:
+                info[done_key], info[terminated_key] = out[4], out[5]
+            else:     # wide flag leaves: one small gather, then the reference's elementwise ops (:2190-2205)
+                have = {k: v for k, v in (("done", done_all), ("terminated", term_all)) if v is not None}
+                rows = dict(zip(have, be.gather(list(have.values()), index, len(storage)))) if have else {}
+                done, term = rows.get("done"), rows.get("terminated")
+                info[done_key] = truncated.clone() if done is None else done.reshape(truncated.shape) | truncated
+                info[terminated_key] = torch.zeros_like(truncated) if term is None else term
+        if is_init_all is not None:   # every slice start is an init for recurrent modules (:2217-2268)
+            is_init = be.gather([is_init_all], index, len(storage))[0]
+            marker = torch.zeros_like(is_init)
             if slice_starts is None:
                 slice_starts = torch.arange(num_slices, device=dev) * seq_length
             marker[slice_starts] = True
-            info["is_init"] = marker | rows["is_init"]
+            info["is_init"] = marker | is_init
         return (index,), info
 
 

@@ -54,7 +54,8 @@ _SIGNATURES = {
     "rlb_affine_scan": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "rlb_traj_table_workspace_bytes": (_sz, [_i64]),
     "rlb_traj_table": (_i32, [_vp, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "rlb_slice_index": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rlb_slice_index": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                               _vp, _vp, _vp]),
     "rlb_slice_mask_starts": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
     "rlb_tree_update_range": (_i32, [_vp, _vp, _i64, _i32, _i64, _i64, _i64, _i32, _vp, _f64, _f64, _f64, _i32, _vp,
                                      _vp, _vp]),
@@ -410,9 +411,11 @@ class CudaBackend:
 
     def slice_index(self, start, length, n_traj: int, traj_draw, u, seq_length: int, storage_length: int,
                     variable: bool = False, pad_output: bool = False, out_offset=None, total: int | None = None,
-                    want_index: bool = True):
-        """Returns (index int64[n], truncated bool[n, 1], mask bool[n] | None, seq int64[num_slices])."""
-        dev = self._cuda(start, length, traj_draw, u, out_offset)
+                    want_index: bool = True, flags: tuple | None = None):
+        """Returns (index int64[n], truncated bool[n, 1], mask bool[n] | None, seq int64[num_slices]); with
+        ``flags=(done_leaf | None, terminated_leaf | None)`` (the storage's one-byte-per-slot flags) two more entries:
+        ``done[index] | truncated`` and ``terminated[index]`` as bool [n, 1]."""
+        dev = self._cuda(start, length, traj_draw, u, out_offset, *(f for f in (flags or ()) if f is not None))
         S = traj_draw.numel()
         seq = torch.empty(S, dtype=torch.int64, device=dev)
         index = trunc = mask = None
@@ -421,11 +424,20 @@ class CudaBackend:
             index = torch.empty(n, dtype=torch.int64, device=dev)
             trunc = torch.empty((n, 1), dtype=torch.bool, device=dev)
             mask = torch.empty(n, dtype=torch.bool, device=dev) if (variable and pad_output) else None
+        done_src = term_src = done_out = term_out = None
+        if flags is not None and want_index:
+            done_src, term_src = (None if f is None else f.contiguous().view(torch.uint8) for f in flags)
+            both = torch.empty((2, n, 1), dtype=torch.bool, device=dev)
+            done_out, term_out = both[0], both[1]
         with self._Guard(dev):
             self._check(self.L.rlb_slice_index(start.data_ptr(), length.data_ptr(), n_traj, traj_draw.data_ptr(),
                                                u.data_ptr(), S, seq_length, storage_length, int(variable),
                                                int(pad_output), self._p(out_offset), self._p(index), self._p(trunc),
-                                               self._p(mask), seq.data_ptr(), self._stream(dev)), "rlb_slice_index")
+                                               self._p(mask), seq.data_ptr(), self._p(done_src), self._p(term_src),
+                                               self._p(done_out), self._p(term_out), self._stream(dev)),
+                        "rlb_slice_index")
+        if flags is not None and want_index:
+            return index, trunc, mask, seq, done_out, term_out
         return index, trunc, mask, seq
 
     def slice_mask_starts(self, masked_tree: torch.Tensor, capacity: int, stop, length, n_traj: int, seq_length: int,

@@ -194,7 +194,7 @@ class OracleBackend:
             row[:len(a)] = torch.from_numpy(a)
 
     def slice_index(self, start, length, n_traj, traj_draw, u, seq_length, storage_length, variable=False,
-                    pad_output=False, out_offset=None, total=None, want_index=True):
+                    pad_output=False, out_offset=None, total=None, want_index=True, flags=None):
         from oracle import slice_oracle as so
 
         idx, tr, mask, seq = so.slice_index(start[:n_traj].numpy(), length[:n_traj].numpy(), seq_length=seq_length,
@@ -204,8 +204,14 @@ class OracleBackend:
         seq = torch.from_numpy(np.asarray(seq))
         if not want_index:
             return None, None, None, seq
-        return (torch.from_numpy(idx), torch.from_numpy(tr).reshape(-1, 1),
-                None if mask is None else torch.from_numpy(mask), seq)
+        out = (torch.from_numpy(idx), torch.from_numpy(tr).reshape(-1, 1),
+               None if mask is None else torch.from_numpy(mask), seq)
+        if flags is None:
+            return out
+        index, trunc = out[0], out[1]
+        done = trunc.clone() if flags[0] is None else flags[0].reshape(-1)[index].reshape(-1, 1).bool() | trunc
+        term = torch.zeros_like(trunc) if flags[1] is None else flags[1].reshape(-1)[index].reshape(-1, 1).bool()
+        return (*out, done, term)
 
     def slice_mask_starts(self, masked_tree, capacity, stop, length, n_traj, seq_length, ring_length):
         from oracle import slice_oracle as so

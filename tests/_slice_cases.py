@@ -51,6 +51,8 @@ def _slice_cases():
         "loose_padded": (dict(num_slices=16, end_key=("next", "done"), strict_length=False, pad_output=True),
                          {("next", "done"): short}, L, L, None, 16 * 30),
         "no_end_full": (dict(num_slices=3, end_key=("next", "done")), {("next", "done"): nodone}, L, L, None, 60),
+        "with_is_init": (dict(num_slices=8, end_key=("next", "done")),
+                         {("next", "done"): done, "is_init": torch.roll(done, 1, 0)}, L, L, None, 64),
         "with_terminated": (dict(num_slices=8, end_key=("next", "done")),
                             {("next", "done"): done, ("next", "terminated"): done & (torch.rand(L, 1, generator=g) < 0.5)},
                             L, L, None, 64),

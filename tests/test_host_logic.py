@@ -482,7 +482,7 @@ def test_sampler_without_replacement(emul, drop_last, shuffle):
 
 
 @pytest.mark.parametrize("case", ["end_full", "end_partial", "traj_full", "strict_filter", "loose_variable", "loose_padded",
-                                  "with_terminated", "no_end_full"])
+                                  "with_terminated", "with_is_init", "no_end_full"])
 def test_slice_sampler_equals_live_reference(emul, ref_samplers, case):
     """rl_b200 SliceSampler inside a TensorDictReplayBuffer (kernels emulated by the oracle) against the UNMODIFIED
     reference sampler on the same contents with the same CPU generator seed: same slices, same info, same rows."""
