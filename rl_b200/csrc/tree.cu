@@ -48,6 +48,31 @@ __global__ void tree_level_dense_kernel(T *tree, int64_t level_start, int64_t le
   }
 }
 
+// Dense recomputation of eleven levels at once: each CTA takes kRebuildTile consecutive leaves, reduces its subtree
+// pairwise in shared memory (same child pairs, same operation order as the level-by-level form) and writes every node
+// of it -- one launch instead of eleven for the bulk of a rebuild (load_state_dict, loads, the masked copy the
+// prioritized slice sampler draws from).
+constexpr int kRebuildTile = 2048;
+template <typename T, bool IsMin>
+__global__ void __launch_bounds__(256) tree_rebuild_tiles_kernel(T *tree, int64_t capacity) {
+  __shared__ T buf[2][kRebuildTile];
+  const int64_t leaf0 = capacity + (int64_t)blockIdx.x * kRebuildTile;
+  for (int j = threadIdx.x; j < kRebuildTile; j += blockDim.x) buf[0][j] = tree[leaf0 + j];
+  __syncthreads();
+  int cur = 0;
+  int64_t level_start = capacity >> 1;  // first node of the level being produced
+  for (int w = kRebuildTile >> 1; w >= 1; w >>= 1, level_start >>= 1) {
+    const int64_t node0 = level_start + (int64_t)blockIdx.x * w;
+    for (int j = threadIdx.x; j < w; j += blockDim.x) {
+      const T v = tree_op<T, IsMin>(buf[cur][2 * j], buf[cur][2 * j + 1]);
+      buf[cur ^ 1][j] = v;
+      tree[node0 + j] = v;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
 // Dense recomputation of the top of the tree by ONE CTA: loads the W nodes [W, 2W) (W <= 1024, a
 // power of two), reduces pairwise in shared memory and writes every node in [1, W).
 template <typename T, bool IsMin>
@@ -820,6 +845,16 @@ static int tree_rebuild_impl(void *tree_, int64_t capacity, int is_min, cudaStre
   T *tree = static_cast<T *>(tree_);
   const int threads = 256;
   int64_t W = capacity >> 1;  // width of the deepest internal level
+  if (capacity >= 2 * kRebuildTile) {  // eleven levels per launch: every tile's subtree, down to width capacity / 2048
+    const unsigned tiles = (unsigned)(capacity / kRebuildTile);
+    if (is_min)
+      tree_rebuild_tiles_kernel<T, true><<<tiles, threads, 0, st>>>(tree, capacity);
+    else
+      tree_rebuild_tiles_kernel<T, false><<<tiles, threads, 0, st>>>(tree, capacity);
+    int rc = check_launch("tree_rebuild_tiles_kernel");
+    if (rc) return rc;
+    W = capacity / kRebuildTile / 2;
+  }
   for (; W >= 1024; W >>= 1) {
     int64_t blocks = (W + threads - 1) / threads;
     const int64_t cap_blocks = (int64_t)sm_count() * 16;

@@ -191,6 +191,36 @@ def test_range_default_follows_the_running_max_on_replay(cuda_backend):
     assert float(smp._max_priority_buf[0]) == float(np.float32(np.float32(7.0) + eps))   # the default itself is a raw priority
 
 
+@pytest.mark.parametrize("size", [3, 1000, 2047, 2048, 4095, 5000, 1_000_000, 3_000_000])
+def test_tree_rebuild_matches_oracle(cuda_backend, size):
+    """rlb_tree_rebuild (eleven levels per launch over 2048-leaf tiles, dense levels above, single-CTA top) from random
+    leaves: every internal node bit-equal to the reference tree holding the same leaves; fp64 against numpy."""
+    from rl_b200.data.segment_tree import (MinSegmentTreeFp32, MinSegmentTreeFp64, SumSegmentTreeFp32,
+                                           SumSegmentTreeFp64)
+
+    rng = np.random.default_rng(size)
+    leaves = (rng.random(size) * 5 + 1e-3).astype(np.float32)
+    for cls, is_min in ((SumSegmentTreeFp32, False), (MinSegmentTreeFp32, True)):
+        t = cls(size, dev())
+        t.load_leaves(torch.from_numpy(leaves).to(dev()))
+        o = po.OracleTree(size, is_min)
+        o.load_leaves(leaves)
+        np.testing.assert_array_equal(t.values.cpu().numpy()[1:], o.values()[1:])
+    l64 = rng.random(size) * 5 + 1e-3
+    for cls, is_min in ((SumSegmentTreeFp64, False), (MinSegmentTreeFp64, True)):
+        t = cls(size, dev())
+        t.load_leaves(torch.from_numpy(l64).to(dev()))
+        cap = t.capacity
+        h = np.full(2 * cap, np.finfo(np.float64).max if is_min else 0.0)
+        h[cap:cap + size] = l64
+        w = cap // 2
+        while w >= 1:
+            a, b = h[2 * w:4 * w:2], h[2 * w + 1:4 * w:2]
+            h[w:2 * w] = np.minimum(a, b) if is_min else a + b
+            w //= 2
+        np.testing.assert_array_equal(t.values.cpu().numpy()[1:], h[1:])
+
+
 def test_tree_kat_and_queries(cuda_backend):
     # test/rb/test_prioritized.py:113-140
     from rl_b200.data.segment_tree import MinSegmentTreeFp32, SumSegmentTreeFp32
