@@ -737,3 +737,28 @@ def test_predraw_keeps_the_random_stream(emul):
         return torch.stack(out)
 
     assert torch.equal(run(False), run(True))
+
+
+@pytest.mark.parametrize("drop_last", [True, False])
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_sampler_without_replacement_equals_live_reference(emul, ref_samplers, drop_last, shuffle):
+    """SamplerWithoutReplacement against the UNMODIFIED reference class (samplers.py:221-362): same index batches, same
+    ran_out sequence and _remaining_batches over three sweeps and a storage that grows in between."""
+    from rl_b200.data import SamplerWithoutReplacement
+
+    ref = ref_samplers.mod.SamplerWithoutReplacement(drop_last=drop_last, shuffle=shuffle)
+    mine = SamplerWithoutReplacement(drop_last=drop_last, shuffle=shuffle)
+    ref._rng = torch.Generator().manual_seed(8)
+    mine._rng = torch.Generator().manual_seed(8)
+    st_ref = ref_samplers.make_storage({"obs": torch.zeros(64)}, 23, 64)
+    st = LazyTensorStorage(64, device="cpu")
+    st.set(slice(0, 23), TensorDict({"obs": torch.zeros(23)}, [23]))
+    for it in range(30):
+        if it == 17:            # the storage grows: both start a new permutation
+            st_ref._len = 40
+            st.set(slice(23, 40), TensorDict({"obs": torch.zeros(17)}, [17]))
+        a, _ = ref.sample(st_ref, 5)
+        b, _ = mine.sample(st, 5)
+        assert torch.equal(a, b), it
+        assert ref.ran_out == mine.ran_out
+        assert ref._remaining_batches == mine._remaining_batches
