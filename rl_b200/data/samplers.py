@@ -1093,22 +1093,29 @@ class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):
             if self.index_ready is None:
                 self.index_ready = torch.cuda.Event()
             self.index_ready.record(torch.cuda.current_stream(dev))
-        steps = torch.arange(seq_length, device=dev)
-        index = ((starts.unsqueeze(1) + steps) % storage.shape[0]).reshape(-1)            # :2963-2966
         info: dict = {"priority_weight": weight.repeat_interleave(seq_length)}            # :2969-2971
+        # expansion of the starts (:2963-2966), truncated markers and the stored flags of the sampled steps in one
+        # rlb_slice_index launch: every start is a one-entry "trajectory" of exactly seq_length steps, offset 0
+        contents = storage[:]
+        done_all = term_all = None
         if self.truncated_key is not None:
             done_key = _replace_last(self.truncated_key, "done")
             terminated_key = _replace_last(self.truncated_key, "terminated")
-            truncated = torch.zeros((num_slices, seq_length), dtype=torch.bool, device=dev)
-            truncated[:, -1] = True
-            truncated = truncated.reshape(-1, 1)
-            contents = storage[:]
-            have = {k: v for k, v in (("done", contents.get(done_key, None)),
-                                      ("terminated", contents.get(terminated_key, None))) if v is not None}
-            rows = dict(zip(have, be.gather(list(have.values()), index, length))) if have else {}
+            done_all, term_all = contents.get(done_key, None), contents.get(terminated_key, None)
+        one_byte = lambda t: t is None or (t.element_size() == 1 and t.numel() == t.shape[0] and t.is_contiguous())
+        fused = self.truncated_key is not None and one_byte(done_all) and one_byte(term_all)
+        out = be.slice_index(starts, torch.full_like(starts, seq_length), num_slices,
+                             torch.arange(num_slices, device=dev), torch.zeros(num_slices, device=dev), seq_length,
+                             storage.shape[0], **(dict(flags=(done_all, term_all)) if fused else {}))
+        index, truncated = out[0], out[1]
+        if self.truncated_key is not None:
             info[self.truncated_key] = truncated
-            done = rows.get("done")
-            info[done_key] = truncated.clone() if done is None else done.reshape(truncated.shape) | truncated
-            term = rows.get("terminated")
-            info[terminated_key] = torch.zeros_like(truncated) if term is None else term
+            if fused:
+                info[done_key], info[terminated_key] = out[4], out[5]
+            else:
+                have = {k: v for k, v in (("done", done_all), ("terminated", term_all)) if v is not None}
+                rows = dict(zip(have, be.gather(list(have.values()), index, length))) if have else {}
+                done, term = rows.get("done"), rows.get("terminated")
+                info[done_key] = truncated.clone() if done is None else done.reshape(truncated.shape) | truncated
+                info[terminated_key] = torch.zeros_like(truncated) if term is None else term
         return (index,), info
