@@ -78,7 +78,8 @@ def _oracle_slice(kwargs, data, length, max_size, last_cursor, batch_size, rec):
     strict = kwargs.get("strict_length", True)
     start, stop, lens = so.valid_trajectories(start, stop, lens, seq, strict)
     assert rec["maxval"] == len(start)
-    return so.slice_index(start, lens, seq_length=seq, num_slices=num_slices, storage_length=max_size,
+    # storage.shape[0] is truncated to the fill level while the storage is not full (storages.py:856-863)
+    return so.slice_index(start, lens, seq_length=seq, num_slices=num_slices, storage_length=length,
                           traj_draw=rec["traj"].numpy(), u=rec["u"].numpy(), strict_length=strict,
                           pad_output=kwargs.get("pad_output", False))
 

@@ -362,3 +362,48 @@ def test_prioritized_slice_golden_fixture():
             oi, ow, otr, _ = _oracle_pslice(gt("done"), gt("sum_leaves"), gt("min_leaves"), L, filled, S, T, gt("u")[d])
             np.testing.assert_array_equal(oi, gt("index")[d])
             np.testing.assert_array_equal(ow, gt("weight")[d])
+
+
+def test_slice_oracle_randomized_against_live_reference(ref_samplers):
+    """Sixty random SliceSampler configurations (ring length, fill level, cursor, end density, flags vs trajectory ids,
+    num_slices vs slice_len, strict / loose / padded) through the unmodified reference and through the restatement."""
+    rng = np.random.default_rng(123)
+    done_cases = 0
+    for trial in range(60):
+        L = int(rng.integers(8, 300))
+        filled = L if rng.random() < 0.6 else int(rng.integers(4, L + 1))
+        density = float(rng.choice([0.0, 0.02, 0.1, 0.4]))
+        by_traj = bool(rng.random() < 0.3)
+        done = torch.from_numpy(rng.random((L, 1)) < density)
+        traj = torch.from_numpy(np.cumsum(rng.random(L) < max(density, 0.02)))
+        seq = int(rng.integers(1, 12))
+        S = int(rng.integers(1, 9))
+        kwargs = dict(traj_key="episode") if by_traj else dict(end_key=("next", "done"))
+        kwargs.update(dict(num_slices=S) if rng.random() < 0.5 else dict(slice_len=seq))
+        mode = rng.integers(0, 3)
+        if mode == 1:
+            kwargs["strict_length"] = False
+        elif mode == 2:
+            kwargs.update(strict_length=False, pad_output=True)
+        cursor = None
+        if filled == L and rng.random() < 0.5:
+            cursor = int(rng.integers(0, L)) if rng.random() < 0.5 else torch.arange(3, int(rng.integers(4, L + 1)))
+        data = {("next", "done"): done, "episode": traj}
+        try:
+            index, info, rec = _ref_slice_run(ref_samplers, kwargs, data, filled, L, cursor, S * seq, seed=trial)
+        except RuntimeError as err:                       # no trajectory long enough: the restatement must agree
+            assert "sufficient length" in str(err)
+            from oracle import slice_oracle as so
+
+            c = None if cursor is None else int(cursor[-1] if isinstance(cursor, torch.Tensor) else cursor)
+            start, stop, lens = (so.traj_table(trajectory=traj[:filled].numpy(), at_capacity=filled == L, cursor=c)
+                                 if by_traj else so.traj_table(end=done[:filled].numpy(), at_capacity=filled == L, cursor=c))
+            assert (lens < seq).all()
+            continue
+        oi, otr, omask, _ = _oracle_slice(kwargs, data, filled, L, cursor, S * seq, rec)
+        np.testing.assert_array_equal(index.numpy(), oi, err_msg=f"trial {trial}: {kwargs}")
+        np.testing.assert_array_equal(info[("next", "truncated")].numpy().reshape(-1), otr)
+        if omask is not None:
+            np.testing.assert_array_equal(info[("collector", "mask")].numpy(), omask)
+        done_cases += 1
+    assert done_cases >= 40
