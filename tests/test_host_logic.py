@@ -762,3 +762,108 @@ def test_sampler_without_replacement_equals_live_reference(emul, ref_samplers, d
         assert torch.equal(a, b), it
         assert ref.ran_out == mine.ran_out
         assert ref._remaining_batches == mine._remaining_batches
+
+
+def test_slice_sampler_randomized_buffer_flows_vs_live_reference(emul, ref_samplers):
+    """Forty random buffers (ring length, several writer batches that may wrap, end density, strict / loose / padded,
+    num_slices / slice_len, cache on / off): rl_b200's SliceSampler in a TensorDictReplayBuffer against the unmodified
+    reference sampler on a mirror of the ring, same CPU generator seed."""
+    from rl_b200.data import SliceSampler
+
+    rng = np.random.default_rng(77)
+    compared = 0
+    for trial in range(40):
+        L = int(rng.integers(10, 200))
+        seq, S = int(rng.integers(1, 9)), int(rng.integers(1, 7))
+        kwargs = dict(end_key=("next", "done"))
+        kwargs.update(dict(num_slices=S) if rng.random() < 0.5 else dict(slice_len=seq))
+        mode = int(rng.integers(0, 3))
+        if mode == 1:
+            kwargs["strict_length"] = False
+        elif mode == 2:
+            kwargs.update(strict_length=False, pad_output=True)
+        cache = bool(rng.random() < 0.5)
+        rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device="cpu"), batch_size=S * seq,
+                                    sampler=SliceSampler(cache_values=cache, **kwargs),
+                                    generator=torch.Generator().manual_seed(trial))
+        ref = ref_samplers.mod.SliceSampler(cache_values=False, **kwargs)
+        ref._rng = torch.Generator().manual_seed(trial)
+        ring_done = torch.zeros(L, 1, dtype=torch.bool)
+        ring_obs = torch.zeros(L, 1)
+        total = 0
+        for _ in range(int(rng.integers(1, 4))):
+            n = int(rng.integers(1, L + 1))
+            done = torch.from_numpy(rng.random((n, 1)) < float(rng.choice([0.0, 0.05, 0.3])))
+            obs = torch.arange(total, total + n, dtype=torch.float32).unsqueeze(-1)
+            rb.extend(TensorDict({("next", "done"): done, "obs": obs}, [n]))
+            slots = (total + torch.arange(n)) % L
+            ring_done[slots], ring_obs[slots] = done, obs
+            total += n
+            filled = min(L, total)
+            cur = rb.storage._last_cursor
+            cur = range(cur.start, cur.stop) if isinstance(cur, slice) else cur
+            st = ref_samplers.make_storage({("next", "done"): ring_done, "obs": ring_obs}, filled, L, cur)
+            for _ in range(2):
+                try:
+                    want_index, want_info = ref.sample(st, S * seq)
+                except RuntimeError as err:
+                    assert "sufficient length" in str(err)
+                    with pytest.raises(RuntimeError, match="sufficient length"):
+                        rb.sample()
+                    continue
+                got = rb.sample()
+                assert torch.equal(got.get("index").reshape(-1), want_index[0]), (trial, kwargs)
+                for k, v in want_info.items():
+                    assert torch.equal(got.get(k).reshape(v.shape), v), (trial, k)
+                assert torch.equal(got.get("obs").reshape(-1), ring_obs[want_index[0]].reshape(-1))
+                compared += 1
+    assert compared >= 60
+
+
+def test_prioritized_slice_sampler_randomized_vs_live_reference(emul, ref_samplers):
+    """Twenty-five random PrioritizedSliceSampler buffers (wrapping writer batches, TD-error write-backs with duplicates)
+    against the unmodified reference class: same starts, per-step weights and flags."""
+    from rl_b200.data import PrioritizedSliceSampler
+
+    rng = np.random.default_rng(5)
+    compared = 0
+    for trial in range(25):
+        L = int(rng.integers(30, 200))
+        seq, S = int(rng.integers(2, 8)), int(rng.integers(1, 6))
+        alpha, beta = float(rng.choice([0.5, 0.7, 1.0])), float(rng.choice([0.4, 1.0]))
+        kw = dict(num_slices=S, end_key=("next", "done"))
+        rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device="cpu"), batch_size=S * seq,
+                                    sampler=PrioritizedSliceSampler(L, alpha, beta, **kw),
+                                    generator=torch.Generator().manual_seed(trial))
+        ref = ref_samplers.mod.PrioritizedSliceSampler(L, alpha, beta, **kw)
+        ref._rng = torch.Generator().manual_seed(trial)
+        ring_done = torch.zeros(L, 1, dtype=torch.bool)
+        total = 0
+        for _ in range(int(rng.integers(1, 4))):
+            n = int(rng.integers(1, L + 1))
+            done = torch.from_numpy(rng.random((n, 1)) < float(rng.choice([0.02, 0.1])))
+            rb.extend(TensorDict({("next", "done"): done, "obs": torch.zeros(n, 1)}, [n]))
+            slots = (total + torch.arange(n)) % L
+            ring_done[slots] = done
+            total += n
+            filled = min(L, total)
+            cur = rb.storage._last_cursor
+            cur = range(cur.start, cur.stop) if isinstance(cur, slice) else cur
+            st = ref_samplers.make_storage({("next", "done"): ring_done}, filled, L, cur)
+            ref.mark_update(slots, storage=st)
+            k = int(rng.integers(1, 40))
+            ix = torch.from_numpy(rng.integers(0, filled, k))
+            pr = torch.from_numpy((rng.random(k) * 3).astype(np.float32))
+            rb.update_priority(ix, pr)
+            ref.update_priority(ix, pr, storage=st)
+            try:
+                want_index, want_info = ref.sample(st, S * seq)
+            except RuntimeError as err:          # every start masked out (all trajectories shorter than the slice)
+                assert "p_sum" in str(err) or "sufficient" in str(err), err
+                continue
+            got = rb.sample()
+            assert torch.equal(got.get("index").reshape(-1), want_index[0]), trial
+            assert torch.equal(got.get("priority_weight").reshape(-1), want_info["priority_weight"]), trial
+            assert torch.equal(got.get(("next", "done")).reshape(-1), want_info[("next", "done")].reshape(-1))
+            compared += 1
+    assert compared >= 25
