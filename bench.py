@@ -14,8 +14,10 @@ A "step" is one pass of the hot path over one batch of synthetic input (BASELINE
 
 `value` = (256 sampled + 4096*128 GAE) transitions per step / device time per step, whole job.  With N > 1
 the buffer is sharded by capacity (one 1M shard per rank), every rank draws 256 from its shard
-and ONE NCCL all-gather assembles the 256*N global minibatch on every rank; GAE rows are split by rank
-(weak scaling: per-GPU work is fixed).
+and the 256*N global minibatch is assembled on every rank by the gather kernel itself (NVLink peer stores,
+split-phase: a step returns the previous draw, so the transfer overlaps the rest of the step); every rank runs its
+own GAE (weak scaling: per-GPU work is fixed).  N > 1 also runs BASELINE.json configs[3] and [4] ("c4", "c5": 1.25M /
+6.25M slots per shard, 128 / 512 rows per rank) and reports them as extra keys of the same JSON line.
 
 Timing: CUDA events on the launching stream around exactly K steps after W warm-ups, barrier +
 synchronize on both sides, max over ranks.  Inputs are larger than L2 (the storage is 56 GB; the GAE inputs
@@ -44,6 +46,21 @@ GAE_ROWS, GAE_T = 4096, 128
 ROW_BYTES = 2 * 4 * 84 * 84 + 8 + 4 + 1 + 1  # 56 462 B per Atari transition
 TRANSITIONS_PER_STEP = BATCH + GAE_ROWS * GAE_T
 METRIC = "transitions/sec sampled+GAE at 1M buffer / Atari frames"
+WORKLOAD = "C2 PER sample+update B=256 @1M Atari transitions (56462 B/row) + C3 GAE [4096,128]"
+N_BUFFERS = 4                    # receive slots of the pipelined sharded exchange
+NVLINK_GBPS_PER_DIR = 900.0      # NVLink 5, per GPU per direction (B200_PROFILING.md)
+GAE_SHAPES = ((4096, 128), (300, 500), (32, 512), (1, 512))  # C3 + benchmarks/test_objectives_benchmarks.py:122-153
+
+
+def make_config(world: int) -> dict:
+    """The workload description -- identical on both arms (ours / reference)."""
+    return {"workload": WORKLOAD, "capacity_per_gpu": CAPACITY, "batch_per_gpu": BATCH,
+            "gae_shape": [GAE_ROWS, GAE_T, 1], "alpha": ALPHA, "beta": BETA, "gamma": GAMMA, "lmbda": LMBDA,
+            "arithmetic": "fp32 priorities / trees / GAE, byte-exact u8 row moves, int64 indices",
+            "transitions_per_step_per_gpu": TRANSITIONS_PER_STEP,
+            "parallelism": f"capacity-sharded x{world} (one 1M shard + 256 draws per GPU, global minibatch on every rank)"
+                           if world > 1 else "single GPU",
+            "l2": "inputs larger than L2: 56 GB storage per GPU with random rows; GAE inputs rotate through >160 MB"}
 
 
 # ------------------------------------------------------------------------------------------- helpers
@@ -136,7 +153,7 @@ def gae_ring(dev, rows: int, T: int, g, min_bytes: int = 160 << 20):
     """Input sets for GAE whose total footprint exceeds L2 so that every call reads cold data."""
     per = rows * T * 14
     n = max(2, -(-min_bytes // per))
-    n += n % 2  # even: the sharded buffer alternates its two receive buffers from one step to the next
+    n = -(-n // N_BUFFERS) * N_BUFFERS  # the sharded buffer's receive slots rotate with the ring slot
     ring = []
     for _ in range(n):
         v, nv, r = (torch.randn(rows, T, 1, device=dev, generator=g) for _ in range(3))
@@ -279,42 +296,228 @@ def write_path_probe(dev, rb, g, hbm_peak: float) -> dict | None:
         return {"error": f"{type(e).__name__}: {e}"[:200]}
 
 
-def run_ours(args) -> dict:
-    from rl_b200 import ops
-    from rl_b200.graphs import CudaGraphStep
+def graph_us(fn_list, dev, reps: int = 5) -> float:
+    """Median device time (us) of ONE call, measured as a CUDA-graph replay of all callables in `fn_list` back to back
+    on one stream (CUDA events around the replay; no host in the loop)."""
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        fn_list[0]()
+        stream.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=stream):
+            keep = [fn() for fn in fn_list]
+        gr.replay()
+        stream.synchronize()
+        ms = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            gr.replay()
+            e1.record(stream)
+            stream.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        del keep, gr
+    return sorted(ms)[len(ms) // 2] * 1e3 / len(fn_list)
 
+
+def component_times(dev, rb, ring8, td_err, gs, be) -> dict:
+    """Graph-replayed device time of each component of the step on its own (20 calls back to back): the numbers the
+    per-component CPU ratios are formed from -- the headline is dominated by GAE elements, these are not."""
+    g = torch.Generator(device=dev).manual_seed(321)
+    n = 20
+    out = {}
+    gen = rb.sampler._rng
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        rb.sample()
+        stream.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        gr.register_generator_state(gen)
+        with torch.cuda.graph(gr, stream=stream):
+            keep = [rb.sample() for _ in range(n)]
+        gr.replay()
+        stream.synchronize()
+        ms = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            gr.replay()
+            e1.record(stream)
+            stream.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        del keep, gr
+    out["sample_us"] = round(sorted(ms)[2] * 1e3 / n, 2)
+    idx = [torch.randint(0, CAPACITY, (BATCH,), device=dev, generator=g) for _ in range(n)]
+    out["update_priority_us"] = round(graph_us([(lambda ix=ix: rb.update_priority(ix, td_err)) for ix in idx], dev), 2)
+    out["gae_us"] = round(graph_us([(lambda x=x: be.gae(x[0], x[1], x[2], x[3], x[4], gs[0], gs[1], GAE_ROWS, GAE_T, 1))
+                                    for x in ring8[:n]], dev), 2)
+    out["sample_transitions_per_s"] = round(BATCH / (out["sample_us"] * 1e-6), 1)
+    out["update_transitions_per_s"] = round(BATCH / (out["update_priority_us"] * 1e-6), 1)
+    out["gae_transitions_per_s"] = round(GAE_ROWS * GAE_T / (out["gae_us"] * 1e-6), 1)
+    out["method"] = "CUDA-graph replay of 20 public-API calls back to back, CUDA events, median of 5"
+    return out
+
+
+def gae_shape_sweep(dev, be, hbm_peak: float) -> dict:
+    """The GAE kernel at C3 and at the reference benchmark's own shapes (few rows / long T), graph-replayed on inputs
+    that rotate through more than L2."""
+    g = torch.Generator(device=dev).manual_seed(77)
+    out = {}
+    for rows, T in GAE_SHAPES:
+        per = rows * T * 14
+        n = int(min(64, max(4, (160 << 20) // per)))
+        sets = []
+        for _ in range(n):
+            v, nv, r = (torch.randn(rows, T, 1, device=dev, generator=g) for _ in range(3))
+            term = torch.rand(rows, T, 1, device=dev, generator=g) < 0.02
+            done = term | (torch.rand(rows, T, 1, device=dev, generator=g) < 0.02)
+            sets.append((v, nv, r, done.view(torch.uint8), term.view(torch.uint8)))
+        us = graph_us([(lambda x=x: be.gae(x[0], x[1], x[2], x[3], x[4], GAMMA, GAMMA * LMBDA, rows, T, 1)) for x in sets], dev)
+        alg = rows * T * 22
+        out[f"{rows}x{T}"] = {"us_per_launch": round(us, 3), "achieved": round(alg / us / 1e3, 1),
+                              "frac": round(alg / us / 1e3 / hbm_peak, 4), "algorithmic_bytes": alg}
+    return out
+
+
+def reference_gpu_kernels(dev, rb, ring, td_err) -> dict:
+    """BASELINE LEG (SURVEY 8d "kernel to beat"): the reference's OWN GPU paths timed on the same box, same inputs,
+    same method (graph-replayed back-to-back calls, cold rows): aten::index per leaf (storages.py:1260-1263), the
+    reference CUDA segment tree (csrc/cuda_segment_tree.cu, compiled unmodified into oracle/_ref/cuda) and its
+    conv-based vec GAE on cuda (functional.py:211-267).  Never fatal to the bench."""
+    out = {}
+    try:
+        st = rb.storage
+        g = torch.Generator(device=dev).manual_seed(123)
+        from rl_b200 import ops
+
+        be = ops.backend()
+        for bb, reps in ((256, 20), (1024, 8), (16384, 2)):
+            idxs = [torch.randint(0, len(st), (bb,), device=dev, generator=g) for _ in range(reps)]
+            ref_us = graph_us([(lambda ix=ix: [leaf[ix] for leaf in st._leaves]) for ix in idxs], dev)
+            our_us = graph_us([(lambda ix=ix: be.gather(st._leaves, ix, len(st))) for ix in idxs], dev)
+            out[f"gather_B{bb}"] = {"aten_index_us": round(ref_us, 2), "rlb_gather_us": round(our_us, 2),
+                                    "speedup": round(ref_us / our_us, 2), "launches_ref": len(st._leaves), "launches_ours": 1}
+    except Exception as e:  # noqa: BLE001
+        out["gather_error"] = f"{type(e).__name__}: {e}"[:200]
+    try:
+        from oracle import gae_torch
+
+        v, nv, r, d, t = ring[0]
+        gm, lm = torch.tensor(GAMMA, device=dev), torch.tensor(LMBDA, device=dev)
+        with torch.no_grad():
+            for _ in range(3):
+                gae_torch.vec_gae(gm, lm, v, nv, r, d, t)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(20):
+                x = ring[i % len(ring)]
+                gae_torch.vec_gae(gm, lm, x[0], x[1], x[2], x[3], x[4])
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ref_us = e0.elapsed_time(e1) * 1e3 / 20
+        from rl_b200 import ops
+
+        be = ops.backend()
+        our_us = graph_us([(lambda x=x: be.gae(x[0], x[1], x[2], x[3].view(torch.uint8), x[4].view(torch.uint8), GAMMA,
+                                               GAMMA * LMBDA, GAE_ROWS, GAE_T, 1)) for x in ring[:20]], dev)
+        out["gae_4096x128"] = {"reference_vec_gae_cuda_us": round(ref_us, 1), "rlb_gae_us": round(our_us, 2),
+                               "speedup": round(ref_us / our_us, 1),
+                               "note": "reference = its conv1d path as torch ops on cuda (eager: it has host syncs and cannot be captured)"}
+    except Exception as e:  # noqa: BLE001
+        out["gae_error"] = f"{type(e).__name__}: {e}"[:200]
+    try:
+        from oracle.ref_loader import reference_ext
+
+        ext = reference_ext("cuda")
+        if ext is None or not hasattr(ext, "CudaSumSegmentTreeFp32"):
+            raise RuntimeError("oracle/_ref/cuda/_torchrl.so not available")
+        smp = rb.sampler
+        rs, rm = ext.CudaSumSegmentTreeFp32(CAPACITY, dev), ext.CudaMinSegmentTreeFp32(CAPACITY, dev)
+        leaves = smp._sum_tree.dump_leaves()
+        all_idx = torch.arange(CAPACITY, device=dev)
+        rs.update(all_idx, leaves)
+        rm.update(all_idx, leaves)
+        g = torch.Generator(device=dev).manual_seed(5)
+        idx = [torch.randint(0, CAPACITY, (BATCH,), device=dev, generator=g) for _ in range(10)]
+        val = torch.rand(BATCH, device=dev, generator=g)
+        mass = torch.rand(BATCH, device=dev, generator=g) * rs.query(0, CAPACITY)
+
+        def t_eager(fn, n=10):
+            fn(0)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) * 1e3 / n
+
+        def ref_update(i):
+            rs.update(idx[i % 10], val)
+            rm.update(idx[i % 10], val)
+
+        ref_upd = t_eager(ref_update)
+        ref_scan = t_eager(lambda i: rs.scan_lower_bound(mass))
+        from rl_b200 import ops
+
+        be = ops.backend()
+        ws = smp._tree_workspace(BATCH)
+        our_upd = graph_us([(lambda ix=ix: be.tree_update(smp._sum_tree.values, smp._min_tree.values, smp._sum_tree.capacity,
+                                                         ix, val, ws, 1)) for ix in idx], dev)
+        our_scan = graph_us([(lambda: be.tree_scan_lower_bound(smp._sum_tree.values, CAPACITY, smp._sum_tree.capacity, mass))
+                             for _ in range(10)], dev)
+        out["tree_B256"] = {"reference_cuda_update_us": round(ref_upd, 1), "rlb_tree_update_us": round(our_upd, 2),
+                            "update_speedup": round(ref_upd / our_upd, 1),
+                            "reference_cuda_scan_lower_bound_us": round(ref_scan, 1),
+                            "rlb_tree_scan_lower_bound_us": round(our_scan, 2), "scan_speedup": round(ref_scan / our_scan, 1),
+                            "note": "reference CUDA tree = <<<1,1>>> leaf loop + one full-level launch per level per tree (eager; device time by CUDA events)"}
+        # restore our leaves' ancestors (tree_update above wrote random values into the product trees)
+        smp._sum_tree.load_leaves(leaves)
+        ml = leaves.clone()
+        smp._min_tree.load_leaves(torch.where(all_idx < len(rb.storage), ml, torch.full_like(ml, torch.finfo(ml.dtype).max)))
+    except Exception as e:  # noqa: BLE001
+        out["tree_error"] = f"{type(e).__name__}: {e}"[:200]
+    return out
+
+
+def run_ours(args) -> dict:
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    distributed = world > 1
-    if distributed:
+    if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+        try:
+            result = run_distributed(args, dev, rank, world)
+        finally:
+            pass
+        dist.barrier()
+        dist.destroy_process_group()
+        return result
+    return run_single(args, dev)
+
+
+def run_single(args, dev) -> dict:
+    from rl_b200 import ops
+    from rl_b200.graphs import CudaGraphStep
+
     be = ops.backend()
-    gbatch = BATCH * world
-    if distributed:
-        rb, g = build_sharded(dev, CAPACITY, world, rank)
-    else:
-        rb, g = build_buffer(dev, CAPACITY, seed=rank)
+    rb, g = build_buffer(dev, CAPACITY, seed=0)
     ring = gae_ring(dev, GAE_ROWS, GAE_T, g)
     ring8 = [(v, nv, r, d.view(torch.uint8), t.view(torch.uint8)) for v, nv, r, d, t in ring]
     R = len(ring)
-    td_err = torch.rand(gbatch, device=dev, generator=g)
+    td_err = torch.rand(BATCH, device=dev, generator=g)
     gs = (float(torch.tensor(GAMMA)), float(torch.tensor(GAMMA) * torch.tensor(LMBDA)))
 
     def sync_all():
         torch.cuda.synchronize()
-        if distributed:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     side_gae, side_upd = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     smp = rb.sampler
     smp.record_index_event = True
-    # optional: each sample also draws the NEXT sample's uniforms (same torch.rand calls, same order), taking the RNG
-    # kernel off the chain rand -> per_sample -> update.  Measured: 37.6 -> 37.1 us per step, so the headline keeps the
-    # plain call sequence
     smp.predraw = os.environ.get("RLB_BENCH_PREDRAW", "0") != "0"
 
     def make_step(slot: int):
@@ -322,7 +525,7 @@ def run_ours(args) -> dict:
 
         def step():
             # three independent chains of the same step run on three streams (fork / join with events):
-            #   main      rand -> per_sample -> gather [-> all-gather]
+            #   main      rand -> per_sample -> gather
             #   side_upd  update_priority(index): needs the sampled indices only, overlaps the gather
             #   side_gae  GAE of this step's rollout: independent of the replay path
             main = torch.cuda.current_stream(dev)
@@ -331,10 +534,7 @@ def run_ours(args) -> dict:
                 a, tg = be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
             batch = rb.sample()
             index = batch.get("index")
-            if distributed:
-                side_upd.wait_stream(main)           # global indices exist only after the all-gather
-            else:
-                side_upd.wait_event(smp.index_ready)
+            side_upd.wait_event(smp.index_ready)
             with torch.cuda.stream(side_upd):
                 rb.update_priority(index, td_err)    # fused pow + tree write-back
             main.wait_stream(side_upd)
@@ -358,83 +558,33 @@ def run_ours(args) -> dict:
     eager_steps = [make_eager_step(i) for i in range(R)]
 
     # ---- (1) eager: every call goes through the Python API
-    clocks = ClockSampler(local) if rank == 0 else None
+    clocks = ClockSampler(dev.index or 0)
     ms_eager = timed(lambda i: eager_steps[i % R](), args.steps, args.warmup, sync_all)
 
-    # ---- (2) the same steps captured once into CUDA graphs (one per GAE input set) and replayed.  With N > 1 the
-    # NCCL all-gather is issued eagerly between two captured halves: [local draw into the send buffer] and
-    # [weights + priority write-back + GAE].
+    # ---- (2) the same steps captured once into CUDA graphs (one per GAE input set) and replayed
     graphs, graph_err, ms_graph = None, None, None
     try:
         gen = rb.sampler._rng
-        if not distributed:
-            graphs = [CudaGraphStep(st, generators=[gen], warmup=1) for st in steps]
-            ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
-        elif rb._use_nvlink(dev):
-            # sharded + NVLink transport: the gather kernel itself broadcasts the rows into every rank's receive
-            # buffer and a signal-pad barrier closes the exchange -- no NCCL call, so the WHOLE step is one graph.
-            # Receive buffers are double-buffered: slot i uses buffer i % 2 (R is even), fixed at capture time.
-            def make_dist_step(slot: int):
-                v, nv, r, d8, t8 = ring8[slot]
-
-                def step():
-                    main = torch.cuda.current_stream(dev)
-                    side_gae.wait_stream(main)
-                    with torch.cuda.stream(side_gae):
-                        a, tg = be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
-                    rb.local_draw()
-                    rb.exchange()
-                    batch = rb.finalize()
-                    rb.update_priority(batch.get("index"), td_err)
-                    main.wait_stream(side_gae)
-                    return batch, a, tg
-
-                return step
-
-            graphs = [CudaGraphStep(make_dist_step(i), generators=[gen], warmup=2) for i in range(R)]  # 3 calls/slot
-            ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
-        else:
-            draw = CudaGraphStep(lambda: rb.local_draw(static_buffers=True), generators=[gen], warmup=1)
-
-            def make_tail(slot: int):
-                v, nv, r, d8, t8 = ring8[slot]
-
-                def tail():
-                    batch = rb.finalize()
-                    rb.update_priority(batch.get("index"), td_err)
-                    return batch, be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
-
-                return tail
-
-            rb.exchange()
-            tails = [CudaGraphStep(make_tail(i), warmup=1) for i in range(R)]
-
-            def graph_step(i):
-                draw()
-                rb.exchange()
-                return tails[i % R]()
-
-            ms_graph = timed(graph_step, args.steps, args.warmup, sync_all)
+        graphs = [CudaGraphStep(st, generators=[gen], warmup=1) for st in steps]
+        ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
+        # a longer replay run of the same graphs (the driver's --steps 20 makes the timed region < 1 ms)
+        ms_graph_long = timed(lambda i: graphs[i % R](), max(args.steps, 400), 5, sync_all)
     except Exception as err:
         import traceback
 
         graph_err = f"{type(err).__name__}: {err}"[:300]
-        print(f"[bench rank {rank}] CUDA-graph path failed, falling back to eager: {graph_err}\n"
+        print(f"[bench] CUDA-graph path failed, falling back to eager: {graph_err}\n"
               + "".join(traceback.format_exc().splitlines(True)[-6:]), file=sys.stderr, flush=True)
-        graphs, ms_graph = None, None
-        # a capture that died half-way leaves the generator in capture mode: give the sampler a fresh one
+        graphs, ms_graph, ms_graph_long = None, None, None
         torch.cuda.synchronize()
-        fresh = torch.Generator(device=dev).manual_seed(4242 + rank)
-        if hasattr(rb, "local"):
-            rb.local.set_rng(fresh)
-        else:
-            rb.set_rng(fresh)
+        fresh = torch.Generator(device=dev).manual_seed(4242)
+        rb.set_rng(fresh)
         g = fresh
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop()
 
     # ---- sub-metrics (eager, same method)
     ms_sample = timed(lambda i: rb.sample(), args.steps, 3, sync_all)
-    idx_pool = [torch.randint(0, CAPACITY * world, (gbatch,), device=dev, generator=g) for _ in range(8)]
+    idx_pool = [torch.randint(0, CAPACITY, (BATCH,), device=dev, generator=g) for _ in range(8)]
     ms_update = timed(lambda i: rb.update_priority(idx_pool[i % 8], td_err), args.steps, 3, sync_all)
 
     def gae_only(i):
@@ -443,19 +593,64 @@ def run_ours(args) -> dict:
 
     ms_gae = timed(gae_only, args.steps, 3, sync_all)
 
-    # ---- (3) end to end with HOST buffers: H2D of the step's inputs and D2H of the step's results every step.
-    # Three independent lanes (stream + pinned buffers + device staging) rotate so that one step's D2H overlaps
-    # the next steps' H2D and compute (PCIe is full duplex); every step still synchronises on its own results.
+    ms_e2e, h2d, d2h, n_lanes = e2e_run(args, dev, rb, ring, td_err, gs, be, sync_all, slice(None), 3)
+
+    hbm_peak, peak_src = peaks()
+    roof = kernel_roofline(dev, rb, ring, hbm_peak, peak_src)
+    try:
+        roof["gae_shapes"] = gae_shape_sweep(dev, be, hbm_peak)
+    except Exception as e:  # noqa: BLE001
+        roof["gae_shapes"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:
+        comp = component_times(dev, rb, ring8, td_err, gs, be)
+    except Exception as e:  # noqa: BLE001
+        comp = {"error": f"{type(e).__name__}: {e}"[:200]}
+    write_path = write_path_probe(dev, rb, g, hbm_peak)
+    ref_gpu = reference_gpu_kernels(dev, rb, ring, td_err)
+    cpu = cpu_baseline_run(steps=None)
+    if "error" not in comp and cpu.get("phases_ms"):
+        ph = cpu["phases_ms"]
+        comp["vs_cpu"] = {"sample(tree+gather)": round((ph["tree_sample"] + ph["gather"]) * 1e3 / comp["sample_us"], 1),
+                          "update_priority": round(ph["tree_update"] * 1e3 / comp["update_priority_us"], 1),
+                          "gae": round(ph["gae"] * 1e3 / comp["gae_us"], 1)}
+    ms = ms_graph if ms_graph is not None else ms_eager
+    n_leaves = len(rb.storage._leaves)
+    cfg = make_config(1)
+    detail = {"n_leaves": n_leaves,
+              "launch": "cuda_graph replay of the public-API step" if ms_graph is not None else "eager python API"}
+    result = {
+        "metric": METRIC, "value": round(TRANSITIONS_PER_STEP / (ms * 1e-3), 1), "unit": "transitions/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "impl_detail": detail,
+        "e2e": {"value": round(TRANSITIONS_PER_STEP / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5),
+                "note": f"eager python API, pinned host buffers, {n_lanes} lane(s): with several lanes D2H overlaps the next steps' H2D + compute"},
+        "gpu_launches": 4 * args.steps,  # ours per step: per_sample, gather, update, gae (torch.rand is torch's)
+        "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
+                      "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),
+                      "graph_ms_per_step_long_run": None if ms_graph_long is None else round(ms_graph_long, 5),
+                      "graph_error": graph_err,
+                      "eager_value": round(TRANSITIONS_PER_STEP / (ms_eager * 1e-3), 1),
+                      "eager_sample_us": round(ms_sample * 1e3, 2), "eager_update_priority_us": round(ms_update * 1e3, 2),
+                      "eager_gae_us": round(ms_gae * 1e3, 2),
+                      "components_graph_replayed": comp,
+                      "write_path": write_path,
+                      "reference_gpu": ref_gpu},
+        "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+    }
+    return result
+
+
+def e2e_run(args, dev, rb, ring, td_err, gs, be, sync_all, own, n_lanes):
+    """End to end with HOST buffers: H2D of the step's inputs and D2H of the step's results every step.  Independent
+    lanes (stream + pinned buffers + device staging) rotate so that one step's D2H overlaps the next steps' H2D and
+    compute (PCIe is full duplex); every step still synchronises on its own results."""
+    R = len(ring)
     pin = lambda t: t.cpu().pin_memory()
     sample0 = rb.sample()
     out_keys = list(sample0.keys(True, True))
-    # N > 1: every rank delivers ITS rows of the gathered batch to the host (the job as a whole lands the global
-    # minibatch in host memory once), plus its own GAE outputs
-    own = slice(rank * BATCH, (rank + 1) * BATCH) if distributed else slice(None)
     lanes = []
-    # N > 1: one lane -- the sharded buffer's two receive buffers are overwritten by the PEERS' next-but-one draw,
-    # which is only ordered against work on the sampling stream
-    n_lanes = 1 if distributed else 3
     for lane in range(n_lanes):
         s = torch.cuda.Stream(dev)
         host_in = tuple(pin(x) for x in ring[lane % R])
@@ -491,111 +686,418 @@ def run_ours(args) -> dict:
             e2e_body(L)
             L["done"].record()
 
-    def timed_e2e(steps_, warmup_):
-        for i in range(warmup_):
-            e2e_step(i)
-        sync_all()
-        cur = torch.cuda.current_stream()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(cur)
-        for L in lanes:
-            L["stream"].wait_event(e0)
-        for i in range(steps_):
-            e2e_step(warmup_ + i)
-        for L in lanes:
-            cur.wait_stream(L["stream"])
-        e1.record(cur)
-        sync_all()
-        return e0.elapsed_time(e1) / steps_
-
-    ms_e2e = timed_e2e(args.steps, args.warmup)
-
-    # ---- max over ranks
-    vals = [ms_eager, ms_graph if ms_graph is not None else -1.0, ms_e2e, ms_sample, ms_update, ms_gae]
-    if distributed:
-        t = torch.tensor(vals, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        vals = t.tolist()
-    ms_eager, ms_graph, ms_e2e, ms_sample, ms_update, ms_gae = vals
-    if ms_graph is not None and ms_graph <= 0:
-        ms_graph = None
-
-    hbm_peak, peak_src = peaks()
-    transport = None
-    if distributed:
-        transport = ("gather kernel broadcasts over NVLink peer memory + signal-pad barrier" if rb._symm not in (None, False)
-                     else "NCCL all-gather issued eagerly between two graphs")
-    result = None
-    if rank == 0:
-        roof = kernel_roofline(dev, rb, ring, hbm_peak, peak_src) if world == 1 else None
-        cpu = cpu_baseline_run(steps=None) if world == 1 else None
-        per_step = TRANSITIONS_PER_STEP * world
-        ms = ms_graph if ms_graph is not None else ms_eager
-        n_leaves = len(rb.storage._leaves)
-        result = {
-            "metric": METRIC, "value": round(per_step / (ms * 1e-3), 1), "unit": "transitions/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2 PER sample+update B=256 @1M Atari transitions ({n_leaves} leaves) + C3 GAE [4096,128]",
-                       "capacity_per_gpu": CAPACITY, "batch_per_gpu": BATCH, "gae_shape": [GAE_ROWS, GAE_T, 1],
-                       "arithmetic": "fp32 priorities / trees / GAE, byte-exact u8 row moves, int64 indices",
-                       "alpha": ALPHA, "beta": BETA, "gamma": GAMMA, "lmbda": LMBDA,
-                       "launch": ("cuda_graph replay of the public-API step" + (f" ({transport})" if world > 1 else "")) if ms_graph is not None else "eager python API",
-                       "parallelism": f"capacity-sharded x{world}, {transport}" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (56 GB storage, random rows; GAE inputs rotate through >160 MB)"},
-            "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5),
-                    "note": f"eager python API, pinned host buffers, {n_lanes} lane(s): with several lanes D2H overlaps the next steps' H2D + compute"},
-            "gpu_launches": (4 if world == 1 else 6) * args.steps,  # ours per step: per_sample, gather, update, gae [+ pack, weights]
-            "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
-                          "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),
-                          "graph_error": graph_err,
-                          "eager_value": round(per_step / (ms_eager * 1e-3), 1),
-                          "sample_us": round(ms_sample * 1e3, 2), "update_priority_us": round(ms_update * 1e3, 2),
-                          "gae_us": round(ms_gae * 1e3, 2),
-                          "sample_transitions_per_s": round(gbatch / (ms_sample * 1e-3), 1),
-                          "gae_transitions_per_s": round(GAE_ROWS * GAE_T * world / (ms_gae * 1e-3), 1)},
-            "clocks": clk,
-        }
-        if roof:
-            result["roofline"] = roof
-        if cpu:
-            result["cpu_baseline"] = cpu
-        if world == 1:
-            result["breakdown"]["write_path"] = write_path_probe(dev, rb, g, hbm_peak)
-    if distributed:
-        dist.barrier()
-        dist.destroy_process_group()
-    return result
+    for i in range(args.warmup):
+        e2e_step(i)
+    sync_all()
+    cur = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    for L in lanes:
+        L["stream"].wait_event(e0)
+    for i in range(args.steps):
+        e2e_step(args.warmup + i)
+    for L in lanes:
+        cur.wait_stream(L["stream"])
+    e1.record(cur)
+    sync_all()
+    return e0.elapsed_time(e1) / args.steps, h2d, d2h, n_lanes
 
 
-def build_sharded(dev, capacity_per_rank: int, world: int, rank: int):
-    """One 1M shard per rank of a capacity-sharded buffer (weak scaling), filled with synthetic transitions."""
+# ------------------------------------------------------------------------------------------- N > 1
+def make_rows(kind: str, n: int, dev, g):
     from rl_b200.data import TensorDict
-    from rl_b200.data.sharded import ShardedPrioritizedReplayBuffer
 
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    rb = ShardedPrioritizedReplayBuffer(alpha=ALPHA, beta=BETA, capacity=capacity_per_rank * world,
-                                        batch_size=BATCH * world, device=dev, generator=g)
-    chunk = 50_000
-    for lo in range(0, capacity_per_rank, chunk):
-        n = min(chunk, capacity_per_rank - lo)
-        rb.extend(TensorDict({
+    if kind == "atari":     # DQN-shaped Atari transition: 56 462 B + td_error
+        return TensorDict({
             "pixels": torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
             "action": torch.randint(0, 18, (n, 1), device=dev, generator=g),
             "next": {"pixels": torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
                      "reward": torch.randn(n, device=dev, generator=g),
                      "done": torch.rand(n, 1, device=dev, generator=g) < 0.01,
                      "terminated": torch.rand(n, 1, device=dev, generator=g) < 0.01},
-            "td_error": torch.rand(n, device=dev, generator=g)}, [n]))
+            "td_error": torch.rand(n, device=dev, generator=g)}, [n])
+    # SAC continuous control (C5): obs / next obs f32[376], action f32[17], reward, done, terminated: 3 082 B + td_error
+    return TensorDict({
+        "observation": torch.randn(n, 376, device=dev, generator=g),
+        "action": torch.randn(n, 17, device=dev, generator=g),
+        "next": {"observation": torch.randn(n, 376, device=dev, generator=g),
+                 "reward": torch.randn(n, device=dev, generator=g),
+                 "done": torch.rand(n, 1, device=dev, generator=g) < 0.01,
+                 "terminated": torch.rand(n, 1, device=dev, generator=g) < 0.01},
+        "td_error": torch.rand(n, device=dev, generator=g)}, [n])
+
+
+def build_sharded(dev, capacity_per_rank: int, world: int, rank: int, batch_per_rank: int = BATCH, kind: str = "atari",
+                  fresh_rows: bool = True):
+    """One shard per rank of a capacity-sharded buffer (weak scaling), filled with synthetic transitions.
+    fresh_rows=False replicates one random chunk (new priorities per chunk): same bytes in HBM, much faster to fill."""
+    from rl_b200.data.sharded import ShardedPrioritizedReplayBuffer
+
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    rb = ShardedPrioritizedReplayBuffer(alpha=ALPHA, beta=BETA, capacity=capacity_per_rank * world,
+                                        batch_size=batch_per_rank * world, device=dev, generator=g, pipeline=True,
+                                        n_buffers=N_BUFFERS)
+    chunk = 50_000 if kind == "atari" else 250_000
+    td = None
+    for lo in range(0, capacity_per_rank, chunk):
+        n = min(chunk, capacity_per_rank - lo)
+        if td is None or fresh_rows or n != td.batch_size[0]:
+            td = make_rows(kind, n, dev, g)
+        else:
+            td.set("td_error", torch.rand(n, device=dev, generator=g))
+        rb.extend(td)
     return rb, g
+
+
+def dist_parity_check(rb, dev, rank: int, world: int) -> dict:
+    """Warm-up assertion of the N > 1 run (SURVEY 8e parity row), product code only: this rank's draw must equal
+    what the STAND-ALONE tree kernels (rlb_tree_query / rlb_tree_scan_lower_bound, not the fused sampler) give for the
+    same uniforms; the gathered batch must equal the rank-order concatenation (NCCL all-gather) of aten::index rows of
+    those draws; weights and indices must be identical on every rank.  The oracle-pinned version of the same statement
+    is tests/mgpu_check.py (tests/test_mgpu.py)."""
+    import torch.distributed as dist
+    from rl_b200 import ops
+
+    be = ops.backend()
+    smp, st = rb.sampler, rb.storage
+    smp._maybe_init_from_storage(st)
+    gen = smp._rng
+    state = gen.get_state()
+    batch = rb.sample_now()
+    torch.cuda.synchronize(dev)
+    rb.check_exchange()
+    g2 = torch.Generator(device=dev)
+    g2.set_state(state)
+    b_loc = rb._batch_size // world
+    u = torch.rand(b_loc, device=dev, generator=g2)
+    n = len(st)
+    cap = smp._sum_tree.capacity
+    zero, ln = torch.zeros(1, dtype=torch.long, device=dev), torch.full((1,), n, dtype=torch.long, device=dev)
+    p_sum = be.tree_query(smp._sum_tree.values, smp._max_capacity, cap, False, zero, ln, True)
+    idx = be.tree_scan_lower_bound(smp._sum_tree.values, smp._max_capacity, cap, u * p_sum).clamp_max(n - 1)
+    ok = bool(torch.equal(idx, rb.local_index))
+    detail = [] if ok else ["local draw != stand-alone tree kernels"]
+
+    def gathered(x):
+        out = torch.empty((world * x.shape[0], *x.shape[1:]), dtype=x.dtype, device=dev)
+        dist.all_gather_into_tensor(out.view(torch.uint8) if x.dtype == torch.bool else out,
+                                    x.contiguous().view(torch.uint8) if x.dtype == torch.bool else x.contiguous())
+        return out
+
+    if not torch.equal(batch.get("index"), gathered(idx + rank * rb.shard_capacity)):
+        ok = False
+        detail.append("index")
+    keys = [k for k in batch.keys(True, True) if k not in ("index", "priority_weight")]
+    data = unflatten_leaves(st)
+    for k in keys:
+        if not torch.equal(batch.get(k), gathered(data[k][idx])):
+            ok = False
+            detail.append(str(k))
+    w = batch.get("priority_weight")
+    w0 = w.clone()
+    dist.broadcast(w0, 0)
+    if not torch.equal(w, w0):
+        ok = False
+        detail.append("weights differ between ranks")
+    flag = torch.tensor([int(ok)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"parity_checked": bool(flag.item()),
+            "parity_detail": "gathered batch == rank-order concat of aten::index rows of each rank's draw; draw == "
+                             "stand-alone tree kernels for the same uniforms; weights identical on all ranks"
+                             if flag.item() else "FAILED on some rank: " + ",".join(detail)}
+
+
+def unflatten_leaves(st) -> dict:
+    """{key: [N, ...] storage leaf} for a TensorDict-structured storage."""
+    from rl_b200.data.storages import unflatten_data
+
+    td = unflatten_data(st._leaves, st._spec, (st._leaves[0].shape[0],))
+    return {k: td.get(k) for k in td.keys(True, True)}
+
+
+def exchange_probe(rb, dev, world: int) -> dict:
+    """The fused gather + NVLink broadcast kernel on its own: graph of N_BUFFERS launches (rotating receive slots), all
+    ranks at once.  Device time per launch and the resulting per-GPU NVLink egress / ingress rate."""
+    import torch.distributed as dist
+    from rl_b200 import ops
+
+    be = ops.backend()
+    st, lay = rb.storage, rb._layout
+    bufs, _, _, peers = rb._symm
+    b_loc = rb._batch_size // world
+    g = torch.Generator(device=dev).manual_seed(17 + rb.rank)
+    idxs = [torch.randint(0, len(st), (b_loc,), device=dev, generator=g) for _ in range(2 * N_BUFFERS)]
+    fns = []
+    for k, ix in enumerate(idxs):
+        send = bufs[k % N_BUFFERS][rb.rank * b_loc:(rb.rank + 1) * b_loc]
+        fns.append(lambda ix=ix, send=send: be.gather(st._leaves, ix, len(st), out=lay.leaf_views(send), peer_delta=peers))
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    us = graph_us(fns, dev)
+    t = torch.tensor([us], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    us = float(t.item())
+    payload = b_loc * sum(c[1] for c in lay.cols)
+    dist.barrier()
+    return {"gather_broadcast_us": round(us, 2), "payload_bytes_per_rank": payload,
+            "nvlink_egress_GBps": round((world - 1) * payload / us / 1e3, 1),
+            "frac_of_nvlink_per_dir": round((world - 1) * payload / us / 1e3 / NVLINK_GBPS_PER_DIR, 3)}
+
+
+def run_distributed(args, dev, rank: int, world: int) -> dict:
+    import torch.distributed as dist
+    from rl_b200 import ops
+    from rl_b200.graphs import CudaGraphStep
+
+    be = ops.backend()
+    gbatch = BATCH * world
+    rb, g = build_sharded(dev, CAPACITY, world, rank)
+    ring = gae_ring(dev, GAE_ROWS, GAE_T, g)
+    ring8 = [(v, nv, r, d.view(torch.uint8), t.view(torch.uint8)) for v, nv, r, d, t in ring]
+    R = len(ring)
+    td_err = torch.rand(gbatch, device=dev, generator=g)
+    td_loc = td_err[rank * BATCH:(rank + 1) * BATCH].contiguous()
+    gs = (float(torch.tensor(GAMMA)), float(torch.tensor(GAMMA) * torch.tensor(LMBDA)))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    parity = dist_parity_check(rb, dev, rank, world)
+    nvlink = rb._symm not in (None, False)
+    side_gae, side_upd = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    rb.record_index_event = True
+
+    def make_step(slot: int):
+        v, nv, r, d8, t8 = ring8[slot]
+
+        def step():
+            # main      rand -> per_sample -> gather + NVLink broadcast -> trailers + publish   (draw k)
+            # fin       wait for the flags of draw k-1 -> importance weights                    (inside rb.sample)
+            # side_upd  priority write-back of draw k's local rows: needs the sampled indices only
+            # side_gae  GAE of this step's rollout
+            main = torch.cuda.current_stream(dev)
+            side_gae.wait_stream(main)
+            with torch.cuda.stream(side_gae):
+                a, tg = be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
+            batch = rb.sample(slot=slot if nvlink else None)     # returns the finalised draw k-1
+            side_upd.wait_event(rb.index_ready)
+            with torch.cuda.stream(side_upd):
+                rb.update_local_priority(td_loc)
+            main.wait_stream(side_upd)
+            main.wait_stream(side_gae)
+            return batch, a, tg
+
+        return step
+
+    def make_eager_step(slot: int):
+        v, nv, r, d8, t8 = ring8[slot]
+
+        def step():
+            batch = rb.sample()
+            rb.update_priority(batch.get("index"), td_err)
+            a, tg = be.gae(v, nv, r, d8, t8, gs[0], gs[1], GAE_ROWS, GAE_T, 1)
+            return batch, a, tg
+
+        return step
+
+    eager_steps = [make_eager_step(i) for i in range(R)]
+    clocks = ClockSampler(dev.index or 0) if rank == 0 else None
+    ms_eager = timed(lambda i: eager_steps[i % R](), args.steps, args.warmup, sync_all)
+
+    graphs, graph_err, ms_graph, ms_graph_long = None, None, None, None
+    try:
+        if not nvlink:
+            raise RuntimeError("NVLink transport unavailable (symmetric memory): the NCCL all-gather cannot be captured with the step")
+        gen = rb.sampler._rng
+        graphs = [CudaGraphStep(make_step(i), generators=[gen], warmup=1) for i in range(R)]
+        ms_graph = timed(lambda i: graphs[i % R](), args.steps, max(args.warmup, N_BUFFERS), sync_all)
+        ms_graph_long = timed(lambda i: graphs[i % R](), max(args.steps, 200), N_BUFFERS, sync_all)
+        torch.cuda.synchronize()
+        rb.check_exchange()
+    except Exception as err:
+        import traceback
+
+        graph_err = f"{type(err).__name__}: {err}"[:300]
+        print(f"[bench rank {rank}] CUDA-graph path failed, falling back to eager: {graph_err}\n"
+              + "".join(traceback.format_exc().splitlines(True)[-6:]), file=sys.stderr, flush=True)
+        graphs, ms_graph, ms_graph_long = None, None, None
+        torch.cuda.synchronize()
+        fresh = torch.Generator(device=dev).manual_seed(4242 + rank)
+        rb.local.set_rng(fresh)
+        g = fresh
+    clk = clocks.stop() if clocks else None
+
+    ms_sample = timed(lambda i: rb.sample(), args.steps, 3, sync_all)
+    own = slice(rank * BATCH, (rank + 1) * BATCH)
+    ms_e2e, h2d, d2h, n_lanes = e2e_run(args, dev, rb, ring, td_err, gs, be, sync_all, own, 1)
+    xprobe = None
+    if nvlink:
+        try:
+            xprobe = exchange_probe(rb, dev, world)
+        except Exception as e:  # noqa: BLE001
+            xprobe = {"error": f"{type(e).__name__}: {e}"[:200]}
+
+    vals = [ms_eager, ms_graph if ms_graph is not None else -1.0, ms_e2e, ms_sample,
+            ms_graph_long if ms_graph_long is not None else -1.0]
+    t = torch.tensor(vals, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_eager, ms_graph, ms_e2e, ms_sample, ms_graph_long = t.tolist()
+    if ms_graph <= 0:
+        ms_graph = None
+    if ms_graph_long <= 0:
+        ms_graph_long = None
+    payload = BATCH * sum(c[1] for c in rb._layout.cols)
+    row_packed = rb._layout.row
+    n_leaves = len(rb.storage._leaves)
+    # free the C2 buffer before the bigger workloads
+    del graphs, eager_steps, rb, ring, ring8
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    extra = {}
+    for name in ("c4", "c5"):
+        try:
+            extra[name] = sharded_workload(name, dev, rank, world, max(args.steps, 50), be)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+
+            extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            print(f"[bench rank {rank}] workload {name} failed:\n" + "".join(traceback.format_exc().splitlines(True)[-8:]),
+                  file=sys.stderr, flush=True)
+        gc.collect()
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    per_step = TRANSITIONS_PER_STEP * world
+    ms = ms_graph if ms_graph is not None else ms_eager
+    ingress = (world - 1) * BATCH * row_packed
+    transport = ("gather kernel stores rows into every rank's symmetric receive buffer over NVLink peer memory; "
+                 "flag release/acquire closes the exchange; sample() returns the previous draw" if nvlink
+                 else "NCCL all-gather (eager)")
+    cfg = make_config(world)
+    detail = {"n_leaves": n_leaves, "transport": transport,
+              "launch": ("cuda_graph replay of the public-API step" if ms_graph is not None else "eager python API")}
+    result = {
+        "metric": METRIC, "value": round(per_step / (ms * 1e-3), 1), "unit": "transitions/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "impl_detail": detail,
+        "e2e": {"value": round(per_step / (ms_e2e * 1e-3), 1), "unit": "transitions/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 5),
+                "note": "eager python API, pinned host buffers; every rank lands ITS rows of the global minibatch + its GAE outputs on the host"},
+        "gpu_launches": 6 * args.steps,  # ours per step: per_sample, gather(+broadcast), pack(+publish), weights(+wait), update, gae
+        **parity,
+        "nvlink": {"ingress_bytes_per_step_per_gpu": ingress, "egress_bytes_per_step_per_gpu": ingress,
+                   "nvlink_ingress_GBps": round(ingress / (ms * 1e-3) / 1e9, 1),
+                   "nvlink_egress_GBps": round(ingress / (ms * 1e-3) / 1e9, 1),
+                   "wire_bound_us_per_step": round(ingress / (NVLINK_GBPS_PER_DIR * 1e9) * 1e6, 1),
+                   "payload_bytes_per_rank": payload, "exchange_kernel": xprobe,
+                   "note": "every rank receives the whole global minibatch (all-gather semantics): ingress = egress = (N-1) x 256 packed rows"},
+        "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
+                      "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),
+                      "graph_ms_per_step_long_run": None if ms_graph_long is None else round(ms_graph_long, 5),
+                      "graph_error": graph_err, "eager_value": round(per_step / (ms_eager * 1e-3), 1),
+                      "eager_sample_us": round(ms_sample * 1e3, 2)},
+        "clocks": clk,
+        "c4": extra.get("c4"), "c5": extra.get("c5"),
+    }
+    return result
+
+
+def sharded_workload(name: str, dev, rank: int, world: int, steps: int, be) -> dict:
+    """BASELINE.json configs[3] / [4] at their per-shard sizes (weak-scaled below 8 GPUs):
+    c4  10M-slot sharded PER of DQN-shaped Atari transitions, global batch 1024 at 8 GPUs (1.25M slots, 128 rows per rank)
+    c5  50M-slot HBM-resident SAC buffer (obs 376 / act 17 f32), global batch 4096 at 8 GPUs (6.25M slots, 512 rows per
+        rank) + TD-error priority write-back of the returned batch.
+    A step = rb.sample() [+ write-back]; captured through the public API, replayed cyclically over the receive slots."""
+    import torch.distributed as dist
+    from rl_b200.graphs import CudaGraphStep
+
+    spec = {"c4": dict(cap=1_250_000, b_loc=128, kind="atari"), "c5": dict(cap=6_250_000, b_loc=512, kind="mujoco")}[name]
+    cap, b_loc, kind = spec["cap"], spec["b_loc"], spec["kind"]
+    rb, g = build_sharded(dev, cap, world, rank, batch_per_rank=b_loc, kind=kind, fresh_rows=False)
+    gb = b_loc * world
+    td_err = torch.rand(gb, device=dev, generator=g)
+    td_loc = td_err[rank * b_loc:(rank + 1) * b_loc].contiguous()
+    rb.record_index_event = True
+    side = torch.cuda.Stream(dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    parity = dist_parity_check(rb, dev, rank, world)
+    nvlink = rb._symm not in (None, False)
+
+    def make_step(slot: int):
+        def step():
+            main = torch.cuda.current_stream(dev)
+            batch = rb.sample(slot=slot if nvlink else None)
+            if name == "c5":
+                # TD-error write-back of the batch the learner just consumed (the returned draw): global indices,
+                # replicated priorities; this rank rewrites the rows it owns
+                rb.update_priority(batch.get("index"), td_err)
+            else:
+                side.wait_event(rb.index_ready)
+                with torch.cuda.stream(side):
+                    rb.update_local_priority(td_loc)
+                main.wait_stream(side)
+            return batch
+
+        return step
+
+    gen = rb.sampler._rng
+    out = {}
+    if nvlink:
+        graphs = [CudaGraphStep(make_step(i), generators=[gen], warmup=1) for i in range(N_BUFFERS)]
+        ms = timed(lambda i: graphs[i % N_BUFFERS](), steps, 2 * N_BUFFERS, sync_all)
+        torch.cuda.synchronize()
+        rb.check_exchange()
+        launch = "cuda_graph replay"
+    else:
+        eager = make_step(0)
+        ms = timed(lambda i: eager(), steps, 4, sync_all)
+        launch = "eager (NCCL transport)"
+    ms_eager = timed(lambda i: rb.sample(), steps, 3, sync_all)
+    wb = None
+    if name == "c5":
+        # the write-back alone, both ways: the returned index tensor (this rank's 512 rows, one launch) and an arbitrary
+        # replicated global index vector of 4096 entries filtered inside the kernel (general path)
+        batch = rb.sample()
+        gi = batch.get("index")
+        fast = graph_us([(lambda: rb.update_priority(gi, td_err)) for _ in range(10)], dev)
+        gi2 = gi.clone()
+        general = graph_us([(lambda: rb.update_priority(gi2, td_err)) for _ in range(10)], dev)
+        wb = {"returned_batch_us": round(fast, 2), "general_global_index_us": round(general, 2), "n_global": gb}
+    t = torch.tensor([ms, ms_eager], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_eager = t.tolist()
+    lay = rb._layout
+    row = sum(c[1] for c in lay.cols)
+    ingress = (world - 1) * b_loc * lay.row
+    out = {"workload": ("C4 sharded PER 10M DQN-shaped Atari transitions, batch 1024 @ 8 GPUs" if name == "c4" else
+                        "C5 50M HBM-resident SAC transitions (obs 376 / act 17 f32), batch 4096 @ 8 GPUs + TD-error write-back"),
+           "n_gpus": world, "capacity_global": cap * world, "capacity_per_gpu": cap, "global_batch": gb,
+           "batch_per_gpu": b_loc, "row_bytes": row, "hbm_bytes_per_gpu": cap * row,
+           "ms_per_step": round(ms, 5), "transitions_per_s": round(gb / (ms * 1e-3), 1), "launch": launch,
+           "eager_sample_us": round(ms_eager * 1e3, 2),
+           "nvlink_bytes_per_step_per_gpu": ingress, "nvlink_ingress_GBps": round(ingress / (ms * 1e-3) / 1e9, 1),
+           "wire_bound_us_per_step": round(ingress / (NVLINK_GBPS_PER_DIR * 1e9) * 1e6, 2),
+           "writeback": wb, "matches_named_config": world == 8, **parity}
+    del rb
+    return out
 
 
 # ------------------------------------------------------------------------------------------- reference arm
 def cpu_baseline_run(steps: int | None, warmup: int = 2) -> dict:
     """The reference's own CPU path on the host cores: compiled reference segment trees (oracle/_ref/cpu) under
     the restated sampler glue, aten::index gather on CPU tensors, and the faster of the reference's two GAE code
-    paths.  Bounded sample: a 20k-row CPU storage (gather cost is per row, not per capacity) and ~10-20 s of work."""
+    paths.  Bounded sample: a 20k-row CPU storage (gather cost is per row, not per capacity) and ~10-20 s of work; the
+    timed run is repeated three times and the MEDIAN is reported (the host is shared: single runs vary 2x)."""
     from oracle import gae_torch
     from oracle import per_oracle as po
     from oracle.ref_loader import reference_trees
@@ -640,32 +1142,48 @@ def cpu_baseline_run(steps: int | None, warmup: int = 2) -> dict:
             if t < best_gather[1]:
                 best_gather = (c, t)
     gae_fn = gae_torch.loop_gae if best_gae[0] == "loop" else gae_torch.vec_gae
-    t_loop = t_vec = best_gae[2]
+    phases = {"tree_sample": 0.0, "gather": 0.0, "tree_update": 0.0, "gae": 0.0}
 
     def step():
+        t0 = time.perf_counter()
         torch.set_num_threads(best_gather[0])
         idx, w = smp.sample(CAPACITY, BATCH, generator=g)
+        t1 = time.perf_counter()
         ridx = idx % rows  # bounded storage: same number of random 28 KB rows touched
         batch = {k: x[ridx] for k, x in store.items()}
+        t2 = time.perf_counter()
         smp.update_priority(idx, td)
+        t3 = time.perf_counter()
         torch.set_num_threads(best_gae[1])
         with torch.no_grad():
             a, t = gae_fn(gm, lm, v, nv, r, done, term)
+        t4 = time.perf_counter()
+        phases["tree_sample"] += t1 - t0
+        phases["gather"] += t2 - t1
+        phases["tree_update"] += t3 - t2
+        phases["gae"] += t4 - t3
         return batch, a, t
 
     for _ in range(warmup):
         step()
     if steps is None:
         t1 = t_of(step, 2)
-        steps = max(5, min(400, int(12.0 / max(t1, 1e-4))))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
+        steps = max(5, min(400, int(4.0 / max(t1, 1e-4))))
+    runs = []
+    for _ in range(3):
+        for k in phases:
+            phases[k] = 0.0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        runs.append(((time.perf_counter() - t0) / steps, {k: v / steps * 1e3 for k, v in phases.items()}))
+    runs.sort(key=lambda x: x[0])
+    dt, ph = runs[1]
     return {"value": round(TRANSITIONS_PER_STEP / dt, 1), "unit": "transitions/s",
             "cores": max(best_gather[0], best_gae[1]), "host_cores": cores, "kind": kind,
-            "ms_per_step": round(dt * 1e3, 3), "steps": steps,
-            "sample": (f"{steps} steps of [reference C++ SumSegmentTree/MinSegmentTree sample+update B=256 @1M "
+            "ms_per_step": round(dt * 1e3, 3), "steps": steps, "cpu_storage_rows": rows,
+            "runs_ms_per_step": [round(x[0] * 1e3, 3) for x in runs], "phases_ms": {k: round(v, 4) for k, v in ph.items()},
+            "sample": (f"median of 3 x {steps} steps of [reference C++ SumSegmentTree/MinSegmentTree sample+update B=256 @1M "
                        f"(single-threaded by construction) + aten::index gather of 256 Atari transitions from a "
                        f"{rows}-row CPU storage ({best_gather[0]} threads, {best_gather[1] * 1e3:.2f} ms) + "
                        f"{best_gae[0]} GAE [4096,128] ({best_gae[1]} threads, {best_gae[2] * 1e3:.1f} ms)]; thread "
@@ -677,12 +1195,12 @@ def run_reference(args) -> dict | None:
     if rank != 0:
         return None
     cpu = cpu_baseline_run(steps=args.steps, warmup=args.warmup)
+    cfg = make_config(world)
     return {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "transitions/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "C2 PER sample+update B=256 @1M Atari transitions (56462 B/row) + C3 GAE [4096,128]",
-                       "note": "reference CPU implementation on the host cores; rank 0 only"},
+            "data": "synthetic", "config": cfg,
+            "impl_note": "reference CPU implementation on the host cores; rank 0 only",
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 

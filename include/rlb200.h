@@ -57,6 +57,7 @@ extern "C" {
 #define RLB_STATUS_NONPOS_PSUM 2  /* sample: p_sum <= 0  (samplers.py:911-912, CPU-only check there) */
 #define RLB_STATUS_NONPOS_PMIN 4  /* sample: p_min <= 0  (samplers.py:913-914) */
 #define RLB_STATUS_BACKOFF_FAIL 8 /* sample: zero-weight back-off ran below index 0 (samplers.py:940-941) */
+#define RLB_STATUS_EXCHANGE_TIMEOUT 16 /* sharded exchange: a peer's rows did not arrive within the time limit */
 
 typedef void *rlb_stream_t; /* cudaStream_t */
 
@@ -194,14 +195,25 @@ int rlb_scatter(const void *const *src /*[host]*/, void *const *dst /*[host]*/,
  * (8-byte aligned).  rlb_shard_pack fills the trailer of the B local rows from rlb_per_sample's outputs
  * (index + index_base, leaf, psum_pmin); rlb_shard_weights reads the trailers of the B gathered rows and
  * writes  w_i = ((p_i/S_r) / min_b(m_b/S_b)) ** -beta  (= samplers.py:945-953 for one shard) plus,
- * optionally, a contiguous copy of the global indices. */
+ * optionally, a contiguous copy of the global indices.
+ *
+ * Split-phase exchange (NVLink transport, `flags` != NULL): `flags` is this rank's array of one uint64 per rank
+ * inside its symmetric receive allocation (zero-initialised; peers address it with the same `peer_delta` as the
+ * rows).  rlb_shard_pack -- enqueued after the rlb_gather that pushed the rows into every peer -- increments
+ * *seq_counter and RELEASE-stores the new value (system scope) into slot `rank` of every destination's flags.
+ * rlb_shard_weights increments *wait_counter and ACQUIRE-spins until all `n_ranks` slots of its own flags have
+ * reached that value (at most `timeout_s` seconds, then RLB_STATUS_EXCHANGE_TIMEOUT is ORed into *status and the
+ * kernel carries on), then computes the weights.  Both counters live in device memory and are advanced by the
+ * kernels, so a captured step replays correctly; the i-th wait pairs with the i-th publish of every rank. */
 int rlb_shard_pack(void *rows /*[dev] B x row_bytes*/, int64_t row_bytes, int64_t meta_offset,
                    const int64_t *index /*[dev] B*/, const float *leaf /*[dev] B*/,
                    const float *psum_pmin /*[dev] 2*/, int64_t index_base, int64_t B,
-                   const int64_t *peer_delta /*[host] or NULL*/, int n_peers, rlb_stream_t stream);
+                   const int64_t *peer_delta /*[host] or NULL*/, int n_peers, uint64_t *flags /*[dev] or NULL*/,
+                   uint64_t *seq_counter /*[dev] or NULL*/, int rank, rlb_stream_t stream);
 int rlb_shard_weights(const void *rows /*[dev] B x row_bytes*/, int64_t row_bytes, int64_t meta_offset, int64_t B,
                       double beta, float *weight_out /*[dev] B*/, int64_t *index_out /*[dev] B or NULL*/,
-                      rlb_stream_t stream);
+                      const uint64_t *flags /*[dev] or NULL*/, uint64_t *wait_counter /*[dev] or NULL*/, int n_ranks,
+                      double timeout_s, int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Generalized advantage estimation -- replaces vec_generalized_advantage_estimate /

@@ -12,17 +12,24 @@ every rank and assembles the global minibatch with ONE all-gather over NVLink:
     the gather, normalised over the WHOLE buffer as the reference normalises over its single buffer:
         w_i = ((p_i / S_r) / min_r'(m_r' / S_r')) ** -beta          (W = 1  ->  (p_i / p_min) ** -beta)
   * transport "nvlink" (default on CUDA when torch's symmetric memory is available): the receive buffers of all
-    ranks are ONE symmetric allocation (``torch.distributed._symmetric_memory``), so every rank knows the
-    address of its rows in every peer's buffer and the gather kernel's shared-memory stages are stored W times
-    -- once locally, W-1 times through NVLink peer memory.  Gather and all-gather are the SAME launch
-    (``rlb_gather`` with ``peer_delta``); a signal-pad barrier (one tiny kernel) closes the exchange, and the
-    whole step is capturable in a CUDA graph.  Receive buffers are double-buffered: a returned batch stays valid
-    until the second next ``sample()``.
+    ranks are ONE symmetric allocation (``torch.distributed._symmetric_memory`` is used for the allocation and the
+    peer addresses only), so every rank knows the address of its rows in every peer's buffer and the gather
+    kernel's shared-memory stages are stored W times -- once locally, W-1 times through NVLink peer memory.
+    Gather and all-gather are the SAME launch (``rlb_gather`` with ``peer_delta``).  The exchange is split-phase
+    and closed by the library's own flags: ``rlb_shard_pack`` (trailers) ends with a system-scope release of the
+    draw's sequence number into every peer's flag array, ``rlb_shard_weights`` (finalize) starts with an acquire
+    spin on its own flags.  No NCCL call and no library barrier, so the whole step is capturable in one graph.
+  * ``pipeline=True`` (split-phase across calls, like the reference's ``prefetch=1``): ``sample()`` issues draw k
+    and returns the finalised batch k-1, so the NVLink transfer of a draw overlaps everything that runs until
+    the next call and the flag wait never stalls.  Receive buffers rotate over ``n_buffers`` slots (4 when
+    pipelined: a batch stays valid until the second next ``sample()``; 2 otherwise).
   * transport "nccl": ``torch.distributed.all_gather_into_tensor`` moves ``B/W * row`` bytes per rank (also the
     CPU/gloo test path).  Either way the leaves of the returned batch are strided views into the receive buffer.
 
 ``update_priority`` takes GLOBAL indices (replicated on every rank, or any subset): each rank rewrites the
 ones it owns and skips the rest inside the kernel (negative local index) -- no collective, no sync.
+``update_local_priority`` takes priorities for the rows this rank drew last (``local_index``): it only needs the
+sampled indices, so it can be issued right after the tree kernel, concurrently with the exchange.
 """
 from __future__ import annotations
 
@@ -89,11 +96,16 @@ class ShardedPrioritizedReplayBuffer:
         generator: this rank's random generator (seed it with ``seed + rank``).
         process_group: defaults to the global group; ``None`` with an uninitialised torch.distributed runs as a
             single shard (world size 1).
+        transport ("auto" | "nvlink" | "nccl"): see the module docstring.
+        pipeline (bool): ``sample()`` returns the PREVIOUS draw (the first call draws twice).
+        n_buffers (int): receive-buffer slots of the nvlink transport (default 4 pipelined, 2 otherwise).
+        exchange_timeout_s (float): bound of the in-kernel wait for the peers' rows.
     """
 
     def __init__(self, *, alpha: float, beta: float, capacity: int, eps: float = 1e-8, priority_key: str = "td_error",
                  batch_size: int | None = None, device="cuda", generator=None, process_group=None,
-                 transport: str = "auto"):
+                 transport: str = "auto", pipeline: bool = False, n_buffers: int | None = None,
+                 exchange_timeout_s: float = 10.0):
         import torch.distributed as dist
 
         self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
@@ -113,14 +125,26 @@ class ShardedPrioritizedReplayBuffer:
         if transport not in ("auto", "nvlink", "nccl"):
             raise ValueError("transport must be 'auto', 'nvlink' or 'nccl'")
         self.transport = transport
+        self.pipeline = bool(pipeline)
+        self.n_buffers = int(n_buffers) if n_buffers is not None else (4 if pipeline else 2)
+        if self.n_buffers < (3 if pipeline else 2):
+            raise ValueError("n_buffers must be >= 2 (>= 3 when pipelined)")
+        self.exchange_timeout_s = float(exchange_timeout_s)
         self._last_gidx = None
-        self._symm = None        # (symmetric double buffer, handle, peer byte offsets)
-        self._parity = 0
+        self._symm = None        # (buffers [n_buffers, B, row], flags u64[W], handle, peer byte offsets)
+        self._draws = 0          # host-side count of issued draws: picks the receive slot
+        self._ctr = None         # device counters: [0] draws published, [1] draws waited for
+        self._xstatus = None     # device status word of the exchange (RLB_STATUS_EXCHANGE_TIMEOUT)
         self._layout = None
         self._static = None
-        self._send = self._recv = None
-        self._bs = None
+        self._cur = None         # the draw in flight: dict(send, recv, bs, nvlink)
+        self._pending = None     # pipelined: the draw the NEXT sample() returns
+        self._fin_stream = None
         self.local_index = None  # local indices of this rank's last draw
+        #: set to True to have ``local_draw`` record ``index_ready`` (a CUDA event) right after the tree kernel: work
+        #: that only needs the sampled indices (``update_local_priority`` on a side stream) overlaps the exchange
+        self.record_index_event = False
+        self.index_ready = None
 
     # ---- writes: every rank feeds its own shard (data-parallel collectors) --------------------------------
     def extend(self, data) -> torch.Tensor:
@@ -140,8 +164,8 @@ class ShardedPrioritizedReplayBuffer:
         return self.local.storage
 
     # ---- sample --------------------------------------------------------------------------------------
-    # sample() = local_draw() -> exchange() -> finalize().  The three stages are public so that a training step can
-    # capture the two compute stages in CUDA graphs and issue the collective eagerly in between.
+    # sample() = local_draw() -> exchange() -> finalize().  The stages are public so that a training step can place
+    # them on streams of its choice (and, with the NCCL transport, issue the collective between two captured graphs).
     def _resolve_batch(self, batch_size):
         if batch_size is None:
             batch_size = self._batch_size
@@ -151,11 +175,17 @@ class ShardedPrioritizedReplayBuffer:
             raise ValueError(f"batch_size={batch_size} must be divisible by the world size {self.world}")
         return batch_size
 
-    def local_draw(self, batch_size: int | None = None, *, static_buffers: bool = False) -> torch.Tensor:
-        """Draw ``batch_size / world`` rows from this shard straight into the packed send buffer (returned).
+    def local_draw(self, batch_size: int | None = None, *, static_buffers: bool = False,
+                   slot: int | None = None) -> torch.Tensor:
+        """Draw ``batch_size / world`` rows from this shard straight into the packed send buffer (returned); with the
+        nvlink transport the same launch stores them into every peer's receive buffer and the trailer kernel
+        publishes the draw.
 
-        ``static_buffers=True`` reuses one send / receive buffer pair across calls (needed under CUDA-graph capture;
-        the returned batch is then overwritten by the next sample).
+        ``static_buffers=True`` reuses one send / receive buffer pair across calls (NCCL transport under CUDA-graph
+        capture; the returned batch is then overwritten by the next sample).  ``slot`` picks the receive slot of the
+        nvlink transport explicitly (captured steps: every rank must use the same slot for the same draw, and a
+        slot must not come round again while its batch is still in use -- replay ``k * n_buffers`` captured steps
+        cyclically); default: issued draws modulo ``n_buffers``.
         """
         batch_size = self._resolve_batch(batch_size)
         b_loc = batch_size // self.world
@@ -169,7 +199,7 @@ class ShardedPrioritizedReplayBuffer:
         if self._layout is None:
             self._layout = _PackedLayout(st._leaves)
         lay = self._layout
-        peers = None
+        peers = flags = None
         nv = None
         if self._use_nvlink(dev):
             try:
@@ -177,8 +207,8 @@ class ShardedPrioritizedReplayBuffer:
             except _NoSymmetricMemory:
                 nv = None
         if nv is not None:
-            buf, hdl, peers = nv
-            recv = buf[self._parity]
+            bufs, flags, _, peers = nv
+            recv = bufs[(self._draws if slot is None else slot) % self.n_buffers]
             send = recv[self.rank * b_loc:(self.rank + 1) * b_loc]  # my rows inside the gathered batch
         elif static_buffers:
             if self._static is None or self._static[0].shape[0] != b_loc:
@@ -193,24 +223,28 @@ class ShardedPrioritizedReplayBuffer:
             idx, _, leaf, pp = be.per_sample(smp._sum_tree.values, smp._min_tree.values, smp._max_capacity,
                                              smp._sum_tree.capacity, length, u, smp._beta, smp._semantics == "cpu",
                                              status=smp._status, want_aux=True)
+            if self.record_index_event and dev.type == "cuda":
+                if self.index_ready is None:
+                    self.index_ready = torch.cuda.Event()
+                self.index_ready.record(torch.cuda.current_stream(dev))
             # with `peers` the rows are written into every rank's receive buffer by this very launch
             be.gather(st._leaves, idx, length, out=lay.leaf_views(send), peer_delta=peers)
-            be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity, peer_delta=peers)
+            # trailers; with `flags`: "my rows of this draw are in your buffer" to every rank (release)
+            be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity, peer_delta=peers,
+                          flags=flags, seq_counter=None if flags is None else self._ctr[0:1], rank=self.rank)
         self.local_index = idx
-        self._send, self._recv, self._bs = send, recv, batch_size
+        self._draws += 1
+        self._cur = {"send": send, "recv": recv, "bs": batch_size, "nvlink": nv is not None, "exchanged": False}
         return send
 
     def exchange(self) -> torch.Tensor:
-        """Close the exchange of sample().  nvlink: the rows are already on their way into every peer's buffer; a
-        signal-pad barrier (one small kernel, stream-ordered) waits until everybody's have landed.  nccl: the ONE
-        collective, an all-gather of the packed local draws."""
-        if self.world > 1:
-            if self._symm is not None and self._recv.data_ptr() == self._symm[0][self._parity].data_ptr():
-                self._symm[1].barrier(channel=self._parity)
-                self._parity ^= 1  # the next draw fills the other buffer; this one stays valid meanwhile
-            else:
-                self._dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
-        return self._recv
+        """nccl: the ONE collective, an all-gather of the packed local draws.  nvlink: nothing to issue -- the rows
+        are already on their way into every peer's buffer; ``finalize`` waits for the flags."""
+        cur = self._cur
+        if self.world > 1 and not cur["nvlink"] and not cur["exchanged"]:
+            self._dist.all_gather_into_tensor(cur["recv"], cur["send"], group=self.group)
+        cur["exchanged"] = True
+        return cur["recv"]
 
     def _use_nvlink(self, dev) -> bool:
         if self.world == 1 or dev.type != "cuda" or self.transport == "nccl":
@@ -219,63 +253,150 @@ class ShardedPrioritizedReplayBuffer:
             return False
         return True
 
+    _FLAG_BYTES = 256  # one u64 per rank (RLB_MAX_PEERS = 16), padded so that the row buffers stay 128-B aligned
+
     def _symmetric_buffers(self, batch_size: int, dev):
-        """[2, B, row] symmetric receive buffer + the byte offsets from MY buffer to every rank's (0 for myself)."""
+        """Symmetric allocation  [flags u64[W] | n_buffers x [B, row]]  + the byte offsets from MY allocation to every
+        rank's (0 for myself)."""
         if self._symm is not None and self._symm is not False and self._symm[0].shape[1] == batch_size:
             return self._symm
         try:
             import torch.distributed._symmetric_memory as symm_mem
 
-            buf = symm_mem.empty((2, batch_size, self._layout.row), dtype=torch.uint8, device=dev)
-            hdl = symm_mem.rendezvous(buf, group=self.group if self.group is not None else self._dist.group.WORLD)
+            row = self._layout.row
+            nbytes = self._FLAG_BYTES + self.n_buffers * batch_size * row
+            raw = symm_mem.empty((nbytes,), dtype=torch.uint8, device=dev)
+            hdl = symm_mem.rendezvous(raw, group=self.group if self.group is not None else self._dist.group.WORLD)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
             peers = [p - ptrs[self.rank] for p in ptrs]
-            if any(d % 16 for d in peers):
+            if any(d % 16 for d in peers) or raw.data_ptr() % 16:
                 raise RuntimeError("symmetric buffers are not 16-byte aligned relative to each other")
-            self._symm = (buf, hdl, peers)
-            self._parity = 0
-        except Exception:
+            raw.zero_()
+            torch.cuda.synchronize(dev)
+            self._dist.barrier(group=self.group)   # nobody publishes into flags that are not zeroed yet
+            flags = raw[:self._FLAG_BYTES].view(torch.int64)[:self.world]
+            bufs = raw[self._FLAG_BYTES:].view(self.n_buffers, batch_size, row)
+            self._ctr = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._xstatus = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._symm = (bufs, flags, hdl, peers)
+            self._raw = raw
+        except Exception as err:
             if self.transport == "nvlink":
                 raise
+            import warnings
+
+            warnings.warn(f"ShardedPrioritizedReplayBuffer: symmetric memory unavailable ({type(err).__name__}: {err}); "
+                          "using the NCCL all-gather transport")
             self._symm = False  # fall back to the NCCL all-gather for good
             raise _NoSymmetricMemory()
         return self._symm
 
-
-    def finalize(self):
-        """Views of the gathered buffer as the global batch + importance weights over the whole sharded buffer."""
-        lay, recv, smp = self._layout, self._recv, self.local.sampler
+    def finalize(self, draw: dict | None = None):
+        """Views of the gathered buffer as the global batch + importance weights over the whole sharded buffer.  With
+        the nvlink transport the weights kernel first waits until every rank's rows of this draw have landed."""
+        cur = self._cur if draw is None else draw
+        lay, recv, smp = self._layout, cur["recv"], self.local.sampler
         leaves = lay.leaf_views(recv)
-        batch = unflatten_data(leaves, self.local.storage._spec, (self._bs,))
-        weight, gidx = ops.backend().shard_weights(recv, lay.meta, smp._beta)  # identical on every rank
+        batch = unflatten_data(leaves, self.local.storage._spec, (cur["bs"],))
+        if cur["nvlink"]:
+            weight, gidx = ops.backend().shard_weights(recv, lay.meta, smp._beta, flags=self._symm[1],
+                                                       wait_counter=self._ctr[1:2], n_ranks=self.world,
+                                                       timeout_s=self.exchange_timeout_s, status=self._xstatus,
+                                                       out=cur.get("out"))
+        else:
+            weight, gidx = ops.backend().shard_weights(recv, lay.meta, smp._beta)  # identical on every rank
         self._last_gidx = gidx
+        self._last_bs = cur["bs"]
         if is_tensor_collection(batch):
             batch.set("index", gidx)
             batch.set("priority_weight", weight)
             return batch
         return batch, {"index": gidx, "priority_weight": weight}
 
-    def sample(self, batch_size: int | None = None):
-        self.local_draw(batch_size)
+    def check_exchange(self) -> None:
+        """Synchronise and raise if a peer's rows ever failed to arrive within ``exchange_timeout_s``."""
+        if self._xstatus is not None and int(self._xstatus.item()) & ops.STATUS_EXCHANGE_TIMEOUT:
+            self._xstatus.zero_()
+            raise RuntimeError("sharded exchange: a peer's rows did not arrive in time")
+
+    def sample_now(self, batch_size: int | None = None, *, slot: int | None = None):
+        """Draw, exchange and finalise in one go (what ``sample`` does when not pipelined)."""
+        if self._pending is not None:
+            raise RuntimeError("a pipelined draw is pending: call sample() (or flush()) first")
+        self.local_draw(batch_size, slot=slot)
         self.exchange()
         return self.finalize()
+
+    def sample(self, batch_size: int | None = None, *, slot: int | None = None):
+        """The global minibatch.  Pipelined: issues draw k and returns the finalised draw k-1 (the first call issues two
+        draws); the finalisation runs on a side stream forked from / joined to the current one, so in a captured step it
+        is not chained behind the new draw."""
+        if not self.pipeline:
+            return self.sample_now(batch_size, slot=slot)
+        if self._pending is None:
+            self.local_draw(batch_size, slot=None if slot is None else slot - 1)
+            self.exchange()
+            self._pending = self._cur
+        prev = self._pending
+        if slot is not None and prev["nvlink"]:
+            # explicit slots (captured steps replayed cyclically): the draw this call finalises is the one the step
+            # with slot - 1 issued, whatever Python call happened to precede this one at capture time
+            prev = dict(prev, recv=self._symm[0][(slot - 1) % self.n_buffers])
+        dev = self.local.sampler._sum_tree.device
+        if dev.type == "cuda" and prev["nvlink"]:
+            # outputs are allocated on the caller's stream, the wait + weights kernel runs beside the new draw
+            prev["out"] = (torch.empty(prev["bs"], dtype=torch.float32, device=dev),
+                           torch.empty(prev["bs"], dtype=torch.int64, device=dev))
+            if self._fin_stream is None:
+                self._fin_stream = torch.cuda.Stream(dev)
+            main = torch.cuda.current_stream(dev)
+            self._fin_stream.wait_stream(main)
+            with torch.cuda.stream(self._fin_stream):
+                out = self.finalize(prev)
+            self.local_draw(batch_size, slot=slot)
+            self.exchange()
+            main.wait_stream(self._fin_stream)
+        else:
+            self.local_draw(batch_size, slot=slot)
+            self.exchange()
+            out = self.finalize(prev)
+        self._pending = self._cur
+        return out
+
+    def flush(self):
+        """Pipelined: finalise and return the pending draw without issuing a new one (``None`` if there is none)."""
+        if self._pending is None:
+            return None
+        prev, self._pending = self._pending, None
+        return self.finalize(prev)
 
     # ---- priority write-back ---------------------------------------------------------------------------
     def update_priority(self, index: torch.Tensor, priority) -> None:
         """``index`` holds GLOBAL indices; entries owned by other ranks are skipped inside the kernel."""
         index = torch.as_tensor(index, dtype=torch.long, device=self.device)
-        if index is self._last_gidx and self._bs is not None:
-            # the index vector of the batch sample() just returned: rows [rank*B/W, (rank+1)*B/W) are exactly the
-            # draws from this shard, every other row belongs to another rank -- no need to scan them
-            b_loc = self._bs // self.world
+        last = self._last_gidx
+        if (last is not None and index.numel() == last.numel() and index.data_ptr() == last.data_ptr()
+                and index.is_contiguous()):
+            # the index vector of the batch sample() returned last (the tensor itself or a view of it): rows
+            # [rank*B/W, (rank+1)*B/W) are exactly the draws from this shard, every other row belongs to another
+            # rank -- no need to scan them.  Anything else (a clone, a subset, a permutation) takes the general path.
+            b_loc = self._last_bs // self.world
             lo = self.rank * b_loc
             priority = torch.as_tensor(priority, device=self.device)
             if priority.numel() > 1:
                 priority = priority.reshape(-1)[lo:lo + b_loc]
-            index = index[lo:lo + b_loc]
+            index = index.reshape(-1)[lo:lo + b_loc]
         self.local.sampler.update_priority(index, priority, storage=self.local.storage,
                                            index_base=self.rank * self.shard_capacity,
                                            index_limit=self.shard_capacity)
+
+    def update_local_priority(self, priority) -> None:
+        """Priorities for the rows THIS rank drew in its latest ``local_draw`` (``local_index``, in draw order).  Needs
+        nothing but the sampled indices, so it may be issued as soon as ``index_ready`` has fired -- concurrently with
+        the gather / exchange of the same draw."""
+        if self.local_index is None:
+            raise RuntimeError("no draw yet")
+        self.local.sampler.update_priority(self.local_index, priority, storage=self.local.storage)
 
     def update_tensordict_priority(self, data) -> None:
         priority = data.get(self.local.priority_key)

@@ -24,6 +24,7 @@ RLB_F32, RLB_F64 = 0, 1
 GATHER_AUTO, GATHER_VECTOR, GATHER_BULK = 0, 1, 2
 MAX_LEAVES = 24
 STATUS_INDEX_OOB, STATUS_NONPOS_PSUM, STATUS_NONPOS_PMIN, STATUS_BACKOFF_FAIL = 1, 2, 4, 8
+STATUS_EXCHANGE_TIMEOUT = 16
 
 _vp, _i64, _i32, _f64, _sz, _u32 = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                     ctypes.c_size_t, ctypes.c_uint32)
@@ -45,8 +46,8 @@ _SIGNATURES = {
                                _vp, _vp]),
     "rlb_per_update": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _f64, _f64, _vp, _vp, _vp, _sz, _u32, _i64, _i64,
                                _vp]),
-    "rlb_shard_pack": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp]),
-    "rlb_shard_weights": (_i32, [_vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp]),
+    "rlb_shard_pack": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "rlb_shard_weights": (_i32, [_vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp]),
     "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
@@ -274,23 +275,36 @@ class CudaBackend:
 
     # -- sharded minibatch trailer -----------------------------------------------------------------
     def shard_pack(self, rows: torch.Tensor, meta_offset: int, index, leaf, psum_pmin, index_base: int,
-                   peer_delta: Sequence[int] | None = None) -> None:
-        dev = self._cuda(rows, index, leaf, psum_pmin)
+                   peer_delta: Sequence[int] | None = None, flags: torch.Tensor | None = None,
+                   seq_counter: torch.Tensor | None = None, rank: int = 0) -> None:
+        """Trailers of the local rows (into every peer with ``peer_delta``) and, with ``flags``, the release of this
+        draw's sequence number into every peer's flag array (the split-phase exchange's "my rows are there")."""
+        dev = self._cuda(rows, index, leaf, psum_pmin, flags, seq_counter)
         n_peers = 0 if peer_delta is None else len(peer_delta)
         peers = (ctypes.c_int64 * n_peers)(*peer_delta) if n_peers else None
         with self._Guard(dev):
             self._check(self.L.rlb_shard_pack(rows.data_ptr(), rows.stride(0), meta_offset, index.data_ptr(),
                                               leaf.data_ptr(), psum_pmin.data_ptr(), int(index_base), rows.shape[0],
-                                              peers, n_peers, self._stream(dev)), "rlb_shard_pack")
+                                              peers, n_peers, self._p(flags), self._p(seq_counter), int(rank),
+                                              self._stream(dev)), "rlb_shard_pack")
 
-    def shard_weights(self, rows: torch.Tensor, meta_offset: int, beta: float):
-        dev = self._cuda(rows)
+    def shard_weights(self, rows: torch.Tensor, meta_offset: int, beta: float, flags: torch.Tensor | None = None,
+                      wait_counter: torch.Tensor | None = None, n_ranks: int = 0, timeout_s: float = 10.0,
+                      status: torch.Tensor | None = None, out: tuple | None = None):
+        """Importance weights + global indices of the gathered rows; with ``flags`` the kernel first waits (acquire)
+        until every rank has published the draw it finalises."""
+        dev = self._cuda(rows, flags, wait_counter, status)
         B = rows.shape[0]
-        weight = torch.empty(B, dtype=torch.float32, device=dev)
-        gidx = torch.empty(B, dtype=torch.int64, device=dev)
+        if out is None:
+            weight = torch.empty(B, dtype=torch.float32, device=dev)
+            gidx = torch.empty(B, dtype=torch.int64, device=dev)
+        else:
+            weight, gidx = out
         with self._Guard(dev):
             self._check(self.L.rlb_shard_weights(rows.data_ptr(), rows.stride(0), meta_offset, B, float(beta),
-                                                 weight.data_ptr(), gidx.data_ptr(), self._stream(dev)),
+                                                 weight.data_ptr(), gidx.data_ptr(), self._p(flags),
+                                                 self._p(wait_counter), int(n_ranks), float(timeout_s),
+                                                 self._p(status), self._stream(dev)),
                         "rlb_shard_weights")
         return weight, gidx
 

@@ -220,14 +220,16 @@ class OracleBackend:
         masked_tree[capacity + torch.from_numpy(bad)] = 0
 
     # ---- sharded minibatch trailer
-    def shard_pack(self, rows, meta_offset, index, leaf, psum_pmin, index_base, peer_delta=None):
+    def shard_pack(self, rows, meta_offset, index, leaf, psum_pmin, index_base, peer_delta=None, flags=None,
+                   seq_counter=None, rank=0):
         m = meta_offset
         rows[:, m:m + 8].view(torch.int64).view(-1).copy_(index + index_base)
         rows[:, m + 8:m + 12].view(torch.float32).view(-1).copy_(leaf)
         rows[:, m + 12:m + 16].view(torch.float32).view(-1).copy_(psum_pmin[0].expand(rows.shape[0]))
         rows[:, m + 16:m + 20].view(torch.float32).view(-1).copy_(psum_pmin[1].expand(rows.shape[0]))
 
-    def shard_weights(self, rows, meta_offset, beta):
+    def shard_weights(self, rows, meta_offset, beta, flags=None, wait_counter=None, n_ranks=0, timeout_s=10.0,
+                      status=None, out=None):
         m = meta_offset
         gidx = rows[:, m:m + 8].view(torch.int64).view(-1).clone()
         p = rows[:, m + 8:m + 12].view(torch.float32).view(-1)

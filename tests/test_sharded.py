@@ -122,3 +122,45 @@ def test_sharded_single_process(emul):
     sa, sb = a.sample(), b.sample()
     assert torch.equal(sa.get("index"), sb.get("index")) and torch.equal(sa.get("x"), sb.get("x"))
     torch.testing.assert_close(sa.get("priority_weight"), sb.get("priority_weight"), rtol=1e-6, atol=0)
+
+
+def test_sharded_pipelined_returns_previous_draw(emul):
+    """pipeline=True: sample() issues draw k and returns draw k-1, so without write-backs in between the returned
+    sequence is the plain buffer's; flush() hands out the draw still in flight; update_priority on the returned index
+    vector (or a clone of it) rewrites this shard's rows only."""
+    from rl_b200.data import TensorDict
+    from rl_b200.data.sharded import ShardedPrioritizedReplayBuffer
+
+    mk = lambda: torch.Generator().manual_seed(11)
+    data = TensorDict({"x": torch.randn(300, 5), "td_error": torch.rand(300)}, [300])
+    a = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=512, batch_size=16, device="cpu", generator=mk(),
+                                       pipeline=True)
+    b = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=512, batch_size=16, device="cpu", generator=mk())
+    assert a.n_buffers == 4 and b.n_buffers == 2
+    a.extend(data.clone())
+    b.extend(data.clone())
+    want = [b.sample() for _ in range(4)]
+    got = [a.sample() for _ in range(3)]
+    got.append(a.flush())
+    assert a.flush() is None
+    for w, g in zip(want, got):
+        assert torch.equal(w.get("index"), g.get("index")) and torch.equal(w.get("x"), g.get("x"))
+        torch.testing.assert_close(w.get("priority_weight"), g.get("priority_weight"), rtol=1e-6, atol=0)
+    # the fast path keys on the storage of the returned index tensor, not on object identity; a clone takes the
+    # general path and must give the same trees
+    last = got[-1].get("index")
+    pr = torch.rand(16) + 1.0
+    a.update_priority(last, pr)
+    b.update_priority(want[-1].get("index").clone(), pr)
+    assert torch.equal(a.sampler._sum_tree.values, b.sampler._sum_tree.values)
+    # update_local_priority: the rows of the latest local draw
+    c = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=512, batch_size=16, device="cpu", generator=mk())
+    c.extend(data.clone())
+    sc = c.sample()
+    c.update_local_priority(pr)
+    d = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=512, batch_size=16, device="cpu", generator=mk())
+    d.extend(data.clone())
+    sd = d.sample()
+    d.update_priority(sd.get("index"), pr)
+    assert torch.equal(sc.get("index"), sd.get("index"))
+    assert torch.equal(c.sampler._sum_tree.values, d.sampler._sum_tree.values)
