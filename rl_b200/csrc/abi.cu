@@ -1,5 +1,6 @@
 // abi.cu -- error plumbing and device queries shared by the C-ABI entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,6 +24,15 @@ int check_cuda(cudaError_t e, const char *what) {
 }
 
 int check_launch(const char *kernel) { return check_cuda(cudaPeekAtLastError(), kernel); }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("RLB_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 int sm_count() {
   // cached per device ordinal (one process per GPU is the deployment model, but be correct anyway)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "rlb200.h"
 
@@ -24,6 +25,28 @@ int sm_count();
   } while (0)
 
 static inline cudaStream_t as_stream(rlb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+bool pdl_enabled();  // RLB_PDL=0 in the environment turns programmatic dependent launch off (A/B measurements)
+
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute: the kernel may be scheduled while
+// the previous kernel of the stream is still running and must call pdl_wait() before touching its results.  Under
+// stream capture this becomes a programmatic dependency edge of the graph.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -124,6 +147,12 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint3
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor in the
+// stream is still draining; everything it does before pdl_wait() must not depend on the predecessor's results.
+// pdl_trigger() in the predecessor lets the dependent's CTAs become resident early.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");

@@ -218,6 +218,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
     fence_proxy_async_smem();
   }
   __syncwarp();
+  pdl_wait();  // everything above overlapped the tail of the kernel that produced the index (PDL launches)
 
   // locate the first piece
   int l = 0;
@@ -295,7 +296,12 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
       ++n_stored;
     }
   }
-  if (lane == 0) bulk_wait_all();  // all s->g copies complete (and visible) before the CTA retires
+  // the CTA may retire once the DMA engine has READ the last stages (the writes complete on their own and are
+  // visible at the kernel boundary); with NVLink peers the publish kernel that follows relies on completed writes,
+  // so wait for them in full
+  if (lane == 0) {
+    if (P.n_peers > 1) bulk_wait_all(); else bulk_wait_read<0>();
+  }
   __syncwarp();
 }
 
@@ -309,6 +315,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const __grid_con
     return;
   }
   const int vec_ctas = (int)gridDim.x - P.bulk_ctas;
+  pdl_wait();
   vector_role<SCATTER>(P, (int64_t)blockIdx.x - P.bulk_ctas, vec_ctas);
 }
 
@@ -471,7 +478,9 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
   static bool attr_set_dev[64] = {};  // function attributes are per device
   if (smem && (rc = allow_bulk_smem(gather_kernel<SCATTER>, attr_set_dev, "cudaFuncSetAttribute(gather_kernel)")))
     return rc;
-  gather_kernel<SCATTER><<<P.bulk_ctas + vec_ctas, kGatherThreads, smem, st>>>(P);
+  rc = check_cuda(launch_pdl(gather_kernel<SCATTER>, dim3(P.bulk_ctas + vec_ctas), dim3(kGatherThreads), smem, st, P),
+                  SCATTER ? "gather_kernel<scatter>" : "gather_kernel<gather>");
+  if (rc) return rc;
   return check_launch(SCATTER ? "gather_kernel<scatter>" : "gather_kernel<gather>");
 }
 

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(1024) shard_pack_kernel(uint8_t *rows, int64_t
                                                           unsigned long long *flags, unsigned long long *seq_counter,
                                                           int rank) {
   __shared__ unsigned long long s_seq;
+  pdl_wait();  // PDL launch: the gather kernel before this one has completed and its stores are performed
   if (flags && threadIdx.x == 0) {
     s_seq = *seq_counter + 1ull;
     *seq_counter = s_seq;
@@ -175,10 +176,12 @@ int rlb_shard_pack(void *rows, int64_t row_bytes, int64_t meta_offset, const int
   }
   int threads = 32;
   while (threads < B && threads < 1024) threads <<= 1;
-  shard_pack_kernel<<<1, threads, 0, as_stream(stream)>>>(static_cast<uint8_t *>(rows), row_bytes, meta_offset, index,
-                                                         leaf, psum_pmin, index_base, B, peers,
-                                                         reinterpret_cast<unsigned long long *>(flags),
-                                                         reinterpret_cast<unsigned long long *>(seq_counter), rank);
+  int rc = check_cuda(launch_pdl(shard_pack_kernel, dim3(1), dim3(threads), 0, as_stream(stream),
+                                 static_cast<uint8_t *>(rows), row_bytes, meta_offset, index, leaf, psum_pmin, index_base,
+                                 B, peers, reinterpret_cast<unsigned long long *>(flags),
+                                 reinterpret_cast<unsigned long long *>(seq_counter), rank),
+                      "shard_pack_kernel");
+  if (rc) return rc;
   return check_launch("shard_pack_kernel");
 }
 

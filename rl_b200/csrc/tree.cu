@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   constexpr int kTopLevels = 9;  // nodes 1..511 of the sum tree are staged in shared memory: 8 descent steps
   __shared__ T s_p[2];
   __shared__ T s_top[1 << kTopLevels];
+  pdl_trigger();  // a dependent launch (the gather) may become resident now; it waits for this grid before the index
   if (dbg && (blockIdx.x != 0 || threadIdx.x != 0)) dbg = nullptr;
   if (dbg) dbg[8] = (long long)clock64();
   const int warp = threadIdx.x >> 5;
@@ -394,24 +395,40 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
 // ------------------------------------------------------------------------------------------------
 // update: batches of <= 1024 in ONE launch
 // ------------------------------------------------------------------------------------------------
-// Sorted-merge climb.  The batch is sorted by leaf (bitonic, in shared memory; ties broken so that the
-// LAST input position comes first and wins -- csrc/segment_tree.h:222-226 / cuda_segment_tree.cu:32-37)
-// and compacted to the m distinct leaves.  Item j's root path coincides with its left neighbour's from
-// level L_j = bitlength(key_j ^ key_{j-1}) upwards, so j carries its own nodes for levels < L_j and then
-// hands its value to the group on its left.  Below the merge levels every sibling is untouched by the
-// batch, so its OLD global value is what the reference's serial update would read.
+// Semantics: input order, the LAST duplicate wins (csrc/segment_tree.h:222-226 / cuda_segment_tree.cu:32-37), then every
+// touched ancestor = op(children).  fp addition commutes and min is exact, so once the winning leaf values are fixed
+// the final heap does not depend on the order in which the reference's serial loop visits the items.
 //
-// Those sibling reads are 2 x depth scattered 4-byte loads per item -- ~10k sectors for a batch of 256 on
-// a 2^20 tree -- and a single SM's L1 moves only about one sector wavefront every ~2 cycles, which made
-// them the whole cost of earlier single-CTA versions (ncu: 20k of 28k cycles).  So the launch has TWO
-// phases: (A) a grid of CTAs spread over the chip reads every (item, level) sibling of both trees and
-// writes it, coalesced, to a scratch tile; the last CTA to finish (atomic ticket) alone continues with
-// (B): it pulls the scratch tile into shared memory with coalesced 16-byte cp.async, sorts, compacts and
-// climbs level-synchronously touching only registers and shared memory: per level a living item combines
-// (left, right) from {its value, a deposited partner value, a prefetched sibling}, writes the parent to
-// the global tree and, if it merges at the next level, deposits the value for its left group.
-// FUSED (fp32): `value` holds RAW priorities; the leaf is (p + eps) ** alpha (samplers.py:1076, torch.pow
-// semantics) and the maximum raw priority of the valid items is folded into *max_out.
+// The tree is cut at level `bot` above the leaves (bot = depth - kDenseLevels, W = 2^kDenseLevels nodes there):
+//
+//   * BELOW the cut -- sorted-merge climb.  The batch is sorted by (leaf, reversed position): the head of each run of
+//     equal leaves is its last writer.  Head j's root path coincides with its left neighbour's from level
+//     L_j = bitlength(leaf_j ^ leaf_{j-1}) upwards, so j carries its own nodes for levels < L_j and then hands its
+//     value to the group on its left: the leader of that group (the leftmost item sharing the prefix leaf_j >> L_j, a
+//     lower bound in the sorted keys) consumes, at iteration L_j - 1, the slot [L_j - 1][pos_leader] of the sibling
+//     tile, which until then holds the OLD value of exactly the node j carries -- j simply overwrites it, and the
+//     leader's loop body is the same whether its sibling was touched or not.  Every other sibling is untouched by the
+//     batch: its OLD global value is what the reference's serial update would read.  A CTA barrier is only needed
+//     after a level at which some item hands over (a bit mask of the merge levels says which; for 256 random items in
+//     a 2^20 tree that is a handful of the levels).
+//   * ABOVE the cut -- dense.  The W cut-level nodes of both trees are pulled into shared memory (coalesced, async),
+//     the items that reach the cut overwrite their node, and the W - 1 nodes above are recomputed pairwise, exactly
+//     node = op(node 2k, node 2k+1) as the reference computes them (untouched nodes come out bit-identical because the
+//     invariant holds everywhere), and stored back coalesced.  Merges above the cut need no bookkeeping at all.
+//
+// The sibling reads below the cut are 2 x bot scattered 4-byte loads per item, and a single SM's L1 moves only about
+// one sector wavefront every ~2 cycles, which made them the whole cost of earlier single-CTA versions.  So the launch
+// has TWO phases: (A) 2 x bot CTAs spread over the chip read every (item, level) sibling and write it, coalesced, to a
+// scratch tile; the last CTA to finish (atomic ticket) alone continues with (B): sort, merge levels, climb, dense top.
+// Finished node values are streamed to the global trees by WRITER warps (the upper half of the block), signalled per
+// level through mbarriers, because a global store before a CTA barrier makes the barrier wait for the L2 round trip.
+// FUSED (fp32): `value` holds RAW priorities; the leaf is (p + eps) ** alpha (samplers.py:1076, torch.pow semantics)
+// and the maximum raw priority of the valid items is folded into *max_out.
+#ifndef RLB_UPDATE_DENSE_LEVELS
+#define RLB_UPDATE_DENSE_LEVELS 10
+#endif
+constexpr int kDenseLevels = RLB_UPDATE_DENSE_LEVELS;
+
 __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
   int *ia = reinterpret_cast<int *>(addr);
   int old = *ia;
@@ -431,10 +448,15 @@ constexpr size_t kUpdCtrlBytes = 1024;                 // ticket counter lives a
 constexpr size_t kUpdScratchBytes = (size_t(1) << 20) - kUpdCtrlBytes;
 constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // stamps of the general path start here
 
+__host__ __device__ inline int upd_bot_levels(int depth) { return depth > kDenseLevels ? depth - kDenseLevels : 0; }
+
 template <typename T>
 __host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
-  // xbuf u64[2*np] | ukey u32[np] | upos u32[np] | Lw i32[np] | sraw T[np] | lv T[np] | sib_s, sib_m T[depth*np] each
-  return (size_t)np * (16 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (2 + 2 * (size_t)depth);
+  // xbuf u64[2*np] | sleaf u32[np] | spos u32[np] | Lw i32[np] | sraw T[np] | lv T[np] | sib T[2][bot][np] |
+  // cut heaps T[2][2W]
+  const int bot = upd_bot_levels(depth);
+  const size_t W = size_t(1) << (depth - bot);
+  return (size_t)np * (16 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (2 + 2 * (size_t)bot) + 4 * W * sizeof(T);
 }
 
 #define RLB_TICK(k)                                                   \
@@ -461,14 +483,19 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   // that stream finished node values to the global trees while the compute warps are still climbing
   const int tid = threadIdx.x;
   const bool has_writers = (int)blockDim.x == 2 * NP;
-  const int lane = tid & 31, warp = tid >> 5;
-  __shared__ int warp_cnt[32];
-  __shared__ int s_total;
+  const int lane = tid & 31;
+  const int bot = upd_bot_levels(depth);   // levels climbed item by item; the rest is dense
+  const int W = 1 << (depth - bot);        // nodes at the cut level
   __shared__ int s_last;
+  __shared__ unsigned s_lmask;                       // bit L set: some item hands over at level L (1 <= L <= bot)
   __shared__ __align__(8) uint64_t s_level_done[33];  // mbarriers: [l] = level l is final, [32] = item info is final
-  if (has_writers && tid == 0) {
-    for (int k = 0; k < 33; ++k) mbar_init(&s_level_done[k], 1);
-    fence_mbar_init();
+  if (tid == 0) {
+    s_lmask = 0u;
+    if (has_writers) {
+      for (int k = 0; k < 32; ++k) mbar_init(&s_level_done[k], NP >> 5);  // one arrival per compute warp
+      mbar_init(&s_level_done[32], 1);
+      fence_mbar_init();
+    }
   }
 
   const long long t_start = dbg ? (long long)clock64() : 0;  // stamps are taken by the CTA that runs phase B
@@ -484,10 +511,10 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     raw = scalar ? __ldg(value) : __ldg(value + tid);
   }
 
-  // ---- phase A (all CTAs): scratch[t][l][i] = tree_t[((capacity + index[i]) >> l) ^ 1], one element per
-  // thread per pass (the grid is sized so that there is normally a single pass)
-  {
-    const uint32_t per_tree = (uint32_t)depth * (uint32_t)NP;
+  // ---- phase A (all CTAs): scratch[t][l][i] = tree_t[((capacity + index[i]) >> l) ^ 1] for the levels below the
+  // cut, one element per thread per pass (the grid is sized so that there is normally a single pass)
+  if (bot > 0) {
+    const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP;
     const uint32_t total = 2u * per_tree;
     for (uint32_t e = blockIdx.x * (uint32_t)NP + tid; tid < NP && e < total; e += gridDim.x * (uint32_t)NP) {
       const uint32_t t = e >= per_tree;
@@ -502,74 +529,89 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
       scratch[e] = v;
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const int prev = atomicAdd(ticket, 1);
-      s_last = (prev == (int)gridDim.x - 1);
-      if (s_last) *ticket = 0;  // ready for the next launch
+    if (gridDim.x > 1) {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const int prev = atomicAdd(ticket, 1);
+        s_last = (prev == (int)gridDim.x - 1);
+        if (s_last) *ticket = 0;  // ready for the next launch
+      }
+      __syncthreads();
+      if (!s_last) return;
+      __threadfence();
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
   }
+  __syncthreads();  // s_lmask / mbarrier initialisation visible to everybody
   if (dbg && threadIdx.x == 0) dbg[0] = t_start;
   RLB_TICK(1);
 
   // ---- phase B (last CTA only)
   unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
-  uint32_t *ukey = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);
-  uint32_t *upos = ukey + NP;
-  int *Lw = reinterpret_cast<int *>(upos + NP);  // merge level of each distinct leaf (for the writer warps)
+  uint32_t *sleaf = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);  // sorted leaf index (0xffffffff: not an item)
+  uint32_t *spos = sleaf + NP;                                    // its input position
+  int *Lw = reinterpret_cast<int *>(spos + NP);  // merge level of each head (0: not a head) -- for the writer warps
   T *sraw = reinterpret_cast<T *>(Lw + NP);
-  T *lv = sraw + NP;   // leaf value of each distinct leaf (for the writer warps)
-  T *sib = lv + NP;    // [2][depth][NP], indexed by ORIGINAL input position; reused as the output staging tile
+  T *lv = sraw + NP;   // leaf value of each head (for the writer warps)
+  T *sib = lv + NP;    // [2][bot][NP], indexed by ORIGINAL input position; reused as the output staging tile
+  T *cut_s = sib + 2 * (size_t)bot * NP;  // heap layout over the top of the tree: node k at [k], 1 <= k < 2W
+  T *cut_m = cut_s + 2 * (size_t)W;
   if (tid >= NP) {
     // ---- writer warps: wait until a level is final, then scatter it.  Their stores drain on their own
     // barriers, never on the compute warps' one.
     const int w = tid - NP;
     mbar_wait_parity(&s_level_done[32], 0);
-    const int mm = s_total;
-    uint32_t wleaf = 0, wpos = 0;
-    int wL = 0;
-    if (w < mm) {
-      wleaf = ukey[w];
-      wpos = upos[w];
-      wL = Lw[w];
+    const int wL = Lw[w];
+    const uint32_t wleaf = (uint32_t)capacity + sleaf[w];
+    const uint32_t wpos = spos[w];
+    if (wL > 0) {
       const T v = lv[w];
       if (sum) sum[wleaf] = v;
       if (mn) mn[wleaf] = v;
     }
-    for (int l = 0; l < depth; ++l) {
+    for (int l = 0; l < bot; ++l) {
       mbar_wait_parity(&s_level_done[l], 0);
-      if (w < mm && wL > l + 1) {  // item w carried node (wleaf >> (l + 1))
+      if (wL > l + 1) {  // item w carried node (wleaf >> (l + 1))
         const uint32_t parent = wleaf >> (l + 1);
         if (sum) sum[parent] = sib[(size_t)l * NP + wpos];
-        if (mn) mn[parent] = sib[(size_t)depth * NP + (size_t)l * NP + wpos];
+        if (mn) mn[parent] = sib[(size_t)bot * NP + (size_t)l * NP + wpos];
       }
     }
     return;
   }
   auto compute_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(NP) : "memory"); };
   {
-    // coalesced 16-byte async copies of the whole scratch tile (lands while we sort)
-    const size_t bytes = 2 * (size_t)depth * NP * sizeof(T);
+    // coalesced 16-byte async copies: the scratch tile and the cut level of both trees (land while we sort)
+    const size_t bytes = 2 * (size_t)bot * NP * sizeof(T);
     const unsigned char *g = reinterpret_cast<const unsigned char *>(scratch);
     unsigned char *d = reinterpret_cast<unsigned char *>(sib);
     for (size_t off = (size_t)tid * 16; off < bytes; off += (size_t)NP * 16) cp_async16(d + off, g + off);
+    constexpr int kPer16 = 16 / (int)sizeof(T);
+    if (W >= kPer16) {
+      for (int k = tid * kPer16; k < W; k += NP * kPer16) {
+        if (sum) cp_async16(cut_s + W + k, sum + W + k);
+        if (mn) cp_async16(cut_m + W + k, mn + W + k);
+      }
+    } else {
+      for (int k = tid; k < W; k += NP) {
+        if (sum) cut_s[W + k] = ld_cg(sum + W + k);
+        if (mn) cut_m[W + k] = ld_cg(mn + W + k);
+      }
+    }
   }
 
-  // ---- 1. keys: (leaf node id, reversed input position) -- ascending sort puts the last writer first.  When
-  // both fit in 32 bits (trees up to 2^21 slots with 1024-item batches) the whole sort runs on 32-bit keys.
+  // ---- 1. keys: (leaf index, reversed input position) -- ascending sort puts the last writer first; entries that
+  // are not items get an all-ones leaf field (still unique through the position, so ranks are a permutation).  When
+  // both fields fit in 32 bits (trees up to 2^21 slots with 1024-item batches) the whole sort runs on 32-bit keys.
   const int pos_bits = 31 - __clz(NP);  // log2(NP)
   const bool key32 = (depth + 1 + pos_bits) <= 32;
-  unsigned long long key = ~0ull;
-  if (valid) {
-    const unsigned long long leaf = (unsigned long long)(capacity + my_ix);
-    const unsigned long long rpos = (unsigned long long)(NP - 1 - tid);
-    key = key32 ? ((leaf << pos_bits) | rpos) : ((leaf << 32) | rpos);
-  } else if (key32) {
-    key = 0xffffffffull;
+  const uint32_t rpos = (uint32_t)(NP - 1 - tid);
+  const uint32_t none32 = 0xffffffffu >> pos_bits;  // all-ones leaf field of a 32-bit key
+  unsigned long long key;
+  if (key32) {
+    key = ((valid ? (uint32_t)my_ix : none32) << pos_bits) | rpos;
+  } else {
+    key = ((unsigned long long)(valid ? (uint32_t)my_ix : 0xffffffffu) << 32) | rpos;
   }
   if constexpr (FUSED) {
     if (max_out) {
@@ -581,9 +623,25 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   sraw[tid] = raw;
   RLB_TICK(2);
 
-  // ---- 2. bitonic sort of NP keys, one key per thread: strides < 32 with warp shuffles, larger strides through
-  // double-buffered shared memory (one barrier per such step)
-  if (key32) {
+  // ---- 2. sort.  Up to 256 keys of 32 bits: rank by counting (every thread compares its key with all the others,
+  // read as broadcast 128-bit shared loads; keys are unique, so the ranks are a permutation).  Otherwise bitonic, one
+  // key per thread: strides < 32 with warp shuffles, larger strides through double-buffered shared memory.
+  if (key32 && NP <= 256) {
+    uint32_t k32 = (uint32_t)key;
+    uint32_t *xb32 = reinterpret_cast<uint32_t *>(xbuf);
+    xb32[tid] = k32;
+    compute_sync();
+    const uint4 *kv = reinterpret_cast<const uint4 *>(xb32);
+    uint32_t rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < (NP >> 2); ++j) {
+      const uint4 q = kv[j];
+      rank += (q.x < k32) + (q.y < k32) + (q.z < k32) + (q.w < k32);
+    }
+    xb32[NP + rank] = k32;
+    compute_sync();
+    key = xb32[NP + tid];
+  } else if (key32) {
     uint32_t k32 = (uint32_t)key;
     uint32_t *xb32 = reinterpret_cast<uint32_t *>(xbuf);
     int flip = 0;
@@ -625,91 +683,64 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   }
   RLB_TICK(3);
 
-  // ---- 3. distinct leaves: head of each run of equal leaf ids, compacted by a block-wide exclusive scan
-  const bool key_valid = key32 ? ((uint32_t)key != 0xffffffffu) : (key != ~0ull);
-  const uint32_t myleaf = key32 ? ((uint32_t)key >> pos_bits) : (uint32_t)(key >> 32);
-  const uint32_t mypos = (uint32_t)(NP - 1) - (uint32_t)(key & (unsigned long long)(NP - 1));
-  {
-    uint32_t *buf = reinterpret_cast<uint32_t *>(xbuf);  // both exchange buffers are free again after a barrier
-    compute_sync();
-    buf[tid] = key_valid ? myleaf : 0xffffffffu;
-    compute_sync();
-  }
-  const uint32_t *sorted_leaf = reinterpret_cast<const uint32_t *>(xbuf);
-  const bool head = key_valid && (tid == 0 || sorted_leaf[tid - 1] != myleaf);
-  const unsigned bal = __ballot_sync(0xffffffffu, head);
-  if (lane == 0) warp_cnt[warp] = __popc(bal);
-  compute_sync();
-  if (warp == 0) {
-    const int nw = NP >> 5;
-    int c = (lane < nw) ? warp_cnt[lane] : 0;
-    int incl = c;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane < nw) warp_cnt[lane] = incl - c;
-    if (lane == 31) s_total = incl;
-  }
-  compute_sync();
-  if (head) {
-    const int u = warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u));
-    ukey[u] = myleaf;
-    upos[u] = mypos;
-  }
+  // ---- 3. heads: the first entry of each run of equal leaves is its last writer.  No compaction: everything below
+  // works on the sorted array as it is (entries that are not heads are simply dead).
+  const uint32_t leaf_field = key32 ? ((uint32_t)key >> pos_bits) : (uint32_t)(key >> 32);
+  const bool key_valid = key32 ? (leaf_field != none32) : (leaf_field != 0xffffffffu);
+  const uint32_t myleaf = key_valid ? leaf_field : 0xffffffffu;
+  const uint32_t pos = (uint32_t)(NP - 1) - (uint32_t)(key & (unsigned long long)(NP - 1));
+  sleaf[tid] = myleaf;
+  spos[tid] = pos;
   cp_async_wait_all();
   compute_sync();
   RLB_TICK(4);
-  const int m = s_total;
 
-  // ---- 4. per distinct leaf j: merge level L_j, and WHERE its hand-over goes.  The group j merges into at level
-  // L_j is led by the leftmost item sharing the prefix key_j >> L_j (a lower bound in the sorted keys); that
-  // leader consumes, at iteration L_j - 1, the slot [L_j - 1][pos_leader] of the sibling tile -- which until then
-  // holds the OLD value of exactly the node j carries.  So j simply overwrites that slot with the new value:
-  // the leader's loop body is the same whether its sibling was touched or not.
-  bool alive = tid < m;
-  uint32_t leafnode = 0, pos = 0;
+  // ---- 4. per head j: merge level L_j, and WHERE its hand-over goes (only merges below the cut hand over)
+  const uint32_t left = tid > 0 ? sleaf[tid - 1] : 0u;
+  bool alive = key_valid && (tid == 0 || left != myleaf);
   int L = 0;
   T vs = (T)0, vm = (T)0, leaf_v = (T)0;
   T *hand_s = nullptr, *hand_m = nullptr;
   if (alive) {
-    leafnode = ukey[tid];
-    pos = upos[tid];
     T v = sraw[pos];
     if constexpr (FUSED) v = (T)pow_like_torch(add_rn((float)v, eps), alpha);
     vs = v;
     vm = v;
     leaf_v = v;
-    L = (tid == 0) ? depth + 1 : 32 - __clz(leafnode ^ ukey[tid - 1]);
-    Lw[tid] = L;
+    L = (tid == 0) ? depth + 1 : 32 - __clz(myleaf ^ left);
     lv[tid] = v;
-    if (tid > 0) {
-      const uint32_t prefix = leafnode >> L;
-      int lo = 0, hi = tid;  // first index in [0, tid) whose key has this prefix
+    if (L <= bot) {
+      const uint32_t prefix = myleaf >> L;
+      int lo = 0, hi = tid;  // first index in [0, tid) whose leaf has this prefix: the leader of the group on my left
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if ((ukey[mid] >> L) < prefix) lo = mid + 1; else hi = mid;
+        if ((sleaf[mid] >> L) < prefix) lo = mid + 1; else hi = mid;
       }
-      const uint32_t lead_pos = upos[lo];
+      const uint32_t lead_pos = spos[lo];
       hand_s = sib + (size_t)(L - 1) * NP + lead_pos;
-      hand_m = sib + (size_t)depth * NP + (size_t)(L - 1) * NP + lead_pos;
+      hand_m = sib + (size_t)bot * NP + (size_t)(L - 1) * NP + lead_pos;
       if (L == 1) {  // sibling leaves: hand the leaf value over before the first iteration
         *hand_s = vs;
         *hand_m = vm;
       }
     }
   }
+  Lw[tid] = L;
+  {
+    const unsigned m = __reduce_or_sync(0xffffffffu, (alive && L <= bot) ? (1u << L) : 0u);
+    if (lane == 0 && m) atomicOr(&s_lmask, m);
+  }
   compute_sync();
-  if (has_writers && tid == 0) mbar_arrive(&s_level_done[32]);  // item info (ukey/upos/Lw/lv/s_total) is final
+  const unsigned lmask = s_lmask;
+  if (has_writers && tid == 0) mbar_arrive(&s_level_done[32]);  // item info (sleaf/spos/Lw/lv) is final
   RLB_TICK(5);
 
-  // ---- 5. climb.  Nothing but registers and shared memory inside the loop: the parent computed at level l
-  // overwrites the (consumed) sibling slot [l][pos] and is flushed to the global trees afterwards -- a global
-  // store before a barrier would make every level wait for its L2 acknowledgement.
+  // ---- 5. climb below the cut.  Nothing but registers and shared memory inside the loop: the parent computed at
+  // level l overwrites the (consumed) sibling slot [l][pos] and is flushed to the global trees by the writer warps.
   T *io_s = sib + pos;
-  T *io_m = sib + (size_t)depth * NP + pos;
+  T *io_m = sib + (size_t)bot * NP + pos;
   int levels_done = 0;
-  for (int l = 0; l < depth; ++l) {
+  for (int l = 0; l < bot; ++l) {
     if (alive) {
       if (L == l + 1) {
         alive = false;  // my level-l value was handed over; the leader of the group on my left carries the parent
@@ -717,23 +748,46 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         const uint32_t off = (uint32_t)l * (uint32_t)NP;
         const T os = io_s[off], om = io_m[off];  // sibling: old global value, or the value handed over to me
         vs = tree_op<T, false>(vs, os);          // IEEE addition commutes: operand order is immaterial
-        vm = ((leafnode >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
-        io_s[off] = vs;  // value of node (leafnode >> (l + 1))
+        vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+        io_s[off] = vs;  // value of node (leaf >> (l + 1))
         io_m[off] = vm;
         levels_done = l + 1;
-        if (L == l + 2) {  // I merge at the next level: hand the value just computed to the leader
+        if (L == l + 2 && L <= bot) {  // I merge at the next level: hand the value just computed to the leader
           *hand_s = vs;
           *hand_m = vm;
         }
       }
     }
-    compute_sync();
-    if (has_writers && tid == 0) mbar_arrive(&s_level_done[l]);  // level l of the staging tile is final
+    if ((lmask >> (l + 2)) & 1u) compute_sync();  // somebody handed over: the leader reads it in the next iteration
+    if (has_writers) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_level_done[l]);  // this warp's level-l values are in the staging tile
+    }
   }
   RLB_TICK(6);
 
-  // ---- 6. flush (only when there are no writer warps): leaf + every ancestor this item carried
-  if (!has_writers && tid < m) {
+  // ---- 6. dense top: items that reached the cut overwrite their node, then W - 1 pairwise recomputations
+  if (alive) {
+    const uint32_t node = ((uint32_t)capacity + myleaf) >> bot;  // in [W, 2W)
+    cut_s[node] = vs;
+    cut_m[node] = vm;
+  }
+  compute_sync();
+  for (int w = W >> 1; w >= 1; w >>= 1) {
+    for (int k = tid; k < w; k += NP) {
+      const int node = w + k;
+      if (sum) cut_s[node] = tree_op<T, false>(cut_s[node << 1], cut_s[(node << 1) | 1]);
+      if (mn) cut_m[node] = tree_op<T, true>(cut_m[node << 1], cut_m[(node << 1) | 1]);
+    }
+    compute_sync();
+  }
+  for (int k = 1 + tid; k < W; k += NP) {
+    if (sum) sum[k] = cut_s[k];
+    if (mn) mn[k] = cut_m[k];
+  }
+  // ---- 7. without writer warps: leaf + every ancestor below the cut this item carried
+  if (!has_writers && L > 0) {
+    const uint32_t leafnode = (uint32_t)capacity + myleaf;
     if (sum) sum[leafnode] = leaf_v;
     if (mn) mn[leafnode] = leaf_v;
     for (int l = 0; l < levels_done; ++l) {
@@ -907,8 +961,8 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
     if (rc) return rc;
     attr_set = true;
   }
-  // phase A grid: one scattered sibling read per thread (2 * depth CTAs), at most one CTA per SM
-  int64_t grid = 2 * (int64_t)depth;
+  // phase A grid: one scattered sibling read per thread (2 * bot CTAs), at most one CTA per SM
+  int64_t grid = 2 * (int64_t)upd_bot_levels(depth);
   const int sms = sm_count();
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
@@ -927,7 +981,7 @@ static bool update_fits_cta(int64_t n, int64_t capacity, int depth) {
   int np = 32;
   while (np < n) np <<= 1;
   return upd_smem_bytes<T>(np, depth) <= (size_t)kUpdateSmemLimit &&
-         2 * (size_t)depth * np * sizeof(T) <= kUpdScratchBytes;
+         2 * (size_t)upd_bot_levels(depth) * np * sizeof(T) <= kUpdScratchBytes;
 }
 
 

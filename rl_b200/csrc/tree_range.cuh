@@ -112,8 +112,15 @@ __device__ __forceinline__ void range_role(const RangeParams &R, int cta, int nc
       p = __ldg(static_cast<const float *>(R.value));
     } else {
       // "no priority seen yet" is decided on the device (the running max is still -inf), not by the host's flag, so
-      // that a launch captured in a CUDA graph stays right when it is replayed after priorities have arrived
-      const float mx = ld_cg(R.max_buf);
+      // that a launch captured in a CUDA graph stays right when it is replayed after priorities have arrived.
+      // ONE thread reads the running max and the CTA shares it: the ticket below (taken by thread 0 after the barrier)
+      // then really means "every thread of this CTA has its copy of the OLD max" -- with per-thread reads the last
+      // CTA could publish the new max while warps of an earlier CTA had not loaded yet, and those warps would fill
+      // their nodes with a different leaf value.
+      __shared__ float s_mx;
+      if (tid == 0) s_mx = ld_cg(R.max_buf);
+      __syncthreads();
+      const float mx = s_mx;
       p = (R.has_max && mx > -INFINITY) ? pow_like_torch(add_rn(mx, R.eps), R.alpha) : R.first_default;
     }
     v = (T)pow_like_torch(add_rn(p, R.eps), R.alpha);

@@ -592,6 +592,54 @@ def test_gather_peer_replication_single_gpu(cuda_backend, mode):
     assert torch.equal(gidx, idx + 1000)
 
 
+def test_shard_flag_exchange_single_gpu(cuda_backend):
+    """The split-phase exchange's flags on one GPU: three 'ranks' are three regions [flags | rows] of one buffer.
+    rlb_shard_pack(rank=r) release-stores its sequence number into slot r of every region's flags; rlb_shard_weights
+    waits until all slots have reached its own call count; a missing rank trips the bounded wait and the status bit."""
+    from rl_b200 import ops
+    from rl_b200.data.sharded import _PackedLayout
+
+    N, B, W = 2000, 64, 3
+    g = torch.Generator(device=dev()).manual_seed(14)
+    leaves = [torch.randn(N, 24, device=dev(), generator=g), torch.randint(0, 9, (N, 1), device=dev(), generator=g)]
+    lay = _PackedLayout(leaves)
+    region = 256 + W * B * lay.row
+    region += (-region) % 256
+    raw = torch.zeros(W * region, dtype=torch.uint8, device=dev())
+    flags = [raw[r * region:r * region + 256].view(torch.int64)[:W] for r in range(W)]
+    rows = [raw[r * region + 256:r * region + 256 + W * B * lay.row].view(W * B, lay.row) for r in range(W)]
+    ctr = torch.zeros((W, 2), dtype=torch.int64, device=dev())
+    status = torch.zeros(1, dtype=torch.int32, device=dev())
+    pp = torch.tensor([2.0, 0.5], device=dev())
+    for seq in (1, 2):
+        idxs = []
+        for r in range(W):
+            idx = torch.randint(0, N, (B,), device=dev(), generator=g)
+            idxs.append(idx)
+            mine = rows[r][r * B:(r + 1) * B]
+            peers = [(q - r) * region for q in range(W)]
+            cuda_backend.gather(leaves, idx, N, out=lay.leaf_views(mine), peer_delta=peers)
+            cuda_backend.shard_pack(mine, lay.meta, idx, torch.rand(B, device=dev(), generator=g) + 0.5, pp, r * N,
+                                    peer_delta=peers, flags=flags[r], seq_counter=ctr[r, 0:1], rank=r)
+            if r == W - 2 and seq == 2:
+                # rank W-1 has not published draw 2 yet: a wait on region 0 must time out and say so
+                w, gi = cuda_backend.shard_weights(rows[0], lay.meta, 0.4, flags=flags[0], wait_counter=ctr[0, 1:2],
+                                                   n_ranks=W, timeout_s=0.05, status=status)
+                torch.cuda.synchronize()
+                assert int(status.item()) & ops.STATUS_EXCHANGE_TIMEOUT
+                status.zero_()
+                ctr[0, 1] -= 1   # that wait did not pair with a complete draw
+        for r in range(W):
+            assert flags[r].tolist() == [seq] * W
+            w, gi = cuda_backend.shard_weights(rows[r], lay.meta, 0.4, flags=flags[r], wait_counter=ctr[r, 1:2],
+                                               n_ranks=W, timeout_s=5.0, status=status)
+            assert torch.equal(gi, torch.cat([idxs[q] + q * N for q in range(W)]))
+            for leaf, view in zip(leaves, lay.leaf_views(rows[r])):
+                assert torch.equal(view, torch.cat([leaf[idxs[q]] for q in range(W)]))
+        assert int(status.item()) == 0
+    assert ctr[:, 0].tolist() == [2] * W and ctr[:, 1].tolist() == [2] * W
+
+
 def test_update_priority_chunked_under_capture(cuda_backend):
     """More than 1024 priorities inside a CUDA graph: applied as <=1024-item chunks, same heap as the eager call."""
     from rl_b200.data import PrioritizedSampler
