@@ -80,20 +80,14 @@ __device__ __forceinline__ void scan_coeffs(T vv, T nvv, T rr, bool dn, bool tm,
   }
 }
 
+// One 128-step tile of one row, as seen by one warp: each lane's four (d, c) pairs + state values.
 template <typename T, bool VEC, int MODE>
-__global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
-    const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r, const uint8_t *__restrict__ done,
-    const uint8_t *__restrict__ term, T gamma, T gl, T oml, int64_t rows, int64_t Tlen, T *__restrict__ adv,
-    T *__restrict__ tgt) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = blockIdx.x * (int64_t)kGaeWarpsPerCta + (threadIdx.x >> 5);
-  if (row >= rows) return;  // whole warps leave together
-  const int64_t base = row * Tlen;
-  const int64_t ntiles = (Tlen + kGaeTile - 1) / kGaeTile;
-  T carry = (T)0;  // A at the first step of the tile processed before (later in time); prev_advantage = 0
-  for (int64_t tile = ntiles - 1; tile >= 0; --tile) {
-    const int64_t t0 = tile * kGaeTile + 4 * lane;  // first of this lane's four steps
-    T d[4], c[4], sv[4];
+struct GaeTile {
+  T d[4], c[4], sv[4];
+
+  __device__ __forceinline__ void load(const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r,
+                                       const uint8_t *__restrict__ done, const uint8_t *__restrict__ term, int64_t base,
+                                       int64_t t0, int64_t Tlen, T gamma, T gl, T oml) {
     if (VEC && t0 + 4 <= Tlen) {
       Vec4<T> qv = {{(T)0, (T)0, (T)0, (T)0}};
       if constexpr (MODE == 0) qv = load4<T>(v + base + t0);
@@ -130,15 +124,18 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
         }
       }
     }
-    // lane-local composition: A_{t0} = Bq + Cq * A_{t0+4}
-    T Bq = d[3], Cq = c[3];
+  }
+
+  // inclusive suffix scan of the lane maps: afterwards A_{t0(lane)} = Bs + Cs * (A entering the tile from the right)
+  __device__ __forceinline__ void scan(int lane, T &Bs, T &Cs) const {
+    T Bq = d[3], Cq = c[3];  // lane-local composition: A_{t0} = Bq + Cq * A_{t0+4}
 #pragma unroll
     for (int j = 2; j >= 0; --j) {
       Bq = d[j] + c[j] * Bq;
       Cq = c[j] * Cq;
     }
-    // inclusive suffix scan across lanes: afterwards A_{t0(lane)} = Bs + Cs * carry
-    T Bs = Bq, Cs = Cq;
+    Bs = Bq;
+    Cs = Cq;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const T Bo = __shfl_down_sync(0xffffffffu, Bs, o);
@@ -148,6 +145,11 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
         Cs = Cs * Co;
       }
     }
+  }
+
+  // the four local values re-derived serially from the value entering the lane; returns A at the tile's first step
+  __device__ __forceinline__ T finish(int lane, T Bs, T Cs, T carry, int64_t base, int64_t t0, int64_t Tlen,
+                                      T *__restrict__ adv, T *__restrict__ tgt) const {
     const T a_first = Bs + Cs * carry;
     // value entering this lane from the right = A at the first step of lane+1 (carry for lane 31)
     T a_next = __shfl_down_sync(0xffffffffu, a_first, 1);
@@ -159,7 +161,6 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
       oa.v[j] = a_next;
       ot.v[j] = a_next + sv[j];  // value_target = advantage + state_value (functional.py:178)
     }
-    carry = __shfl_sync(0xffffffffu, oa.v[0], 0);
     if (VEC && t0 + 4 <= Tlen) {
       store4(adv + base + t0, oa);
       if constexpr (MODE == 0) store4(tgt + base + t0, ot);
@@ -172,6 +173,74 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
         }
       }
     }
+    return __shfl_sync(0xffffffffu, oa.v[0], 0);
+  }
+};
+
+// Many rows: one WARP per row (blockDim.x / 32 rows per CTA); rows longer than a tile are walked from the end.
+template <typename T, bool VEC, int MODE>
+__global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
+    const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r, const uint8_t *__restrict__ done,
+    const uint8_t *__restrict__ term, T gamma, T gl, T oml, int64_t rows, int64_t Tlen, T *__restrict__ adv,
+    T *__restrict__ tgt) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;  // whole warps leave together
+  pdl_wait();
+  const int64_t base = row * Tlen;
+  const int64_t ntiles = (Tlen + kGaeTile - 1) / kGaeTile;
+  T carry = (T)0;  // A at the first step of the tile processed before (later in time); prev_advantage = 0
+  for (int64_t tile = ntiles - 1; tile >= 0; --tile) {
+    const int64_t t0 = tile * kGaeTile + 4 * lane;  // first of this lane's four steps
+    GaeTile<T, VEC, MODE> g;
+    g.load(v, nv, r, done, term, base, t0, Tlen, gamma, gl, oml);
+    T Bs, Cs;
+    g.scan(lane, Bs, Cs);
+    carry = g.finish(lane, Bs, Cs, carry, base, t0, Tlen, adv, tgt);
+  }
+}
+
+// Few rows (the reference benchmark's [300,500], [32,512], [1,512]): one CTA per row, one WARP per TILE.  All tiles of a
+// chunk are loaded at once (the serial walk above pays one DRAM round trip per tile); lane 0 of each warp publishes
+// its tile's composite map, and every warp folds the maps of the tiles to its right -- the serial recurrence at tile
+// granularity -- to get the value entering its tile.  Rows longer than blockDim.x * 4 steps go chunk by chunk.
+constexpr int kGaeMaxRowWarps = 16;
+template <typename T, bool VEC, int MODE>
+__global__ void __launch_bounds__(kGaeMaxRowWarps * 32) gae_row_cta_kernel(
+    const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r, const uint8_t *__restrict__ done,
+    const uint8_t *__restrict__ term, T gamma, T gl, T oml, int64_t rows, int64_t Tlen, T *__restrict__ adv,
+    T *__restrict__ tgt) {
+  __shared__ T sB[kGaeMaxRowWarps], sC[kGaeMaxRowWarps];
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t row = blockIdx.x;
+  const int64_t base = row * Tlen;
+  const int64_t ntiles = (Tlen + kGaeTile - 1) / kGaeTile;
+  pdl_wait();
+  T chunk_carry = (T)0;
+  for (int64_t hi = ntiles; hi > 0; hi -= nw) {      // tiles [hi - nw, hi) of this chunk, later tiles first
+    const int64_t tile = hi - nw + warp;             // may be negative in the last chunk: an empty tile
+    const int64_t t0 = tile * kGaeTile + 4 * lane;
+    GaeTile<T, VEC, MODE> g;
+    T Bs = (T)0, Cs = (T)1;                          // identity map for an empty tile
+    if (tile >= 0) {
+      g.load(v, nv, r, done, term, base, t0, Tlen, gamma, gl, oml);
+      g.scan(lane, Bs, Cs);
+    }
+    if (lane == 0) {
+      sB[warp] = Bs;
+      sC[warp] = Cs;
+    }
+    __syncthreads();
+    T cin = chunk_carry, mine = chunk_carry;
+    for (int w = nw - 1; w >= 0; --w) {              // value entering tile w = A at the first step of tile w + 1
+      if (w == warp) mine = cin;
+      cin = sB[w] + sC[w] * cin;
+    }
+    chunk_carry = cin;                               // A at the first step of the chunk
+    if (tile >= 0) g.finish(lane, Bs, Cs, mine, base, t0, Tlen, adv, tgt);
+    __syncthreads();
   }
 }
 
@@ -208,18 +277,32 @@ static int gae_impl(const void *v, const void *nv, const void *r, const uint8_t 
   const T *pv = static_cast<const T *>(v), *pn = static_cast<const T *>(nv), *pr = static_cast<const T *>(r);
   T *pa = static_cast<T *>(adv), *pt = static_cast<T *>(tgt);
   if (F == 1) {
-    const int64_t blocks = (rows + kGaeWarpsPerCta - 1) / kGaeWarpsPerCta;
-    RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many rows for one launch");
     auto al = [](const void *p, uintptr_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
     const bool vec = (Tlen % 4 == 0) && al(v, 16) && al(nv, 16) && al(r, 16) && al(adv, 16) && al(tgt, 16) &&
                      al(done, 4) && al(term, 4);
+    const int sms = sm_count();
+    const int64_t ntiles = (Tlen + kGaeTile - 1) / kGaeTile;
+    if (ntiles >= 2 && rows <= 4 * (int64_t)sms) {  // few long rows: CTA per row, warp per tile
+      const int nw = (int)(ntiles < kGaeMaxRowWarps ? ntiles : kGaeMaxRowWarps);
+      if (vec)
+        return check_cuda(launch_pdl(gae_row_cta_kernel<T, true, MODE>, dim3((unsigned)rows), dim3(nw * 32), 0, st, pv,
+                                     pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt),
+                          "gae_row_cta_kernel");
+      return check_cuda(launch_pdl(gae_row_cta_kernel<T, false, MODE>, dim3((unsigned)rows), dim3(nw * 32), 0, st, pv,
+                                   pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt),
+                        "gae_row_cta_kernel");
+    }
+    // many rows: warp per row; with few (short) rows one warp per CTA so that they spread over the SMs
+    const int wpc = rows >= 8 * (int64_t)sms ? kGaeWarpsPerCta : (rows >= 2 * (int64_t)sms ? 2 : 1);
+    const int64_t blocks = (rows + wpc - 1) / wpc;
+    RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many rows for one launch");
     if (vec)
-      gae_rows_kernel<T, true, MODE><<<(unsigned)blocks, kGaeWarpsPerCta * 32, 0, st>>>(
-          pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt);
-    else
-      gae_rows_kernel<T, false, MODE><<<(unsigned)blocks, kGaeWarpsPerCta * 32, 0, st>>>(
-          pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt);
-    return check_launch("gae_rows_kernel");
+      return check_cuda(launch_pdl(gae_rows_kernel<T, true, MODE>, dim3((unsigned)blocks), dim3(wpc * 32), 0, st, pv,
+                                   pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt),
+                        "gae_rows_kernel");
+    return check_cuda(launch_pdl(gae_rows_kernel<T, false, MODE>, dim3((unsigned)blocks), dim3(wpc * 32), 0, st, pv,
+                                 pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt),
+                      "gae_rows_kernel");
   }
   const int64_t cols = rows * F;
   const int64_t blocks = (cols + 255) / 256;

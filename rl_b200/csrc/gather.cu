@@ -308,6 +308,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
 template <bool SCATTER>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const __grid_constant__ GatherParams P) {
   extern __shared__ __align__(128) uint8_t gsmem[];
+  pdl_trigger();  // whatever follows in the stream (the trailer kernel, the next gather) may start launching
   if ((int)blockIdx.x < P.bulk_ctas) {
     PipeSmem *ps = reinterpret_cast<PipeSmem *>(gsmem);
     uint8_t *ring = gsmem + kPipeHeaderBytes;  // PipeSmem[kPipes] header; stages stay 128-B aligned

@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   __shared__ T s_p[2];
   __shared__ T s_top[1 << kTopLevels];
   pdl_trigger();  // a dependent launch (the gather) may become resident now; it waits for this grid before the index
+  pdl_wait();     // launched with PDL itself: the uniforms (torch.rand) and the trees are final from here on
   if (dbg && (blockIdx.x != 0 || threadIdx.x != 0)) dbg = nullptr;
   if (dbg) dbg[8] = (long long)clock64();
   const int warp = threadIdx.x >> 5;
@@ -418,10 +419,13 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
 //
 // The sibling reads below the cut are 2 x bot scattered 4-byte loads per item, and a single SM's L1 moves only about
 // one sector wavefront every ~2 cycles, which made them the whole cost of earlier single-CTA versions.  So the launch
-// has TWO phases: (A) 2 x bot CTAs spread over the chip read every (item, level) sibling and write it, coalesced, to a
-// scratch tile; the last CTA to finish (atomic ticket) alone continues with (B): sort, merge levels, climb, dense top.
-// Finished node values are streamed to the global trees by WRITER warps (the upper half of the block), signalled per
-// level through mbarriers, because a global store before a CTA barrier makes the barrier wait for the L2 round trip.
+// is ONE THREAD-BLOCK CLUSTER of 8 CTAs: CTA 0 (the leader) sorts and climbs; the seven helpers read every (item,
+// level) sibling of both trees and store it straight into the LEADER's shared-memory tile through distributed shared
+// memory (st.shared::cluster), then release a cluster barrier the leader acquires just before it needs the tile --
+// by then it has loaded its keys and sorted them, so the fetch costs it nothing.  No scratch in global memory, no
+// atomic ticket, no second round trip (earlier versions: a grid of CTAs wrote a scratch tile, the last one to take a
+// ticket re-read it).  Finished node values are streamed to the global trees by WRITER warps (the upper half of the
+// leader) once the climb is done, while the compute warps recompute the dense top.
 // FUSED (fp32): `value` holds RAW priorities; the leaf is (p + eps) ** alpha (samplers.py:1076, torch.pow semantics)
 // and the maximum raw priority of the valid items is folded into *max_out.
 #ifndef RLB_UPDATE_DENSE_LEVELS
@@ -444,9 +448,7 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-constexpr size_t kUpdCtrlBytes = 1024;                 // ticket counter lives at the start of the workspace
-constexpr size_t kUpdScratchBytes = (size_t(1) << 20) - kUpdCtrlBytes;
-constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // stamps of the general path start here
+constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // (reserved head of the workspace) stamps of the general path start here
 
 __host__ __device__ inline int upd_bot_levels(int depth) { return depth > kDenseLevels ? depth - kDenseLevels : 0; }
 
@@ -470,36 +472,126 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long)hi << 32) | lo;
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void *smem_ptr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(smem_ptr)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+constexpr int kUpdCluster = 8;  // CTAs per update launch: the leader + seven sibling fetchers (portable cluster size)
+
 template <typename T, bool FUSED>
 __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, int64_t capacity, int depth,
                                                                const int64_t *__restrict__ index,
                                                                const T *__restrict__ value, int n, int scalar,
                                                                float alpha, float eps, float *max_out,
-                                                               int *ticket, T *__restrict__ scratch,
                                                                long long *dbg, int64_t index_base,
                                                                int64_t index_limit, int NP) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // NP (a power of two >= n) compute threads; when the block has 2*NP threads the upper half are WRITER warps
-  // that stream finished node values to the global trees while the compute warps are still climbing
+  // that stream finished node values to the global trees while the compute warps recompute the dense top
   const int tid = threadIdx.x;
   const bool has_writers = (int)blockDim.x == 2 * NP;
   const int lane = tid & 31;
   const int bot = upd_bot_levels(depth);   // levels climbed item by item; the rest is dense
   const int W = 1 << (depth - bot);        // nodes at the cut level
-  __shared__ int s_last;
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
   __shared__ unsigned s_lmask;                       // bit L set: some item hands over at level L (1 <= L <= bot)
-  __shared__ __align__(8) uint64_t s_level_done[33];  // mbarriers: [l] = level l is final, [32] = item info is final
+  __shared__ __align__(8) uint64_t s_done[2];        // mbarriers: [0] = item info is final, [1] = the climb is done
+  unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
+  uint32_t *sleaf = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);  // sorted leaf index (0xffffffff: not an item)
+  uint32_t *spos = sleaf + NP;                                    // its input position
+  int *Lw = reinterpret_cast<int *>(spos + NP);  // merge level of each head (0: not a head) -- for the writer warps
+  T *sraw = reinterpret_cast<T *>(Lw + NP);
+  T *lv = sraw + NP;   // leaf value of each head (for the writer warps)
+  T *sib = lv + NP;    // [2][bot][NP], indexed by ORIGINAL input position; reused as the output staging tile
+  T *cut_s = sib + 2 * (size_t)bot * NP;  // heap layout over the top of the tree: node k at [k], 1 <= k < 2W
+  T *cut_m = cut_s + 2 * (size_t)W;
+
+  // every thread of the cluster arrives once here: after the matching wait all CTAs are known to be running, which
+  // is what remote shared-memory stores need
+  cluster_arrive_release();
+
+  if (crank != 0) {
+    // ---- helpers: sib[t][l][i] (in the LEADER's shared memory) = tree_t[((capacity + index[i]) >> l) ^ 1] for the
+    // levels below the cut.  The loads are issued before the cluster is known to be up, the stores after.
+    constexpr int kMaxPer = 4;
+    const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
+    const uint32_t nthreads = (csize - 1u) * blockDim.x, g = (crank - 1u) * blockDim.x + tid;
+    T val[kMaxPer];
+    uint32_t el[kMaxPer];
+#pragma unroll
+    for (int k = 0; k < kMaxPer; ++k) {
+      const uint32_t e = g + (uint32_t)k * nthreads;
+      el[k] = e;
+      val[k] = (T)0;
+      if (e < total) {
+        const uint32_t t = e >= per_tree;
+        const uint32_t rem = e - t * per_tree;
+        const uint32_t l = rem / (uint32_t)NP;
+        const uint32_t i = rem - l * (uint32_t)NP;
+        const T *tree = t ? mn : sum;
+        if (tree && i < (uint32_t)n) {
+          const int64_t ix = __ldg(index + i) - index_base;
+          if (ix >= 0 && ix < index_limit) val[k] = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+        }
+      }
+    }
+    cluster_wait_acquire();
+#pragma unroll
+    for (int k = 0; k < kMaxPer; ++k)
+      if (el[k] < total) st_cluster(map_to_cta(sib + el[k], 0), val[k]);
+    for (uint32_t e = g + kMaxPer * nthreads; e < total; e += nthreads) {  // (only with fewer helpers than planned)
+      const uint32_t t = e >= per_tree;
+      const uint32_t rem = e - t * per_tree;
+      const uint32_t l = rem / (uint32_t)NP;
+      const uint32_t i = rem - l * (uint32_t)NP;
+      const T *tree = t ? mn : sum;
+      T v = (T)0;
+      if (tree && i < (uint32_t)n) {
+        const int64_t ix = __ldg(index + i) - index_base;
+        if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+      }
+      st_cluster(map_to_cta(sib + e, 0), v);
+    }
+    cluster_arrive_release();  // my stores are performed before the leader's wait returns
+    return;
+  }
+
+  // ---- leader
   if (tid == 0) {
     s_lmask = 0u;
     if (has_writers) {
-      for (int k = 0; k < 32; ++k) mbar_init(&s_level_done[k], NP >> 5);  // one arrival per compute warp
-      mbar_init(&s_level_done[32], 1);
+      mbar_init(&s_done[0], 1);
+      mbar_init(&s_done[1], 1);
       fence_mbar_init();
     }
   }
-
-  const long long t_start = dbg ? (long long)clock64() : 0;  // stamps are taken by the CTA that runs phase B
-  // my own item (every CTA loads it: phase A needs the indices anyway, the last CTA needs the values)
+  if (dbg && tid == 0) dbg[0] = (long long)clock64();
+  // my own item
   bool valid = false;
   int64_t my_ix = -1;
   T raw = (T)0;
@@ -510,57 +602,17 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     valid = (my_ix >= 0 && my_ix < index_limit);
     raw = scalar ? __ldg(value) : __ldg(value + tid);
   }
-
-  // ---- phase A (all CTAs): scratch[t][l][i] = tree_t[((capacity + index[i]) >> l) ^ 1] for the levels below the
-  // cut, one element per thread per pass (the grid is sized so that there is normally a single pass)
-  if (bot > 0) {
-    const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP;
-    const uint32_t total = 2u * per_tree;
-    for (uint32_t e = blockIdx.x * (uint32_t)NP + tid; tid < NP && e < total; e += gridDim.x * (uint32_t)NP) {
-      const uint32_t t = e >= per_tree;
-      const uint32_t rem = e - t * per_tree;
-      const uint32_t l = rem / (uint32_t)NP;
-      const uint32_t i = rem - l * (uint32_t)NP;  // == tid
-      const T *tree = t ? mn : sum;
-      T v = (T)0;
-      if (tree && i < (uint32_t)n) {
-        const int64_t ix = (i == (uint32_t)tid) ? my_ix : __ldg(index + i) - index_base;
-        if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
-      }
-      scratch[e] = v;
-    }
-    if (gridDim.x > 1) {
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) {
-        const int prev = atomicAdd(ticket, 1);
-        s_last = (prev == (int)gridDim.x - 1);
-        if (s_last) *ticket = 0;  // ready for the next launch
-      }
-      __syncthreads();
-      if (!s_last) return;
-      __threadfence();
-    }
-  }
   __syncthreads();  // s_lmask / mbarrier initialisation visible to everybody
-  if (dbg && threadIdx.x == 0) dbg[0] = t_start;
   RLB_TICK(1);
 
-  // ---- phase B (last CTA only)
-  unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
-  uint32_t *sleaf = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);  // sorted leaf index (0xffffffff: not an item)
-  uint32_t *spos = sleaf + NP;                                    // its input position
-  int *Lw = reinterpret_cast<int *>(spos + NP);  // merge level of each head (0: not a head) -- for the writer warps
-  T *sraw = reinterpret_cast<T *>(Lw + NP);
-  T *lv = sraw + NP;   // leaf value of each head (for the writer warps)
-  T *sib = lv + NP;    // [2][bot][NP], indexed by ORIGINAL input position; reused as the output staging tile
-  T *cut_s = sib + 2 * (size_t)bot * NP;  // heap layout over the top of the tree: node k at [k], 1 <= k < 2W
-  T *cut_m = cut_s + 2 * (size_t)W;
   if (tid >= NP) {
-    // ---- writer warps: wait until a level is final, then scatter it.  Their stores drain on their own
-    // barriers, never on the compute warps' one.
+    // ---- writer warps: the cluster protocol first (every thread arrives on both phases), then wait until the item
+    // info and the climb are final and scatter leaves + carried ancestors.  Only lane 0 polls.
+    cluster_wait_acquire();
+    cluster_arrive_release();
     const int w = tid - NP;
-    mbar_wait_parity(&s_level_done[32], 0);
+    if (lane == 0) mbar_wait_parity(&s_done[0], 0);
+    __syncwarp();
     const int wL = Lw[w];
     const uint32_t wleaf = (uint32_t)capacity + sleaf[w];
     const uint32_t wpos = spos[w];
@@ -569,23 +621,18 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       if (sum) sum[wleaf] = v;
       if (mn) mn[wleaf] = v;
     }
-    for (int l = 0; l < bot; ++l) {
-      mbar_wait_parity(&s_level_done[l], 0);
-      if (wL > l + 1) {  // item w carried node (wleaf >> (l + 1))
-        const uint32_t parent = wleaf >> (l + 1);
-        if (sum) sum[parent] = sib[(size_t)l * NP + wpos];
-        if (mn) mn[parent] = sib[(size_t)bot * NP + (size_t)l * NP + wpos];
-      }
+    if (lane == 0) mbar_wait_parity(&s_done[1], 0);
+    __syncwarp();
+    for (int l = 0; l < bot && wL > l + 1; ++l) {  // item w carried node (wleaf >> (l + 1)) for every l + 1 < wL
+      const uint32_t parent = wleaf >> (l + 1);
+      if (sum) sum[parent] = sib[(size_t)l * NP + wpos];
+      if (mn) mn[parent] = sib[(size_t)bot * NP + (size_t)l * NP + wpos];
     }
     return;
   }
   auto compute_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(NP) : "memory"); };
   {
-    // coalesced 16-byte async copies: the scratch tile and the cut level of both trees (land while we sort)
-    const size_t bytes = 2 * (size_t)bot * NP * sizeof(T);
-    const unsigned char *g = reinterpret_cast<const unsigned char *>(scratch);
-    unsigned char *d = reinterpret_cast<unsigned char *>(sib);
-    for (size_t off = (size_t)tid * 16; off < bytes; off += (size_t)NP * 16) cp_async16(d + off, g + off);
+    // coalesced 16-byte async copies of the cut level of both trees (land while we sort)
     constexpr int kPer16 = 16 / (int)sizeof(T);
     if (W >= kPer16) {
       for (int k = tid * kPer16; k < W; k += NP * kPer16) {
@@ -692,7 +739,29 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   sleaf[tid] = myleaf;
   spos[tid] = pos;
   cp_async_wait_all();
+  // the sibling tile: every helper has stored its share into this CTA's shared memory once this returns
+  cluster_wait_acquire();
+  cluster_arrive_release();
+  if (csize > 1) cluster_wait_acquire();
   compute_sync();
+  if (csize == 1 && bot > 0) {
+    // (launched without helpers: fetch the siblings here -- correct, just slow)
+    const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
+    for (uint32_t e = tid; e < total; e += NP) {
+      const uint32_t t = e >= per_tree;
+      const uint32_t rem = e - t * per_tree;
+      const uint32_t l = rem / (uint32_t)NP;
+      const uint32_t i = rem - l * (uint32_t)NP;
+      const T *tree = t ? mn : sum;
+      T v = (T)0;
+      if (tree && i < (uint32_t)n) {
+        const int64_t ix = __ldg(index + i) - index_base;
+        if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+      }
+      sib[e] = v;
+    }
+    compute_sync();
+  }
   RLB_TICK(4);
 
   // ---- 4. per head j: merge level L_j, and WHERE its hand-over goes (only merges below the cut hand over)
@@ -732,7 +801,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   }
   compute_sync();
   const unsigned lmask = s_lmask;
-  if (has_writers && tid == 0) mbar_arrive(&s_level_done[32]);  // item info (sleaf/spos/Lw/lv) is final
+  if (has_writers && tid == 0) mbar_arrive(&s_done[0]);  // item info (sleaf/spos/Lw/lv) is final
   RLB_TICK(5);
 
   // ---- 5. climb below the cut.  Nothing but registers and shared memory inside the loop: the parent computed at
@@ -759,28 +828,79 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
     }
     if ((lmask >> (l + 2)) & 1u) compute_sync();  // somebody handed over: the leader reads it in the next iteration
-    if (has_writers) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_level_done[l]);  // this warp's level-l values are in the staging tile
-    }
   }
   RLB_TICK(6);
 
-  // ---- 6. dense top: items that reached the cut overwrite their node, then W - 1 pairwise recomputations
+  // ---- 6. dense top: items that reached the cut overwrite their node, then the W - 1 nodes above are recomputed,
+  // node = op(node 2k, node 2k+1).  Three barriers in all: each thread reduces the subtree over its own `per`
+  // consecutive cut nodes alone, warps continue with shuffles, warp 0 finishes.
   if (alive) {
     const uint32_t node = ((uint32_t)capacity + myleaf) >> bot;  // in [W, 2W)
     cut_s[node] = vs;
     cut_m[node] = vm;
   }
   compute_sync();
-  for (int w = W >> 1; w >= 1; w >>= 1) {
-    for (int k = tid; k < w; k += NP) {
-      const int node = w + k;
-      if (sum) cut_s[node] = tree_op<T, false>(cut_s[node << 1], cut_s[(node << 1) | 1]);
-      if (mn) cut_m[node] = tree_op<T, true>(cut_m[node << 1], cut_m[(node << 1) | 1]);
+  if (has_writers && tid == 0) mbar_arrive(&s_done[1]);  // staging tile final: the writer warps may scatter it
+  {
+    const int per = W >= NP ? W / NP : 1;      // cut nodes per thread
+    const int A = W >= NP ? NP : W;            // threads that own a subtree; its root is node A + tid
+    const bool act = tid < A;
+    const int plev = 31 - __clz(per);          // levels inside the thread-private subtree
+    T rs = (T)0, rm = (T)0;
+    if (act) {
+      const int r = A + tid;
+      for (int lev = plev - 1; lev >= 0; --lev) {
+        const int first = r << lev;
+        for (int j = 0; j < (1 << lev); ++j) {
+          const int node = first + j;
+          if (sum) cut_s[node] = tree_op<T, false>(cut_s[node << 1], cut_s[(node << 1) | 1]);
+          if (mn) cut_m[node] = tree_op<T, true>(cut_m[node << 1], cut_m[(node << 1) | 1]);
+        }
+      }
+      if (sum) rs = cut_s[r];
+      if (mn) rm = cut_m[r];
     }
-    compute_sync();
+    // warp level: lanes whose index is a multiple of 2^(s+1) combine with the lane 2^s to their right
+    const int wlev = A >= 32 ? 5 : 31 - __clz(A);
+    int node = A + tid;
+    for (int sft = 0; sft < wlev; ++sft) {
+      const T os = __shfl_down_sync(0xffffffffu, rs, 1 << sft);
+      const T om = __shfl_down_sync(0xffffffffu, rm, 1 << sft);
+      node >>= 1;
+      if (act && (lane & ((2 << sft) - 1)) == 0) {
+        rs = tree_op<T, false>(rs, os);
+        rm = tree_op<T, true>(rm, om);
+        if (sum) cut_s[node] = rs;
+        if (mn) cut_m[node] = rm;
+      }
+    }
+    if (A > 32) {  // A / 32 subtree roots left (nodes A/32 + warp), one per warp: warp 0 finishes
+      compute_sync();
+      const int A2 = A >> 5;
+      if (tid < 32) {
+        const bool act2 = tid < A2;
+        T qs = (T)0, qm = (T)0;
+        if (act2) {
+          if (sum) qs = cut_s[A2 + tid];
+          if (mn) qm = cut_m[A2 + tid];
+        }
+        int node2 = A2 + tid;
+        const int lev2 = 31 - __clz(A2);
+        for (int sft = 0; sft < lev2; ++sft) {
+          const T os = __shfl_down_sync(0xffffffffu, qs, 1 << sft);
+          const T om = __shfl_down_sync(0xffffffffu, qm, 1 << sft);
+          node2 >>= 1;
+          if (act2 && (lane & ((2 << sft) - 1)) == 0) {
+            qs = tree_op<T, false>(qs, os);
+            qm = tree_op<T, true>(qm, om);
+            if (sum) cut_s[node2] = qs;
+            if (mn) cut_m[node2] = qm;
+          }
+        }
+      }
+    }
   }
+  compute_sync();
   for (int k = 1 + tid; k < W; k += NP) {
     if (sum) sum[k] = cut_s[k];
     if (mn) mn[k] = cut_m[k];
@@ -961,17 +1081,29 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
     if (rc) return rc;
     attr_set = true;
   }
-  // phase A grid: one scattered sibling read per thread (2 * bot CTAs), at most one CTA per SM
-  int64_t grid = 2 * (int64_t)upd_bot_levels(depth);
-  const int sms = sm_count();
-  if (grid > sms) grid = sms;
-  if (grid < 1) grid = 1;
-  int *ticket = static_cast<int *>(workspace);
-  T *scratch = reinterpret_cast<T *>(static_cast<unsigned char *>(workspace) + kUpdCtrlBytes);
+  // one cluster: the leader + the sibling fetchers (none needed when the whole tree is above the cut)
+  const int bot = upd_bot_levels(depth);
   const int threads = (np <= 512 && depth <= 32) ? 2 * np : np;  // room for the writer warps?
-  tree_update_cta_kernel<T, FUSED><<<(unsigned)grid, threads, smem, st>>>(
-      sum, mn, capacity, depth, index, value, (int)n, scalar, fp.alpha, fp.eps, fp.max_out, ticket, scratch,
-      g_debug_ticks, fp.index_base, fp.index_limit < 0 ? capacity : fp.index_limit, np);
+  const unsigned cluster = bot > 0 ? kUpdCluster : 1;
+  (void)workspace;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int rc = check_cuda(cudaLaunchKernelEx(&cfg, tree_update_cta_kernel<T, FUSED>, sum, mn, capacity, depth, index, value,
+                                         (int)n, scalar, fp.alpha, fp.eps, fp.max_out, g_debug_ticks, fp.index_base,
+                                         fp.index_limit < 0 ? capacity : fp.index_limit, np),
+                      "tree_update_cta_kernel");
+  if (rc) return rc;
   return check_launch("tree_update_cta_kernel");
 }
 
@@ -980,8 +1112,8 @@ static bool update_fits_cta(int64_t n, int64_t capacity, int depth) {
   if (n > 1024 || capacity > (int64_t(1) << 30)) return false;
   int np = 32;
   while (np < n) np <<= 1;
-  return upd_smem_bytes<T>(np, depth) <= (size_t)kUpdateSmemLimit &&
-         2 * (size_t)upd_bot_levels(depth) * np * sizeof(T) <= kUpdScratchBytes;
+  // the helpers stage at most 4 siblings per thread in registers (and loop beyond that)
+  return upd_smem_bytes<T>(np, depth) <= (size_t)kUpdateSmemLimit;
 }
 
 
@@ -1181,18 +1313,22 @@ int rlb_per_sample(const void *sum_tree, const void *min_tree, int64_t size, int
     if (spc > 32) spc = 32;
   }
   const unsigned blocks = (unsigned)((B + spc - 1) / spc);
+  int rc;
   if (dtype == RLB_F32)
-    per_sample_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(
-        (const float *)sum_tree, (const float *)min_tree, size, capacity, depth, len, (const float *)u, B,
-        (float)(-beta), cpu_semantics, speculative, spc, index_out, weight_out, (float *)leaf_out,
-        (float *)psum_pmin_out, status, g_debug_ticks);
+    rc = check_cuda(launch_pdl(per_sample_kernel<float>, dim3(blocks), dim3(threads), 0, as_stream(stream),
+                               (const float *)sum_tree, (const float *)min_tree, size, capacity, depth, len,
+                               (const float *)u, B, (float)(-beta), cpu_semantics, speculative, spc, index_out,
+                               weight_out, (float *)leaf_out, (float *)psum_pmin_out, status, g_debug_ticks),
+                    "per_sample_kernel");
   else if (dtype == RLB_F64)
-    per_sample_kernel<double><<<blocks, threads, 0, as_stream(stream)>>>(
-        (const double *)sum_tree, (const double *)min_tree, size, capacity, depth, len, (const double *)u, B,
-        -beta, cpu_semantics, speculative, spc, index_out, weight_out, (double *)leaf_out, (double *)psum_pmin_out,
-        status, g_debug_ticks);
+    rc = check_cuda(launch_pdl(per_sample_kernel<double>, dim3(blocks), dim3(threads), 0, as_stream(stream),
+                               (const double *)sum_tree, (const double *)min_tree, size, capacity, depth, len,
+                               (const double *)u, B, (double)(-beta), cpu_semantics, speculative, spc, index_out,
+                               weight_out, (double *)leaf_out, (double *)psum_pmin_out, status, g_debug_ticks),
+                    "per_sample_kernel");
   else
     RLB_REQUIRE(false, RLB_EINVAL, "rlb_per_sample: unsupported dtype %d", dtype);
+  if (rc) return rc;
   return check_launch("per_sample_kernel");
 }
 

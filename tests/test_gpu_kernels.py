@@ -468,7 +468,11 @@ def _gae_inputs(shape, seed, p=0.05, dtype=torch.float32):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (1, 5, 1), (3, 200, 1), (7, 3, 3, 1), (64, 128, 1), (9, 131, 1),
-                                   (2, 1000, 1), (4096, 128, 1), (5, 33, 3), (16, 64, 40), (300, 500, 1)])
+                                   (2, 1000, 1), (4096, 128, 1), (5, 33, 3), (16, 64, 40), (300, 500, 1),
+                                   # few rows / long T: CTA per row, warp per tile (benchmarks/test_objectives_benchmarks.py:122-153),
+                                   # several chunks of 16 tiles, ragged last tile, scalar (unaligned T) path, warp-per-CTA rows
+                                   (32, 512, 1), (1, 512, 1), (3, 4100, 1), (2, 2049, 1), (5, 257, 1), (700, 129, 1),
+                                   (400, 64, 1)])
 @pytest.mark.parametrize("gamma,lmbda", [(0.99, 0.95), (0.5, 0.1)])
 def test_gae_matches_f64_oracle(cuda_backend, shape, gamma, lmbda):
     from rl_b200.objectives.value import generalized_advantage_estimate, vec_generalized_advantage_estimate
@@ -668,7 +672,8 @@ def test_update_priority_chunked_under_capture(cuda_backend):
 
 
 # ---------------------------------------------------------------------------------------------------- TD(lambda)
-@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 200, 1), (9, 131, 1), (4096, 128, 1), (5, 33, 3), (2, 1000, 1)])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 200, 1), (9, 131, 1), (4096, 128, 1), (5, 33, 3), (2, 1000, 1),
+                                   (3, 4100, 1), (300, 500, 1)])
 @pytest.mark.parametrize("gamma,lmbda", [(0.99, 0.95), (0.97, 1.0), (0.9, 0.0)])
 def test_td_lambda_matches_f64_oracle(cuda_backend, shape, gamma, lmbda):
     from rl_b200.objectives.value import td1_return_estimate, vec_td_lambda_advantage_estimate, vec_td_lambda_return_estimate
@@ -698,7 +703,8 @@ def test_td_lambda_golden(cuda_backend):
         torch.testing.assert_close(got.cpu(), gt("vec"), rtol=1e-4, atol=1e-4)   # the reference's own bar
 
 
-@pytest.mark.parametrize("shape", [(16, 80, 1), (3, 1000, 1), (5, 33, 3), (2, 3, 7, 1), (300, 5, 1), (1, 1, 1)])
+@pytest.mark.parametrize("shape", [(16, 80, 1), (3, 1000, 1), (5, 33, 3), (2, 3, 7, 1), (300, 5, 1), (1, 1, 1),
+                                   (2, 2300, 1)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_affine_scan_matches_oracle(cuda_backend, shape, dtype):
     """rlb_affine_scan against the C recurrence: fp64 to 1e-12, fp32 within the 1e-5 bar of the fp64 recurrence."""
@@ -907,3 +913,72 @@ def test_empty_and_degenerate_inputs(cuda_backend):
     one = SumSegmentTreeFp32(1, dev())
     one[torch.tensor([0], device=dev())] = torch.tensor([2.5], device=dev())
     assert one.capacity == 2 and one.query(0, 1) == 2.5 and one.scan_lower_bound(1.0) == 0
+
+
+# ------------------------------------------------------------------------- the reference's OWN CUDA path, end to end
+def test_sampler_matches_reference_cuda_path_without_leaf_injection(cuda_backend):
+    """The closing leg of the parity loop: this repo's PrioritizedSampler against the reference's CUDA branch --
+    the UNMODIFIED csrc/cuda_segment_tree.cu (oracle/_ref/cuda/_torchrl.so: CudaSum/MinSegmentTreeFp32) driven by the
+    glue of samplers.py:895-956 / :1054-1078 restated line by line, with torch.pow / torch.rand on the device.  Nothing
+    is injected: both sides start from raw priorities, apply (p + eps) ** alpha themselves (torch.pow there, the fused
+    kernel here), and must produce the same leaves, the same query results and the same sampled indices and weights
+    through several rounds of sample -> write-back with duplicate indices (shape of test/rb/test_prioritized.py:103-140)."""
+    from oracle.ref_loader import reference_ext
+    from rl_b200.data import PrioritizedSampler
+
+    ext = reference_ext("cuda")
+    if ext is None or not hasattr(ext, "CudaSumSegmentTreeFp32"):
+        pytest.skip("oracle/_ref/cuda/_torchrl.so not built")
+    N, n_filled, B, alpha, beta, eps = 50_000, 41_234, 256, 0.6, 0.4, 1e-8
+    d = dev()
+    rs, rm = ext.CudaSumSegmentTreeFp32(N, d), ext.CudaMinSegmentTreeFp32(N, d)
+    ours = PrioritizedSampler(N, alpha, beta, eps=eps, device=d, semantics="cuda")
+
+    class _St:  # what the sampler needs from a storage (benchmarks/test_replaybuffer_benchmark.py:95-105)
+        ndim, shape, device = 1, (n_filled,), d
+
+        def __len__(self):
+            return n_filled
+
+    st = _St()
+
+    def ref_update(index, priority):           # samplers.py:1076-1078 on the CUDA branch
+        leaf = torch.pow(priority + eps, alpha)
+        rs[index] = leaf
+        rm[index] = leaf
+
+    def ref_sample(gen):                       # samplers.py:899-953 on the CUDA branch
+        left = torch.zeros((), dtype=torch.long, device=d)
+        right = torch.full((), n_filled, dtype=torch.long, device=d)
+        p_sum, p_min = rs.query(left, right), rm.query(left, right)
+        mass = torch.rand(B, device=d, generator=gen) * p_sum
+        index = rs.scan_lower_bound(mass)
+        index.clamp_max_(n_filled - 1)
+        weight = torch.pow(rs[index] / p_min, -beta)
+        return index, weight, p_sum, p_min
+
+    g = torch.Generator(device=d).manual_seed(3)
+    all_idx = torch.arange(n_filled, device=d)
+    p0 = torch.rand(n_filled, device=d, generator=g) * 3
+    p0[::97] = 0.0                                        # eps keeps zero priorities positive
+    ref_update(all_idx, p0)
+    ours.update_priority(all_idx, p0)
+    g_ref, g_our = torch.Generator(device=d).manual_seed(9), torch.Generator(device=d).manual_seed(9)
+    ours._rng = g_our
+    for rnd in range(6):
+        assert torch.equal(rs[all_idx], ours._sum_tree[all_idx]), rnd           # leaves, bit for bit
+        assert torch.equal(rm[all_idx], ours._min_tree[all_idx]), rnd
+        lq = torch.randint(0, n_filled // 2, (64,), device=d, generator=g)
+        rq = lq + torch.randint(1, n_filled // 2, (64,), device=d, generator=g)
+        assert torch.equal(rs.query(lq, rq), ours._sum_tree.query(lq, rq, root_fast_path=False))  # internal nodes
+        assert torch.equal(rm.query(lq, rq), ours._min_tree.query(lq, rq, root_fast_path=False))
+        ri, rw, p_sum, p_min = ref_sample(g_ref)
+        oi, info = ours.sample(st, B)
+        assert torch.equal(ri, oi), rnd
+        assert torch.equal(rw, info["priority_weight"]), rnd
+        # write-back with duplicates (last writer wins on both sides) and fresh priorities
+        wi = torch.cat([oi, oi[:32], oi[5:9]])
+        wp = torch.rand(wi.numel(), device=d, generator=g) * 2
+        ref_update(wi, wp)
+        ours.update_priority(wi, wp)
+    torch.cuda.synchronize()
