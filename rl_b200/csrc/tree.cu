@@ -20,6 +20,7 @@
 // These are latency-bound pointer chases over an L2-resident array (16 MB for two 2^20 fp32 trees):
 // no tensor cores, no smem tiling of the tree itself.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tree_range.cuh"
@@ -388,7 +389,12 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   }
   index_out[i] = idx;
   if (leaf_out) leaf_out[i] = leaf;
-  const float w = (float)pow_like_torch(leaf / p_min, neg_beta);  // samplers.py:953
+  // samplers.py:953  torch.pow(weight / p_min, -beta).  On the reference's CPU branch that is a true division.  On its
+  // CUDA branch p_min is a PYTHON FLOAT (pybind resolves query(0-d tensor, 0-d tensor) to the (int64, int64) overload
+  // through __index__, csrc/cuda_segment_tree.h:268-270), and ATen's CUDA div by a CPU scalar multiplies by the
+  // reciprocal instead (BinaryDivTrueKernel.cu) -- up to one ulp away.  `cpu_semantics` selects which one is reproduced.
+  const T ratio = cpu_semantics ? leaf / p_min : mul_rn(leaf, (T)1 / p_min);
+  const float w = (float)pow_like_torch(ratio, neg_beta);
   weight_out[i] = w;
   if (dbg) dbg[11] = (long long)clock64() + (w > 1e30f ? 1 : 0);
 }
@@ -452,13 +458,21 @@ constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // (reserved head of the 
 
 __host__ __device__ inline int upd_bot_levels(int depth) { return depth > kDenseLevels ? depth - kDenseLevels : 0; }
 
+constexpr int kUpdCluster = 8;  // CTAs per update launch: the leader + seven helpers (portable cluster size)
+constexpr int kUpdHoist = 16;   // sibling values of this many levels are held in registers during the climb
+
+// rows of finished nodes: 2 leaf rows (sum / min tree) + 2 * bot (tree, level) rows, dealt out to the helpers
+__host__ __device__ inline int upd_row_slots(int bot) { return (2 * bot + 2 + (kUpdCluster - 2)) / (kUpdCluster - 1); }
+
 template <typename T>
 __host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
-  // xbuf u64[2*np] | sleaf u32[np] | spos u32[np] | Lw i32[np] | sraw T[np] | lv T[np] | sib T[2][bot][np] |
-  // cut heaps T[2][2W]
+  // xbuf u64[2*np] | sleaf u32[np] | spos u32[np] | sraw T[np] | sib T[2][bot][np] | cut heaps T[2][2W] |
+  // pnode u32[slots][np] | pval T[slots][np]
   const int bot = upd_bot_levels(depth);
   const size_t W = size_t(1) << (depth - bot);
-  return (size_t)np * (16 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (2 + 2 * (size_t)bot) + 4 * W * sizeof(T);
+  const size_t slots = (size_t)upd_row_slots(bot);
+  return (size_t)np * (16 + 4 + 4) + (size_t)np * sizeof(T) * (1 + 2 * (size_t)bot) + 4 * W * sizeof(T) +
+         slots * np * (4 + sizeof(T));
 }
 
 #define RLB_TICK(k)                                                   \
@@ -488,6 +502,16 @@ __device__ __forceinline__ void cluster_arrive_release() {
 __device__ __forceinline__ void cluster_wait_acquire() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// arrival that publishes nothing: no release fence (a release has to wait for the thread's outstanding global
+// stores to be acknowledged -- a microsecond the phases that carry no data should not pay)
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // address of the same shared-memory location in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t map_to_cta(const void *smem_ptr, uint32_t rank) {
   uint32_t r;
@@ -501,7 +525,9 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, double v) {
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-constexpr int kUpdCluster = 8;  // CTAs per update launch: the leader + seven sibling fetchers (portable cluster size)
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
 template <typename T, bool FUSED>
 __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, int64_t capacity, int depth,
@@ -509,38 +535,42 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
                                                                const T *__restrict__ value, int n, int scalar,
                                                                float alpha, float eps, float *max_out,
                                                                long long *dbg, int64_t index_base,
-                                                               int64_t index_limit, int NP) {
+                                                               int64_t index_limit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // NP (a power of two >= n) compute threads; when the block has 2*NP threads the upper half are WRITER warps
-  // that stream finished node values to the global trees while the compute warps recompute the dense top
+  const int NP = (int)blockDim.x;          // a power of two >= n: one item per thread
   const int tid = threadIdx.x;
-  const bool has_writers = (int)blockDim.x == 2 * NP;
   const int lane = tid & 31;
   const int bot = upd_bot_levels(depth);   // levels climbed item by item; the rest is dense
   const int W = 1 << (depth - bot);        // nodes at the cut level
+  const int slots = upd_row_slots(bot);
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
-  __shared__ unsigned s_lmask;                       // bit L set: some item hands over at level L (1 <= L <= bot)
-  __shared__ __align__(8) uint64_t s_done[2];        // mbarriers: [0] = item info is final, [1] = the climb is done
+  __shared__ unsigned s_lmask;             // bit L set: some item hands over at level L (1 <= L <= bot)
   unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
   uint32_t *sleaf = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);  // sorted leaf index (0xffffffff: not an item)
   uint32_t *spos = sleaf + NP;                                    // its input position
-  int *Lw = reinterpret_cast<int *>(spos + NP);  // merge level of each head (0: not a head) -- for the writer warps
-  T *sraw = reinterpret_cast<T *>(Lw + NP);
-  T *lv = sraw + NP;   // leaf value of each head (for the writer warps)
-  T *sib = lv + NP;    // [2][bot][NP], indexed by ORIGINAL input position; reused as the output staging tile
+  T *sraw = reinterpret_cast<T *>(spos + NP);                     // leaf values by input position
+  T *sib = sraw + NP;  // [2][bot][NP] sibling values, indexed by ORIGINAL input position
   T *cut_s = sib + 2 * (size_t)bot * NP;  // heap layout over the top of the tree: node k at [k], 1 <= k < 2W
   T *cut_m = cut_s + 2 * (size_t)W;
+  // HELPERS' side of the result rows: row r lives in helper 1 + r % (csize - 1), slot r / (csize - 1); the leader
+  // pushes (node id, value) pairs into it as it climbs, the helper scatters them to the trees (node 0 = nothing)
+  T *pval = cut_m + 2 * (size_t)W;
+  uint32_t *pnode = reinterpret_cast<uint32_t *>(pval + (size_t)slots * NP);
 
-  // every thread of the cluster arrives once here: after the matching wait all CTAs are known to be running, which
-  // is what remote shared-memory stores need
-  cluster_arrive_release();
+  // Cluster barrier phases (every thread of every CTA arrives on each, in this order):
+  //   1  "all CTAs are running" (remote shared-memory accesses are legal afterwards)
+  //   2  helpers -> leader: the sibling tile is complete (and the helpers' result rows are cleared)
+  //   3  leader -> helpers: every finished node below the cut has been pushed into its row
+  if (crank != 0) for (int k = tid; k < slots * NP; k += NP) pnode[k] = 0u;
+  cluster_arrive_relaxed();  // phase 1
+  if (dbg && tid == 0 && crank <= 1) dbg[32 + 8 * crank] = (long long)globaltimer_ns();
 
   if (crank != 0) {
-    // ---- helpers: sib[t][l][i] (in the LEADER's shared memory) = tree_t[((capacity + index[i]) >> l) ^ 1] for the
-    // levels below the cut.  The loads are issued before the cluster is known to be up, the stores after.
+    // ---- helpers, part 1: sib[t][l][i] (in the LEADER's shared memory) = tree_t[((capacity + index[i]) >> l) ^ 1]
+    // for the levels below the cut.  The loads are issued before the cluster is known to be up, the stores after.
     constexpr int kMaxPer = 4;
     const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
-    const uint32_t nthreads = (csize - 1u) * blockDim.x, g = (crank - 1u) * blockDim.x + tid;
+    const uint32_t nthreads = (csize - 1u) * (uint32_t)NP, g = (crank - 1u) * (uint32_t)NP + tid;
     T val[kMaxPer];
     uint32_t el[kMaxPer];
 #pragma unroll
@@ -560,11 +590,11 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         }
       }
     }
-    cluster_wait_acquire();
+    cluster_wait_acquire();  // phase 1
 #pragma unroll
     for (int k = 0; k < kMaxPer; ++k)
       if (el[k] < total) st_cluster(map_to_cta(sib + el[k], 0), val[k]);
-    for (uint32_t e = g + kMaxPer * nthreads; e < total; e += nthreads) {  // (only with fewer helpers than planned)
+    for (uint32_t e = g + kMaxPer * nthreads; e < total; e += nthreads) {  // (deep trees: more than 4 per thread)
       const uint32_t t = e >= per_tree;
       const uint32_t rem = e - t * per_tree;
       const uint32_t l = rem / (uint32_t)NP;
@@ -577,60 +607,39 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
       st_cluster(map_to_cta(sib + e, 0), v);
     }
-    cluster_arrive_release();  // my stores are performed before the leader's wait returns
+    cluster_arrive_release();  // phase 2: my stores (and my cleared rows) are performed before the leader goes on
+    if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 1] = (long long)globaltimer_ns();
+    cluster_wait_acquire();
+    cluster_arrive_relaxed();  // phase 3: nothing to publish; wait for the leader's climb
+    cluster_wait_acquire();
+    if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 2] = (long long)globaltimer_ns();
+    // ---- helpers, part 2: scatter my rows (local shared memory now)
+    const int units = (int)csize - 1, unit = (int)crank - 1;
+    for (int sl = 0; sl < slots; ++sl) {
+      const int r = unit + sl * units;
+      if (r >= 2 * bot + 2) break;
+      T *tree = (r < 2) ? (r ? mn : sum) : (((r - 2) >= bot) ? mn : sum);
+      const uint32_t node = pnode[sl * NP + tid];
+      if (tree && node) tree[node] = pval[sl * NP + tid];
+    }
+    if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 3] = (long long)globaltimer_ns();
     return;
   }
 
   // ---- leader
-  if (tid == 0) {
-    s_lmask = 0u;
-    if (has_writers) {
-      mbar_init(&s_done[0], 1);
-      mbar_init(&s_done[1], 1);
-      fence_mbar_init();
-    }
-  }
+  if (tid == 0) s_lmask = 0u;
   if (dbg && tid == 0) dbg[0] = (long long)clock64();
   // my own item
   bool valid = false;
   int64_t my_ix = -1;
   T raw = (T)0;
-  if (tid < n && tid < NP) {
+  if (tid < n) {
     // index_base maps GLOBAL indices of a sharded buffer onto this shard; entries that fall outside
     // [0, index_limit) are skipped, like the negative "do not write" markers of samplers.py:1040-1052
     my_ix = __ldg(index + tid) - index_base;
     valid = (my_ix >= 0 && my_ix < index_limit);
     raw = scalar ? __ldg(value) : __ldg(value + tid);
   }
-  __syncthreads();  // s_lmask / mbarrier initialisation visible to everybody
-  RLB_TICK(1);
-
-  if (tid >= NP) {
-    // ---- writer warps: the cluster protocol first (every thread arrives on both phases), then wait until the item
-    // info and the climb are final and scatter leaves + carried ancestors.  Only lane 0 polls.
-    cluster_wait_acquire();
-    cluster_arrive_release();
-    const int w = tid - NP;
-    if (lane == 0) mbar_wait_parity(&s_done[0], 0);
-    __syncwarp();
-    const int wL = Lw[w];
-    const uint32_t wleaf = (uint32_t)capacity + sleaf[w];
-    const uint32_t wpos = spos[w];
-    if (wL > 0) {
-      const T v = lv[w];
-      if (sum) sum[wleaf] = v;
-      if (mn) mn[wleaf] = v;
-    }
-    if (lane == 0) mbar_wait_parity(&s_done[1], 0);
-    __syncwarp();
-    for (int l = 0; l < bot && wL > l + 1; ++l) {  // item w carried node (wleaf >> (l + 1)) for every l + 1 < wL
-      const uint32_t parent = wleaf >> (l + 1);
-      if (sum) sum[parent] = sib[(size_t)l * NP + wpos];
-      if (mn) mn[parent] = sib[(size_t)bot * NP + (size_t)l * NP + wpos];
-    }
-    return;
-  }
-  auto compute_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(NP) : "memory"); };
   {
     // coalesced 16-byte async copies of the cut level of both trees (land while we sort)
     constexpr int kPer16 = 16 / (int)sizeof(T);
@@ -652,13 +661,15 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   // both fields fit in 32 bits (trees up to 2^21 slots with 1024-item batches) the whole sort runs on 32-bit keys.
   const int pos_bits = 31 - __clz(NP);  // log2(NP)
   const bool key32 = (depth + 1 + pos_bits) <= 32;
-  const uint32_t rpos = (uint32_t)(NP - 1 - tid);
   const uint32_t none32 = 0xffffffffu >> pos_bits;  // all-ones leaf field of a 32-bit key
   unsigned long long key;
-  if (key32) {
-    key = ((valid ? (uint32_t)my_ix : none32) << pos_bits) | rpos;
-  } else {
-    key = ((unsigned long long)(valid ? (uint32_t)my_ix : 0xffffffffu) << 32) | rpos;
+  {
+    const uint32_t rpos = (uint32_t)(NP - 1 - tid);
+    if (key32) {
+      key = ((valid ? (uint32_t)my_ix : none32) << pos_bits) | rpos;
+    } else {
+      key = ((unsigned long long)(valid ? (uint32_t)my_ix : 0xffffffffu) << 32) | rpos;
+    }
   }
   if constexpr (FUSED) {
     if (max_out) {
@@ -666,27 +677,35 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       for (int o = 16; o > 0; o >>= 1) p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
       if (lane == 0 && p > -INFINITY) red_max_float(max_out, p);
     }
+    raw = (T)pow_like_torch(add_rn((float)raw, eps), alpha);  // the leaf value, while the loads above are in flight
   }
   sraw[tid] = raw;
   RLB_TICK(2);
 
-  // ---- 2. sort.  Up to 256 keys of 32 bits: rank by counting (every thread compares its key with all the others,
-  // read as broadcast 128-bit shared loads; keys are unique, so the ranks are a permutation).  Otherwise bitonic, one
-  // key per thread: strides < 32 with warp shuffles, larger strides through double-buffered shared memory.
+  // ---- 2. sort.  Up to 256 keys of 32 bits: rank by counting -- key k's rank is the number of keys below it, read as
+  // broadcast 128-bit shared loads (keys are unique, so the ranks are a permutation).  Otherwise bitonic, one key per
+  // thread: strides < 32 with warp shuffles, larger strides through double-buffered shared memory.
   if (key32 && NP <= 256) {
-    uint32_t k32 = (uint32_t)key;
-    uint32_t *xb32 = reinterpret_cast<uint32_t *>(xbuf);
+    uint32_t *xb32 = reinterpret_cast<uint32_t *>(xbuf);  // [0,NP) keys | [NP,2NP) sorted
+    const uint32_t k32 = (uint32_t)key;
     xb32[tid] = k32;
-    compute_sync();
+    __syncthreads();
     const uint4 *kv = reinterpret_cast<const uint4 *>(xb32);
-    uint32_t rank = 0;
+    uint32_t r0 = 0, r1 = 0;
 #pragma unroll 8
     for (int j = 0; j < (NP >> 2); ++j) {
       const uint4 q = kv[j];
-      rank += (q.x < k32) + (q.y < k32) + (q.z < k32) + (q.w < k32);
+      // 0xffffffff where the other key is smaller: two set instructions feed one three-input subtract
+      uint32_t d0, d1, d2, d3;
+      asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(d0) : "r"(q.x), "r"(k32));
+      asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(d1) : "r"(q.y), "r"(k32));
+      asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(d2) : "r"(q.z), "r"(k32));
+      asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(d3) : "r"(q.w), "r"(k32));
+      r0 = r0 - d0 - d1;
+      r1 = r1 - d2 - d3;
     }
-    xb32[NP + rank] = k32;
-    compute_sync();
+    xb32[NP + r0 + r1] = k32;
+    __syncthreads();
     key = xb32[NP + tid];
   } else if (key32) {
     uint32_t k32 = (uint32_t)key;
@@ -698,7 +717,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         if (j >= 32) {
           uint32_t *buf = xb32 + flip * NP;
           buf[tid] = k32;
-          compute_sync();
+          __syncthreads();
           other = buf[tid ^ j];
           flip ^= 1;
         } else {
@@ -717,7 +736,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         if (j >= 32) {
           unsigned long long *buf = xbuf + flip * NP;
           buf[tid] = key;
-          compute_sync();
+          __syncthreads();
           other = buf[tid ^ j];
           flip ^= 1;
         } else {
@@ -739,11 +758,11 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   sleaf[tid] = myleaf;
   spos[tid] = pos;
   cp_async_wait_all();
-  // the sibling tile: every helper has stored its share into this CTA's shared memory once this returns
+  // the sibling tile: every helper has stored its share into this CTA's shared memory once phase 2 completes
+  cluster_wait_acquire();     // phase 1
+  cluster_arrive_relaxed();   // phase 2
   cluster_wait_acquire();
-  cluster_arrive_release();
-  if (csize > 1) cluster_wait_acquire();
-  compute_sync();
+  __syncthreads();
   if (csize == 1 && bot > 0) {
     // (launched without helpers: fetch the siblings here -- correct, just slow)
     const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
@@ -760,24 +779,38 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
       sib[e] = v;
     }
-    compute_sync();
+    __syncthreads();
   }
   RLB_TICK(4);
+
+  // where a finished node goes: row r -> (helper, slot); without helpers the leader stores it itself
+  const int units = (int)csize - 1;
+  auto publish = [&](int r, uint32_t node, T v) {
+    if (units > 0) {
+      const int sl = r / units;
+      const uint32_t h = 1u + (uint32_t)(r - sl * units);
+      st_cluster(map_to_cta(pval + sl * NP + tid, h), v);
+      st_cluster_u32(map_to_cta(pnode + sl * NP + tid, h), node);
+    } else {
+      T *tree = (r < 2) ? (r ? mn : sum) : (((r - 2) >= bot) ? mn : sum);
+      if (tree) tree[node] = v;
+    }
+  };
 
   // ---- 4. per head j: merge level L_j, and WHERE its hand-over goes (only merges below the cut hand over)
   const uint32_t left = tid > 0 ? sleaf[tid - 1] : 0u;
   bool alive = key_valid && (tid == 0 || left != myleaf);
+  const uint32_t leafnode = (uint32_t)capacity + myleaf;
   int L = 0;
-  T vs = (T)0, vm = (T)0, leaf_v = (T)0;
+  T vs = (T)0, vm = (T)0;
   T *hand_s = nullptr, *hand_m = nullptr;
   if (alive) {
-    T v = sraw[pos];
-    if constexpr (FUSED) v = (T)pow_like_torch(add_rn((float)v, eps), alpha);
+    const T v = sraw[pos];
     vs = v;
     vm = v;
-    leaf_v = v;
     L = (tid == 0) ? depth + 1 : 32 - __clz(myleaf ^ left);
-    lv[tid] = v;
+    if (sum) publish(0, leafnode, v);
+    if (mn) publish(1, leafnode, v);
     if (L <= bot) {
       const uint32_t prefix = myleaf >> L;
       int lo = 0, hi = tid;  // first index in [0, tid) whose leaf has this prefix: the leader of the group on my left
@@ -794,53 +827,88 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
     }
   }
-  Lw[tid] = L;
   {
     const unsigned m = __reduce_or_sync(0xffffffffu, (alive && L <= bot) ? (1u << L) : 0u);
     if (lane == 0 && m) atomicOr(&s_lmask, m);
   }
-  compute_sync();
+  __syncthreads();
   const unsigned lmask = s_lmask;
-  if (has_writers && tid == 0) mbar_arrive(&s_done[0]);  // item info (sleaf/spos/Lw/lv) is final
   RLB_TICK(5);
 
-  // ---- 5. climb below the cut.  Nothing but registers and shared memory inside the loop: the parent computed at
-  // level l overwrites the (consumed) sibling slot [l][pos] and is flushed to the global trees by the writer warps.
-  T *io_s = sib + pos;
-  T *io_m = sib + (size_t)bot * NP + pos;
-  int levels_done = 0;
-  for (int l = 0; l < bot; ++l) {
+  // ---- 5. climb below the cut.  The sibling values of the first kUpdHoist levels are pulled into registers up
+  // front (independent shared loads); a level into which somebody handed a value over is re-read after the barrier
+  // that follows the hand-over.  Every parent computed goes straight into its row in a helper's shared memory.
+  const T *io_s = sib + pos;
+  const T *io_m = sib + (size_t)bot * NP + pos;
+  T hs[kUpdHoist], hm[kUpdHoist];
+#pragma unroll
+  for (int l = 0; l < kUpdHoist; ++l) {
+    hs[l] = (T)0;
+    hm[l] = (T)0;
+    if (l < bot) {
+      hs[l] = io_s[(size_t)l * NP];
+      hm[l] = io_m[(size_t)l * NP];
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < kUpdHoist; ++l) {
+    if (l < bot) {
+      if (alive) {
+        if (L == l + 1) {
+          alive = false;  // my level-l value was handed over; the leader of the group on my left carries the parent
+        } else {
+          T os = hs[l], om = hm[l];
+          if ((lmask >> (l + 1)) & 1u) {  // somebody may have handed its value into row l (possibly my slot)
+            os = io_s[(size_t)l * NP];
+            om = io_m[(size_t)l * NP];
+          }
+          vs = tree_op<T, false>(vs, os);          // IEEE addition commutes: operand order is immaterial
+          vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+          if (L == l + 2 && L <= bot) {  // I merge at the next level: hand the value just computed to the leader
+            *hand_s = vs;
+            *hand_m = vm;
+          }
+          const uint32_t parent = leafnode >> (l + 1);
+          if (sum) publish(2 + l, parent, vs);
+          if (mn) publish(2 + bot + l, parent, vm);
+        }
+      }
+      if ((lmask >> (l + 2)) & 1u) __syncthreads();  // somebody handed over: its leader reads it in the next iteration
+    }
+  }
+  for (int l = kUpdHoist; l < bot; ++l) {  // (trees deeper than 2^(kDenseLevels + kUpdHoist))
     if (alive) {
       if (L == l + 1) {
-        alive = false;  // my level-l value was handed over; the leader of the group on my left carries the parent
+        alive = false;
       } else {
-        const uint32_t off = (uint32_t)l * (uint32_t)NP;
-        const T os = io_s[off], om = io_m[off];  // sibling: old global value, or the value handed over to me
-        vs = tree_op<T, false>(vs, os);          // IEEE addition commutes: operand order is immaterial
+        const T os = io_s[(size_t)l * NP], om = io_m[(size_t)l * NP];
+        vs = tree_op<T, false>(vs, os);
         vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
-        io_s[off] = vs;  // value of node (leaf >> (l + 1))
-        io_m[off] = vm;
-        levels_done = l + 1;
-        if (L == l + 2 && L <= bot) {  // I merge at the next level: hand the value just computed to the leader
+        if (L == l + 2 && L <= bot) {
           *hand_s = vs;
           *hand_m = vm;
         }
+        const uint32_t parent = leafnode >> (l + 1);
+        if (sum) publish(2 + l, parent, vs);
+        if (mn) publish(2 + bot + l, parent, vm);
       }
     }
-    if ((lmask >> (l + 2)) & 1u) compute_sync();  // somebody handed over: the leader reads it in the next iteration
+    if ((lmask >> (l + 2)) & 1u) __syncthreads();
   }
   RLB_TICK(6);
 
   // ---- 6. dense top: items that reached the cut overwrite their node, then the W - 1 nodes above are recomputed,
-  // node = op(node 2k, node 2k+1).  Three barriers in all: each thread reduces the subtree over its own `per`
-  // consecutive cut nodes alone, warps continue with shuffles, warp 0 finishes.
+  // node = op(node 2k, node 2k+1).  Each thread reduces the subtree over its own `per` consecutive cut nodes alone,
+  // warps continue with shuffles, warp 0 finishes.
   if (alive) {
-    const uint32_t node = ((uint32_t)capacity + myleaf) >> bot;  // in [W, 2W)
+    const uint32_t node = leafnode >> bot;  // in [W, 2W)
     cut_s[node] = vs;
     cut_m[node] = vm;
   }
-  compute_sync();
-  if (has_writers && tid == 0) mbar_arrive(&s_done[1]);  // staging tile final: the writer warps may scatter it
+  if (dbg && tid == 0) dbg[12] = (long long)clock64();
+  cluster_arrive_release();  // phase 3: every row is complete -- the helpers scatter them while the top is recomputed
+  if (dbg && tid == 0) dbg[13] = (long long)clock64();
+  __syncthreads();
   {
     const int per = W >= NP ? W / NP : 1;      // cut nodes per thread
     const int A = W >= NP ? NP : W;            // threads that own a subtree; its root is node A + tid
@@ -875,7 +943,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
     }
     if (A > 32) {  // A / 32 subtree roots left (nodes A/32 + warp), one per warp: warp 0 finishes
-      compute_sync();
+      __syncthreads();
       const int A2 = A >> 5;
       if (tid < 32) {
         const bool act2 = tid < A2;
@@ -900,23 +968,16 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
     }
   }
-  compute_sync();
+  __syncthreads();
+  if (dbg && tid == 0) dbg[14] = (long long)clock64();
   for (int k = 1 + tid; k < W; k += NP) {
     if (sum) sum[k] = cut_s[k];
     if (mn) mn[k] = cut_m[k];
   }
-  // ---- 7. without writer warps: leaf + every ancestor below the cut this item carried
-  if (!has_writers && L > 0) {
-    const uint32_t leafnode = (uint32_t)capacity + myleaf;
-    if (sum) sum[leafnode] = leaf_v;
-    if (mn) mn[leafnode] = leaf_v;
-    for (int l = 0; l < levels_done; ++l) {
-      const uint32_t parent = leafnode >> (l + 1);
-      if (sum) sum[parent] = io_s[(size_t)l * NP];
-      if (mn) mn[parent] = io_m[(size_t)l * NP];
-    }
-  }
   RLB_TICK(7);
+  if (dbg && tid == 0) dbg[32 + 1] = (long long)globaltimer_ns();
+  cluster_wait_acquire();  // phase 3 (completes at once: every helper arrived long ago)
+  if (dbg && tid == 0) dbg[32 + 2] = (long long)globaltimer_ns();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1081,15 +1142,14 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
     if (rc) return rc;
     attr_set = true;
   }
-  // one cluster: the leader + the sibling fetchers (none needed when the whole tree is above the cut)
+  // one cluster: the leader + the helpers (none needed when the whole tree is above the cut)
   const int bot = upd_bot_levels(depth);
-  const int threads = (np <= 512 && depth <= 32) ? 2 * np : np;  // room for the writer warps?
   const unsigned cluster = bot > 0 ? kUpdCluster : 1;
   (void)workspace;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(cluster);
-  cfg.blockDim = dim3(threads);
+  cfg.blockDim = dim3(np);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1101,7 +1161,7 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   cfg.numAttrs = 1;
   int rc = check_cuda(cudaLaunchKernelEx(&cfg, tree_update_cta_kernel<T, FUSED>, sum, mn, capacity, depth, index, value,
                                          (int)n, scalar, fp.alpha, fp.eps, fp.max_out, g_debug_ticks, fp.index_base,
-                                         fp.index_limit < 0 ? capacity : fp.index_limit, np),
+                                         fp.index_limit < 0 ? capacity : fp.index_limit),
                       "tree_update_cta_kernel");
   if (rc) return rc;
   return check_launch("tree_update_cta_kernel");

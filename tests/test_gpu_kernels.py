@@ -360,8 +360,10 @@ def test_per_sample_matches_oracle(cuda_backend, size, filled, B, cpu_sem):
     assert pp[0].item() == p_sum and pp[1].item() == p_min
     np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
     np.testing.assert_allclose(w.cpu().numpy(), want_w, rtol=2e-6)
-    # the weight is torch's own CUDA pow on the same operands, bit for bit
-    tw = torch.pow(leaf / pp[1], -0.4)
+    # the weight is torch's own CUDA pow on the same operands, bit for bit.  CPU semantics: a true division (what the
+    # reference's CPU branch computes); CUDA semantics: p_min is a Python float there, and ATen's CUDA division by a
+    # CPU scalar multiplies by its reciprocal
+    tw = torch.pow(leaf / pp[1], -0.4) if cpu_sem else torch.pow(leaf / pp[1].item(), -0.4)
     assert torch.equal(tw, w)
 
 
@@ -954,6 +956,9 @@ def test_sampler_matches_reference_cuda_path_without_leaf_injection(cuda_backend
         mass = torch.rand(B, device=d, generator=gen) * p_sum
         index = rs.scan_lower_bound(mass)
         index.clamp_max_(n_filled - 1)
+        # NB: p_sum / p_min come back as PYTHON FLOATS here -- pybind accepts a 0-d integer tensor for the (int64, int64)
+        # overload of query through __index__ -- so this division is ATen's CUDA "multiply by the reciprocal of a CPU
+        # scalar"; semantics="cuda" reproduces exactly that
         weight = torch.pow(rs[index] / p_min, -beta)
         return index, weight, p_sum, p_min
 
@@ -975,7 +980,16 @@ def test_sampler_matches_reference_cuda_path_without_leaf_injection(cuda_backend
         ri, rw, p_sum, p_min = ref_sample(g_ref)
         oi, info = ours.sample(st, B)
         assert torch.equal(ri, oi), rnd
-        assert torch.equal(rw, info["priority_weight"]), rnd
+        ow = info["priority_weight"]
+        if not torch.equal(rw, ow):
+            bad = (rw != ow).nonzero().flatten()[:5]
+            op = ours._min_tree.query(torch.zeros(1, dtype=torch.long, device=d),
+                                      torch.full((1,), n_filled, dtype=torch.long, device=d), root_fast_path=False)
+            raise AssertionError(f"round {rnd}: {int((rw != ow).sum())} of {B} weights differ; ref p_min={float(p_min).hex()} "
+                                 f"ours p_min={op.item().hex()}; first: " + "; ".join(
+                                     f"i={int(i)} leaf={rs[ri[i:i + 1]].item().hex()} ref={rw[i].item().hex()} "
+                                     f"ours={ow[i].item().hex()} torch.pow(leaf/p_min)={torch.pow(rs[ri[i:i + 1]] / op, -beta).item().hex()}"
+                                     for i in bad))
         # write-back with duplicates (last writer wins on both sides) and fresh priorities
         wi = torch.cat([oi, oi[:32], oi[5:9]])
         wp = torch.rand(wi.numel(), device=d, generator=g) * 2
