@@ -272,7 +272,7 @@ int rlb_extend(const void *const *src /*[host] of [dev]*/, void *const *dst /*[h
                int has_max, float *max_priority /*[dev]*/, uint32_t *ticket /*[dev]*/, rlb_stream_t stream);
 
 /* ---- trajectory slices -------------------------------------------------------------------
- * SliceSampler for 1-d storages (samplers.py:1207-2300).
+ * SliceSampler (samplers.py:1207-2300); N-d storages run one table per ring (column) on the host side.
  *
  * rlb_traj_table: the (start, stop, length) table of the trajectories stored in a ring of L slots
  * (_find_start_stop_traj :1652-1706, _end_to_start_stop :1708-1743).  signal: RLB_TRAJ_END = L end-of-trajectory bytes,
@@ -282,12 +282,15 @@ int rlb_extend(const void *const *src /*[host] of [dev]*/, void *const *dst /*[h
  * counts[1] = how many are at least min_len long; filter != 0 keeps only those in the table (strict_length, :1993-2010).
  * start / stop / length need room for L entries.  workspace: rlb_traj_table_workspace_bytes(L) bytes, zeroed once.
  *
- * rlb_slice_index: _get_index :2058-2215 with span = False.  Slice s takes trajectory traj_draw[s] (the output of
+ * rlb_slice_index: _get_index :2058-2215.  Slice s takes trajectory traj_draw[s] (the output of
  * torch.randint(n_traj, ...)) and starts floor(u[s] * (len - seq + 1)) steps into it (fp32 product, as torch.rand() *
  * int64 tensor); index = (start + step) % storage_length; truncated marks the last real step of every slice.
  * variable != 0: slices of trajectories shorter than seq_length are shortened (strict_length = False, :2033-2037); then
  * pad_output pads them to seq_length by repeating the last real index and writes mask, otherwise slice s is written at
  * out_offset[s] (exclusive cumsum of seq_out, obtained by a first call with index_out == NULL).
+ * span_left / span_right (SliceSampler(span=...), :2071-2118): 0 = off, -1 = True, k > 0: the slice may start up to k steps
+ * (True: seq_length - 1) before its trajectory / run up to k steps past its end; the part outside is cut off, so lengths
+ * vary (requires variable != 0).
  * done_src / term_src: the storage's one-byte-per-slot done / terminated flags; done_out = done_src[index] | truncated and
  * term_out = term_src[index] (zero / truncated alone when a source is NULL) -- the info of samplers.py:2190-2205. */
 #define RLB_TRAJ_END 0
@@ -298,7 +301,8 @@ int rlb_traj_table(const void *signal /*[dev]*/, int kind, int64_t L, int at_cap
                    int64_t *counts /*[dev] 2*/, void *workspace /*[dev]*/, size_t workspace_bytes, rlb_stream_t stream);
 int rlb_slice_index(const int64_t *start /*[dev]*/, const int64_t *length /*[dev]*/, int64_t n_traj,
                     const int64_t *traj_draw /*[dev]*/, const float *u /*[dev]*/, int64_t num_slices, int64_t seq_length,
-                    int64_t storage_length, int variable, int pad_output, const int64_t *out_offset /*[dev] or NULL*/,
+                    int64_t storage_length, int variable, int pad_output, int64_t span_left, int64_t span_right,
+                    const int64_t *out_offset /*[dev] or NULL*/,
                     int64_t *index_out /*[dev] or NULL*/, uint8_t *truncated_out /*[dev] or NULL*/,
                     uint8_t *mask_out /*[dev] or NULL*/, int64_t *seq_out /*[dev] or NULL*/,
                     const uint8_t *done_src /*[dev] or NULL*/, const uint8_t *term_src /*[dev] or NULL*/,

@@ -168,9 +168,16 @@ def reference_samplers(root: str = "/root/reference"):
         pass
 
     class TensorStorage(Storage):
-        def __init__(self, data: dict, length: int, max_size: int, last_cursor=None):
+        """``columns`` > 0: an ndim=2 storage whose leaves are [max_size, columns, ...] (time along dim 0); ``length`` and
+        ``max_size`` then count ROWS, as ``_len_along_dim0`` does in the reference (storages.py:828-863)."""
+
+        def __init__(self, data: dict, length: int, max_size: int, last_cursor=None, columns: int = 0):
             self._storage = StubTD(data)
-            self._len, self.max_size, self._last_cursor = int(length), int(max_size), last_cursor
+            self._rows, self._max_rows, self._last_cursor = int(length), int(max_size), last_cursor
+            self._columns = int(columns)
+            self.ndim = 2 if columns else 1
+            self.max_size = self._max_rows * max(1, self._columns)
+            self._len = self._rows * max(1, self._columns)
             self.device = next(iter(data.values())).device
 
         def __len__(self):
@@ -182,19 +189,19 @@ def reference_samplers(root: str = "/root/reference"):
 
         @property
         def _total_shape(self):
-            return torch.Size([self.max_size])
+            return torch.Size([self._max_rows] + ([self._columns] if self._columns else []))
 
         @property
         def _len_along_dim0(self):
-            return self._len
+            return self._rows
 
         @property
         def shape(self):          # truncated to the fill level, as TensorStorage.shape (storages.py:856-863)
-            return torch.Size([self.max_size if self._is_full else self._len])
+            return torch.Size([self._max_rows if self._is_full else self._rows] + ([self._columns] if self._columns else []))
 
         def __getitem__(self, index):
             if isinstance(index, slice) and index == slice(None):
-                return StubTD({k: v[: self._len] for k, v in self._storage._d.items()})
+                return StubTD({k: v[: self._rows] for k, v in self._storage._d.items()})
             if isinstance(index, tuple) and len(index) == 1:
                 index = index[0]
             return self._storage[index]

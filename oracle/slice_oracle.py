@@ -1,8 +1,8 @@
-"""TEST INFRASTRUCTURE -- CPU restatement of the reference's SliceSampler arithmetic for 1-d storages.
+"""TEST INFRASTRUCTURE -- CPU restatement of the reference's SliceSampler arithmetic (1-d storages; N-d ring by ring).
 
 Follows torchrl/data/replay_buffers/samplers.py (SliceSampler):
     traj_table    _find_start_stop_traj :1652-1706  +  _end_to_start_stop :1708-1743
-    slice_index   _sample_slices :1973-2056  +  _get_index :2058-2215  (span = False)
+    slice_index   _sample_slices :1973-2056  +  _get_index :2058-2215  (incl. span)
 with the random draws passed in explicitly (``traj_draw`` = the output of ``torch.randint(maxval, (num_slices,))``,
 ``u`` = the output of ``torch.rand(num_slices)``; the reference makes exactly these two calls in this order, :1987-1990 and
 :2099-2102), so that a CUDA run can be checked against it with the draws its own generator produced.
@@ -50,10 +50,11 @@ def valid_trajectories(start, stop, length, seq_length: int, strict_length: bool
 
 
 def slice_index(start, length, *, seq_length: int, num_slices: int, storage_length: int, traj_draw, u,
-                strict_length: bool = True, pad_output: bool = False):
+                strict_length: bool = True, pad_output: bool = False, span=(0, 0), force_variable: bool = False):
     """index int64[n_out], truncated bool[n_out], mask bool[n_out] | None, per-slice lengths int64[num_slices].
 
-    ``start`` / ``length`` are the (already filtered) trajectories; ``traj_draw`` in [0, len(start))."""
+    ``start`` / ``length`` are the (already filtered) trajectories; ``traj_draw`` in [0, len(start)).
+    ``span`` = (left, right) as the kernel takes it: 0 off, -1 True, k > 0 (:2071-2118)."""
     traj = np.asarray(traj_draw, dtype=np.int64)
     u = np.asarray(u, dtype=np.float32)
     lens = np.asarray(length, dtype=np.int64)[traj]
@@ -62,10 +63,24 @@ def slice_index(start, length, *, seq_length: int, num_slices: int, storage_leng
         variable = True
     else:
         seq = np.full(num_slices, seq_length, dtype=np.int64)
-        variable = False
-    end_point = lens - seq + 1                                       # :2072-2074, span[1] False
+        variable = bool(force_variable)
+    span0, span1 = (int(x) for x in span)
+    last_indexable_start = lens - seq + 1                            # :2072
+    end_point = last_indexable_start if span1 == 0 else (lens + 1 if span1 < 0 else lens - span1)      # :2073-2083
+    start_point = np.zeros_like(seq) if span0 == 0 else (1 - seq if span0 < 0 else np.full_like(seq, -span0))  # :2085-2097
     # torch.rand(fp32) * int64 tensor -> fp32 product, floor, cast (:2099-2102)
-    rel = np.floor(u * end_point.astype(np.float32)).astype(np.int64)
+    rel = np.floor(u * (end_point - start_point).astype(np.float32)).astype(np.int64) + start_point
+    if span0:                                                        # :2104-2111
+        out = rel < 0
+        if out.any():
+            seq = np.where(out, seq + rel, seq)
+            rel = np.where(out, 0, rel)
+            variable = True
+    if span1:                                                        # :2112-2118
+        out = rel + seq > lens
+        if out.any():
+            seq = np.minimum(seq, lens - rel)
+            variable = True
     starts = np.asarray(start, dtype=np.int64)[traj] + rel           # :2120-2126
     if variable and pad_output:
         T = seq_length
@@ -88,6 +103,24 @@ def slice_index(start, length, *, seq_length: int, num_slices: int, storage_leng
     truncated = np.zeros(num_slices * seq_length, dtype=bool)
     truncated.reshape(num_slices, seq_length)[:, -1] = True          # :2185
     return index, truncated, None, seq
+
+
+def traj_table_nd(*, end=None, trajectory=None, at_capacity: bool, cursor=None):
+    """N-d storages ([T, E, ...] signals, time along dim 0): the reference transposes and takes nonzero (:1717-1718), i.e.
+    trajectories are listed ring by ring (column by column), each ring exactly as a 1-d storage.  Returns
+    (start_t, stop_t, length, column) with the column index of every trajectory."""
+    sig = np.asarray(end if end is not None else trajectory)
+    T = sig.shape[0]
+    cols = sig.reshape(T, -1)
+    out = [[], [], [], []]
+    for e in range(cols.shape[1]):
+        if end is not None:
+            st, sp, ln = traj_table(end=cols[:, e], at_capacity=at_capacity, cursor=cursor)
+        else:
+            st, sp, ln = traj_table(trajectory=cols[:, e], at_capacity=at_capacity, cursor=cursor)
+        for o, a in zip(out, (st, sp, ln, np.full(len(st), e, dtype=np.int64))):
+            o.append(a)
+    return tuple(np.concatenate(o) for o in out)
 
 
 def invalid_starts(stop, length, seq_length: int, ring_length: int):

@@ -299,6 +299,7 @@ struct SliceParams {
   const int64_t *start, *length, *traj_draw, *out_offset;
   const float *u;
   int64_t n_traj, num_slices, seq_length, storage_length;
+  int64_t span0, span1;  // SliceSampler(span=(left, right)): 0 = off, -1 = True, k > 0 = at most k steps outside
   int variable, pad_output;
   int64_t *index_out, *seq_out;
   uint8_t *truncated_out, *mask_out;
@@ -319,10 +320,18 @@ __global__ void __launch_bounds__(128) slice_index_kernel(const SliceParams P) {
   const int64_t len = __ldg(P.length + t);
   int64_t seq = P.seq_length;
   if (P.variable && len < seq) seq = len;                          // lengths[traj_idx].clamp_max(seq_length), :2037
-  const int64_t end_point = len - seq + 1;                         // :2072-2074
+  // :2071-2097: the range the relative start is drawn from; a span lets the slice hang out of the trajectory on the
+  // left (start_point < 0) and / or on the right (end_point beyond the last indexable start)
+  const int64_t end_point = P.span1 == 0 ? len - seq + 1 : (P.span1 < 0 ? len + 1 : len - P.span1);
+  const int64_t start_point = P.span0 == 0 ? 0 : (P.span0 < 0 ? 1 - seq : -P.span0);
   // torch.rand(fp32) * int64 tensor: the integer is converted to fp32 and the product rounded once (:2099-2102)
-  const float prod = mul_rn(__ldg(P.u + s), (float)end_point);
-  const int64_t rel = (int64_t)floorf(prod);
+  const float prod = mul_rn(__ldg(P.u + s), (float)(end_point - start_point));
+  int64_t rel = (int64_t)floorf(prod) + start_point;
+  if (P.span0 && rel < 0) {                                        // :2104-2111: fewer elements, from the first step
+    seq += rel;
+    rel = 0;
+  }
+  if (P.span1 && rel + seq > len) seq = len - rel;                 // :2112-2118
   const int64_t first = __ldg(P.start + t) + rel;
   if (P.seq_out && lane == 0) P.seq_out[s] = seq;
   if (!P.index_out) return;
@@ -426,7 +435,7 @@ int rlb_traj_table(const void *signal, int kind, int64_t L, int at_capacity, int
 
 int rlb_slice_index(const int64_t *start, const int64_t *length, int64_t n_traj, const int64_t *traj_draw,
                     const float *u, int64_t num_slices, int64_t seq_length, int64_t storage_length, int variable,
-                    int pad_output, const int64_t *out_offset, int64_t *index_out, uint8_t *truncated_out,
+                    int pad_output, int64_t span_left, int64_t span_right, const int64_t *out_offset, int64_t *index_out, uint8_t *truncated_out,
                     uint8_t *mask_out, int64_t *seq_out, const uint8_t *done_src, const uint8_t *term_src,
                     uint8_t *done_out, uint8_t *term_out, rlb_stream_t stream) {
   RLB_REQUIRE(num_slices >= 0 && seq_length > 0 && storage_length > 0 && n_traj > 0, RLB_EINVAL,
@@ -447,6 +456,12 @@ int rlb_slice_index(const int64_t *start, const int64_t *length, int64_t n_traj,
   P.num_slices = num_slices;
   P.seq_length = seq_length;
   P.storage_length = storage_length;
+  RLB_REQUIRE(span_left < seq_length && span_right < seq_length, RLB_EINVAL,
+              "rlb_slice_index: The right and left span must be strictly lower than the sequence length");
+  RLB_REQUIRE(!(span_left || span_right) || variable, RLB_EINVAL,
+              "rlb_slice_index: a span makes slice lengths variable: pass variable=1");
+  P.span0 = span_left;
+  P.span1 = span_right;
   P.variable = variable ? 1 : 0;
   P.pad_output = pad_output ? 1 : 0;
   P.index_out = index_out;

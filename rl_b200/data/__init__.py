@@ -1,4 +1,5 @@
 """rl_b200.data -- mirror of ``torchrl.data``'s replay-buffer surface for the B200 hot path."""
+from .checkpointers import StorageCheckpointerBase, TensorStorageCheckpointer
 from .replay_buffers import (PrioritizedReplayBuffer, ReplayBuffer, TensorDictPrioritizedReplayBuffer,
                              TensorDictReplayBuffer)
 from .samplers import (PrioritizedSampler, PrioritizedSliceSampler, RandomSampler, Sampler, SamplerWithoutReplacement,
@@ -12,5 +13,5 @@ __all__ = [
     "ReplayBuffer", "PrioritizedReplayBuffer", "TensorDictReplayBuffer", "TensorDictPrioritizedReplayBuffer",
     "Sampler", "RandomSampler", "SamplerWithoutReplacement", "SliceSampler", "SliceSamplerWithoutReplacement", "PrioritizedSliceSampler", "PrioritizedSampler", "Storage", "ListStorage", "TensorStorage",
     "LazyTensorStorage", "Writer", "RoundRobinWriter", "TensorDictRoundRobinWriter", "TensorDict",
-    "is_tensor_collection", "SumSegmentTreeFp32", "SumSegmentTreeFp64", "MinSegmentTreeFp32", "MinSegmentTreeFp64",
+    "is_tensor_collection", "StorageCheckpointerBase", "TensorStorageCheckpointer", "SumSegmentTreeFp32", "SumSegmentTreeFp64", "MinSegmentTreeFp32", "MinSegmentTreeFp64",
 ]

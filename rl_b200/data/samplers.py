@@ -246,10 +246,16 @@ class SliceSampler(Sampler):
             the batch may be shorter than asked. Defaults to ``True`` (they are never sampled).
         pad_output (bool, optional): with ``strict_length=False``, pad short slices to the slice length by repeating
             their last step and return ``("collector", "mask")``.
-        span, compile, use_gpu: accepted for signature compatibility; ``span`` must be falsy, the other two have no
-            effect (everything already runs on the storage's device).
+        span (bool, int, Tuple[bool | int, bool | int], optional): let a slice hang out of its trajectory on the left
+            and / or on the right (``True``: by up to ``slice_len - 1`` steps, an int: by up to that many); the part
+            outside is cut off, so such slices are shorter (:2071-2118).  Makes slice lengths variable, like
+            ``strict_length=False``.
+        compile, use_gpu: accepted for signature compatibility; no effect (everything already runs on the storage's
+            device).
 
-    One-dimensional storages only.  Both halves of the reference's index arithmetic are kernels: ``rlb_traj_table``
+    Storages with ``ndim`` 1 or 2 (``[T, E]``: one ring per column, the table is built ring by ring -- the order of the
+    reference's transposed ``nonzero`` -- and the sample is a ``(time, column)`` index pair).  Both halves of the
+    reference's index arithmetic are kernels: ``rlb_traj_table``
     (trajectory boundaries of the ring; the reference's nonzero / roll / boolean-index sequence, :1652-1743, :1993-2010)
     and ``rlb_slice_index`` (slice expansion, :2058-2215).  The two random draws are the reference's own calls
     (``torch.randint(n_trajectories, (num_slices,))`` then ``torch.rand(num_slices)``), so a seeded generator yields the
@@ -273,9 +279,9 @@ class SliceSampler(Sampler):
         self.pad_output = pad_output
         if isinstance(span, (bool, int)):
             span = (span, span)
-        if any(span):
-            raise NotImplementedError("SliceSampler(span=...) is not supported by the B200 slice kernels")
-        self.span = span
+        self.span = tuple(span)
+        # the kernel's encoding: 0 = off, -1 = True, k > 0 = at most k steps outside the trajectory
+        self._span_code = tuple(0 if not v else (-1 if v is True else int(v)) for v in self.span)
         self._cache: dict = {}
         self._given = None          # (signal tensor, by_id) passed to the constructor
         self._fetch_traj, self._traj_key_auto = True, False
@@ -288,8 +294,8 @@ class SliceSampler(Sampler):
             if not cache_values:
                 raise RuntimeError(f"To be used, {what} requires `cache_values` to be set to `True`.")
             sig = trajectories if trajectories is not None else ends
-            if sig.ndim != 1:
-                raise NotImplementedError("SliceSampler supports 1-d storages only")
+            if sig.ndim > 2:
+                raise NotImplementedError("SliceSampler supports storages with ndim 1 or 2")
             self._given = (sig, trajectories is not None)
         else:
             if traj_key is not None:
@@ -303,6 +309,8 @@ class SliceSampler(Sampler):
             raise TypeError("Either num_slices or slice_len must be not None, and not both. "
                             f"Got num_slices={num_slices} and slice_len={slice_len}.")
         self._traj_buf = self._traj_counts = self._traj_ws = None
+        self._traj_ws_len = 0
+        self._column = None          # N-d storages: the ring (column) of every table entry
 
     def __repr__(self) -> str:
         return (f"{self.__class__.__name__}(num_slices={self.num_slices}, slice_len={self.slice_len}, "
@@ -368,10 +376,13 @@ class SliceSampler(Sampler):
                 if attempt or (not self._fetch_traj and self.traj_key is None):
                     raise KeyError(f"SliceSampler could not find {key!r} in the storage")
                 self._fetch_traj = not self._fetch_traj      # fall back to the other signal (:1893-1927)
-        sig = sig.squeeze() if sig.ndim > 1 else sig
-        if sig.ndim != 1:
+        nd = getattr(storage, "ndim", 1)
+        while sig.ndim > nd and sig.shape[-1] == 1:
+            sig = sig.squeeze(-1)
+        if sig.ndim != nd or nd > 2:
             raise NotImplementedError(
-                f"SliceSampler on the B200 engine supports 1-d storages; got a signal of shape {tuple(sig.shape)}")
+                f"SliceSampler on the B200 engine supports storages with ndim 1 or 2; got a signal of shape "
+                f"{tuple(sig.shape)} for ndim={nd}")
         cursor = getattr(storage, "_last_cursor", None)
         if isinstance(cursor, slice):
             cursor = cursor.stop - 1
@@ -379,10 +390,37 @@ class SliceSampler(Sampler):
             cursor = cursor[-1]
         elif isinstance(cursor, torch.Tensor):
             cursor = int(cursor.reshape(-1)[-1])
-        return sig[:len(storage)], self._fetch_traj, bool(storage._is_full), -1 if cursor is None else int(cursor)
+        if isinstance(cursor, tuple):       # N-d writes address (row, ...) tuples: the row is what closes a trajectory
+            cursor = cursor[0]
+            cursor = int(cursor.reshape(-1)[-1]) if isinstance(cursor, torch.Tensor) else cursor
+        n0 = storage.shape[0] if nd > 1 else len(storage)
+        return sig[:n0], self._fetch_traj, bool(storage._is_full), -1 if cursor is None else int(cursor)
+
+    def _table_nd(self, sig, by_id, at_capacity, cursor, seq_length: int):
+        """[T, E] signal: one ring per column.  Every column goes through ``rlb_traj_table`` on its own (a transposing
+        copy makes it contiguous); all counters come back in ONE read, then the per-column tables are concatenated in
+        column order -- the order of the reference's ``end.transpose(0, -1).nonzero()`` (:1717-1718).  Returns
+        (table [3, n], column int64[n], n_trajectories, n_long_enough)."""
+        T, E = sig.shape
+        dev = sig.device
+        be = ops.backend()
+        cols = sig.t().contiguous()
+        tables = torch.empty((E, 3, T), dtype=torch.int64, device=dev)
+        counts = torch.zeros((E, 2), dtype=torch.int64, device=dev)
+        if self._traj_ws is None or self._traj_ws_len < T or self._traj_ws.device != dev:
+            self._traj_ws, self._traj_ws_len = be.traj_workspace(T, dev), T
+        for e in range(E):
+            be.traj_table(cols[e], by_id, T, at_capacity, cursor, seq_length, self.strict_length, tables[e], counts[e],
+                          self._traj_ws)
+        cnt = counts.tolist()                                                # the one synchronisation of a table build
+        keep = [c[1] if self.strict_length else c[0] for c in cnt]
+        table = torch.cat([tables[e, :, :k] for e, k in enumerate(keep)], dim=1)
+        column = torch.repeat_interleave(torch.arange(E, device=dev), torch.tensor(keep, device=dev))
+        return table, column, sum(c[0] for c in cnt), sum(c[1] for c in cnt)
 
     def _table(self, storage, seq_length: int):
-        """(table int64 [3, L] = start / stop / length rows, n_trajectories, n_long_enough)."""
+        """(table int64 [3, L] = start / stop / length rows, n_trajectories, n_long_enough); N-d storages also cache the
+        column of every trajectory (``self._cache[("column", seq_length)]``)."""
         key = ("table", seq_length)
         if self.cache_values and key in self._cache:
             return self._cache[key]
@@ -390,13 +428,20 @@ class SliceSampler(Sampler):
         L = sig.shape[0]
         if L == 0:
             raise RuntimeError(_EMPTY_STORAGE_ERROR)
+        if sig.ndim == 2:
+            table, column, n_all, n_long = self._table_nd(sig, by_id, at_capacity, cursor, seq_length)
+            self._column = column
+            out = (table, n_all, n_long)
+            if self.cache_values:
+                self._cache[key] = out
+            return out
         dev = sig.device
         be = ops.backend()
         if self._traj_buf is None or self._traj_buf.shape[1] < L or self._traj_buf.device != dev:
             size = max(L, getattr(storage, "max_size", L))
             self._traj_buf = torch.empty((3, size), dtype=torch.int64, device=dev)
             self._traj_counts = torch.zeros(2, dtype=torch.int64, device=dev)
-            self._traj_ws = be.traj_workspace(size, dev)
+            self._traj_ws, self._traj_ws_len = be.traj_workspace(size, dev), size
         table = self._traj_buf if not self.cache_values else torch.empty_like(self._traj_buf)
         be.traj_table(sig, by_id, L, at_capacity, cursor, seq_length, self.strict_length, table, self._traj_counts,
                       self._traj_ws)
@@ -429,10 +474,15 @@ class SliceSampler(Sampler):
 
     # ---- sample (samplers.py:1947-2215) -------------------------------------------------------------
     def sample(self, storage: Storage, batch_size: int) -> tuple[Any, dict]:
-        if storage.ndim != 1:
-            raise NotImplementedError("SliceSampler on the B200 engine supports 1-d storages only")
+        nd = storage.ndim
+        if nd > 2:
+            raise NotImplementedError("SliceSampler on the B200 engine supports storages with ndim 1 or 2")
         seq_length, num_slices = self._adjusted_batch_size(batch_size)
+        span = self._span_code
+        if any(k >= seq_length for k in span):
+            raise ValueError("The right and left span must be strictly lower than the sequence length")
         table, n_traj, variable, traj = self._plan(storage, seq_length, num_slices)
+        variable = variable or any(span)        # a span cuts slices short where they leave their trajectory
         dev = table.device
         if traj is None:
             traj = torch.randint(n_traj, (num_slices,), device=dev, generator=self._rng)    # :1987-1990
@@ -450,39 +500,51 @@ class SliceSampler(Sampler):
             terminated_key = _replace_last(self.truncated_key, "terminated")
             done_all, term_all = get(done_key), get(terminated_key)
         one_byte = lambda t: t is None or (t.element_size() == 1 and t.numel() == t.shape[0] and t.is_contiguous())
-        fused = self.truncated_key is not None and one_byte(done_all) and one_byte(term_all)
+        fused = nd == 1 and self.truncated_key is not None and one_byte(done_all) and one_byte(term_all)
         kw = dict(flags=(done_all, term_all)) if fused else {}
         if variable and not self.pad_output:
-            seq = be.slice_index(*args, variable=True, want_index=False)[3]
+            seq = be.slice_index(*args, variable=True, want_index=False, span=span)[3]
             ends_at = seq.cumsum(0)
             total = int(ends_at[-1])                                                         # data-dependent batch size
-            out = be.slice_index(*args, variable=True, out_offset=ends_at - seq, total=total, **kw)
+            out = be.slice_index(*args, variable=True, out_offset=ends_at - seq, total=total, span=span, **kw)
             slice_starts = ends_at - seq
+            per_slice = seq
         else:
-            out = be.slice_index(*args, variable=variable, pad_output=self.pad_output, **kw)
+            out = be.slice_index(*args, variable=variable, pad_output=self.pad_output, span=span, **kw)
             slice_starts = None
+            per_slice = None
         index, truncated, mask = out[0], out[1], out[2]
+        flat = index
+        if nd == 2:
+            # the column of every sampled step: that of its trajectory; rows of the [T, E, ...] leaves are t * E + e
+            col = self._column[traj]
+            col = col.repeat_interleave(per_slice) if per_slice is not None else col.repeat_interleave(seq_length)
+            flat = index * storage.shape[1] + col
         info: dict = {}
         if mask is not None:
             info[("collector", "mask")] = mask
         is_init_all = get("is_init")
+        n_rows = len(storage)
+        rows_of = (lambda t: t.reshape(-1, *t.shape[nd:])) if nd > 1 else (lambda t: t)
         if self.truncated_key is not None:
             info[self.truncated_key] = truncated
             if fused:
                 info[done_key], info[terminated_key] = out[4], out[5]
             else:     # wide flag leaves: one small gather, then the reference's elementwise ops (:2190-2205)
-                have = {k: v for k, v in (("done", done_all), ("terminated", term_all)) if v is not None}
-                rows = dict(zip(have, be.gather(list(have.values()), index, len(storage)))) if have else {}
+                have = {k: rows_of(v) for k, v in (("done", done_all), ("terminated", term_all)) if v is not None}
+                rows = dict(zip(have, be.gather(list(have.values()), flat, n_rows))) if have else {}
                 done, term = rows.get("done"), rows.get("terminated")
                 info[done_key] = truncated.clone() if done is None else done.reshape(truncated.shape) | truncated
-                info[terminated_key] = torch.zeros_like(truncated) if term is None else term
+                info[terminated_key] = torch.zeros_like(truncated) if term is None else term.reshape(truncated.shape)
         if is_init_all is not None:   # every slice start is an init for recurrent modules (:2217-2268)
-            is_init = be.gather([is_init_all], index, len(storage))[0]
+            is_init = be.gather([rows_of(is_init_all)], flat, n_rows)[0]
             marker = torch.zeros_like(is_init)
             if slice_starts is None:
                 slice_starts = torch.arange(num_slices, device=dev) * seq_length
             marker[slice_starts] = True
             info["is_init"] = marker | is_init
+        if nd == 2:
+            return (index, col), info
         return (index,), info
 
 

@@ -172,12 +172,17 @@ class Storage(abc.ABC):
         raise RuntimeError(f"storage.flatten is not supported for storages of type {type(self)} when ndim > 1.")
 
     def dumps(self, path) -> None:
+        # storages.py:305-311: the storage's checkpointer decides the on-disk layout (ListStorage: one pickled file)
+        if self.checkpointer is not None:
+            return self.checkpointer.dumps(self, path)
         import os
 
         os.makedirs(path, exist_ok=True)
         torch.save(self.state_dict(), os.path.join(str(path), "storage.pt"))
 
     def loads(self, path) -> None:
+        if self.checkpointer is not None:
+            return self.checkpointer.loads(self, path)
         import os
 
         self.load_state_dict(torch.load(os.path.join(str(path), "storage.pt"), weights_only=False))
@@ -304,7 +309,9 @@ class TensorStorage(Storage):
         elif storage is not None:
             max_size = _batch_len(storage)
         self.ndim = ndim
-        super().__init__(max_size, compilable=compilable)
+        from .checkpointers import TensorStorageCheckpointer  # the reference's default (storages.py:612-613)
+
+        super().__init__(max_size, checkpointer=TensorStorageCheckpointer(), compilable=compilable)
         self.initialized = storage is not None
         self._len = max_size if self.initialized else 0
         if device == "auto":

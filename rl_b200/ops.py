@@ -55,8 +55,8 @@ _SIGNATURES = {
     "rlb_affine_scan": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "rlb_traj_table_workspace_bytes": (_sz, [_i64]),
     "rlb_traj_table": (_i32, [_vp, _i32, _i64, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "rlb_slice_index": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                               _vp, _vp, _vp]),
+    "rlb_slice_index": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
+                               _vp, _vp, _vp, _vp, _vp]),
     "rlb_slice_mask_starts": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
     "rlb_tree_update_range": (_i32, [_vp, _vp, _i64, _i32, _i64, _i64, _i64, _i32, _vp, _f64, _f64, _f64, _i32, _vp,
                                      _vp, _vp]),
@@ -425,7 +425,7 @@ class CudaBackend:
 
     def slice_index(self, start, length, n_traj: int, traj_draw, u, seq_length: int, storage_length: int,
                     variable: bool = False, pad_output: bool = False, out_offset=None, total: int | None = None,
-                    want_index: bool = True, flags: tuple | None = None):
+                    want_index: bool = True, flags: tuple | None = None, span: tuple = (0, 0)):
         """Returns (index int64[n], truncated bool[n, 1], mask bool[n] | None, seq int64[num_slices]); with
         ``flags=(done_leaf | None, terminated_leaf | None)`` (the storage's one-byte-per-slot flags) two more entries:
         ``done[index] | truncated`` and ``terminated[index]`` as bool [n, 1]."""
@@ -446,7 +446,8 @@ class CudaBackend:
         with self._Guard(dev):
             self._check(self.L.rlb_slice_index(start.data_ptr(), length.data_ptr(), n_traj, traj_draw.data_ptr(),
                                                u.data_ptr(), S, seq_length, storage_length, int(variable),
-                                               int(pad_output), self._p(out_offset), self._p(index), self._p(trunc),
+                                               int(pad_output), int(span[0]), int(span[1]), self._p(out_offset),
+                                               self._p(index), self._p(trunc),
                                                self._p(mask), seq.data_ptr(), self._p(done_src), self._p(term_src),
                                                self._p(done_out), self._p(term_out), self._stream(dev)),
                         "rlb_slice_index")

@@ -194,13 +194,13 @@ class OracleBackend:
             row[:len(a)] = torch.from_numpy(a)
 
     def slice_index(self, start, length, n_traj, traj_draw, u, seq_length, storage_length, variable=False,
-                    pad_output=False, out_offset=None, total=None, want_index=True, flags=None):
+                    pad_output=False, out_offset=None, total=None, want_index=True, flags=None, span=(0, 0)):
         from oracle import slice_oracle as so
 
         idx, tr, mask, seq = so.slice_index(start[:n_traj].numpy(), length[:n_traj].numpy(), seq_length=seq_length,
                                             num_slices=traj_draw.numel(), storage_length=storage_length,
                                             traj_draw=traj_draw.numpy(), u=u.numpy(), strict_length=not variable,
-                                            pad_output=pad_output)
+                                            pad_output=pad_output, span=span, force_variable=variable)
         seq = torch.from_numpy(np.asarray(seq))
         if not want_index:
             return None, None, None, seq

@@ -470,3 +470,89 @@ def test_predraw_same_stream_eager_and_graph(cuda_backend):
         assert not torch.equal(rb.sampler._u_next, u)    # and the replay refilled the buffer for the next one
         seen.append(idx)
     assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+
+
+def test_storage_checkpoint_roundtrip_on_device(cuda_backend, tmp_path):
+    """TensorStorageCheckpointer from / to HBM: filled rows stream through a pinned buffer into the tensordict-memmap
+    layout and back (checkpointers.py:326-455); buffer.dumps / loads carries storage + sampler + writer."""
+    import json
+
+    from rl_b200.data import LazyTensorStorage, TensorDict, TensorDictPrioritizedReplayBuffer
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    mk = lambda: TensorDictPrioritizedReplayBuffer(alpha=0.6, beta=0.4, storage=LazyTensorStorage(5000, device=dev),
+                                                   batch_size=64, generator=torch.Generator(device=dev).manual_seed(5))
+    rb = mk()
+    data = TensorDict({"pixels": torch.randint(0, 255, (3000, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+                       "next": {"reward": torch.randn(3000, device=dev, generator=g),
+                                "done": torch.rand(3000, 1, device=dev, generator=g) < 0.1},
+                       "td_error": torch.rand(3000, device=dev, generator=g)}, [3000])
+    rb.extend(data)
+    rb.dumps(tmp_path / "ckpt")
+    meta = json.loads((tmp_path / "ckpt" / "storage" / "storage_metadata.json").read_text())
+    assert meta["len"] == 3000 and meta["is_pytree"] is False
+    assert (tmp_path / "ckpt" / "storage" / "pixels.memmap").stat().st_size == 5000 * 4 * 84 * 84
+    rb2 = mk()
+    rb2.extend(data[:10])          # initialised with something else
+    rb2.loads(tmp_path / "ckpt")
+    assert len(rb2) == 3000
+    idx = torch.arange(3000, device=dev)
+    a, b = rb.storage.get(idx), rb2.storage.get(idx)
+    for k in ("pixels", ("next", "reward"), ("next", "done")):
+        assert torch.equal(a.get(k), b.get(k)), k
+    assert torch.equal(rb.sampler._sum_tree.values, rb2.sampler._sum_tree.values)
+    s1, s2 = rb.sample(), rb2.sample()
+    assert torch.equal(s1.get("index"), s2.get("index")) and torch.equal(s1.get("pixels"), s2.get("pixels"))
+
+
+@pytest.mark.parametrize("mode", ["strict", "loose", "span"])
+def test_slice_sampler_2d_storage_on_device(cuda_backend, mode):
+    """SliceSampler on an ndim=2 storage ([T, E]: one ring per column) on the GPU: (time, column) index pairs, flags
+    and rows against the oracle's ring-by-ring table for the draws of the buffer's own CUDA generator (the same
+    construction is pinned to the unmodified reference on CPU, tests/test_host_logic.py)."""
+    from oracle import slice_oracle as so
+    from rl_b200.data import LazyTensorStorage, SliceSampler, TensorDict, TensorDictReplayBuffer
+
+    dev = torch.device("cuda", 0)
+    Tm, E, S, T = 6000, 8, 24, 12
+    kw = dict(strict=dict(), loose=dict(strict_length=False), span=dict(span=(True, 3)))[mode]
+    g = torch.Generator(device=dev).manual_seed(9)
+    rb = TensorDictReplayBuffer(storage=LazyTensorStorage(Tm * E, device=dev, ndim=2), batch_size=S * T, generator=g,
+                                sampler=SliceSampler(num_slices=S, end_key=("next", "done"), **kw), dim_extend=0)
+    rng = np.random.default_rng(4)
+    written = 0
+    for n in (4000, 1500, 1700):                      # the third batch wraps around
+        done = torch.from_numpy(rng.random((n, E, 1)) < 0.05)
+        obs = (torch.arange(written, written + n).view(n, 1, 1) * 16 + torch.arange(E).view(1, E, 1)).float()
+        rb.extend(TensorDict({"obs": obs.to(dev), ("next", "done"): done.to(dev)}, [n, E]))
+        written += n
+        rows = min(Tm, written)
+        stored = rb.storage._leaves
+        full = rb.storage.get(slice(None))
+        stored_done = full.get(("next", "done"))[:rows].reshape(rows, E).cpu().numpy()
+        cursor = rb.storage._last_cursor
+        cursor = cursor.stop - 1 if isinstance(cursor, slice) else int(torch.as_tensor(cursor).reshape(-1)[-1])
+        st, sp, ln, col = so.traj_table_nd(end=stored_done, at_capacity=rows == Tm, cursor=cursor)
+        strict = mode == "strict"
+        if strict:
+            keep = ln >= T
+            st, sp, ln, col = st[keep], sp[keep], ln[keep], col[keep]
+        for _ in range(2):
+            state = g.get_state()
+            batch = rb.sample()
+            g.set_state(state)
+            traj = torch.randint(len(st), (S,), device=dev, generator=g)
+            u = torch.rand(S, device=dev, generator=g)
+            span = (-1, 3) if mode == "span" else (0, 0)
+            oi, otr, _, oseq = so.slice_index(st, ln, seq_length=T, num_slices=S, storage_length=rows, traj_draw=traj.cpu().numpy(),
+                                              u=u.cpu().numpy(), strict_length=strict, span=span,
+                                              force_variable=mode == "span")
+            ocol = np.repeat(col[traj.cpu().numpy()], oseq)
+            idx = batch.get("index")
+            np.testing.assert_array_equal(idx[..., 0].reshape(-1).cpu().numpy(), oi)
+            np.testing.assert_array_equal(idx[..., 1].reshape(-1).cpu().numpy(), ocol)
+            np.testing.assert_array_equal(batch.get(("next", "truncated")).reshape(-1).cpu().numpy(), otr)
+            np.testing.assert_array_equal(batch.get(("next", "done")).reshape(-1).cpu().numpy(), stored_done[oi, ocol] | otr)
+            want_obs = full.get("obs")[torch.from_numpy(oi).to(dev), torch.from_numpy(ocol).to(dev)]
+            assert torch.equal(batch.get("obs").reshape(-1), want_obs.reshape(-1))

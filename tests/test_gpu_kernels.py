@@ -996,3 +996,42 @@ def test_sampler_matches_reference_cuda_path_without_leaf_injection(cuda_backend
         ref_update(wi, wp)
         ours.update_priority(wi, wp)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("span", [(-1, 0), (0, -1), (-1, -1), (3, 0), (0, 5), (2, 7), (-1, 4)])
+@pytest.mark.parametrize("pad", [False, True])
+def test_slice_index_span_matches_oracle(cuda_backend, span, pad):
+    """SliceSampler(span=...) in rlb_slice_index (samplers.py:2071-2118): the slice may start before its trajectory
+    (left) or run past its end (right); the part outside is cut off.  Index / truncated / mask / lengths bit-equal to the
+    restatement (itself pinned to the unmodified reference in tests/test_host_logic.py) for the same draws."""
+    from oracle import slice_oracle as so
+
+    L, S, T = 200_000, 512, 16
+    rng = np.random.default_rng(abs(hash(span)) % 1000)
+    end = rng.random(L) < 1 / 40
+    start, stop, length = so.traj_table(end=end, at_capacity=True, cursor=None)
+    table = torch.empty((3, L), dtype=torch.int64, device=dev())
+    counts = torch.zeros(2, dtype=torch.int64, device=dev())
+    cuda_backend.traj_table(torch.from_numpy(end).to(dev()), False, L, True, -1, T, False, table, counts,
+                            cuda_backend.traj_workspace(L, dev()))
+    n_all = int(counts[0])
+    assert n_all == len(start)
+    g = torch.Generator(device=dev()).manual_seed(1)
+    traj = torch.randint(n_all, (S,), device=dev(), generator=g)
+    u = torch.rand(S, device=dev(), generator=g)
+    args = (table[0], table[2], n_all, traj, u, T, L)
+    oi, otr, omask, oseq = so.slice_index(start, length, seq_length=T, num_slices=S, storage_length=L,
+                                          traj_draw=traj.cpu().numpy(), u=u.cpu().numpy(), strict_length=False,
+                                          pad_output=pad, span=span, force_variable=True)
+    if pad:
+        index, trunc, mask, sq = cuda_backend.slice_index(*args, variable=True, pad_output=True, span=span)
+        np.testing.assert_array_equal(mask.cpu().numpy(), omask)
+    else:
+        sq = cuda_backend.slice_index(*args, variable=True, want_index=False, span=span)[3]
+        ends_at = sq.cumsum(0)
+        index, trunc, mask, _ = cuda_backend.slice_index(*args, variable=True, out_offset=ends_at - sq,
+                                                         total=int(ends_at[-1]), span=span)
+    np.testing.assert_array_equal(sq.cpu().numpy(), oseq)
+    np.testing.assert_array_equal(index.cpu().numpy(), oi)
+    np.testing.assert_array_equal(trunc.cpu().numpy().reshape(-1), otr)
+    assert (oseq < T).any() and (oseq > 0).all() if span != (0, -1) else True   # some slices were cut

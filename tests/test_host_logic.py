@@ -517,8 +517,8 @@ def test_slice_sampler_contract(emul):
         SliceSampler()
     with pytest.raises(ValueError, match="pad_output=True is incompatible"):
         SliceSampler(num_slices=2, pad_output=True)
-    with pytest.raises(NotImplementedError, match="span"):
-        SliceSampler(num_slices=2, span=True)
+    assert SliceSampler(num_slices=2, span=True)._span_code == (-1, -1)
+    assert SliceSampler(num_slices=2, span=(False, 3))._span_code == (0, 3)
     with pytest.raises(RuntimeError, match="requires `cache_values`"):
         SliceSampler(num_slices=2, ends=torch.zeros(10, dtype=torch.bool))
     L = 60
@@ -764,6 +764,15 @@ def test_sampler_without_replacement_equals_live_reference(emul, ref_samplers, d
         assert ref._remaining_batches == mine._remaining_batches
 
 
+def _sample_quietly(rb):
+    """A draw whose result is not compared (the reference could not produce it); the oracle-backed emulator may itself
+    give up on degenerate batches (every slice cut to zero steps)."""
+    try:
+        rb.sample()
+    except (RuntimeError, IndexError, ValueError):
+        pass
+
+
 def test_slice_sampler_randomized_buffer_flows_vs_live_reference(emul, ref_samplers):
     """Forty random buffers (ring length, several writer batches that may wrap, end density, strict / loose / padded,
     num_slices / slice_len, cache on / off): rl_b200's SliceSampler in a TensorDictReplayBuffer against the unmodified
@@ -772,7 +781,7 @@ def test_slice_sampler_randomized_buffer_flows_vs_live_reference(emul, ref_sampl
 
     rng = np.random.default_rng(77)
     compared = 0
-    for trial in range(40):
+    for trial in range(80):
         L = int(rng.integers(10, 200))
         seq, S = int(rng.integers(1, 9)), int(rng.integers(1, 7))
         kwargs = dict(end_key=("next", "done"))
@@ -782,6 +791,15 @@ def test_slice_sampler_randomized_buffer_flows_vs_live_reference(emul, ref_sampl
             kwargs["strict_length"] = False
         elif mode == 2:
             kwargs.update(strict_length=False, pad_output=True)
+        if trial >= 40:   # span=: slices may hang out of their trajectory on either side and are cut there (:2071-2118)
+            pick = lambda: [False, True, int(rng.integers(1, max(2, seq)))][int(rng.integers(0, 3))]
+            sp = (pick(), pick())
+            sp = tuple(v if (v is True or v is False or v < seq) else False for v in sp)
+            if not any(sp):
+                sp = (True, False)
+            kwargs["span"] = sp
+            if mode == 2:     # (the padded + span corner emits a mask only when a slice was actually cut, data-dependent
+                kwargs.pop("pad_output")   # in the reference; the concatenated form is the one pinned here)
         cache = bool(rng.random() < 0.5)
         rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device="cpu"), batch_size=S * seq,
                                     sampler=SliceSampler(cache_values=cache, **kwargs),
@@ -807,9 +825,35 @@ def test_slice_sampler_randomized_buffer_flows_vs_live_reference(emul, ref_sampl
                 try:
                     want_index, want_info = ref.sample(st, S * seq)
                 except RuntimeError as err:
+                    if "Boolean value of Tensor" in str(err) and kwargs.get("span"):
+                        # an integer span next to per-slice lengths (strict_length=False): the reference compares the int
+                        # with a tensor in an `if` (samplers.py:2079 / :2091) and cannot produce this batch at all
+                        _sample_quietly(rb)
+                        rb._rng.set_state(ref._rng.get_state())
+                        continue
                     assert "sufficient length" in str(err)
                     with pytest.raises(RuntimeError, match="sufficient length"):
                         rb.sample()
+                    continue
+                except ValueError as err:
+                    # (with strict_length=False the reference compares the span with the CLAMPED per-slice length when
+                    # there is a single slice -- a data-dependent rejection this engine does not reproduce)
+                    assert "strictly lower than the sequence length" in str(err)
+                    _sample_quietly(rb)
+                    rb._rng.set_state(ref._rng.get_state())
+                    continue
+                except IndexError as err:   # a single stored step: the reference squeezes its flags to 0-d (:1913-1915)
+                    # (or every slice was cut to zero steps by a span: the reference indexes an empty tensor, :2187)
+                    assert "0-dim" in str(err) or "size 0" in str(err)
+                    _sample_quietly(rb)
+                    rb._rng.set_state(ref._rng.get_state())
+                    continue
+                except TypeError as err:
+                    # the reference's right span calls torch.minimum(int, Tensor) when nothing made seq_length a tensor
+                    # before (samplers.py:2114): it cannot produce this batch at all.  Keep the generators in step.
+                    assert "minimum()" in str(err) and kwargs.get("span")
+                    _sample_quietly(rb)
+                    rb._rng.set_state(ref._rng.get_state())
                     continue
                 got = rb.sample()
                 assert torch.equal(got.get("index").reshape(-1), want_index[0]), (trial, kwargs)
@@ -817,7 +861,7 @@ def test_slice_sampler_randomized_buffer_flows_vs_live_reference(emul, ref_sampl
                     assert torch.equal(got.get(k).reshape(v.shape), v), (trial, k)
                 assert torch.equal(got.get("obs").reshape(-1), ring_obs[want_index[0]].reshape(-1))
                 compared += 1
-    assert compared >= 60
+    assert compared >= 120
 
 
 def test_prioritized_slice_sampler_randomized_vs_live_reference(emul, ref_samplers):
@@ -867,3 +911,141 @@ def test_prioritized_slice_sampler_randomized_vs_live_reference(emul, ref_sample
             assert torch.equal(got.get(("next", "done")).reshape(-1), want_info[("next", "done")].reshape(-1))
             compared += 1
     assert compared >= 25
+
+
+# ---------------------------------------------------------------------------------------------------- checkpointer
+def test_tensor_storage_checkpointer_layout_and_roundtrip(emul, tmp_path):
+    """TensorStorageCheckpointer (checkpointers.py:326-455): tensordict-memmap layout for TensorDict storages -- one raw
+    <key>.memmap per leaf in nested directories + meta.json + storage_metadata.json -- and the reference's own pytree
+    layout for tensors / pytrees; both round-trip, and only the filled rows travel."""
+    import json
+
+    import numpy as np
+
+    from rl_b200.data import LazyTensorStorage, TensorDict, TensorStorageCheckpointer
+
+    g = torch.Generator().manual_seed(0)
+    st = LazyTensorStorage(50, device="cpu")
+    assert isinstance(st.checkpointer, TensorStorageCheckpointer)
+    data = TensorDict({"obs": torch.randn(30, 4, generator=g), "action": torch.randint(0, 5, (30, 1), generator=g),
+                       "next": {"obs": torch.randn(30, 4, generator=g), "done": torch.rand(30, 1, generator=g) < 0.5,
+                                "half": torch.randn(30, 3, generator=g).to(torch.bfloat16)}}, [30])
+    st.set(slice(0, 30), data)
+    st.dumps(tmp_path / "td")
+    meta = json.loads((tmp_path / "td" / "storage_metadata.json").read_text())
+    assert meta == {"metadata": {}, "is_pytree": False, "len": 30}
+    root = json.loads((tmp_path / "td" / "meta.json").read_text())
+    assert root["shape"] == [50] and root["obs"] == {"device": "cpu", "shape": [50, 4], "dtype": "torch.float32"}
+    assert root["action"]["dtype"] == "torch.int64" and "_type" in root
+    nxt = json.loads((tmp_path / "td" / "next" / "meta.json").read_text())
+    assert nxt["done"] == {"device": "cpu", "shape": [50, 1], "dtype": "torch.bool"}
+    raw = np.memmap(tmp_path / "td" / "obs.memmap", dtype=np.float32, mode="r", shape=(50, 4))   # the full-size leaf
+    np.testing.assert_array_equal(raw[:30], data.get("obs").numpy())
+    assert (tmp_path / "td" / "next" / "obs.memmap").stat().st_size == 50 * 4 * 4
+    # into an initialised storage and into a fresh lazy one
+    for fresh in (False, True):
+        st2 = LazyTensorStorage(50, device="cpu")
+        if not fresh:
+            st2.set(slice(0, 5), data[:5])
+        st2.loads(tmp_path / "td")
+        assert len(st2) == 30
+        got = st2.get(torch.arange(30))
+        for k in data.keys(True, True):
+            assert torch.equal(got.get(k), data.get(k)), k
+    # pytree / bare tensor storages: the reference's _save_pytree layout (utils.py:818-873)
+    tree = {"a": torch.randn(20, 3, generator=g), "b": (torch.arange(20), torch.rand(20, 2, generator=g))}
+    sp = LazyTensorStorage(40, device="cpu")
+    sp.set(slice(0, 20), tree)
+    sp.dumps(tmp_path / "tree")
+    md = json.loads((tmp_path / "tree" / "storage_metadata.json").read_text())
+    assert md["is_pytree"] and md["len"] == 20
+    assert md["metadata"]["a"] == {"dtype": "torch.float32", "shape": [40, 3]}
+    assert md["metadata"]["b.0"] == {"dtype": "torch.int64", "shape": [40]} and "b.1" in md["metadata"]
+    assert (tmp_path / "tree" / "b" / "1.memmap").exists()
+    sp2 = LazyTensorStorage(40, device="cpu")
+    sp2.set(slice(0, 3), {"a": tree["a"][:3], "b": (tree["b"][0][:3], tree["b"][1][:3])})
+    sp2.loads(tmp_path / "tree")
+    out = sp2.get(torch.arange(20))
+    assert torch.equal(out["a"], tree["a"]) and torch.equal(out["b"][0], tree["b"][0]) and torch.equal(out["b"][1], tree["b"][1])
+    s1 = LazyTensorStorage(10, device="cpu")
+    s1.set(slice(0, 4), torch.arange(8.0).view(4, 2))
+    s1.dumps(tmp_path / "single")
+    assert (tmp_path / "single" / "_-single-tensor-_.memmap").exists()
+    with pytest.raises(RuntimeError, match="non-initialized"):
+        LazyTensorStorage(10, device="cpu").dumps(tmp_path / "empty")
+
+
+@pytest.mark.parametrize("mode", ["strict", "loose", "padded", "span", "traj"])
+def test_slice_sampler_2d_storage_equals_live_reference(emul, ref_samplers, mode):
+    """ndim=2 storages ([T, E]: one ring per column, samplers.py:1652-1743, :1955): rl_b200's SliceSampler in a
+    TensorDictReplayBuffer against the unmodified reference sampler on the same [T, E, ...] contents -- partially filled
+    and full rings, same CPU generator seed: same (time, column) index pairs, same info, same rows."""
+    from rl_b200.data import SliceSampler
+
+    rng = np.random.default_rng({"strict": 1, "loose": 2, "padded": 3, "span": 4, "traj": 5}[mode])
+    for trial in range(6):
+        T, E = int(rng.integers(20, 90)), int(rng.integers(2, 6))
+        seq, S = int(rng.integers(2, 7)), int(rng.integers(1, 6))
+        kwargs = dict(num_slices=S) if rng.random() < 0.5 else dict(slice_len=seq)
+        if mode == "traj":
+            kwargs["traj_key"] = "episode"
+        else:
+            kwargs["end_key"] = ("next", "done")
+        if mode == "loose":
+            kwargs["strict_length"] = False
+        elif mode == "padded":
+            kwargs.update(strict_length=False, pad_output=True)
+        elif mode == "span":
+            kwargs["span"] = (True, int(rng.integers(1, seq))) if rng.random() < 0.5 else (False, True)
+        # time along dim 0 of the storage: the data below is [time, env], so it is extended along dim 0
+        rb = TensorDictReplayBuffer(storage=LazyTensorStorage(T * E, device="cpu", ndim=2), batch_size=S * seq,
+                                    sampler=SliceSampler(**kwargs), generator=torch.Generator().manual_seed(trial),
+                                    dim_extend=0)
+        ref = ref_samplers.mod.SliceSampler(**kwargs)
+        ref._rng = torch.Generator().manual_seed(trial)
+        ring = {("next", "done"): torch.zeros(T, E, 1, dtype=torch.bool), "obs": torch.zeros(T, E, 1),
+                "episode": torch.zeros(T, E, dtype=torch.long)}
+        total = 0
+        ep = torch.arange(E) * 1000
+        for _ in range(int(rng.integers(1, 4))):
+            n = int(rng.integers(1, T + 1))
+            done = torch.from_numpy(rng.random((n, E, 1)) < float(rng.choice([0.03, 0.1, 0.3])))
+            obs = (torch.arange(total, total + n, dtype=torch.float32).view(n, 1, 1) * 10 + torch.arange(E).view(1, E, 1)).float()
+            episode = torch.empty(n, E, dtype=torch.long)
+            for t in range(n):
+                episode[t] = ep
+                ep = ep + done[t, :, 0].long()
+            rb.extend(TensorDict({("next", "done"): done, "obs": obs, "episode": episode}, [n, E]))
+            rows = (total + torch.arange(n)) % T
+            ring[("next", "done")][rows], ring["obs"][rows], ring["episode"][rows] = done, obs, episode
+            total += n
+            filled = min(T, total)
+            cur = rb.storage._last_cursor
+            cur = range(cur.start, cur.stop) if isinstance(cur, slice) else cur
+            st = ref_samplers.make_storage(dict(ring), filled, T, cur, columns=E)
+            for _ in range(2):
+                try:
+                    want_index, want_info = ref.sample(st, S * seq)
+                except RuntimeError as err:
+                    if "Boolean value of Tensor" in str(err) and kwargs.get("span"):
+                        # an integer span next to per-slice lengths (strict_length=False): the reference compares the int
+                        # with a tensor in an `if` (samplers.py:2079 / :2091) and cannot produce this batch at all
+                        _sample_quietly(rb)
+                        rb._rng.set_state(ref._rng.get_state())
+                        continue
+                    assert "sufficient length" in str(err)
+                    with pytest.raises(RuntimeError, match="sufficient length"):
+                        rb.sample()
+                    continue
+                except TypeError as err:   # the reference's torch.minimum(int, Tensor) bug (samplers.py:2114)
+                    assert "minimum()" in str(err) and kwargs.get("span")
+                    _sample_quietly(rb)
+                    rb._rng.set_state(ref._rng.get_state())
+                    continue
+                got = rb.sample()
+                gi = got.get("index")
+                assert torch.equal(gi[..., 0].reshape(-1), want_index[0]) and torch.equal(gi[..., 1].reshape(-1), want_index[1]), \
+                    (mode, trial, kwargs)
+                for k, v in want_info.items():
+                    assert torch.equal(got.get(k).reshape(v.shape), v), (mode, trial, k)
+                assert torch.equal(got.get("obs").reshape(-1), ring["obs"][want_index].reshape(-1))
