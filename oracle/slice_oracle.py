@@ -81,6 +81,7 @@ def slice_index(start, length, *, seq_length: int, num_slices: int, storage_leng
         if out.any():
             seq = np.minimum(seq, lens - rel)
             variable = True
+    seq = np.maximum(seq, 0)                                         # (a trajectory shorter than the span)
     starts = np.asarray(start, dtype=np.int64)[traj] + rel           # :2120-2126
     if variable and pad_output:
         T = seq_length
@@ -123,26 +124,29 @@ def traj_table_nd(*, end=None, trajectory=None, at_capacity: bool, cursor=None):
     return tuple(np.concatenate(o) for o in out)
 
 
-def invalid_starts(stop, length, seq_length: int, ring_length: int):
-    """PrioritizedSliceSampler._preceding_stop_idx (:2854-2888, strict_length=True, span=False): the slots a slice of
-    ``seq_length`` steps must not start at -- the last ``seq_length - 1`` steps of every trajectory (all of a shorter one).
-    The reference lists them through a left-padded index matrix in "trajectory order" coordinates and shifts by the first
-    start when the ring is full; in storage coordinates that is simply ``stop - j`` (mod ring) for j < min(len, seq - 1).
+def invalid_starts(stop, length, seq_length: int, ring_length: int, strict_length: bool = True):
+    """PrioritizedSliceSampler._preceding_stop_idx (:2854-2888, span=False): the slots a slice of ``seq_length`` steps must
+    not start at -- the last ``seq_length - 1`` steps of every trajectory (all of a shorter one); with
+    ``strict_length=False`` the first step of a trajectory is never among them (:2863-2871 removes the starts from the
+    candidates first).  The reference lists them through a left-padded index matrix in "trajectory order" coordinates and
+    shifts by the first start when the ring is full; in storage coordinates that is simply ``stop - j`` (mod ring) for
+    j < min(len, seq - 1) (len - 1 when not strict).
     Order: trajectory by trajectory, ascending within each, like the reference's boolean-mask read-out."""
     out = []
     for sp, ln in zip(np.asarray(stop, dtype=np.int64), np.asarray(length, dtype=np.int64)):
-        m = int(min(ln, seq_length - 1))
+        m = int(min(ln if strict_length else ln - 1, seq_length - 1))
         out.append((sp - np.arange(m - 1, -1, -1, dtype=np.int64)) % ring_length)
     return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
 
 
 def prioritized_slice_sample(orc_sampler, start, stop, length, *, seq_length: int, num_slices: int, storage_len: int,
-                             u):
+                             u, strict_length: bool = True):
     """PrioritizedSliceSampler.sample (:2890-3004) on an oracle.per_oracle.OraclePrioritizedSampler: zero the invalid
     starts in the sum tree (:2910-2912), draw ``num_slices`` starts like PrioritizedSampler.sample (:2915-2917), restore
-    (:2918), expand (:2963-2966) and repeat the weights (:2969-2971).
-    Returns (index int64[S*T], weight fp32[S*T], truncated bool[S*T], starts int64[S])."""
-    bad = invalid_starts(stop, length, seq_length, storage_len)
+    (:2918), cut every slice at the end of its trajectory when not strict (:2919-2951), expand (:2963-2966) and repeat
+    the weights (:2969-2971).
+    Returns (index int64[n], weight fp32[n], truncated bool[n], starts int64[S])."""
+    bad = invalid_starts(stop, length, seq_length, storage_len, strict_length)
     tree = orc_sampler._sum_tree
     vals = np.array(tree[bad], dtype=np.float32)
     tree[bad] = np.zeros(len(bad), dtype=np.float32)
@@ -153,8 +157,21 @@ def prioritized_slice_sample(orc_sampler, start, stop, length, *, seq_length: in
     finally:
         tree[bad] = vals
     starts = starts.numpy().astype(np.int64)
-    index = ((starts[:, None] + np.arange(seq_length, dtype=np.int64)[None, :]) % storage_len).reshape(-1)
-    weight = np.repeat(w.numpy(), seq_length)
-    truncated = np.zeros(num_slices * seq_length, dtype=bool)
-    truncated.reshape(num_slices, seq_length)[:, -1] = True
+    if strict_length:
+        index = ((starts[:, None] + np.arange(seq_length, dtype=np.int64)[None, :]) % storage_len).reshape(-1)
+        weight = np.repeat(w.numpy(), seq_length)
+        truncated = np.zeros(num_slices * seq_length, dtype=bool)
+        truncated.reshape(num_slices, seq_length)[:, -1] = True
+        return index, weight, truncated, starts
+    stop = np.asarray(stop, dtype=np.int64)
+    start = np.asarray(start, dtype=np.int64)
+    stop_corr = np.where(stop < start, stop + storage_len, stop)                  # :2929-2934
+    diff = stop_corr[:, None] - starts[None, :]                                  # :2935
+    diff[diff < 0] = diff.max() + 1                                              # :2942
+    stops = stop_corr[diff.argmin(axis=0)]                                       # :2944-2945
+    seq = np.minimum(stops - starts + 1, seq_length)                             # :2950
+    index = np.concatenate([s + np.arange(n, dtype=np.int64) for s, n in zip(starts, seq)]) % storage_len
+    weight = np.repeat(w.numpy(), seq)
+    truncated = np.zeros(index.shape[0], dtype=bool)
+    truncated[np.cumsum(seq) - 1] = True
     return index, weight, truncated, starts

@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(128) slice_index_kernel(const SliceParams P) {
     rel = 0;
   }
   if (P.span1 && rel + seq > len) seq = len - rel;                 // :2112-2118
+  if (seq < 0) seq = 0;  // (a trajectory shorter than the span: nothing of the slice is inside it)
   const int64_t first = __ldg(P.start + t) + rel;
   if (P.seq_out && lane == 0) P.seq_out[s] = seq;
   if (!P.index_out) return;

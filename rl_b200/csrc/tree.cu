@@ -461,18 +461,13 @@ __host__ __device__ inline int upd_bot_levels(int depth) { return depth > kDense
 constexpr int kUpdCluster = 8;  // CTAs per update launch: the leader + seven helpers (portable cluster size)
 constexpr int kUpdHoist = 16;   // sibling values of this many levels are held in registers during the climb
 
-// rows of finished nodes: 2 leaf rows (sum / min tree) + 2 * bot (tree, level) rows, dealt out to the helpers
-__host__ __device__ inline int upd_row_slots(int bot) { return (2 * bot + 2 + (kUpdCluster - 2)) / (kUpdCluster - 1); }
 
 template <typename T>
 __host__ __device__ inline size_t upd_smem_bytes(int np, int depth) {
-  // xbuf u64[2*np] | sleaf u32[np] | spos u32[np] | sraw T[np] | sib T[2][bot][np] | cut heaps T[2][2W] |
-  // pnode u32[slots][np] | pval T[slots][np]
+  // xbuf u64[2*np] | sleaf u32[np] | spos u32[np] | Lpos i32[np] | sraw T[np] | sib T[2][bot][np] | cut heaps T[2][2W]
   const int bot = upd_bot_levels(depth);
   const size_t W = size_t(1) << (depth - bot);
-  const size_t slots = (size_t)upd_row_slots(bot);
-  return (size_t)np * (16 + 4 + 4) + (size_t)np * sizeof(T) * (1 + 2 * (size_t)bot) + 4 * W * sizeof(T) +
-         slots * np * (4 + sizeof(T));
+  return (size_t)np * (16 + 4 + 4 + 4) + (size_t)np * sizeof(T) * (1 + 2 * (size_t)bot) + 4 * W * sizeof(T);
 }
 
 #define RLB_TICK(k)                                                   \
@@ -525,8 +520,20 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, double v) {
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_cluster(uint32_t addr, float) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_cluster(uint32_t addr, double) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
 }
 
 template <typename T, bool FUSED>
@@ -542,26 +549,23 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   const int lane = tid & 31;
   const int bot = upd_bot_levels(depth);   // levels climbed item by item; the rest is dense
   const int W = 1 << (depth - bot);        // nodes at the cut level
-  const int slots = upd_row_slots(bot);
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
   __shared__ unsigned s_lmask;             // bit L set: some item hands over at level L (1 <= L <= bot)
   unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
   uint32_t *sleaf = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);  // sorted leaf index (0xffffffff: not an item)
   uint32_t *spos = sleaf + NP;                                    // its input position
-  T *sraw = reinterpret_cast<T *>(spos + NP);                     // leaf values by input position
-  T *sib = sraw + NP;  // [2][bot][NP] sibling values, indexed by ORIGINAL input position
+  int *Lpos = reinterpret_cast<int *>(spos + NP);                 // by INPUT POSITION: merge level of the item if it is
+                                                                  // the last writer of its leaf, else 0
+  T *sraw = reinterpret_cast<T *>(Lpos + NP);                     // leaf values by input position
+  T *sib = sraw + NP;  // [2][bot][NP] by input position: sibling values in, finished ancestors out (staging tile)
   T *cut_s = sib + 2 * (size_t)bot * NP;  // heap layout over the top of the tree: node k at [k], 1 <= k < 2W
   T *cut_m = cut_s + 2 * (size_t)W;
-  // HELPERS' side of the result rows: row r lives in helper 1 + r % (csize - 1), slot r / (csize - 1); the leader
-  // pushes (node id, value) pairs into it as it climbs, the helper scatters them to the trees (node 0 = nothing)
-  T *pval = cut_m + 2 * (size_t)W;
-  uint32_t *pnode = reinterpret_cast<uint32_t *>(pval + (size_t)slots * NP);
 
   // Cluster barrier phases (every thread of every CTA arrives on each, in this order):
   //   1  "all CTAs are running" (remote shared-memory accesses are legal afterwards)
-  //   2  helpers -> leader: the sibling tile is complete (and the helpers' result rows are cleared)
-  //   3  leader -> helpers: every finished node below the cut has been pushed into its row
-  if (crank != 0) for (int k = tid; k < slots * NP; k += NP) pnode[k] = 0u;
+  //   2  helpers -> leader: the sibling tile is complete
+  //   3  leader -> helpers: merge levels, leaf values and the staging tile are final -- scatter them
+  //   4  helpers -> leader: nobody reads the leader's shared memory any more
   cluster_arrive_relaxed();  // phase 1
   if (dbg && tid == 0 && crank <= 1) dbg[32 + 8 * crank] = (long long)globaltimer_ns();
 
@@ -571,6 +575,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     constexpr int kMaxPer = 4;
     const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
     const uint32_t nthreads = (csize - 1u) * (uint32_t)NP, g = (crank - 1u) * (uint32_t)NP + tid;
+    const int64_t ix_self = (tid < n) ? __ldg(index + tid) - index_base : -1;  // (for part 2: the item at position tid)
     T val[kMaxPer];
     uint32_t el[kMaxPer];
 #pragma unroll
@@ -607,22 +612,37 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
       st_cluster(map_to_cta(sib + e, 0), v);
     }
-    cluster_arrive_release();  // phase 2: my stores (and my cleared rows) are performed before the leader goes on
+    cluster_arrive_release();  // phase 2: my stores are performed before the leader goes on
     if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 1] = (long long)globaltimer_ns();
     cluster_wait_acquire();
     cluster_arrive_relaxed();  // phase 3: nothing to publish; wait for the leader's climb
     cluster_wait_acquire();
     if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 2] = (long long)globaltimer_ns();
-    // ---- helpers, part 2: scatter my rows (local shared memory now)
-    const int units = (int)csize - 1, unit = (int)crank - 1;
-    for (int sl = 0; sl < slots; ++sl) {
-      const int r = unit + sl * units;
-      if (r >= 2 * bot + 2) break;
-      T *tree = (r < 2) ? (r ? mn : sum) : (((r - 2) >= bot) ? mn : sum);
-      const uint32_t node = pnode[sl * NP + tid];
-      if (tree && node) tree[node] = pval[sl * NP + tid];
+    // ---- helpers, part 2: scatter my rows.  Row r (0, 1: the leaves of the sum / min tree; 2 + t * bot + l: level
+    // l + 1 of tree t) holds one value per INPUT POSITION p; it is a finished node iff the item at p is the last writer
+    // of its leaf and carried its path beyond level l (Lpos[p] > l + 1).  Rows are read from the leader's shared
+    // memory in position order -- coalesced 128-byte DSMEM reads -- and the node id comes from the index this helper
+    // reads itself.
+    {
+      const int units = (int)csize - 1, unit = (int)crank - 1, nrows = 2 * bot + 2;
+      const int64_t ix = ix_self;
+      const int Lp = (int)ld_cluster_u32(map_to_cta(Lpos + tid, 0));
+      if (Lp > 0 && ix >= 0 && ix < index_limit) {
+        const uint32_t leafnode = (uint32_t)(capacity + ix);
+        for (int r = unit; r < nrows; r += units) {
+          if (r < 2) {
+            T *tree = r ? mn : sum;
+            if (tree) tree[leafnode] = ld_cluster(map_to_cta(sraw + tid, 0), T());
+          } else {
+            const int t = (r - 2) >= bot, l = (r - 2) - t * bot;
+            T *tree = t ? mn : sum;
+            if (tree && Lp > l + 1) tree[leafnode >> (l + 1)] = ld_cluster(map_to_cta(sib + ((size_t)(r - 2)) * NP + tid, 0), T());
+          }
+        }
+      }
     }
     if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 3] = (long long)globaltimer_ns();
+    cluster_arrive_relaxed();  // phase 4 (nothing to publish: the global stores complete with the kernel)
     return;
   }
 
@@ -783,20 +803,6 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   }
   RLB_TICK(4);
 
-  // where a finished node goes: row r -> (helper, slot); without helpers the leader stores it itself
-  const int units = (int)csize - 1;
-  auto publish = [&](int r, uint32_t node, T v) {
-    if (units > 0) {
-      const int sl = r / units;
-      const uint32_t h = 1u + (uint32_t)(r - sl * units);
-      st_cluster(map_to_cta(pval + sl * NP + tid, h), v);
-      st_cluster_u32(map_to_cta(pnode + sl * NP + tid, h), node);
-    } else {
-      T *tree = (r < 2) ? (r ? mn : sum) : (((r - 2) >= bot) ? mn : sum);
-      if (tree) tree[node] = v;
-    }
-  };
-
   // ---- 4. per head j: merge level L_j, and WHERE its hand-over goes (only merges below the cut hand over)
   const uint32_t left = tid > 0 ? sleaf[tid - 1] : 0u;
   bool alive = key_valid && (tid == 0 || left != myleaf);
@@ -809,8 +815,6 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     vs = v;
     vm = v;
     L = (tid == 0) ? depth + 1 : 32 - __clz(myleaf ^ left);
-    if (sum) publish(0, leafnode, v);
-    if (mn) publish(1, leafnode, v);
     if (L <= bot) {
       const uint32_t prefix = myleaf >> L;
       int lo = 0, hi = tid;  // first index in [0, tid) whose leaf has this prefix: the leader of the group on my left
@@ -827,6 +831,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
     }
   }
+  if (key_valid) Lpos[pos] = L;  // (0 for the losers of a duplicated leaf; positions that hold no item stay unread)
   {
     const unsigned m = __reduce_or_sync(0xffffffffu, (alive && L <= bot) ? (1u << L) : 0u);
     if (lane == 0 && m) atomicOr(&s_lmask, m);
@@ -837,9 +842,10 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
 
   // ---- 5. climb below the cut.  The sibling values of the first kUpdHoist levels are pulled into registers up
   // front (independent shared loads); a level into which somebody handed a value over is re-read after the barrier
-  // that follows the hand-over.  Every parent computed goes straight into its row in a helper's shared memory.
-  const T *io_s = sib + pos;
-  const T *io_m = sib + (size_t)bot * NP + pos;
+  // that follows the hand-over.  The parent computed at level l overwrites the (consumed) sibling slot [l][pos]: the
+  // tile doubles as the staging area the helpers scatter from.
+  T *io_s = sib + pos;
+  T *io_m = sib + (size_t)bot * NP + pos;
   T hs[kUpdHoist], hm[kUpdHoist];
 #pragma unroll
   for (int l = 0; l < kUpdHoist; ++l) {
@@ -864,13 +870,12 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
           }
           vs = tree_op<T, false>(vs, os);          // IEEE addition commutes: operand order is immaterial
           vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+          io_s[(size_t)l * NP] = vs;  // value of node (leaf >> (l + 1))
+          io_m[(size_t)l * NP] = vm;
           if (L == l + 2 && L <= bot) {  // I merge at the next level: hand the value just computed to the leader
             *hand_s = vs;
             *hand_m = vm;
           }
-          const uint32_t parent = leafnode >> (l + 1);
-          if (sum) publish(2 + l, parent, vs);
-          if (mn) publish(2 + bot + l, parent, vm);
         }
       }
       if ((lmask >> (l + 2)) & 1u) __syncthreads();  // somebody handed over: its leader reads it in the next iteration
@@ -884,13 +889,12 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         const T os = io_s[(size_t)l * NP], om = io_m[(size_t)l * NP];
         vs = tree_op<T, false>(vs, os);
         vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+        io_s[(size_t)l * NP] = vs;
+        io_m[(size_t)l * NP] = vm;
         if (L == l + 2 && L <= bot) {
           *hand_s = vs;
           *hand_m = vm;
         }
-        const uint32_t parent = leafnode >> (l + 1);
-        if (sum) publish(2 + l, parent, vs);
-        if (mn) publish(2 + bot + l, parent, vm);
       }
     }
     if ((lmask >> (l + 2)) & 1u) __syncthreads();
@@ -906,7 +910,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     cut_m[node] = vm;
   }
   if (dbg && tid == 0) dbg[12] = (long long)clock64();
-  cluster_arrive_release();  // phase 3: every row is complete -- the helpers scatter them while the top is recomputed
+  cluster_arrive_release();  // phase 3: merge levels + staging tile final -- the helpers scatter while the top is recomputed
   if (dbg && tid == 0) dbg[13] = (long long)clock64();
   __syncthreads();
   {
@@ -977,6 +981,22 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   RLB_TICK(7);
   if (dbg && tid == 0) dbg[32 + 1] = (long long)globaltimer_ns();
   cluster_wait_acquire();  // phase 3 (completes at once: every helper arrived long ago)
+  if (csize == 1) {
+    // without helpers (the whole tree is above the cut, or a plain launch): the leader scatters its own nodes
+    const int Lp = Lpos[tid];
+    const int64_t ix2 = my_ix;
+    if (valid && Lp > 0) {
+      const uint32_t ln = (uint32_t)(capacity + ix2);
+      if (sum) sum[ln] = sraw[tid];
+      if (mn) mn[ln] = sraw[tid];
+      for (int l = 0; l < bot && Lp > l + 1; ++l) {
+        if (sum) sum[ln >> (l + 1)] = sib[(size_t)l * NP + tid];
+        if (mn) mn[ln >> (l + 1)] = sib[((size_t)bot + l) * NP + tid];
+      }
+    }
+  }
+  cluster_arrive_relaxed();  // phase 4
+  cluster_wait_acquire();    // the helpers have finished reading this CTA's shared memory
   if (dbg && tid == 0) dbg[32 + 2] = (long long)globaltimer_ns();
 }
 

@@ -1071,7 +1071,9 @@ class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):
     The start of every slice is drawn with probability proportional to its priority among the steps from which a whole
     slice fits inside the trajectory; the slice then runs ``slice_len`` steps forward and every step carries the start's
     importance weight.  Constructor arguments are those of :class:`PrioritizedSampler` followed by the keyword arguments
-    of :class:`SliceSampler` (``strict_length=True`` and ``span=False`` only; 1-d storages).
+    of :class:`SliceSampler` (``span=False`` only; 1-d storages).  With ``strict_length=False`` the first step of every
+    trajectory stays a legal start however short the trajectory is, and a slice stops where its trajectory stops, so
+    slices may be shorter than ``slice_len`` and the batch smaller than asked (:2863-2871, :2919-2951).
 
     The reference forbids bad starts by zeroing their leaves in the sum tree before each draw and writing them back
     afterwards -- two tree updates of ``n_trajectories * (slice_len - 1)`` items per sample, done index by index on the
@@ -1088,8 +1090,6 @@ class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):
                  trajectories: torch.Tensor | None = None, cache_values: bool = False,
                  truncated_key=("next", "truncated"), strict_length: bool = True, compile=False, span=False,
                  max_priority_within_buffer: bool = False, device=None, semantics: str = "cpu"):
-        if not strict_length:
-            raise NotImplementedError("PrioritizedSliceSampler(strict_length=False) is not supported by the B200 engine")
         SliceSampler.__init__(self, num_slices=num_slices, slice_len=slice_len, end_key=end_key, traj_key=traj_key,
                               cache_values=cache_values, truncated_key=truncated_key, strict_length=strict_length,
                               ends=ends, trajectories=trajectories, compile=compile, span=span)
@@ -1145,7 +1145,10 @@ class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):
             self._masked = torch.empty_like(st.values)
         cap = st.capacity
         self._masked[cap:].copy_(st.values[cap:])                                        # :2910 (vals = tree[idx])
-        be.slice_mask_starts(self._masked, cap, table[1], table[2], n_all, seq_length, storage.shape[0])   # :2911
+        # strict: the last slice_len - 1 steps of a trajectory cannot start a slice (all of a shorter one); loose: the
+        # same but never its FIRST step (:2863-2871 drops the starts from the candidates) -- i.e. one step fewer
+        tail = table[2] if self.strict_length else table[2] - 1
+        be.slice_mask_starts(self._masked, cap, table[1], tail, n_all, seq_length, storage.shape[0])   # :2911
         be.tree_rebuild(self._masked, cap, False)
         dev = st.device
         u = torch.rand(num_slices, device=dev, generator=self._rng, dtype=st._dtype)       # PrioritizedSampler.sample
@@ -1155,9 +1158,18 @@ class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):
             if self.index_ready is None:
                 self.index_ready = torch.cuda.Event()
             self.index_ready.record(torch.cuda.current_stream(dev))
-        info: dict = {"priority_weight": weight.repeat_interleave(seq_length)}            # :2969-2971
+        seq = None
+        if not self.strict_length:
+            # :2919-2951 -- a slice ends with its trajectory: the stop that follows the start (the table is ordered by
+            # stop; past the last one the trajectory wraps and ends at the first stop of the ring)
+            stops = table[1, :n_all]
+            j = torch.searchsorted(stops, starts)
+            ring = storage.shape[0]
+            stop_after = torch.where(j < n_all, stops[j.clamp_max(n_all - 1)], stops[0] + ring)
+            seq = (stop_after - starts + 1).clamp_max(seq_length)
+        info: dict = {"priority_weight": weight.repeat_interleave(seq_length if seq is None else seq)}   # :2969-2971
         # expansion of the starts (:2963-2966), truncated markers and the stored flags of the sampled steps in one
-        # rlb_slice_index launch: every start is a one-entry "trajectory" of exactly seq_length steps, offset 0
+        # rlb_slice_index launch: every start is a one-entry "trajectory" of exactly its slice's steps, offset 0
         contents = storage[:]
         done_all = term_all = None
         if self.truncated_key is not None:
@@ -1166,9 +1178,15 @@ class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):
             done_all, term_all = contents.get(done_key, None), contents.get(terminated_key, None)
         one_byte = lambda t: t is None or (t.element_size() == 1 and t.numel() == t.shape[0] and t.is_contiguous())
         fused = self.truncated_key is not None and one_byte(done_all) and one_byte(term_all)
-        out = be.slice_index(starts, torch.full_like(starts, seq_length), num_slices,
-                             torch.arange(num_slices, device=dev), torch.zeros(num_slices, device=dev), seq_length,
-                             storage.shape[0], **(dict(flags=(done_all, term_all)) if fused else {}))
+        kw = dict(flags=(done_all, term_all)) if fused else {}
+        arange, zeros = torch.arange(num_slices, device=dev), torch.zeros(num_slices, device=dev)
+        if seq is None:
+            out = be.slice_index(starts, torch.full_like(starts, seq_length), num_slices, arange, zeros, seq_length,
+                                 storage.shape[0], **kw)
+        else:
+            ends_at = seq.cumsum(0)
+            out = be.slice_index(starts, seq, num_slices, arange, zeros, seq_length, storage.shape[0], variable=True,
+                                 out_offset=ends_at - seq, total=int(ends_at[-1]), **kw)      # data-dependent batch size
         index, truncated = out[0], out[1]
         if self.truncated_key is not None:
             info[self.truncated_key] = truncated

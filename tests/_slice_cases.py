@@ -90,7 +90,7 @@ def _pslice_scenarios():
             "short_slices": (400, 400, 6, 3, 3), "long_slices": (1000, 1000, 4, 40, 4)}
 
 
-def _ref_pslice_run(R, L, filled, S, T, seed, draws=3):
+def _ref_pslice_run(R, L, filled, S, T, seed, draws=3, strict=True):
     """Run the unmodified PrioritizedSliceSampler; returns done flags, the sum/min leaves it sampled from and, per draw,
     (u, index, weight, truncated)."""
     from unittest import mock
@@ -99,7 +99,7 @@ def _ref_pslice_run(R, L, filled, S, T, seed, draws=3):
     g = torch.Generator().manual_seed(seed)
     done = torch.rand(L, 1, generator=g) < 0.06
     st = R.make_storage({("next", "done"): done}, filled, L, None)
-    ref = m.PrioritizedSliceSampler(L, 0.7, 0.9, num_slices=S, end_key=("next", "done"))
+    ref = m.PrioritizedSliceSampler(L, 0.7, 0.9, num_slices=S, end_key=("next", "done"), strict_length=strict)
     ref._rng = torch.Generator().manual_seed(seed + 100)
     ref.mark_update(torch.arange(filled), storage=st)
     ref.update_priority(torch.arange(filled), torch.rand(filled, generator=g) * 3, storage=st)

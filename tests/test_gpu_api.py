@@ -339,8 +339,10 @@ def test_slice_sampler_buffer_on_device(cuda_backend, strict):
     assert rb.storage._is_full
 
 
-def test_prioritized_slice_sampler_buffer_on_device(cuda_backend):
-    """TensorDictReplayBuffer + PrioritizedSliceSampler on the GPU at a 1M-slot ring: starts are the oracle's for the
+@pytest.mark.parametrize("strict", [True, False])
+def test_prioritized_slice_sampler_buffer_on_device(cuda_backend, strict):
+    """TensorDictReplayBuffer + PrioritizedSliceSampler on the GPU at a 1M-slot ring (strict_length=False: slices stop
+    with their trajectory, the batch shrinks): starts are the oracle's for the
     draws of the buffer's CUDA generator and the device's own leaves; slices stay inside one trajectory; every step
     carries its start's weight; the true priorities are untouched by sampling."""
     from oracle import slice_oracle as so
@@ -350,10 +352,10 @@ def test_prioritized_slice_sampler_buffer_on_device(cuda_backend):
     g = torch.Generator(device=dev()).manual_seed(9)
     rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device=dev()), batch_size=S * T, generator=g,
                                 sampler=PrioritizedSliceSampler(L, 0.6, 0.4, num_slices=S, end_key=("next", "done"),
-                                                                cache_values=True))
+                                                                cache_values=True, strict_length=strict))
     rng = np.random.default_rng(2)
     for n in (600_000, 400_000, 123_456):             # fills the ring, then wraps
-        done = torch.from_numpy(rng.random(n) < 0.01).reshape(n, 1).to(dev())
+        done = torch.from_numpy(rng.random(n) < (0.01 if strict else 0.04)).reshape(n, 1).to(dev())
         rb.extend(TensorDict({"t": torch.arange(n, device=dev()).reshape(n, 1), ("next", "done"): done}, [n]))
         filled = len(rb)
         ix = torch.from_numpy(rng.integers(0, filled, 50_000)).to(dev())
@@ -372,14 +374,18 @@ def test_prioritized_slice_sampler_buffer_on_device(cuda_backend):
             g.set_state(state)
             u = torch.rand(S, device=dev(), generator=g)
             oi, ow, otr, _ = so.prioritized_slice_sample(orc, start, stop, length, seq_length=T, num_slices=S,
-                                                         storage_len=filled, u=u.cpu().numpy())
+                                                         storage_len=filled, u=u.cpu().numpy(), strict_length=strict)
             idx = batch.get("index").reshape(-1).cpu().numpy()
             np.testing.assert_array_equal(idx, oi)
-            np.testing.assert_allclose(batch.get("priority_weight").cpu().numpy(), ow, rtol=2e-6)
+            np.testing.assert_allclose(batch.get("priority_weight").reshape(-1).cpu().numpy(), ow, rtol=2e-6)
             np.testing.assert_array_equal(batch.get(("next", "truncated")).reshape(-1).cpu().numpy(), otr)
-            assert not stored_done[idx.reshape(S, T)[:, :-1]].any()          # no slice crosses a trajectory end
-            w = batch.get("priority_weight").reshape(S, T)
-            assert (w == w[:, :1]).all()
+            if strict:
+                assert not stored_done[idx.reshape(S, T)[:, :-1]].any()          # no slice crosses a trajectory end
+                w = batch.get("priority_weight").reshape(S, T)
+                assert (w == w[:, :1]).all()
+            else:
+                assert len(idx) < S * T                                          # some slice was cut at its trajectory's end
+                assert not stored_done[idx[~otr]].any()
         assert torch.equal(rb.sampler._sum_tree.values, before)
 
 
@@ -534,7 +540,7 @@ def test_slice_sampler_2d_storage_on_device(cuda_backend, mode):
         cursor = rb.storage._last_cursor
         cursor = cursor.stop - 1 if isinstance(cursor, slice) else int(torch.as_tensor(cursor).reshape(-1)[-1])
         st, sp, ln, col = so.traj_table_nd(end=stored_done, at_capacity=rows == Tm, cursor=cursor)
-        strict = mode == "strict"
+        strict = mode != "loose"
         if strict:
             keep = ln >= T
             st, sp, ln, col = st[keep], sp[keep], ln[keep], col[keep]

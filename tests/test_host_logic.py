@@ -546,8 +546,9 @@ def test_slice_sampler_contract(emul):
     assert (t[:, 1:] - t[:, :-1] == 1).all()
 
 
+@pytest.mark.parametrize("strict", [True, False])
 @pytest.mark.parametrize("filled", [400, 250])
-def test_prioritized_slice_sampler_equals_live_reference(emul, ref_samplers, filled):
+def test_prioritized_slice_sampler_equals_live_reference(emul, ref_samplers, filled, strict):
     """PrioritizedSliceSampler in a TensorDictReplayBuffer (kernels emulated) against the UNMODIFIED reference class:
     same starts, slices, per-step weights and flags for the same CPU generator seed, through writes, TD-error
     write-backs and repeated draws."""
@@ -556,7 +557,7 @@ def test_prioritized_slice_sampler_equals_live_reference(emul, ref_samplers, fil
     L, S, T = 400, 8, 10
     g = torch.Generator().manual_seed(0)
     done = torch.rand(L, 1, generator=g) < 0.06
-    kw = dict(num_slices=S, end_key=("next", "done"))
+    kw = dict(num_slices=S, end_key=("next", "done"), strict_length=strict)
     rb = TensorDictReplayBuffer(storage=LazyTensorStorage(L, device="cpu"), batch_size=S * T,
                                 sampler=PrioritizedSliceSampler(L, 0.7, 0.9, **kw),
                                 generator=torch.Generator().manual_seed(2), priority_key="td_error")
@@ -577,13 +578,13 @@ def test_prioritized_slice_sampler_equals_live_reference(emul, ref_samplers, fil
         assert torch.equal(got.get("priority_weight").reshape(-1), want_info["priority_weight"])
         for k in (("next", "truncated"), ("next", "done"), ("next", "terminated")):
             assert torch.equal(got.get(k).reshape(-1), want_info[k].reshape(-1)), k
-        t = got.get("obs").reshape(S, T)
-        assert (t[:, 1:] - t[:, :-1] == 1).all() and not done[:filled][got.get("index").reshape(S, T)[:, :-1]].any()
+        assert torch.equal(got.get("obs").reshape(-1), obs[want_index[0]].reshape(-1))
+        if strict:
+            t = got.get("obs").reshape(S, T)
+            assert (t[:, 1:] - t[:, :-1] == 1).all() and not done[:filled][got.get("index").reshape(S, T)[:, :-1]].any()
     # the true priorities were never altered by sampling
     orc_leaves = torch.tensor([ref._sum_tree[i] for i in range(filled)])
     assert torch.equal(rb.sampler._sum_tree.dump_leaves()[:filled].cpu(), orc_leaves)
-    with pytest.raises(NotImplementedError, match="strict_length=False"):
-        PrioritizedSliceSampler(L, 0.7, 0.9, num_slices=2, strict_length=False)
 
 
 @pytest.mark.parametrize("case", ["end_full", "strict_filter", "loose_variable", "traj_partial"])

@@ -328,22 +328,24 @@ def test_slice_golden_fixture():
             np.testing.assert_array_equal(omask, gt("mask"))
 
 
-def _oracle_pslice(done, sum_leaves, min_leaves, L, filled, S, T, u):
+def _oracle_pslice(done, sum_leaves, min_leaves, L, filled, S, T, u, strict=True):
     from oracle import slice_oracle as so
 
     orc = po.OraclePrioritizedSampler(L, 0.7, 0.9)
     orc._sum_tree.load_leaves(sum_leaves)
     orc._min_tree.load_leaves(min_leaves)
     start, stop, length = so.traj_table(end=done[:filled], at_capacity=filled == L, cursor=None)
-    return so.prioritized_slice_sample(orc, start, stop, length, seq_length=T, num_slices=S, storage_len=filled, u=u)
+    return so.prioritized_slice_sample(orc, start, stop, length, seq_length=T, num_slices=S, storage_len=filled, u=u,
+                                       strict_length=strict)
 
 
+@pytest.mark.parametrize("strict", [True, False])
 @pytest.mark.parametrize("name", sorted(_pslice_scenarios()))
-def test_prioritized_slice_oracle_equals_live_reference(ref_samplers, name):
+def test_prioritized_slice_oracle_equals_live_reference(ref_samplers, name, strict):
     L, filled, S, T, seed = _pslice_scenarios()[name]
-    done, sl, ml, draws = _ref_pslice_run(ref_samplers, L, filled, S, T, seed)
+    done, sl, ml, draws = _ref_pslice_run(ref_samplers, L, filled, S, T, seed, strict=strict)
     for u, index, weight, truncated in draws:
-        oi, ow, otr, _ = _oracle_pslice(done, sl, ml, L, filled, S, T, u)
+        oi, ow, otr, _ = _oracle_pslice(done, sl, ml, L, filled, S, T, u, strict=strict)
         np.testing.assert_array_equal(oi, index)
         np.testing.assert_array_equal(ow, weight)
         np.testing.assert_array_equal(otr, truncated)
