@@ -53,7 +53,7 @@ extern "C" {
 #define RLB_GATHER_BULK 2   /* force bulk-DMA staging wherever a leaf is eligible */
 
 /* bits of the [dev] int32 status word the kernels OR into (optional, may be NULL) */
-#define RLB_STATUS_INDEX_OOB 1    /* gather: an index was outside [-len, len) and was clamped */
+#define RLB_STATUS_INDEX_OOB 1    /* gather: an index outside [-len, len) was clamped; scatter: that write was dropped */
 #define RLB_STATUS_NONPOS_PSUM 2  /* sample: p_sum <= 0  (samplers.py:911-912, CPU-only check there) */
 #define RLB_STATUS_NONPOS_PMIN 4  /* sample: p_min <= 0  (samplers.py:913-914) */
 #define RLB_STATUS_BACKOFF_FAIL 8 /* sample: zero-weight back-off ran below index 0 (samplers.py:940-941) */

@@ -19,8 +19,8 @@
 //     observations): flat (row, vector) units, widest vector the leaf's alignment allows (16/8/4/2/1 B),
 //     4 independent units per thread, streaming cache hints.
 //
-// Index semantics follow torch indexing: negative indices wrap by `len`; out-of-range indices are
-// clamped and reported through the status word (torch would raise IndexError).
+// Index semantics follow torch indexing: negative indices wrap by `len`; out-of-range indices are reported through
+// the status word (torch would raise IndexError) -- a gather reads the clamped row, a scatter drops the write.
 #include "common.cuh"
 #include "tree_range.cuh"
 
@@ -153,7 +153,19 @@ __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams
 #pragma unroll
   for (int k = 0; k < kVecUnroll; ++k) {
     if (ok[k]) {
-      ix[k] = fix_index(ix[k], P.len, P.status);
+      if constexpr (SCATTER && !IMPLICIT) {
+        // a WRITE through an out-of-range index is dropped (and reported), never redirected to slot 0 / len - 1:
+        // clamping would silently overwrite somebody else's transition
+        int64_t w = ix[k] < 0 ? ix[k] + P.len : ix[k];
+        if (w < 0 || w >= P.len) {
+          if (P.status) atomicOr(P.status, RLB_STATUS_INDEX_OOB);
+          ok[k] = false;
+          continue;
+        }
+        ix[k] = w;
+      } else {
+        ix[k] = fix_index(ix[k], P.len, P.status);
+      }
       const int64_t srow = SCATTER ? b[k] * L.ostride : ix[k] * L.stride;
       val[k] = ld_stream(reinterpret_cast<const V *>(L.src + srow) + j[k]);
     }

@@ -262,7 +262,10 @@ class ReplayBuffer:
         with self._replay_lock, self._write_lock:
             index, info = self._sampler.sample(self._storage, batch_size)
             info["index"] = index
-            data = self._storage.get(_storage_index(index, self._storage))
+            # indices a sampler of this engine produced are in range by construction: the unchecked gather
+            six = _storage_index(index, self._storage)
+            trusted = getattr(self._storage, "_get_trusted", None)
+            data = trusted(six) if (trusted is not None and isinstance(six, torch.Tensor)) else self._storage.get(six)
         if not isinstance(index, INT_CLASSES):
             data = self._collate_fn(data)
         return data, info

@@ -688,7 +688,11 @@ class PrioritizedSampler(Sampler):
         self._max_priority_buf = torch.full((1,), float("-inf"), dtype=torch.float32, device=dev)
         self._has_max_priority = False
         self._max_priority_index = None
-        self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        from .storages import DeferredStatus
+
+        self._status_mirror = DeferredStatus(dev)    # asynchronous host mirror: errors surface without a sync
+        self._status = self._status_mirror.word
+        self._status_calls = 0
         self._workspace = None
         self._range_ticket = None
         self._epoch = 0
@@ -743,6 +747,7 @@ class PrioritizedSampler(Sampler):
         if length == 0:
             raise RuntimeError(_EMPTY_STORAGE_ERROR)
         dev = self._sum_tree.device
+        self._poll_status()
         u = self._draw(batch_size, dev)
         index, weight = ops.backend().per_sample(
             self._sum_tree.values, self._min_tree.values, self._max_capacity, self._sum_tree.capacity, length, u,
@@ -775,6 +780,34 @@ class PrioritizedSampler(Sampler):
         # ONE buffer: the sample kernel reads it, the refill that follows on the same stream overwrites it (stream
         # order keeps the two apart), and a captured step therefore reads what its previous replay drew
         return self._u_next
+
+    #: how often ``sample`` starts an asynchronous copy of the device status word (every call would add a small D2H)
+    status_check_every = 16
+
+    def _poll_status(self) -> None:
+        """The deferred-error contract: the CPU reference raises "non-positive p_sum / p_min" and "Failed to find a
+        suitable index" inside the offending ``sample`` (samplers.py:910-914, :940-941).  Here the kernel ORs a bit into a
+        device word; every ``status_check_every``-th eager ``sample`` mirrors it to pinned host memory asynchronously and
+        a LATER ``sample`` raises once the copy has landed -- no synchronisation on the hot path (``check_status()``
+        synchronises and raises at once; captured steps never poll)."""
+        mirror = getattr(self, "_status_mirror", None)
+        if mirror is None:
+            return
+        bits = mirror.poll()
+        if bits:
+            self._raise_status(bits)
+        self._status_calls += 1
+        if self._status_calls % self.status_check_every == 0:
+            mirror.arm()
+
+    @staticmethod
+    def _raise_status(st: int) -> None:
+        if st & ops.STATUS_NONPOS_PSUM:
+            raise RuntimeError("non-positive p_sum")
+        if st & ops.STATUS_NONPOS_PMIN:
+            raise RuntimeError("non-positive p_min")
+        if st & ops.STATUS_BACKOFF_FAIL:
+            raise RuntimeError("Failed to find a suitable index")
 
     def check_status(self) -> None:
         """Synchronise and raise what the CPU reference raises eagerly (samplers.py:910-914,940-941)."""

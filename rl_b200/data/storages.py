@@ -28,6 +28,47 @@ from .tensordict_lite import TensorDict, is_tensor_collection
 from .utils import INT_CLASSES, _is_int
 
 
+class DeferredStatus:
+    """A device status word the kernels OR error bits into, mirrored to pinned host memory ASYNCHRONOUSLY: ``poll`` never
+    synchronises -- it reports bits whose copy has already completed -- so an error raised by the reference immediately
+    (IndexError, "non-positive p_sum", ...) surfaces here on a later call of the same object.  ``check`` synchronises."""
+
+    def __init__(self, device):
+        self.word = torch.zeros(1, dtype=torch.int32, device=device)
+        self._cuda = self.word.is_cuda
+        self._host = torch.zeros(1, dtype=torch.int32).pin_memory() if self._cuda else self.word
+        self._evt = None
+
+    def arm(self) -> None:
+        """Start mirroring the current bits (no-op under CUDA-graph capture and on CPU)."""
+        if not self._cuda or torch.cuda.is_current_stream_capturing():
+            return
+        self._host.copy_(self.word, non_blocking=True)
+        if self._evt is None:
+            self._evt = torch.cuda.Event()
+        self._evt.record()
+
+    def poll(self) -> int:
+        if not self._cuda:
+            bits = int(self.word)
+            self.word.zero_()
+            return bits
+        if self._evt is None or not self._evt.query():
+            return 0
+        bits = int(self._host)
+        if bits:
+            self._host.zero_()
+            self.word.zero_()
+        return bits
+
+    def check(self) -> int:
+        bits = int(self.word.item())
+        self.word.zero_()
+        if self._cuda:
+            self._host.zero_()
+        return bits
+
+
 # ----------------------------------------------------------------------------------------------------
 # leaf flattening for Tensor | TensorDict-like | pytree (dict / tuple / list of tensors)
 # ----------------------------------------------------------------------------------------------------
@@ -484,8 +525,11 @@ class TensorStorage(Storage):
             if cursor.ndim > 1:
                 raise RuntimeError("tensor cursors must be one-dimensional")
         cursor = cursor.to(stores[0].device)
+        st = self._index_status()
         ops.backend().scatter(stores, [self._cast(d, s) for d, s in zip(leaves, stores)], cursor,
-                              stores[0].shape[0])
+                              stores[0].shape[0], status=None if st is None else st.word)
+        if st is not None:
+            st.arm()
 
     # ---- reads -------------------------------------------------------------------------------------
     def _linear_index(self, index: tuple) -> torch.Tensor:
@@ -497,6 +541,31 @@ class TensorStorage(Storage):
             ix = torch.as_tensor(ix, dtype=torch.long, device=self._leaves[0].device)
             lin = ix if lin is None else lin * ts[d] + ix
         return lin
+
+    def _index_status(self):
+        """The status word of user-facing tensor indexing (on by default on CUDA storages).  Polling it first raises --
+        one call late, without a sync -- the IndexError torch indexing would have raised at once."""
+        if self._status is False:
+            return None
+        if self._status is None:
+            dev = self._leaves[0].device
+            if dev.type != "cuda":
+                self._status = False
+                return None
+            self._status = DeferredStatus(dev)
+        if self._status.poll() & ops.STATUS_INDEX_OOB:
+            raise IndexError("index out of range in an earlier tensor-indexed read / write of this storage "
+                             "(reads returned the clamped row, writes were dropped)")
+        return self._status
+
+    def _get_trusted(self, index: torch.Tensor):
+        """``get`` for indices a sampler of this engine produced (in range by construction): no status bookkeeping."""
+        if self.ndim > 1 or not (isinstance(index, torch.Tensor) and index.ndim == 1 and index.dtype == torch.int64
+                                 and index.device == self._leaves[0].device):
+            return self.get(index)
+        if self._plan is None:
+            self._plan = ops.backend().gather_plan(self._leaves)
+        return unflatten_data(self._plan.run(index, self._len_along_dim0), self._spec, index.shape)
 
     def get(self, index):
         if not self.initialized:
@@ -514,7 +583,10 @@ class TensorStorage(Storage):
             lin = self._linear_index(index)
             leaves = [leaf.flatten(0, self.ndim - 1) for leaf in self._leaves]
             length = n0 * self._total_shape[1:].numel()
-            out = be.gather(leaves, lin.reshape(-1), length, status=self._status)
+            st = self._index_status()
+            out = be.gather(leaves, lin.reshape(-1), length, status=None if st is None else st.word)
+            if st is not None:
+                st.arm()
             out = [o.reshape(*lin.shape, *o.shape[1:]) for o in out]
             return unflatten_data(out, self._spec, lin.shape)
         if not (isinstance(index, torch.Tensor) and index.dtype == torch.int64 and index.device == self._leaves[0].device):
@@ -528,21 +600,26 @@ class TensorStorage(Storage):
             return unflatten_data(out, self._spec, out[0].shape[: index.ndim + self.ndim - 1])
         if self._plan is None:
             self._plan = be.gather_plan(self._leaves)
+        st = self._index_status()
+        word = None if st is None else st.word
         if index.ndim == 1:
-            return unflatten_data(self._plan.run(index, n0, status=self._status), self._spec, index.shape)
-        out = self._plan.run(index.reshape(-1), n0, status=self._status)
-        out = [o.reshape(*index.shape, *o.shape[1:]) for o in out]
+            out = self._plan.run(index, n0, status=word)
+        else:
+            out = self._plan.run(index.reshape(-1), n0, status=word)
+            out = [o.reshape(*index.shape, *o.shape[1:]) for o in out]
+        if st is not None:
+            st.arm()
         return unflatten_data(out, self._spec, index.shape)
 
     def enable_index_check(self, enabled: bool = True) -> None:
-        """Opt-in IndexError parity: kernels record out-of-range indices in a device word that
-        ``check_index_status`` reads (one sync) -- torch.index would have raised immediately."""
-        self._status = torch.zeros(1, dtype=torch.int32, device=self.device) if enabled else None
+        """IndexError parity for tensor indices (ON by default on CUDA): kernels record out-of-range indices in a device
+        word; the next tensor-indexed call of this storage polls its asynchronous host mirror and raises, and
+        ``check_index_status`` synchronises and raises now."""
+        self._status = None if enabled else False
 
     def check_index_status(self) -> None:
-        if self._status is not None and int(self._status.item()) & ops.STATUS_INDEX_OOB:
-            self._status.zero_()
-            raise IndexError("index out of range in storage gather")
+        if isinstance(self._status, DeferredStatus) and self._status.check() & ops.STATUS_INDEX_OOB:
+            raise IndexError("index out of range in storage gather / scatter")
 
     def __len__(self) -> int:
         return self._len

@@ -102,10 +102,13 @@ class GAE(nn.Module):
         return [self.tensor_keys.advantage, self.tensor_keys.value_target]
 
     def _scalars(self, dtype: torch.dtype):
-        # one host read of the 0-d buffers per dtype, at first use; forward() itself stays sync-free
-        if dtype not in self._scalar_cache:
-            self._scalar_cache[dtype] = gae_scalars(self.gamma.cpu(), self.lmbda.cpu(), dtype)
-        return self._scalar_cache[dtype]
+        # one host read of the 0-d buffers per dtype; forward() itself stays sync-free afterwards.  The cache is keyed on
+        # the buffers' version counters and identities, so load_state_dict / .fill_() / annealing the discount (all
+        # in-place or re-assignments) are picked up, as in the reference, which reads the buffers on every call
+        key = (dtype, id(self.gamma), self.gamma._version, id(self.lmbda), self.lmbda._version)
+        if self._scalar_cache.get("key") != key:
+            self._scalar_cache = {"key": key, "value": gae_scalars(self.gamma.cpu(), self.lmbda.cpu(), dtype)}
+        return self._scalar_cache["value"]
 
     def _get_time_dim(self, time_dim, data) -> int:
         # index of the time dimension among the tensordict's batch dims; the last one by default
@@ -154,15 +157,18 @@ class GAE(nn.Module):
         terminated = tensordict.get(_nk("next", tk.terminated), None)
         if terminated is None:
             terminated = done
+        gamma = None
+        if steps is not None:
+            # n-step transitions: gamma ** steps_to_next_obs, one discount per step (advantages.py:1576-1578) -- computed
+            # BEFORE the auto-reset bootstrap below, which uses it too (:1615-1618)
+            gamma = self.gamma.to(reward.device) ** steps.view_as(reward)
         if self.auto_reset_env:
             truncated = tensordict.get(("next", "truncated"))
-            reward = reward + self.gamma.to(reward.device) * value * truncated
+            reward = reward + (self.gamma.to(reward.device) if gamma is None else gamma) * value * truncated
             terminated = done
         td = self._get_time_dim(time_dim, tensordict)
         if steps is not None:
-            # n-step transitions: gamma ** steps_to_next_obs, one discount per step (advantages.py:1576-1578) --
             # the per-step form of the scan (rlb_affine_scan)
-            gamma = self.gamma.to(reward.device) ** steps.view_as(reward)
             adv, value_target = _gae_impl(gamma, self.lmbda.to(reward.device), value, next_value, reward, done,
                                           terminated, td)
         else:
@@ -295,6 +301,7 @@ class TDLambdaEstimator(_ReturnEstimator):
                                              time_dim=time_dim)
 
     def _lmbda_host(self) -> float:
-        if "lmbda" not in self._scalar_cache:           # one host read, at first use
-            self._scalar_cache["lmbda"] = float(self.lmbda.cpu())
+        key = ("lmbda", id(self.lmbda), self.lmbda._version)   # one host read per value of the buffer
+        if self._scalar_cache.get("lmbda_key") != key:
+            self._scalar_cache["lmbda_key"], self._scalar_cache["lmbda"] = key, float(self.lmbda.cpu())
         return self._scalar_cache["lmbda"]

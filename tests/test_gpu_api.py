@@ -161,12 +161,30 @@ def test_index_check_mode(cuda_backend):
     from rl_b200.data import TensorStorage
 
     st = TensorStorage(torch.arange(100.0, device=dev()).reshape(50, 2), device=dev())
-    st.enable_index_check()
-    st.get(torch.tensor([0, 49], device=dev()))
+    st.get(torch.tensor([0, 49], device=dev()))            # the status word is on by default for tensor indices
     st.check_index_status()
-    st.get(torch.tensor([0, 50], device=dev()))
+    out = st.get(torch.tensor([0, 50], device=dev()))      # out of range: reads the clamped row ...
+    assert torch.equal(out[1], st.get(torch.tensor([49], device=dev()))[0])
+    with pytest.raises(IndexError):
+        st.check_index_status()                            # ... and the synchronising check says so
+    # deferred form: no sync anywhere -- a LATER tensor-indexed call of the same storage raises
+    st.get(torch.tensor([0, 77], device=dev()))
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError, match="earlier"):
+        st.get(torch.tensor([1], device=dev()))
+    # an out-of-range WRITE is dropped, never redirected onto another slot
+    before = st.get(slice(None)).clone()
+    st.set(torch.tensor([3, 50, -51], device=dev()), torch.full((3, 2), -1.0, device=dev()))
+    after = st.get(slice(None))
+    assert torch.equal(after[3], torch.full((2,), -1.0, device=dev()))
+    keep = torch.ones(50, dtype=torch.bool, device=dev())
+    keep[3] = False
+    assert torch.equal(after[keep], before[keep])
     with pytest.raises(IndexError):
         st.check_index_status()
+    st.enable_index_check(False)
+    st.get(torch.tensor([0, 99], device=dev()))
+    st.check_index_status()
 
 
 def test_c5_shaped_gather_and_writeback(cuda_backend):
@@ -562,3 +580,31 @@ def test_slice_sampler_2d_storage_on_device(cuda_backend, mode):
             np.testing.assert_array_equal(batch.get(("next", "done")).reshape(-1).cpu().numpy(), stored_done[oi, ocol] | otr)
             want_obs = full.get("obs")[torch.from_numpy(oi).to(dev), torch.from_numpy(ocol).to(dev)]
             assert torch.equal(batch.get("obs").reshape(-1), want_obs.reshape(-1))
+
+
+def test_sampler_status_surfaces_without_sync(cuda_backend):
+    """the CPU reference raises "non-positive p_sum" inside sample(); here the kernel sets a bit and a LATER
+    sample() raises once the asynchronous host mirror of the status word has landed (check_status() raises at once)."""
+    from rl_b200.data import PrioritizedSampler
+
+    class _St:
+        ndim, shape, device = 1, (100,), torch.device("cuda", 0)
+
+        def __len__(self):
+            return 100
+
+    smp = PrioritizedSampler(100, 0.6, 0.4, device=torch.device("cuda", 0))
+    smp._rng = torch.Generator(device="cuda").manual_seed(0)
+    smp.status_check_every = 1
+    smp.sample(_St(), 8)                 # the trees are empty: p_sum == 0
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="non-positive p_sum"):
+        for _ in range(3):               # the copy armed by one call is seen by a later one
+            smp.sample(_St(), 8)
+            torch.cuda.synchronize()
+    smp.update_priority(torch.arange(100, device="cuda"), torch.rand(100, device="cuda") + 0.1)
+    smp.check_status() if False else smp._status.zero_()
+    for _ in range(3):
+        smp.sample(_St(), 8)
+        torch.cuda.synchronize()
+    smp.check_status()

@@ -1050,3 +1050,27 @@ def test_slice_sampler_2d_storage_equals_live_reference(emul, ref_samplers, mode
                 for k, v in want_info.items():
                     assert torch.equal(got.get(k).reshape(v.shape), v), (mode, trial, k)
                 assert torch.equal(got.get("obs").reshape(-1), ring["obs"][want_index].reshape(-1))
+
+
+def test_gae_module_rereads_annealed_discount(emul):
+    """GAE caches its scalar discounts for a sync-free forward, but in-place changes of the buffers (annealing,
+    load_state_dict) must be seen: the cache is keyed on the buffers' version counters."""
+    from rl_b200.objectives.value import GAE, vec_generalized_advantage_estimate
+
+    td = _gae_td(3, 12, seed=4)
+    mod = GAE(gamma=0.99, lmbda=0.95, value_network=None)
+    out1 = mod(td.clone()).get("advantage")
+    mod.gamma.fill_(0.5)
+    mod.lmbda.mul_(0.5)
+    out2 = mod(td.clone()).get("advantage")
+    want, _ = vec_generalized_advantage_estimate(0.5, 0.475, td.get("state_value"), td.get(("next", "state_value")),
+                                                 td.get(("next", "reward")), td.get(("next", "done")),
+                                                 td.get(("next", "terminated")), time_dim=-2)
+    assert not torch.allclose(out1, out2)
+    torch.testing.assert_close(out2, want, rtol=1e-6, atol=1e-6)
+    sd = GAE(gamma=0.9, lmbda=0.8, value_network=None).state_dict()
+    mod.load_state_dict(sd)
+    want3, _ = vec_generalized_advantage_estimate(0.9, 0.8, td.get("state_value"), td.get(("next", "state_value")),
+                                                  td.get(("next", "reward")), td.get(("next", "done")),
+                                                  td.get(("next", "terminated")), time_dim=-2)
+    torch.testing.assert_close(mod(td.clone()).get("advantage"), want3, rtol=1e-6, atol=1e-6)
