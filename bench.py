@@ -296,6 +296,23 @@ def write_path_probe(dev, rb, g, hbm_peak: float) -> dict | None:
         return {"error": f"{type(e).__name__}: {e}"[:200]}
 
 
+def steps_per_graph(k: int) -> int:
+    """Consecutive steps captured into ONE graph.  A graph replay costs ~8 us on its own (torch refreshes the Philox
+    seed / offset of the registered generator with two small fill kernels, then the launch itself), so a training loop
+    that captures a few steps at a time pays it once per group; the timed region still runs EXACTLY `k` steps."""
+    for spg in (4, 2):
+        if k % spg == 0:
+            return spg
+    return 1
+
+
+def timed_groups(graphs, spg: int, steps: int, warmup: int, sync_all) -> float:
+    """ms per STEP over exactly `steps` steps, issued as steps / spg replays of graphs holding spg steps each."""
+    n_g = len(graphs)
+    launches, warm = steps // spg, -(-warmup // spg)
+    return timed(lambda i: graphs[i % n_g](), launches, warm, sync_all) / spg
+
+
 def graph_us(fn_list, dev, reps: int = 5) -> float:
     """Median device time (us) of ONE call, measured as a CUDA-graph replay of all callables in `fn_list` back to back
     on one stream (CUDA events around the replay; no host in the loop)."""
@@ -561,21 +578,28 @@ def run_single(args, dev) -> dict:
     clocks = ClockSampler(dev.index or 0)
     ms_eager = timed(lambda i: eager_steps[i % R](), args.steps, args.warmup, sync_all)
 
-    # ---- (2) the same steps captured once into CUDA graphs (one per GAE input set) and replayed
+    # ---- (2) the same steps captured into CUDA graphs -- `spg` consecutive steps (each with its own GAE input set) per
+    # graph -- and replayed
     graphs, graph_err, ms_graph = None, None, None
+    spg = steps_per_graph(args.steps)
     try:
         gen = rb.sampler._rng
-        graphs = [CudaGraphStep(st, generators=[gen], warmup=1) for st in steps]
-        ms_graph = timed(lambda i: graphs[i % R](), args.steps, args.warmup, sync_all)
+        groups = [steps[i:i + spg] for i in range(0, R - R % spg, spg)]
+        graphs = [CudaGraphStep((lambda grp=grp: [st() for st in grp]), generators=[gen], warmup=1) for grp in groups]
+        ms_graph = timed_groups(graphs, spg, args.steps, args.warmup, sync_all)
         # a longer replay run of the same graphs (the driver's --steps 20 makes the timed region < 1 ms)
-        ms_graph_long = timed(lambda i: graphs[i % R](), max(args.steps, 400), 5, sync_all)
+        ms_graph_long = timed_groups(graphs, spg, max(args.steps, 400) // spg * spg, 8, sync_all)
+        # and the one-step-per-graph figure, for comparison with round 1
+        single = [CudaGraphStep(st, generators=[gen], warmup=1) for st in steps[:8]]
+        ms_graph_single = timed(lambda i: single[i % 8](), 200, 8, sync_all)
+        del single
     except Exception as err:
         import traceback
 
         graph_err = f"{type(err).__name__}: {err}"[:300]
         print(f"[bench] CUDA-graph path failed, falling back to eager: {graph_err}\n"
               + "".join(traceback.format_exc().splitlines(True)[-6:]), file=sys.stderr, flush=True)
-        graphs, ms_graph, ms_graph_long = None, None, None
+        graphs, ms_graph, ms_graph_long, ms_graph_single = None, None, None, None
         torch.cuda.synchronize()
         fresh = torch.Generator(device=dev).manual_seed(4242)
         rb.set_rng(fresh)
@@ -616,8 +640,9 @@ def run_single(args, dev) -> dict:
     ms = ms_graph if ms_graph is not None else ms_eager
     n_leaves = len(rb.storage._leaves)
     cfg = make_config(1)
-    detail = {"n_leaves": n_leaves,
-              "launch": "cuda_graph replay of the public-API step" if ms_graph is not None else "eager python API"}
+    detail = {"n_leaves": n_leaves, "steps_per_graph": spg if ms_graph is not None else None,
+              "launch": (f"cuda_graph replay of the public-API step, {spg} consecutive steps per graph"
+                         if ms_graph is not None else "eager python API")}
     result = {
         "metric": METRIC, "value": round(TRANSITIONS_PER_STEP / (ms * 1e-3), 1), "unit": "transitions/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
@@ -630,6 +655,7 @@ def run_single(args, dev) -> dict:
         "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
                       "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),
                       "graph_ms_per_step_long_run": None if ms_graph_long is None else round(ms_graph_long, 5),
+                      "graph_ms_per_step_one_step_per_graph": None if ms_graph_single is None else round(ms_graph_single, 5),
                       "graph_error": graph_err,
                       "eager_value": round(TRANSITIONS_PER_STEP / (ms_eager * 1e-3), 1),
                       "eager_sample_us": round(ms_sample * 1e3, 2), "eager_update_priority_us": round(ms_update * 1e3, 2),
@@ -911,9 +937,23 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
         if not nvlink:
             raise RuntimeError("NVLink transport unavailable (symmetric memory): the NCCL all-gather cannot be captured with the step")
         gen = rb.sampler._rng
-        graphs = [CudaGraphStep(make_step(i), generators=[gen], warmup=1) for i in range(R)]
-        ms_graph = timed(lambda i: graphs[i % R](), args.steps, max(args.warmup, N_BUFFERS), sync_all)
-        ms_graph_long = timed(lambda i: graphs[i % R](), max(args.steps, 200), N_BUFFERS, sync_all)
+        spg = N_BUFFERS   # one graph = one turn over the receive slots; the exchanges run beside the compute chain
+
+        def make_group(g0: int):
+            fns = [make_step(g0 + k) for k in range(spg)]
+
+            def group():
+                outs = [fn() for fn in fns]
+                rb.join_exchange()      # the exchange stream joins the capture once per graph, not once per step
+                return outs
+
+            return group
+
+        if args.steps % spg:
+            raise RuntimeError(f"--steps must be a multiple of {spg} with the pipelined NVLink exchange")
+        graphs = [CudaGraphStep(make_group(g0), generators=[gen], warmup=1) for g0 in range(0, R, spg)]
+        ms_graph = timed_groups(graphs, spg, args.steps, max(args.warmup, spg), sync_all)
+        ms_graph_long = timed_groups(graphs, spg, max(args.steps, 200) // spg * spg, spg, sync_all)
         torch.cuda.synchronize()
         rb.check_exchange()
     except Exception as err:
@@ -978,8 +1018,10 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
                  "flag release/acquire closes the exchange; sample() returns the previous draw" if nvlink
                  else "NCCL all-gather (eager)")
     cfg = make_config(world)
-    detail = {"n_leaves": n_leaves, "transport": transport,
-              "launch": ("cuda_graph replay of the public-API step" if ms_graph is not None else "eager python API")}
+    detail = {"n_leaves": n_leaves, "transport": transport, "steps_per_graph": N_BUFFERS if ms_graph is not None else None,
+              "launch": (f"cuda_graph replay of the public-API step, {N_BUFFERS} consecutive steps per graph; the exchange "
+                         "of a draw runs on its own stream beside the next steps" if ms_graph is not None
+                         else "eager python API")}
     result = {
         "metric": METRIC, "value": round(per_step / (ms * 1e-3), 1), "unit": "transitions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
@@ -1053,11 +1095,17 @@ def sharded_workload(name: str, dev, rank: int, world: int, steps: int, be) -> d
     gen = rb.sampler._rng
     out = {}
     if nvlink:
-        graphs = [CudaGraphStep(make_step(i), generators=[gen], warmup=1) for i in range(N_BUFFERS)]
-        ms = timed(lambda i: graphs[i % N_BUFFERS](), steps, 2 * N_BUFFERS, sync_all)
+        def group():
+            outs = [make_step(k)() for k in range(N_BUFFERS)]
+            rb.join_exchange()
+            return outs
+
+        graphs = [CudaGraphStep(group, generators=[gen], warmup=1)]
+        steps = steps // N_BUFFERS * N_BUFFERS
+        ms = timed_groups(graphs, N_BUFFERS, steps, 2 * N_BUFFERS, sync_all)
         torch.cuda.synchronize()
         rb.check_exchange()
-        launch = "cuda_graph replay"
+        launch = f"cuda_graph replay, {N_BUFFERS} steps per graph"
     else:
         eager = make_step(0)
         ms = timed(lambda i: eager(), steps, 4, sync_all)

@@ -51,14 +51,22 @@ def make_step(slot):
 
 
 R = bench.N_BUFFERS
-graphs = [CudaGraphStep(make_step(i), generators=[rb.sampler._rng], warmup=1) for i in range(R)]
-for i in range(3 * R):
-    graphs[i % R]()
+
+
+def group():
+    outs = [make_step(k)() for k in range(R)]
+    rb.join_exchange()
+    return outs
+
+
+graphs = [CudaGraphStep(group, generators=[rb.sampler._rng], warmup=1)]
+for i in range(6):
+    graphs[0]()
 torch.cuda.synchronize()
 dist.barrier()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for i in range(2 * R):
-        graphs[i % R]()
+    for i in range(2):
+        graphs[0]()
     torch.cuda.synchronize()
 dist.barrier()
 if rank == 0:

@@ -106,16 +106,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the waiting thread is parked by the hardware (up to the hint, in ns) instead of
+  // spinning through the issue slots of the warps that share its scheduler -- the row mover's elected lanes wait for
+  // microseconds at a time next to the latency-critical tree kernels
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "RLB_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra RLB_DONE_%=;\n"
       "bra RLB_WAIT_%=;\n"
       "RLB_DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(20000u)
       : "memory");
 }
 // global -> shared bulk copy; completion (bytes) is signalled on `bar`.  16-B aligned, size % 16 == 0.

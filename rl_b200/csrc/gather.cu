@@ -48,6 +48,10 @@ constexpr uint32_t kChunk = RLB_GATHER_CHUNK;    // bytes per stage
 constexpr int kVecUnroll = 4;                    // units per thread per tile (vector role)
 constexpr int kTileUnits = kGatherThreads * kVecUnroll;
 constexpr int64_t kBulkMinRowBytes = 4096;       // AUTO mode: rows at least this wide use the DMA role
+#ifndef RLB_GATHER_PEER_RESERVED_SMS
+#define RLB_GATHER_PEER_RESERVED_SMS 20
+#endif
+constexpr int kPeerReservedSms = RLB_GATHER_PEER_RESERVED_SMS;  // SMs a peer-broadcasting launch leaves free
 
 struct GatherLeaf {
   const uint8_t *src;
@@ -484,8 +488,11 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
   RLB_REQUIRE(index, RLB_EINVAL, "%s: null argument", who);
   GatherParams P;
   int vec_ctas = 0;
+  // with NVLink peers the launch is bound by the wire, not by HBM: leave some SMs to whatever runs beside the
+  // exchange (the priority write-back's cluster, the next draw) instead of parking a 161 KB CTA on every one
+  const int reserved = n_peers > 1 ? kPeerReservedSms : 0;
   int rc = plan_rows<SCATTER>(P, vec_ctas, src, dst, row_bytes, stride, ostride, peer_delta, n_peers, n_leaves, index,
-                              0, B, len, mode, status, who);
+                              0, B, len, mode, status, who, reserved);
   if (rc) return rc;
   const size_t smem = P.bulk_ctas > 0 ? kBulkSmemBytes : 0;
   static bool attr_set_dev[64] = {};  // function attributes are per device

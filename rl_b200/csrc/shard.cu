@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(1024) shard_pack_kernel(uint8_t *rows, int64_t
     }
   }
   if (!flags) return;
-  __threadfence_system();  // my trailer stores are performed system-wide ...
-  __syncthreads();         // ... and so are everybody else's, before any flag goes out
+  // every thread's trailer stores happen-before the barrier; the releasing store below (system scope, issued by a
+  // thread that passed the barrier) is cumulative over them -- the grid-sync pattern: bar.sync, then ONE fence
+  __syncthreads();
   if ((int)threadIdx.x < peers.n) {
     unsigned long long *dst =
         reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(flags) + peers.delta[threadIdx.x]) + rank;

@@ -791,8 +791,8 @@ class PrioritizedSampler(Sampler):
         a LATER ``sample`` raises once the copy has landed -- no synchronisation on the hot path (``check_status()``
         synchronises and raises at once; captured steps never poll)."""
         mirror = getattr(self, "_status_mirror", None)
-        if mirror is None:
-            return
+        if mirror is None or (mirror._cuda and torch.cuda.is_current_stream_capturing()):
+            return    # (an event query would invalidate a capture)
         bits = mirror.poll()
         if bits:
             self._raise_status(bits)

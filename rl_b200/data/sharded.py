@@ -140,6 +140,12 @@ class ShardedPrioritizedReplayBuffer:
         self._cur = None         # the draw in flight: dict(send, recv, bs, nvlink)
         self._pending = None     # pipelined: the draw the NEXT sample() returns
         self._fin_stream = None
+        self._x_stream = None    # the exchange (gather + NVLink broadcast + publish) runs here, beside the caller's stream
+        self._x_done = {}        # slot -> event: that slot's previous exchange has left this GPU
+        self._res = {}           # slot -> persistent (index, weight, leaf, psum_pmin) of the draw using it
+        #: nvlink transport: issue the exchange on an internal stream so that the caller's stream goes straight on to
+        #: the priority write-back / the next draw (the trees do not depend on it).  ``join_exchange()`` joins it.
+        self.overlap_exchange = True
         self.local_index = None  # local indices of this rank's last draw
         #: set to True to have ``local_draw`` record ``index_ready`` (a CUDA event) right after the tree kernel: work
         #: that only needs the sampled indices (``update_local_priority`` on a side stream) overlaps the exchange
@@ -149,6 +155,7 @@ class ShardedPrioritizedReplayBuffer:
     # ---- writes: every rank feeds its own shard (data-parallel collectors) --------------------------------
     def extend(self, data) -> torch.Tensor:
         """Writes ``data`` into this rank's shard; returns the GLOBAL indices of the written slots."""
+        self.join_exchange()   # an exchange still in flight reads the rows this write may replace
         local = self.local.extend(data)
         return local + self.rank * self.shard_capacity
 
@@ -218,24 +225,62 @@ class ShardedPrioritizedReplayBuffer:
         else:
             send = torch.empty((b_loc, lay.row), dtype=torch.uint8, device=dev)
             recv = torch.empty((batch_size, lay.row), dtype=torch.uint8, device=dev) if self.world > 1 else send
+        slot_i = (self._draws if slot is None else slot) % self.n_buffers
+        res = self._res.get(slot_i)
+        if res is None or res[0].numel() != b_loc or res[0].device != dev:
+            # persistent results of the tree kernel, one set per receive slot: they are read by the exchange on its own
+            # stream and by write-backs on side streams, so they must not be caching-allocator temporaries
+            dt = smp._sum_tree._dtype
+            res = self._res[slot_i] = (torch.empty(b_loc, dtype=torch.int64, device=dev),
+                                       torch.empty(b_loc, dtype=torch.float32, device=dev),
+                                       torch.empty(b_loc, dtype=dt, device=dev), torch.empty(2, dtype=dt, device=dev))
+        side = nv is not None and self.overlap_exchange and dev.type == "cuda"
+        capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
         with self.local._replay_lock:
+            if side and not capturing and slot_i in self._x_done:
+                # the exchange that used this slot's buffers last must have left the GPU (eager mode; a captured region
+                # must not come back to a slot before join_exchange())
+                torch.cuda.current_stream(dev).wait_event(self._x_done[slot_i])
             u = torch.rand(b_loc, device=dev, generator=smp._rng, dtype=smp._sum_tree._dtype)
             idx, _, leaf, pp = be.per_sample(smp._sum_tree.values, smp._min_tree.values, smp._max_capacity,
                                              smp._sum_tree.capacity, length, u, smp._beta, smp._semantics == "cpu",
-                                             status=smp._status, want_aux=True)
+                                             status=smp._status, out=res)
             if self.record_index_event and dev.type == "cuda":
                 if self.index_ready is None:
                     self.index_ready = torch.cuda.Event()
                 self.index_ready.record(torch.cuda.current_stream(dev))
-            # with `peers` the rows are written into every rank's receive buffer by this very launch
-            be.gather(st._leaves, idx, length, out=lay.leaf_views(send), peer_delta=peers)
-            # trailers; with `flags`: "my rows of this draw are in your buffer" to every rank (release)
-            be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity, peer_delta=peers,
-                          flags=flags, seq_counter=None if flags is None else self._ctr[0:1], rank=self.rank)
+
+            def exchange_kernels():
+                # with `peers` the rows are written into every rank's receive buffer by this very launch
+                be.gather(st._leaves, idx, length, out=lay.leaf_views(send), peer_delta=peers)
+                # trailers; with `flags`: "my rows of this draw are in your buffer" to every rank (release)
+                be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity, peer_delta=peers,
+                              flags=flags, seq_counter=None if flags is None else self._ctr[0:1], rank=self.rank)
+
+            if side:
+                if self._x_stream is None:
+                    self._x_stream = torch.cuda.Stream(dev)
+                cur = torch.cuda.current_stream(dev)
+                self._x_stream.wait_stream(cur)
+                with torch.cuda.stream(self._x_stream):
+                    exchange_kernels()
+                    if not capturing:
+                        ev = self._x_done.get(slot_i)
+                        if ev is None:
+                            ev = self._x_done[slot_i] = torch.cuda.Event()
+                        ev.record(self._x_stream)
+            else:
+                exchange_kernels()
         self.local_index = idx
         self._draws += 1
         self._cur = {"send": send, "recv": recv, "bs": batch_size, "nvlink": nv is not None, "exchanged": False}
         return send
+
+    def join_exchange(self) -> None:
+        """Make the current stream wait for every exchange issued so far (needed before the storage is written to, and
+        before a CUDA-graph capture that issued draws ends).  A no-op when nothing runs beside the caller's stream."""
+        if self._x_stream is not None:
+            torch.cuda.current_stream(self._x_stream.device).wait_stream(self._x_stream)
 
     def exchange(self) -> torch.Tensor:
         """nccl: the ONE collective, an all-gather of the packed local draws.  nvlink: nothing to issue -- the rows

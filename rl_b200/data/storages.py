@@ -553,6 +553,8 @@ class TensorStorage(Storage):
                 self._status = False
                 return None
             self._status = DeferredStatus(dev)
+        if self._status._cuda and torch.cuda.is_current_stream_capturing():
+            return self._status    # (an event query would invalidate a capture)
         if self._status.poll() & ops.STATUS_INDEX_OOB:
             raise IndexError("index out of range in an earlier tensor-indexed read / write of this storage "
                              "(reads returned the clamped row, writes were dropped)")

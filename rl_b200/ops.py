@@ -239,14 +239,21 @@ class CudaBackend:
 
     # -- fused sampler arithmetic ------------------------------------------------------------------
     def per_sample(self, sum_tree, min_tree, size: int, capacity: int, length: int, u: torch.Tensor, beta: float,
-                   cpu_semantics: bool, status: torch.Tensor | None = None, want_aux: bool = False):
+                   cpu_semantics: bool, status: torch.Tensor | None = None, want_aux: bool = False,
+                   out: tuple | None = None):
+        """``out=(index, weight, leaf, psum_pmin)``: caller-owned result tensors (persistent buffers of a captured or
+        multi-stream step)."""
         dev = self._cuda(sum_tree, min_tree, u, status)
         B = u.numel()
         u = u.contiguous()
-        index = torch.empty(B, dtype=torch.int64, device=dev)
-        weight = torch.empty(B, dtype=torch.float32, device=dev)
-        leaf = torch.empty(B, dtype=sum_tree.dtype, device=dev) if want_aux else None
-        pp = torch.empty(2, dtype=sum_tree.dtype, device=dev) if want_aux else None
+        if out is not None:
+            index, weight, leaf, pp = out
+            want_aux = True
+        else:
+            index = torch.empty(B, dtype=torch.int64, device=dev)
+            weight = torch.empty(B, dtype=torch.float32, device=dev)
+            leaf = torch.empty(B, dtype=sum_tree.dtype, device=dev) if want_aux else None
+            pp = torch.empty(2, dtype=sum_tree.dtype, device=dev) if want_aux else None
         with self._Guard(dev):
             self._check(self.L.rlb_per_sample(
                 sum_tree.data_ptr(), min_tree.data_ptr(), size, capacity, _dtype_code(sum_tree.dtype), length,

@@ -113,7 +113,7 @@ class OracleBackend:
 
     # ---- fused sampler arithmetic (restates include/rlb200.h rlb_per_sample / rlb_per_update)
     def per_sample(self, sum_tree, min_tree, size, capacity, length, u, beta, cpu_semantics, status=None,
-                   want_aux=False):
+                   want_aux=False, out=None):
         p_sum = self._query1(sum_tree, size, capacity, False, 0, length, bool(cpu_semantics))
         p_min = self._query1(min_tree, size, capacity, True, 0, length, bool(cpu_semantics))
         if status is not None:
@@ -137,6 +137,10 @@ class OracleBackend:
                 leaf = sum_tree[index + capacity]
                 zero = leaf == 0
         weight = torch.pow(leaf / p_min, -beta).to(torch.float32)
+        if out is not None:
+            for dst, src in zip(out, (index, weight, leaf, torch.stack([p_sum, p_min]))):
+                dst.copy_(src)
+            return out
         if want_aux:
             return index, weight, leaf, torch.stack([p_sum, p_min])
         return index, weight

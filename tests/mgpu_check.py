@@ -133,7 +133,8 @@ def main():
             with torch.cuda.stream(side):
                 rb.update_local_priority(pr_loc)   # needs the sampled indices only: overlaps the exchange
             main.wait_stream(side)
-            return batch, rb.local_index
+            rb.join_exchange()                     # the exchange stream must rejoin before the capture ends
+            return batch, rb.local_index.clone()
 
         return step
 

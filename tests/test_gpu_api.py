@@ -163,8 +163,9 @@ def test_index_check_mode(cuda_backend):
     st = TensorStorage(torch.arange(100.0, device=dev()).reshape(50, 2), device=dev())
     st.get(torch.tensor([0, 49], device=dev()))            # the status word is on by default for tensor indices
     st.check_index_status()
+    last = st.get(torch.tensor([49], device=dev()))[0].clone()
     out = st.get(torch.tensor([0, 50], device=dev()))      # out of range: reads the clamped row ...
-    assert torch.equal(out[1], st.get(torch.tensor([49], device=dev()))[0])
+    assert torch.equal(out[1], last)
     with pytest.raises(IndexError):
         st.check_index_status()                            # ... and the synchronising check says so
     # deferred form: no sync anywhere -- a LATER tensor-indexed call of the same storage raises
