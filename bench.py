@@ -296,11 +296,66 @@ def write_path_probe(dev, rb, g, hbm_peak: float) -> dict | None:
         return {"error": f"{type(e).__name__}: {e}"[:200]}
 
 
+def framestack_probe(dev, g, hbm_peak: float) -> dict:
+    """SURVEY 8(f)-1, second half: the de-duplicated frame-stack storage next to the materialised one.  8 environment
+    streams of 84x84 frames, 4-stacks, 262144 transitions (pool 2.3 GB, far beyond L2); a B=256 tensor-index read rebuilds
+    both stacks inside the gather launch.  Reports pixel bytes per stored transition and the read / write times.  Never
+    fatal to the bench."""
+    try:
+        from rl_b200.data import FrameStackStorage, LazyTensorStorage, TensorDict
+
+        E, T, k, cap = 8, 512, 4, 262144
+        out = {}
+        stores = {"dedup": FrameStackStorage(cap, n_envs=E, device=dev, min_episode_length=64),
+                  "dedup_views": FrameStackStorage(cap, n_envs=E, device=dev, min_episode_length=64, materialize=False),
+                  "materialised": LazyTensorStorage(cap, device=dev)}
+        tail = torch.randint(0, 256, (k, E, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+        cursor, batch = 0, None
+        for _ in range(cap // (E * T)):
+            frames = torch.cat([tail, torch.randint(0, 256, (T, E, 84, 84), dtype=torch.uint8, device=dev, generator=g)])
+            tail = frames[-k:]
+            win = frames.unfold(0, k + 1, 1).permute(1, 0, 4, 2, 3)            # [E, T, k + 1, 84, 84] windows of the stream
+            n = E * T
+            batch = TensorDict({"pixels": win[:, :, :k].reshape(n, k, 84, 84), "action": torch.zeros(n, 1, dtype=torch.int64, device=dev),
+                                "next": {"pixels": win[:, :, 1:].reshape(n, k, 84, 84), "reward": torch.zeros(n, device=dev),
+                                         "done": torch.zeros(n, 1, dtype=torch.bool, device=dev)}}, [n])
+            slots = torch.arange(cursor, cursor + n, device=dev)
+            for st in stores.values():
+                st.set(slots, batch)
+            cursor += n
+        idx = [torch.randint(0, cap, (BATCH,), device=dev, generator=g) for _ in range(20)]
+        a, b = stores["dedup"].get(idx[0]), stores["materialised"].get(idx[0])
+        c = stores["dedup_views"].get(idx[0])
+        same = all(torch.equal(a.get(key), b.get(key)) and torch.equal(c.get(key), b.get(key))
+                   for key in ("pixels", ("next", "pixels")))
+        for st in stores.values():
+            if hasattr(st, "check_index_status"):
+                st.check_index_status()
+        out["batches_equal_materialised_storage"] = bool(same)
+        frame = 84 * 84
+        out["pixel_bytes_per_transition"] = {"dedup": round(stores["dedup"].frame_bytes_per_transition, 1),
+                                             "materialised": 2 * k * frame}
+        for name, st in stores.items():
+            us = graph_us([(lambda ix=ix, st=st: st.get(ix)) for ix in idx], dev)
+            moved = BATCH * frame * ((k + 1) * 2 if name == "dedup_views" else (k + 1) + 2 * k if name == "dedup" else 4 * k)
+            out[f"get_B{BATCH}_{name}_us"] = round(us, 2)
+            out[f"get_B{BATCH}_{name}_unique_GBps"] = round(moved / us / 1e3, 1)
+        writes = [(lambda st=st: st.set(torch.arange(0, E * T, device=dev), batch)) for st in (stores["dedup"],)] * 4
+        out[f"set_n{E * T}_dedup_us"] = round(graph_us(writes, dev), 2)
+        writes = [(lambda: stores["materialised"].set(torch.arange(0, E * T, device=dev), batch))] * 4
+        out[f"set_n{E * T}_materialised_us"] = round(graph_us(writes, dev), 2)
+        out["note"] = ("unique_GBps counts every distinct byte once (dedup reads k + 1 frames per transition and writes "
+                       "2 k, or k + 1 as overlapping views); hbm peak %.0f GB/s" % hbm_peak)
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def steps_per_graph(k: int) -> int:
     """Consecutive steps captured into ONE graph.  A graph replay costs ~8 us on its own (torch refreshes the Philox
     seed / offset of the registered generator with two small fill kernels, then the launch itself), so a training loop
     that captures a few steps at a time pays it once per group; the timed region still runs EXACTLY `k` steps."""
-    for spg in (4, 2):
+    for spg in (20, 12, 8, 4, 2):
         if k % spg == 0:
             return spg
     return 1
@@ -584,7 +639,8 @@ def run_single(args, dev) -> dict:
     spg = steps_per_graph(args.steps)
     try:
         gen = rb.sampler._rng
-        groups = [steps[i:i + spg] for i in range(0, R - R % spg, spg)]
+        n_groups = max(1, min(3, R // spg))
+        groups = [[steps[(gi * spg + k) % R] for k in range(spg)] for gi in range(n_groups)]
         graphs = [CudaGraphStep((lambda grp=grp: [st() for st in grp]), generators=[gen], warmup=1) for grp in groups]
         ms_graph = timed_groups(graphs, spg, args.steps, args.warmup, sync_all)
         # a longer replay run of the same graphs (the driver's --steps 20 makes the timed region < 1 ms)
@@ -630,6 +686,8 @@ def run_single(args, dev) -> dict:
     except Exception as e:  # noqa: BLE001
         comp = {"error": f"{type(e).__name__}: {e}"[:200]}
     write_path = write_path_probe(dev, rb, g, hbm_peak)
+    if isinstance(write_path, dict):
+        write_path["framestack"] = framestack_probe(dev, g, hbm_peak)
     ref_gpu = reference_gpu_kernels(dev, rb, ring, td_err)
     cpu = cpu_baseline_run(steps=None)
     if "error" not in comp and cpu.get("phases_ms"):
@@ -932,15 +990,19 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
     clocks = ClockSampler(dev.index or 0) if rank == 0 else None
     ms_eager = timed(lambda i: eager_steps[i % R](), args.steps, args.warmup, sync_all)
 
-    graphs, graph_err, ms_graph, ms_graph_long = None, None, None, None
+    graphs, graph_err, ms_graph, ms_graph_long, spg = None, None, None, None, None
     try:
         if not nvlink:
             raise RuntimeError("NVLink transport unavailable (symmetric memory): the NCCL all-gather cannot be captured with the step")
         gen = rb.sampler._rng
-        spg = N_BUFFERS   # one graph = one turn over the receive slots; the exchanges run beside the compute chain
+        # spg consecutive steps per graph (a multiple of the receive-slot count, so graphs chain slot-continuously); the
+        # exchanges run on their own stream beside the compute chain and rejoin once per graph
+        spg = next((c for c in (20, 12, 8, 4) if args.steps % c == 0), None)
+        if spg is None:
+            raise RuntimeError(f"--steps must be a multiple of {N_BUFFERS} with the pipelined NVLink exchange")
 
         def make_group(g0: int):
-            fns = [make_step(g0 + k) for k in range(spg)]
+            fns = [make_step((g0 + k) % R) for k in range(spg)]
 
             def group():
                 outs = [fn() for fn in fns]
@@ -949,9 +1011,7 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
 
             return group
 
-        if args.steps % spg:
-            raise RuntimeError(f"--steps must be a multiple of {spg} with the pipelined NVLink exchange")
-        graphs = [CudaGraphStep(make_group(g0), generators=[gen], warmup=1) for g0 in range(0, R, spg)]
+        graphs = [CudaGraphStep(make_group(g0), generators=[gen], warmup=1) for g0 in (0, spg)]
         ms_graph = timed_groups(graphs, spg, args.steps, max(args.warmup, spg), sync_all)
         ms_graph_long = timed_groups(graphs, spg, max(args.steps, 200) // spg * spg, spg, sync_all)
         torch.cuda.synchronize()
@@ -1018,8 +1078,8 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
                  "flag release/acquire closes the exchange; sample() returns the previous draw" if nvlink
                  else "NCCL all-gather (eager)")
     cfg = make_config(world)
-    detail = {"n_leaves": n_leaves, "transport": transport, "steps_per_graph": N_BUFFERS if ms_graph is not None else None,
-              "launch": (f"cuda_graph replay of the public-API step, {N_BUFFERS} consecutive steps per graph; the exchange "
+    detail = {"n_leaves": n_leaves, "transport": transport, "steps_per_graph": spg if ms_graph is not None else None,
+              "launch": (f"cuda_graph replay of the public-API step, {spg} consecutive steps per graph; the exchange "
                          "of a draw runs on its own stream beside the next steps" if ms_graph is not None
                          else "eager python API")}
     result = {
@@ -1095,17 +1155,19 @@ def sharded_workload(name: str, dev, rank: int, world: int, steps: int, be) -> d
     gen = rb.sampler._rng
     out = {}
     if nvlink:
+        spg = 4 * N_BUFFERS
+
         def group():
-            outs = [make_step(k)() for k in range(N_BUFFERS)]
+            outs = [make_step(k)() for k in range(spg)]
             rb.join_exchange()
             return outs
 
         graphs = [CudaGraphStep(group, generators=[gen], warmup=1)]
-        steps = steps // N_BUFFERS * N_BUFFERS
-        ms = timed_groups(graphs, N_BUFFERS, steps, 2 * N_BUFFERS, sync_all)
+        steps = max(spg, steps // spg * spg)
+        ms = timed_groups(graphs, spg, steps, spg, sync_all)
         torch.cuda.synchronize()
         rb.check_exchange()
-        launch = f"cuda_graph replay, {N_BUFFERS} steps per graph"
+        launch = f"cuda_graph replay, {spg} steps per graph"
     else:
         eager = make_step(0)
         ms = timed(lambda i: eager(), steps, 4, sync_all)

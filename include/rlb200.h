@@ -181,6 +181,47 @@ int rlb_gather(const void *const *src /*[host] n_leaves [dev] pointers*/,
                const int64_t *index /*[dev] B*/, int64_t B, int64_t len, int mode,
                int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
 
+/* ---- de-duplicated frame-stack storage (no reference counterpart: the reference stores the
+ * k-frame observation stack AND the k-frame next-observation stack of every transition, storages.py:1028-1096) --------
+ * Every frame of an environment's stream is kept ONCE, in that environment's ring of the frame pool
+ * pool[n_envs * ring, frame_bytes]; a transition owns the frame word
+ *     fpos = env << RLB_FRAME_ENV_SHIFT | position            (position = index of its NEWEST frame in the env's log)
+ * and its observation / next-observation stacks are the log positions [position - k, position) / (position - k, position].
+ * An episode's first transition logs its k reset frames before its newest one, so the rule has no special cases. */
+#define RLB_FRAME_ENV_SHIFT 40
+#define RLB_FRAME_POS_MASK ((1ll << RLB_FRAME_ENV_SHIFT) - 1)
+#define RLB_STATUS_FRAME_EVICTED 32 /* a gathered transition's frames were already overwritten in the env's ring */
+
+typedef struct rlb_frame_leaf {
+  const int64_t *fpos; /* [dev] per-slot frame words, or NULL: an ordinary leaf */
+  const int64_t *head; /* [dev] per-env count of frames logged so far (eviction check), or NULL */
+  int64_t ring;        /* frames per env ring */
+  int32_t offset;      /* which frame of the window: j - k for j in [0, k] (0 = the newest) */
+  int32_t reserved;
+} rlb_frame_leaf;
+
+/* rlb_gather whose leaf k, when frames[k].fpos != NULL, reads row  env * ring + (position + offset) mod ring  of
+ * src[k] (the frame pool) for the slot index[b]: the stacks are rebuilt by the gather kernel itself, written into
+ * consecutive frame slots of the batch through dst / dst_stride_bytes.  The other leaves behave as in rlb_gather. */
+int rlb_gather_frames(const void *const *src /*[host]*/, void *const *dst /*[host]*/, const int64_t *row_bytes /*[host]*/,
+                      const int64_t *src_stride_bytes /*[host]*/, const int64_t *dst_stride_bytes /*[host] or NULL*/,
+                      const int64_t *peer_delta /*[host] or NULL*/, int n_peers, int n_leaves,
+                      const rlb_frame_leaf *frames /*[host] n_leaves*/, const int64_t *index /*[dev] B*/, int64_t B,
+                      int64_t len, int mode, int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
+
+/* Logs the frames of n incoming transitions (n_envs environments x n / n_envs consecutive steps each; layout 0: row
+ * i = env * steps + step, the flattened [E, T] collector batch; layout 1: row i = step * n_envs + env) and returns their
+ * frame words.  A transition is an episode start when is_init[i] (or, is_init == NULL, when the previous transition
+ * of its environment had done = 1 -- carried across calls in last_done, which starts at 1): its k observation frames
+ * are logged, then its newest frame  next_obs[i, k - 1]; every other transition logs the newest frame only and
+ * shares the rest with its predecessors.  Two launches: the per-env position scan, then the frame copies. */
+int rlb_framestack_push(const void *obs /*[dev] n x k x frame_bytes*/, const void *next_obs /*[dev] same*/,
+                        int64_t obs_row_stride, int64_t next_row_stride, const uint8_t *is_init /*[dev] n or NULL*/,
+                        const uint8_t *done /*[dev] n or NULL*/, uint8_t *last_done /*[dev] n_envs*/,
+                        int64_t *head /*[dev] n_envs*/, void *pool /*[dev]*/, int64_t *fpos_out /*[dev] n*/,
+                        uint8_t *init_scratch /*[dev] n*/, int64_t n, int n_envs, int layout, int k,
+                        int64_t frame_bytes, int64_t ring, rlb_stream_t stream);
+
 /* TensorStorage.set for a tensor cursor (storages.py:1028-1096: storage[cursor] = data per leaf,
  * aten::index_put_):  dst[k][index[b], :] = src[k][b, :].  Duplicate indices: the last wins only
  * if the caller passes unique indices (round-robin writers do, writers.py:190-216). */

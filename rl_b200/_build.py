@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 SO = PKG / "librlb200.so"
-SOURCES = ["abi.cu", "tree.cu", "gae.cu", "gather.cu", "shard.cu", "slice.cu"]
+SOURCES = ["abi.cu", "tree.cu", "gae.cu", "gather.cu", "shard.cu", "slice.cu", "framestack.cu"]
 
 
 def nvcc_path() -> str:
@@ -32,13 +32,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -shared -> rl_b200/librlb200.so"""
     if not force and not needs_build():
         return SO
+    tmp = SO.with_name(SO.name + ".partial")   # linked beside the target, then renamed: never a half-written library
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-shared", "-o", str(SO)]
+           "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-shared", "-o", str(tmp)]
     cmd += [str(CSRC / s) for s in SOURCES] + ["-lcudart"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    tmp.replace(SO)
     return SO
 
 

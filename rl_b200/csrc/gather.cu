@@ -64,7 +64,13 @@ struct GatherLeaf {
   uint32_t upr;     // vector role: vectors per row
   int32_t vec_log2; // vector role: log2(vector bytes)
   int32_t bulk;     // 1 -> bulk-DMA role
-  int32_t pad_;
+  int32_t foff;     // frame leaf: which frame of the transition's window, relative to its newest one (j - k)
+  // frame leaf (de-duplicated frame-stack storage, framestack.cu): the slot index is translated through the slot's
+  // frame word  fpos[slot] = env << 40 | position  into the row  env * ring + (position + foff) mod ring  of the
+  // frame pool (= src); null for ordinary leaves
+  const int64_t *fpos;
+  const int64_t *fhead;  // per-env count of frames pushed so far (eviction check), may be null
+  int64_t ring;          // frames per env ring
 };
 
 struct GatherParams {
@@ -95,9 +101,22 @@ __device__ __forceinline__ int64_t fix_index(int64_t ix, int64_t len, int32_t *s
   return ix;
 }
 
+// gather side: range-check the slot, then (frame leaves) translate it into the frame-pool row
+__device__ __forceinline__ int64_t resolve_row(const GatherParams &P, const GatherLeaf &L, int64_t ix) {
+  ix = fix_index(ix, P.len, P.status);
+  if (L.fpos) {
+    const int64_t w = __ldg(L.fpos + ix);
+    const int64_t env = w >> RLB_FRAME_ENV_SHIFT, q = (w & RLB_FRAME_POS_MASK) + L.foff;
+    // positions [head - ring, head) of an env's log are still in its ring
+    if (L.fhead && P.status && (q < 0 || __ldg(L.fhead + env) - q > L.ring)) atomicOr(P.status, RLB_STATUS_FRAME_EVICTED);
+    ix = env * L.ring + (q < 0 ? 0 : q % L.ring);
+  }
+  return ix;
+}
+
 // IMPLICIT (write path only): no index array, slot = (ibase + b) mod len
 template <bool IMPLICIT>
-__device__ __forceinline__ int64_t load_index(const GatherParams &P, int64_t b) {
+__device__ __forceinline__ int64_t load_index(const GatherParams &P, const GatherLeaf &L, int64_t b) {
   if constexpr (!IMPLICIT) {
     return __ldg(P.index + b);
   } else {
@@ -151,7 +170,7 @@ __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams
       b[k] = ok[k] ? u / L.upr : 0;
       j[k] = ok[k] ? (uint32_t)(u - b[k] * L.upr) : 0;
     }
-    ix[k] = ok[k] ? load_index<IMPLICIT>(P, b[k]) : 0;
+    ix[k] = ok[k] ? load_index<IMPLICIT>(P, L, b[k]) : 0;
   }
   V val[kVecUnroll];
 #pragma unroll
@@ -168,7 +187,7 @@ __device__ __forceinline__ void vec_tile(const GatherLeaf &L, const GatherParams
         }
         ix[k] = w;
       } else {
-        ix[k] = fix_index(ix[k], P.len, P.status);
+        ix[k] = resolve_row(P, L, ix[k]);
       }
       const int64_t srow = SCATTER ? b[k] * L.ostride : ix[k] * L.stride;
       val[k] = ld_stream(reinterpret_cast<const V *>(L.src + srow) + j[k]);
@@ -246,8 +265,14 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
   int64_t b = byte_in_leaf / P.leaf[l].row_bytes;
   int64_t off = byte_in_leaf - b * P.leaf[l].row_bytes;
   // index window: lane j holds index[win0 + j]
+  // (gather: already range-checked and, for frame leaves, translated -- one dependent load per 32 rows, not per piece)
+  auto window = [&](const GatherLeaf &L, int64_t first) -> int64_t {
+    if (first + lane >= P.B) return 0;
+    const int64_t raw = load_index<IMPLICIT>(P, L, first + lane);
+    if constexpr (SCATTER) return raw; else return resolve_row(P, L, raw);
+  };
   int64_t win0 = b;
-  int64_t my_ix = (win0 + lane < P.B) ? load_index<IMPLICIT>(P, win0 + lane) : 0;
+  int64_t my_ix = window(P.leaf[l], win0);
 
   int64_t n_loaded = 0, n_stored = 0;
   bool more = true;
@@ -257,10 +282,10 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
       const GatherLeaf &L = P.leaf[l];
       if (b >= win0 + 32) {  // warp-uniform: refill the index window
         win0 = b;
-        my_ix = (win0 + lane < P.B) ? load_index<IMPLICIT>(P, win0 + lane) : 0;
+        my_ix = window(L, win0);
       }
       int64_t ix = __shfl_sync(0xffffffffu, my_ix, (int)(b - win0));
-      ix = fix_index(ix, P.len, lane == 0 ? P.status : nullptr);
+      if constexpr (SCATTER) ix = fix_index(ix, P.len, lane == 0 ? P.status : nullptr);
       int64_t nbytes = L.row_bytes - off;
       if (nbytes > (int64_t)kChunk) nbytes = kChunk;
       const int64_t left = (end - pos) << 4;
@@ -296,7 +321,7 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
         b = 0;
         off = 0;
         win0 = 0;
-        my_ix = (lane < P.B) ? load_index<IMPLICIT>(P, lane) : 0;
+        my_ix = window(P.leaf[l], 0);
       }
     }
     // ---- retire the oldest staged piece: wait for its bytes, then DMA it out
@@ -378,7 +403,8 @@ template <bool SCATTER>
 static int plan_rows(GatherParams &P, int &vec_ctas_out, const void *const *src, void *const *dst,
                      const int64_t *row_bytes, const int64_t *stride, const int64_t *ostride,
                      const int64_t *peer_delta, int n_peers, int n_leaves, const int64_t *index, int64_t ibase,
-                     int64_t B, int64_t len, int mode, int32_t *status, const char *who, int reserved_sms = 0) {
+                     int64_t B, int64_t len, int mode, int32_t *status, const char *who, int reserved_sms = 0,
+                     const rlb_frame_leaf *frames = nullptr) {
   RLB_REQUIRE(src && dst && row_bytes && stride, RLB_EINVAL, "%s: null argument", who);
   const int sms = sm_count();
   if (sms <= 0) return RLB_ENODEV;
@@ -407,6 +433,17 @@ static int plan_rows(GatherParams &P, int &vec_ctas_out, const void *const *src,
     L.row_bytes = row_bytes[k];
     L.stride = stride[k];
     L.ostride = ostride ? ostride[k] : row_bytes[k];
+    L.fpos = nullptr;
+    L.fhead = nullptr;
+    L.ring = 0;
+    L.foff = 0;
+    if (frames && frames[k].fpos) {
+      RLB_REQUIRE(frames[k].ring > 0 && frames[k].offset <= 0, RLB_EINVAL, "%s: leaf %d: bad frame window", who, k);
+      L.fpos = frames[k].fpos;
+      L.fhead = frames[k].head;
+      L.ring = frames[k].ring;
+      L.foff = frames[k].offset;
+    }
     RLB_REQUIRE(L.ostride >= row_bytes[k], RLB_EINVAL, "%s: leaf %d batch-side stride < row_bytes", who, k);
     const int lg = pick_vec_log2(src[k], dst[k], row_bytes[k], stride[k], L.ostride);
     const bool eligible = lg == 4 && row_bytes[k] >= 16;  // (rlb_scatter asks for the vector role)
@@ -479,7 +516,7 @@ template <bool SCATTER>
 static int launch_rows(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *stride,
                        const int64_t *ostride, const int64_t *peer_delta, int n_peers, int n_leaves,
                        const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status, cudaStream_t st,
-                       const char *who) {
+                       const char *who, const rlb_frame_leaf *frames = nullptr) {
   RLB_REQUIRE(n_leaves >= 0 && n_leaves <= RLB_MAX_LEAVES, RLB_ELIMIT, "%s: n_leaves=%d exceeds RLB_MAX_LEAVES=%d",
               who, n_leaves, RLB_MAX_LEAVES);
   RLB_REQUIRE(B >= 0 && len >= 0, RLB_EINVAL, "%s: negative B or len", who);
@@ -492,7 +529,7 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
   // exchange (the priority write-back's cluster, the next draw) instead of parking a 161 KB CTA on every one
   const int reserved = n_peers > 1 ? kPeerReservedSms : 0;
   int rc = plan_rows<SCATTER>(P, vec_ctas, src, dst, row_bytes, stride, ostride, peer_delta, n_peers, n_leaves, index,
-                              0, B, len, mode, status, who, reserved);
+                              0, B, len, mode, status, who, reserved, frames);
   if (rc) return rc;
   const size_t smem = P.bulk_ctas > 0 ? kBulkSmemBytes : 0;
   static bool attr_set_dev[64] = {};  // function attributes are per device
@@ -528,6 +565,17 @@ int rlb_gather(const void *const *src, void *const *dst, const int64_t *row_byte
               "rlb_gather: unknown mode %d", mode);
   return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, dst_stride_bytes, peer_delta, n_peers, n_leaves,
                             index, B, len, mode, status, as_stream(stream), "rlb_gather");
+}
+
+int rlb_gather_frames(const void *const *src, void *const *dst, const int64_t *row_bytes,
+                      const int64_t *src_stride_bytes, const int64_t *dst_stride_bytes, const int64_t *peer_delta,
+                      int n_peers, int n_leaves, const rlb_frame_leaf *frames, const int64_t *index, int64_t B,
+                      int64_t len, int mode, int32_t *status, rlb_stream_t stream) {
+  RLB_REQUIRE(mode == RLB_GATHER_AUTO || mode == RLB_GATHER_VECTOR || mode == RLB_GATHER_BULK, RLB_EINVAL,
+              "rlb_gather_frames: unknown mode %d", mode);
+  RLB_REQUIRE(frames, RLB_EINVAL, "rlb_gather_frames: null frames");
+  return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, dst_stride_bytes, peer_delta, n_peers, n_leaves,
+                            index, B, len, mode, status, as_stream(stream), "rlb_gather_frames", frames);
 }
 
 int rlb_scatter(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *dst_stride_bytes,

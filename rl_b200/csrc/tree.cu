@@ -460,6 +460,8 @@ __host__ __device__ inline int upd_bot_levels(int depth) { return depth > kDense
 
 constexpr int kUpdCluster = 8;  // CTAs per update launch: the leader + seven helpers (portable cluster size)
 constexpr int kUpdHoist = 16;   // sibling values of this many levels are held in registers during the climb
+constexpr int kUpdMaxItemsPerRound = 1024;  // one item per thread
+constexpr int kUpdMaxRounds = 8;            // batches up to 8192 items in one launch
 
 
 template <typename T>
@@ -536,22 +538,65 @@ __device__ __forceinline__ double ld_cluster(uint32_t addr, double) {
   return v;
 }
 
+// Sort NP unique keys, one per thread: bucket them by `bucket` (NP buckets over the leaf range + bucket NP for the
+// entries that are not items: one key per bucket on average for the random leaves prioritized sampling produces), lay
+// the buckets out with a prefix sum, and order each bucket by counting -- a key's rank is its bucket's base plus the
+// number of smaller keys in the bucket.  Keys are unique, so the ranks are a permutation.  (A count-everything rank
+// costs ~3k cycles of shared-memory bandwidth for 256 keys, a bitonic network ~11k for 1024; this is a handful of
+// barriers.  Crowded buckets -- duplicates, clustered leaves -- only make the last loop longer.)
+template <typename K>
+__device__ __forceinline__ K bucket_rank_sort(K key, uint32_t bucket, K *bucketed, K *sorted, uint32_t *cnt,
+                                              uint32_t *s_wsum, int NP, int tid, int lane) {
+  cnt[tid] = 0u;
+  if (tid == 0) cnt[NP] = 0u;
+  __syncthreads();
+  const uint32_t slot = atomicAdd(&cnt[bucket], 1u);
+  __syncthreads();
+  // exclusive prefix sum of the NP + 1 counts (the non-item bucket comes last: its base is the number of items)
+  const uint32_t c = cnt[tid];
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_wsum[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < (tid >> 5); ++w) woff += s_wsum[w];
+  const uint32_t excl = woff + incl - c;  // base of bucket `tid`
+  __syncthreads();                        // (everybody has read cnt[] and s_wsum[])
+  cnt[tid] = excl;
+  if (tid == NP - 1) cnt[NP] = excl + c;  // base of the non-item bucket
+  __syncthreads();
+  const uint32_t base = cnt[bucket];
+  bucketed[base + slot] = key;
+  __syncthreads();
+  const uint32_t bend = (bucket == (uint32_t)NP) ? (uint32_t)NP : cnt[bucket + 1];
+  uint32_t rank = base;
+  for (uint32_t j = base; j < bend; ++j) rank += (bucketed[j] < key);
+  sorted[rank] = key;
+  __syncthreads();
+  return sorted[tid];
+}
+
 template <typename T, bool FUSED>
 __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, int64_t capacity, int depth,
-                                                               const int64_t *__restrict__ index,
-                                                               const T *__restrict__ value, int n, int scalar,
+                                                               const int64_t *__restrict__ index_all,
+                                                               const T *__restrict__ value_all, int n_all, int scalar,
                                                                float alpha, float eps, float *max_out,
                                                                long long *dbg, int64_t index_base,
                                                                int64_t index_limit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NP = (int)blockDim.x;          // a power of two >= n: one item per thread
+  const int NP = (int)blockDim.x;          // a power of two: one item per thread and round
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int bot = upd_bot_levels(depth);   // levels climbed item by item; the rest is dense
   const int W = 1 << (depth - bot);        // nodes at the cut level
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
   __shared__ unsigned s_lmask;             // bit L set: some item hands over at level L (1 <= L <= bot)
-  unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] exchange buffers
+  __shared__ uint32_t s_wsum[32];
+  unsigned long long *xbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // [2][NP] sort buffers
   uint32_t *sleaf = reinterpret_cast<uint32_t *>(xbuf + 2 * NP);  // sorted leaf index (0xffffffff: not an item)
   uint32_t *spos = sleaf + NP;                                    // its input position
   int *Lpos = reinterpret_cast<int *>(spos + NP);                 // by INPUT POSITION: merge level of the item if it is
@@ -561,107 +606,109 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   T *cut_s = sib + 2 * (size_t)bot * NP;  // heap layout over the top of the tree: node k at [k], 1 <= k < 2W
   T *cut_m = cut_s + 2 * (size_t)W;
 
-  // Cluster barrier phases (every thread of every CTA arrives on each, in this order):
-  //   1  "all CTAs are running" (remote shared-memory accesses are legal afterwards)
-  //   2  helpers -> leader: the sibling tile is complete
-  //   3  leader -> helpers: merge levels, leaf values and the staging tile are final -- scatter them
-  //   4  helpers -> leader: nobody reads the leader's shared memory any more
+  // Batches above NP items are applied in ROUNDS of NP consecutive items, in input order, inside this one launch (a
+  // later round overwrites an earlier one: "the last duplicate wins" holds across rounds); the dense top is recomputed
+  // once, after the last round.  Cluster barrier phases (every thread of every CTA arrives on each, in this order):
+  //   1          "all CTAs are running" (remote shared-memory accesses are legal afterwards)
+  //   per round: 2  helpers -> leader: the sibling tile is complete
+  //              3  leader -> helpers: merge levels, leaf values and the staging tile are final -- scatter them
+  //              4  helpers -> everybody: the round's nodes are in the trees, nobody reads the leader's tile any more
+  const int rounds = (n_all + NP - 1) / NP;
   cluster_arrive_relaxed();  // phase 1
   if (dbg && tid == 0 && crank <= 1) dbg[32 + 8 * crank] = (long long)globaltimer_ns();
 
   if (crank != 0) {
-    // ---- helpers, part 1: sib[t][l][i] (in the LEADER's shared memory) = tree_t[((capacity + index[i]) >> l) ^ 1]
-    // for the levels below the cut.  The loads are issued before the cluster is known to be up, the stores after.
-    constexpr int kMaxPer = 4;
-    const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
-    const uint32_t nthreads = (csize - 1u) * (uint32_t)NP, g = (crank - 1u) * (uint32_t)NP + tid;
-    const int64_t ix_self = (tid < n) ? __ldg(index + tid) - index_base : -1;  // (for part 2: the item at position tid)
-    T val[kMaxPer];
-    uint32_t el[kMaxPer];
+    for (int rnd = 0; rnd < rounds; ++rnd) {
+      const int64_t *index = index_all + (size_t)rnd * NP;
+      const int n = min(NP, n_all - rnd * NP);
+      // ---- helpers, part 1: sib[t][l][i] (in the LEADER's shared memory) = tree_t[((capacity + index[i]) >> l) ^ 1]
+      // for the levels below the cut.  The loads are issued before the cluster is known to be up, the stores after.
+      constexpr int kMaxPer = 4;
+      const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
+      const uint32_t nthreads = (csize - 1u) * (uint32_t)NP, g = (crank - 1u) * (uint32_t)NP + tid;
+      const int64_t ix_self = (tid < n) ? __ldg(index + tid) - index_base : -1;  // (part 2: the item at position tid)
+      T val[kMaxPer];
+      uint32_t el[kMaxPer];
 #pragma unroll
-    for (int k = 0; k < kMaxPer; ++k) {
-      const uint32_t e = g + (uint32_t)k * nthreads;
-      el[k] = e;
-      val[k] = (T)0;
-      if (e < total) {
+      for (int k = 0; k < kMaxPer; ++k) {
+        const uint32_t e = g + (uint32_t)k * nthreads;
+        el[k] = e;
+        val[k] = (T)0;
+        if (e < total) {
+          const uint32_t t = e >= per_tree;
+          const uint32_t rem = e - t * per_tree;
+          const uint32_t l = rem / (uint32_t)NP;
+          const uint32_t i = rem - l * (uint32_t)NP;
+          const T *tree = t ? mn : sum;
+          if (tree && i < (uint32_t)n) {
+            const int64_t ix = __ldg(index + i) - index_base;
+            if (ix >= 0 && ix < index_limit) val[k] = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+          }
+        }
+      }
+      if (rnd == 0) cluster_wait_acquire();  // phase 1
+#pragma unroll
+      for (int k = 0; k < kMaxPer; ++k)
+        if (el[k] < total) st_cluster(map_to_cta(sib + el[k], 0), val[k]);
+      for (uint32_t e = g + kMaxPer * nthreads; e < total; e += nthreads) {  // (deep trees: more than 4 per thread)
         const uint32_t t = e >= per_tree;
         const uint32_t rem = e - t * per_tree;
         const uint32_t l = rem / (uint32_t)NP;
         const uint32_t i = rem - l * (uint32_t)NP;
         const T *tree = t ? mn : sum;
+        T v = (T)0;
         if (tree && i < (uint32_t)n) {
           const int64_t ix = __ldg(index + i) - index_base;
-          if (ix >= 0 && ix < index_limit) val[k] = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+          if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
         }
+        st_cluster(map_to_cta(sib + e, 0), v);
       }
-    }
-    cluster_wait_acquire();  // phase 1
-#pragma unroll
-    for (int k = 0; k < kMaxPer; ++k)
-      if (el[k] < total) st_cluster(map_to_cta(sib + el[k], 0), val[k]);
-    for (uint32_t e = g + kMaxPer * nthreads; e < total; e += nthreads) {  // (deep trees: more than 4 per thread)
-      const uint32_t t = e >= per_tree;
-      const uint32_t rem = e - t * per_tree;
-      const uint32_t l = rem / (uint32_t)NP;
-      const uint32_t i = rem - l * (uint32_t)NP;
-      const T *tree = t ? mn : sum;
-      T v = (T)0;
-      if (tree && i < (uint32_t)n) {
-        const int64_t ix = __ldg(index + i) - index_base;
-        if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
-      }
-      st_cluster(map_to_cta(sib + e, 0), v);
-    }
-    cluster_arrive_release();  // phase 2: my stores are performed before the leader goes on
-    if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 1] = (long long)globaltimer_ns();
-    cluster_wait_acquire();
-    cluster_arrive_relaxed();  // phase 3: nothing to publish; wait for the leader's climb
-    cluster_wait_acquire();
-    if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 2] = (long long)globaltimer_ns();
-    // ---- helpers, part 2: scatter my rows.  Row r (0, 1: the leaves of the sum / min tree; 2 + t * bot + l: level
-    // l + 1 of tree t) holds one value per INPUT POSITION p; it is a finished node iff the item at p is the last writer
-    // of its leaf and carried its path beyond level l (Lpos[p] > l + 1).  Rows are read from the leader's shared
-    // memory in position order -- coalesced 128-byte DSMEM reads -- and the node id comes from the index this helper
-    // reads itself.
-    {
-      const int units = (int)csize - 1, unit = (int)crank - 1, nrows = 2 * bot + 2;
-      const int64_t ix = ix_self;
-      const int Lp = (int)ld_cluster_u32(map_to_cta(Lpos + tid, 0));
-      if (Lp > 0 && ix >= 0 && ix < index_limit) {
-        const uint32_t leafnode = (uint32_t)(capacity + ix);
-        for (int r = unit; r < nrows; r += units) {
-          if (r < 2) {
-            T *tree = r ? mn : sum;
-            if (tree) tree[leafnode] = ld_cluster(map_to_cta(sraw + tid, 0), T());
-          } else {
-            const int t = (r - 2) >= bot, l = (r - 2) - t * bot;
-            T *tree = t ? mn : sum;
-            if (tree && Lp > l + 1) tree[leafnode >> (l + 1)] = ld_cluster(map_to_cta(sib + ((size_t)(r - 2)) * NP + tid, 0), T());
+      cluster_arrive_release();  // phase 2: my stores are performed before the leader goes on
+      if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 1] = (long long)globaltimer_ns();
+      cluster_wait_acquire();
+      cluster_arrive_relaxed();  // phase 3: nothing to publish; wait for the leader's climb
+      cluster_wait_acquire();
+      if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 2] = (long long)globaltimer_ns();
+      // ---- helpers, part 2: scatter my rows.  Row r (0, 1: the leaves of the sum / min tree; 2 + t * bot + l: level
+      // l + 1 of tree t) holds one value per INPUT POSITION p; it is a finished node iff the item at p is the last
+      // writer of its leaf and carried its path beyond level l (Lpos[p] > l + 1).  Rows are read from the leader's
+      // shared memory in position order -- coalesced 128-byte DSMEM reads -- and the node id comes from the index this
+      // helper read itself.
+      {
+        const int units = (int)csize - 1, unit = (int)crank - 1, nrows = 2 * bot + 2;
+        const int Lp = (int)ld_cluster_u32(map_to_cta(Lpos + tid, 0));
+        if (Lp > 0 && ix_self >= 0 && ix_self < index_limit) {
+          const uint32_t leafnode = (uint32_t)(capacity + ix_self);
+          for (int r = unit; r < nrows; r += units) {
+            if (r < 2) {
+              T *tree = r ? mn : sum;
+              if (tree) tree[leafnode] = ld_cluster(map_to_cta(sraw + tid, 0), T());
+            } else {
+              const int t = (r - 2) >= bot, l = (r - 2) - t * bot;
+              T *tree = t ? mn : sum;
+              if (tree && Lp > l + 1)
+                tree[leafnode >> (l + 1)] = ld_cluster(map_to_cta(sib + ((size_t)(r - 2)) * NP + tid, 0), T());
+            }
           }
         }
       }
+      if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 3] = (long long)globaltimer_ns();
+      // phase 4.  With another round to come the nodes just stored must be visible to the next round's sibling reads
+      // (release); after the last round the kernel boundary does that
+      if (rnd + 1 < rounds) {
+        cluster_arrive_release();
+        cluster_wait_acquire();
+      } else {
+        cluster_arrive_relaxed();
+      }
     }
-    if (dbg && tid == 0 && crank == 1) dbg[32 + 8 + 3] = (long long)globaltimer_ns();
-    cluster_arrive_relaxed();  // phase 4 (nothing to publish: the global stores complete with the kernel)
     return;
   }
 
   // ---- leader
-  if (tid == 0) s_lmask = 0u;
   if (dbg && tid == 0) dbg[0] = (long long)clock64();
-  // my own item
-  bool valid = false;
-  int64_t my_ix = -1;
-  T raw = (T)0;
-  if (tid < n) {
-    // index_base maps GLOBAL indices of a sharded buffer onto this shard; entries that fall outside
-    // [0, index_limit) are skipped, like the negative "do not write" markers of samplers.py:1040-1052
-    my_ix = __ldg(index + tid) - index_base;
-    valid = (my_ix >= 0 && my_ix < index_limit);
-    raw = scalar ? __ldg(value) : __ldg(value + tid);
-  }
   {
-    // coalesced 16-byte async copies of the cut level of both trees (land while we sort)
+    // coalesced 16-byte async copies of the cut level of both trees (land while the first round sorts)
     constexpr int kPer16 = 16 / (int)sizeof(T);
     if (W >= kPer16) {
       for (int k = tid * kPer16; k < W; k += NP * kPer16) {
@@ -675,243 +722,225 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       }
     }
   }
-
-  // ---- 1. keys: (leaf index, reversed input position) -- ascending sort puts the last writer first; entries that
-  // are not items get an all-ones leaf field (still unique through the position, so ranks are a permutation).  When
-  // both fields fit in 32 bits (trees up to 2^21 slots with 1024-item batches) the whole sort runs on 32-bit keys.
   const int pos_bits = 31 - __clz(NP);  // log2(NP)
   const bool key32 = (depth + 1 + pos_bits) <= 32;
   const uint32_t none32 = 0xffffffffu >> pos_bits;  // all-ones leaf field of a 32-bit key
-  unsigned long long key;
-  {
+  const int bshift = depth > pos_bits ? depth - pos_bits : 0;   // leaf index -> one of NP buckets
+
+  for (int rnd = 0; rnd < rounds; ++rnd) {
+    const int64_t *index = index_all + (size_t)rnd * NP;
+    const T *value = scalar ? value_all : value_all + (size_t)rnd * NP;
+    const int n = min(NP, n_all - rnd * NP);
+    const bool last_round = rnd + 1 == rounds;
+    if (tid == 0) s_lmask = 0u;
+    // my own item
+    bool valid = false;
+    int64_t my_ix = -1;
+    T raw = (T)0;
+    if (tid < n) {
+      // index_base maps GLOBAL indices of a sharded buffer onto this shard; entries that fall outside
+      // [0, index_limit) are skipped, like the negative "do not write" markers of samplers.py:1040-1052
+      my_ix = __ldg(index + tid) - index_base;
+      valid = (my_ix >= 0 && my_ix < index_limit);
+      raw = scalar ? __ldg(value) : __ldg(value + tid);
+    }
+
+    // ---- 1. keys: (leaf index, reversed input position) -- ascending order puts the last writer first; entries that
+    // are not items get an all-ones leaf field (still unique through the position, so ranks are a permutation).  When
+    // both fields fit in 32 bits (trees up to 2^21 slots with 1024-item batches) the sort runs on 32-bit keys.
     const uint32_t rpos = (uint32_t)(NP - 1 - tid);
+    const uint32_t lf0 = valid ? (uint32_t)my_ix : (key32 ? none32 : 0xffffffffu);
+    const uint32_t bucket = valid ? min(lf0 >> bshift, (uint32_t)NP - 1u) : (uint32_t)NP;
+    if constexpr (FUSED) {
+      if (max_out) {
+        float p = valid ? (float)raw : -INFINITY;
+        for (int o = 16; o > 0; o >>= 1) p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
+        if (lane == 0 && p > -INFINITY) red_max_float(max_out, p);
+      }
+      raw = (T)pow_like_torch(add_rn((float)raw, eps), alpha);  // the leaf value, while the loads above are in flight
+    }
+    sraw[tid] = raw;
+    RLB_TICK(2);
+
+    // ---- 2. sort (bucket_rank_sort above; the counters borrow the sleaf / spos arrays, written only afterwards)
+    unsigned long long key;
     if (key32) {
-      key = ((valid ? (uint32_t)my_ix : none32) << pos_bits) | rpos;
+      uint32_t *xb32 = reinterpret_cast<uint32_t *>(xbuf);
+      key = bucket_rank_sort<uint32_t>((lf0 << pos_bits) | rpos, bucket, xb32, xb32 + NP, sleaf, s_wsum, NP, tid, lane);
     } else {
-      key = ((unsigned long long)(valid ? (uint32_t)my_ix : 0xffffffffu) << 32) | rpos;
+      key = bucket_rank_sort<unsigned long long>(((unsigned long long)lf0 << 32) | rpos, bucket, xbuf, xbuf + NP, sleaf,
+                                                 s_wsum, NP, tid, lane);
     }
-  }
-  if constexpr (FUSED) {
-    if (max_out) {
-      float p = valid ? (float)raw : -INFINITY;
-      for (int o = 16; o > 0; o >>= 1) p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
-      if (lane == 0 && p > -INFINITY) red_max_float(max_out, p);
-    }
-    raw = (T)pow_like_torch(add_rn((float)raw, eps), alpha);  // the leaf value, while the loads above are in flight
-  }
-  sraw[tid] = raw;
-  RLB_TICK(2);
+    RLB_TICK(3);
 
-  // ---- 2. sort.  Up to 256 keys of 32 bits: rank by counting -- key k's rank is the number of keys below it, read as
-  // broadcast 128-bit shared loads (keys are unique, so the ranks are a permutation).  Otherwise bitonic, one key per
-  // thread: strides < 32 with warp shuffles, larger strides through double-buffered shared memory.
-  if (key32 && NP <= 256) {
-    uint32_t *xb32 = reinterpret_cast<uint32_t *>(xbuf);  // [0,NP) keys | [NP,2NP) sorted
-    const uint32_t k32 = (uint32_t)key;
-    xb32[tid] = k32;
+    // ---- 3. heads: the first entry of each run of equal leaves is its last writer.  No compaction: everything below
+    // works on the sorted array as it is (entries that are not heads are simply dead).
+    const uint32_t leaf_field = key32 ? ((uint32_t)key >> pos_bits) : (uint32_t)(key >> 32);
+    const bool key_valid = key32 ? (leaf_field != none32) : (leaf_field != 0xffffffffu);
+    const uint32_t myleaf = key_valid ? leaf_field : 0xffffffffu;
+    const uint32_t pos = (uint32_t)(NP - 1) - (uint32_t)(key & (unsigned long long)(NP - 1));
+    __syncthreads();  // (the sort's counters lived in sleaf / spos)
+    sleaf[tid] = myleaf;
+    spos[tid] = pos;
+    if (rnd == 0) {
+      cp_async_wait_all();
+      cluster_wait_acquire();   // phase 1
+    }
+    // the sibling tile: every helper has stored its share into this CTA's shared memory once phase 2 completes
+    cluster_arrive_relaxed();   // phase 2
+    cluster_wait_acquire();
     __syncthreads();
-    const uint4 *kv = reinterpret_cast<const uint4 *>(xb32);
-    uint32_t r0 = 0, r1 = 0;
-#pragma unroll 8
-    for (int j = 0; j < (NP >> 2); ++j) {
-      const uint4 q = kv[j];
-      // 0xffffffff where the other key is smaller: two set instructions feed one three-input subtract
-      uint32_t d0, d1, d2, d3;
-      asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(d0) : "r"(q.x), "r"(k32));
-      asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(d1) : "r"(q.y), "r"(k32));
-      asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(d2) : "r"(q.z), "r"(k32));
-      asm("set.lt.u32.u32 %0, %1, %2;" : "=r"(d3) : "r"(q.w), "r"(k32));
-      r0 = r0 - d0 - d1;
-      r1 = r1 - d2 - d3;
-    }
-    xb32[NP + r0 + r1] = k32;
-    __syncthreads();
-    key = xb32[NP + tid];
-  } else if (key32) {
-    uint32_t k32 = (uint32_t)key;
-    uint32_t *xb32 = reinterpret_cast<uint32_t *>(xbuf);
-    int flip = 0;
-    for (int k = 2; k <= NP; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        uint32_t other;
-        if (j >= 32) {
-          uint32_t *buf = xb32 + flip * NP;
-          buf[tid] = k32;
-          __syncthreads();
-          other = buf[tid ^ j];
-          flip ^= 1;
-        } else {
-          other = __shfl_xor_sync(0xffffffffu, k32, j);
+    if (csize == 1 && bot > 0) {
+      // (launched without helpers: fetch the siblings here -- correct, just slow)
+      const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
+      for (uint32_t e = tid; e < total; e += NP) {
+        const uint32_t t = e >= per_tree;
+        const uint32_t rem = e - t * per_tree;
+        const uint32_t l = rem / (uint32_t)NP;
+        const uint32_t i = rem - l * (uint32_t)NP;
+        const T *tree = t ? mn : sum;
+        T v = (T)0;
+        if (tree && i < (uint32_t)n) {
+          const int64_t ix = __ldg(index + i) - index_base;
+          if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
         }
-        const bool take_min = (((tid & j) == 0) == ((tid & k) == 0));
-        k32 = (take_min == (other < k32)) ? other : k32;
+        sib[e] = v;
       }
+      __syncthreads();
     }
-    key = k32;
-  } else {
-    int flip = 0;
-    for (int k = 2; k <= NP; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        unsigned long long other;
-        if (j >= 32) {
-          unsigned long long *buf = xbuf + flip * NP;
-          buf[tid] = key;
-          __syncthreads();
-          other = buf[tid ^ j];
-          flip ^= 1;
-        } else {
-          other = shfl_xor_u64(key, j);
-        }
-        const bool take_min = (((tid & j) == 0) == ((tid & k) == 0));
-        key = (take_min == (other < key)) ? other : key;
-      }
-    }
-  }
-  RLB_TICK(3);
+    RLB_TICK(4);
 
-  // ---- 3. heads: the first entry of each run of equal leaves is its last writer.  No compaction: everything below
-  // works on the sorted array as it is (entries that are not heads are simply dead).
-  const uint32_t leaf_field = key32 ? ((uint32_t)key >> pos_bits) : (uint32_t)(key >> 32);
-  const bool key_valid = key32 ? (leaf_field != none32) : (leaf_field != 0xffffffffu);
-  const uint32_t myleaf = key_valid ? leaf_field : 0xffffffffu;
-  const uint32_t pos = (uint32_t)(NP - 1) - (uint32_t)(key & (unsigned long long)(NP - 1));
-  sleaf[tid] = myleaf;
-  spos[tid] = pos;
-  cp_async_wait_all();
-  // the sibling tile: every helper has stored its share into this CTA's shared memory once phase 2 completes
-  cluster_wait_acquire();     // phase 1
-  cluster_arrive_relaxed();   // phase 2
-  cluster_wait_acquire();
-  __syncthreads();
-  if (csize == 1 && bot > 0) {
-    // (launched without helpers: fetch the siblings here -- correct, just slow)
-    const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
-    for (uint32_t e = tid; e < total; e += NP) {
-      const uint32_t t = e >= per_tree;
-      const uint32_t rem = e - t * per_tree;
-      const uint32_t l = rem / (uint32_t)NP;
-      const uint32_t i = rem - l * (uint32_t)NP;
-      const T *tree = t ? mn : sum;
-      T v = (T)0;
-      if (tree && i < (uint32_t)n) {
-        const int64_t ix = __ldg(index + i) - index_base;
-        if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
-      }
-      sib[e] = v;
-    }
-    __syncthreads();
-  }
-  RLB_TICK(4);
-
-  // ---- 4. per head j: merge level L_j, and WHERE its hand-over goes (only merges below the cut hand over)
-  const uint32_t left = tid > 0 ? sleaf[tid - 1] : 0u;
-  bool alive = key_valid && (tid == 0 || left != myleaf);
-  const uint32_t leafnode = (uint32_t)capacity + myleaf;
-  int L = 0;
-  T vs = (T)0, vm = (T)0;
-  T *hand_s = nullptr, *hand_m = nullptr;
-  if (alive) {
-    const T v = sraw[pos];
-    vs = v;
-    vm = v;
-    L = (tid == 0) ? depth + 1 : 32 - __clz(myleaf ^ left);
-    if (L <= bot) {
-      const uint32_t prefix = myleaf >> L;
-      int lo = 0, hi = tid;  // first index in [0, tid) whose leaf has this prefix: the leader of the group on my left
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((sleaf[mid] >> L) < prefix) lo = mid + 1; else hi = mid;
-      }
-      const uint32_t lead_pos = spos[lo];
-      hand_s = sib + (size_t)(L - 1) * NP + lead_pos;
-      hand_m = sib + (size_t)bot * NP + (size_t)(L - 1) * NP + lead_pos;
-      if (L == 1) {  // sibling leaves: hand the leaf value over before the first iteration
-        *hand_s = vs;
-        *hand_m = vm;
-      }
-    }
-  }
-  if (key_valid) Lpos[pos] = L;  // (0 for the losers of a duplicated leaf; positions that hold no item stay unread)
-  {
-    const unsigned m = __reduce_or_sync(0xffffffffu, (alive && L <= bot) ? (1u << L) : 0u);
-    if (lane == 0 && m) atomicOr(&s_lmask, m);
-  }
-  __syncthreads();
-  const unsigned lmask = s_lmask;
-  RLB_TICK(5);
-
-  // ---- 5. climb below the cut.  The sibling values of the first kUpdHoist levels are pulled into registers up
-  // front (independent shared loads); a level into which somebody handed a value over is re-read after the barrier
-  // that follows the hand-over.  The parent computed at level l overwrites the (consumed) sibling slot [l][pos]: the
-  // tile doubles as the staging area the helpers scatter from.
-  T *io_s = sib + pos;
-  T *io_m = sib + (size_t)bot * NP + pos;
-  T hs[kUpdHoist], hm[kUpdHoist];
-#pragma unroll
-  for (int l = 0; l < kUpdHoist; ++l) {
-    hs[l] = (T)0;
-    hm[l] = (T)0;
-    if (l < bot) {
-      hs[l] = io_s[(size_t)l * NP];
-      hm[l] = io_m[(size_t)l * NP];
-    }
-  }
-#pragma unroll
-  for (int l = 0; l < kUpdHoist; ++l) {
-    if (l < bot) {
-      if (alive) {
-        if (L == l + 1) {
-          alive = false;  // my level-l value was handed over; the leader of the group on my left carries the parent
-        } else {
-          T os = hs[l], om = hm[l];
-          if ((lmask >> (l + 1)) & 1u) {  // somebody may have handed its value into row l (possibly my slot)
-            os = io_s[(size_t)l * NP];
-            om = io_m[(size_t)l * NP];
-          }
-          vs = tree_op<T, false>(vs, os);          // IEEE addition commutes: operand order is immaterial
-          vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
-          io_s[(size_t)l * NP] = vs;  // value of node (leaf >> (l + 1))
-          io_m[(size_t)l * NP] = vm;
-          if (L == l + 2 && L <= bot) {  // I merge at the next level: hand the value just computed to the leader
-            *hand_s = vs;
-            *hand_m = vm;
-          }
-        }
-      }
-      if ((lmask >> (l + 2)) & 1u) __syncthreads();  // somebody handed over: its leader reads it in the next iteration
-    }
-  }
-  for (int l = kUpdHoist; l < bot; ++l) {  // (trees deeper than 2^(kDenseLevels + kUpdHoist))
+    // ---- 4. per head j: merge level L_j, and WHERE its hand-over goes (only merges below the cut hand over)
+    const uint32_t left = tid > 0 ? sleaf[tid - 1] : 0u;
+    bool alive = key_valid && (tid == 0 || left != myleaf);
+    const uint32_t leafnode = (uint32_t)capacity + myleaf;
+    int L = 0;
+    T vs = (T)0, vm = (T)0;
+    T *hand_s = nullptr, *hand_m = nullptr;
     if (alive) {
-      if (L == l + 1) {
-        alive = false;
-      } else {
-        const T os = io_s[(size_t)l * NP], om = io_m[(size_t)l * NP];
-        vs = tree_op<T, false>(vs, os);
-        vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
-        io_s[(size_t)l * NP] = vs;
-        io_m[(size_t)l * NP] = vm;
-        if (L == l + 2 && L <= bot) {
+      const T v = sraw[pos];
+      vs = v;
+      vm = v;
+      L = (tid == 0) ? depth + 1 : 32 - __clz(myleaf ^ left);
+      if (L <= bot) {
+        const uint32_t prefix = myleaf >> L;
+        int lo = 0, hi = tid;  // first index in [0, tid) whose leaf has this prefix: the leader of the group on my left
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if ((sleaf[mid] >> L) < prefix) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t lead_pos = spos[lo];
+        hand_s = sib + (size_t)(L - 1) * NP + lead_pos;
+        hand_m = sib + (size_t)bot * NP + (size_t)(L - 1) * NP + lead_pos;
+        if (L == 1) {  // sibling leaves: hand the leaf value over before the first iteration
           *hand_s = vs;
           *hand_m = vm;
         }
       }
     }
-    if ((lmask >> (l + 2)) & 1u) __syncthreads();
-  }
-  RLB_TICK(6);
+    if (key_valid) Lpos[pos] = L;  // (0 for the losers of a duplicated leaf; positions that hold no item stay unread)
+    {
+      const unsigned m = __reduce_or_sync(0xffffffffu, (alive && L <= bot) ? (1u << L) : 0u);
+      if (lane == 0 && m) atomicOr(&s_lmask, m);
+    }
+    __syncthreads();
+    const unsigned lmask = s_lmask;
+    RLB_TICK(5);
 
-  // ---- 6. dense top: items that reached the cut overwrite their node, then the W - 1 nodes above are recomputed,
-  // node = op(node 2k, node 2k+1).  Each thread reduces the subtree over its own `per` consecutive cut nodes alone,
-  // warps continue with shuffles, warp 0 finishes.
-  if (alive) {
-    const uint32_t node = leafnode >> bot;  // in [W, 2W)
-    cut_s[node] = vs;
-    cut_m[node] = vm;
+    // ---- 5. climb below the cut.  The sibling values of the first kUpdHoist levels are pulled into registers up
+    // front (independent shared loads); a level into which somebody handed a value over is re-read after the barrier
+    // that follows the hand-over.  The parent computed at level l overwrites the (consumed) sibling slot [l][pos]: the
+    // tile doubles as the staging area the helpers scatter from.
+    T *io_s = sib + pos;
+    T *io_m = sib + (size_t)bot * NP + pos;
+    T hs[kUpdHoist], hm[kUpdHoist];
+#pragma unroll
+    for (int l = 0; l < kUpdHoist; ++l) {
+      hs[l] = (T)0;
+      hm[l] = (T)0;
+      if (l < bot) {
+        hs[l] = io_s[(size_t)l * NP];
+        hm[l] = io_m[(size_t)l * NP];
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < kUpdHoist; ++l) {
+      if (l < bot) {
+        if (alive) {
+          if (L == l + 1) {
+            alive = false;  // my level-l value was handed over; the leader of the group on my left carries the parent
+          } else {
+            T os = hs[l], om = hm[l];
+            if ((lmask >> (l + 1)) & 1u) {  // somebody may have handed its value into row l (possibly my slot)
+              os = io_s[(size_t)l * NP];
+              om = io_m[(size_t)l * NP];
+            }
+            vs = tree_op<T, false>(vs, os);          // IEEE addition commutes: operand order is immaterial
+            vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+            io_s[(size_t)l * NP] = vs;  // value of node (leaf >> (l + 1))
+            io_m[(size_t)l * NP] = vm;
+            if (L == l + 2 && L <= bot) {  // I merge at the next level: hand the value just computed to the leader
+              *hand_s = vs;
+              *hand_m = vm;
+            }
+          }
+        }
+        if ((lmask >> (l + 2)) & 1u) __syncthreads();  // somebody handed over: its leader reads it next iteration
+      }
+    }
+    for (int l = kUpdHoist; l < bot; ++l) {  // (trees deeper than 2^(kDenseLevels + kUpdHoist))
+      if (alive) {
+        if (L == l + 1) {
+          alive = false;
+        } else {
+          const T os = io_s[(size_t)l * NP], om = io_m[(size_t)l * NP];
+          vs = tree_op<T, false>(vs, os);
+          vm = ((myleaf >> l) & 1u) ? tree_op<T, true>(om, vm) : tree_op<T, true>(vm, om);
+          io_s[(size_t)l * NP] = vs;
+          io_m[(size_t)l * NP] = vm;
+          if (L == l + 2 && L <= bot) {
+            *hand_s = vs;
+            *hand_m = vm;
+          }
+        }
+      }
+      if ((lmask >> (l + 2)) & 1u) __syncthreads();
+    }
+    RLB_TICK(6);
+
+    // ---- 6. items that reached the cut overwrite their node of the dense top (kept in shared memory across rounds)
+    if (alive) {
+      const uint32_t node = leafnode >> bot;  // in [W, 2W)
+      cut_s[node] = vs;
+      cut_m[node] = vm;
+    }
+    if (dbg && tid == 0) dbg[12] = (long long)clock64();
+    cluster_arrive_release();  // phase 3: merge levels + staging tile final -- the helpers scatter
+    if (dbg && tid == 0) dbg[13] = (long long)clock64();
+    if (csize == 1) {
+      // without helpers (the whole tree is above the cut, or a plain launch): the leader scatters its own nodes
+      __syncthreads();
+      const int Lp = Lpos[tid];
+      if (valid && Lp > 0) {
+        const uint32_t ln = (uint32_t)(capacity + my_ix);
+        if (sum) sum[ln] = sraw[tid];
+        if (mn) mn[ln] = sraw[tid];
+        for (int l = 0; l < bot && Lp > l + 1; ++l) {
+          if (sum) sum[ln >> (l + 1)] = sib[(size_t)l * NP + tid];
+          if (mn) mn[ln >> (l + 1)] = sib[((size_t)bot + l) * NP + tid];
+        }
+      }
+    }
+    if (!last_round) {
+      cluster_wait_acquire();     // phase 3
+      cluster_arrive_release();   // phase 4 (release: a no-helper round's stores above feed the next round's loads)
+      cluster_wait_acquire();     // the round's nodes are in the trees; the tile may be refilled
+      __syncthreads();
+    }
   }
-  if (dbg && tid == 0) dbg[12] = (long long)clock64();
-  cluster_arrive_release();  // phase 3: merge levels + staging tile final -- the helpers scatter while the top is recomputed
-  if (dbg && tid == 0) dbg[13] = (long long)clock64();
+
+  // ---- 7. dense top: the W - 1 nodes above the cut are recomputed, node = op(node 2k, node 2k+1).  Each thread
+  // reduces the subtree over its own `per` consecutive cut nodes alone, warps continue with shuffles, warp 0 finishes.
   __syncthreads();
   {
     const int per = W >= NP ? W / NP : 1;      // cut nodes per thread
@@ -980,21 +1009,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   }
   RLB_TICK(7);
   if (dbg && tid == 0) dbg[32 + 1] = (long long)globaltimer_ns();
-  cluster_wait_acquire();  // phase 3 (completes at once: every helper arrived long ago)
-  if (csize == 1) {
-    // without helpers (the whole tree is above the cut, or a plain launch): the leader scatters its own nodes
-    const int Lp = Lpos[tid];
-    const int64_t ix2 = my_ix;
-    if (valid && Lp > 0) {
-      const uint32_t ln = (uint32_t)(capacity + ix2);
-      if (sum) sum[ln] = sraw[tid];
-      if (mn) mn[ln] = sraw[tid];
-      for (int l = 0; l < bot && Lp > l + 1; ++l) {
-        if (sum) sum[ln >> (l + 1)] = sib[(size_t)l * NP + tid];
-        if (mn) mn[ln >> (l + 1)] = sib[((size_t)bot + l) * NP + tid];
-      }
-    }
-  }
+  cluster_wait_acquire();    // phase 3 of the last round (every helper arrived long ago)
   cluster_arrive_relaxed();  // phase 4
   cluster_wait_acquire();    // the helpers have finished reading this CTA's shared memory
   if (dbg && tid == 0) dbg[32 + 2] = (long long)globaltimer_ns();
@@ -1144,7 +1159,7 @@ template <typename T, bool FUSED>
 static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const int64_t *index, const T *value,
                              int64_t n, int scalar, const FusedPow &fp, void *workspace, cudaStream_t st) {
   int np = 32;
-  while (np < n) np <<= 1;
+  while (np < n && np < kUpdMaxItemsPerRound) np <<= 1;   // larger batches: rounds of np items inside the launch
   const size_t smem = upd_smem_bytes<T>(np, depth);
   static bool attr_set_dev[64] = {};  // function attributes are per device
   int cur_dev = 0;
@@ -1189,10 +1204,11 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
 
 template <typename T>
 static bool update_fits_cta(int64_t n, int64_t capacity, int depth) {
-  if (n > 1024 || capacity > (int64_t(1) << 30)) return false;
+  // the cluster kernel takes up to kUpdMaxRounds rounds of kUpdMaxItemsPerRound items in ONE launch (capturable, no
+  // epoch stamp); beyond that the stamp + sweep path below is the better algorithm (it is bandwidth-, not latency-bound)
+  if (n > (int64_t)kUpdMaxRounds * kUpdMaxItemsPerRound || capacity > (int64_t(1) << 30)) return false;
   int np = 32;
-  while (np < n) np <<= 1;
-  // the helpers stage at most 4 siblings per thread in registers (and loop beyond that)
+  while (np < n && np < kUpdMaxItemsPerRound) np <<= 1;
   return upd_smem_bytes<T>(np, depth) <= (size_t)kUpdateSmemLimit;
 }
 

@@ -1,4 +1,5 @@
 """rl_b200.data -- mirror of ``torchrl.data``'s replay-buffer surface for the B200 hot path."""
+from .framestack import FrameStackStorage
 from .checkpointers import StorageCheckpointerBase, TensorStorageCheckpointer
 from .replay_buffers import (PrioritizedReplayBuffer, ReplayBuffer, TensorDictPrioritizedReplayBuffer,
                              TensorDictReplayBuffer)
@@ -12,6 +13,6 @@ from .writers import RoundRobinWriter, TensorDictRoundRobinWriter, Writer
 __all__ = [
     "ReplayBuffer", "PrioritizedReplayBuffer", "TensorDictReplayBuffer", "TensorDictPrioritizedReplayBuffer",
     "Sampler", "RandomSampler", "SamplerWithoutReplacement", "SliceSampler", "SliceSamplerWithoutReplacement", "PrioritizedSliceSampler", "PrioritizedSampler", "Storage", "ListStorage", "TensorStorage",
-    "LazyTensorStorage", "Writer", "RoundRobinWriter", "TensorDictRoundRobinWriter", "TensorDict",
+    "LazyTensorStorage", "FrameStackStorage", "Writer", "RoundRobinWriter", "TensorDictRoundRobinWriter", "TensorDict",
     "is_tensor_collection", "StorageCheckpointerBase", "TensorStorageCheckpointer", "SumSegmentTreeFp32", "SumSegmentTreeFp64", "MinSegmentTreeFp32", "MinSegmentTreeFp64",
 ]

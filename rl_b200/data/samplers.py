@@ -895,10 +895,10 @@ class PrioritizedSampler(Sampler):
         if tree_dtype == torch.float32:
             priority = priority.to(torch.float32)
             n = index.numel()
-            # batches above 1024 use an epoch-stamped scatter whose epoch would be frozen into a captured graph;
-            # under capture they are applied as consecutive chunks of <= 1024 instead (input order is preserved, so
-            # "the last duplicate wins" still holds across chunks)
-            step = 1024 if (n > 1024 and dev.type == "cuda" and torch.cuda.is_current_stream_capturing()) else n
+            # batches up to 8192 items are ONE cluster launch (rounds of 1024 inside the kernel); larger ones use an
+            # epoch-stamped scatter whose epoch would be frozen into a captured graph, so under capture they are applied
+            # as consecutive chunks of <= 8192 instead (input order is preserved: "the last duplicate wins" still holds)
+            step = 8192 if (n > 8192 and dev.type == "cuda" and torch.cuda.is_current_stream_capturing()) else n
             for lo in range(0, n, step):
                 pr = priority if priority.numel() == 1 else priority[lo:lo + step]
                 ops.backend().per_update(self._sum_tree.values, self._min_tree.values, self._sum_tree.capacity,

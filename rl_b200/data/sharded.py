@@ -142,6 +142,7 @@ class ShardedPrioritizedReplayBuffer:
         self._fin_stream = None
         self._x_stream = None    # the exchange (gather + NVLink broadcast + publish) runs here, beside the caller's stream
         self._x_done = {}        # slot -> event: that slot's previous exchange has left this GPU
+        self._x_done_cap = {}    # the same for draws issued inside the CUDA-graph capture in progress
         self._res = {}           # slot -> persistent (index, weight, leaf, psum_pmin) of the draw using it
         #: nvlink transport: issue the exchange on an internal stream so that the caller's stream goes straight on to
         #: the priority write-back / the next draw (the trees do not depend on it).  ``join_exchange()`` joins it.
@@ -237,10 +238,12 @@ class ShardedPrioritizedReplayBuffer:
         side = nv is not None and self.overlap_exchange and dev.type == "cuda"
         capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
         with self.local._replay_lock:
-            if side and not capturing and slot_i in self._x_done:
-                # the exchange that used this slot's buffers last must have left the GPU (eager mode; a captured region
-                # must not come back to a slot before join_exchange())
-                torch.cuda.current_stream(dev).wait_event(self._x_done[slot_i])
+            done = (self._x_done_cap if capturing else self._x_done).get(slot_i) if side else None
+            if done is not None:
+                # the exchange that used this slot's buffers last must have left the GPU before the tree kernel
+                # overwrites them (inside a capture: only draws of the same capture are known, and join_exchange()
+                # at its end orders everything else)
+                torch.cuda.current_stream(dev).wait_event(done)
             u = torch.rand(b_loc, device=dev, generator=smp._rng, dtype=smp._sum_tree._dtype)
             idx, _, leaf, pp = be.per_sample(smp._sum_tree.values, smp._min_tree.values, smp._max_capacity,
                                              smp._sum_tree.capacity, length, u, smp._beta, smp._semantics == "cpu",
@@ -264,11 +267,11 @@ class ShardedPrioritizedReplayBuffer:
                 self._x_stream.wait_stream(cur)
                 with torch.cuda.stream(self._x_stream):
                     exchange_kernels()
-                    if not capturing:
-                        ev = self._x_done.get(slot_i)
-                        if ev is None:
-                            ev = self._x_done[slot_i] = torch.cuda.Event()
-                        ev.record(self._x_stream)
+                    table = self._x_done_cap if capturing else self._x_done
+                    ev = table.get(slot_i)
+                    if ev is None:
+                        ev = table[slot_i] = torch.cuda.Event()
+                    ev.record(self._x_stream)
             else:
                 exchange_kernels()
         self.local_index = idx
@@ -281,6 +284,7 @@ class ShardedPrioritizedReplayBuffer:
         before a CUDA-graph capture that issued draws ends).  A no-op when nothing runs beside the caller's stream."""
         if self._x_stream is not None:
             torch.cuda.current_stream(self._x_stream.device).wait_stream(self._x_stream)
+        self._x_done_cap = {}
 
     def exchange(self) -> torch.Tensor:
         """nccl: the ONE collective, an all-gather of the packed local draws.  nvlink: nothing to issue -- the rows

@@ -25,6 +25,8 @@ GATHER_AUTO, GATHER_VECTOR, GATHER_BULK = 0, 1, 2
 MAX_LEAVES = 24
 STATUS_INDEX_OOB, STATUS_NONPOS_PSUM, STATUS_NONPOS_PMIN, STATUS_BACKOFF_FAIL = 1, 2, 4, 8
 STATUS_EXCHANGE_TIMEOUT = 16
+STATUS_FRAME_EVICTED = 32
+FRAME_ENV_SHIFT = 40
 
 _vp, _i64, _i32, _f64, _sz, _u32 = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                     ctypes.c_size_t, ctypes.c_uint32)
@@ -50,6 +52,9 @@ _SIGNATURES = {
     "rlb_shard_weights": (_i32, [_vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp]),
     "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
+    "rlb_gather_frames": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "rlb_framestack_push": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
+                                   _i64, _i64, _vp]),
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "rlb_td_lambda_return": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "rlb_affine_scan": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
@@ -63,6 +68,11 @@ _SIGNATURES = {
     "rlb_extend": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _f64,
                           _f64, _f64, _i32, _vp, _vp, _vp]),
 }
+
+
+class FrameLeaf(ctypes.Structure):
+    """``rlb_frame_leaf`` (include/rlb200.h)."""
+    _fields_ = [("fpos", _vp), ("head", _vp), ("ring", _i64), ("offset", _i32), ("reserved", _i32)]
 
 
 def exported_symbols() -> list[str]:
@@ -272,7 +282,7 @@ class CudaBackend:
         n = index.numel()
         scalar = int(priority.numel() == 1)
         index, priority = index.contiguous(), priority.contiguous()
-        scratch = torch.empty(n, dtype=torch.float32, device=dev) if n > 1024 else None
+        scratch = torch.empty(n, dtype=torch.float32, device=dev) if n > 8192 else None
         with self._Guard(dev):
             self._check(self.L.rlb_per_update(
                 self._p(sum_tree), self._p(min_tree), capacity, index.data_ptr(), priority.data_ptr(), n, scalar,
@@ -354,10 +364,32 @@ class CudaBackend:
         `peer_delta` (byte offsets, including 0) replicates every written byte into NVLink peer buffers."""
         return self.gather_plan(leaves).run(index, length, mode=mode, status=status, out=out, peer_delta=peer_delta)
 
-    def gather_plan(self, leaves: Sequence[torch.Tensor]) -> "GatherPlan":
+    def gather_plan(self, leaves: Sequence[torch.Tensor], frames: Sequence | None = None) -> "GatherPlan":
         """Pre-marshalled source side of rlb_gather for a fixed set of storage leaves (pointers, row sizes and
-        strides do not change between samples); storages cache it."""
-        return GatherPlan(self, leaves)
+        strides do not change between samples); storages cache it.  ``frames[k] = (fpos, head, ring, offset)`` marks
+        leaf k as a frame of the de-duplicated frame-stack storage (leaves[k] is the frame pool), ``None`` otherwise."""
+        return GatherPlan(self, leaves, frames)
+
+    def framestack_push(self, obs: torch.Tensor, next_obs: torch.Tensor, is_init, done, last_done: torch.Tensor,
+                        head: torch.Tensor, pool: torch.Tensor, n_envs: int, layout: int, k: int, ring: int) -> torch.Tensor:
+        """Logs the frames of ``obs.shape[0]`` transitions into ``pool`` and returns their frame words (int64 [n])."""
+        dev = self._cuda(obs, next_obs, is_init, done, last_done, head, pool)
+        n = obs.shape[0]
+        fpos = torch.empty(n, dtype=torch.int64, device=dev)
+        if n == 0:
+            return fpos
+        scratch = torch.empty(n, dtype=torch.uint8, device=dev)
+        for t in (obs, next_obs):
+            if not t[0].is_contiguous():
+                raise RuntimeError("framestack_push: the frame stacks of a transition must be contiguous")
+        frame_bytes = pool[0].numel() * pool.element_size()
+        with self._Guard(dev):
+            self._check(self.L.rlb_framestack_push(
+                obs.data_ptr(), next_obs.data_ptr(), obs.stride(0) * obs.element_size(),
+                next_obs.stride(0) * next_obs.element_size(), self._p(is_init), self._p(done), last_done.data_ptr(),
+                head.data_ptr(), pool.data_ptr(), fpos.data_ptr(), scratch.data_ptr(), n, n_envs, layout, k, frame_bytes,
+                ring, self._stream(dev)), "rlb_framestack_push")
+        return fpos
 
     def scatter(self, leaves: Sequence[torch.Tensor], data: Sequence[torch.Tensor], index: torch.Tensor, length: int,
                 status: torch.Tensor | None = None) -> None:
@@ -523,9 +555,10 @@ class RangeUpdate:
 class GatherPlan:
     """Source-side arguments of ``rlb_gather`` marshalled once for a set of [N, ...] leaves."""
 
-    def __init__(self, be: CudaBackend, leaves: Sequence[torch.Tensor]):
+    def __init__(self, be: CudaBackend, leaves: Sequence[torch.Tensor], frames: Sequence | None = None):
         self.be = be
         self.leaves = list(leaves)
+        self.frames = None if frames is None or not any(f is not None for f in frames) else list(frames)
         for t in self.leaves:
             be._check_rows(t)
         self.dev = be._cuda(*self.leaves)
@@ -540,8 +573,17 @@ class GatherPlan:
             n = len(ts)
             P, I = ctypes.c_void_p * n, ctypes.c_int64 * n
             rowb = [t.element_size() * (t[0].numel() if t.ndim > 1 else 1) for t in ts]
+            fr = None
+            if self.frames is not None and any(self.frames[k] is not None for k in ks):
+                fr = (FrameLeaf * n)()
+                for slot, k in enumerate(ks):
+                    f = self.frames[k]
+                    if f is not None:
+                        fpos, head, ring, offset = f
+                        fr[slot] = FrameLeaf(fpos.data_ptr(), None if head is None else head.data_ptr(), int(ring),
+                                             int(offset), 0)
             self.chunks.append((ks, n, P, P(*[t.data_ptr() for t in ts]), I(*rowb),
-                                I(*[t.stride(0) * t.element_size() for t in ts]), I))
+                                I(*[t.stride(0) * t.element_size() for t in ts]), I, fr))
 
     def run(self, index: torch.Tensor, length: int, mode: int = GATHER_AUTO, status: torch.Tensor | None = None,
             out: Sequence[torch.Tensor] | None = None, peer_delta: Sequence[int] | None = None) -> list[torch.Tensor]:
@@ -570,13 +612,18 @@ class GatherPlan:
             raise RuntimeError("rl_b200: cannot index an empty storage (len == 0)")
         stream = be._stream(dev)
         with be._Guard(dev):
-            for ks, n, P, srcp, rowb, sstride, I in self.chunks:
+            for ks, n, P, srcp, rowb, sstride, I, fr in self.chunks:
                 outs = [out[k] for k in ks]
                 dstp = P(*[o.data_ptr() for o in outs])
                 dstride = None
                 if strided:
                     dstride = I(*[(o.stride(0) if B > 1 else (o[0].numel() if o.ndim > 1 else 1)) * o.element_size()
                                   for o in outs])
+                if fr is not None:
+                    be._check(be.L.rlb_gather_frames(srcp, dstp, rowb, sstride, dstride, peers, n_peers, n, fr,
+                                                     index.data_ptr(), B, length, mode, be._p(status), stream),
+                              "rlb_gather_frames")
+                    continue
                 be._check(be.L.rlb_gather(srcp, dstp, rowb, sstride, dstride, peers, n_peers, n, index.data_ptr(), B,
                                           length, mode, be._p(status), stream), "rlb_gather")
         return list(out)

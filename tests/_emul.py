@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from oracle import lib as orc_lib
+from oracle import framestack_oracle as fo
 from oracle import per_oracle as po
 
 
@@ -255,14 +256,36 @@ class OracleBackend:
             return list(out)
         return res
 
-    def gather_plan(self, leaves):
+    def gather_plan(self, leaves, frames=None):
         be = self
 
         class _Plan:
             def run(self, index, length, mode=0, status=None, out=None, peer_delta=None):
-                return be.gather(leaves, index, length, mode=mode, status=status, out=out)
+                if frames is None or not any(f is not None for f in frames):
+                    return be.gather(leaves, index, length, mode=mode, status=status, out=out)
+                res = []
+                for k, (leaf, f) in enumerate(zip(leaves, frames)):
+                    if f is None:
+                        r = be.gather([leaf], index, length, status=status)[0]
+                    else:   # rlb_gather_frames: slot -> frame word -> pool row
+                        word, head, ring, off = f
+                        w = be.gather([word], index, length, status=status)[0]
+                        env, q = w >> fo.ENV_SHIFT, (w & fo.POS_MASK) + off
+                        if head is not None and status is not None and ((q < 0) | (head[env] - q > ring)).any():
+                            status |= 32
+                        r = leaf[env * ring + q.clamp(min=0) % ring]
+                    if out is not None:
+                        out[k].copy_(r)
+                    res.append(r)
+                return list(out) if out is not None else res
 
         return _Plan()
+
+    def framestack_push(self, obs, next_obs, is_init, done, last_done, head, pool, n_envs, layout, k, ring):
+        pl, hd, ld = pool.numpy(), head.numpy(), last_done.numpy()   # CPU tensors: numpy views, mutated in place
+        words = fo.push(pl, hd, ld, obs.numpy(), next_obs.numpy(), None if is_init is None else is_init.numpy(),
+                        None if done is None else done.numpy(), n_envs=n_envs, layout=layout, k=k, ring=ring)
+        return torch.from_numpy(words)
 
     def scatter(self, leaves, data, index, length, status=None):
         ix = torch.where(index < 0, index + length, index)

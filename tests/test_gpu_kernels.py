@@ -1036,3 +1036,46 @@ def test_slice_index_span_matches_oracle(cuda_backend, span, pad):
     np.testing.assert_array_equal(index.cpu().numpy(), oi)
     np.testing.assert_array_equal(trunc.cpu().numpy().reshape(-1), otr)
     assert (oseq < T).any() and (oseq >= 0).all()                                # some slices were cut
+
+
+@pytest.mark.parametrize("n", [1025, 4096, 8192])
+def test_update_rounds_in_one_launch(cuda_backend, n):
+    """Batches above 1024 items: rounds of 1024 inside ONE cluster launch (no epoch stamp, capturable).  A 6.25M-slot
+    shard (BASELINE configs[4]: capacity 2^23), heavy duplication inside and ACROSS rounds -- the last writer of a leaf
+    must win -- against the oracle; then the same call captured in a CUDA graph and replayed on fresh priorities."""
+    from rl_b200.data import PrioritizedSampler
+
+    N = 6_250_000
+    rng = np.random.default_rng(n)
+    smp = PrioritizedSampler(N, 0.6, 0.4, device=dev())
+    base = rng.integers(0, N, 2000)
+    idx = np.concatenate([rng.integers(0, N, n - n // 4), rng.choice(base, n // 4)]).astype(np.int64)
+    rng.shuffle(idx)
+    idx[-5:] = idx[:5]                                 # duplicates that span the first and the last round
+    pr = (rng.random(n, dtype=np.float32) * 4).astype(np.float32)
+    ti, tp = torch.from_numpy(idx).to(dev()), torch.from_numpy(pr).to(dev())
+    smp.update_priority(ti, tp)
+    leaves = torch.pow(tp + 1e-8, 0.6)                 # the fused pow is torch's (test_fused_pow_is_torch_pow)
+    os_, om = po.OracleTree(N, False), po.OracleTree(N, True)
+    os_[idx] = leaves.cpu().numpy()
+    om[idx] = leaves.cpu().numpy()
+    np.testing.assert_array_equal(smp._sum_tree.values.cpu().numpy()[1:], os_.values()[1:])
+    np.testing.assert_array_equal(smp._min_tree.values.cpu().numpy()[1:], om.values()[1:])
+    assert smp._max_priority[0].item() == pr.max()
+    # captured: one graph node per call, replay-safe
+    tp2 = torch.empty_like(tp)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            smp.update_priority(ti, tp2)
+    for rep in range(2):
+        pr2 = (rng.random(n, dtype=np.float32) * 4).astype(np.float32)
+        tp2.copy_(torch.from_numpy(pr2))
+        g.replay()
+        torch.cuda.synchronize()
+        l2 = torch.pow(tp2 + 1e-8, 0.6).cpu().numpy()
+        os_[idx] = l2
+        om[idx] = l2
+        np.testing.assert_array_equal(smp._sum_tree.values.cpu().numpy()[1:], os_.values()[1:])
+        np.testing.assert_array_equal(smp._min_tree.values.cpu().numpy()[1:], om.values()[1:])
