@@ -462,6 +462,18 @@ constexpr int kUpdCluster = 8;  // CTAs per update launch: the leader + seven he
 constexpr int kUpdHoist = 16;   // sibling values of this many levels are held in registers during the climb
 constexpr int kUpdMaxItemsPerRound = 1024;  // one item per thread
 constexpr int kUpdMaxRounds = 8;            // batches up to 8192 items in one launch
+constexpr int kUpdMaxItems = kUpdMaxItemsPerRound * kUpdMaxRounds;
+// Batches above one round are SPLIT OVER SEVERAL CLUSTERS by leaf range (the items of cluster g are the leaves in
+// [g, g + 1) * capacity / G): below the cut level the clusters touch disjoint nodes, so each runs the single-cluster
+// algorithm on its own compacted share; each stores its slice of the cut level and the last one to finish (ticket)
+// recomputes the dense top.  Scratch in the reserved head of the update workspace:
+constexpr int kUpdMaxGroups = 16;            // 16 clusters x 8 CTAs = 128 of the 148 SMs
+constexpr int kUpdGroupTarget = 320;         // split until a cluster's expected share is at most this
+constexpr size_t kUpdTicketOff = 0;          // u32 ticket (returns to 0 at the end of every launch)
+constexpr size_t kUpdCountOff = 256;         // i32[kUpdMaxGroups] items per cluster
+constexpr size_t kUpdIlistOff = 4096;        // i32[kUpdMaxGroups][kUpdMaxItems] shard-local leaf indices, input order
+constexpr size_t kUpdPlistOff = kUpdIlistOff + sizeof(int32_t) * kUpdMaxGroups * kUpdMaxItems;  // u16[...] input positions
+static_assert(kUpdPlistOff + sizeof(uint16_t) * kUpdMaxGroups * kUpdMaxItems <= kUpdWorkspaceHead, "workspace head");
 
 
 template <typename T>
@@ -486,6 +498,11 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
   return r;
 }
 __device__ __forceinline__ uint32_t cluster_nctarank() {
@@ -586,7 +603,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
                                                                const T *__restrict__ value_all, int n_all, int scalar,
                                                                float alpha, float eps, float *max_out,
                                                                long long *dbg, int64_t index_base,
-                                                               int64_t index_limit) {
+                                                               int64_t index_limit, int groups,
+                                                               unsigned char *__restrict__ mc_scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NP = (int)blockDim.x;          // a power of two: one item per thread and round
   const int tid = threadIdx.x;
@@ -613,20 +631,75 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   //   per round: 2  helpers -> leader: the sibling tile is complete
   //              3  leader -> helpers: merge levels, leaf values and the staging tile are final -- scatter them
   //              4  helpers -> everybody: the round's nodes are in the trees, nobody reads the leader's tile any more
+  //
+  // groups > 1 (see kUpdMaxGroups): phase 1 additionally publishes the leader's compaction of this cluster's share --
+  // local leaf indices + input positions, in input order -- and `n_all` becomes the share's size.
+  __shared__ int s_flag;
+  const uint32_t gcl = groups > 1 ? cluster_id_x() : 0u;
+  const int32_t *ilist = nullptr;   // groups > 1: my cluster's items (already shard-local and in range)
+  const uint16_t *plist = nullptr;  //             and their positions in the caller's arrays
+  if (groups > 1) {
+    int32_t *il = reinterpret_cast<int32_t *>(mc_scratch + kUpdIlistOff) + (size_t)gcl * kUpdMaxItems;
+    uint16_t *pl = reinterpret_cast<uint16_t *>(mc_scratch + kUpdPlistOff) + (size_t)gcl * kUpdMaxItems;
+    int *count = reinterpret_cast<int *>(mc_scratch + kUpdCountOff) + gcl;
+    if (crank == 0) {
+      const int64_t span = capacity / groups, lo = span * gcl;
+      int base = 0;
+      for (int c0 = 0; c0 < n_all; c0 += NP) {
+        const int i = c0 + tid;
+        int64_t ix = -1;
+        if (i < n_all) ix = __ldg(index_all + i) - index_base;
+        const bool in = ix >= 0 && ix < index_limit && ix >= lo && ix < lo + span;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wsum[tid >> 5] = (uint32_t)__popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < (NP >> 5); ++w) {
+          const int c = (int)s_wsum[w];
+          if (w < (tid >> 5)) woff += c;
+          tot += c;
+        }
+        if (in) {
+          const int at = base + woff + __popc(bal & ((1u << lane) - 1u));
+          il[at] = (int32_t)ix;
+          pl[at] = (uint16_t)i;
+        }
+        base += tot;
+        __syncthreads();
+      }
+      if (tid == 0) *count = base;
+      n_all = base;
+      cluster_arrive_release();  // phase 1: the lists are published to the helpers
+    } else {
+      cluster_arrive_relaxed();  // phase 1
+      cluster_wait_acquire();
+      n_all = __ldcg(count);
+    }
+    ilist = il;
+    plist = pl;
+    index_base = 0;
+    index_limit = capacity;
+  } else {
+    cluster_arrive_relaxed();  // phase 1
+  }
   const int rounds = (n_all + NP - 1) / NP;
-  cluster_arrive_relaxed();  // phase 1
+  // shard-local leaf index of item i of round rnd, or -1: not an item of this shard
+  auto item_ix = [&](int rnd, int i) -> int64_t {
+    if (ilist) return (int64_t)__ldcg(ilist + (size_t)rnd * NP + i);
+    const int64_t ix = __ldg(index_all + (size_t)rnd * NP + i) - index_base;
+    return (ix >= 0 && ix < index_limit) ? ix : -1;
+  };
   if (dbg && tid == 0 && crank <= 1) dbg[32 + 8 * crank] = (long long)globaltimer_ns();
 
   if (crank != 0) {
     for (int rnd = 0; rnd < rounds; ++rnd) {
-      const int64_t *index = index_all + (size_t)rnd * NP;
       const int n = min(NP, n_all - rnd * NP);
       // ---- helpers, part 1: sib[t][l][i] (in the LEADER's shared memory) = tree_t[((capacity + index[i]) >> l) ^ 1]
       // for the levels below the cut.  The loads are issued before the cluster is known to be up, the stores after.
       constexpr int kMaxPer = 4;
       const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
       const uint32_t nthreads = (csize - 1u) * (uint32_t)NP, g = (crank - 1u) * (uint32_t)NP + tid;
-      const int64_t ix_self = (tid < n) ? __ldg(index + tid) - index_base : -1;  // (part 2: the item at position tid)
+      const int64_t ix_self = (tid < n) ? item_ix(rnd, tid) : -1;  // (part 2: the item at position tid)
       T val[kMaxPer];
       uint32_t el[kMaxPer];
 #pragma unroll
@@ -641,12 +714,12 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
           const uint32_t i = rem - l * (uint32_t)NP;
           const T *tree = t ? mn : sum;
           if (tree && i < (uint32_t)n) {
-            const int64_t ix = __ldg(index + i) - index_base;
-            if (ix >= 0 && ix < index_limit) val[k] = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+            const int64_t ix = item_ix(rnd, (int)i);
+            if (ix >= 0) val[k] = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
           }
         }
       }
-      if (rnd == 0) cluster_wait_acquire();  // phase 1
+      if (rnd == 0 && groups <= 1) cluster_wait_acquire();  // phase 1
 #pragma unroll
       for (int k = 0; k < kMaxPer; ++k)
         if (el[k] < total) st_cluster(map_to_cta(sib + el[k], 0), val[k]);
@@ -658,8 +731,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         const T *tree = t ? mn : sum;
         T v = (T)0;
         if (tree && i < (uint32_t)n) {
-          const int64_t ix = __ldg(index + i) - index_base;
-          if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+          const int64_t ix = item_ix(rnd, (int)i);
+          if (ix >= 0) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
         }
         st_cluster(map_to_cta(sib + e, 0), v);
       }
@@ -677,7 +750,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       {
         const int units = (int)csize - 1, unit = (int)crank - 1, nrows = 2 * bot + 2;
         const int Lp = (int)ld_cluster_u32(map_to_cta(Lpos + tid, 0));
-        if (Lp > 0 && ix_self >= 0 && ix_self < index_limit) {
+        if (Lp > 0 && ix_self >= 0) {
           const uint32_t leafnode = (uint32_t)(capacity + ix_self);
           for (int r = unit; r < nrows; r += units) {
             if (r < 2) {
@@ -728,8 +801,6 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   const int bshift = depth > pos_bits ? depth - pos_bits : 0;   // leaf index -> one of NP buckets
 
   for (int rnd = 0; rnd < rounds; ++rnd) {
-    const int64_t *index = index_all + (size_t)rnd * NP;
-    const T *value = scalar ? value_all : value_all + (size_t)rnd * NP;
     const int n = min(NP, n_all - rnd * NP);
     const bool last_round = rnd + 1 == rounds;
     if (tid == 0) s_lmask = 0u;
@@ -740,9 +811,10 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     if (tid < n) {
       // index_base maps GLOBAL indices of a sharded buffer onto this shard; entries that fall outside
       // [0, index_limit) are skipped, like the negative "do not write" markers of samplers.py:1040-1052
-      my_ix = __ldg(index + tid) - index_base;
-      valid = (my_ix >= 0 && my_ix < index_limit);
-      raw = scalar ? __ldg(value) : __ldg(value + tid);
+      my_ix = item_ix(rnd, tid);
+      valid = my_ix >= 0;
+      const size_t at = plist ? (size_t)__ldcg(plist + (size_t)rnd * NP + tid) : (size_t)rnd * NP + tid;
+      raw = scalar ? __ldg(value_all) : __ldg(value_all + at);
     }
 
     // ---- 1. keys: (leaf index, reversed input position) -- ascending order puts the last writer first; entries that
@@ -801,8 +873,8 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
         const T *tree = t ? mn : sum;
         T v = (T)0;
         if (tree && i < (uint32_t)n) {
-          const int64_t ix = __ldg(index + i) - index_base;
-          if (ix >= 0 && ix < index_limit) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
+          const int64_t ix = item_ix(rnd, (int)i);
+          if (ix >= 0) v = ld_cg(tree + (((capacity + ix) >> l) ^ 1));
         }
         sib[e] = v;
       }
@@ -939,10 +1011,43 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     }
   }
 
+  if (rounds == 0) {  // (a cluster whose share of a split batch is empty never entered the loop)
+    cp_async_wait_all();
+    cluster_wait_acquire();  // phase 1
+  }
+  bool do_top = true;
+  if (groups > 1) {
+    // my slice of the cut level goes to the trees; the cluster that takes the last ticket reloads the whole level (the
+    // other clusters' slices) and recomputes the top
+    __syncthreads();
+    const int slice = W / groups;
+    for (int k = tid; k < slice; k += NP) {
+      const int node = W + (int)gcl * slice + k;
+      if (sum) sum[node] = cut_s[node];
+      if (mn) mn[node] = cut_m[node];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      unsigned *ticket = reinterpret_cast<unsigned *>(mc_scratch + kUpdTicketOff);
+      const unsigned t = atomicAdd(ticket, 1u);
+      s_flag = (t == (unsigned)groups - 1u);
+      if (s_flag) *ticket = 0u;  // everybody has drawn: ready for the next launch / graph replay
+      __threadfence();
+    }
+    __syncthreads();
+    do_top = s_flag != 0;
+    if (do_top) {
+      for (int k = tid; k < W; k += NP) {
+        if (sum) cut_s[W + k] = ld_cg(sum + W + k);
+        if (mn) cut_m[W + k] = ld_cg(mn + W + k);
+      }
+    }
+  }
   // ---- 7. dense top: the W - 1 nodes above the cut are recomputed, node = op(node 2k, node 2k+1).  Each thread
   // reduces the subtree over its own `per` consecutive cut nodes alone, warps continue with shuffles, warp 0 finishes.
   __syncthreads();
-  {
+  if (do_top) {
     const int per = W >= NP ? W / NP : 1;      // cut nodes per thread
     const int A = W >= NP ? NP : W;            // threads that own a subtree; its root is node A + tid
     const bool act = tid < A;
@@ -1003,15 +1108,19 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
   }
   __syncthreads();
   if (dbg && tid == 0) dbg[14] = (long long)clock64();
-  for (int k = 1 + tid; k < W; k += NP) {
-    if (sum) sum[k] = cut_s[k];
-    if (mn) mn[k] = cut_m[k];
+  if (do_top) {
+    for (int k = 1 + tid; k < W; k += NP) {
+      if (sum) sum[k] = cut_s[k];
+      if (mn) mn[k] = cut_m[k];
+    }
   }
   RLB_TICK(7);
   if (dbg && tid == 0) dbg[32 + 1] = (long long)globaltimer_ns();
-  cluster_wait_acquire();    // phase 3 of the last round (every helper arrived long ago)
-  cluster_arrive_relaxed();  // phase 4
-  cluster_wait_acquire();    // the helpers have finished reading this CTA's shared memory
+  if (rounds > 0) {
+    cluster_wait_acquire();    // phase 3 of the last round (every helper arrived long ago)
+    cluster_arrive_relaxed();  // phase 4
+    cluster_wait_acquire();    // the helpers have finished reading this CTA's shared memory
+  }
   if (dbg && tid == 0) dbg[32 + 2] = (long long)globaltimer_ns();
 }
 
@@ -1147,6 +1256,36 @@ static int tree_rebuild_impl(void *tree_, int64_t capacity, int is_min, cudaStre
 
 constexpr int kUpdateSmemLimit = 224 * 1024;  // dynamic shared memory the single-CTA update may use
 
+static int getenv_int(const char *name, int fallback) {  // (A/B measurements: RLB_UPDATE_GROUPS=1 keeps one cluster)
+  static int cached = -2;
+  if (cached == -2) {
+    const char *e = getenv(name);
+    cached = e ? atoi(e) : fallback;
+  }
+  return cached;
+}
+
+// threads per CTA (= items per round) and clusters for a batch of n items
+static void upd_shape(int64_t n, int depth, int *np_out, int *groups_out) {
+  int np = 32, groups = 1;
+  const int bot = upd_bot_levels(depth);
+  const int64_t W = int64_t(1) << (depth - bot);
+  if (n > kUpdMaxItemsPerRound && bot > 0 && getenv_int("RLB_UPDATE_GROUPS", -1) != 1) {
+    groups = 2;
+    while (groups < kUpdMaxGroups && groups < W && n / groups > kUpdGroupTarget) groups <<= 1;
+    const int forced = getenv_int("RLB_UPDATE_GROUPS", -1);
+    if (forced > 1 && forced <= kUpdMaxGroups && (forced & (forced - 1)) == 0 && forced <= W) groups = forced;
+    // a cluster's share is binomial around n / groups: a quarter of head-room keeps it to one round almost always
+    const int64_t share = n / groups + n / groups / 4;
+    np = 256;
+    while (np < share && np < kUpdMaxItemsPerRound) np <<= 1;
+  } else {
+    while (np < n && np < kUpdMaxItemsPerRound) np <<= 1;  // larger batches: rounds of np items inside the launch
+  }
+  *np_out = np;
+  *groups_out = groups;
+}
+
 struct FusedPow {
   bool on = false;
   float alpha = 0.f, eps = 0.f;
@@ -1158,8 +1297,8 @@ struct FusedPow {
 template <typename T, bool FUSED>
 static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const int64_t *index, const T *value,
                              int64_t n, int scalar, const FusedPow &fp, void *workspace, cudaStream_t st) {
-  int np = 32;
-  while (np < n && np < kUpdMaxItemsPerRound) np <<= 1;   // larger batches: rounds of np items inside the launch
+  int np = 32, groups = 1;
+  upd_shape(n, depth, &np, &groups);
   const size_t smem = upd_smem_bytes<T>(np, depth);
   static bool attr_set_dev[64] = {};  // function attributes are per device
   int cur_dev = 0;
@@ -1180,10 +1319,9 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   // one cluster: the leader + the helpers (none needed when the whole tree is above the cut)
   const int bot = upd_bot_levels(depth);
   const unsigned cluster = bot > 0 ? kUpdCluster : 1;
-  (void)workspace;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(cluster);
+  cfg.gridDim = dim3(cluster * (unsigned)groups);
   cfg.blockDim = dim3(np);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -1196,7 +1334,8 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   cfg.numAttrs = 1;
   int rc = check_cuda(cudaLaunchKernelEx(&cfg, tree_update_cta_kernel<T, FUSED>, sum, mn, capacity, depth, index, value,
                                          (int)n, scalar, fp.alpha, fp.eps, fp.max_out, g_debug_ticks, fp.index_base,
-                                         fp.index_limit < 0 ? capacity : fp.index_limit),
+                                         fp.index_limit < 0 ? capacity : fp.index_limit, groups,
+                                         static_cast<unsigned char *>(workspace)),
                       "tree_update_cta_kernel");
   if (rc) return rc;
   return check_launch("tree_update_cta_kernel");
@@ -1204,11 +1343,11 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
 
 template <typename T>
 static bool update_fits_cta(int64_t n, int64_t capacity, int depth) {
-  // the cluster kernel takes up to kUpdMaxRounds rounds of kUpdMaxItemsPerRound items in ONE launch (capturable, no
-  // epoch stamp); beyond that the stamp + sweep path below is the better algorithm (it is bandwidth-, not latency-bound)
-  if (n > (int64_t)kUpdMaxRounds * kUpdMaxItemsPerRound || capacity > (int64_t(1) << 30)) return false;
-  int np = 32;
-  while (np < n && np < kUpdMaxItemsPerRound) np <<= 1;
+  // the cluster kernel takes up to kUpdMaxItems items in ONE launch (capturable, no epoch stamp); beyond that the
+  // stamp + sweep path below is the better algorithm (it is bandwidth-, not latency-bound)
+  if (n > (int64_t)kUpdMaxItems || capacity > (int64_t(1) << 30)) return false;
+  int np = 32, groups = 1;
+  upd_shape(n, depth, &np, &groups);
   return upd_smem_bytes<T>(np, depth) <= (size_t)kUpdateSmemLimit;
 }
 

@@ -84,7 +84,7 @@ class FrameStackStorage(Storage):
         self._head = None           # int64 [n_envs]: frames logged per env
         self._last_done = None      # uint8 [n_envs]
         self._ring = None
-        self._plan = None
+        self._plans = {}            # materialize? -> (plan, the inner leaves it was built for, keys, kept leaf numbers)
         self._status = None
 
     # ---- layout ------------------------------------------------------------------------------------
@@ -167,7 +167,6 @@ class FrameStackStorage(Storage):
                                "break the frame sharing")
         rest, obs, nxt = self._push(data)
         self._inner.set(cursor, rest, set_cursor=True)
-        self._plan = self._plan if self._plan_valid() else None
         if self.validate:
             self._read_back(cursor, obs, nxt)
 
@@ -179,7 +178,6 @@ class FrameStackStorage(Storage):
         fused ``rlb_extend`` launch of the inner storage."""
         rest, obs, nxt = self._push(data)
         self._inner._extend_range(cursor, n, rest, trees)
-        self._plan = self._plan if self._plan_valid() else None
         if self.validate:
             self._read_back(torch.arange(cursor, cursor + n, device=self.device) % self.max_size, obs, nxt)
 
@@ -194,23 +192,44 @@ class FrameStackStorage(Storage):
                                "per environment (obs[t] != next[t-1] inside an episode, or a wrong n_envs / batch_layout)")
 
     # ---- reads -------------------------------------------------------------------------------------
-    def _plan_valid(self) -> bool:
-        return self._plan is not None and self._plan[1] is self._inner._leaves
-
-    def _gather_plan(self):
-        if not self._plan_valid():
+    def _gather_plan(self, materialize: bool):
+        """The launch plan: the inner leaves (minus the frame words) as ordinary leaves + the frame pool once per output
+        frame -- 2 k of them (both stacks written out) or k + 1 (one window the two stacks are views of)."""
+        cached = self._plans.get(materialize)
+        if cached is None or cached[1] is not self._inner._leaves or cached[4] is not self._pool:
             inner = self._inner
             keys = [_norm_key(k) for k in inner._spec[1]]
             keep = [i for i, k in enumerate(keys) if k != (FRAME_WORD_KEY,)]
             word = inner._leaves[keys.index((FRAME_WORD_KEY,))]
             k = self.num_frames
-            offsets = ([j - k for j in range(k)] + [j - k + 1 for j in range(k)]) if self.materialize \
+            offsets = ([j - k for j in range(k)] + [j - k + 1 for j in range(k)]) if materialize \
                 else [j - k for j in range(k + 1)]
             leaves = [inner._leaves[i] for i in keep] + [self._pool] * len(offsets)
             frames = [None] * len(keep) + [(word, self._head, self._ring, off) for off in offsets]
             plan = ops.backend().gather_plan(leaves, frames)
-            self._plan = (plan, inner._leaves, [keys[i] for i in keep], keep)
-        return self._plan
+            cached = self._plans[materialize] = (plan, inner._leaves, [keys[i] for i in keep], keep, self._pool)
+        return cached[:4]
+
+    # -- the packed form the sharded buffer exchanges: the other leaves + ONE [k + 1, *frame] window per transition
+    def _packed_templates(self) -> list:
+        _, _, _, keep = self._gather_plan(False)
+        return [self._inner._leaves[i] for i in keep] + \
+            [torch.empty((1, self.num_frames + 1, *self._pool.shape[1:]), dtype=self._pool.dtype, device=self.device)]
+
+    def _gather_packed(self, index: torch.Tensor, out: list, peer_delta=None) -> None:
+        """``out``: one [B, ...] (possibly strided) view per template; the last one is the window."""
+        plan, _, _, keep = self._gather_plan(False)
+        win = out[-1]
+        st = self._status_word()
+        plan.run(index, len(self), status=st.word, out=list(out[:len(keep)]) + [win[:, j] for j in range(self.num_frames + 1)],
+                 peer_delta=peer_delta)
+        st.arm()
+
+    def _unpack(self, views: list, batch_size):
+        _, _, keys, keep = self._gather_plan(False)
+        win, k = views[-1], self.num_frames
+        return TensorDict._from_leaves(keys + [self.obs_key, self.next_key], list(views[:len(keep)]) + [win[:, :k], win[:, 1:]],
+                                       batch_size)
 
     def _status_word(self):
         if self._status is None:
@@ -233,7 +252,7 @@ class FrameStackStorage(Storage):
             self._raise(self._status.check())
 
     def _gather(self, index: torch.Tensor):
-        plan, _, keys, keep = self._gather_plan()
+        plan, _, keys, keep = self._gather_plan(self.materialize)
         B, k = index.numel(), self.num_frames
         frame = tuple(self._pool.shape[1:])
         inner = self._inner
@@ -295,7 +314,7 @@ class FrameStackStorage(Storage):
 
     def load_state_dict(self, sd: dict) -> None:
         self._inner.load_state_dict(sd["inner"])
-        self._plan = None
+        self._plans = {}
         if sd["pool"] is not None:
             self._ring, self.num_frames = sd["ring"], sd["num_frames"]
             self._pool = sd["pool"].to(self.device)
@@ -334,7 +353,7 @@ class FrameStackStorage(Storage):
         _read_leaf(path / "frames" / "pool.memmap", shape, dt, self._pool, shape[0])
         self._head = torch.tensor(meta["head"], dtype=torch.int64, device=self.device)
         self._last_done = torch.tensor(meta["last_done"], dtype=torch.uint8, device=self.device)
-        self._plan = None
+        self._plans = {}
 
     def __repr__(self) -> str:
         return (f"FrameStackStorage(max_size={self.max_size}, len={len(self)}, n_envs={self.n_envs}, "

@@ -100,12 +100,16 @@ class ShardedPrioritizedReplayBuffer:
         pipeline (bool): ``sample()`` returns the PREVIOUS draw (the first call draws twice).
         n_buffers (int): receive-buffer slots of the nvlink transport (default 4 pipelined, 2 otherwise).
         exchange_timeout_s (float): bound of the in-kernel wait for the peers' rows.
+        storage: this rank's shard storage (``shard_capacity`` slots); default ``LazyTensorStorage``.  With a
+            ``FrameStackStorage`` the exchanged row carries the k + 1 distinct frames of a transition instead of both
+            k-frame stacks (35.3 KB instead of 56.4 KB per Atari transition), and ``obs`` / ``next`` of the returned batch
+            are two views of that window.
     """
 
     def __init__(self, *, alpha: float, beta: float, capacity: int, eps: float = 1e-8, priority_key: str = "td_error",
                  batch_size: int | None = None, device="cuda", generator=None, process_group=None,
                  transport: str = "auto", pipeline: bool = False, n_buffers: int | None = None,
-                 exchange_timeout_s: float = 10.0):
+                 exchange_timeout_s: float = 10.0, storage=None):
         import torch.distributed as dist
 
         self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
@@ -120,8 +124,10 @@ class ShardedPrioritizedReplayBuffer:
         self.device = torch.device(device)
         self.local = TensorDictPrioritizedReplayBuffer(
             alpha=alpha, beta=beta, eps=eps, priority_key=priority_key,
-            storage=LazyTensorStorage(self.shard_capacity, device=self.device),
+            storage=storage if storage is not None else LazyTensorStorage(self.shard_capacity, device=self.device),
             batch_size=None if batch_size is None else batch_size // self.world, generator=generator)
+        if storage is not None and storage.max_size != self.shard_capacity:
+            raise ValueError(f"the shard storage must hold {self.shard_capacity} slots, got {storage.max_size}")
         if transport not in ("auto", "nvlink", "nccl"):
             raise ValueError("transport must be 'auto', 'nvlink' or 'nccl'")
         self.transport = transport
@@ -205,7 +211,7 @@ class ShardedPrioritizedReplayBuffer:
         be = ops.backend()
         dev = smp._sum_tree.device
         if self._layout is None:
-            self._layout = _PackedLayout(st._leaves)
+            self._layout = _PackedLayout(st._packed_templates() if hasattr(st, "_packed_templates") else st._leaves)
         lay = self._layout
         peers = flags = None
         nv = None
@@ -255,7 +261,10 @@ class ShardedPrioritizedReplayBuffer:
 
             def exchange_kernels():
                 # with `peers` the rows are written into every rank's receive buffer by this very launch
-                be.gather(st._leaves, idx, length, out=lay.leaf_views(send), peer_delta=peers)
+                if hasattr(st, "_gather_packed"):   # FrameStackStorage: k + 1 unique frames per transition on the wire
+                    st._gather_packed(idx, lay.leaf_views(send), peer_delta=peers)
+                else:
+                    be.gather(st._leaves, idx, length, out=lay.leaf_views(send), peer_delta=peers)
                 # trailers; with `flags`: "my rows of this draw are in your buffer" to every rank (release)
                 be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity, peer_delta=peers,
                               flags=flags, seq_counter=None if flags is None else self._ctr[0:1], rank=self.rank)
@@ -346,7 +355,8 @@ class ShardedPrioritizedReplayBuffer:
         cur = self._cur if draw is None else draw
         lay, recv, smp = self._layout, cur["recv"], self.local.sampler
         leaves = lay.leaf_views(recv)
-        batch = unflatten_data(leaves, self.local.storage._spec, (cur["bs"],))
+        st = self.local.storage
+        batch = st._unpack(leaves, (cur["bs"],)) if hasattr(st, "_unpack") else unflatten_data(leaves, st._spec, (cur["bs"],))
         if cur["nvlink"]:
             weight, gidx = ops.backend().shard_weights(recv, lay.meta, smp._beta, flags=self._symm[1],
                                                        wait_counter=self._ctr[1:2], n_ranks=self.world,

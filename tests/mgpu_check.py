@@ -153,8 +153,36 @@ def main():
             for k in KEYS:
                 assert torch.equal(batch.get(k).cpu(), prev_expect[k]), ("graph", it, k)
         prev_expect = expect
+    # ---- a FrameStackStorage shard: k + 1 unique frames per transition on the wire, same batches as the plain shard
+    from rl_b200.data import FrameStackStorage
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    from test_framestack import _batches
+
+    bufs = []
+    for fs in (True, False):
+        g = torch.Generator(device=dev).manual_seed(300 + rank)
+        bufs.append(ShardedPrioritizedReplayBuffer(
+            alpha=0.6, beta=0.4, capacity=4096 * world, batch_size=B, device=dev, generator=g, transport="nvlink",
+            storage=FrameStackStorage(4096, n_envs=4, device=dev) if fs else None))
+    for td in _batches(4, 256, 64, "env_major", seed=40 + rank, pad="same", frame=(84, 84), dev=dev, min_len=20, max_len=90):
+        td.set("td_error", torch.rand(td.shape[0], device=dev, generator=torch.Generator(device=dev).manual_seed(3)))
+        for rb in bufs:
+            rb.extend(td.clone())
+        x, y = (rb.sample() for rb in bufs)
+        torch.cuda.synchronize()
+        for rb in bufs:
+            rb.check_exchange()
+        for k in ("index", "pixels", ("next", "pixels"), "action", ("next", "reward"), "priority_weight"):
+            assert torch.equal(x.get(k), y.get(k)), ("framestack shard", k)
+        pr = torch.rand(B, device=dev, generator=torch.Generator(device=dev).manual_seed(9))
+        for rb, batch in zip(bufs, (x, y)):
+            rb.update_priority(batch.get("index"), pr)
+    bufs[0].storage.check_index_status()
+    assert bufs[0]._layout.row < 0.65 * bufs[1]._layout.row
     dist.barrier()
     if rank == 0:
+        print(f"framestack shard: {bufs[0]._layout.row} B per exchanged transition instead of {bufs[1]._layout.row}")
         print(f"mgpu_check ok: world={world}, nvlink == nvlink-pipelined == nccl == rank-order concat of index-exact "
               f"local draws; captured pipelined step replayed over {rb.n_buffers} slots")
     dist.destroy_process_group()

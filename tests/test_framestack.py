@@ -210,3 +210,27 @@ def test_framestack_eviction_is_reported():
     st.get(torch.arange(0, 8, device=dev))
     with pytest.raises(RuntimeError, match="frame_capacity"):
         st.check_index_status()
+
+
+def test_sharded_buffer_over_framestack_storage_host_logic(emul):
+    """The sharded buffer with a FrameStackStorage shard: the exchanged row carries the k + 1 distinct frames (one window),
+    and the batch equals the plain sharded buffer's fed the same stream with the same generator."""
+    from rl_b200.data.sharded import ShardedPrioritizedReplayBuffer
+
+    mk = lambda: torch.Generator().manual_seed(5)
+    a = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=128, batch_size=32, device="cpu", generator=mk(),
+                                       storage=FrameStackStorage(128, n_envs=2, device="cpu", min_episode_length=1))
+    b = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=128, batch_size=32, device="cpu", generator=mk())
+    for td in _batches(2, 80, 8, "env_major", seed=21, pad="same"):
+        td.set("td_error", torch.rand(td.shape[0], generator=torch.Generator().manual_seed(int(td.shape[0]))))
+        a.extend(td.clone())
+        b.extend(td.clone())
+        x, y = a.sample(), b.sample()
+        for key in ("index", "pixels", ("next", "pixels"), "action", ("next", "reward"), "priority_weight"):
+            assert torch.equal(x.get(key), y.get(key)), key
+        a.update_priority(x.get("index"), torch.ones(32))
+        b.update_priority(y.get("index"), torch.ones(32))
+    frame = 6 * 5
+    assert b._layout.row - a._layout.row >= 3 * frame - 16      # 5 frames instead of 8 on the wire
+    win = x.get("pixels")
+    assert win.stride(0) >= 5 * frame                            # obs / next are views of one [B, k + 1, ...] window

@@ -1079,3 +1079,60 @@ def test_update_rounds_in_one_launch(cuda_backend, n):
         om[idx] = l2
         np.testing.assert_array_equal(smp._sum_tree.values.cpu().numpy()[1:], os_.values()[1:])
         np.testing.assert_array_equal(smp._min_tree.values.cpu().numpy()[1:], om.values()[1:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", ["one-range", "two-ranges", "sharded", "fp64-plain"])
+def test_update_split_over_clusters_skewed(cuda_backend, shape):
+    """The multi-cluster split of large batches with lopsided leaf ranges: every item in ONE cluster's range (the others
+    get empty shares, that one runs several rounds), two far-apart ranges, global indices of a sharded buffer (entries
+    outside the shard are skipped), and the plain fp64 tree update -- all bit-exact against the oracle."""
+    rng = np.random.default_rng(7)
+    n = 4096
+    if shape == "fp64-plain":
+        from rl_b200.data import SumSegmentTreeFp64
+
+        N = 3_000_000
+        tree = SumSegmentTreeFp64(N, dev())
+        idx = rng.integers(0, N, n).astype(np.int64)
+        idx[100:200] = idx[:100]
+        val = rng.random(n)
+        tree[torch.from_numpy(idx).to(dev())] = torch.from_numpy(val).to(dev())
+        cap = tree.capacity
+        want = np.zeros(2 * cap)
+        want[cap + idx] = val                                         # (numpy fancy assignment: the last duplicate wins)
+        level = want[cap:]
+        while len(level) > 1:                                         # every node = left child + right child, in fp64
+            level = level[0::2] + level[1::2]
+            want[len(level):2 * len(level)] = level
+        np.testing.assert_array_equal(tree.values.cpu().numpy()[1:], want[1:])
+        return
+    from rl_b200.data import PrioritizedSampler
+
+    N = 6_250_000
+    smp = PrioritizedSampler(N, 0.6, 0.4, device=dev())
+    base, limit = 0, N
+    if shape == "one-range":
+        idx = rng.integers(5_000_000, 5_000_000 + 3000, n)          # heavy duplication inside 1/16 of the leaves
+    elif shape == "two-ranges":
+        idx = np.concatenate([rng.integers(0, 40_000, n // 2), rng.integers(6_000_000, N, n // 2)])
+        rng.shuffle(idx)
+    else:
+        base, limit = 3 * N, N                                        # this shard owns [3N, 4N) of a 8N global buffer
+        idx = rng.integers(0, 8 * N, n)
+        idx[: n // 2] = rng.integers(3 * N, 4 * N, n // 2)
+        rng.shuffle(idx)
+    idx = idx.astype(np.int64)
+    pr = (rng.random(n, dtype=np.float32) * 4).astype(np.float32)
+    ti, tp = torch.from_numpy(idx).to(dev()), torch.from_numpy(pr).to(dev())
+    for rep in range(2):                                              # (the ticket must be back at zero for the second call)
+        smp.update_priority(ti, tp, index_base=base, index_limit=limit) if shape == "sharded" else smp.update_priority(ti, tp)
+    torch.cuda.synchronize()
+    mine = (idx >= base) & (idx < base + limit)
+    leaves = torch.pow(tp + 1e-8, 0.6).cpu().numpy()
+    os_, om = po.OracleTree(N, False), po.OracleTree(N, True)
+    os_[idx[mine] - base] = leaves[mine]
+    om[idx[mine] - base] = leaves[mine]
+    np.testing.assert_array_equal(smp._sum_tree.values.cpu().numpy()[1:], os_.values()[1:])
+    np.testing.assert_array_equal(smp._min_tree.values.cpu().numpy()[1:], om.values()[1:])
+    assert smp._max_priority[0].item() == pr[mine].max()
