@@ -811,6 +811,26 @@ def make_rows(kind: str, n: int, dev, g):
         "td_error": torch.rand(n, device=dev, generator=g)}, [n])
 
 
+STREAM_ENVS, STREAM_STEPS = 8, 512
+
+
+def make_stream_chunk(dev, g):
+    """8 environment streams x 512 steps of 4-stacked 84x84 frames, flattened env-major like a collector batch.  The
+    stream is periodic (its first stack is made of its own last frames), so writing the chunk again continues it."""
+    from rl_b200.data import TensorDict
+
+    E, T, k = STREAM_ENVS, STREAM_STEPS, 4
+    frames = torch.randint(0, 256, (T, E, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+    win = torch.cat([frames[-k:], frames]).unfold(0, k + 1, 1).permute(1, 0, 4, 2, 3)   # [E, T, k + 1, 84, 84]
+    n = E * T
+    return TensorDict({
+        "pixels": win[:, :, :k].reshape(n, k, 84, 84), "action": torch.randint(0, 18, (n, 1), device=dev, generator=g),
+        "next": {"pixels": win[:, :, 1:].reshape(n, k, 84, 84), "reward": torch.randn(n, device=dev, generator=g),
+                 "done": torch.zeros(n, 1, dtype=torch.bool, device=dev),
+                 "terminated": torch.zeros(n, 1, dtype=torch.bool, device=dev)},
+        "td_error": torch.rand(n, device=dev, generator=g)}, [n])
+
+
 def build_sharded(dev, capacity_per_rank: int, world: int, rank: int, batch_per_rank: int = BATCH, kind: str = "atari",
                   fresh_rows: bool = True):
     """One shard per rank of a capacity-sharded buffer (weak scaling), filled with synthetic transitions.
@@ -818,9 +838,21 @@ def build_sharded(dev, capacity_per_rank: int, world: int, rank: int, batch_per_
     from rl_b200.data.sharded import ShardedPrioritizedReplayBuffer
 
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    storage = None
+    if kind == "atari_stream":
+        from rl_b200.data import FrameStackStorage
+
+        storage = FrameStackStorage(capacity_per_rank, n_envs=STREAM_ENVS, device=dev, min_episode_length=64)
     rb = ShardedPrioritizedReplayBuffer(alpha=ALPHA, beta=BETA, capacity=capacity_per_rank * world,
                                         batch_size=batch_per_rank * world, device=dev, generator=g, pipeline=True,
-                                        n_buffers=N_BUFFERS)
+                                        n_buffers=N_BUFFERS, storage=storage)
+    if kind == "atari_stream":
+        td = make_stream_chunk(dev, g)
+        assert capacity_per_rank % td.batch_size[0] == 0
+        for _ in range(capacity_per_rank // td.batch_size[0]):
+            td.set("td_error", torch.rand(td.batch_size[0], device=dev, generator=g))
+            rb.extend(td)
+        return rb, g
     chunk = 50_000 if kind == "atari" else 250_000
     td = None
     for lo in range(0, capacity_per_rank, chunk):
@@ -872,9 +904,14 @@ def dist_parity_check(rb, dev, rank: int, world: int) -> dict:
         ok = False
         detail.append("index")
     keys = [k for k in batch.keys(True, True) if k not in ("index", "priority_weight")]
-    data = unflatten_leaves(st)
+    if hasattr(st, "_gather_packed"):   # frame-stack shard: the rows are the storage's own (single-GPU) tensor-index read
+        mine = st.get(idx)
+        rows = {k: mine.get(k) for k in keys}
+    else:
+        data = unflatten_leaves(st)
+        rows = {k: data[k][idx] for k in keys}
     for k in keys:
-        if not torch.equal(batch.get(k), gathered(data[k][idx])):
+        if not torch.equal(batch.get(k), gathered(rows[k])):
             ok = False
             detail.append(str(k))
     w = batch.get("priority_weight")
@@ -1058,7 +1095,7 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
     gc.collect()
     torch.cuda.empty_cache()
     extra = {}
-    for name in ("c4", "c5"):
+    for name in ("c4", "c4_framestack", "c5"):
         try:
             extra[name] = sharded_workload(name, dev, rank, world, max(args.steps, 50), be)
         except Exception as e:  # noqa: BLE001
@@ -1104,7 +1141,7 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
                       "graph_error": graph_err, "eager_value": round(per_step / (ms_eager * 1e-3), 1),
                       "eager_sample_us": round(ms_sample * 1e3, 2)},
         "clocks": clk,
-        "c4": extra.get("c4"), "c5": extra.get("c5"),
+        "c4": extra.get("c4"), "c4_framestack": extra.get("c4_framestack"), "c5": extra.get("c5"),
     }
     return result
 
@@ -1118,7 +1155,8 @@ def sharded_workload(name: str, dev, rank: int, world: int, steps: int, be) -> d
     import torch.distributed as dist
     from rl_b200.graphs import CudaGraphStep
 
-    spec = {"c4": dict(cap=1_250_000, b_loc=128, kind="atari"), "c5": dict(cap=6_250_000, b_loc=512, kind="mujoco")}[name]
+    spec = {"c4": dict(cap=1_250_000, b_loc=128, kind="atari"), "c5": dict(cap=6_250_000, b_loc=512, kind="mujoco"),
+            "c4_framestack": dict(cap=305 * STREAM_ENVS * STREAM_STEPS, b_loc=128, kind="atari_stream")}[name]
     cap, b_loc, kind = spec["cap"], spec["b_loc"], spec["kind"]
     rb, g = build_sharded(dev, cap, world, rank, batch_per_rank=b_loc, kind=kind, fresh_rows=False)
     gb = b_loc * world
@@ -1189,10 +1227,17 @@ def sharded_workload(name: str, dev, rank: int, world: int, steps: int, be) -> d
     lay = rb._layout
     row = sum(c[1] for c in lay.cols)
     ingress = (world - 1) * b_loc * lay.row
-    out = {"workload": ("C4 sharded PER 10M DQN-shaped Atari transitions, batch 1024 @ 8 GPUs" if name == "c4" else
-                        "C5 50M HBM-resident SAC transitions (obs 376 / act 17 f32), batch 4096 @ 8 GPUs + TD-error write-back"),
+    labels = {"c4": "C4 sharded PER 10M DQN-shaped Atari transitions, batch 1024 @ 8 GPUs",
+              "c5": "C5 50M HBM-resident SAC transitions (obs 376 / act 17 f32), batch 4096 @ 8 GPUs + TD-error write-back",
+              "c4_framestack": "C4 on de-duplicated frame-stack shards (FrameStackStorage, 8 env streams per rank): the same "
+                               "transitions, k + 1 = 5 distinct frames per exchanged row instead of 8"}
+    if hasattr(rb.storage, "frame_bytes_per_transition"):
+        hbm = int(rb.storage._pool.numel() + sum(l[0].numel() * l.element_size() for l in rb.storage._inner._leaves) * cap)
+    else:
+        hbm = cap * row
+    out = {"workload": labels[name],
            "n_gpus": world, "capacity_global": cap * world, "capacity_per_gpu": cap, "global_batch": gb,
-           "batch_per_gpu": b_loc, "row_bytes": row, "hbm_bytes_per_gpu": cap * row,
+           "batch_per_gpu": b_loc, "row_bytes": row, "hbm_bytes_per_gpu": hbm,
            "ms_per_step": round(ms, 5), "transitions_per_s": round(gb / (ms * 1e-3), 1), "launch": launch,
            "eager_sample_us": round(ms_eager * 1e3, 2),
            "nvlink_bytes_per_step_per_gpu": ingress, "nvlink_ingress_GBps": round(ingress / (ms * 1e-3) / 1e9, 1),
