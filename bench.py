@@ -948,21 +948,27 @@ def exchange_probe(rb, dev, world: int) -> dict:
     b_loc = rb._batch_size // world
     g = torch.Generator(device=dev).manual_seed(17 + rb.rank)
     idxs = [torch.randint(0, len(st), (b_loc,), device=dev, generator=g) for _ in range(2 * N_BUFFERS)]
-    fns = []
-    for k, ix in enumerate(idxs):
-        send = bufs[k % N_BUFFERS][rb.rank * b_loc:(rb.rank + 1) * b_loc]
-        fns.append(lambda ix=ix, send=send: be.gather(st._leaves, ix, len(st), out=lay.leaf_views(send), peer_delta=peers))
-    torch.cuda.synchronize(dev)
-    dist.barrier()
-    us = graph_us(fns, dev)
-    t = torch.tensor([us], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    us = float(t.item())
     payload = b_loc * sum(c[1] for c in lay.cols)
-    dist.barrier()
-    return {"gather_broadcast_us": round(us, 2), "payload_bytes_per_rank": payload,
-            "nvlink_egress_GBps": round((world - 1) * payload / us / 1e3, 1),
-            "frac_of_nvlink_per_dir": round((world - 1) * payload / us / 1e3 / NVLINK_GBPS_PER_DIR, 3)}
+    out = {"payload_bytes_per_rank": payload, "multicast_available": rb._mc_delta != 0}
+    for name, mc in (("unicast", 0), ("multicast", rb._mc_delta)):
+        if name == "multicast" and not mc:
+            continue
+        fns = []
+        for k, ix in enumerate(idxs):
+            send = bufs[k % N_BUFFERS][rb.rank * b_loc:(rb.rank + 1) * b_loc]
+            fns.append(lambda ix=ix, send=send, mc=mc: be.gather(st._leaves, ix, len(st), out=lay.leaf_views(send),
+                                                                 peer_delta=peers, multicast_delta=mc))
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        us = graph_us(fns, dev)
+        t = torch.tensor([us], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item())
+        dist.barrier()
+        out[name] = {"gather_broadcast_us": round(us, 2),
+                     "nvlink_ingress_GBps": round((world - 1) * payload / us / 1e3, 1),
+                     "frac_of_nvlink_per_dir": round((world - 1) * payload / us / 1e3 / NVLINK_GBPS_PER_DIR, 3)}
+    return out
 
 
 def run_distributed(args, dev, rank: int, world: int) -> dict:
@@ -1086,6 +1092,7 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
     if ms_graph_long <= 0:
         ms_graph_long = None
     payload = BATCH * sum(c[1] for c in rb._layout.cols)
+    multicast = bool(getattr(rb, "_mc_delta", 0))
     row_packed = rb._layout.row
     n_leaves = len(rb.storage._leaves)
     # free the C2 buffer before the bigger workloads
@@ -1129,12 +1136,13 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
                 "note": "eager python API, pinned host buffers; every rank lands ITS rows of the global minibatch + its GAE outputs on the host"},
         "gpu_launches": 6 * args.steps,  # ours per step: per_sample, gather(+broadcast), pack(+publish), weights(+wait), update, gae
         **parity,
-        "nvlink": {"ingress_bytes_per_step_per_gpu": ingress, "egress_bytes_per_step_per_gpu": ingress,
+        "nvlink": {"ingress_bytes_per_step_per_gpu": ingress,
+                   "egress_bytes_per_step_per_gpu": payload if multicast else ingress, "multicast": multicast,
                    "nvlink_ingress_GBps": round(ingress / (ms * 1e-3) / 1e9, 1),
-                   "nvlink_egress_GBps": round(ingress / (ms * 1e-3) / 1e9, 1),
+                   "nvlink_egress_GBps": round((payload if multicast else ingress) / (ms * 1e-3) / 1e9, 1),
                    "wire_bound_us_per_step": round(ingress / (NVLINK_GBPS_PER_DIR * 1e9) * 1e6, 1),
                    "payload_bytes_per_rank": payload, "exchange_kernel": xprobe,
-                   "note": "every rank receives the whole global minibatch (all-gather semantics): ingress = egress = (N-1) x 256 packed rows"},
+                   "note": "every rank receives the whole global minibatch (all-gather semantics): ingress = (N-1) x 256 packed rows; egress the same with unicast copies, 1 x with multicast stores (the switch replicates)"},
         "breakdown": {"eager_ms_per_step": round(ms_eager, 5),
                       "graph_ms_per_step": None if ms_graph is None else round(ms_graph, 5),
                       "graph_ms_per_step_long_run": None if ms_graph_long is None else round(ms_graph_long, 5),

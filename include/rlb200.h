@@ -200,14 +200,27 @@ typedef struct rlb_frame_leaf {
   int32_t reserved;
 } rlb_frame_leaf;
 
-/* rlb_gather whose leaf k, when frames[k].fpos != NULL, reads row  env * ring + (position + offset) mod ring  of
- * src[k] (the frame pool) for the slot index[b]: the stacks are rebuilt by the gather kernel itself, written into
- * consecutive frame slots of the batch through dst / dst_stride_bytes.  The other leaves behave as in rlb_gather. */
-int rlb_gather_frames(const void *const *src /*[host]*/, void *const *dst /*[host]*/, const int64_t *row_bytes /*[host]*/,
-                      const int64_t *src_stride_bytes /*[host]*/, const int64_t *dst_stride_bytes /*[host] or NULL*/,
-                      const int64_t *peer_delta /*[host] or NULL*/, int n_peers, int n_leaves,
-                      const rlb_frame_leaf *frames /*[host] n_leaves*/, const int64_t *index /*[dev] B*/, int64_t B,
-                      int64_t len, int mode, int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
+/* rlb_gather with options (all optional; a zeroed struct makes it rlb_gather without peers):
+ *   frames            leaf k, when frames[k].fpos != NULL, reads row  env * ring + (position + offset) mod ring  of src[k]
+ *                     (the frame pool) for the slot index[b]: the stacks are rebuilt by the gather kernel itself, written
+ *                     into consecutive frame slots of the batch through dst / dst_stride_bytes;
+ *   peer_delta        as in rlb_gather;
+ *   multicast_delta   != 0: byte offset from dst[k] to its alias in an NVLink-SHARP multicast mapping of the symmetric
+ *                     receive buffers (cuMulticast* / torch symmetric memory `multicast_ptr`).  Wide rows are then stored
+ *                     ONCE with multimem.st -- the switch replicates them into every member GPU, this one included --
+ *                     instead of n_peers unicast copies; narrow leaves still go through peer_delta. */
+typedef struct rlb_gather_opts {
+  const rlb_frame_leaf *frames; /* [host] n_leaves entries, or NULL */
+  const int64_t *peer_delta;    /* [host] n_peers entries, or NULL */
+  int64_t multicast_delta;
+  int32_t n_peers;
+  int32_t reserved;
+} rlb_gather_opts;
+
+int rlb_gather_ex(const void *const *src /*[host]*/, void *const *dst /*[host]*/, const int64_t *row_bytes /*[host]*/,
+                  const int64_t *src_stride_bytes /*[host]*/, const int64_t *dst_stride_bytes /*[host] or NULL*/,
+                  int n_leaves, const rlb_gather_opts *opts /*[host]*/, const int64_t *index /*[dev] B*/, int64_t B,
+                  int64_t len, int mode, int32_t *status /*[dev] or NULL*/, rlb_stream_t stream);
 
 /* Logs the frames of n incoming transitions (n_envs environments x n / n_envs consecutive steps each; layout 0: row
  * i = env * steps + step, the flattened [E, T] collector batch; layout 1: row i = step * n_envs + env) and returns their

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE -- CPU restatement of the de-duplicated frame-stack storage (include/rlb200.h: rlb_framestack_push,
-rlb_gather_frames).
+rlb_gather_ex).
 
 The reference has no such storage: what it does with the same transitions is keep both stacks of every transition verbatim
 (TensorStorage.set / get, torchrl/data/replay_buffers/storages.py:1028-1096 and :1098-1130).  The parity statement of the

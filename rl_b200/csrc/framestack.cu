@@ -11,7 +11,7 @@
 //
 // so that transition i, whose newest frame sits at log position p, always has
 //   obs[i, j] = log[p - k + j],  next[i, j] = log[p - k + 1 + j]          (j in [0, k)).
-// Its frame word  env << 40 | p  is the only per-transition pixel state; rlb_gather_frames turns (slot -> frame word ->
+// Its frame word  env << 40 | p  is the only per-transition pixel state; rlb_gather_ex turns (slot -> frame word ->
 // pool rows) inside the gather launch.  Byte copies only: a batch read back is bit-identical to what was written as long as
 // the stream really is a frame stack (FrameStackStorage(validate=True) checks exactly that).
 //

@@ -79,6 +79,9 @@ struct GatherParams {
   // others are the same location of the symmetric receive buffer on peer GPUs (NVLink peer memory), so the
   // gathered rows are broadcast by the gather kernel itself -- no separate all-gather
   int64_t peer_delta[RLB_MAX_PEERS];
+  // != 0: dst + mc_delta is the same location in a multicast mapping of all ranks' buffers: bulk-role stages are stored
+  // once with multimem.st (replicated by the NVSwitch into every member, this GPU included) instead of n_peers copies
+  int64_t mc_delta;
   int n_peers;
   int pad0_;
   const int64_t *index;  // null: the implicit modular range  (ibase + b) % len  (the writer's cursor; B <= len)
@@ -223,6 +226,13 @@ __device__ __forceinline__ void vector_role(const GatherParams &P, int64_t first
   }
 }
 
+// one 16-byte store into a multicast mapping: the NVSwitch writes it into every GPU bound to the multicast object
+__device__ __forceinline__ void multimem_st16(void *mc_addr, const uint4 v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
 // ---- bulk-DMA role -----------------------------------------------------------------------------------
 struct PipeSmem {
   uint64_t full[kStages];   // mbarriers: stage filled by the g->s bulk copy
@@ -327,7 +337,19 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
     // ---- retire the oldest staged piece: wait for its bytes, then DMA it out
     if (n_stored < n_loaded) {
       const int stage = (int)(n_stored % kStages);
-      if (lane == 0) {
+      if (P.mc_delta != 0) {
+        // multicast: the whole warp copies the stage out of shared memory, 16 bytes per lane and store
+        mbar_wait_parity(&my->full[stage], (uint32_t)((n_stored / kStages) & 1));
+        __syncwarp();  // (lane 0 wrote the piece's destination and size)
+        const uint8_t *sp = my_ring + (size_t)stage * kChunk;
+        uint8_t *dp = my->dst[stage] + P.mc_delta;
+        const uint32_t units = my->bytes[stage] >> 4;
+        for (uint32_t u = lane; u < units; u += 32) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(sp + ((size_t)u << 4));
+          multimem_st16(dp + ((size_t)u << 4), v);
+        }
+        __syncwarp();  // the stage may be refilled once every lane has read it
+      } else if (lane == 0) {
         mbar_wait_parity(&my->full[stage], (uint32_t)((n_stored / kStages) & 1));
         fence_proxy_async_smem();
         for (int p = 0; p < P.n_peers; ++p)  // local buffer and, when sharded, every peer's receive buffer
@@ -404,7 +426,7 @@ static int plan_rows(GatherParams &P, int &vec_ctas_out, const void *const *src,
                      const int64_t *row_bytes, const int64_t *stride, const int64_t *ostride,
                      const int64_t *peer_delta, int n_peers, int n_leaves, const int64_t *index, int64_t ibase,
                      int64_t B, int64_t len, int mode, int32_t *status, const char *who, int reserved_sms = 0,
-                     const rlb_frame_leaf *frames = nullptr) {
+                     const rlb_frame_leaf *frames = nullptr, int64_t mc_delta = 0) {
   RLB_REQUIRE(src && dst && row_bytes && stride, RLB_EINVAL, "%s: null argument", who);
   const int sms = sm_count();
   if (sms <= 0) return RLB_ENODEV;
@@ -412,6 +434,8 @@ static int plan_rows(GatherParams &P, int &vec_ctas_out, const void *const *src,
   RLB_REQUIRE(n_peers >= 0 && n_peers <= RLB_MAX_PEERS && (n_peers == 0 || peer_delta), RLB_ELIMIT,
               "%s: n_peers=%d outside [0, %d] or null peer_delta", who, n_peers, RLB_MAX_PEERS);
   memset(&P, 0, sizeof(P));
+  RLB_REQUIRE(mc_delta % 16 == 0 && (mc_delta == 0 || !SCATTER), RLB_EINVAL, "%s: bad multicast_delta", who);
+  P.mc_delta = mc_delta;
   P.n_peers = n_peers > 0 ? n_peers : 1;  // no peer list = the local buffer only
   for (int p = 0; p < n_peers; ++p) {
     RLB_REQUIRE(peer_delta[p] % 16 == 0, RLB_EINVAL, "%s: peer_delta[%d] is not 16-byte aligned", who, p);
@@ -516,7 +540,7 @@ template <bool SCATTER>
 static int launch_rows(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *stride,
                        const int64_t *ostride, const int64_t *peer_delta, int n_peers, int n_leaves,
                        const int64_t *index, int64_t B, int64_t len, int mode, int32_t *status, cudaStream_t st,
-                       const char *who, const rlb_frame_leaf *frames = nullptr) {
+                       const char *who, const rlb_frame_leaf *frames = nullptr, int64_t mc_delta = 0) {
   RLB_REQUIRE(n_leaves >= 0 && n_leaves <= RLB_MAX_LEAVES, RLB_ELIMIT, "%s: n_leaves=%d exceeds RLB_MAX_LEAVES=%d",
               who, n_leaves, RLB_MAX_LEAVES);
   RLB_REQUIRE(B >= 0 && len >= 0, RLB_EINVAL, "%s: negative B or len", who);
@@ -529,7 +553,7 @@ static int launch_rows(const void *const *src, void *const *dst, const int64_t *
   // exchange (the priority write-back's cluster, the next draw) instead of parking a 161 KB CTA on every one
   const int reserved = n_peers > 1 ? kPeerReservedSms : 0;
   int rc = plan_rows<SCATTER>(P, vec_ctas, src, dst, row_bytes, stride, ostride, peer_delta, n_peers, n_leaves, index,
-                              0, B, len, mode, status, who, reserved, frames);
+                              0, B, len, mode, status, who, reserved, frames, mc_delta);
   if (rc) return rc;
   const size_t smem = P.bulk_ctas > 0 ? kBulkSmemBytes : 0;
   static bool attr_set_dev[64] = {};  // function attributes are per device
@@ -567,15 +591,15 @@ int rlb_gather(const void *const *src, void *const *dst, const int64_t *row_byte
                             index, B, len, mode, status, as_stream(stream), "rlb_gather");
 }
 
-int rlb_gather_frames(const void *const *src, void *const *dst, const int64_t *row_bytes,
-                      const int64_t *src_stride_bytes, const int64_t *dst_stride_bytes, const int64_t *peer_delta,
-                      int n_peers, int n_leaves, const rlb_frame_leaf *frames, const int64_t *index, int64_t B,
-                      int64_t len, int mode, int32_t *status, rlb_stream_t stream) {
+int rlb_gather_ex(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *src_stride_bytes,
+                  const int64_t *dst_stride_bytes, int n_leaves, const rlb_gather_opts *opts, const int64_t *index,
+                  int64_t B, int64_t len, int mode, int32_t *status, rlb_stream_t stream) {
   RLB_REQUIRE(mode == RLB_GATHER_AUTO || mode == RLB_GATHER_VECTOR || mode == RLB_GATHER_BULK, RLB_EINVAL,
-              "rlb_gather_frames: unknown mode %d", mode);
-  RLB_REQUIRE(frames, RLB_EINVAL, "rlb_gather_frames: null frames");
-  return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, dst_stride_bytes, peer_delta, n_peers, n_leaves,
-                            index, B, len, mode, status, as_stream(stream), "rlb_gather_frames", frames);
+              "rlb_gather_ex: unknown mode %d", mode);
+  RLB_REQUIRE(opts, RLB_EINVAL, "rlb_gather_ex: null opts");
+  return launch_rows<false>(src, dst, row_bytes, src_stride_bytes, dst_stride_bytes, opts->peer_delta, opts->n_peers,
+                            n_leaves, index, B, len, mode, status, as_stream(stream), "rlb_gather_ex", opts->frames,
+                            opts->multicast_delta);
 }
 
 int rlb_scatter(const void *const *src, void *const *dst, const int64_t *row_bytes, const int64_t *dst_stride_bytes,

@@ -8,7 +8,7 @@ transitions (same ``set`` / ``get`` / ``len`` contract, same batch out, bit for 
   * write (``rlb_framestack_push``, csrc/framestack.cu): per environment stream, an episode's first transition logs its k
     observation frames and its newest next-observation frame, every other transition logs the newest frame only; the
     transition keeps one int64 frame word (environment, log position).
-  * read: the stacks are rebuilt by the gather kernel itself (``rlb_gather_frames``, csrc/gather.cu resolve_row) -- frame
+  * read: the stacks are rebuilt by the gather kernel itself (``rlb_gather_ex``, csrc/gather.cu resolve_row) -- frame
     j of ``obs`` is log position p - k + j, frame j of ``next`` is p - k + 1 + j -- in the SAME launch that gathers the other
     leaves.  The k + 1 distinct frames of a transition are read from HBM once (the second use hits L2).
 
@@ -216,13 +216,13 @@ class FrameStackStorage(Storage):
         return [self._inner._leaves[i] for i in keep] + \
             [torch.empty((1, self.num_frames + 1, *self._pool.shape[1:]), dtype=self._pool.dtype, device=self.device)]
 
-    def _gather_packed(self, index: torch.Tensor, out: list, peer_delta=None) -> None:
+    def _gather_packed(self, index: torch.Tensor, out: list, peer_delta=None, multicast_delta: int = 0) -> None:
         """``out``: one [B, ...] (possibly strided) view per template; the last one is the window."""
         plan, _, _, keep = self._gather_plan(False)
         win = out[-1]
         st = self._status_word()
         plan.run(index, len(self), status=st.word, out=list(out[:len(keep)]) + [win[:, j] for j in range(self.num_frames + 1)],
-                 peer_delta=peer_delta)
+                 peer_delta=peer_delta, multicast_delta=multicast_delta)
         st.arm()
 
     def _unpack(self, views: list, batch_size):

@@ -717,7 +717,7 @@ class PrioritizedSampler(Sampler):
         return self._epoch
 
     def _tree_workspace(self, n: int):
-        if self._workspace is None:  # ticket + sibling scratch (<= 1024 items) and stamps (larger batches)
+        if self._workspace is None:  # ticket + per-cluster item lists (<= 8192 items) and stamps (larger batches)
             self._workspace = ops.backend().tree_workspace(self._max_capacity, self._sum_tree.device)
         return self._workspace
 
@@ -895,7 +895,7 @@ class PrioritizedSampler(Sampler):
         if tree_dtype == torch.float32:
             priority = priority.to(torch.float32)
             n = index.numel()
-            # batches up to 8192 items are ONE cluster launch (rounds of 1024 inside the kernel); larger ones use an
+            # batches up to 8192 items are ONE launch (one cluster up to 1024 items, up to 16 above); larger ones use an
             # epoch-stamped scatter whose epoch would be frozen into a captured graph, so under capture they are applied
             # as consecutive chunks of <= 8192 instead (input order is preserved: "the last duplicate wins" still holds)
             step = 8192 if (n > 8192 and dev.type == "cuda" and torch.cuda.is_current_stream_capturing()) else n

@@ -33,6 +33,7 @@ sampled indices, so it can be issued right after the tree kernel, concurrently w
 """
 from __future__ import annotations
 
+import os
 
 import torch
 
@@ -100,6 +101,10 @@ class ShardedPrioritizedReplayBuffer:
         pipeline (bool): ``sample()`` returns the PREVIOUS draw (the first call draws twice).
         n_buffers (int): receive-buffer slots of the nvlink transport (default 4 pipelined, 2 otherwise).
         exchange_timeout_s (float): bound of the in-kernel wait for the peers' rows.
+        multicast (bool | "auto"): nvlink transport: store the wide rows ONCE through the NVLink-SHARP multicast mapping of
+            the symmetric receive buffers (``multimem.st``; the switch replicates them into every rank) instead of one copy
+            per rank -- NVLink egress per rank drops from (W - 1) x to 1 x the local draw.  "auto": when torch's symmetric
+            memory exposes a multicast pointer (env ``RLB_SHARD_MULTICAST=0/1`` overrides).
         storage: this rank's shard storage (``shard_capacity`` slots); default ``LazyTensorStorage``.  With a
             ``FrameStackStorage`` the exchanged row carries the k + 1 distinct frames of a transition instead of both
             k-frame stacks (35.3 KB instead of 56.4 KB per Atari transition), and ``obs`` / ``next`` of the returned batch
@@ -109,7 +114,7 @@ class ShardedPrioritizedReplayBuffer:
     def __init__(self, *, alpha: float, beta: float, capacity: int, eps: float = 1e-8, priority_key: str = "td_error",
                  batch_size: int | None = None, device="cuda", generator=None, process_group=None,
                  transport: str = "auto", pipeline: bool = False, n_buffers: int | None = None,
-                 exchange_timeout_s: float = 10.0, storage=None):
+                 exchange_timeout_s: float = 10.0, storage=None, multicast: bool | str = "auto"):
         import torch.distributed as dist
 
         self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
@@ -136,6 +141,9 @@ class ShardedPrioritizedReplayBuffer:
         if self.n_buffers < (3 if pipeline else 2):
             raise ValueError("n_buffers must be >= 2 (>= 3 when pipelined)")
         self.exchange_timeout_s = float(exchange_timeout_s)
+        env = os.environ.get("RLB_SHARD_MULTICAST")
+        self.multicast = multicast if env is None else {"0": False, "1": True}.get(env, "auto")
+        self._mc_delta = 0       # byte offset from my symmetric allocation to its NVLink multicast alias (0: unicast copies)
         self._last_gidx = None
         self._symm = None        # (buffers [n_buffers, B, row], flags u64[W], handle, peer byte offsets)
         self._draws = 0          # host-side count of issued draws: picks the receive slot
@@ -261,10 +269,11 @@ class ShardedPrioritizedReplayBuffer:
 
             def exchange_kernels():
                 # with `peers` the rows are written into every rank's receive buffer by this very launch
+                mc = self._mc_delta if peers is not None else 0
                 if hasattr(st, "_gather_packed"):   # FrameStackStorage: k + 1 unique frames per transition on the wire
-                    st._gather_packed(idx, lay.leaf_views(send), peer_delta=peers)
+                    st._gather_packed(idx, lay.leaf_views(send), peer_delta=peers, multicast_delta=mc)
                 else:
-                    be.gather(st._leaves, idx, length, out=lay.leaf_views(send), peer_delta=peers)
+                    be.gather(st._leaves, idx, length, out=lay.leaf_views(send), peer_delta=peers, multicast_delta=mc)
                 # trailers; with `flags`: "my rows of this draw are in your buffer" to every rank (release)
                 be.shard_pack(send, lay.meta, idx, leaf, pp, self.rank * self.shard_capacity, peer_delta=peers,
                               flags=flags, seq_counter=None if flags is None else self._ctr[0:1], rank=self.rank)
@@ -332,6 +341,17 @@ class ShardedPrioritizedReplayBuffer:
             raw.zero_()
             torch.cuda.synchronize(dev)
             self._dist.barrier(group=self.group)   # nobody publishes into flags that are not zeroed yet
+            mc = 0
+            if self.multicast in (True, "auto"):
+                try:
+                    mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                except Exception:  # a fabric / driver without NVLink SHARP: unicast copies
+                    mc = 0
+                if self.multicast is True and not mc:
+                    raise RuntimeError("multicast=True, but the symmetric allocation has no multicast mapping")
+            self._mc_delta = (mc - raw.data_ptr()) if mc else 0
+            if self._mc_delta % 16:
+                self._mc_delta = 0
             flags = raw[:self._FLAG_BYTES].view(torch.int64)[:self.world]
             bufs = raw[self._FLAG_BYTES:].view(self.n_buffers, batch_size, row)
             self._ctr = torch.zeros(2, dtype=torch.int64, device=dev)

@@ -11,8 +11,9 @@ This is the B200-idiomatic replacement for the reference's ``compilable=True`` /
 
 Caveats (all checked or documented): the storage length, batch size, beta and every tensor passed in by
 reference are frozen at capture time -- re-capture when they change; random draws are fresh on every replay
-(the generator's Philox offset is advanced by the graph); ``update_priority`` batches above 1024 use an
-epoch-stamped scatter that is not replay-safe and refuse to be captured.
+(the generator's Philox offset is advanced by the graph); ``update_priority`` batches up to 8192 items are one
+replay-safe cluster launch, larger ones are applied under capture as consecutive chunks of 8192 (the epoch-stamped
+path of very large eager batches is not replay-safe).
 """
 from __future__ import annotations
 

@@ -52,7 +52,7 @@ _SIGNATURES = {
     "rlb_shard_weights": (_i32, [_vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp]),
     "rlb_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "rlb_scatter": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp]),
-    "rlb_gather_frames": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "rlb_gather_ex": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "rlb_framestack_push": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
                                    _i64, _i64, _vp]),
     "rlb_gae": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
@@ -73,6 +73,11 @@ _SIGNATURES = {
 class FrameLeaf(ctypes.Structure):
     """``rlb_frame_leaf`` (include/rlb200.h)."""
     _fields_ = [("fpos", _vp), ("head", _vp), ("ring", _i64), ("offset", _i32), ("reserved", _i32)]
+
+
+class GatherOpts(ctypes.Structure):
+    """``rlb_gather_opts`` (include/rlb200.h)."""
+    _fields_ = [("frames", _vp), ("peer_delta", _vp), ("multicast_delta", _i64), ("n_peers", _i32), ("reserved", _i32)]
 
 
 def exported_symbols() -> list[str]:
@@ -359,10 +364,12 @@ class CudaBackend:
 
     def gather(self, leaves: Sequence[torch.Tensor], index: torch.Tensor, length: int, mode: int = GATHER_AUTO,
                status: torch.Tensor | None = None, out: Sequence[torch.Tensor] | None = None,
-               peer_delta: Sequence[int] | None = None) -> list[torch.Tensor]:
+               peer_delta: Sequence[int] | None = None, multicast_delta: int = 0) -> list[torch.Tensor]:
         """out[k][b] = leaves[k][index[b]].  `out` may be given (rows may be strided views into a packed buffer);
-        `peer_delta` (byte offsets, including 0) replicates every written byte into NVLink peer buffers."""
-        return self.gather_plan(leaves).run(index, length, mode=mode, status=status, out=out, peer_delta=peer_delta)
+        `peer_delta` (byte offsets, including 0) replicates every written byte into NVLink peer buffers;
+        `multicast_delta`: offset of the NVLink multicast alias of `out` (wide rows are then stored once)."""
+        return self.gather_plan(leaves).run(index, length, mode=mode, status=status, out=out, peer_delta=peer_delta,
+                                            multicast_delta=multicast_delta)
 
     def gather_plan(self, leaves: Sequence[torch.Tensor], frames: Sequence | None = None) -> "GatherPlan":
         """Pre-marshalled source side of rlb_gather for a fixed set of storage leaves (pointers, row sizes and
@@ -586,7 +593,8 @@ class GatherPlan:
                                 I(*[t.stride(0) * t.element_size() for t in ts]), I, fr))
 
     def run(self, index: torch.Tensor, length: int, mode: int = GATHER_AUTO, status: torch.Tensor | None = None,
-            out: Sequence[torch.Tensor] | None = None, peer_delta: Sequence[int] | None = None) -> list[torch.Tensor]:
+            out: Sequence[torch.Tensor] | None = None, peer_delta: Sequence[int] | None = None,
+            multicast_delta: int = 0) -> list[torch.Tensor]:
         be = self.be
         n_peers = 0 if peer_delta is None else len(peer_delta)
         peers = (ctypes.c_int64 * n_peers)(*peer_delta) if n_peers else None
@@ -619,10 +627,12 @@ class GatherPlan:
                 if strided:
                     dstride = I(*[(o.stride(0) if B > 1 else (o[0].numel() if o.ndim > 1 else 1)) * o.element_size()
                                   for o in outs])
-                if fr is not None:
-                    be._check(be.L.rlb_gather_frames(srcp, dstp, rowb, sstride, dstride, peers, n_peers, n, fr,
-                                                     index.data_ptr(), B, length, mode, be._p(status), stream),
-                              "rlb_gather_frames")
+                if fr is not None or multicast_delta:
+                    opts = GatherOpts(None if fr is None else ctypes.cast(fr, _vp),
+                                      None if peers is None else ctypes.cast(peers, _vp), int(multicast_delta), n_peers, 0)
+                    be._check(be.L.rlb_gather_ex(srcp, dstp, rowb, sstride, dstride, n, ctypes.byref(opts),
+                                                 index.data_ptr(), B, length, mode, be._p(status), stream),
+                              "rlb_gather_ex")
                     continue
                 be._check(be.L.rlb_gather(srcp, dstp, rowb, sstride, dstride, peers, n_peers, n, index.data_ptr(), B,
                                           length, mode, be._p(status), stream), "rlb_gather")

@@ -243,7 +243,7 @@ class OracleBackend:
         return torch.pow((p / S) / (mn / S).min(), -beta), gidx
 
     # ---- storage rows
-    def gather(self, leaves, index, length, mode=0, status=None, out=None, peer_delta=None):
+    def gather(self, leaves, index, length, mode=0, status=None, out=None, peer_delta=None, multicast_delta=0):
         ix = torch.where(index < 0, index + length, index)
         if ((ix < 0) | (ix >= length)).any():
             if status is not None:
@@ -260,14 +260,14 @@ class OracleBackend:
         be = self
 
         class _Plan:
-            def run(self, index, length, mode=0, status=None, out=None, peer_delta=None):
+            def run(self, index, length, mode=0, status=None, out=None, peer_delta=None, multicast_delta=0):
                 if frames is None or not any(f is not None for f in frames):
                     return be.gather(leaves, index, length, mode=mode, status=status, out=out)
                 res = []
                 for k, (leaf, f) in enumerate(zip(leaves, frames)):
                     if f is None:
                         r = be.gather([leaf], index, length, status=status)[0]
-                    else:   # rlb_gather_frames: slot -> frame word -> pool row
+                    else:   # rlb_gather_ex: slot -> frame word -> pool row
                         word, head, ring, off = f
                         w = be.gather([word], index, length, status=status)[0]
                         env, q = w >> fo.ENV_SHIFT, (w & fo.POS_MASK) + off

@@ -68,10 +68,12 @@ def main():
         return {k: torch.cat([e[k] for e in everyone]) for k in KEYS}
 
     results = {}
-    for mode in ("nvlink", "nvlink-pipelined", "nccl"):
+    mc_used = False
+    for mode in ("nvlink", "nvlink-unicast", "nvlink-pipelined", "nccl"):
         g = torch.Generator(device=dev).manual_seed(7 + rank)
         rb = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=cap, batch_size=B, device=dev, generator=g,
-                                            transport=mode.split("-")[0], pipeline=mode.endswith("pipelined"))
+                                            transport=mode.split("-")[0], pipeline=mode.endswith("pipelined"),
+                                            multicast=False if mode.endswith("unicast") else "auto")
         rb.extend(data.clone())
         outs, queue = [], deque()
         for it in range(6):  # every receive slot comes round at least once
@@ -106,11 +108,14 @@ def main():
         assert not queue
         results[mode] = outs
         assert (rb._symm not in (None, False)) == mode.startswith("nvlink")
+        mc_used = mc_used or rb._mc_delta != 0
+        assert not (mode.endswith("unicast") and rb._mc_delta)
     # the plain nvlink and nccl runs see identical trees and draws: bit-equal batches (the pipelined run applies its
     # write-backs one draw later, so its later batches legitimately differ)
-    for a, b in zip(results["nvlink"], results["nccl"]):
-        for k in a:
-            assert torch.equal(a[k], b[k]), k
+    for name in ("nvlink", "nvlink-unicast"):
+        for a, b in zip(results[name], results["nccl"]):
+            for k in a:
+                assert torch.equal(a[k], b[k]), (name, k)
     for k in results["nvlink"][0]:
         assert torch.equal(results["nvlink"][0][k], results["nvlink-pipelined"][0][k]), k
 
@@ -183,6 +188,7 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"framestack shard: {bufs[0]._layout.row} B per exchanged transition instead of {bufs[1]._layout.row}")
+        print(f"multicast (multimem.st through the NVSwitch) {'ACTIVE' if mc_used else 'not available: unicast copies'}")
         print(f"mgpu_check ok: world={world}, nvlink == nvlink-pipelined == nccl == rank-order concat of index-exact "
               f"local draws; captured pipelined step replayed over {rb.n_buffers} slots")
     dist.destroy_process_group()
