@@ -344,9 +344,18 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
         const uint8_t *sp = my_ring + (size_t)stage * kChunk;
         uint8_t *dp = my->dst[stage] + P.mc_delta;
         const uint32_t units = my->bytes[stage] >> 4;
-        for (uint32_t u = lane; u < units; u += 32) {
-          const uint4 v = *reinterpret_cast<const uint4 *>(sp + ((size_t)u << 4));
-          multimem_st16(dp + ((size_t)u << 4), v);
+        for (uint32_t u0 = 0; u0 < units; u0 += 128) {  // four independent 16-byte loads, then four stores, per lane
+          uint4 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t u = u0 + (uint32_t)q * 32u + lane;
+            if (u < units) v[q] = *reinterpret_cast<const uint4 *>(sp + ((size_t)u << 4));
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t u = u0 + (uint32_t)q * 32u + lane;
+            if (u < units) multimem_st16(dp + ((size_t)u << 4), v[q]);
+          }
         }
         __syncwarp();  // the stage may be refilled once every lane has read it
       } else if (lane == 0) {

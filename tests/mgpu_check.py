@@ -43,6 +43,11 @@ def expected_draws(rb, g, n, b_loc, n_draws, dev):
     return out
 
 
+def _mc_default():
+    """Exercise the multicast path wherever the fabric offers it (the product's "auto" starts at 4 ranks)."""
+    return {"0": False, "1": True}.get(os.environ.get("RLB_MGPU_MULTICAST", ""), "probe")
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -73,7 +78,7 @@ def main():
         g = torch.Generator(device=dev).manual_seed(7 + rank)
         rb = ShardedPrioritizedReplayBuffer(alpha=0.6, beta=0.4, capacity=cap, batch_size=B, device=dev, generator=g,
                                             transport=mode.split("-")[0], pipeline=mode.endswith("pipelined"),
-                                            multicast=False if mode.endswith("unicast") else "auto")
+                                            multicast=False if mode.endswith("unicast") else _mc_default())
         rb.extend(data.clone())
         outs, queue = [], deque()
         for it in range(6):  # every receive slot comes round at least once
