@@ -83,6 +83,21 @@ def _worker(rank: int, world: int, port: int, q):
         touched[(batch.get("index")[own] - rank * 500)] = True
         assert torch.equal(after[~touched], before[~touched])
         assert torch.allclose(after[touched], torch.tensor(5.0 + 1e-8) ** alpha)
+        # pipelined (sample() returns the previous draw) against plain, same seeds, no write-backs in between: the same
+        # sequence of global batches on both ranks; flush() hands out the draw still in flight
+        bufs = []
+        for pipe in (True, False):
+            gp = torch.Generator().manual_seed(200 + rank)
+            rbp = ShardedPrioritizedReplayBuffer(alpha=alpha, beta=beta, capacity=cap, batch_size=B, device="cpu",
+                                                 generator=gp, pipeline=pipe)
+            rbp.extend(data.clone())
+            bufs.append(rbp)
+        for it in range(4):
+            x = bufs[0].sample() if it < 3 else bufs[0].flush()
+            y = bufs[1].sample()
+            for key in ("index", "obs", "frame", "flag", "priority_weight"):
+                assert torch.equal(x.get(key), y.get(key)), ("pipelined", it, key)
+        assert bufs[0].flush() is None
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
