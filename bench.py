@@ -355,17 +355,33 @@ def steps_per_graph(k: int) -> int:
     """Consecutive steps captured into ONE graph.  A graph replay costs ~8 us on its own (torch refreshes the Philox
     seed / offset of the registered generator with two small fill kernels, then the launch itself), so a training loop
     that captures a few steps at a time pays it once per group; the timed region still runs EXACTLY `k` steps."""
-    for spg in (20, 12, 8, 4, 2):
-        if k % spg == 0:
-            return spg
-    return 1
+    return group_plan(k, 1)[0]
 
 
-def timed_groups(graphs, spg: int, steps: int, warmup: int, sync_all) -> float:
-    """ms per STEP over exactly `steps` steps, issued as steps / spg replays of graphs holding spg steps each."""
+def group_plan(k: int, quantum: int) -> tuple[int, int]:
+    """(steps per graph, remainder) for a timed region of EXACTLY k steps: the largest group size <= 20 that is a multiple
+    of `quantum` (the receive-slot count of the pipelined exchange; 1 on one GPU) and divides k; when only tiny groups
+    divide k (a prime step count), groups of up to 20 plus ONE shorter graph holding the k % spg left-over steps."""
+    top = max(quantum, min(20, k) // quantum * quantum)
+    for spg in range(top, 0, -quantum):
+        if k % spg == 0 and spg >= min(8, top):
+            return spg, 0
+    return top, k % top
+
+
+def timed_groups(graphs, spg: int, steps: int, warmup: int, sync_all, tail=None) -> float:
+    """ms per STEP over exactly `steps` steps, issued as steps // spg replays of graphs holding spg steps each plus, when
+    spg does not divide `steps`, one replay of `tail` (a graph of the steps % spg left-over steps)."""
     n_g = len(graphs)
     launches, warm = steps // spg, -(-warmup // spg)
-    return timed(lambda i: graphs[i % n_g](), launches, warm, sync_all) / spg
+    rem = steps % spg
+    if not rem:
+        return timed(lambda i: graphs[i % n_g](), launches, warm, sync_all) / spg
+    if tail is None:
+        raise RuntimeError(f"{steps} steps do not divide into groups of {spg} and no tail graph was given")
+    calls = launches + 1
+    # (timed() numbers its calls warm, warm + 1, ...: the last one of the timed region is the tail)
+    return timed(lambda i: (graphs[i % n_g]() if i - warm < launches else tail()), calls, warm, sync_all) * calls / steps
 
 
 def graph_us(fn_list, dev, reps: int = 5) -> float:
@@ -636,13 +652,14 @@ def run_single(args, dev) -> dict:
     # ---- (2) the same steps captured into CUDA graphs -- `spg` consecutive steps (each with its own GAE input set) per
     # graph -- and replayed
     graphs, graph_err, ms_graph = None, None, None
-    spg = steps_per_graph(args.steps)
+    spg, rem = group_plan(args.steps, 1)
     try:
         gen = rb.sampler._rng
         n_groups = max(1, min(3, R // spg))
         groups = [[steps[(gi * spg + k) % R] for k in range(spg)] for gi in range(n_groups)]
         graphs = [CudaGraphStep((lambda grp=grp: [st() for st in grp]), generators=[gen], warmup=1) for grp in groups]
-        ms_graph = timed_groups(graphs, spg, args.steps, args.warmup, sync_all)
+        tail = CudaGraphStep((lambda: [steps[k % R]() for k in range(rem)]), generators=[gen], warmup=1) if rem else None
+        ms_graph = timed_groups(graphs, spg, args.steps, args.warmup, sync_all, tail)
         # a longer replay run of the same graphs (the driver's --steps 20 makes the timed region < 1 ms)
         ms_graph_long = timed_groups(graphs, spg, max(args.steps, 400) // spg * spg, 8, sync_all)
         # and the one-step-per-graph figure, for comparison with round 1
@@ -1040,12 +1057,10 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
         gen = rb.sampler._rng
         # spg consecutive steps per graph (a multiple of the receive-slot count, so graphs chain slot-continuously); the
         # exchanges run on their own stream beside the compute chain and rejoin once per graph
-        spg = next((c for c in (20, 12, 8, 4) if args.steps % c == 0), None)
-        if spg is None:
-            raise RuntimeError(f"--steps must be a multiple of {N_BUFFERS} with the pipelined NVLink exchange")
+        spg, rem = group_plan(args.steps, N_BUFFERS)
 
-        def make_group(g0: int):
-            fns = [make_step((g0 + k) % R) for k in range(spg)]
+        def make_group(g0: int, n: int | None = None):
+            fns = [make_step((g0 + k) % R) for k in range(spg if n is None else n)]
 
             def group():
                 outs = [fn() for fn in fns]
@@ -1055,7 +1070,9 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
             return group
 
         graphs = [CudaGraphStep(make_group(g0), generators=[gen], warmup=1) for g0 in (0, spg)]
-        ms_graph = timed_groups(graphs, spg, args.steps, max(args.warmup, spg), sync_all)
+        # (left-over steps of a step count that is not a multiple of the slot count: one shorter graph, replayed last)
+        tail = CudaGraphStep(make_group((args.steps // spg) * spg, rem), generators=[gen], warmup=1) if rem else None
+        ms_graph = timed_groups(graphs, spg, args.steps, max(args.warmup, spg), sync_all, tail)
         ms_graph_long = timed_groups(graphs, spg, max(args.steps, 200) // spg * spg, spg, sync_all)
         torch.cuda.synchronize()
         rb.check_exchange()
