@@ -451,18 +451,19 @@ def gae_shape_sweep(dev, be, hbm_peak: float) -> dict:
     that rotate through more than L2."""
     g = torch.Generator(device=dev).manual_seed(77)
     out = {}
-    for rows, T in GAE_SHAPES:
-        per = rows * T * 14
+    for rows, T, *rest in GAE_SHAPES + ((1024, 128, 4),):
+        F = rest[0] if rest else 1
+        per = rows * T * F * 14
         n = int(min(64, max(4, (160 << 20) // per)))
         sets = []
         for _ in range(n):
-            v, nv, r = (torch.randn(rows, T, 1, device=dev, generator=g) for _ in range(3))
-            term = torch.rand(rows, T, 1, device=dev, generator=g) < 0.02
-            done = term | (torch.rand(rows, T, 1, device=dev, generator=g) < 0.02)
+            v, nv, r = (torch.randn(rows, T, F, device=dev, generator=g) for _ in range(3))
+            term = torch.rand(rows, T, F, device=dev, generator=g) < 0.02
+            done = term | (torch.rand(rows, T, F, device=dev, generator=g) < 0.02)
             sets.append((v, nv, r, done.view(torch.uint8), term.view(torch.uint8)))
-        us = graph_us([(lambda x=x: be.gae(x[0], x[1], x[2], x[3], x[4], GAMMA, GAMMA * LMBDA, rows, T, 1)) for x in sets], dev)
-        alg = rows * T * 22
-        out[f"{rows}x{T}"] = {"us_per_launch": round(us, 3), "achieved": round(alg / us / 1e3, 1),
+        us = graph_us([(lambda x=x: be.gae(x[0], x[1], x[2], x[3], x[4], GAMMA, GAMMA * LMBDA, rows, T, F)) for x in sets], dev)
+        alg = rows * T * F * 22
+        out[f"{rows}x{T}" + (f"x{F}" if F > 1 else "")] = {"us_per_launch": round(us, 3), "achieved": round(alg / us / 1e3, 1),
                               "frac": round(alg / us / 1e3 / hbm_peak, 4), "algorithmic_bytes": alg}
     return out
 
@@ -1119,7 +1120,7 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
     gc.collect()
     torch.cuda.empty_cache()
     extra = {}
-    for name in ("c4", "c4_framestack", "c5"):
+    for name in (() if os.environ.get("RLB_BENCH_SKIP_EXTRAS") == "1" else ("c4", "c4_framestack", "c5")):
         try:
             extra[name] = sharded_workload(name, dev, rank, world, max(args.steps, 50), be)
         except Exception as e:  # noqa: BLE001

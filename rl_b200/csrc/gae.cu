@@ -27,6 +27,8 @@
 // MODE 2 = the bare scan  A_t = d_t + c_t*A_{t+1}  over caller-supplied coefficient tensors: V-trace
 // (functional.py:1297-1382) and GAE with per-step gamma / lmbda tensors (functional.py:317-370) reduce to it after an
 // elementwise prologue, without the [B, T, T] gamma tensor of value/utils.py:130-181.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rlb {
@@ -87,7 +89,8 @@ struct GaeTile {
 
   __device__ __forceinline__ void load(const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r,
                                        const uint8_t *__restrict__ done, const uint8_t *__restrict__ term, int64_t base,
-                                       int64_t t0, int64_t Tlen, T gamma, T gl, T oml) {
+                                       int64_t t0, int64_t Tlen, T gamma, T gl, T oml, int64_t es = 1) {
+    // es: element stride between consecutive steps (F for one feature column of a [T, F] row; scalar path only)
     if (VEC && t0 + 4 <= Tlen) {
       Vec4<T> qv = {{(T)0, (T)0, (T)0, (T)0}};
       if constexpr (MODE == 0) qv = load4<T>(v + base + t0);
@@ -111,12 +114,12 @@ struct GaeTile {
       for (int j = 0; j < 4; ++j) {
         const int64_t t = t0 + j;
         if (t < Tlen) {
-          const T vv = (MODE == 0) ? __ldg(v + base + t) : (T)0;
+          const int64_t i = base + t * es;
+          const T vv = (MODE == 0) ? __ldg(v + i) : (T)0;
           sv[j] = vv;
-          const bool dn = (MODE != 2) ? (__ldg(done + base + t) != 0) : false;
-          const bool tm = (MODE != 2) ? (__ldg(term + base + t) != 0) : false;
-          scan_coeffs<T, MODE>(vv, __ldg(nv + base + t), __ldg(r + base + t), dn, tm, t == Tlen - 1, gamma, gl, oml,
-                               d[j], c[j]);
+          const bool dn = (MODE != 2) ? (__ldg(done + i) != 0) : false;
+          const bool tm = (MODE != 2) ? (__ldg(term + i) != 0) : false;
+          scan_coeffs<T, MODE>(vv, __ldg(nv + i), __ldg(r + i), dn, tm, t == Tlen - 1, gamma, gl, oml, d[j], c[j]);
         } else {  // beyond the row: A = 0 there, contributes nothing
           sv[j] = (T)0;
           d[j] = (T)0;
@@ -149,7 +152,7 @@ struct GaeTile {
 
   // the four local values re-derived serially from the value entering the lane; returns A at the tile's first step
   __device__ __forceinline__ T finish(int lane, T Bs, T Cs, T carry, int64_t base, int64_t t0, int64_t Tlen,
-                                      T *__restrict__ adv, T *__restrict__ tgt) const {
+                                      T *__restrict__ adv, T *__restrict__ tgt, int64_t es = 1) const {
     const T a_first = Bs + Cs * carry;
     // value entering this lane from the right = A at the first step of lane+1 (carry for lane 31)
     T a_next = __shfl_down_sync(0xffffffffu, a_first, 1);
@@ -168,8 +171,8 @@ struct GaeTile {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (t0 + j < Tlen) {
-          adv[base + t0 + j] = oa.v[j];
-          if constexpr (MODE == 0) tgt[base + t0 + j] = ot.v[j];
+          adv[base + (t0 + j) * es] = oa.v[j];
+          if constexpr (MODE == 0) tgt[base + (t0 + j) * es] = ot.v[j];
         }
       }
     }
@@ -178,26 +181,29 @@ struct GaeTile {
 };
 
 // Many rows: one WARP per row (blockDim.x / 32 rows per CTA); rows longer than a tile are walked from the end.
+// F > 1 (scalar path): `rows` counts (row, feature) COLUMNS of [rows / F, T, F] tensors; column q = row * F + f starts
+// at row * T * F + f and steps by F.  The F warps of a row sit next to each other in a CTA, so the row's cache lines are
+// fetched once and shared through L1 (a thread-per-column walk touches 4 bytes of every 32-byte sector per step).
 template <typename T, bool VEC, int MODE>
 __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
     const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r, const uint8_t *__restrict__ done,
     const uint8_t *__restrict__ term, T gamma, T gl, T oml, int64_t rows, int64_t Tlen, T *__restrict__ adv,
-    T *__restrict__ tgt) {
+    T *__restrict__ tgt, int64_t F) {
   pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;  // whole warps leave together
   pdl_wait();
-  const int64_t base = row * Tlen;
+  const int64_t base = VEC ? row * Tlen : (row / F) * Tlen * F + (row % F);
   const int64_t ntiles = (Tlen + kGaeTile - 1) / kGaeTile;
   T carry = (T)0;  // A at the first step of the tile processed before (later in time); prev_advantage = 0
   for (int64_t tile = ntiles - 1; tile >= 0; --tile) {
     const int64_t t0 = tile * kGaeTile + 4 * lane;  // first of this lane's four steps
     GaeTile<T, VEC, MODE> g;
-    g.load(v, nv, r, done, term, base, t0, Tlen, gamma, gl, oml);
+    g.load(v, nv, r, done, term, base, t0, Tlen, gamma, gl, oml, F);
     T Bs, Cs;
     g.scan(lane, Bs, Cs);
-    carry = g.finish(lane, Bs, Cs, carry, base, t0, Tlen, adv, tgt);
+    carry = g.finish(lane, Bs, Cs, carry, base, t0, Tlen, adv, tgt, F);
   }
 }
 
@@ -298,10 +304,23 @@ static int gae_impl(const void *v, const void *nv, const void *r, const uint8_t 
     RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many rows for one launch");
     if (vec)
       return check_cuda(launch_pdl(gae_rows_kernel<T, true, MODE>, dim3((unsigned)blocks), dim3(wpc * 32), 0, st, pv,
-                                   pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt),
+                                   pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt, (int64_t)1),
                         "gae_rows_kernel");
     return check_cuda(launch_pdl(gae_rows_kernel<T, false, MODE>, dim3((unsigned)blocks), dim3(wpc * 32), 0, st, pv,
-                                 pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt),
+                                 pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt, (int64_t)1),
+                      "gae_rows_kernel");
+  }
+  static const bool force_cols = [] {  // (A/B measurements: RLB_GAE_COLUMN_KERNEL=1 keeps the thread-per-column walk)
+    const char *e = getenv("RLB_GAE_COLUMN_KERNEL");
+    return e && e[0] == '1';
+  }();
+  if (F <= 16 && Tlen >= 16 && !force_cols) {
+    // narrow feature dim: a warp per (row, feature) column, time-parallel like F == 1 (see gae_rows_kernel)
+    const int64_t cols = rows * F;
+    const int64_t blocks = (cols + kGaeWarpsPerCta - 1) / kGaeWarpsPerCta;
+    RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many columns for one launch");
+    return check_cuda(launch_pdl(gae_rows_kernel<T, false, MODE>, dim3((unsigned)blocks), dim3(kGaeWarpsPerCta * 32), 0,
+                                 st, pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml, cols, Tlen, pa, pt, F),
                       "gae_rows_kernel");
   }
   const int64_t cols = rows * F;

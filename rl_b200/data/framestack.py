@@ -271,6 +271,14 @@ class FrameStackStorage(Storage):
         st.arm()
         return TensorDict._from_leaves(keys + [self.obs_key, self.next_key], out[:len(keep)] + [obs, nxt], (B,))
 
+    def _signal_view(self):
+        """Views of every stored leaf except the two stacks (what the slice samplers look their episode signals up in)."""
+        return self._inner.get(slice(None))
+
+    @property
+    def _last_cursor(self):
+        return self._inner._last_cursor
+
     def _get_trusted(self, index: torch.Tensor):
         return self.get(index)
 
@@ -279,6 +287,10 @@ class FrameStackStorage(Storage):
             raise RuntimeError("Cannot get elements out of a non-initialized storage.")
         n = len(self)
         squeeze = False
+        if isinstance(index, tuple):
+            if len(index) != 1:
+                raise RuntimeError("FrameStackStorage is one-dimensional: expected a single index")
+            index = index[0]
         if _is_int(index):
             index, squeeze = torch.tensor([index + n if index < 0 else index], device=self.device), True
         elif isinstance(index, slice) or index is None or index is Ellipsis:

@@ -36,6 +36,14 @@ from .utils import unravel_index
 _EMPTY_STORAGE_ERROR = "Cannot sample from an empty storage."
 
 
+
+def _contents(storage):
+    """The stored leaves the slice samplers read their signals from (``storage[:]`` in the reference).  Storages whose
+    full read would have to rebuild something (``FrameStackStorage``: every frame stack) expose the cheap part as
+    ``_signal_view()``."""
+    view = getattr(storage, "_signal_view", None)
+    return view() if view is not None else storage[:]
+
 class Sampler(abc.ABC):
     """A generic sampler base class for composable replay buffers (samplers.py:99-171)."""
 
@@ -360,7 +368,7 @@ class SliceSampler(Sampler):
             sig, by_id = self._given
             return sig.to(storage.device) if hasattr(storage, "device") else sig, by_id, True, -1
         try:
-            contents = storage[:]
+            contents = _contents(storage)
         except Exception:
             raise RuntimeError("Could not get a tensordict out of the storage, which is required for SliceSampler to "
                                "compute the trajectories.")
@@ -492,7 +500,7 @@ class SliceSampler(Sampler):
         storage_length = storage.shape[0]
         args = (table[0], table[2], n_traj, traj, u, seq_length, storage_length)
         # the stored done / terminated flags of the sampled steps ride in the same launch when they are one byte per slot
-        contents = storage[:] if hasattr(storage, "get") else None
+        contents = _contents(storage) if hasattr(storage, "get") else None
         get = (lambda k: contents.get(k, None)) if contents is not None and hasattr(contents, "get") else (lambda k: None)
         done_all = term_all = None
         if self.truncated_key is not None:
@@ -1203,7 +1211,7 @@ class PrioritizedSliceSampler(SliceSampler, PrioritizedSampler):
         info: dict = {"priority_weight": weight.repeat_interleave(seq_length if seq is None else seq)}   # :2969-2971
         # expansion of the starts (:2963-2966), truncated markers and the stored flags of the sampled steps in one
         # rlb_slice_index launch: every start is a one-entry "trajectory" of exactly its slice's steps, offset 0
-        contents = storage[:]
+        contents = _contents(storage)
         done_all = term_all = None
         if self.truncated_key is not None:
             done_key = _replace_last(self.truncated_key, "done")

@@ -234,3 +234,36 @@ def test_sharded_buffer_over_framestack_storage_host_logic(emul):
     assert b._layout.row - a._layout.row >= 3 * frame - 16      # 5 frames instead of 8 on the wire
     win = x.get("pixels")
     assert win.stride(0) >= 5 * frame                            # obs / next are views of one [B, k + 1, ...] window
+
+
+def _slice_buffers(dev):
+    from rl_b200.data import SliceSampler
+
+    def make(storage):
+        g = torch.Generator(device=dev).manual_seed(31)
+        return TensorDictReplayBuffer(storage=storage, batch_size=64, generator=g,
+                                      sampler=SliceSampler(num_slices=8, end_key=("next", "done"), strict_length=True))
+
+    return make(FrameStackStorage(512, device=dev, min_episode_length=1)), make(LazyTensorStorage(512, device=dev))
+
+
+def _check_slices(dev):
+    """Trajectory slices (SliceSampler reads its episode signal through the storage's cheap view, the frames through the
+    rebuilding gather): identical batches from the de-duplicated and the materialised storage."""
+    a, b = _slice_buffers(dev)
+    for td in _batches(1, 600, 60, "env_major", seed=17, pad="constant", dev=dev, min_len=9, max_len=40):
+        a.extend(td.clone())
+        b.extend(td.clone())
+        x, y = a.sample(), b.sample()
+        for key in ("index", "pixels", ("next", "pixels"), "action", ("next", "done"), ("next", "truncated")):
+            assert torch.equal(x.get(key), y.get(key)), key
+    a._storage.check_index_status()
+
+
+def test_slice_sampler_over_framestack_storage_host_logic(emul):
+    _check_slices("cpu")
+
+
+@pytest.mark.gpu
+def test_slice_sampler_over_framestack_storage():
+    _check_slices("cuda")
