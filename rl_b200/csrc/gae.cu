@@ -207,6 +207,105 @@ __global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_kernel(
   }
 }
 
+// [rows, T, F] with F in {2, 3, 4} and T % 4 == 0 (16-byte aligned arrays): a lane's 4 steps x F features are 4F CONTIGUOUS
+// values of the row, so every array moves with the same coalesced 128-bit accesses as the F == 1 tile; the F scans of a lane
+// run side by side in registers.
+template <typename T, int F, int MODE>
+__global__ void __launch_bounds__(kGaeWarpsPerCta * 32) gae_rows_f_kernel(
+    const T *__restrict__ v, const T *__restrict__ nv, const T *__restrict__ r, const uint8_t *__restrict__ done,
+    const uint8_t *__restrict__ term, T gamma, T gl, T oml, int64_t rows, int64_t Tlen, T *__restrict__ adv,
+    T *__restrict__ tgt) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  pdl_wait();
+  const int64_t base = row * Tlen * F;
+  const int64_t ntiles = (Tlen + kGaeTile - 1) / kGaeTile;
+  T carry[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) carry[f] = (T)0;
+  for (int64_t tile = ntiles - 1; tile >= 0; --tile) {
+    const int64_t t0 = tile * kGaeTile + 4 * lane;
+    T d[4 * F], c[4 * F], sv[4 * F];  // element (step j, feature f) at [j * F + f]
+    const bool in = t0 < Tlen;        // (T % 4 == 0: a lane's four steps are inside the row together)
+    if (in) {
+      const int64_t e0 = base + t0 * F;
+#pragma unroll
+      for (int q = 0; q < F; ++q) {
+        Vec4<T> qv = {{(T)0, (T)0, (T)0, (T)0}};
+        if constexpr (MODE == 0) qv = load4<T>(v + e0 + 4 * q);
+        const Vec4<T> qn = load4<T>(nv + e0 + 4 * q);
+        const Vec4<T> qr = load4<T>(r + e0 + 4 * q);
+        uchar4 qd = make_uchar4(0, 0, 0, 0), qt = make_uchar4(0, 0, 0, 0);
+        if constexpr (MODE != 2) {
+          qd = __ldg(reinterpret_cast<const uchar4 *>(done + e0 + 4 * q));
+          qt = __ldg(reinterpret_cast<const uchar4 *>(term + e0 + 4 * q));
+        }
+        const uint8_t dd[4] = {qd.x, qd.y, qd.z, qd.w};
+        const uint8_t tt[4] = {qt.x, qt.y, qt.z, qt.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int e = 4 * q + k;  // flat position among the lane's 4F values: step e / F
+          sv[e] = qv.v[k];
+          scan_coeffs<T, MODE>(qv.v[k], qn.v[k], qr.v[k], dd[k] != 0, tt[k] != 0, t0 + e / F == Tlen - 1, gamma, gl, oml,
+                               d[e], c[e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4 * F; ++e) {
+        d[e] = (T)0;
+        c[e] = (T)0;
+        sv[e] = (T)0;
+      }
+    }
+    T oa[4 * F], ot[4 * F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      T Bs = d[3 * F + f], Cs = c[3 * F + f];  // lane-local composition, then the warp scan (as GaeTile::scan)
+#pragma unroll
+      for (int j = 2; j >= 0; --j) {
+        Bs = d[j * F + f] + c[j * F + f] * Bs;
+        Cs = c[j * F + f] * Cs;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const T Bo = __shfl_down_sync(0xffffffffu, Bs, o);
+        const T Co = __shfl_down_sync(0xffffffffu, Cs, o);
+        if (lane + o < 32) {
+          Bs = Bs + Cs * Bo;
+          Cs = Cs * Co;
+        }
+      }
+      const T a_first = Bs + Cs * carry[f];
+      T a_next = __shfl_down_sync(0xffffffffu, a_first, 1);
+      if (lane == 31) a_next = carry[f];
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {  // the four local values re-derived serially (accuracy of the serial recurrence)
+        a_next = d[j * F + f] + c[j * F + f] * a_next;
+        oa[j * F + f] = a_next;
+        ot[j * F + f] = a_next + sv[j * F + f];
+      }
+      carry[f] = __shfl_sync(0xffffffffu, oa[f], 0);
+    }
+    if (in) {
+      const int64_t e0 = base + t0 * F;
+#pragma unroll
+      for (int q = 0; q < F; ++q) {
+        Vec4<T> xa, xt;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          xa.v[k] = oa[4 * q + k];
+          xt.v[k] = ot[4 * q + k];
+        }
+        store4(adv + e0 + 4 * q, xa);
+        if constexpr (MODE == 0) store4(tgt + e0 + 4 * q, xt);
+      }
+    }
+  }
+}
+
 // Few rows (the reference benchmark's [300,500], [32,512], [1,512]): one CTA per row, one WARP per TILE.  All tiles of a
 // chunk are loaded at once (the serial walk above pays one DRAM round trip per tile); lane 0 of each warp publishes
 // its tile's composite map, and every warp folds the maps of the tiles to its right -- the serial recurrence at tile
@@ -309,6 +408,34 @@ static int gae_impl(const void *v, const void *nv, const void *r, const uint8_t 
     return check_cuda(launch_pdl(gae_rows_kernel<T, false, MODE>, dim3((unsigned)blocks), dim3(wpc * 32), 0, st, pv,
                                  pn, pr, done, term, (T)gamma, (T)gl, (T)oml, rows, Tlen, pa, pt, (int64_t)1),
                       "gae_rows_kernel");
+  }
+  {
+    // F in {2, 3, 4}: contiguous 4F-value lanes (gae_rows_f_kernel) when the vector accesses are aligned
+    auto al = [](const void *p, uintptr_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+    const bool vecf = F >= 2 && F <= 4 && (Tlen % 4 == 0) && al(v, 16) && al(nv, 16) && al(r, 16) && al(adv, 16) &&
+                      al(tgt, 16) && al(done, 4) && al(term, 4);
+    static const bool no_f = [] {
+      const char *e = getenv("RLB_GAE_NO_F_KERNEL");
+      return e && e[0] == '1';
+    }();
+    if (vecf && !no_f) {
+      const int sms = sm_count();
+      const int wpc = rows >= 8 * (int64_t)sms ? kGaeWarpsPerCta : (rows >= 2 * (int64_t)sms ? 2 : 1);
+      const int64_t blocks = (rows + wpc - 1) / wpc;
+      RLB_REQUIRE(blocks < (int64_t(1) << 31), RLB_ELIMIT, "rlb_gae: too many rows for one launch");
+      const dim3 grid((unsigned)blocks), block(wpc * 32);
+      cudaError_t e;
+      if (F == 2)
+        e = launch_pdl(gae_rows_f_kernel<T, 2, MODE>, grid, block, 0, st, pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml,
+                       rows, Tlen, pa, pt);
+      else if (F == 3)
+        e = launch_pdl(gae_rows_f_kernel<T, 3, MODE>, grid, block, 0, st, pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml,
+                       rows, Tlen, pa, pt);
+      else
+        e = launch_pdl(gae_rows_f_kernel<T, 4, MODE>, grid, block, 0, st, pv, pn, pr, done, term, (T)gamma, (T)gl, (T)oml,
+                       rows, Tlen, pa, pt);
+      return check_cuda(e, "gae_rows_f_kernel");
+    }
   }
   static const bool force_cols = [] {  // (A/B measurements: RLB_GAE_COLUMN_KERNEL=1 keeps the thread-per-column walk)
     const char *e = getenv("RLB_GAE_COLUMN_KERNEL");

@@ -760,15 +760,16 @@ class PrioritizedSampler(Sampler):
         index, weight = ops.backend().per_sample(
             self._sum_tree.values, self._min_tree.values, self._max_capacity, self._sum_tree.capacity, length, u,
             self._beta, self._semantics == "cpu", status=self._status)
-        if self.predraw:
-            # the NEXT call's uniforms, drawn now: the same torch.rand calls in the same order, but off the critical
-            # path of the next sample (it only has to wait for the priority write-back, not for an RNG kernel first)
-            torch.rand(batch_size, device=dev, generator=self._rng, dtype=u.dtype, out=self._u_next)
-            self._u_ready = batch_size
         if self.record_index_event and dev.type == "cuda":
             if self.index_ready is None:
                 self.index_ready = torch.cuda.Event()
             self.index_ready.record(torch.cuda.current_stream(dev))
+        if self.predraw:
+            # the NEXT call's uniforms, drawn now: the same torch.rand calls in the same order, but off the critical
+            # path of the next sample (it only has to wait for the priority write-back, not for an RNG kernel first).
+            # Issued AFTER the index event: a write-back waiting for the indices must not wait for this kernel too.
+            torch.rand(batch_size, device=dev, generator=self._rng, dtype=u.dtype, out=self._u_next)
+            self._u_ready = batch_size
         if storage.ndim > 1:
             index = unravel_index(index, storage.shape)
         return index, {"priority_weight": weight}

@@ -139,7 +139,12 @@ class CudaBackend:
 
     @staticmethod
     def _stream(dev: torch.device) -> int:
-        return torch.cuda.current_stream(dev).cuda_stream
+        """Raw handle of torch's current stream on `dev` (the binding Triton and the inductor runtime use: ~0.3 us, where
+        ``torch.cuda.current_stream(dev).cuda_stream`` builds a Stream object first: ~7 us of every eager call)."""
+        raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        if raw is None:
+            return torch.cuda.current_stream(dev).cuda_stream
+        return raw(dev.index if dev.index is not None else torch.cuda.current_device())
 
     @staticmethod
     def _p(t: torch.Tensor | None) -> int | None:

@@ -476,7 +476,8 @@ def _gae_inputs(shape, seed, p=0.05, dtype=torch.float32):
                                    (32, 512, 1), (1, 512, 1), (3, 4100, 1), (2, 2049, 1), (5, 257, 1), (700, 129, 1),
                                    (400, 64, 1),
                                    # narrow feature dims: a warp per (row, feature) column; short T and wide F: the column kernel
-                                   (37, 300, 2), (256, 128, 4), (3, 1000, 16), (11, 15, 4), (6, 40, 17)])
+                                   (37, 300, 2), (256, 128, 4), (3, 1000, 16), (11, 15, 4), (6, 40, 17), (5, 64, 3), (9, 516, 3), (2, 132, 4),
+                                   (7, 130, 2)])
 @pytest.mark.parametrize("gamma,lmbda", [(0.99, 0.95), (0.5, 0.1)])
 def test_gae_matches_f64_oracle(cuda_backend, shape, gamma, lmbda):
     from rl_b200.objectives.value import generalized_advantage_estimate, vec_generalized_advantage_estimate
