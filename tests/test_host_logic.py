@@ -1074,3 +1074,19 @@ def test_gae_module_rereads_annealed_discount(emul):
                                                   td.get(("next", "reward")), td.get(("next", "done")),
                                                   td.get(("next", "terminated")), time_dim=-2)
     torch.testing.assert_close(mod(td.clone()).get("advantage"), want3, rtol=1e-6, atol=1e-6)
+
+
+def test_bench_group_plan_covers_every_step_count():
+    """bench.py times EXACTLY K steps whatever K is: full groups of the planned size plus one shorter tail graph."""
+    import bench
+
+    for quantum in (1, 4):
+        for k in range(1, 260):
+            spg, rem = bench.group_plan(k, quantum)
+            assert spg % quantum == 0 and 1 <= spg <= max(20, quantum)
+            assert (k // spg) * spg + rem == k and 0 <= rem < spg
+            if rem == 0:
+                assert k % spg == 0
+    assert bench.group_plan(200, 1) == (20, 0) and bench.group_plan(20, 4) == (20, 0) and bench.group_plan(50, 1) == (10, 0)
+    cfg = bench.make_config(1)
+    assert cfg["workload"] == bench.make_config(8)["workload"]
