@@ -220,6 +220,80 @@ __device__ __forceinline__ int64_t descend4_f32(const float *__restrict__ tree, 
   return (node << 4) | c;
 }
 
+// fp32, a GROUP of G lanes per sample (small batches leave most lanes of the single-warp CTAs idle): up to
+// log2(G) + 2 levels per round trip.  The left children the next K comparisons can possibly need are, level by level,
+// the contiguous runs tree[(n << k) + 0 .. 2^k) -- 2^k / 4 aligned 16-byte units at level k >= 2, one 8-byte unit at
+// level 1.  The deepest level's units go to lanes [0, 2^(K-2)) (register A), the levels above it are packed behind one
+// another over the same lanes (register B: level k starts at lane 2^(K-2) - 2^(k-1)), so every lane issues at most two
+// independent loads.  Then EVERY lane of the group walks the K comparisons -- the reference's, in the reference's order --
+// fetching each candidate from its owner with a shuffle: `cur` and the path stay uniform across the group.
+__device__ __forceinline__ int64_t descend_group_f32(const float *__restrict__ tree, int64_t node, int K, int G,
+                                                  float &cur, float &landed) {
+  // (deliberately compact: rolled loops, one copy -- a single-warp CTA runs this once, instruction fetch is part of its
+  // latency)
+  const int gl = threadIdx.x & (G - 1);
+  const int nA = 1 << (K - 2);
+  float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+  if (gl < nA) qa = __ldg(reinterpret_cast<const float4 *>(tree + (node << K)) + gl);
+  {
+    // my unit of the packed upper levels: lane gl holds level k with  nA - 2^(k-1) <= gl < nA - 2^(k-2)  (k >= 2),
+    // lane nA - 1 holds level 1
+    const int d = nA - gl;  // in [1, nA] for the lanes that hold something
+    if (d >= 1 && K >= 2 && gl < nA) {
+      if (d == 1) {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(tree + (node << 1)));
+        qb.x = t.x;
+        qb.y = t.y;
+      } else {
+        const int k = 32 - __clz(d - 1) + 1;  // 2^(k-2) < d <= 2^(k-1)
+        if (k < K) qb = __ldg(reinterpret_cast<const float4 *>(tree + (node << k)) + (gl - (nA - (1 << (k - 1)))));
+      }
+    }
+  }
+  int c = 0;
+#pragma unroll 1
+  for (int k = 1; k <= K; ++k) {
+    const int e = c << 1;  // the left child of the node reached so far, as an element of level k's run
+    const float4 q = (k == K) ? qa : qb;
+    const int comp = e & 3;
+    const float sel = comp == 0 ? q.x : (comp == 1 ? q.y : (comp == 2 ? q.z : q.w));
+    const int src = (k == K ? 0 : nA - (1 << (k - 1))) + (e >> 2);
+    const float l = __shfl_sync(0xffffffffu, sel, src, G);
+    c = e;
+    if (cur > l) {
+      cur = sub_rn(cur, l);
+      c |= 1;
+    }
+  }
+  {  // value of the node we end on: element c of the deepest level's run
+    const int comp = c & 3;
+    const float sel = comp == 0 ? qa.x : (comp == 1 ? qa.y : (comp == 2 ? qa.z : qa.w));
+    landed = __shfl_sync(0xffffffffu, sel, c >> 2, G);
+  }
+  return (node << K) | c;
+}
+
+// the remaining `rem` levels below `node`, cooperatively: rounds of at most log2(G) + 2 levels, evenly sized
+__device__ __forceinline__ int64_t descend_group_all(const float *__restrict__ tree, int64_t node, int rem, int G,
+                                                     float &cur, float &landed, bool &have_landed) {
+  const int kMax = (G == 32 ? 5 : G == 16 ? 4 : 3) + 2;
+  have_landed = false;
+#pragma unroll 1
+  while (rem >= 2) {
+    const int rounds = (rem + kMax - 1) / kMax;
+    const int K = (rem + rounds - 1) / rounds;
+    if (K < 2) break;
+    node = descend_group_f32(tree, node, K, G, cur, landed);
+    rem -= K;
+    have_landed = rem == 0;
+  }
+  if (rem > 0) {  // (a single left-over level)
+    node = descend_plain<float>(tree, node, rem, cur);
+    have_landed = false;
+  }
+  return node;
+}
+
 template <typename T>
 __device__ __forceinline__ int64_t scan_lower_bound_one(const T *__restrict__ tree, int64_t size, int64_t capacity,
                                                         int depth, T value, T root, bool speculative = true) {
@@ -297,8 +371,13 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   if (dbg) dbg[8] = (long long)clock64();
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  const bool lane_on = (int)threadIdx.x < spc;  // spc == blockDim.x for full CTAs
-  const int64_t i = lane_on ? blockIdx.x * (int64_t)spc + threadIdx.x : B;
+  // Single-warp CTAs with at most 4 samples: the warp splits into groups of G = 32 / 16 / 8 lanes, one per sample, that
+  // descend cooperatively (descend_group_f32); only the first lane of a group writes results.
+  const bool coop = speculative && sizeof(T) == 4 && blockDim.x == 32 && spc <= 4 && depth >= 9;
+  const int G = !coop ? 1 : (spc == 1 ? 32 : (spc == 2 ? 16 : 8));
+  const int grp = coop ? (int)threadIdx.x / G : (int)threadIdx.x;
+  const bool lane_on = grp < spc;  // spc == blockDim.x for full CTAs
+  const int64_t i = lane_on ? blockIdx.x * (int64_t)spc + grp : B;
   // ---- round 0: every load below is independent -- the draw, both roots (or the prefix walks) and the top of the tree
   const T ui = (i < B) ? __ldg(u + i) : (T)0;
   const bool use_top = speculative && depth >= kTopLevels && sizeof(T) == 4;
@@ -335,7 +414,7 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
       if (st) atomicOr(status, st);
     }
   }
-  if (i >= B) return;
+  if (i >= B && !coop) return;  // (cooperating lanes stay for the shuffles; a group without a sample walks a dummy path)
   if (dbg) dbg[9] = (long long)clock64();
   const T mass = mul_rn(ui, p_sum);  // samplers.py:919 / :923 -- one rounding, never fused downstream
   int64_t idx;
@@ -343,32 +422,37 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   bool have_leaf = false;
   if constexpr (sizeof(T) == 4) {
     if (use_top) {
-      // ScanLowerBound (csrc/segment_tree.h:249-264): 8 steps from shared memory, then 4 levels per round trip
+      // ScanLowerBound (csrc/segment_tree.h:249-264): 8 steps from shared memory, then 4 levels per round trip by one
+      // lane, or up to 7 by a cooperating group of lanes
       const T rootv = s_top[1];
-      if (mass > rootv) {
-        idx = size;
-      } else {
-        int64_t node = 1;
-        T cur = mass;
+      const bool over = mass > rootv;  // -> size, no descent (segment_tree.h:250-252)
+      int64_t node = 1;
+      T cur = over ? (T)0 : mass;      // (cooperating lanes walk a harmless all-left path for such a sample)
 #pragma unroll
-        for (int k = 0; k < kTopLevels - 1; ++k) {
-          node <<= 1;
-          descend_step(cur, node, s_top[node]);
-        }
-        int lev = kTopLevels - 1;
-        float landed = 0.f;
+      for (int k = 0; k < kTopLevels - 1; ++k) {
+        node <<= 1;
+        descend_step(cur, node, s_top[node]);
+      }
+      int lev = kTopLevels - 1;
+      float landed = 0.f;
+      if (coop) {
+        bool hl = false;
+        node = descend_group_all(sum, node, depth - lev, G, cur, landed, hl);
+        have_leaf = hl && !over;
+      } else if (!over) {
         for (; lev + 4 <= depth; lev += 4) node = descend4_f32(sum, node, cur, landed);
         have_leaf = (lev == depth) && (depth > kTopLevels - 1);
         node = descend_plain<T>(sum, node, depth - lev, cur);
-        idx = node ^ capacity;
-        leaf = landed;
       }
+      idx = over ? size : (node ^ capacity);
+      leaf = landed;
     } else {
       idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1), speculative != 0);
     }
   } else {
     idx = scan_lower_bound_one<T>(sum, size, capacity, depth, mass, __ldg(sum + 1), speculative != 0);
   }
+  if (coop && (i >= B || (threadIdx.x & (G - 1)) != 0)) return;  // one lane per sample goes on
   if (idx > len - 1) {  // samplers.py:933
     idx = len - 1;
     have_leaf = false;

@@ -332,7 +332,12 @@ def test_per_sample_golden(cuda_backend):
 
 
 @pytest.mark.parametrize("size,filled,B", [(16, 16, 64), (1000, 313, 256), (1_000_000, 1_000_000, 256),
-                                           (1_000_000, 400_000, 4096), (3_000_000, 3_000_000, 65536)])
+                                           (1_000_000, 400_000, 4096), (3_000_000, 3_000_000, 65536),
+                                           # group-cooperative descent: 1 / 2 / 3 / 4 samples per single-warp CTA (groups
+                                           # of 32 / 16 / 8 lanes), tree depths that leave 1 .. 15 levels below the staged top
+                                           (6_250_000, 6_250_000, 256), (6_250_000, 5_000_000, 512), (600, 600, 300),
+                                           (1100, 1100, 37), (3000, 2999, 800), (300_000, 300_000, 1100),
+                                           (70_000, 70_000, 128), (2_100_000, 2_100_000, 600)])
 @pytest.mark.parametrize("cpu_sem", [True, False])
 def test_per_sample_matches_oracle(cuda_backend, size, filled, B, cpu_sem):
     from rl_b200.data.segment_tree import MinSegmentTreeFp32, SumSegmentTreeFp32
