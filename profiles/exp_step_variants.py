@@ -61,5 +61,7 @@ for so in [str(ops._SO)] + sorted(glob.glob(str(Path(ops._PKG) / "variant_*.so")
     us_gather = bench.graph_us([(lambda ix=ix: be.gather(st._leaves, ix, len(st))) for ix in idxs], dev)
     big = [torch.randint(0, len(st), (4096,), device=dev, generator=g) for _ in range(4)]
     us_big = bench.graph_us([(lambda ix=ix: be.gather(st._leaves, ix, len(st))) for ix in big], dev)
-    print(f"{Path(so).name:36s} step {us_step:6.2f} us   gather B=256 alone {us_gather:6.2f} us   B=4096 {us_big:6.1f} us", flush=True)
+    us_upd = bench.graph_us([(lambda ix=ix: rb.update_priority(ix, td_err)) for ix in idxs], dev)
+    print(f"{Path(so).name:36s} step {us_step:6.2f} us   gather B=256 alone {us_gather:6.2f} us   B=4096 {us_big:6.1f} us   "
+          f"update B=256 alone {us_upd:6.2f} us", flush=True)
     del gs

@@ -543,7 +543,10 @@ constexpr size_t kUpdWorkspaceHead = size_t(1) << 20;  // (reserved head of the 
 __host__ __device__ inline int upd_bot_levels(int depth) { return depth > kDenseLevels ? depth - kDenseLevels : 0; }
 
 constexpr int kUpdCluster = 8;  // CTAs per update launch: the leader + seven helpers (portable cluster size)
-constexpr int kUpdHoist = 16;   // sibling values of this many levels are held in registers during the climb
+#ifndef RLB_UPDATE_HOIST
+#define RLB_UPDATE_HOIST 16
+#endif
+constexpr int kUpdHoist = RLB_UPDATE_HOIST;   // sibling values of this many levels are held in registers during the climb
 constexpr int kUpdMaxItemsPerRound = 1024;  // one item per thread
 constexpr int kUpdMaxRounds = 8;            // batches up to 8192 items in one launch
 constexpr int kUpdMaxItems = kUpdMaxItemsPerRound * kUpdMaxRounds;
