@@ -1004,10 +1004,15 @@ def run_distributed(args, dev, rank: int, world: int) -> dict:
     td_loc = td_err[rank * BATCH:(rank + 1) * BATCH].contiguous()
     gs = (float(torch.tensor(GAMMA)), float(torch.tensor(GAMMA) * torch.tensor(LMBDA)))
 
+    tick = torch.zeros(1, device=dev)
+
     def sync_all():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+        # ... and a device-side barrier on the stream: the host barrier releases the ranks tens of microseconds apart,
+        # which a timed region of one graph replay would count as step time of whoever waits for the late rank's rows
+        dist.all_reduce(tick)
 
     parity = dist_parity_check(rb, dev, rank, world)
     nvlink = rb._symm not in (None, False)
@@ -1191,10 +1196,15 @@ def sharded_workload(name: str, dev, rank: int, world: int, steps: int, be) -> d
     rb.record_index_event = True
     side = torch.cuda.Stream(dev)
 
+    tick = torch.zeros(1, device=dev)
+
     def sync_all():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+        # ... and a device-side barrier on the stream: the host barrier releases the ranks tens of microseconds apart,
+        # which a timed region of one graph replay would count as step time of whoever waits for the late rank's rows
+        dist.all_reduce(tick)
 
     parity = dist_parity_check(rb, dev, rank, world)
     nvlink = rb._symm not in (None, False)

@@ -21,6 +21,8 @@
 //
 // Index semantics follow torch indexing: negative indices wrap by `len`; out-of-range indices are reported through
 // the status word (torch would raise IndexError) -- a gather reads the clamped row, a scatter drops the write.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tree_range.cuh"
 
@@ -83,7 +85,7 @@ struct GatherParams {
   // once with multimem.st (replicated by the NVSwitch into every member, this GPU included) instead of n_peers copies
   int64_t mc_delta;
   int n_peers;
-  int pad0_;
+  int rotate;  // rotate the peer order per piece (see bulk_role)
   const int64_t *index;  // null: the implicit modular range  (ibase + b) % len  (the writer's cursor; B <= len)
   int64_t ibase;
   int64_t B;
@@ -361,8 +363,15 @@ __device__ __forceinline__ void bulk_role(const GatherParams &P, uint8_t *ring, 
       } else if (lane == 0) {
         mbar_wait_parity(&my->full[stage], (uint32_t)((n_stored / kStages) & 1));
         fence_proxy_async_smem();
-        for (int p = 0; p < P.n_peers; ++p)  // local buffer and, when sharded, every peer's receive buffer
+        // local buffer and, when sharded, every peer's receive buffer.  The destinations are visited in an order that
+        // ROTATES from piece to piece and from pipeline to pipeline: every rank runs this same loop, and a fixed order
+        // would aim all of them at the same receiver at the same time
+        const int np = P.n_peers;
+        int p = P.rotate ? (int)((n_stored + (int64_t)blockIdx.x * kPipes + (threadIdx.x >> 5)) % np) : 0;
+        for (int q = 0; q < np; ++q) {
           bulk_s2g(my->dst[stage] + P.peer_delta[p], my_ring + (size_t)stage * kChunk, my->bytes[stage]);
+          p = p + 1 == np ? 0 : p + 1;
+        }
         bulk_commit();
       }
       ++n_stored;
@@ -445,6 +454,11 @@ static int plan_rows(GatherParams &P, int &vec_ctas_out, const void *const *src,
   memset(&P, 0, sizeof(P));
   RLB_REQUIRE(mc_delta % 16 == 0 && (mc_delta == 0 || !SCATTER), RLB_EINVAL, "%s: bad multicast_delta", who);
   P.mc_delta = mc_delta;
+  static const bool no_rotate = [] {  // (A/B measurements: RLB_GATHER_PEER_ROTATE=0 keeps the fixed peer order)
+    const char *e = getenv("RLB_GATHER_PEER_ROTATE");
+    return e && e[0] == '0';
+  }();
+  P.rotate = (n_peers > 1 && !no_rotate) ? 1 : 0;
   P.n_peers = n_peers > 0 ? n_peers : 1;  // no peer list = the local buffer only
   for (int p = 0; p < n_peers; ++p) {
     RLB_REQUIRE(peer_delta[p] % 16 == 0, RLB_EINVAL, "%s: peer_delta[%d] is not 16-byte aligned", who, p);
