@@ -409,3 +409,41 @@ def test_slice_oracle_randomized_against_live_reference(ref_samplers):
             np.testing.assert_array_equal(info[("collector", "mask")].numpy(), omask)
         done_cases += 1
     assert done_cases >= 40
+
+
+def test_framestack_oracle_rebuilds_what_was_written():
+    """oracle/framestack_oracle.py: the plain-loop frame log, read back, equals the materialised stacks for every padding
+    mode / layout / episode-start signal, and reports evictions when a ring is lapped."""
+    from oracle import framestack_oracle as fo
+
+    for n_envs, layout, pad, use_init in ((1, 0, "same", True), (3, 0, "constant", False), (4, 1, "same", False)):
+        k, steps, per = 4, 96, 12
+        obs, nxt, done, init = fo.make_stream(n_envs, steps, k, (3, 2), seed=5 + n_envs, pad=pad, min_len=1, max_len=15)
+        ring = steps * (k + 1)
+        pool = np.zeros((n_envs * ring, 3, 2), dtype=np.uint8)
+        head, last = np.zeros(n_envs, dtype=np.int64), np.ones(n_envs, dtype=np.uint8)
+        words, flat_o, flat_x = [], [], []
+        for t0 in range(0, steps, per):
+            def flat(a):
+                a = a[t0:t0 + per]
+                if layout == 0:
+                    a = np.swapaxes(a, 0, 1)
+                return np.ascontiguousarray(a).reshape(-1, *a.shape[2:])
+            o, x, d, i = flat(obs), flat(nxt), flat(done), flat(init)
+            words.append(fo.push(pool, head, last, o, x, i if use_init else None, d, n_envs=n_envs, layout=layout, k=k, ring=ring))
+            flat_o.append(o)
+            flat_x.append(x)
+        w = np.concatenate(words)
+        ro, rx, evicted = fo.rebuild(pool, head, w, k=k, ring=ring)
+        assert not evicted.any()
+        np.testing.assert_array_equal(ro, np.concatenate(flat_o))
+        np.testing.assert_array_equal(rx, np.concatenate(flat_x))
+        assert (w >> fo.ENV_SHIFT).max() == n_envs - 1
+    # a lapped ring is reported
+    obs, nxt, done, init = fo.make_stream(1, 40, 4, (2, 2), seed=1, min_len=1, max_len=1)
+    pool = np.zeros((30, 2, 2), dtype=np.uint8)
+    head, last = np.zeros(1, dtype=np.int64), np.ones(1, dtype=np.uint8)
+    w = np.concatenate([fo.push(pool, head, last, obs[t:t + 5, 0], nxt[t:t + 5, 0], None, done[t:t + 5, 0], n_envs=1, layout=0,
+                                k=4, ring=30) for t in range(0, 40, 5)])
+    _, _, evicted = fo.rebuild(pool, head, w, k=4, ring=30)
+    assert evicted[:30].all() and not evicted[-5:].any()

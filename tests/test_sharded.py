@@ -98,6 +98,26 @@ def _worker(rank: int, world: int, port: int, q):
             for key in ("index", "obs", "frame", "flag", "priority_weight"):
                 assert torch.equal(x.get(key), y.get(key)), ("pipelined", it, key)
         assert bufs[0].flush() is None
+        # a FrameStackStorage shard next to a plain one: same global batches, k + 1 frames per exchanged row
+        from rl_b200.data import FrameStackStorage
+        from test_framestack import _batches
+
+        pair = []
+        for fs in (True, False):
+            gp = torch.Generator().manual_seed(300 + rank)
+            pair.append(ShardedPrioritizedReplayBuffer(
+                alpha=alpha, beta=beta, capacity=256, batch_size=16, device="cpu", generator=gp,
+                storage=FrameStackStorage(128, n_envs=2, device="cpu", min_episode_length=1) if fs else None))
+        for td in _batches(2, 48, 8, "env_major", seed=60 + rank, pad="constant"):
+            td.set("td_error", torch.rand(td.shape[0], generator=torch.Generator().manual_seed(4)))
+            for rbp in pair:
+                rbp.extend(td.clone())
+            x, y = (rbp.sample() for rbp in pair)
+            for key in ("index", "pixels", ("next", "pixels"), "action", ("next", "reward"), "priority_weight"):
+                assert torch.equal(x.get(key), y.get(key)), ("framestack shard", key)
+            for rbp, batch in zip(pair, (x, y)):
+                rbp.update_priority(batch.get("index"), torch.full((16,), 0.5 + rank))
+        assert pair[0]._layout.row < pair[1]._layout.row
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
