@@ -13,7 +13,7 @@ from rl_b200 import ops  # noqa: E402
 from rl_b200.graphs import CudaGraphStep  # noqa: E402
 
 dev = torch.device("cuda", 0)
-rb, g = bench.build_buffer(dev, 400_000, seed=0)
+rb, g = bench.build_buffer(dev, int(sys.argv[1]) if len(sys.argv) > 1 else 400_000, seed=0)
 ring = bench.gae_ring(dev, bench.GAE_ROWS, bench.GAE_T, g)
 td_err = torch.rand(bench.BATCH, device=dev, generator=g)
 smp, st = rb.sampler, rb.storage

@@ -544,7 +544,13 @@ __host__ __device__ inline int upd_bot_levels(int depth) { return depth > kDense
 
 constexpr int kUpdCluster = 8;  // CTAs per update launch: the leader + seven helpers (portable cluster size)
 #ifndef RLB_UPDATE_HOIST
-#define RLB_UPDATE_HOIST 16
+#define RLB_UPDATE_HOIST 2
+#endif
+#ifndef RLB_UPDATE_SPLIT_KEYS
+#define RLB_UPDATE_SPLIT_KEYS 0
+#endif
+#ifndef RLB_UPDATE_HELPER_LOADS
+#define RLB_UPDATE_HELPER_LOADS 4
 #endif
 constexpr int kUpdHoist = RLB_UPDATE_HOIST;   // sibling values of this many levels are held in registers during the climb
 constexpr int kUpdMaxItemsPerRound = 1024;  // one item per thread
@@ -684,7 +690,12 @@ __device__ __forceinline__ K bucket_rank_sort(K key, uint32_t bucket, K *buckete
   return sorted[tid];
 }
 
-template <typename T, bool FUSED>
+// This kernel runs once per launch on a cold instruction cache: its code size is part of its latency.  Register-hoisting
+// the sibling values of 16 levels (kUpdHoist = 16, two fully unrolled loops) made it 0.9 us SLOWER than re-reading
+// shared memory level by level (profiles/README.md: 9.1 us -> 8.2 us with kUpdHoist = 2).
+// KEYS: 0 -- the key width of the sort is decided at run time (default), 1 / 2 -- one instantiation per width
+// (RLB_UPDATE_SPLIT_KEYS=1: measured, no gain).
+template <typename T, bool FUSED, int KEYS>
 __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, int64_t capacity, int depth,
                                                                const int64_t *__restrict__ index_all,
                                                                const T *__restrict__ value_all, int n_all, int scalar,
@@ -783,7 +794,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
       const int n = min(NP, n_all - rnd * NP);
       // ---- helpers, part 1: sib[t][l][i] (in the LEADER's shared memory) = tree_t[((capacity + index[i]) >> l) ^ 1]
       // for the levels below the cut.  The loads are issued before the cluster is known to be up, the stores after.
-      constexpr int kMaxPer = 4;
+      constexpr int kMaxPer = RLB_UPDATE_HELPER_LOADS;
       const uint32_t per_tree = (uint32_t)bot * (uint32_t)NP, total = 2u * per_tree;
       const uint32_t nthreads = (csize - 1u) * (uint32_t)NP, g = (crank - 1u) * (uint32_t)NP + tid;
       const int64_t ix_self = (tid < n) ? item_ix(rnd, tid) : -1;  // (part 2: the item at position tid)
@@ -883,7 +894,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     }
   }
   const int pos_bits = 31 - __clz(NP);  // log2(NP)
-  const bool key32 = (depth + 1 + pos_bits) <= 32;
+  const bool key32 = KEYS == 1 ? true : (KEYS == 2 ? false : (depth + 1 + pos_bits) <= 32);
   const uint32_t none32 = 0xffffffffu >> pos_bits;  // all-ones leaf field of a 32-bit key
   const int bshift = depth > pos_bits ? depth - pos_bits : 0;   // leaf index -> one of NP buckets
 
@@ -1012,7 +1023,7 @@ __global__ void __launch_bounds__(1024) tree_update_cta_kernel(T *sum, T *mn, in
     // tile doubles as the staging area the helpers scatter from.
     T *io_s = sib + pos;
     T *io_m = sib + (size_t)bot * NP + pos;
-    T hs[kUpdHoist], hm[kUpdHoist];
+    T hs[kUpdHoist > 0 ? kUpdHoist : 1], hm[kUpdHoist > 0 ? kUpdHoist : 1];
 #pragma unroll
     for (int l = 0; l < kUpdHoist; ++l) {
       hs[l] = (T)0;
@@ -1381,9 +1392,28 @@ struct FusedPow {
   int64_t index_limit = -1;  // valid local indices are [0, index_limit); -1 = capacity
 };
 
+template <typename T, bool FUSED, int KEYS>
+static int launch_update_cta_k(T *sum, T *mn, int64_t capacity, int depth, const int64_t *index, const T *value,
+                               int64_t n, int scalar, const FusedPow &fp, void *workspace, cudaStream_t st);
+
 template <typename T, bool FUSED>
 static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const int64_t *index, const T *value,
                              int64_t n, int scalar, const FusedPow &fp, void *workspace, cudaStream_t st) {
+#if RLB_UPDATE_SPLIT_KEYS
+  int np = 32, groups = 1, pos_bits = 0;
+  upd_shape(n, depth, &np, &groups);
+  while ((1 << pos_bits) < np) ++pos_bits;
+  if (depth + 1 + pos_bits <= 32)
+    return launch_update_cta_k<T, FUSED, 1>(sum, mn, capacity, depth, index, value, n, scalar, fp, workspace, st);
+  return launch_update_cta_k<T, FUSED, 2>(sum, mn, capacity, depth, index, value, n, scalar, fp, workspace, st);
+#else
+  return launch_update_cta_k<T, FUSED, 0>(sum, mn, capacity, depth, index, value, n, scalar, fp, workspace, st);
+#endif
+}
+
+template <typename T, bool FUSED, int KEYS>
+static int launch_update_cta_k(T *sum, T *mn, int64_t capacity, int depth, const int64_t *index, const T *value,
+                               int64_t n, int scalar, const FusedPow &fp, void *workspace, cudaStream_t st) {
   int np = 32, groups = 1;
   upd_shape(n, depth, &np, &groups);
   const size_t smem = upd_smem_bytes<T>(np, depth);
@@ -1392,11 +1422,11 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   cudaGetDevice(&cur_dev);
   bool &attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T, FUSED>,
+    int rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T, FUSED, KEYS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmemLimit),
                         "cudaFuncSetAttribute(tree_update_cta_kernel)");
     if (rc) return rc;
-    rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T, FUSED>,
+    rc = check_cuda(cudaFuncSetAttribute(tree_update_cta_kernel<T, FUSED, KEYS>,
                                          cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared),
                     "cudaFuncSetAttribute(tree_update_cta_kernel, carveout)");
@@ -1419,7 +1449,7 @@ static int launch_update_cta(T *sum, T *mn, int64_t capacity, int depth, const i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int rc = check_cuda(cudaLaunchKernelEx(&cfg, tree_update_cta_kernel<T, FUSED>, sum, mn, capacity, depth, index, value,
+  int rc = check_cuda(cudaLaunchKernelEx(&cfg, tree_update_cta_kernel<T, FUSED, KEYS>, sum, mn, capacity, depth, index, value,
                                          (int)n, scalar, fp.alpha, fp.eps, fp.max_out, g_debug_ticks, fp.index_base,
                                          fp.index_limit < 0 ? capacity : fp.index_limit, groups,
                                          static_cast<unsigned char *>(workspace)),
