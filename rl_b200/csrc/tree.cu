@@ -362,7 +362,10 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
                                                          int64_t *__restrict__ index_out,
                                                          float *__restrict__ weight_out, T *leaf_out,
                                                          T *psum_pmin_out, int32_t *status, long long *dbg) {
-  constexpr int kTopLevels = 9;  // nodes 1..511 of the sum tree are staged in shared memory: 8 descent steps
+#ifndef RLB_SAMPLE_TOP_LEVELS
+#define RLB_SAMPLE_TOP_LEVELS 9
+#endif
+  constexpr int kTopLevels = RLB_SAMPLE_TOP_LEVELS;  // nodes 1..2^k-1 of the sum tree are staged in shared memory: k - 1 descent steps
   __shared__ T s_p[2];
   __shared__ T s_top[1 << kTopLevels];
   pdl_trigger();  // a dependent launch (the gather) may become resident now; it waits for this grid before the index
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const T *__restrict__ s
   const int nwarps = blockDim.x >> 5;
   // Single-warp CTAs with at most 4 samples: the warp splits into groups of G = 32 / 16 / 8 lanes, one per sample, that
   // descend cooperatively (descend_group_f32); only the first lane of a group writes results.
-  const bool coop = speculative && sizeof(T) == 4 && blockDim.x == 32 && spc <= 4 && depth >= 9;
+  const bool coop = speculative && sizeof(T) == 4 && blockDim.x == 32 && spc <= 4 && depth >= kTopLevels;
   const int G = !coop ? 1 : (spc == 1 ? 32 : (spc == 2 ? 16 : 8));
   const int grp = coop ? (int)threadIdx.x / G : (int)threadIdx.x;
   const bool lane_on = grp < spc;  // spc == blockDim.x for full CTAs
